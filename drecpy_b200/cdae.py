@@ -1,0 +1,333 @@
+"""CDAE (Collaborative Denoising Auto-Encoder) on the native B200 step -- drop-in for DRecPy's CDAE.
+
+Mirrors DRecPy/Recommender/cdae.py: constructor :25-32, _pre_fit :34-45 (Glorot-uniform W[I,K], W_[K,I], V[U,K]
+and -- as in the reference -- Glorot-initialised biases b[K], b_[I]; variable order [W, W_, V, b, b_]),
+_sample_batch :47-48, the per-user reconstruct / loss / reg math :50-82 (now drb_cdae_step), _predict :84-88 and
+_rank :90-103 (now drb_cdae_rank_candidates / drb_cdae_topk).
+
+New keywords, all with reference-faithful defaults:
+  label_mode='batch_mean'   the Keras-2 (B,B,I) loss broadcast of the reference; 'per_user' = the
+                            per-user targets of the CDAE paper
+  rng_mode='mt19937'        bit-exact replay of the reference's corruption stream (n_items draws per sampled user,
+                            cdae.py:63-64); 'philox' = counter-based mask generated on the GPU (documented
+                            deviation for throughput configurations)
+  adam_t='per_variable'     Adam step counter advances once per variable (Q2); 'per_step' = textbook Adam
+  init_weights=None         dict with any of W, W_, V, b, b_ (reference shapes) to inject initial weights
+"""
+import ctypes as C
+import random
+
+import numpy as np
+
+from . import _lib
+from .recommender import DeepRecommenderABC
+from .sampler import PointSampler
+
+_RING = 4
+
+
+class CDAE(DeepRecommenderABC):
+    def __init__(self, hidden_factors=50, corruption_level=0.2, loss='bce', **kwds):
+        super(CDAE, self).__init__(**kwds)
+        self.hidden_factors = hidden_factors
+        self.corruption_level = corruption_level
+        if loss not in ('mse', 'bce'):
+            raise Exception(f'Loss function "{loss}" is not supported. Supported losses: "mse", "bce".')
+        self.loss = loss
+        self.label_mode = kwds.get('label_mode', 'batch_mean')
+        self.rng_mode = kwds.get('rng_mode', 'mt19937')
+        self.adam_t = kwds.get('adam_t', 'per_variable')
+        assert self.label_mode in _lib.DRB_LABEL and self.rng_mode in ('mt19937', 'philox')
+        assert self.adam_t in ('per_variable', 'per_step')
+        self._native = None
+        self._ctx = None
+
+    # ------------------------------------------------------------------ setup
+    def _pre_fit(self, learning_rate, neg_ratio, reg_rate, batch_size=32, **kwds):
+        import torch
+        self._torch = torch
+        if not torch.cuda.is_available():
+            raise RuntimeError('drecpy_b200 needs a CUDA device (sm_100a); there is no CPU fallback')
+        self._dev = torch.device(self.device or f'cuda:{torch.cuda.current_device()}')
+        self._max_batch = int(max(batch_size, min(1024, self.n_users), kwds.get('score_batch', 0)))
+        self._alloc_and_init(kwds.get('init_weights', None))
+        self._build_native()
+        self._sampler = kwds.get('sampler') or PointSampler(self._data, neg_ratio, self.interaction_threshold, self.seed)
+        mask_seed = self.seed if self.seed is not None else random.SystemRandom().getrandbits(63)
+        self._mask_seed = abs(int(mask_seed))
+        self._mask_rng = _lib.HostRng(self._mask_seed)      # replays self._rng of recommender_abc.py:74
+        self._setup_staging(batch_size)
+
+    def _alloc_and_init(self, init_weights):
+        torch = self._torch
+        lib = _lib.load()
+        L = _lib.CdaeLayout()
+        _lib.check(lib.drb_cdae_layout(self.n_users, self.n_items, self.hidden_factors, C.byref(L)))
+        self._L = L
+        dev = self._dev
+        self._params = torch.zeros(L.total, dtype=torch.float32, device=dev)
+        self._adam_m = torch.zeros_like(self._params)
+        self._adam_v = torch.zeros_like(self._params)
+        self._grads = torch.zeros_like(self._params)
+        K, I, U = self.hidden_factors, self.n_items, self.n_users
+        gen = torch.Generator().manual_seed(abs(int(self.seed)) if self.seed is not None else random.getrandbits(62))
+
+        def glorot(shape, fan_in, fan_out):       # tf.initializers.GlorotUniform (cdae.py:35-41)
+            lim = float(np.sqrt(6.0 / (fan_in + fan_out)))
+            return (torch.rand(shape, generator=gen, dtype=torch.float32) * 2 - 1) * lim
+        init = {'W': glorot((I, K), I, K), 'W_': glorot((K, I), K, I), 'V': glorot((U, K), U, K),
+                'b': glorot((K,), K, K), 'b_': glorot((I,), I, I)}
+        for k, v in (init_weights or {}).items():
+            assert k in init, f'unknown weight {k}'
+            v = torch.as_tensor(np.asarray(v), dtype=torch.float32)
+            assert tuple(v.shape) == tuple(init[k].shape), f'{k}: expected shape {tuple(init[k].shape)}'
+            init[k] = v
+        self.W.copy_(init['W'])
+        self.W_.copy_(init['W_'])
+        self.V.copy_(init['V'])
+        self.b.copy_(init['b'])
+        self.b_.copy_(init['b_'])
+
+    def _build_native(self):
+        torch = self._torch
+        lib = _lib.load()
+        dev, L = self._dev, self._L
+        self._ctx = _lib.vp()
+        _lib.check(lib.drb_ctx_create(dev.index or 0, C.byref(self._ctx)))
+        self._stream = torch.cuda.current_stream(dev)
+        _lib.check(lib.drb_ctx_set_stream(self._ctx, _lib.vp(self._stream.cuda_stream)))
+        pos = self._data.csr(self.interaction_threshold)     # positives: cdae.py:61
+        seen = self._data.csr()                              # every stored row: cdae.py:93-98
+        self._h_indptr = np.ascontiguousarray(pos[0])
+        self._h_indices = np.ascontiguousarray(pos[1])
+        self._d_indptr = torch.from_numpy(self._h_indptr).to(dev)
+        self._d_indices = torch.from_numpy(self._h_indices).to(dev)
+        self._d_seen_indptr = torch.from_numpy(np.ascontiguousarray(seen[0])).to(dev)
+        self._d_seen_indices = torch.from_numpy(np.ascontiguousarray(seen[1])).to(dev)
+        ws_bytes = lib.drb_cdae_workspace_bytes(self.n_users, self.n_items, self.hidden_factors, self._max_batch)
+        assert ws_bytes > 0
+        self._workspace = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        d = _lib.CdaeDesc()
+        d.n_users, d.n_items, d.hidden = self.n_users, self.n_items, self.hidden_factors
+        d.params, d.adam_m, d.adam_v, d.grads = (self._params.data_ptr(), self._adam_m.data_ptr(),
+                                                 self._adam_v.data_ptr(), self._grads.data_ptr())
+        d.csr_indptr, d.csr_indices = self._d_indptr.data_ptr(), self._d_indices.data_ptr()
+        d.seen_indptr, d.seen_indices = self._d_seen_indptr.data_ptr(), self._d_seen_indices.data_ptr()
+        d.corruption_level = float(self.corruption_level)
+        d.loss_kind = _lib.DRB_LOSS[self.loss]
+        d.label_mode = _lib.DRB_LABEL[self.label_mode]
+        d.workspace, d.workspace_bytes, d.max_batch = self._workspace.data_ptr(), ws_bytes, self._max_batch
+        self._native = _lib.vp()
+        _lib.check(lib.drb_cdae_create(self._ctx, C.byref(d), C.byref(self._native)))
+
+    def _setup_staging(self, batch_size):
+        torch = self._torch
+        deg = np.diff(self._h_indptr)
+        cap = int(np.sort(deg)[::-1][:batch_size].sum()) if len(deg) else 0   # exact bound on a batch's nnz
+        self._slots = []
+        for _ in range(_RING):
+            s = {'uid': torch.empty(batch_size, dtype=torch.int32).pin_memory(),
+                 'iid': np.empty(batch_size, np.int32), 'val': np.empty(batch_size, np.float64),
+                 'off': torch.empty(batch_size + 1, dtype=torch.int32).pin_memory(),
+                 'keep': torch.empty(max(cap, 16), dtype=torch.uint8).pin_memory(),
+                 'event': None}
+            s['uid_np'], s['off_np'], s['keep_np'] = s['uid'].numpy(), s['off'].numpy(), s['keep'].numpy()
+            self._slots.append(s)
+        self._slot_idx = 0
+        self._loss_host = torch.zeros(1, dtype=torch.float32).pin_memory()
+
+    # ------------------------------------------------------------------ weights as reference-shaped views
+    def _seg(self, off, rows, ld):
+        return self._params[off:off + rows * ld].view(rows, ld)
+
+    @property
+    def W(self):
+        return self._seg(self._L.off_w, self.n_items, self._L.ld)[:, :self.hidden_factors]
+
+    @property
+    def W_(self):     # reference layout [K, I]; stored item-major
+        return self._seg(self._L.off_w2t, self.n_items, self._L.ld)[:, :self.hidden_factors].t()
+
+    @property
+    def V(self):
+        return self._seg(self._L.off_v, self.n_users, self._L.ld)[:, :self.hidden_factors]
+
+    @property
+    def b(self):
+        return self._params[self._L.off_b:self._L.off_b + self.hidden_factors]
+
+    @property
+    def b_(self):
+        return self._params[self._L.off_b2:self._L.off_b2 + self.n_items]
+
+    def _params_tensor(self):
+        return self._params
+
+    # ------------------------------------------------------------------ training step
+    def step_args(self, reg_rate):
+        o = self.optimizer
+        a = _lib.CdaeStepArgs()
+        a.learning_rate, a.beta1, a.beta2, a.epsilon = o['learning_rate'], o['beta_1'], o['beta_2'], o['epsilon']
+        a.reg_rate = reg_rate
+        s = self._step
+        for j in range(5):
+            a.t[j] = 5 * (s - 1) + j + 1 if self.adam_t == 'per_variable' else s     # Q2
+        a.philox_seed = self._mask_seed
+        a.philox_step = s
+        return a
+
+    def prepare_batch(self, slot, batch_size):
+        """Host side of one step: sample B triples (only uid is used, cdae.py:52) and build the mask inputs."""
+        lib = _lib.load()
+        self._sampler.sample_arrays(batch_size, out=(slot['uid_np'], slot['iid'], slot['val']))
+        if self.rng_mode == 'mt19937':
+            _lib.check(lib.drb_cdae_corruption_keep_mt(
+                self._mask_rng.handle, _lib.np_ptr(slot['uid_np']), batch_size, self.n_items,
+                float(self.corruption_level), _lib.np_ptr(self._h_indptr), _lib.np_ptr(self._h_indices),
+                _lib.np_ptr(slot['off_np']), _lib.np_ptr(slot['keep_np'])))
+            return _lib.np_ptr(slot['keep_np'])
+        _lib.check(lib.drb_batch_offsets(_lib.np_ptr(slot['uid_np']), batch_size, _lib.np_ptr(self._h_indptr),
+                                         _lib.np_ptr(slot['off_np'])))
+        return None
+
+    def _train_step(self, batch_size, reg_rate, want_loss=False, **kwds):
+        lib = _lib.load()
+        with self._lock:
+            slot = self._slots[self._slot_idx]
+            self._slot_idx = (self._slot_idx + 1) % _RING
+            if slot['event'] is not None:
+                slot['event'].synchronize()          # the async H2D of the step that last used this slot is done
+            keep_ptr = self.prepare_batch(slot, batch_size)
+            args = self.step_args(reg_rate)
+            loss_ptr = _lib.vp(self._loss_host.data_ptr()) if want_loss else None
+            _lib.check(lib.drb_cdae_step_host(self._native, _lib.np_ptr(slot['uid_np']), _lib.np_ptr(slot['off_np']),
+                                              keep_ptr, batch_size, C.byref(args), loss_ptr))
+            if not want_loss:
+                ev = self._torch.cuda.Event()
+                ev.record(self._stream)
+                slot['event'] = ev
+                return None
+            return float(self._loss_host[0])
+
+    def step_device(self, uids_dev, keep_off_dev, keep_dev, reg_rate, loss_dev):
+        """One step on device-resident inputs (torch tensors); keep_dev=None selects the philox mask."""
+        self._step += 1
+        args = self.step_args(reg_rate)
+        _lib.check(_lib.load().drb_cdae_step(self._native, _lib.t_ptr(uids_dev), _lib.t_ptr(keep_off_dev),
+                                             _lib.t_ptr(keep_dev), uids_dev.numel(), C.byref(args),
+                                             _lib.t_ptr(loss_dev)))
+
+    def launch_count(self):
+        return _lib.load().drb_ctx_launch_count(self._ctx)
+
+    def synchronize(self):
+        _lib.check(_lib.load().drb_ctx_synchronize(self._ctx))
+
+    # ------------------------------------------------------------------ scoring
+    def _predict(self, uid, iid=None, **kwds):
+        if uid is None: return None
+        torch = self._torch
+        with self._lock:
+            u = torch.tensor([uid], dtype=torch.int32, device=self._dev)
+            out = torch.empty(self._L.items_pad, dtype=torch.float32, device=self._dev)
+            _lib.check(_lib.load().drb_cdae_predict_all(self._native, _lib.t_ptr(u), 1, _lib.t_ptr(out)))
+            predictions = out[:self.n_items].cpu().numpy()
+        return predictions if iid is None else predictions[iid]
+
+    def hidden(self, uids):
+        torch = self._torch
+        with self._lock:
+            u = torch.as_tensor(np.asarray(uids, np.int32), device=self._dev)
+            out = torch.empty((len(u), self._L.ld), dtype=torch.float32, device=self._dev)
+            for o in range(0, len(u), self._max_batch):
+                n = min(self._max_batch, len(u) - o)
+                _lib.check(_lib.load().drb_cdae_hidden(self._native, _lib.t_ptr(u[o:]), n, _lib.t_ptr(out[o:])))
+            return out[:, :self.hidden_factors].cpu().numpy()
+
+    def _rank_batch(self, uids, cand, cand_count, novelty):
+        torch = self._torch
+        with self._lock:
+            n, max_c = cand.shape
+            if max_c > 4096:
+                return self._rank_batch_dense(uids, cand, cand_count, novelty)
+            d_u = torch.as_tensor(np.ascontiguousarray(uids, np.int32), device=self._dev)
+            d_c = torch.as_tensor(np.ascontiguousarray(cand, np.int32), device=self._dev)
+            d_n = torch.as_tensor(np.ascontiguousarray(cand_count, np.int32), device=self._dev)
+            o_i = torch.empty((n, max_c), dtype=torch.int32, device=self._dev)
+            o_s = torch.empty((n, max_c), dtype=torch.float32, device=self._dev)
+            o_n = torch.empty(n, dtype=torch.int32, device=self._dev)
+            _lib.check(_lib.load().drb_cdae_rank_candidates(self._native, _lib.t_ptr(d_u), n, _lib.t_ptr(d_c),
+                                                            _lib.t_ptr(d_n), max_c, int(bool(novelty)),
+                                                            _lib.t_ptr(o_i), _lib.t_ptr(o_s), _lib.t_ptr(o_n)))
+            return o_i.cpu().numpy(), o_s.cpu().numpy(), o_n.cpu().numpy()
+
+    def _rank_batch_dense(self, uids, cand, cand_count, novelty):
+        """Candidate lists longer than the in-CTA sorter handles: dense scores from the GPU, ordering on the host
+        with the same (score desc, iid desc) rule."""
+        n, max_c = cand.shape
+        o_i = np.zeros((n, max_c), np.int32)
+        o_s = np.zeros((n, max_c), np.float32)
+        o_n = np.zeros(n, np.int32)
+        for r in range(n):
+            p = self._predict(int(uids[r]))
+            c = np.unique(cand[r, :cand_count[r]])
+            if novelty:
+                c = np.setdiff1d(c, self._data.user_items(int(uids[r])))
+            order = np.lexsort((c, p[c]))[::-1]
+            c = c[order]
+            o_i[r, :len(c)], o_s[r, :len(c)], o_n[r] = c, p[c], len(c)
+        return o_i, o_s, o_n
+
+    def topk_batch(self, uids, k, novelty=True, return_device=False):
+        """Full-catalog top-k for many users: (iids [n,k], scores [n,k], n_out [n])."""
+        torch = self._torch
+        with self._lock:
+            d_u = uids if torch.is_tensor(uids) else torch.as_tensor(np.ascontiguousarray(uids, np.int32), device=self._dev)
+            n = d_u.numel()
+            o_i = torch.empty((n, k), dtype=torch.int32, device=self._dev)
+            o_s = torch.empty((n, k), dtype=torch.float32, device=self._dev)
+            o_n = torch.empty(n, dtype=torch.int32, device=self._dev)
+            _lib.check(_lib.load().drb_cdae_topk(self._native, _lib.t_ptr(d_u), n, k, int(bool(novelty)),
+                                                 _lib.t_ptr(o_i), _lib.t_ptr(o_s), _lib.t_ptr(o_n)))
+            if return_device:
+                return o_i, o_s, o_n
+            return o_i.cpu().numpy(), o_s.cpu().numpy(), o_n.cpu().numpy()
+
+    def _recommend(self, uid, n, novelty, threshold):
+        if n <= 2048:
+            o_i, o_s, o_n = self.topk_batch(np.array([uid], np.int32), int(n), novelty)
+            ranked = [(o_s[0, j], int(o_i[0, j])) for j in range(int(o_n[0]))]
+        else:
+            ranked = self._rank(uid, range(self.n_items), n, novelty)
+        if threshold is None:
+            return ranked
+        return [x for x in ranked if x[0] >= threshold]
+
+    # ------------------------------------------------------------------ persistence
+    def __getstate__(self):
+        st = {k: v for k, v in self.__dict__.items()
+              if k not in ('_native', '_ctx', '_torch', '_workspace', '_slots', '_loss_host', '_stream', '_lock',
+                           '_mask_rng', '_sampler', '_d_indptr', '_d_indices', '_d_seen_indptr', '_d_seen_indices',
+                           '_logger', '_dev')}
+        for k in ('_params', '_adam_m', '_adam_v', '_grads'):
+            if k in st: st[k] = st[k].cpu()
+        st['_L'] = {f: getattr(self._L, f) for f, _ in _lib.CdaeLayout._fields_} if getattr(self, '_L', None) is not None else None
+        st['epoch_weights'] = {}
+        return st
+
+    def __setstate__(self, st):
+        import logging
+        import threading
+        L = st.pop('_L', None)
+        self.__dict__.update(st)
+        self._lock = threading.RLock()
+        self._logger = logging.getLogger(f'{self.__class__.__name__}_CLOGGER')
+        self._native = self._ctx = None
+        if L is not None and self.fitted:
+            import torch
+            self._torch = torch
+            self._L = _lib.CdaeLayout(**L)
+            self._dev = torch.device(self.device or f'cuda:{torch.cuda.current_device()}')
+            for k in ('_params', '_adam_m', '_adam_v', '_grads'):
+                setattr(self, k, getattr(self, k).to(self._dev))
+            self._build_native()

@@ -1,0 +1,696 @@
+// C-ABI entry points of libdrb.so: context, CDAE and DMF step / scoring orchestration (see include/drb.h).
+// The step functions only enqueue kernels on the context's stream; nothing here allocates device memory.
+#include <algorithm>
+#include <cstring>
+#include <vector>
+
+#include "kernels.h"
+
+// ------------------------------------------------------------------------------------------ errors
+static thread_local char g_err[512] = "";
+
+int drb_fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+namespace {
+
+struct Carver {  // bump allocator over the caller-provided workspace (256-byte aligned pieces)
+  char* base; int64_t off = 0;
+  explicit Carver(void* p) : base(static_cast<char*>(p)) {}
+  template <typename T>
+  T* take(int64_t count) {
+    T* r = base ? reinterpret_cast<T*>(base + off) : nullptr;
+    off += drb_round_up(count * (int64_t)sizeof(T), 256);
+    return r;
+  }
+};
+
+int gemm_splits(const drb_ctx* ctx, int M, int N, int Kred) {
+  const int tiles = ((M + 127) / 128) * ((N + 127) / 128);
+  int s = (2 * ctx->sm_count + tiles - 1) / tiles;
+  s = std::min(s, std::max(1, Kred / 512));
+  return std::max(1, std::min(s, 32));
+}
+
+}  // namespace
+
+extern "C" {
+
+int drb_version(void) { return DRB_VERSION; }
+const char* drb_last_error(void) { return g_err; }
+
+int drb_ctx_create(int device, drb_ctx** out) {
+  if (!out) return drb_fail(DRB_E_INVALID, "drb_ctx_create: out is NULL");
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) {
+    cudaGetLastError();
+    return drb_fail(DRB_E_NODEVICE, "no CUDA device available (libdrb has no CPU fallback)");
+  }
+  if (device < 0 || device >= count) return drb_fail(DRB_E_INVALID, "device ordinal %d out of range", device);
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess)
+    return drb_fail(DRB_E_CUDA, "cudaGetDeviceProperties failed");
+  if (prop.major != 10)
+    return drb_fail(DRB_E_NODEVICE, "device %d is sm_%d%d; libdrb is built for sm_100a only", device, prop.major,
+                    prop.minor);
+  drb_ctx* c = new (std::nothrow) drb_ctx;
+  if (!c) return drb_fail(DRB_E_NOMEM, "out of memory");
+  c->device = device;
+  c->sm_count = prop.multiProcessorCount;
+  c->stream = nullptr;
+  c->launches = 0;
+  c->sticky = 0;
+  if (cudaSetDevice(device) != cudaSuccess) {
+    delete c;
+    return drb_fail(DRB_E_CUDA, "cudaSetDevice(%d) failed", device);
+  }
+  *out = c;
+  return DRB_OK;
+}
+int drb_ctx_destroy(drb_ctx* ctx) { delete ctx; return DRB_OK; }
+int drb_ctx_set_stream(drb_ctx* ctx, void* stream) {
+  if (!ctx) return drb_fail(DRB_E_INVALID, "ctx is NULL");
+  ctx->stream = static_cast<cudaStream_t>(stream);
+  return DRB_OK;
+}
+int drb_ctx_synchronize(drb_ctx* ctx) {
+  if (!ctx) return drb_fail(DRB_E_INVALID, "ctx is NULL");
+  DRB_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  return DRB_OK;
+}
+int64_t drb_ctx_launch_count(const drb_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+}  // extern "C"
+
+// ========================================================================================== CDAE
+struct CdaeWs {
+  float *h, *dz, *dh_part, *dz1, *col_b2, *col_b, *loss_part, *reg_part, *label_count, *loss_scalar;
+  uint32_t* label_bits;
+  int32_t *uids, *keep_off, *aux_i32;
+  uint8_t* keep;
+  int64_t bytes;
+};
+
+struct drb_cdae {
+  drb_ctx* ctx;
+  drb_cdae_desc d;
+  drb_cdae_layout_t L;
+  CdaeWs ws;
+  int splits, words_per_row;
+  int64_t keep_cap;
+};
+
+static int64_t cdae_keep_cap(int32_t n_items, int32_t max_batch) {
+  // every sampled user can hold at most n_items positives; cap the staging buffer at 1 GiB
+  return std::min<int64_t>((int64_t)max_batch * n_items, (int64_t)1 << 30);
+}
+
+static CdaeWs cdae_carve(void* base, const drb_cdae_layout_t& L, int n_items, int max_batch, int label_mode,
+                         int splits, int sm_count) {
+  Carver c(base);
+  CdaeWs w;
+  const int64_t B = max_batch;
+  const int mt = (max_batch + 127) / 128;
+  w.h = c.take<float>(B * L.ld);
+  w.dz = c.take<float>(B * L.items_pad);
+  w.dh_part = c.take<float>((int64_t)splits * B * L.ld);
+  w.dz1 = c.take<float>(B * L.ld);
+  w.col_b2 = c.take<float>((int64_t)mt * L.items_pad);
+  w.col_b = c.take<float>((int64_t)((max_batch + 31) / 32) * L.ld);
+  w.loss_part = c.take<float>((int64_t)mt * ((L.items_pad + 63) / 64));
+  w.reg_part = c.take<float>((int64_t)sm_count * 16);
+  w.label_count = c.take<float>(L.items_pad);
+  w.loss_scalar = c.take<float>(64);
+  const int64_t words = (L.items_pad + 31) / 32;
+  w.label_bits = c.take<uint32_t>(label_mode == DRB_LABEL_PER_USER ? B * words : 1);
+  w.uids = c.take<int32_t>(B);
+  w.keep_off = c.take<int32_t>(B + 1);
+  w.aux_i32 = c.take<int32_t>(3 * B + 64);
+  w.keep = c.take<uint8_t>(cdae_keep_cap(n_items, max_batch));
+  w.bytes = c.off;
+  return w;
+}
+
+extern "C" {
+
+int drb_cdae_layout(int32_t n_users, int32_t n_items, int32_t hidden, drb_cdae_layout_t* out) {
+  if (!out || n_users <= 0 || n_items <= 0 || hidden <= 0 || hidden > 512)
+    return drb_fail(DRB_E_INVALID, "drb_cdae_layout: need n_users, n_items > 0 and 0 < hidden <= 512");
+  const int64_t ld = drb_round_up(hidden, 4), ip = drb_round_up(n_items, 4);
+  out->ld = (int32_t)ld;
+  out->items_pad = (int32_t)ip;
+  out->off_w2t = 0;
+  out->off_w = out->off_w2t + (int64_t)n_items * ld;
+  out->off_v = out->off_w + (int64_t)n_items * ld;
+  out->off_b = out->off_v + (int64_t)n_users * ld;
+  out->off_b2 = out->off_b + ld;
+  out->total = out->off_b2 + ip;
+  return DRB_OK;
+}
+
+int64_t drb_cdae_workspace_bytes(int32_t n_users, int32_t n_items, int32_t hidden, int32_t max_batch) {
+  drb_cdae_layout_t L;
+  if (drb_cdae_layout(n_users, n_items, hidden, &L) || max_batch <= 0) return -1;
+  // worst case over label modes and split counts (splits <= 32, 148+ SMs -> use 256 as an upper bound)
+  return cdae_carve(nullptr, L, n_items, max_batch, DRB_LABEL_PER_USER, 32, 256).bytes;
+}
+
+int drb_cdae_create(drb_ctx* ctx, const drb_cdae_desc* desc, drb_cdae** out) {
+  if (!ctx || !desc || !out) return drb_fail(DRB_E_INVALID, "drb_cdae_create: NULL argument");
+  drb_cdae_layout_t L;
+  int r = drb_cdae_layout(desc->n_users, desc->n_items, desc->hidden, &L);
+  if (r) return r;
+  if (!desc->params || !desc->csr_indptr || !desc->csr_indices || !desc->workspace || desc->max_batch <= 0)
+    return drb_fail(DRB_E_INVALID, "drb_cdae_create: params, csr and workspace are required");
+  if (((uintptr_t)desc->params | (uintptr_t)desc->adam_m | (uintptr_t)desc->adam_v | (uintptr_t)desc->grads |
+       (uintptr_t)desc->workspace) & 15)
+    return drb_fail(DRB_E_INVALID, "drb_cdae_create: arenas and workspace must be 16-byte aligned");
+  if (!(desc->corruption_level >= 0.f && desc->corruption_level < 1.f))
+    return drb_fail(DRB_E_INVALID, "drb_cdae_create: corruption_level must be in [0, 1)");
+  if (desc->loss_kind != DRB_LOSS_BCE && desc->loss_kind != DRB_LOSS_MSE)
+    return drb_fail(DRB_E_INVALID, "Loss function is not supported. Supported losses: \"mse\", \"bce\".");
+  drb_cdae* m = new (std::nothrow) drb_cdae;
+  if (!m) return drb_fail(DRB_E_NOMEM, "out of memory");
+  m->ctx = ctx;
+  m->d = *desc;
+  if (!m->d.seen_indptr) { m->d.seen_indptr = m->d.csr_indptr; m->d.seen_indices = m->d.csr_indices; }
+  m->L = L;
+  m->splits = gemm_splits(ctx, desc->max_batch, L.ld, desc->n_items);
+  m->words_per_row = (L.items_pad + 31) / 32;
+  m->ws = cdae_carve(desc->workspace, L, desc->n_items, desc->max_batch, desc->label_mode, m->splits,
+                     ctx->sm_count);
+  m->keep_cap = cdae_keep_cap(desc->n_items, desc->max_batch);
+  if (m->ws.bytes > desc->workspace_bytes) {
+    int64_t need = m->ws.bytes;
+    delete m;
+    return drb_fail(DRB_E_INVALID, "drb_cdae_create: workspace too small (%lld < %lld bytes)",
+                    (long long)desc->workspace_bytes, (long long)need);
+  }
+  *out = m;
+  return DRB_OK;
+}
+int drb_cdae_destroy(drb_cdae* m) { delete m; return DRB_OK; }
+
+static int cdae_hidden_into(drb_cdae* m, const int32_t* uids, int n, const int32_t* keep_off, const uint8_t* keep,
+                            float scale, float* h) {
+  GatherArgs g{};
+  g.indptr = m->d.csr_indptr; g.indices = m->d.csr_indices; g.values = nullptr;
+  g.rows = uids; g.keep_off = keep_off; g.keep = keep;
+  g.table = m->d.params + m->L.off_w; g.ld = m->L.ld;
+  g.rowbias = m->d.params + m->L.off_v; g.bias = m->d.params + m->L.off_b;
+  g.row_scale = nullptr; g.scale = scale; g.act = DRB_ACT_SIGMOID; g.width = m->d.hidden;
+  g.out = h;
+  return launch_gather(m->ctx, g, n);
+}
+
+int drb_cdae_step(drb_cdae* m, const int32_t* uids, const int32_t* keep_off, const uint8_t* keep, int32_t batch,
+                  const drb_cdae_step_args* a, float* loss_out) {
+  if (!m || !uids || !keep_off || !a || !loss_out) return drb_fail(DRB_E_INVALID, "drb_cdae_step: NULL argument");
+  if (batch <= 0 || batch > m->d.max_batch)
+    return drb_fail(DRB_E_INVALID, "drb_cdae_step: batch %d outside (0, max_batch=%d]", batch, m->d.max_batch);
+  if (!m->d.adam_m || !m->d.adam_v || !m->d.grads)
+    return drb_fail(DRB_E_STATE, "drb_cdae_step: model was created without optimizer arenas");
+  drb_ctx* ctx = m->ctx;
+  if (ctx->sticky) return drb_fail(DRB_E_CUDA, "context has a sticky CUDA error (%d)", ctx->sticky);
+  const drb_cdae_layout_t& L = m->L;
+  CdaeWs& w = m->ws;
+  const int I = m->d.n_items, U = m->d.n_users, ld = L.ld;
+  float* P = m->d.params;
+  float* G = m->d.grads;
+  const bool per_user = (m->d.label_mode == DRB_LABEL_PER_USER);
+  int r;
+
+  // 0. clear sparse-gradient regions [W | V | b | b2] (W2T's gradient is fully overwritten by the GEMM)
+  DRB_CUDA_TRY(ctx, cudaMemsetAsync(G + L.off_w, 0, (size_t)(L.total - L.off_w) * sizeof(float), ctx->stream));
+  if (per_user)
+    DRB_CUDA_TRY(ctx, cudaMemsetAsync(w.label_bits, 0, (size_t)batch * m->words_per_row * 4, ctx->stream));
+  else
+    DRB_CUDA_TRY(ctx, cudaMemsetAsync(w.label_count, 0, (size_t)L.items_pad * 4, ctx->stream));
+
+  // 1. labels of the batch (cdae.py:61-62) and, in counter mode, the corruption mask (cdae.py:63-64)
+  BatchPrepArgs bp{};
+  bp.indptr = m->d.csr_indptr; bp.indices = m->d.csr_indices; bp.rows = uids; bp.keep_off = keep_off;
+  bp.count = per_user ? nullptr : w.label_count;
+  bp.label_bits = per_user ? w.label_bits : nullptr;
+  bp.words_per_row = m->words_per_row;
+  bp.keep_out = keep ? nullptr : w.keep;
+  bp.seed = a->philox_seed; bp.step = a->philox_step; bp.q = m->d.corruption_level;
+  if ((r = launch_batch_prep(ctx, bp, batch))) return r;
+  const uint8_t* keep_used = keep ? keep : w.keep;
+  if (m->d.corruption_level == 0.f) keep_used = nullptr;
+
+  // 2. K1: h = sigmoid(s * sum_kept W[i] + V[u] + b)
+  const float s = (float)(1.0 / (1.0 - (double)m->d.corruption_level));
+  if ((r = cdae_hidden_into(m, uids, batch, keep_off, keep_used, s, w.h))) return r;
+
+  // 3. K2: z2 = h W'^T + b', p = sigmoid, loss terms, dL/dz2 (never materialises p)
+  GemmArgs g1{};
+  g1.A = w.h; g1.lda = ld; g1.B = P + L.off_w2t; g1.ldb = ld; g1.C = w.dz; g1.ldc = L.items_pad;
+  g1.M = batch; g1.N = I; g1.Kred = ld; g1.splits = 1;
+  g1.bias = P + L.off_b2;
+  g1.label_count = per_user ? nullptr : w.label_count;
+  g1.label_bits = per_user ? w.label_bits : nullptr; g1.words_per_row = m->words_per_row;
+  g1.loss_kind = m->d.loss_kind; g1.inv_count = (float)(1.0 / ((double)batch * (double)I)); g1.batch = batch;
+  g1.loss_part = w.loss_part; g1.col_part = w.col_b2;
+  int n_mtiles = 0, n_blocks = 0;
+  if ((r = launch_gemm(ctx, LAYOUT_KK, EPI_CDAE_LOSS, g1, &n_mtiles, &n_blocks))) return r;
+  if ((r = launch_reduce_partials(ctx, w.col_b2, n_mtiles, L.items_pad, G + L.off_b2, L.items_pad))) return r;
+
+  // 4. K3: dW'^T = dz^T h   (I x K)
+  GemmArgs g2{};
+  g2.A = w.dz; g2.lda = L.items_pad; g2.B = w.h; g2.ldb = ld; g2.C = G + L.off_w2t; g2.ldc = ld;
+  g2.M = I; g2.N = ld; g2.Kred = batch; g2.splits = 1;
+  if ((r = launch_gemm(ctx, LAYOUT_MN, EPI_STORE, g2))) return r;
+
+  // 5. K3: dh = dz W'^T  (B x K), split over the item range, partials reduced by the dz1 kernel
+  GemmArgs g3{};
+  g3.A = w.dz; g3.lda = L.items_pad; g3.B = P + L.off_w2t; g3.ldb = ld; g3.C = w.dh_part; g3.ldc = ld;
+  g3.M = batch; g3.N = ld; g3.Kred = I; g3.splits = m->splits;
+  if ((r = launch_gemm(ctx, LAYOUT_KN, EPI_STORE, g3))) return r;
+  int nb = launch_dz1(ctx, w.dh_part, m->splits, w.h, w.dz1, batch, ld, w.col_b);
+  if (nb < 0) return nb;
+  if ((r = launch_reduce_partials(ctx, w.col_b, nb, ld, G + L.off_b, ld))) return r;
+
+  // 6. K3: scatter dz1 rows into dW (kept items, scaled by s) and dV[u]
+  ScatterArgs sc{};
+  sc.indptr = m->d.csr_indptr; sc.indices = m->d.csr_indices; sc.values = nullptr; sc.rows = uids;
+  sc.keep_off = keep_off; sc.keep = keep_used; sc.row_scale = nullptr; sc.scale = s;
+  sc.d = w.dz1; sc.ld = ld; sc.gtable = G + L.off_w; sc.growbias = G + L.off_v;
+  if ((r = launch_scatter(ctx, sc, batch))) return r;
+
+  // 7. K4: fused Adam + L2 over the arena; t per reference variable [W, W_, V, b, b_]
+  AdamArgs ad{};
+  ad.w = P; ad.m = m->d.adam_m; ad.v = m->d.adam_v; ad.g = G;
+  ad.beta1 = a->beta1; ad.beta2 = a->beta2; ad.eps = a->epsilon;
+  const float c = a->reg_rate / (float)batch;                       // cdae.py:82
+  const int64_t offs[6] = {L.off_w2t, L.off_w, L.off_v, L.off_b, L.off_b2, L.total};
+  const int tmap[5] = {1, 0, 2, 3, 4};
+  for (int sidx = 0; sidx < 5; sidx++) {
+    ad.seg[sidx].off4 = offs[sidx] / 4;
+    ad.seg[sidx].n4 = (offs[sidx + 1] - offs[sidx]) / 4;
+    ad.seg[sidx].alpha = drb_adam_alpha(a->learning_rate, a->beta1, a->beta2, a->t[tmap[sidx]]);
+    ad.seg[sidx].l2 = (sidx < 3) ? c : 0.f;
+    ad.seg[sidx].regw = (sidx < 3) ? 0.5f * c : 0.f;
+  }
+  ad.nseg = 5;
+  ad.reg_part = w.reg_part;
+  int n_reg = 0;
+  if ((r = launch_adam(ctx, ad, &n_reg))) return r;
+  (void)U;
+  return launch_finalize_loss(ctx, w.loss_part, n_blocks, g1.inv_count, w.reg_part, n_reg, loss_out);
+}
+
+int drb_cdae_step_host(drb_cdae* m, const int32_t* uids, const int32_t* keep_off, const uint8_t* keep,
+                       int32_t batch, const drb_cdae_step_args* a, float* loss_host) {
+  if (!m || !uids || !keep_off) return drb_fail(DRB_E_INVALID, "drb_cdae_step_host: NULL argument");
+  if (batch <= 0 || batch > m->d.max_batch)
+    return drb_fail(DRB_E_INVALID, "drb_cdae_step_host: batch %d outside (0, max_batch=%d]", batch, m->d.max_batch);
+  drb_ctx* ctx = m->ctx;
+  CdaeWs& w = m->ws;
+  const int64_t nnz = keep_off[batch];
+  if (nnz > m->keep_cap) return drb_fail(DRB_E_INVALID, "drb_cdae_step_host: batch nnz %lld exceeds staging capacity", (long long)nnz);
+  DRB_CUDA_TRY(ctx, cudaMemcpyAsync(w.uids, uids, (size_t)batch * 4, cudaMemcpyHostToDevice, ctx->stream));
+  DRB_CUDA_TRY(ctx, cudaMemcpyAsync(w.keep_off, keep_off, (size_t)(batch + 1) * 4, cudaMemcpyHostToDevice, ctx->stream));
+  if (keep && nnz > 0)
+    DRB_CUDA_TRY(ctx, cudaMemcpyAsync(w.keep, keep, (size_t)nnz, cudaMemcpyHostToDevice, ctx->stream));
+  int r = drb_cdae_step(m, w.uids, w.keep_off, keep ? w.keep : nullptr, batch, a, w.loss_scalar);
+  if (r) return r;
+  if (loss_host) {
+    DRB_CUDA_TRY(ctx, cudaMemcpyAsync(loss_host, w.loss_scalar, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    DRB_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  }
+  return DRB_OK;
+}
+
+int drb_cdae_hidden(drb_cdae* m, const int32_t* uids, int32_t n, float* h_out) {
+  if (!m || !uids || !h_out || n < 0) return drb_fail(DRB_E_INVALID, "drb_cdae_hidden: bad argument");
+  // prediction path: plain 0/1 input, no corruption, no 1/(1-q) scaling (cdae.py:67-71)
+  return cdae_hidden_into(m, uids, n, nullptr, nullptr, 1.0f, h_out);
+}
+
+static int cdae_scores_chunk(drb_cdae* m, const int32_t* uids, int n, float* out) {
+  int r = cdae_hidden_into(m, uids, n, nullptr, nullptr, 1.0f, m->ws.h);
+  if (r) return r;
+  GemmArgs g{};
+  g.A = m->ws.h; g.lda = m->L.ld; g.B = m->d.params + m->L.off_w2t; g.ldb = m->L.ld; g.C = out;
+  g.ldc = m->L.items_pad; g.M = n; g.N = m->d.n_items; g.Kred = m->L.ld; g.splits = 1;
+  g.bias = m->d.params + m->L.off_b2; g.act = DRB_ACT_SIGMOID;
+  return launch_gemm(m->ctx, LAYOUT_KK, EPI_BIAS_ACT, g);
+}
+
+int drb_cdae_predict_all(drb_cdae* m, const int32_t* uids, int32_t n, float* out) {
+  if (!m || !uids || !out || n < 0) return drb_fail(DRB_E_INVALID, "drb_cdae_predict_all: bad argument");
+  for (int32_t o = 0; o < n; o += m->d.max_batch) {
+    const int c = std::min(m->d.max_batch, n - o);
+    int r = cdae_scores_chunk(m, uids + o, c, out + (int64_t)o * m->L.items_pad);
+    if (r) return r;
+  }
+  return DRB_OK;
+}
+
+int drb_cdae_rank_candidates(drb_cdae* m, const int32_t* uids, int32_t n, const int32_t* cand,
+                             const int32_t* cand_count, int32_t max_cand, int32_t novelty, int32_t* out_iid,
+                             float* out_score, int32_t* n_out) {
+  if (!m || !uids || !cand || !cand_count || !out_iid || !out_score || !n_out || n < 0)
+    return drb_fail(DRB_E_INVALID, "drb_cdae_rank_candidates: bad argument");
+  for (int32_t o = 0; o < n; o += m->d.max_batch) {
+    const int c = std::min(m->d.max_batch, n - o);
+    int r = cdae_hidden_into(m, uids + o, c, nullptr, nullptr, 1.0f, m->ws.h);
+    if (r) return r;
+    CandScoreArgs a{};
+    a.urep = m->ws.h; a.ld_u = m->L.ld; a.table = m->d.params + m->L.off_w2t; a.ld_t = m->L.ld;
+    a.bias = m->d.params + m->L.off_b2; a.width = m->d.hidden; a.mode = 0;
+    a.uids = uids + o; a.cand = cand + (int64_t)o * max_cand; a.cand_count = cand_count + o; a.max_cand = max_cand;
+    a.seen_indptr = m->d.seen_indptr; a.seen_indices = m->d.seen_indices; a.novelty = novelty;
+    a.out_iid = out_iid + (int64_t)o * max_cand; a.out_score = out_score + (int64_t)o * max_cand; a.n_out = n_out + o;
+    if ((r = launch_rank_candidates(m->ctx, a, c))) return r;
+  }
+  return DRB_OK;
+}
+
+int drb_cdae_topk(drb_cdae* m, const int32_t* uids, int32_t n, int32_t k, int32_t novelty, int32_t* out_iid,
+                  float* out_score, int32_t* n_out) {
+  if (!m || !uids || !out_iid || !out_score || !n_out || n < 0)
+    return drb_fail(DRB_E_INVALID, "drb_cdae_topk: bad argument");
+  for (int32_t o = 0; o < n; o += m->d.max_batch) {
+    const int c = std::min(m->d.max_batch, n - o);
+    int r = cdae_scores_chunk(m, uids + o, c, m->ws.dz);
+    if (r) return r;
+    TopkArgs t{};
+    t.scores = m->ws.dz; t.ld = m->L.items_pad; t.n_items = m->d.n_items; t.uids = uids + o;
+    t.seen_indptr = m->d.seen_indptr; t.seen_indices = m->d.seen_indices; t.novelty = novelty; t.k = k;
+    t.out_iid = out_iid + (int64_t)o * k; t.out_score = out_score + (int64_t)o * k; t.n_out = n_out + o;
+    if ((r = launch_topk(m->ctx, t, c))) return r;
+  }
+  return DRB_OK;
+}
+
+}  // extern "C"
+
+// ========================================================================================== DMF
+struct DmfTower {
+  int n_layers; int in_dim;
+  int width[DRB_DMF_MAX_LAYERS], ld[DRB_DMF_MAX_LAYERS];
+  int64_t off_k[DRB_DMF_MAX_LAYERS], off_b[DRB_DMF_MAX_LAYERS];
+  const int64_t* indptr; const int32_t* indices; const float* values; const float* row_scale;
+  float* act[DRB_DMF_MAX_LAYERS];    // [max_batch, ld_l] post-relu activations
+  float* dpre[DRB_DMF_MAX_LAYERS];   // [max_batch, ld_l] gradient w.r.t. pre-activations
+};
+
+struct drb_dmf {
+  drb_ctx* ctx;
+  drb_dmf_desc d;
+  drb_dmf_layout_t L;
+  DmfTower tw[2];  // 0 = user tower (rows over items), 1 = item tower (rows over users)
+  float *col_part, *loss_part, *reg_part, *loss_scalar, *labels, *p_tmp, *item_rep, *user_rep;
+  int32_t *uids, *iids;
+  int64_t ws_bytes;
+};
+
+static int dmf_fill_layout(int32_t n_users, int32_t n_items, const int32_t* uf, int32_t nu, const int32_t* itf,
+                           int32_t ni, drb_dmf_layout_t* L) {
+  if (!L || !uf || !itf || nu < 1 || ni < 1 || nu > DRB_DMF_MAX_LAYERS || ni > DRB_DMF_MAX_LAYERS)
+    return drb_fail(DRB_E_INVALID, "drb_dmf_layout: between 1 and %d layers per tower are supported", DRB_DMF_MAX_LAYERS);
+  if (uf[nu - 1] != itf[ni - 1])
+    return drb_fail(DRB_E_INVALID, "The last user and item factors dimension must be equal (%d != %d)", uf[nu - 1], itf[ni - 1]);
+  std::memset(L, 0, sizeof(*L));
+  L->n_layers_user = nu; L->n_layers_item = ni;
+  int64_t off = 0;
+  for (int t = 0; t < 2; t++) {
+    const int32_t* f = t ? itf : uf;
+    const int n = t ? ni : nu;
+    int64_t in = t ? n_users : n_items;
+    for (int l = 0; l < n; l++) {
+      if (f[l] <= 0 || f[l] > 512) return drb_fail(DRB_E_INVALID, "drb_dmf_layout: layer widths must be in (0, 512]");
+      const int ld = (int)drb_round_up(f[l], 4);
+      (t ? L->ld_item : L->ld_user)[l] = ld;
+      (t ? L->off_kernel_item : L->off_kernel_user)[l] = off; off += in * ld;
+      (t ? L->off_bias_item : L->off_bias_user)[l] = off; off += ld;
+      in = f[l];
+    }
+  }
+  L->total = off;
+  return DRB_OK;
+}
+
+static int64_t dmf_carve(drb_dmf* m, void* base, const drb_dmf_layout_t& L, int n_users, int n_items, int max_batch,
+                         int sm_count) {
+  Carver c(base);
+  const int64_t B = max_batch;
+  int maxld = 4;
+  for (int t = 0; t < 2; t++) {
+    const int n = t ? L.n_layers_item : L.n_layers_user;
+    for (int l = 0; l < n; l++) {
+      const int ld = (t ? L.ld_item : L.ld_user)[l];
+      maxld = std::max(maxld, ld);
+      float* a = c.take<float>(B * ld);
+      float* dp = c.take<float>(B * ld);
+      if (m) { m->tw[t].act[l] = a; m->tw[t].dpre[l] = dp; }
+    }
+  }
+  const int ldl = L.ld_user[L.n_layers_user - 1];
+  float* col = c.take<float>((int64_t)((max_batch + 31) / 32) * maxld);
+  float* lp = c.take<float>(B);
+  float* rp = c.take<float>((int64_t)sm_count * 16);
+  float* ls = c.take<float>(64);
+  float* lab = c.take<float>(B);
+  float* pt = c.take<float>(B);
+  float* irep = c.take<float>((int64_t)n_items * ldl);
+  float* urep = c.take<float>(B * ldl);
+  int32_t* u = c.take<int32_t>(B);
+  int32_t* i = c.take<int32_t>(B);
+  if (m) {
+    m->col_part = col; m->loss_part = lp; m->reg_part = rp; m->loss_scalar = ls; m->labels = lab; m->p_tmp = pt;
+    m->item_rep = irep; m->user_rep = urep; m->uids = u; m->iids = i;
+  }
+  (void)n_users;
+  return c.off;
+}
+
+// forward of one tower for n rows (n <= max_batch); result in tw.act[last]
+static int dmf_tower_fwd(drb_dmf* m, int t, const int32_t* ids, int n) {
+  DmfTower& T = m->tw[t];
+  float* P = m->d.params;
+  GatherArgs g{};
+  g.indptr = T.indptr; g.indices = T.indices; g.values = T.values; g.rows = ids;
+  g.table = P + T.off_k[0]; g.ld = T.ld[0]; g.bias = P + T.off_b[0];
+  g.row_scale = T.row_scale; g.scale = 1.0f; g.act = DRB_ACT_RELU; g.width = T.width[0]; g.out = T.act[0];
+  int r = launch_gather(m->ctx, g, n);
+  if (r) return r;
+  for (int l = 1; l < T.n_layers; l++) {
+    GemmArgs a{};
+    a.A = T.act[l - 1]; a.lda = T.ld[l - 1]; a.B = P + T.off_k[l]; a.ldb = T.ld[l]; a.C = T.act[l]; a.ldc = T.ld[l];
+    a.M = n; a.N = T.width[l]; a.Kred = T.width[l - 1]; a.splits = 1; a.bias = P + T.off_b[l]; a.act = DRB_ACT_RELU;
+    if ((r = launch_gemm(m->ctx, LAYOUT_KN, EPI_BIAS_ACT, a))) return r;
+  }
+  return DRB_OK;
+}
+
+static int dmf_tower_bwd(drb_dmf* m, int t, const int32_t* ids, int n) {
+  DmfTower& T = m->tw[t];
+  float* P = m->d.params;
+  float* G = m->d.grads;
+  int r;
+  for (int l = T.n_layers - 1; l >= 1; l--) {
+    GemmArgs gk{};  // dK_l = act_{l-1}^T dpre_l
+    gk.A = T.act[l - 1]; gk.lda = T.ld[l - 1]; gk.B = T.dpre[l]; gk.ldb = T.ld[l]; gk.C = G + T.off_k[l];
+    gk.ldc = T.ld[l]; gk.M = T.width[l - 1]; gk.N = T.ld[l]; gk.Kred = n; gk.splits = 1;
+    if ((r = launch_gemm(m->ctx, LAYOUT_MN, EPI_STORE, gk))) return r;
+    int nb = launch_colpart(m->ctx, T.dpre[l], n, T.ld[l], m->col_part);
+    if (nb < 0) return nb;
+    if ((r = launch_reduce_partials(m->ctx, m->col_part, nb, T.ld[l], G + T.off_b[l], T.ld[l]))) return r;
+    GemmArgs gd{};  // dpre_{l-1} = (dpre_l K_l^T) * [act_{l-1} > 0]
+    gd.A = T.dpre[l]; gd.lda = T.ld[l]; gd.B = P + T.off_k[l]; gd.ldb = T.ld[l]; gd.C = T.dpre[l - 1];
+    gd.ldc = T.ld[l - 1]; gd.M = n; gd.N = T.width[l - 1]; gd.Kred = T.ld[l]; gd.splits = 1; gd.mask = T.act[l - 1];
+    if ((r = launch_gemm(m->ctx, LAYOUT_KK, EPI_MASK_POS, gd))) return r;
+  }
+  int nb = launch_colpart(m->ctx, T.dpre[0], n, T.ld[0], m->col_part);
+  if (nb < 0) return nb;
+  if ((r = launch_reduce_partials(m->ctx, m->col_part, nb, T.ld[0], G + T.off_b[0], T.ld[0]))) return r;
+  ScatterArgs sc{};
+  sc.indptr = T.indptr; sc.indices = T.indices; sc.values = T.values; sc.rows = ids;
+  sc.row_scale = T.row_scale; sc.scale = 1.0f; sc.d = T.dpre[0]; sc.ld = T.ld[0];
+  sc.gtable = G + T.off_k[0]; sc.growbias = nullptr;
+  return launch_scatter(m->ctx, sc, n);
+}
+
+extern "C" {
+
+int drb_dmf_layout(int32_t n_users, int32_t n_items, const int32_t* user_factors, int32_t n_user_layers,
+                   const int32_t* item_factors, int32_t n_item_layers, drb_dmf_layout_t* out) {
+  if (n_users <= 0 || n_items <= 0) return drb_fail(DRB_E_INVALID, "drb_dmf_layout: n_users, n_items must be > 0");
+  return dmf_fill_layout(n_users, n_items, user_factors, n_user_layers, item_factors, n_item_layers, out);
+}
+
+int64_t drb_dmf_workspace_bytes(int32_t n_users, int32_t n_items, const int32_t* user_factors, int32_t n_user_layers,
+                                const int32_t* item_factors, int32_t n_item_layers, int32_t max_batch) {
+  drb_dmf_layout_t L;
+  if (drb_dmf_layout(n_users, n_items, user_factors, n_user_layers, item_factors, n_item_layers, &L) || max_batch <= 0)
+    return -1;
+  return dmf_carve(nullptr, nullptr, L, n_users, n_items, max_batch, 256);
+}
+
+int drb_dmf_create(drb_ctx* ctx, const drb_dmf_desc* d, drb_dmf** out) {
+  if (!ctx || !d || !out) return drb_fail(DRB_E_INVALID, "drb_dmf_create: NULL argument");
+  drb_dmf_layout_t L;
+  int r = drb_dmf_layout(d->n_users, d->n_items, d->user_factors, d->n_layers_user, d->item_factors,
+                         d->n_layers_item, &L);
+  if (r) return r;
+  if (!d->params || !d->csr_indptr || !d->csr_indices || !d->csr_values || !d->csc_indptr || !d->csc_indices ||
+      !d->csc_values || !d->workspace || d->max_batch <= 0)
+    return drb_fail(DRB_E_INVALID, "drb_dmf_create: params, csr, csc and workspace are required");
+  if (((uintptr_t)d->params | (uintptr_t)d->adam_m | (uintptr_t)d->adam_v | (uintptr_t)d->grads |
+       (uintptr_t)d->workspace) & 15)
+    return drb_fail(DRB_E_INVALID, "drb_dmf_create: arenas and workspace must be 16-byte aligned");
+  drb_dmf* m = new (std::nothrow) drb_dmf;
+  if (!m) return drb_fail(DRB_E_NOMEM, "out of memory");
+  std::memset(m, 0, sizeof(*m));
+  m->ctx = ctx; m->d = *d; m->L = L;
+  for (int t = 0; t < 2; t++) {
+    DmfTower& T = m->tw[t];
+    T.n_layers = t ? L.n_layers_item : L.n_layers_user;
+    T.in_dim = t ? d->n_users : d->n_items;
+    for (int l = 0; l < T.n_layers; l++) {
+      T.width[l] = (t ? d->item_factors : d->user_factors)[l];
+      T.ld[l] = (t ? L.ld_item : L.ld_user)[l];
+      T.off_k[l] = (t ? L.off_kernel_item : L.off_kernel_user)[l];
+      T.off_b[l] = (t ? L.off_bias_item : L.off_bias_user)[l];
+    }
+    T.indptr = t ? d->csc_indptr : d->csr_indptr;
+    T.indices = t ? d->csc_indices : d->csr_indices;
+    T.values = t ? d->csc_values : d->csr_values;
+    T.row_scale = t ? d->csc_row_scale : d->csr_row_scale;
+  }
+  m->ws_bytes = dmf_carve(m, d->workspace, L, d->n_users, d->n_items, d->max_batch, ctx->sm_count);
+  if (m->ws_bytes > d->workspace_bytes) {
+    int64_t need = m->ws_bytes;
+    delete m;
+    return drb_fail(DRB_E_INVALID, "drb_dmf_create: workspace too small (%lld < %lld bytes)",
+                    (long long)d->workspace_bytes, (long long)need);
+  }
+  *out = m;
+  return DRB_OK;
+}
+int drb_dmf_destroy(drb_dmf* m) { delete m; return DRB_OK; }
+
+int drb_dmf_step(drb_dmf* m, const int32_t* uids, const int32_t* iids, const float* labels, int32_t batch,
+                 const drb_dmf_step_args* a, float* loss_out) {
+  if (!m || !uids || !iids || !labels || !a || !loss_out) return drb_fail(DRB_E_INVALID, "drb_dmf_step: NULL argument");
+  if (batch <= 0 || batch > m->d.max_batch)
+    return drb_fail(DRB_E_INVALID, "drb_dmf_step: batch %d outside (0, max_batch=%d]", batch, m->d.max_batch);
+  if (!m->d.adam_m || !m->d.adam_v || !m->d.grads)
+    return drb_fail(DRB_E_STATE, "drb_dmf_step: model was created without optimizer arenas");
+  drb_ctx* ctx = m->ctx;
+  if (ctx->sticky) return drb_fail(DRB_E_CUDA, "context has a sticky CUDA error (%d)", ctx->sticky);
+  int r;
+  DRB_CUDA_TRY(ctx, cudaMemsetAsync(m->d.grads, 0, (size_t)m->L.total * sizeof(float), ctx->stream));
+  if ((r = dmf_tower_fwd(m, 0, uids, batch))) return r;
+  if ((r = dmf_tower_fwd(m, 1, iids, batch))) return r;
+  const int lu = m->tw[0].n_layers - 1, li = m->tw[1].n_layers - 1;
+  DmfHeadArgs h{};
+  h.a = m->tw[0].act[lu]; h.e = m->tw[1].act[li]; h.ld = m->tw[0].ld[lu]; h.width = m->tw[0].width[lu];
+  h.labels = labels; h.p_out = nullptr; h.da = m->tw[0].dpre[lu]; h.de = m->tw[1].dpre[li];
+  h.loss_part = m->loss_part; h.n = batch;
+  if ((r = launch_dmf_head(ctx, h))) return r;
+  if ((r = dmf_tower_bwd(m, 0, uids, batch))) return r;
+  if ((r = dmf_tower_bwd(m, 1, iids, batch))) return r;
+  AdamArgs ad{};
+  ad.w = m->d.params; ad.m = m->d.adam_m; ad.v = m->d.adam_v; ad.g = m->d.grads;
+  ad.beta1 = a->beta1; ad.beta2 = a->beta2; ad.eps = a->epsilon;
+  int ns = 0;
+  for (int t = 0; t < 2; t++) {
+    const float alpha = drb_adam_alpha(a->learning_rate, a->beta1, a->beta2, a->t[t]);
+    DmfTower& T = m->tw[t];
+    int64_t in = T.in_dim;
+    for (int l = 0; l < T.n_layers; l++) {
+      ad.seg[ns].off4 = T.off_k[l] / 4; ad.seg[ns].n4 = in * T.ld[l] / 4; ad.seg[ns].alpha = alpha;
+      ad.seg[ns].l2 = 2.0f * a->reg_rate; ad.seg[ns].regw = a->reg_rate;       // regularizers.l2: reg * sum(w^2)
+      ns++;
+      ad.seg[ns].off4 = T.off_b[l] / 4; ad.seg[ns].n4 = T.ld[l] / 4; ad.seg[ns].alpha = alpha;
+      ad.seg[ns].l2 = 0.f; ad.seg[ns].regw = 0.f;
+      ns++;
+      in = T.width[l];
+    }
+  }
+  ad.nseg = ns;
+  ad.reg_part = m->reg_part;
+  int n_reg = 0;
+  if ((r = launch_adam(ctx, ad, &n_reg))) return r;
+  return launch_finalize_loss(ctx, m->loss_part, batch, 1.0f / (float)batch, m->reg_part, n_reg, loss_out);
+}
+
+int drb_dmf_step_host(drb_dmf* m, const int32_t* uids, const int32_t* iids, const float* labels, int32_t batch,
+                      const drb_dmf_step_args* a, float* loss_host) {
+  if (!m || !uids || !iids || !labels) return drb_fail(DRB_E_INVALID, "drb_dmf_step_host: NULL argument");
+  if (batch <= 0 || batch > m->d.max_batch)
+    return drb_fail(DRB_E_INVALID, "drb_dmf_step_host: batch %d outside (0, max_batch=%d]", batch, m->d.max_batch);
+  drb_ctx* ctx = m->ctx;
+  DRB_CUDA_TRY(ctx, cudaMemcpyAsync(m->uids, uids, (size_t)batch * 4, cudaMemcpyHostToDevice, ctx->stream));
+  DRB_CUDA_TRY(ctx, cudaMemcpyAsync(m->iids, iids, (size_t)batch * 4, cudaMemcpyHostToDevice, ctx->stream));
+  DRB_CUDA_TRY(ctx, cudaMemcpyAsync(m->labels, labels, (size_t)batch * 4, cudaMemcpyHostToDevice, ctx->stream));
+  int r = drb_dmf_step(m, m->uids, m->iids, m->labels, batch, a, m->loss_scalar);
+  if (r) return r;
+  if (loss_host) {
+    DRB_CUDA_TRY(ctx, cudaMemcpyAsync(loss_host, m->loss_scalar, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    DRB_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  }
+  return DRB_OK;
+}
+
+int drb_dmf_forward_pairs(drb_dmf* m, const int32_t* uids, const int32_t* iids, int32_t n, float* p_out) {
+  if (!m || !uids || !iids || !p_out || n < 0) return drb_fail(DRB_E_INVALID, "drb_dmf_forward_pairs: bad argument");
+  const int lu = m->tw[0].n_layers - 1, li = m->tw[1].n_layers - 1;
+  for (int32_t o = 0; o < n; o += m->d.max_batch) {
+    const int c = std::min(m->d.max_batch, n - o);
+    int r;
+    if ((r = dmf_tower_fwd(m, 0, uids + o, c))) return r;
+    if ((r = dmf_tower_fwd(m, 1, iids + o, c))) return r;
+    DmfHeadArgs h{};
+    h.a = m->tw[0].act[lu]; h.e = m->tw[1].act[li]; h.ld = m->tw[0].ld[lu]; h.width = m->tw[0].width[lu];
+    h.labels = nullptr; h.p_out = p_out + o; h.n = c;
+    if ((r = launch_dmf_head(m->ctx, h))) return r;
+  }
+  return DRB_OK;
+}
+
+int drb_dmf_rank_candidates(drb_dmf* m, const int32_t* uids, int32_t n, const int32_t* cand,
+                            const int32_t* cand_count, int32_t max_cand, int32_t novelty, int32_t* out_iid,
+                            float* out_score, int32_t* n_out) {
+  if (!m || !uids || !cand || !cand_count || !out_iid || !out_score || !n_out || n < 0)
+    return drb_fail(DRB_E_INVALID, "drb_dmf_rank_candidates: bad argument");
+  drb_ctx* ctx = m->ctx;
+  const int lu = m->tw[0].n_layers - 1, li = m->tw[1].n_layers - 1;
+  const int ldl = m->tw[1].ld[li];
+  // item tower for every item: ids 0..n_items-1 are generated on the device by a strided memcpy-free trick:
+  // the id list is simply the identity, staged through the iids buffer chunk by chunk from the host.
+  std::vector<int32_t> ident(m->d.max_batch);
+  int r;
+  for (int32_t o = 0; o < m->d.n_items; o += m->d.max_batch) {
+    const int c = std::min(m->d.max_batch, m->d.n_items - o);
+    for (int i = 0; i < c; i++) ident[i] = o + i;
+    DRB_CUDA_TRY(ctx, cudaMemcpyAsync(m->iids, ident.data(), (size_t)c * 4, cudaMemcpyHostToDevice, ctx->stream));
+    DRB_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));  // `ident` is reused by the next chunk
+    if ((r = dmf_tower_fwd(m, 1, m->iids, c))) return r;
+    DRB_CUDA_TRY(ctx, cudaMemcpyAsync(m->item_rep + (int64_t)o * ldl, m->tw[1].act[li], (size_t)c * ldl * 4,
+                                      cudaMemcpyDeviceToDevice, ctx->stream));
+  }
+  for (int32_t o = 0; o < n; o += m->d.max_batch) {
+    const int c = std::min(m->d.max_batch, n - o);
+    if ((r = dmf_tower_fwd(m, 0, uids + o, c))) return r;
+    CandScoreArgs a{};
+    a.urep = m->tw[0].act[lu]; a.ld_u = m->tw[0].ld[lu]; a.table = m->item_rep; a.ld_t = ldl; a.bias = nullptr;
+    a.width = m->tw[0].width[lu]; a.mode = 1;
+    a.uids = uids + o; a.cand = cand + (int64_t)o * max_cand; a.cand_count = cand_count + o; a.max_cand = max_cand;
+    a.seen_indptr = m->d.csr_indptr; a.seen_indices = m->d.csr_indices; a.novelty = novelty;
+    a.out_iid = out_iid + (int64_t)o * max_cand; a.out_score = out_score + (int64_t)o * max_cand; a.n_out = n_out + o;
+    if ((r = launch_rank_candidates(ctx, a, c))) return r;
+  }
+  return DRB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,363 @@
+// Host-side replay of CPython's random.Random (MT19937) and everything on the hot path that is sequential by
+// construction: PointSampler, the CDAE corruption stream, ranking_evaluation's per-user candidate generation.
+// Reference behaviour: DRecPy/Sampler/point_sampler.py:19-96, DRecPy/Dataset/mem_dataset.py:101-163,
+// DRecPy/Recommender/cdae.py:63-64, DRecPy/Evaluation/Processes/ranking_evaluation.py:108-116,163-219.
+// The generator is the published MT19937 with CPython's seeding (init_by_array over the 32-bit limbs of abs(seed)).
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <unordered_set>
+#include <vector>
+
+#include "drb_internal.h"
+
+struct drb_rng {
+  static constexpr int N = 624, M = 397;
+  uint32_t mt[N];
+  int idx;
+
+  void init_genrand(uint32_t s) {
+    mt[0] = s;
+    for (int i = 1; i < N; i++) mt[i] = 1812433253u * (mt[i - 1] ^ (mt[i - 1] >> 30)) + (uint32_t)i;
+    idx = N;
+  }
+  void init_by_array(const uint32_t* key, int len) {
+    init_genrand(19650218u);
+    int i = 1, j = 0;
+    for (int k = (N > len ? N : len); k; k--) {
+      mt[i] = (mt[i] ^ ((mt[i - 1] ^ (mt[i - 1] >> 30)) * 1664525u)) + key[j] + (uint32_t)j;
+      i++; j++;
+      if (i >= N) { mt[0] = mt[N - 1]; i = 1; }
+      if (j >= len) j = 0;
+    }
+    for (int k = N - 1; k; k--) {
+      mt[i] = (mt[i] ^ ((mt[i - 1] ^ (mt[i - 1] >> 30)) * 1566083941u)) - (uint32_t)i;
+      i++;
+      if (i >= N) { mt[0] = mt[N - 1]; i = 1; }
+    }
+    mt[0] = 0x80000000u;
+  }
+  void seed(uint64_t a) {  // random.seed(int): key = little-endian 32-bit limbs of abs(seed), at least one
+    uint32_t key[2] = {(uint32_t)(a & 0xffffffffu), (uint32_t)(a >> 32)};
+    init_by_array(key, key[1] ? 2 : 1);
+  }
+  void twist() {
+    auto mix = [](uint32_t u, uint32_t v) { return (u & 0x80000000u) | (v & 0x7fffffffu); };
+    int kk = 0;
+    for (; kk < N - M; kk++) {
+      uint32_t y = mix(mt[kk], mt[kk + 1]);
+      mt[kk] = mt[kk + M] ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+    }
+    for (; kk < N - 1; kk++) {
+      uint32_t y = mix(mt[kk], mt[kk + 1]);
+      mt[kk] = mt[kk + (M - N)] ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+    }
+    uint32_t y = mix(mt[N - 1], mt[0]);
+    mt[N - 1] = mt[M - 1] ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+    idx = 0;
+  }
+  static inline uint32_t temper(uint32_t y) {
+    y ^= (y >> 11);
+    y ^= (y << 7) & 0x9d2c5680u;
+    y ^= (y << 15) & 0xefc60000u;
+    y ^= (y >> 18);
+    return y;
+  }
+  inline uint32_t next32() {
+    if (idx >= N) twist();
+    return temper(mt[idx++]);
+  }
+  inline void skip(int64_t n) {  // advance the stream by n outputs without tempering
+    while (n > 0) {
+      if (idx >= N) twist();
+      int64_t take = std::min<int64_t>(n, N - idx);
+      idx += (int)take;
+      n -= take;
+    }
+  }
+  inline double random() {
+    uint32_t a = next32() >> 5, b = next32() >> 6;
+    return (a * 67108864.0 + b) * (1.0 / 9007199254740992.0);
+  }
+  inline uint64_t getrandbits(int k) {
+    if (k <= 32) return next32() >> (32 - k);
+    uint64_t lo = next32();  // little-endian limbs, the last limb truncated
+    uint64_t hi = next32() >> (64 - k);
+    return lo | (hi << 32);
+  }
+  inline int64_t randbelow(int64_t n) {
+    int k = 64 - __builtin_clzll((unsigned long long)n);  // n.bit_length()
+    uint64_t r = getrandbits(k);
+    while (r >= (uint64_t)n) r = getrandbits(k);
+    return (int64_t)r;
+  }
+  inline int64_t randint(int64_t a, int64_t b) { return a + randbelow(b - a + 1); }
+};
+
+static void sample_indices(drb_rng& g, int64_t n, int64_t k, int64_t* out) {
+  // random.sample(range(n), k), CPython 3.12 (pool path vs selection-set path)
+  int64_t setsize = 21;
+  if (k > 5) setsize += (int64_t)std::pow(4.0, std::ceil(std::log((double)(k * 3)) / std::log(4.0)));
+  if (n <= setsize) {
+    std::vector<int64_t> pool(n);
+    for (int64_t i = 0; i < n; i++) pool[i] = i;
+    for (int64_t i = 0; i < k; i++) {
+      int64_t j = g.randbelow(n - i);
+      out[i] = pool[j];
+      pool[j] = pool[n - i - 1];
+    }
+  } else {
+    std::unordered_set<int64_t> selected;
+    for (int64_t i = 0; i < k; i++) {
+      int64_t j = g.randbelow(n);
+      while (selected.count(j)) j = g.randbelow(n);
+      selected.insert(j);
+      out[i] = j;
+    }
+  }
+}
+
+static void shuffle_i64(drb_rng& g, int64_t n, int64_t* x) {
+  for (int64_t i = n - 1; i >= 1; i--) {
+    int64_t j = g.randbelow(i + 1);
+    std::swap(x[i], x[j]);
+  }
+}
+
+extern "C" {
+
+int drb_rng_create(uint64_t abs_seed, drb_rng** out) {
+  if (!out) return drb_fail(DRB_E_INVALID, "drb_rng_create: out is NULL");
+  drb_rng* g = new (std::nothrow) drb_rng;
+  if (!g) return drb_fail(DRB_E_NOMEM, "drb_rng_create: out of memory");
+  g->seed(abs_seed);
+  *out = g;
+  return DRB_OK;
+}
+int drb_rng_destroy(drb_rng* rng) { delete rng; return DRB_OK; }
+int drb_rng_seed(drb_rng* rng, uint64_t abs_seed) {
+  if (!rng) return drb_fail(DRB_E_INVALID, "drb_rng_seed: rng is NULL");
+  rng->seed(abs_seed);
+  return DRB_OK;
+}
+double drb_rng_random(drb_rng* rng) { return rng->random(); }
+uint64_t drb_rng_getrandbits(drb_rng* rng, int k) { return (k < 1 || k > 64) ? 0 : rng->getrandbits(k); }
+int64_t drb_rng_randbelow(drb_rng* rng, int64_t n) { return n < 1 ? -1 : rng->randbelow(n); }
+int drb_rng_random_fill(drb_rng* rng, int64_t n, double* out) {
+  if (!rng || (n > 0 && !out)) return drb_fail(DRB_E_INVALID, "drb_rng_random_fill: NULL argument");
+  for (int64_t i = 0; i < n; i++) out[i] = rng->random();
+  return DRB_OK;
+}
+int drb_rng_sample_indices(drb_rng* rng, int64_t n, int64_t k, int64_t* out) {
+  if (!rng || k < 0 || k > n) return drb_fail(DRB_E_INVALID, "drb_rng_sample_indices: need 0 <= k <= n");
+  sample_indices(*rng, n, k, out);
+  return DRB_OK;
+}
+int drb_rng_shuffle_i64(drb_rng* rng, int64_t n, int64_t* x) {
+  if (!rng || (n > 0 && !x)) return drb_fail(DRB_E_INVALID, "drb_rng_shuffle_i64: NULL argument");
+  shuffle_i64(*rng, n, x);
+  return DRB_OK;
+}
+int drb_rng_getstate(const drb_rng* rng, uint32_t state[625]) {
+  if (!rng || !state) return drb_fail(DRB_E_INVALID, "drb_rng_getstate: NULL argument");
+  std::memcpy(state, rng->mt, sizeof(rng->mt));
+  state[624] = (uint32_t)rng->idx;
+  return DRB_OK;
+}
+int drb_rng_setstate(drb_rng* rng, const uint32_t state[625]) {
+  if (!rng || !state || state[624] > 624) return drb_fail(DRB_E_INVALID, "drb_rng_setstate: bad state");
+  std::memcpy(rng->mt, state, sizeof(rng->mt));
+  rng->idx = (int)state[624];
+  return DRB_OK;
+}
+
+}  // extern "C"
+
+// ------------------------------------------------------------------------------------------ PointSampler
+struct drb_sampler {
+  int32_t max_uid, max_iid;
+  const int64_t* pos_indptr; const int32_t* pos_iid; const double* pos_val;
+  const int64_t* all_indptr; const int32_t* all_iid;
+  double neg_ratio;
+  drb_rng rng, null_rng, pos_rng;  // point_sampler.py:30, mem_dataset.py:135-136, :113-114
+};
+
+extern "C" {
+
+int drb_sampler_create(int32_t max_uid, int32_t max_iid, const int64_t* pos_indptr, const int32_t* pos_iid,
+                       const double* pos_val, const int64_t* all_indptr, const int32_t* all_iid_sorted,
+                       double neg_ratio, uint64_t abs_seed, drb_sampler** out) {
+  if (!out || !pos_indptr || !all_indptr || max_uid < 0 || max_iid < 0)
+    return drb_fail(DRB_E_INVALID, "drb_sampler_create: bad argument");
+  if (pos_indptr[(int64_t)max_uid + 1] <= 0)
+    return drb_fail(DRB_E_INVALID, "No records were found to sample from.");  // mem_dataset.py:111
+  drb_sampler* s = new (std::nothrow) drb_sampler;
+  if (!s) return drb_fail(DRB_E_NOMEM, "drb_sampler_create: out of memory");
+  s->max_uid = max_uid; s->max_iid = max_iid;
+  s->pos_indptr = pos_indptr; s->pos_iid = pos_iid; s->pos_val = pos_val;
+  s->all_indptr = all_indptr; s->all_iid = all_iid_sorted;
+  s->neg_ratio = neg_ratio;
+  s->rng.seed(abs_seed); s->null_rng.seed(abs_seed); s->pos_rng.seed(abs_seed);
+  *out = s;
+  return DRB_OK;
+}
+int drb_sampler_destroy(drb_sampler* s) { delete s; return DRB_OK; }
+
+int drb_sampler_sample(drb_sampler* s, int64_t n, int32_t* uid, int32_t* iid, double* val) {
+  if (!s || n < 0 || (n > 0 && (!uid || !iid || !val)))
+    return drb_fail(DRB_E_INVALID, "drb_sampler_sample: bad argument");
+  const double hi = s->neg_ratio + 1.0;
+  for (int64_t t = 0; t < n; t++) {
+    bool null_pair = (0.0 + (hi - 0.0) * s->rng.random()) > 1.0;  // point_sampler.py:58
+    if (null_pair) {
+      for (;;) {  // mem_dataset.py:158-163
+        int64_t u = s->null_rng.randint(0, s->max_uid);
+        int64_t i = s->null_rng.randint(0, s->max_iid);
+        const int32_t* lo = s->all_iid + s->all_indptr[u];
+        const int32_t* hi_ = s->all_iid + s->all_indptr[u + 1];
+        if (!std::binary_search(lo, hi_, (int32_t)i)) {
+          uid[t] = (int32_t)u; iid[t] = (int32_t)i; val[t] = 0.0;
+          break;
+        }
+      }
+    } else {
+      for (;;) {  // mem_dataset.py:119-129
+        int64_t u = s->pos_rng.randint(0, s->max_uid);
+        int64_t cnt = s->pos_indptr[u + 1] - s->pos_indptr[u];
+        if (cnt == 0) continue;
+        int64_t j = s->pos_rng.randint(0, cnt - 1);
+        int64_t r = s->pos_indptr[u] + j;
+        uid[t] = (int32_t)u; iid[t] = s->pos_iid[r]; val[t] = s->pos_val[r];
+        break;
+      }
+    }
+  }
+  return DRB_OK;
+}
+
+int drb_sampler_getstate(const drb_sampler* s, uint32_t state[3 * 625]) {
+  if (!s || !state) return drb_fail(DRB_E_INVALID, "drb_sampler_getstate: NULL argument");
+  drb_rng_getstate(&s->rng, state);
+  drb_rng_getstate(&s->null_rng, state + 625);
+  drb_rng_getstate(&s->pos_rng, state + 1250);
+  return DRB_OK;
+}
+int drb_sampler_setstate(drb_sampler* s, const uint32_t state[3 * 625]) {
+  if (!s || !state) return drb_fail(DRB_E_INVALID, "drb_sampler_setstate: NULL argument");
+  int r = drb_rng_setstate(&s->rng, state);
+  if (!r) r = drb_rng_setstate(&s->null_rng, state + 625);
+  if (!r) r = drb_rng_setstate(&s->pos_rng, state + 1250);
+  return r;
+}
+
+// ------------------------------------------------------------------------------------------ corruption mask
+int drb_batch_offsets(const int32_t* uids, int32_t batch, const int64_t* csr_indptr, int32_t* keep_off) {
+  if (!uids || !csr_indptr || !keep_off || batch < 0) return drb_fail(DRB_E_INVALID, "drb_batch_offsets: bad argument");
+  int64_t acc = 0;
+  keep_off[0] = 0;
+  for (int32_t b = 0; b < batch; b++) {
+    acc += csr_indptr[uids[b] + 1] - csr_indptr[uids[b]];
+    if (acc > INT32_MAX) return drb_fail(DRB_E_INVALID, "drb_batch_offsets: batch nnz exceeds int32");
+    keep_off[b + 1] = (int32_t)acc;
+  }
+  return DRB_OK;
+}
+
+int drb_cdae_corruption_keep_mt(drb_rng* rng, const int32_t* uids, int32_t batch, int32_t n_items, double q,
+                                const int64_t* csr_indptr, const int32_t* csr_indices, int32_t* keep_off,
+                                uint8_t* keep) {
+  if (!rng || !uids || !csr_indptr || !csr_indices || !keep_off || batch < 0 || n_items <= 0)
+    return drb_fail(DRB_E_INVALID, "drb_cdae_corruption_keep_mt: bad argument");
+  int r = drb_batch_offsets(uids, batch, csr_indptr, keep_off);
+  if (r) return r;
+  for (int32_t b = 0; b < batch; b++) {
+    // cdae.py:63-64: draw i of this user decides item i; every draw is rng.uniform(0,1) = two MT outputs.
+    const int64_t lo = csr_indptr[uids[b]], hi = csr_indptr[uids[b] + 1];
+    uint8_t* out = keep + keep_off[b];
+    int64_t pos = 0;  // next item index whose draw has not been consumed yet
+    for (int64_t j = lo; j < hi; j++) {
+      int64_t item = csr_indices[j];
+      rng->skip(2 * (item - pos));
+      double u = 0.0 + (1.0 - 0.0) * rng->random();
+      out[j - lo] = (u < q) ? 0 : 1;
+      pos = item + 1;
+    }
+    rng->skip(2 * ((int64_t)n_items - pos));
+  }
+  return DRB_OK;
+}
+
+// ------------------------------------------------------------------------------------------ evaluation candidates
+int drb_eval_candidates(int64_t n_users, const int64_t* test_indptr, const int64_t* test_item,
+                        const double* test_val, const int64_t* black_indptr, const int64_t* black_item,
+                        int32_t train_evaluation, int64_t n_items, double threshold, int64_t n_pos, double n_neg,
+                        int32_t n_neg_is_frac, int32_t generate_negative_pairs, int64_t seed,
+                        int64_t cand_capacity, int64_t* cand_off, int64_t* cand, int64_t* pos_off, int64_t* pos,
+                        uint8_t* skipped) {
+  if (n_users < 0 || !test_indptr || !cand_off || !pos_off || !skipped)
+    return drb_fail(DRB_E_INVALID, "drb_eval_candidates: bad argument");
+  const int64_t seed_i = seed;
+  drb_rng g;
+  std::vector<int64_t> p_items, n_pool, negs, picked, all;
+  int64_t co = 0, po = 0;
+  cand_off[0] = 0; pos_off[0] = 0;
+  for (int64_t u = 0; u < n_users; u++) {
+    int64_t s = seed_i + u;  // ranking_evaluation.py:111-116
+    g.seed((uint64_t)(s < 0 ? -s : s));
+    skipped[u] = 1;
+    cand_off[u + 1] = co; pos_off[u + 1] = po;
+    const int64_t lo = test_indptr[u], hi = test_indptr[u + 1];
+    p_items.clear(); n_pool.clear();
+    for (int64_t r = lo; r < hi; r++) (test_val[r] >= threshold ? p_items : n_pool).push_back(test_item[r]);
+    std::vector<int64_t> chosen;
+    if (n_pos < 0) {
+      chosen = p_items;
+    } else {
+      if ((int64_t)p_items.size() < n_pos) continue;  // :175-176
+      picked.resize(n_pos);
+      sample_indices(g, (int64_t)p_items.size(), n_pos, picked.data());
+      for (int64_t i : picked) chosen.push_back(p_items[i]);
+    }
+    negs.clear();
+    if (n_neg < 0) {
+      negs = n_pool;
+    } else {
+      int64_t want = n_neg_is_frac ? (int64_t)(n_neg * (double)chosen.size()) : (int64_t)n_neg;  // :187-188
+      int64_t take = std::min<int64_t>(want, (int64_t)n_pool.size());
+      picked.resize(take);
+      sample_indices(g, (int64_t)n_pool.size(), take, picked.data());
+      for (int64_t i : picked) negs.push_back(n_pool[i]);
+      if ((int64_t)negs.size() < want && generate_negative_pairs) {
+        // blacklist = train positives (unless evaluating on train) U test positives  (:193-201)
+        std::vector<int64_t> black(p_items);
+        if (!train_evaluation && black_indptr)
+          black.insert(black.end(), black_item + black_indptr[u], black_item + black_indptr[u + 1]);
+        std::sort(black.begin(), black.end());
+        black.erase(std::unique(black.begin(), black.end()), black.end());
+        if (n_items - (int64_t)black.size() < want) continue;  // :202-207
+        std::unordered_set<int64_t> in_negs(negs.begin(), negs.end());
+        while ((int64_t)negs.size() < want) {
+          int64_t it = g.randint(0, n_items - 1);  // :211 (raw/internal id confusion kept)
+          if (!std::binary_search(black.begin(), black.end(), it) && !in_negs.count(it)) {
+            negs.push_back(it);
+            in_negs.insert(it);
+          }
+        }
+      }
+    }
+    all = chosen;
+    all.insert(all.end(), negs.begin(), negs.end());
+    if (all.empty()) continue;  // :217-218
+    shuffle_i64(g, (int64_t)all.size(), all.data());
+    if (co + (int64_t)all.size() > cand_capacity)
+      return drb_fail(DRB_E_INVALID, "drb_eval_candidates: candidate buffer too small");
+    if (cand) std::copy(all.begin(), all.end(), cand + co);
+    if (pos) std::copy(chosen.begin(), chosen.end(), pos + po);
+    co += (int64_t)all.size(); po += (int64_t)chosen.size();
+    cand_off[u + 1] = co; pos_off[u + 1] = po;
+    skipped[u] = 0;
+  }
+  return DRB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,123 @@
+// Launcher prototypes of the sm_100a kernels behind libdrb.so (internal, not part of the ABI).
+// Kernel ids follow SURVEY.md section 2b: K1 gather, K2/K3 dense output layer + backward, K3 scatter,
+// K4 fused Adam+L2, K5 DMF head, K6 scoring / top-k.
+#ifndef DRB_KERNELS_H
+#define DRB_KERNELS_H
+
+#include "drb_internal.h"
+
+// ------------------------------------------------------------------ sparse.cu
+struct GatherArgs {
+  const int64_t* indptr; const int32_t* indices; const float* values;  // values may be NULL (all ones)
+  const int32_t* rows;                                                  // [n] CSR row of each output row
+  const int32_t* keep_off; const uint8_t* keep;                         // may be NULL (keep everything)
+  const float* table; int ld;                                           // gathered table [*, ld]
+  const float* rowbias;                                                 // may be NULL; [*, ld] indexed by rows[b]
+  const float* bias;                                                    // may be NULL; [ld]
+  const float* row_scale;                                               // may be NULL; per CSR row
+  float scale; int act; int width;                                      // columns >= width are forced to 0
+  float* out;                                                           // [n, ld]
+};
+int launch_gather(drb_ctx* ctx, const GatherArgs& a, int n);
+
+struct ScatterArgs {
+  const int64_t* indptr; const int32_t* indices; const float* values;
+  const int32_t* rows;
+  const int32_t* keep_off; const uint8_t* keep;
+  const float* row_scale; float scale;
+  const float* d; int ld;             // [n, ld] row gradients
+  float* gtable;                      // [*, ld] += w * d[b]   (vector atomics)
+  float* growbias;                    // may be NULL; [*, ld] += d[b] at rows[b]
+};
+int launch_scatter(drb_ctx* ctx, const ScatterArgs& a, int n);
+
+// per batch row: label histogram (batch_mean) or bitmap (per_user) and, in philox mode, the keep bytes
+struct BatchPrepArgs {
+  const int64_t* indptr; const int32_t* indices; const int32_t* rows; const int32_t* keep_off;
+  float* count;            // may be NULL; [items_pad] += 1 per stored positive
+  uint32_t* label_bits;    // may be NULL; [n, words_per_row]
+  int words_per_row;
+  uint8_t* keep_out;       // may be NULL; philox keep bytes
+  uint64_t seed, step; float q;
+};
+int launch_batch_prep(drb_ctx* ctx, const BatchPrepArgs& a, int n);
+
+// dz1 = (sum_s dh_part[s]) * h * (1 - h); column partial sums per 32-row block -> colpart[nblk, ld]
+int launch_dz1(drb_ctx* ctx, const float* dh_part, int splits, const float* h, float* dz1, int n, int ld,
+               float* colpart);
+// column partials of x[n, ld] per 32-row block (generic bias gradient)
+int launch_colpart(drb_ctx* ctx, const float* x, int n, int ld, float* colpart);
+// out[j] = sum_p part[p, ld + j]
+int launch_reduce_partials(drb_ctx* ctx, const float* part, int nparts, int ld, float* out, int n);
+
+// ------------------------------------------------------------------ gemm.cu
+enum { EPI_STORE = 0, EPI_BIAS_ACT = 1, EPI_MASK_POS = 2, EPI_CDAE_LOSS = 3 };
+enum { LAYOUT_KK = 0,   // A[m][k] k-contiguous, B[n][k] k-contiguous      (C = A * B^T)
+       LAYOUT_MN = 1,   // A[k][m] m-contiguous, B[k][n] n-contiguous      (C = A^T * B)
+       LAYOUT_KN = 2 }; // A[m][k] k-contiguous, B[k][n] n-contiguous      (C = A * B)
+struct GemmArgs {
+  const float* A; const float* B; float* C;
+  int M, N, Kred; int lda, ldb, ldc;
+  int splits;                         // split the reduction range; partial s is written at C + s * M * ldc
+  // epilogue
+  const float* bias;                  // [N]  (EPI_BIAS_ACT, EPI_CDAE_LOSS)
+  int act;                            // EPI_BIAS_ACT
+  const float* mask;                  // [M, ldc] (EPI_MASK_POS: C = acc * (mask > 0))
+  // EPI_CDAE_LOSS: C receives dL/dz2
+  const float* label_count;           // [N] batch histogram (batch_mean) or NULL
+  const uint32_t* label_bits; int words_per_row;   // per_user labels or NULL
+  int loss_kind; float inv_count; int batch;
+  float* loss_part;                   // [grid blocks]
+  float* col_part;                    // [m tiles, ldc] column partial sums of C
+};
+int launch_gemm(drb_ctx* ctx, int layout, int epi, const GemmArgs& a, int* n_mtiles_out = nullptr,
+                int* n_blocks_out = nullptr);
+
+// ------------------------------------------------------------------ optim.cu
+#define DRB_MAX_SEGS 40
+struct AdamSeg { int64_t off4, n4; float alpha, l2, regw; };
+struct AdamArgs {
+  float* w; float* m; float* v; const float* g;
+  AdamSeg seg[DRB_MAX_SEGS]; int nseg;
+  float beta1, beta2, eps;
+  float* reg_part;                    // [blocks] partial sums of regw * w^2 (pre-update weights)
+};
+int launch_adam(drb_ctx* ctx, const AdamArgs& a, int* n_blocks_out);
+// loss_out = sum(loss_part) * scale + sum(reg_part)
+int launch_finalize_loss(drb_ctx* ctx, const float* loss_part, int n_loss, float scale, const float* reg_part,
+                         int n_reg, float* loss_out);
+float drb_adam_alpha(float lr, float beta1, float beta2, int t);
+
+// ------------------------------------------------------------------ dmf.cu
+// cosine head: p = max(1e-6, <a/|a|, e/|e|>), BCE vs label, backward through the normalisation and the last relu.
+struct DmfHeadArgs {
+  const float* a; const float* e; int ld; int width;    // last tower activations [n, ld]
+  const float* labels;                                    // may be NULL (forward only)
+  float* p_out;                                           // may be NULL
+  float* da; float* de;                                   // may be NULL; d(pre-activation) of the last layers
+  float* loss_part;                                       // [n] per-pair loss terms
+  int n;
+};
+int launch_dmf_head(drb_ctx* ctx, const DmfHeadArgs& a);
+
+// ------------------------------------------------------------------ score.cu
+struct CandScoreArgs {
+  const float* urep; int ld_u;            // [n, ld] user representation (CDAE: h, DMF: user tower output)
+  const float* table; int ld_t;           // [n_items, ld] item representation (CDAE: W2T, DMF: item tower out)
+  const float* bias;                      // CDAE b2 or NULL
+  int width; int mode;                    // mode 0: sigmoid(dot + bias) (CDAE); 1: max(1e-6, cosine) (DMF)
+  const int32_t* uids;                    // [n]
+  const int32_t* cand; const int32_t* cand_count; int max_cand;
+  const int64_t* seen_indptr; const int32_t* seen_indices; int novelty;
+  int32_t* out_iid; float* out_score; int32_t* n_out;     // [n, max_cand], [n]
+};
+int launch_rank_candidates(drb_ctx* ctx, const CandScoreArgs& a, int n);
+
+struct TopkArgs {
+  const float* scores; int ld; int n_items;   // [n, ld]
+  const int32_t* uids; const int64_t* seen_indptr; const int32_t* seen_indices; int novelty;
+  int k; int32_t* out_iid; float* out_score; int32_t* n_out;
+};
+int launch_topk(drb_ctx* ctx, const TopkArgs& a, int n);
+
+#endif

@@ -1,0 +1,247 @@
+// K6 scoring (sm_100a): candidate dot products + in-CTA ordering, and full-catalog top-k selection.
+//
+// Replaces (reference, DRecPy/): Recommender/cdae.py:90-103 (_rank: full forward, filter to the candidate set
+// minus the user's training items when novelty, heapq.nlargest over (score, iid) tuples),
+// Recommender/recommender_abc.py:454-461 (DMF: one _predict per candidate, then nlargest) and :413-419
+// (_recommend = _rank over range(n_items)).
+// Total order reproduced exactly: (score, iid) compared lexicographically, largest first, duplicates of the
+// same candidate collapsed (the reference builds a set).  Scores are ordered through a monotone float->uint map
+// packed with the item id into one 64-bit key, so ties on the score are broken by the larger item id.
+#include "kernels.h"
+
+namespace {
+
+__device__ __forceinline__ uint32_t f2ord(float f) {
+  const uint32_t u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float ord2f(uint32_t o) {
+  return __uint_as_float((o & 0x80000000u) ? (o & 0x7fffffffu) : ~o);
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ bool row_contains(const int32_t* lo, int n, int32_t x) {
+  int a = 0, b = n;
+  while (a < b) {
+    const int mid = (a + b) >> 1;
+    if (lo[mid] < x) a = mid + 1; else b = mid;
+  }
+  return a < n && lo[a] == x;
+}
+
+// descending bitonic sort of P (power of two) 64-bit keys in shared memory
+__device__ void bitonic_desc(uint64_t* keys, int P) {
+  for (int k = 2; k <= P; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = threadIdx.x; i < P; i += blockDim.x) {
+        const int ixj = i ^ j;
+        if (ixj > i) {
+          const uint64_t a = keys[i], b = keys[ixj];
+          const bool desc = ((i & k) == 0);
+          if (desc ? (a < b) : (a > b)) { keys[i] = b; keys[ixj] = a; }
+        }
+      }
+      __syncthreads();
+    }
+  }
+}
+
+// write keys[0..P) (sorted descending; 0 = invalid) without duplicates; executed by warp 0
+__device__ void emit_sorted(const uint64_t* keys, int P, int limit, int32_t* out_iid, float* out_score,
+                            int32_t* n_out) {
+  if (threadIdx.x >= 32) return;
+  const int lane = threadIdx.x;
+  int running = 0;
+  for (int base = 0; base < P; base += 32) {
+    const int i = base + lane;
+    const uint64_t k = keys[i];
+    const bool flag = (k != 0) && (i == 0 || keys[i - 1] != k);
+    const uint32_t mask = __ballot_sync(0xffffffffu, flag);
+    const int pos = running + __popc(mask & ((1u << lane) - 1u));
+    if (flag && pos < limit) {
+      out_iid[pos] = (int32_t)(uint32_t)(k & 0xffffffffu);
+      out_score[pos] = ord2f((uint32_t)(k >> 32));
+    }
+    running += __popc(mask);
+  }
+  if (lane == 0) *n_out = min(running, limit);
+}
+
+__global__ void __launch_bounds__(128) k_rank_candidates(CandScoreArgs a, int P) {
+  extern __shared__ uint64_t keys[];  // [P]
+  const int u = blockIdx.x;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int uid = a.uids[u];
+  const int cnt = min(a.cand_count[u], a.max_cand);
+  const float* ur = a.urep + (int64_t)u * a.ld_u;
+  const int32_t* seen = nullptr;
+  int nseen = 0;
+  if (a.novelty) {
+    seen = a.seen_indices + a.seen_indptr[uid];
+    nseen = (int)(a.seen_indptr[uid + 1] - a.seen_indptr[uid]);
+  }
+  for (int i = threadIdx.x; i < P; i += blockDim.x) keys[i] = 0;
+  __syncthreads();
+  float uss = 0.f;
+  if (a.mode == 1) {
+    for (int k = lane; k < a.width; k += 32) uss = fmaf(ur[k], ur[k], uss);
+    uss = warp_sum(uss);
+  }
+  for (int c = warp; c < cnt; c += 4) {
+    const int iid = a.cand[(int64_t)u * a.max_cand + c];
+    if (a.novelty && row_contains(seen, nseen, iid)) continue;   // warp-uniform
+    const float* tr = a.table + (int64_t)iid * a.ld_t;
+    float dot = 0.f, tss = 0.f;
+    for (int k = lane; k < a.width; k += 32) {
+      const float t = tr[k];
+      dot = fmaf(ur[k], t, dot);
+      tss = fmaf(t, t, tss);
+    }
+    dot = warp_sum(dot);
+    float score;
+    if (a.mode == 0) {
+      score = 1.0f / (1.0f + expf(-(dot + (a.bias ? a.bias[iid] : 0.f))));
+    } else {
+      tss = warp_sum(tss);
+      const float c_ = dot * (1.0f / sqrtf(fmaxf(uss, 1e-12f))) * (1.0f / sqrtf(fmaxf(tss, 1e-12f)));
+      score = fmaxf(1e-6f, c_);
+    }
+    if (lane == 0) keys[c] = ((uint64_t)f2ord(score) << 32) | (uint32_t)iid;
+  }
+  __syncthreads();
+  bitonic_desc(keys, P);
+  emit_sorted(keys, P, a.max_cand, a.out_iid + (int64_t)u * a.max_cand, a.out_score + (int64_t)u * a.max_cand,
+              a.n_out + u);
+}
+
+// ---------------------------------------------------------------- full-catalog top-k (radix select + sort)
+constexpr int kTopkThreads = 256;
+
+struct SelectState { uint32_t prefix; int need; int bucket_count; };
+
+// one MSB-first 8-bit radix pass over `value(i)` for elements accepted by `live(i)`
+template <typename KeyFn>
+__device__ void radix_pass(int n, int shift, uint32_t prefix_mask, uint32_t prefix, KeyFn key, int* hist,
+                           SelectState* st) {
+  for (int i = threadIdx.x; i < 256; i += blockDim.x) hist[i] = 0;
+  __syncthreads();
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    uint32_t k;
+    if (key(i, &k) && (k & prefix_mask) == prefix) atomicAdd(&hist[(k >> shift) & 0xff], 1);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int need = st->need, d = 255;
+    for (; d > 0; d--) {
+      if (hist[d] >= need) break;
+      need -= hist[d];
+    }
+    st->need = need;                       // rank wanted inside bucket d
+    st->bucket_count = hist[d];
+    st->prefix = prefix | ((uint32_t)d << shift);
+  }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(kTopkThreads) k_topk(TopkArgs a, int P) {
+  extern __shared__ uint64_t keys[];  // [P] selected keys
+  __shared__ int hist[256];
+  __shared__ SelectState st;
+  __shared__ int n_sel;
+  const int u = blockIdx.x;
+  const int uid = a.uids[u];
+  // the score row is scratch: knock out the user's training items (cdae.py:93-98) in place
+  float* row = const_cast<float*>(a.scores) + (int64_t)u * a.ld;
+  if (a.novelty) {
+    const int64_t lo = a.seen_indptr[uid], hi = a.seen_indptr[uid + 1];
+    for (int64_t j = lo + threadIdx.x; j < hi; j += blockDim.x) row[a.seen_indices[j]] = -INFINITY;
+  }
+  for (int i = threadIdx.x; i < P; i += blockDim.x) keys[i] = 0;
+  __syncthreads();
+  const uint32_t dead = f2ord(-INFINITY);
+  // number of live items
+  if (threadIdx.x == 0) { st.need = 0; n_sel = 0; }
+  __syncthreads();
+  int live = 0;
+  for (int i = threadIdx.x; i < a.n_items; i += blockDim.x) live += (f2ord(row[i]) != dead);
+  atomicAdd(&st.need, live);
+  __syncthreads();
+  const int n_live = st.need;
+  const int k = min(a.k, n_live);
+  __syncthreads();
+  if (k == 0) {
+    if (threadIdx.x == 0) a.n_out[u] = 0;
+    return;
+  }
+  auto score_key = [&](int i, uint32_t* out) { *out = f2ord(row[i]); return *out != dead; };
+  uint32_t t32;
+  int need_eq, count_eq;
+  if (k == n_live) {           // everything live is selected
+    t32 = 0; need_eq = 0; count_eq = 0;
+  } else {
+    if (threadIdx.x == 0) { st.need = k; st.prefix = 0; }
+    __syncthreads();
+    uint32_t pm = 0;
+    for (int shift = 24; shift >= 0; shift -= 8) {
+      radix_pass(a.n_items, shift, pm, st.prefix, score_key, hist, &st);
+      pm |= 0xffu << shift;
+    }
+    t32 = st.prefix; need_eq = st.need; count_eq = st.bucket_count;
+  }
+  // ties on the threshold score: keep the need_eq largest item ids
+  uint32_t tiid = 0;
+  if (k != n_live && need_eq < count_eq) {
+    __syncthreads();
+    if (threadIdx.x == 0) { st.need = need_eq; st.prefix = 0; }
+    __syncthreads();
+    auto iid_key = [&](int i, uint32_t* out) { *out = (uint32_t)i; return f2ord(row[i]) == t32; };
+    uint32_t pm = 0;
+    for (int shift = 24; shift >= 0; shift -= 8) {
+      radix_pass(a.n_items, shift, pm, st.prefix, iid_key, hist, &st);
+      pm |= 0xffu << shift;
+    }
+    tiid = st.prefix;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < a.n_items; i += blockDim.x) {
+    const uint32_t o = f2ord(row[i]);
+    if (o == dead) continue;
+    const bool take = (k == n_live) || (o > t32) || (o == t32 && (uint32_t)i >= tiid);
+    if (take) {
+      const int pos = atomicAdd(&n_sel, 1);
+      if (pos < P) keys[pos] = ((uint64_t)o << 32) | (uint32_t)i;
+    }
+  }
+  __syncthreads();
+  bitonic_desc(keys, P);
+  emit_sorted(keys, P, a.k, a.out_iid + (int64_t)u * a.k, a.out_score + (int64_t)u * a.k, a.n_out + u);
+}
+
+int next_pow2(int x) {
+  int p = 32;
+  while (p < x) p <<= 1;
+  return p;
+}
+
+}  // namespace
+
+int launch_rank_candidates(drb_ctx* ctx, const CandScoreArgs& a, int n) {
+  if (n <= 0) return DRB_OK;
+  if (a.max_cand < 1 || a.max_cand > 4096) return drb_fail(DRB_E_INVALID, "rank_candidates: max_cand must be in [1, 4096]");
+  const int P = next_pow2(a.max_cand);
+  k_rank_candidates<<<n, 128, (size_t)P * sizeof(uint64_t), ctx->stream>>>(a, P);
+  DRB_LAUNCH_CHECK(ctx, "k_rank_candidates");
+  return DRB_OK;
+}
+
+int launch_topk(drb_ctx* ctx, const TopkArgs& a, int n) {
+  if (n <= 0) return DRB_OK;
+  if (a.k < 1 || a.k > 2048) return drb_fail(DRB_E_INVALID, "topk: k must be in [1, 2048]");
+  const int P = next_pow2(a.k);
+  k_topk<<<n, kTopkThreads, (size_t)P * sizeof(uint64_t), ctx->stream>>>(a, P);
+  DRB_LAUNCH_CHECK(ctx, "k_topk");
+  return DRB_OK;
+}

@@ -1,0 +1,298 @@
+// K1 / K3 / K5 sparse kernels (sm_100a): CSR row gather-sum fused with mask + row bias + bias + activation,
+// its transpose (vector-atomic scatter of row gradients), and the per-batch label / mask preparation.
+//
+// Replaces (reference, DRecPy/):
+//   Recommender/cdae.py:59-65,73-75   densify + corrupt + tf.matmul([x~], W) + V_u + b + sigmoid
+//   Recommender/dmf.py:75-86,89-90    densify + l2_normalize + first Dense(relu) of each tower
+// and the matching half of tape.gradient (recommender_abc.py:203).
+//
+// Work decomposition: one 128-thread CTA per sampled row.  A row of the table is ld floats (ld % 4 == 0); LPR
+// lanes cooperate on one table row with 128-bit loads, so a warp streams 32/LPR table rows at a time and each
+// lane keeps NV float4 accumulators.  Indices / weights are fetched 32 at a time per warp and broadcast with
+// shuffles.  Masked-out (corrupted) entries are never loaded.  The table (W: 21 MB at the ml-20m shape) is
+// L2-resident on B200, so this kernel is bound by L2->SM bandwidth and load issue, not HBM.
+#include "kernels.h"
+
+namespace {
+
+constexpr int kGatherThreads = 128;
+constexpr int kWarps = kGatherThreads / 32;
+
+__device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+
+__device__ __forceinline__ float apply_act(float x, int act) {
+  if (act == DRB_ACT_SIGMOID) return 1.0f / (1.0f + expf(-x));
+  if (act == DRB_ACT_RELU) return fmaxf(x, 0.0f);
+  return x;
+}
+
+template <int LPR, int NV>
+__global__ void __launch_bounds__(kGatherThreads) k_gather(GatherArgs a) {
+  constexpr int G = 32 / LPR;  // table rows streamed concurrently by one warp
+  extern __shared__ float4 red[];  // [kWarps * G][ld4]
+  const int b = blockIdx.x;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int sub = lane / LPR, c = lane % LPR;
+  const int ld4 = a.ld >> 2;
+  const int row = a.rows[b];
+  const int64_t lo = a.indptr[row], hi = a.indptr[row + 1];
+  const int deg = (int)(hi - lo);
+  const uint8_t* keep = a.keep ? a.keep + a.keep_off[b] : nullptr;
+
+  float4 acc[NV];
+#pragma unroll
+  for (int v = 0; v < NV; v++) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+
+  for (int base = warp * 32; base < deg; base += kWarps * 32) {
+    const int j = base + lane;
+    int my_idx = 0;
+    float my_w = 0.f;
+    if (j < deg) {
+      my_idx = a.indices[lo + j];
+      my_w = a.values ? a.values[lo + j] : 1.0f;
+      if (keep && keep[j] == 0) my_w = 0.f;
+    }
+    const int cnt = min(32, deg - base);
+#pragma unroll 4
+    for (int t = 0; t < cnt; t += G) {
+      const int src = t + sub;
+      const int idx = __shfl_sync(0xffffffffu, my_idx, src & 31);
+      const float w = __shfl_sync(0xffffffffu, my_w, src & 31);
+      if (src < cnt && w != 0.f) {
+        const float* rp = a.table + (int64_t)idx * a.ld;
+#pragma unroll
+        for (int v = 0; v < NV; v++) {
+          const int c4 = c + v * LPR;
+          if (c4 < ld4) {
+            const float4 x = ldg4(rp + c4 * 4);
+            acc[v].x = fmaf(w, x.x, acc[v].x);
+            acc[v].y = fmaf(w, x.y, acc[v].y);
+            acc[v].z = fmaf(w, x.z, acc[v].z);
+            acc[v].w = fmaf(w, x.w, acc[v].w);
+          }
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int v = 0; v < NV; v++) {
+    const int c4 = c + v * LPR;
+    if (c4 < ld4) red[(warp * G + sub) * ld4 + c4] = acc[v];
+  }
+  __syncthreads();
+  // finalize: fixed summation order over the kWarps*G partials -> deterministic
+  const float* redf = reinterpret_cast<const float*>(red);
+  float rs = a.scale;
+  if (a.row_scale) rs *= a.row_scale[row];
+  for (int col = threadIdx.x; col < a.ld; col += kGatherThreads) {
+    float s = 0.f;
+#pragma unroll
+    for (int p = 0; p < kWarps * G; p++) s += redf[p * a.ld + col];
+    float z = s * rs;
+    if (a.rowbias) z += a.rowbias[(int64_t)row * a.ld + col];
+    if (a.bias) z += a.bias[col];
+    a.out[(int64_t)b * a.ld + col] = (col < a.width) ? apply_act(z, a.act) : 0.f;
+  }
+}
+
+template <int LPR, int NV>
+__global__ void __launch_bounds__(kGatherThreads) k_scatter(ScatterArgs a) {
+  constexpr int G = 32 / LPR;
+  const int b = blockIdx.x;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int sub = lane / LPR, c = lane % LPR;
+  const int ld4 = a.ld >> 2;
+  const int row = a.rows[b];
+  const int64_t lo = a.indptr[row], hi = a.indptr[row + 1];
+  const int deg = (int)(hi - lo);
+  const uint8_t* keep = a.keep ? a.keep + a.keep_off[b] : nullptr;
+  float rs = a.scale;
+  if (a.row_scale) rs *= a.row_scale[row];
+
+  float4 d[NV];
+#pragma unroll
+  for (int v = 0; v < NV; v++) {
+    const int c4 = c + v * LPR;
+    d[v] = (c4 < ld4) ? ldg4(a.d + (int64_t)b * a.ld + c4 * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  if (a.growbias && warp == 0 && sub == 0) {
+#pragma unroll
+    for (int v = 0; v < NV; v++) {
+      const int c4 = c + v * LPR;
+      if (c4 < ld4) atomicAdd(reinterpret_cast<float4*>(a.growbias + (int64_t)row * a.ld) + c4, d[v]);
+    }
+  }
+  for (int base = warp * 32; base < deg; base += kWarps * 32) {
+    const int j = base + lane;
+    int my_idx = 0;
+    float my_w = 0.f;
+    if (j < deg) {
+      my_idx = a.indices[lo + j];
+      my_w = (a.values ? a.values[lo + j] : 1.0f) * rs;
+      if (keep && keep[j] == 0) my_w = 0.f;
+    }
+    const int cnt = min(32, deg - base);
+    for (int t = 0; t < cnt; t += G) {
+      const int src = t + sub;
+      const int idx = __shfl_sync(0xffffffffu, my_idx, src & 31);
+      const float w = __shfl_sync(0xffffffffu, my_w, src & 31);
+      if (src < cnt && w != 0.f) {
+        float4* gp = reinterpret_cast<float4*>(a.gtable + (int64_t)idx * a.ld);
+#pragma unroll
+        for (int v = 0; v < NV; v++) {
+          const int c4 = c + v * LPR;
+          if (c4 < ld4) atomicAdd(gp + c4, make_float4(w * d[v].x, w * d[v].y, w * d[v].z, w * d[v].w));
+        }
+      }
+    }
+  }
+}
+
+// philox4x32-10, counter = (item, slot, step_lo, step_hi), key = (seed_lo, seed_hi).  Restated in numpy by
+// oracle/philox.py; the mask is kept iff u >= q with u = (x0 >> 8) * 2^-24.
+__device__ __forceinline__ uint32_t philox_first(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
+                                                 uint32_t k1) {
+#pragma unroll
+  for (int r = 0; r < 10; r++) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    const uint32_t n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
+    c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  return c0;
+}
+
+__global__ void __launch_bounds__(128) k_batch_prep(BatchPrepArgs a) {
+  const int b = blockIdx.x;
+  const int row = a.rows[b];
+  const int64_t lo = a.indptr[row], hi = a.indptr[row + 1];
+  const int koff = a.keep_off ? a.keep_off[b] : 0;
+  for (int64_t j = lo + threadIdx.x; j < hi; j += blockDim.x) {
+    const int item = a.indices[j];
+    if (a.count) atomicAdd(a.count + item, 1.0f);
+    if (a.label_bits) atomicOr(a.label_bits + (int64_t)b * a.words_per_row + (item >> 5), 1u << (item & 31));
+    if (a.keep_out) {
+      const uint32_t x = philox_first((uint32_t)item, (uint32_t)b, (uint32_t)a.step, (uint32_t)(a.step >> 32),
+                                      (uint32_t)a.seed, (uint32_t)(a.seed >> 32));
+      const float u = (float)(x >> 8) * (1.0f / 16777216.0f);
+      a.keep_out[koff + (j - lo)] = (u < a.q) ? 0 : 1;
+    }
+  }
+}
+
+constexpr int kRowsPerBlock = 32;
+
+// dz1 = dh * h * (1-h) with dh = sum over split-K partials; column partial sums for db (cdae.py b gradient)
+__global__ void k_dz1(const float* __restrict__ dh_part, int splits, const float* __restrict__ h,
+                      float* __restrict__ dz1, int n, int ld, float* __restrict__ colpart) {
+  const int r0 = blockIdx.x * kRowsPerBlock;
+  const int r1 = min(n, r0 + kRowsPerBlock);
+  const int64_t plane = (int64_t)n * ld;
+  for (int col = threadIdx.x; col < ld; col += blockDim.x) {
+    float cs = 0.f;
+    for (int r = r0; r < r1; r++) {
+      const int64_t o = (int64_t)r * ld + col;
+      float dh = 0.f;
+      for (int s = 0; s < splits; s++) dh += dh_part[s * plane + o];
+      const float hv = h[o];
+      const float g = dh * hv * (1.0f - hv);
+      dz1[o] = g;
+      cs += g;
+    }
+    colpart[(int64_t)blockIdx.x * ld + col] = cs;
+  }
+}
+
+__global__ void k_colpart(const float* __restrict__ x, int n, int ld, float* __restrict__ colpart) {
+  const int r0 = blockIdx.x * kRowsPerBlock;
+  const int r1 = min(n, r0 + kRowsPerBlock);
+  for (int col = threadIdx.x; col < ld; col += blockDim.x) {
+    float cs = 0.f;
+    for (int r = r0; r < r1; r++) cs += x[(int64_t)r * ld + col];
+    colpart[(int64_t)blockIdx.x * ld + col] = cs;
+  }
+}
+
+__global__ void k_reduce_partials(const float* __restrict__ part, int nparts, int ld, float* __restrict__ out,
+                                  int n) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  float s = 0.f;
+  for (int p = 0; p < nparts; p++) s += part[(int64_t)p * ld + j];
+  out[j] = s;
+}
+
+template <template <int, int> class Launcher, typename Args>
+int dispatch_lpr(drb_ctx* ctx, const Args& a, int n, int ld, const char* name) {
+  const int ld4 = ld >> 2;
+  if (ld4 <= 4) return Launcher<4, 1>::run(ctx, a, n, name);
+  if (ld4 <= 8) return Launcher<8, 1>::run(ctx, a, n, name);
+  if (ld4 <= 16) return Launcher<16, 1>::run(ctx, a, n, name);
+  if (ld4 <= 32) return Launcher<32, 1>::run(ctx, a, n, name);
+  if (ld4 <= 64) return Launcher<32, 2>::run(ctx, a, n, name);
+  if (ld4 <= 96) return Launcher<32, 3>::run(ctx, a, n, name);
+  if (ld4 <= 128) return Launcher<32, 4>::run(ctx, a, n, name);
+  return drb_fail(DRB_E_INVALID, "%s: row width %d exceeds 512 floats", name, ld);
+}
+
+template <int LPR, int NV>
+struct GatherLauncher {
+  static int run(drb_ctx* ctx, const GatherArgs& a, int n, const char* name) {
+    const size_t smem = (size_t)kWarps * (32 / LPR) * a.ld * sizeof(float);
+    k_gather<LPR, NV><<<n, kGatherThreads, smem, ctx->stream>>>(a);
+    DRB_LAUNCH_CHECK(ctx, name);
+    return DRB_OK;
+  }
+};
+template <int LPR, int NV>
+struct ScatterLauncher {
+  static int run(drb_ctx* ctx, const ScatterArgs& a, int n, const char* name) {
+    k_scatter<LPR, NV><<<n, kGatherThreads, 0, ctx->stream>>>(a);
+    DRB_LAUNCH_CHECK(ctx, name);
+    return DRB_OK;
+  }
+};
+
+}  // namespace
+
+int launch_gather(drb_ctx* ctx, const GatherArgs& a, int n) {
+  if (n <= 0) return DRB_OK;
+  if (a.ld % 4) return drb_fail(DRB_E_INVALID, "gather: ld must be a multiple of 4");
+  return dispatch_lpr<GatherLauncher>(ctx, a, n, a.ld, "k_gather");
+}
+
+int launch_scatter(drb_ctx* ctx, const ScatterArgs& a, int n) {
+  if (n <= 0) return DRB_OK;
+  if (a.ld % 4) return drb_fail(DRB_E_INVALID, "scatter: ld must be a multiple of 4");
+  return dispatch_lpr<ScatterLauncher>(ctx, a, n, a.ld, "k_scatter");
+}
+
+int launch_batch_prep(drb_ctx* ctx, const BatchPrepArgs& a, int n) {
+  if (n <= 0) return DRB_OK;
+  k_batch_prep<<<n, 128, 0, ctx->stream>>>(a);
+  DRB_LAUNCH_CHECK(ctx, "k_batch_prep");
+  return DRB_OK;
+}
+
+int launch_dz1(drb_ctx* ctx, const float* dh_part, int splits, const float* h, float* dz1, int n, int ld,
+               float* colpart) {
+  const int nblk = (n + kRowsPerBlock - 1) / kRowsPerBlock;
+  k_dz1<<<nblk, min(512, (int)drb_round_up(ld, 32)), 0, ctx->stream>>>(dh_part, splits, h, dz1, n, ld, colpart);
+  DRB_LAUNCH_CHECK(ctx, "k_dz1");
+  return nblk;
+}
+
+int launch_colpart(drb_ctx* ctx, const float* x, int n, int ld, float* colpart) {
+  const int nblk = (n + kRowsPerBlock - 1) / kRowsPerBlock;
+  k_colpart<<<nblk, min(512, (int)drb_round_up(ld, 32)), 0, ctx->stream>>>(x, n, ld, colpart);
+  DRB_LAUNCH_CHECK(ctx, "k_colpart");
+  return nblk;
+}
+
+int launch_reduce_partials(drb_ctx* ctx, const float* part, int nparts, int ld, float* out, int n) {
+  if (n <= 0) return DRB_OK;
+  k_reduce_partials<<<(n + 255) / 256, 256, 0, ctx->stream>>>(part, nparts, ld, out, n);
+  DRB_LAUNCH_CHECK(ctx, "k_reduce_partials");
+  return DRB_OK;
+}

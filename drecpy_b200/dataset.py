@@ -1,0 +1,218 @@
+"""Host-side interaction table: the members of DRecPy's InteractionDataset that the hot path touches.
+
+Mirrors (reference, DRecPy/Dataset/):
+  mem_dataset.py:309-330   assign_internal_ids  (ids = order of first appearance)
+  mem_dataset.py:480-498   _build_interaction_matrix  (CSR, duplicates summed, column-sorted) -- here a one-pass
+                           sort instead of the reference's O(users * nnz) Python loop
+  mem_dataset.py:165-218   select_user_interaction_vec / select_item_interaction_vec
+  dataset_abc.py           user_to_uid / uid_to_user / item_to_iid / iid_to_item / count_unique / min / max
+Storage, querying and file IO of the reference dataset classes are out of scope; a
+reference InteractionDataset object can be passed to fit() directly and is converted with `from_dataset`.
+"""
+import numpy as np
+import pandas as pd
+
+
+def _build_csr(rows, cols, vals, n_rows, n_cols):
+    rows = np.asarray(rows, np.int64)
+    cols = np.asarray(cols, np.int64)
+    vals = np.asarray(vals, np.float64)
+    if len(rows) == 0:
+        return np.zeros(n_rows + 1, np.int64), np.zeros(0, np.int32), np.zeros(0, np.float64)
+    key = rows * n_cols + cols
+    order = np.argsort(key, kind='stable')
+    key_s = key[order]
+    starts = np.flatnonzero(np.concatenate(([True], key_s[1:] != key_s[:-1])))
+    data = np.add.reduceat(vals[order], starts)          # duplicates summed (scipy csr_matrix semantics)
+    ukey = key_s[starts]
+    r = ukey // n_cols
+    indptr = np.zeros(n_rows + 1, np.int64)
+    np.cumsum(np.bincount(r, minlength=n_rows), out=indptr[1:])
+    return indptr, (ukey % n_cols).astype(np.int32), data
+
+
+class InteractionData:
+    def __init__(self, users, items, interactions):
+        self.user = np.asarray(users)
+        self.item = np.asarray(items)
+        self.interaction = np.asarray(interactions)
+        assert len(self.user) == len(self.item) == len(self.interaction)
+        self.has_internal_ids = False
+        self.uid = self.iid = None
+        self._users = self._items = None
+        self._user_map = self._item_map = None
+        self._cache = {}
+
+    # ------------------------------------------------------------------ construction
+    @classmethod
+    def read_df(cls, df, user_label='user', item_label='item', interaction_label='interaction', **kwds):
+        return cls(df[user_label].values, df[item_label].values, df[interaction_label].values)
+
+    @classmethod
+    def from_dataset(cls, ds):
+        """Accepts an InteractionData or any object shaped like the reference's InteractionDataset."""
+        if isinstance(ds, cls):
+            return ds
+        df = getattr(ds, '_df', None)
+        if df is not None and all(c in df.columns for c in ('user', 'item', 'interaction')):
+            return cls(df['user'].values, df['item'].values, df['interaction'].values)
+        if hasattr(ds, 'values_list'):
+            rows = ds.values_list(['user', 'item', 'interaction'], to_list=True)
+            u, i, v = zip(*rows) if rows else ((), (), ())
+            return cls(np.array(u), np.array(i), np.array(v))
+        raise TypeError(f'cannot read interactions from {type(ds)}')
+
+    def __len__(self):
+        return len(self.user)
+
+    # ------------------------------------------------------------------ id abstraction (mem_dataset.py:309-330)
+    def assign_internal_ids(self):
+        if self.has_internal_ids:
+            return
+        ucodes, users = pd.factorize(self.user)          # codes in order of first appearance
+        icodes, items = pd.factorize(self.item)
+        self.uid = ucodes.astype(np.int32)
+        self.iid = icodes.astype(np.int32)
+        self._users = np.asarray(users)
+        self._items = np.asarray(items)
+        self._user_map = {k: i for i, k in enumerate(self._users.tolist())}
+        self._item_map = {k: i for i, k in enumerate(self._items.tolist())}
+        self.has_internal_ids = True
+        self._cache.clear()
+
+    def user_to_uid(self, user):
+        return self._user_map.get(user.item() if isinstance(user, np.generic) else user)
+
+    def item_to_iid(self, item):
+        return self._item_map.get(item.item() if isinstance(item, np.generic) else item)
+
+    def uid_to_user(self, uid):
+        return self._users[uid].item() if 0 <= uid < len(self._users) else None
+
+    def iid_to_item(self, iid):
+        return self._items[iid].item() if 0 <= iid < len(self._items) else None
+
+    def items_to_iids(self, items):
+        """Vectorised raw -> internal item ids; unknown ids map to -1."""
+        items = np.asarray(items)
+        if 'sorted_items' not in self._cache:
+            order = np.argsort(self._items, kind='stable')
+            self._cache['sorted_items'] = (self._items[order], order.astype(np.int64))
+        s, order = self._cache['sorted_items']
+        pos = np.searchsorted(s, items)
+        pos = np.clip(pos, 0, len(s) - 1)
+        return np.where(s[pos] == items, order[pos], -1)
+
+    @property
+    def raw_items(self):
+        return self._items
+
+    @property
+    def raw_users(self):
+        return self._users
+
+    def count_unique(self, column):
+        if column in ('uid', 'user'):
+            return len(self._users) if self.has_internal_ids else len(np.unique(self.user))
+        if column in ('iid', 'item'):
+            return len(self._items) if self.has_internal_ids else len(np.unique(self.item))
+        raise ValueError(column)
+
+    def min(self, column='interaction'):
+        return getattr(self, column).min()
+
+    def max(self, column='interaction'):
+        return getattr(self, column).max()
+
+    # ------------------------------------------------------------------ sparse views
+    def csr(self, threshold=None):
+        """(indptr int64, indices int32, data float64) over users x items; duplicates summed first, then entries
+        with summed value < threshold dropped (cdae.py:61 binarises the summed row)."""
+        key = ('csr', threshold)
+        if key not in self._cache:
+            assert self.has_internal_ids
+            U, I = self.count_unique('uid'), self.count_unique('iid')
+            indptr, indices, data = _build_csr(self.uid, self.iid, self.interaction, U, I)
+            if threshold is not None:
+                keep = data >= threshold
+                rows = np.repeat(np.arange(U), np.diff(indptr))[keep]
+                indices, data = indices[keep], data[keep]
+                indptr = np.zeros(U + 1, np.int64)
+                np.cumsum(np.bincount(rows, minlength=U), out=indptr[1:])
+            self._cache[key] = (indptr, indices, data)
+        return self._cache[key]
+
+    def csc(self):
+        if 'csc' not in self._cache:
+            assert self.has_internal_ids
+            U, I = self.count_unique('uid'), self.count_unique('iid')
+            self._cache['csc'] = _build_csr(self.iid, self.uid, self.interaction, I, U)
+        return self._cache['csc']
+
+    def rows_by_user(self, threshold=None):
+        """Per-user rows in DataFrame (insertion) order, filtered by interaction >= threshold
+        (select_random_generator's view, mem_dataset.py:119-129)."""
+        key = ('rows', threshold)
+        if key not in self._cache:
+            assert self.has_internal_ids
+            U = self.count_unique('uid')
+            sel = np.arange(len(self)) if threshold is None else np.flatnonzero(self.interaction >= threshold)
+            order = sel[np.argsort(self.uid[sel], kind='stable')]
+            indptr = np.zeros(U + 1, np.int64)
+            np.cumsum(np.bincount(self.uid[sel], minlength=U), out=indptr[1:])
+            self._cache[key] = (indptr, np.ascontiguousarray(self.iid[order]),
+                                np.ascontiguousarray(self.interaction[order].astype(np.float64)))
+        return self._cache[key]
+
+    def select_user_interaction_vec(self, uid):
+        from scipy.sparse import csr_matrix
+        indptr, indices, data = self.csr()
+        lo, hi = indptr[uid], indptr[uid + 1]
+        return csr_matrix((data[lo:hi], indices[lo:hi], [0, hi - lo]), shape=(1, self.count_unique('iid')))
+
+    def select_item_interaction_vec(self, iid):
+        from scipy.sparse import csr_matrix
+        indptr, indices, data = self.csc()
+        lo, hi = indptr[iid], indptr[iid + 1]
+        return csr_matrix((data[lo:hi], indices[lo:hi], [0, hi - lo]), shape=(1, self.count_unique('uid')))
+
+    def user_items(self, uid):
+        indptr, indices, _ = self.csr()
+        return indices[indptr[uid]:indptr[uid + 1]]
+
+
+def synthetic_interactions(n_users, n_items, nnz, seed=10, zipf_a=0.0, rating_low=1, rating_high=5):
+    """Synthetic MovieLens-shaped data: unique (user, item) pairs, every user and item
+    present, raw ids = internal id + 1, integer ratings uniform in [rating_low, rating_high], rows in random
+    order.  zipf_a > 0 draws items from a Zipf-like popularity law (p_i ~ 1/(i+1)^a) and user activity
+    log-normally, for the large configs."""
+    rng = np.random.default_rng(seed)
+    if zipf_a <= 0:
+        total = n_users * n_items
+        if total < 2 ** 62 and nnz <= total:
+            pairs = rng.choice(total, nnz, replace=False) if total <= 50_000_000 else \
+                np.unique(rng.integers(0, total, int(nnz * 1.05)))[:nnz]
+            rng.shuffle(pairs)
+        u, i = pairs // n_items, pairs % n_items
+    else:
+        act = rng.lognormal(0.0, 1.0, n_users)
+        deg = np.maximum(1, np.round(act / act.sum() * nnz)).astype(np.int64)
+        pop = 1.0 / np.power(np.arange(1, n_items + 1, dtype=np.float64), zipf_a)
+        cdf = np.cumsum(pop / pop.sum())
+        u = np.repeat(np.arange(n_users, dtype=np.int64), deg)
+        i = np.searchsorted(cdf, rng.random(len(u))).clip(0, n_items - 1)
+        key = np.unique(u * n_items + i)
+        rng.shuffle(key)
+        u, i = key // n_items, key % n_items
+    # make sure every user / item id occurs so that the nominal shape is the actual shape
+    miss_u = np.setdiff1d(np.arange(n_users), u)
+    miss_i = np.setdiff1d(np.arange(n_items), i)
+    if len(miss_u):
+        u = np.concatenate([u, miss_u]); i = np.concatenate([i, rng.integers(0, n_items, len(miss_u))])
+    if len(miss_i):
+        i = np.concatenate([i, miss_i]); u = np.concatenate([u, rng.integers(0, n_users, len(miss_i))])
+    key = np.unique(u.astype(np.int64) * n_items + i)
+    rng.shuffle(key)
+    u, i = key // n_items, key % n_items
+    val = rng.integers(rating_low, rating_high + 1, len(u))
+    return (u + 1).astype(np.int64), (i + 1).astype(np.int64), val.astype(np.int64)

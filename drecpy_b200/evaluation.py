@@ -1,0 +1,270 @@
+"""ranking_evaluation with batched native scoring, and the ranking metrics on the path.
+
+Mirrors DRecPy/Evaluation/Processes/ranking_evaluation.py:19-246 (same signature, asserts, per-user
+random.Random(seed + idx) candidate generation, shuffle, model.rank, relevancies, round(sum / count, 4)) and
+DRecPy/Evaluation/Metrics/ranking.py (DCG :20-56, NDCG :59-91, HitRatio :94-114, Recall, Precision).
+What changes: the per-user candidate generation runs in libdrb's host C++ (drb_eval_candidates) and all users
+are scored in one batched GPU call (model.rank_batch) instead of 4 Python threads calling model.rank per user.
+Models without rank_batch (any object with .rank) and non-integer raw ids go through the same protocol in Python.
+"""
+import math
+import random
+
+import numpy as np
+import pandas as pd
+
+from . import _lib
+from .dataset import InteractionData
+
+
+# ------------------------------------------------------------------------------------------ metrics
+class RankingMetricABC:
+    @property
+    def name(self):
+        return self.__class__.__name__
+
+
+class DCG(RankingMetricABC):
+    def __init__(self, strong_relevancy=True):
+        self.strong_relevancy = strong_relevancy
+
+    def __call__(self, recommendations, k=None, relevancies=None):
+        if relevancies is None: return 0
+        if k is not None: recommendations = recommendations[:k]
+        curr_dcg = 0
+        for i, r in enumerate(recommendations):
+            rel = float(relevancies[r])
+            if self.strong_relevancy:
+                curr_dcg += (2 ** rel - 1) / math.log2(2 + i)
+            else:
+                curr_dcg += rel / math.log2(2 + i)
+        return curr_dcg
+
+
+class NDCG(RankingMetricABC):
+    def __init__(self, strong_relevancy=True):
+        self.strong_relevancy = strong_relevancy
+        self.dcg = DCG(strong_relevancy=strong_relevancy)
+
+    def __call__(self, recommendations, k=None, relevancies=None):
+        if relevancies is None: return 0
+        curr_dcg = self.dcg(recommendations, relevancies=relevancies, k=k)
+        best_recommendations = sorted(relevancies.keys(), key=lambda x: -relevancies[x])
+        best_dcg = self.dcg(best_recommendations, relevancies=relevancies, k=k)
+        return curr_dcg / best_dcg
+
+
+class HitRatio(RankingMetricABC):
+    def __call__(self, recommendations, k=None, relevant_recommendations=None):
+        if relevant_recommendations is None: return 0
+        if k is not None: recommendations = recommendations[:k]
+        recommendations = set([str(item) for item in recommendations])
+        relevant_recommendations = set([str(item) for item in relevant_recommendations])
+        return len(recommendations.intersection(relevant_recommendations)) / len(relevant_recommendations)
+
+
+class Recall(RankingMetricABC):
+    def __call__(self, recommendations, k=None, relevant_recommendations=None):
+        if relevant_recommendations is None: return 0
+        if k is not None: recommendations = recommendations[:k]
+        in_common = set(recommendations).intersection(set(relevant_recommendations))
+        return len(in_common) / len(relevant_recommendations)
+
+
+class Precision(RankingMetricABC):
+    def __call__(self, recommendations, k=None, relevant_recommendations=None):
+        if relevant_recommendations is None: return 0
+        if k is not None: recommendations = recommendations[:k]
+        in_common = set(recommendations).intersection(set(relevant_recommendations))
+        return len(in_common) / len(recommendations)
+
+
+# ------------------------------------------------------------------------------------------ candidate generation
+def _group_by_user(data):
+    """unique users in first-appearance order + test rows grouped by user with row order preserved."""
+    codes, users = pd.factorize(data.user)
+    order = np.argsort(codes, kind='stable')
+    indptr = np.zeros(len(users) + 1, np.int64)
+    np.cumsum(np.bincount(codes, minlength=len(users)), out=indptr[1:])
+    return np.asarray(users), indptr, order
+
+
+def _train_positive_items(model, users, thr):
+    """per evaluated user: raw item ids of its training rows with interaction >= thr
+    (ranking_evaluation.py:196-199), as CSR-like (indptr, sorted items)."""
+    data = model._data if hasattr(model, '_data') else InteractionData.from_dataset(model.interaction_dataset)
+    data.assign_internal_ids()
+    p_indptr, p_iid, _ = data.rows_by_user(thr)
+    uids = np.array([(-1 if (u := data.user_to_uid(x)) is None else u) for x in users.tolist()], np.int64)
+    lens = np.where(uids >= 0, p_indptr[np.maximum(uids, 0) + 1] - p_indptr[np.maximum(uids, 0)], 0)
+    indptr = np.zeros(len(users) + 1, np.int64)
+    np.cumsum(lens, out=indptr[1:])
+    items = np.empty(indptr[-1], np.int64)
+    raw = data.raw_items
+    for r in np.flatnonzero(lens):
+        u = uids[r]
+        items[indptr[r]:indptr[r + 1]] = np.sort(raw[p_iid[p_indptr[u]:p_indptr[u + 1]]])
+    return indptr, items
+
+
+def generate_candidates(model, data, users, t_indptr, t_order, thr, n_pos, n_neg, generate_negative_pairs,
+                        train_evaluation, seed):
+    """ranking_evaluation.py:163-219 for every user at once (native).  Returns cand_off, cand, pos_off, pos,
+    skipped."""
+    n_users = len(users)
+    t_item = np.ascontiguousarray(data.item[t_order].astype(np.int64))
+    t_val = np.ascontiguousarray(data.interaction[t_order].astype(np.float64))
+    if train_evaluation or not generate_negative_pairs:
+        b_indptr, b_item = np.zeros(n_users + 1, np.int64), np.zeros(1, np.int64)
+    else:
+        b_indptr, b_item = _train_positive_items(model, users, thr)
+        if len(b_item) == 0: b_item = np.zeros(1, np.int64)
+    is_frac = isinstance(n_neg, float)
+    per_user_neg = 0 if n_neg is None else (int(np.ceil(n_neg * np.diff(t_indptr).max())) if is_frac else int(n_neg))
+    cap = int(len(t_item) + n_users * per_user_neg + 16)
+    cand_off = np.zeros(n_users + 1, np.int64)
+    pos_off = np.zeros(n_users + 1, np.int64)
+    cand = np.empty(cap, np.int64)
+    pos = np.empty(cap, np.int64)
+    skipped = np.zeros(n_users, np.uint8)
+    _lib.check(_lib.load().drb_eval_candidates(
+        n_users, _lib.np_ptr(t_indptr), _lib.np_ptr(t_item), _lib.np_ptr(t_val), _lib.np_ptr(b_indptr),
+        _lib.np_ptr(b_item), int(bool(train_evaluation)), int(model.n_items), float(thr),
+        -1 if n_pos is None else int(n_pos), -1.0 if n_neg is None else float(n_neg), int(is_frac),
+        int(bool(generate_negative_pairs)), int(seed), cap, _lib.np_ptr(cand_off), _lib.np_ptr(cand),
+        _lib.np_ptr(pos_off), _lib.np_ptr(pos), _lib.np_ptr(skipped)))
+    return cand_off, cand[:cand_off[-1]], pos_off, pos[:pos_off[-1]], skipped, t_item, t_val
+
+
+def _candidates_python(rng, test_rows, train_pos_items, test_pos_items, n_items, thr, n_pos, n_neg, generate,
+                       train_evaluation):
+    """The same protocol in Python (non-integer raw ids)."""
+    pos = [(it, v) for it, v in test_rows if v >= thr]
+    if n_pos is None:
+        chosen = pos
+    else:
+        if len(pos) < n_pos: return None
+        chosen = rng.sample(pos, n_pos)
+    positives = [it for it, _ in chosen]
+    neg_pool = [it for it, v in test_rows if v < thr]
+    if n_neg is None:
+        negatives = list(neg_pool)
+    else:
+        if isinstance(n_neg, float): n_neg = int(n_neg * len(positives))
+        negatives = rng.sample(neg_pool, min(n_neg, len(neg_pool)))
+        if len(negatives) < n_neg and generate:
+            blacklist = set(test_pos_items) if train_evaluation else set(train_pos_items) | set(test_pos_items)
+            if n_items - len(blacklist) < n_neg: return None
+            while len(negatives) < n_neg:
+                new_item = rng.randint(0, n_items - 1)
+                if new_item not in blacklist and new_item not in negatives:
+                    negatives.append(new_item)
+    all_items = positives + negatives
+    if len(all_items) == 0: return None
+    rng.shuffle(all_items)
+    return all_items, positives
+
+
+# ------------------------------------------------------------------------------------------ the protocol
+def ranking_evaluation(model, ds_test=None, n_test_users=None, k=10, n_pos_interactions=None, n_neg_interactions=None,
+                       generate_negative_pairs=False, novelty=False, seed=0, max_concurrent_threads=4, **kwds):
+    assert n_test_users is None or n_test_users > 0, f'The number of test users ({n_test_users}) should be > 0.'
+    assert n_pos_interactions is None or n_pos_interactions > 0, \
+        f'The number of positive interactions ({n_pos_interactions}) should be None or an integer > 0.'
+    assert n_neg_interactions is None or n_neg_interactions > 0, \
+        f'The number of negative interactions ({n_neg_interactions}) should be None or an integer > 0.'
+    if generate_negative_pairs and n_neg_interactions is None:
+        raise Exception('Cannot generate negative interaction pairs when the number of negative interactions per user '
+                        'is not defined. Either set generate_negative_pairs=False or define the n_neg_interactions '
+                        'parameter.')
+    interaction_threshold = kwds.get('interaction_threshold', model.interaction_threshold)
+    if type(k) is not list: k = [k]
+    for k_ in k: assert k_ > 0, f'k ({k_}) should be > 0.'
+
+    train_evaluation = False
+    if ds_test is None or ds_test is model.interaction_dataset or ds_test is getattr(model, '_data', None):
+        train_evaluation = True
+        ds_test = model.interaction_dataset
+    metrics = kwds.get('metrics', [Precision(), Recall(), HitRatio(), NDCG()])
+    assert isinstance(metrics, list), f'Expected "metrics" argument to be a list and found {type(metrics)}. ' \
+        f'Should contain instances of RankingMetricABC.'
+    for m in metrics:
+        assert hasattr(m, 'name') and callable(m), f'Expected metric {m} to be an instance of type RankingMetricABC.'
+
+    data = InteractionData.from_dataset(ds_test)
+    users, t_indptr, t_order = _group_by_user(data)
+    n_eval = len(users) if n_test_users is None else min(n_test_users, len(users))
+    users, t_indptr = users[:n_eval], np.ascontiguousarray(t_indptr[:n_eval + 1])
+    metric_sums = {(m.name, k_): [0, 0] for m in metrics for k_ in k}
+    record = kwds.get('record', None)      # optional list collecting (user, candidates, ranked) for tests
+
+    native_ids = np.issubdtype(data.item.dtype, np.integer)
+    if native_ids:
+        cand_off, cand, pos_off, pos, skipped, t_item, t_val = generate_candidates(
+            model, data, users, t_indptr, t_order, interaction_threshold, n_pos_interactions, n_neg_interactions,
+            generate_negative_pairs, train_evaluation, seed)
+        active = np.flatnonzero(skipped == 0)
+        cand_lists = [cand[cand_off[u]:cand_off[u + 1]] for u in active]
+        pos_lists = [pos[pos_off[u]:pos_off[u + 1]].tolist() for u in active]
+        rows = [(t_item[t_indptr[u]:t_indptr[u + 1]], t_val[t_indptr[u]:t_indptr[u + 1]]) for u in active]
+    else:
+        active, cand_lists, pos_lists, rows = [], [], [], []
+        tr = InteractionData.from_dataset(model.interaction_dataset)
+        for idx in range(n_eval):
+            sl = t_order[t_indptr[idx]:t_indptr[idx + 1]]
+            trows = list(zip(data.item[sl].tolist(), data.interaction[sl].tolist()))
+            tpos = [it for it, v in trows if v >= interaction_threshold]
+            sel = (tr.user == users[idx]) & (tr.interaction >= interaction_threshold)
+            res = _candidates_python(random.Random(seed + idx), trows, tr.item[sel].tolist(), tpos, model.n_items,
+                                     interaction_threshold, n_pos_interactions, n_neg_interactions,
+                                     generate_negative_pairs, train_evaluation)
+            if res is None: continue
+            active.append(idx)
+            cand_lists.append(np.asarray(res[0], dtype=object))
+            pos_lists.append(res[1])
+            rows.append((data.item[sl], data.interaction[sl]))
+
+    # ---- rank: one batched call when the model supports it (model.rank semantics, ranking_evaluation.py:222)
+    if len(active) == 0:
+        ranked_lists = []
+    elif hasattr(model, 'rank_batch') and native_ids:
+        ranked_lists = []
+        chunk = kwds.get('rank_chunk', 16384)
+        for o in range(0, len(active), chunk):
+            sub_users = users[active[o:o + chunk]].tolist()
+            rl, _, _ = model.rank_batch(sub_users, cand_lists[o:o + chunk], novelty=novelty)
+            ranked_lists.extend(rl)
+    else:
+        ranked_lists = [[item for _, item in model.rank(users[u].item() if hasattr(users[u], 'item') else users[u],
+                                                         list(c.tolist()), novelty=novelty, skip_invalid_items=True)]
+                        for u, c in zip(active, cand_lists)]
+
+    # ---- metrics (ranking_evaluation.py:223-246); exceptions inside a metric skip that (metric, k) for the user
+    for u, all_items, positives, (r_items, r_vals), recommendations in zip(active, cand_lists, pos_lists, rows,
+                                                                          ranked_lists):
+        all_items = all_items.tolist()
+        first_val = {}
+        for it, v in zip(r_items.tolist(), r_vals.tolist()):
+            first_val.setdefault(it, v)
+        relevancies = {item: (first_val.get(item) or 0) for item in all_items}
+        best_item = None if len(positives) == 0 else min(positives, key=lambda it: relevancies[it])
+        if record is not None:
+            record.append((users[u].item() if hasattr(users[u], 'item') else users[u], all_items, list(recommendations)))
+        for m in metrics:
+            param_names = m.__call__.__code__.co_varnames
+            for k_ in k:
+                params = dict()
+                for param_name in param_names:
+                    if param_name == 'recommendations': params[param_name] = recommendations
+                    elif param_name == 'relevant_recommendations': params[param_name] = positives
+                    elif param_name == 'relevant_recommendation': params[param_name] = best_item
+                    elif param_name == 'relevancies': params[param_name] = relevancies
+                    elif param_name == 'k': params[param_name] = k_
+                try:
+                    metric_sums[(m.name, k_)][0] += m(**params)
+                    metric_sums[(m.name, k_)][1] += 1
+                except Exception:
+                    pass
+
+    return {m + f'@{k_}': round(metric_sums[(m, k_)][0] / metric_sums[(m, k_)][1], 4)
+            if metric_sums[(m, k_)][1] > 0 else 0 for m, k_ in metric_sums}

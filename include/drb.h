@@ -1,0 +1,255 @@
+/*
+ * drb.h -- C ABI of libdrb.so: the B200-native hot path behind DRecPy's CDAE / DMF recommenders.
+ *
+ * Every entry point replaces a piece of the reference's Python/TensorFlow hot path (cited per function as
+ * "replaces <file>:<lines>", paths relative to the DRecPy source tree).  The reference has no FFI of its own
+ * (it is pure Python); the binding a maintainer adds is the ctypes stub shown in INTEGRATION.md, which is what
+ * drecpy_b200/_lib.py implements.
+ *
+ * Conventions
+ *   - plain C, no C++ types, no exceptions across the boundary;
+ *   - every function returns int: 0 = OK, <0 = error (DRB_E_*); the message is in drb_last_error()
+ *     (thread-local);
+ *   - device buffers are OWNED BY THE CALLER (PyTorch tensors on the Python side).  The library borrows raw
+ *     device pointers until the owning object is destroyed; it never allocates or frees device memory;
+ *   - there is NO CPU fallback: device entry points fail with DRB_E_NODEVICE without an sm_100 GPU;
+ *   - a context is not re-entrant; serialise calls per context.  All device work is enqueued on the context's
+ *     stream (drb_ctx_set_stream) and is asynchronous unless documented otherwise.
+ */
+#ifndef DRB_H
+#define DRB_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DRB_VERSION 100 /* 0.1.0 */
+
+enum {
+  DRB_OK = 0,
+  DRB_E_INVALID = -1,   /* bad argument (range, alignment, NULL) */
+  DRB_E_NODEVICE = -2,  /* no CUDA device / not sm_100 */
+  DRB_E_CUDA = -3,      /* CUDA runtime error (sticky per context) */
+  DRB_E_STATE = -4,     /* object used in the wrong state */
+  DRB_E_NOMEM = -5
+};
+
+enum { DRB_LOSS_BCE = 0, DRB_LOSS_MSE = 1 };
+enum { DRB_LABEL_BATCH_MEAN = 0, DRB_LABEL_PER_USER = 1 };
+enum { DRB_ACT_NONE = 0, DRB_ACT_SIGMOID = 1, DRB_ACT_RELU = 2 };
+
+typedef struct drb_ctx drb_ctx;
+typedef struct drb_rng drb_rng;
+typedef struct drb_sampler drb_sampler;
+typedef struct drb_cdae drb_cdae;
+typedef struct drb_dmf drb_dmf;
+
+/* ------------------------------------------------------------------ diagnostics */
+int drb_version(void);
+const char* drb_last_error(void);
+
+/* ------------------------------------------------------------------ context */
+/* Creates a context on CUDA device `device`; fails with DRB_E_NODEVICE if it is not compute capability 10.x. */
+int drb_ctx_create(int device, drb_ctx** out);
+int drb_ctx_destroy(drb_ctx* ctx);
+/* `stream` is a cudaStream_t (e.g. torch.cuda.current_stream().cuda_stream); NULL = legacy default stream. */
+int drb_ctx_set_stream(drb_ctx* ctx, void* stream);
+int drb_ctx_synchronize(drb_ctx* ctx);
+/* number of kernel launches this context has enqueued so far (bench.py's gpu_launches claim) */
+int64_t drb_ctx_launch_count(const drb_ctx* ctx);
+
+/* ------------------------------------------------------------------ host RNG: CPython random.Random replay
+ * replaces: the three `random.Random(seed)` streams of DRecPy/Sampler/point_sampler.py:30,
+ * DRecPy/Dataset/mem_dataset.py:113-114,135-136, the corruption stream DRecPy/Recommender/recommender_abc.py:74
+ * and the per-user streams of DRecPy/Evaluation/Processes/ranking_evaluation.py:116.
+ * MT19937 with CPython's init_by_array seeding of abs(seed); bit-exact with CPython >= 3.2. */
+int drb_rng_create(uint64_t abs_seed, drb_rng** out);
+int drb_rng_destroy(drb_rng* rng);
+int drb_rng_seed(drb_rng* rng, uint64_t abs_seed);
+double drb_rng_random(drb_rng* rng);                    /* random.random() */
+uint64_t drb_rng_getrandbits(drb_rng* rng, int k);      /* random.getrandbits(k), 1 <= k <= 64 */
+int64_t drb_rng_randbelow(drb_rng* rng, int64_t n);     /* random._randbelow(n), n >= 1 */
+int drb_rng_random_fill(drb_rng* rng, int64_t n, double* out);
+/* random.sample(range(n), k) (returns indices) and random.shuffle on an index vector (CPython 3.12 algorithms) */
+int drb_rng_sample_indices(drb_rng* rng, int64_t n, int64_t k, int64_t* out);
+int drb_rng_shuffle_i64(drb_rng* rng, int64_t n, int64_t* x);
+/* state[0..623] = mt, state[624] = index (same layout as random.getstate()[1]) */
+int drb_rng_getstate(const drb_rng* rng, uint32_t state[625]);
+int drb_rng_setstate(drb_rng* rng, const uint32_t state[625]);
+
+/* ------------------------------------------------------------------ PointSampler
+ * replaces: DRecPy/Sampler/point_sampler.py:44-96 and the two generators it pulls from,
+ * DRecPy/Dataset/mem_dataset.py:119-129 (positives) and :154-163 (null pairs).
+ * pos_* : per-user rows with interaction >= threshold (all rows if no threshold), in DataFrame row order;
+ * all_* : per-user item ids of ALL rows, sorted ascending (membership test of :161).
+ * Host arrays are borrowed until drb_sampler_destroy. */
+int drb_sampler_create(int32_t max_uid, int32_t max_iid,
+                       const int64_t* pos_indptr, const int32_t* pos_iid, const double* pos_val,
+                       const int64_t* all_indptr, const int32_t* all_iid_sorted,
+                       double neg_ratio, uint64_t abs_seed, drb_sampler** out);
+int drb_sampler_destroy(drb_sampler* s);
+/* fills n triples; val = 0 for null pairs, the stored interaction for positives */
+int drb_sampler_sample(drb_sampler* s, int64_t n, int32_t* uid, int32_t* iid, double* val);
+int drb_sampler_getstate(const drb_sampler* s, uint32_t state[3 * 625]);
+int drb_sampler_setstate(drb_sampler* s, const uint32_t state[3 * 625]);
+
+/* ------------------------------------------------------------------ CDAE corruption mask (host, MT19937)
+ * replaces: DRecPy/Recommender/cdae.py:63-64 -- one rng.uniform(0,1) draw per item, in item order, for every
+ * sampled user (n_items draws per user, zeros included).  Emits one keep byte per stored positive of each
+ * sampled user: keep_off[b]..keep_off[b+1] index `keep` in CSR order of user uids[b] (csr = positives only,
+ * column-sorted, host copy). */
+int drb_cdae_corruption_keep_mt(drb_rng* rng, const int32_t* uids, int32_t batch, int32_t n_items, double q,
+                                const int64_t* csr_indptr, const int32_t* csr_indices,
+                                int32_t* keep_off /* [batch+1] */, uint8_t* keep /* [sum deg] */);
+/* keep_off only (prefix of the sampled users' degrees), for the counter-based (philox) mask mode */
+int drb_batch_offsets(const int32_t* uids, int32_t batch, const int64_t* csr_indptr, int32_t* keep_off);
+
+/* ------------------------------------------------------------------ CDAE
+ * Parameter arena layout (floats), all segments 16-byte aligned, row stride ld = K rounded up to a multiple of 4:
+ *   [ W2T  n_items x ld | W  n_items x ld | V  n_users x ld | b  ld | b2  n_items rounded up to a multiple of 4 ]
+ * W2T is the reference's W_ (cdae.py:37, [K, I]) stored item-major ([I, K]); pad columns k >= K stay zero.
+ * params / adam_m / adam_v / grads share this layout.  Reference variable order for the per-variable Adam
+ * step counters t[5] is [W, W_, V, b, b_] (cdae.py:43). */
+typedef struct {
+  int64_t off_w2t, off_w, off_v, off_b, off_b2, total; /* float offsets into the arena */
+  int32_t ld, items_pad;
+} drb_cdae_layout_t;
+int drb_cdae_layout(int32_t n_users, int32_t n_items, int32_t hidden, drb_cdae_layout_t* out);
+/* workspace bytes needed for batches up to max_batch (training) / max_score_users x max_candidates (scoring) */
+int64_t drb_cdae_workspace_bytes(int32_t n_users, int32_t n_items, int32_t hidden, int32_t max_batch);
+
+typedef struct {
+  int32_t n_users, n_items, hidden;
+  float* params;           /* device arenas (caller-owned) */
+  float* adam_m;
+  float* adam_v;
+  float* grads;
+  const int64_t* csr_indptr;   /* device CSR of positives (interaction >= threshold), column-sorted */
+  const int32_t* csr_indices;
+  const int64_t* seen_indptr;  /* device CSR of ALL stored rows (novelty filter of cdae.py:93-98); may alias csr_* */
+  const int32_t* seen_indices;
+  float corruption_level;      /* q */
+  int32_t loss_kind;           /* DRB_LOSS_* */
+  int32_t label_mode;          /* DRB_LABEL_* */
+  void* workspace;             /* device, >= drb_cdae_workspace_bytes(...) */
+  int64_t workspace_bytes;
+  int32_t max_batch;
+} drb_cdae_desc;
+
+typedef struct {
+  float learning_rate, beta1, beta2, epsilon;  /* Keras Adam (recommender_abc.py:153): 1e-3, .9, .999, 1e-7 */
+  float reg_rate;
+  int32_t t[5];            /* Adam step counter per variable [W, W_, V, b, b_] (Q2: 5(s-1)+j+1) */
+  uint64_t philox_seed;    /* used only when keep == NULL */
+  uint64_t philox_step;
+} drb_cdae_step_args;
+
+int drb_cdae_create(drb_ctx* ctx, const drb_cdae_desc* desc, drb_cdae** out);
+int drb_cdae_destroy(drb_cdae* m);
+/* One training step on device-resident inputs.
+ * replaces: recommender_abc.py:190-205 (tape, gradient, 5x apply_gradients) with cdae.py:50-82 inside.
+ * uids[batch], keep_off[batch+1], keep[keep_off[batch]] are DEVICE pointers; keep == NULL selects the
+ * counter-based mask (philox4x32-10 keyed by (seed, step, slot, item)).  loss_out: device float. */
+int drb_cdae_step(drb_cdae* m, const int32_t* uids, const int32_t* keep_off, const uint8_t* keep,
+                  int32_t batch, const drb_cdae_step_args* args, float* loss_out);
+/* Same step with HOST inputs: copies uids / keep_off / keep to the device (inside the call), runs the step,
+ * and, if loss_host != NULL, copies the loss back and synchronises. */
+int drb_cdae_step_host(drb_cdae* m, const int32_t* uids, const int32_t* keep_off, const uint8_t* keep,
+                       int32_t batch, const drb_cdae_step_args* args, float* loss_host);
+/* Hidden representations h[n, ld] for n users, no corruption (cdae.py:67-76 first line).  uids: device. */
+int drb_cdae_hidden(drb_cdae* m, const int32_t* uids, int32_t n, float* h_out);
+/* Candidate scoring + ranking.  replaces: cdae.py:84-103 (_predict over all items, filter, heapq.nlargest).
+ * cand[n x max_cand] internal item ids (device), cand_count[n]; entries beyond the count are ignored.
+ * If novelty != 0, candidates present in the user's `seen` row are dropped.  Output per user: n_out[u] ranked
+ * entries, ordered by (score desc, iid desc) == heapq.nlargest on (score, iid) tuples. */
+int drb_cdae_rank_candidates(drb_cdae* m, const int32_t* uids, int32_t n, const int32_t* cand,
+                             const int32_t* cand_count, int32_t max_cand, int32_t novelty,
+                             int32_t* out_iid, float* out_score, int32_t* n_out);
+/* Full-catalog top-k.  replaces: recommender_abc.py:413-419 -> cdae.py:90-103 with iids = range(n_items).
+ * out_iid / out_score: [n x k]; n_out[u] <= k. */
+int drb_cdae_topk(drb_cdae* m, const int32_t* uids, int32_t n, int32_t k, int32_t novelty,
+                  int32_t* out_iid, float* out_score, int32_t* n_out);
+/* Dense scores for n users over all items: out[n x items_pad] (cdae.py:84-88 with iid=None). */
+int drb_cdae_predict_all(drb_cdae* m, const int32_t* uids, int32_t n, float* out);
+
+/* ------------------------------------------------------------------ DMF
+ * Tower l has kernel [in_l, out_l] (row stride ld_l = out_l rounded up to a multiple of 4) and bias [ld_l].
+ * Arena layout: user tower layers in order (kernel, bias), then item tower layers.  in_0 = n_items for the
+ * user tower and n_users for the item tower (dmf.py:48-58). */
+#define DRB_DMF_MAX_LAYERS 8
+typedef struct {
+  int32_t n_layers_user, n_layers_item;
+  int64_t off_kernel_user[DRB_DMF_MAX_LAYERS], off_bias_user[DRB_DMF_MAX_LAYERS];
+  int64_t off_kernel_item[DRB_DMF_MAX_LAYERS], off_bias_item[DRB_DMF_MAX_LAYERS];
+  int32_t ld_user[DRB_DMF_MAX_LAYERS], ld_item[DRB_DMF_MAX_LAYERS];
+  int64_t total;
+} drb_dmf_layout_t;
+int drb_dmf_layout(int32_t n_users, int32_t n_items, const int32_t* user_factors, int32_t n_user_layers,
+                   const int32_t* item_factors, int32_t n_item_layers, drb_dmf_layout_t* out);
+int64_t drb_dmf_workspace_bytes(int32_t n_users, int32_t n_items, const int32_t* user_factors,
+                                int32_t n_user_layers, const int32_t* item_factors, int32_t n_item_layers,
+                                int32_t max_batch);
+
+typedef struct {
+  int32_t n_users, n_items;
+  int32_t n_layers_user, n_layers_item;
+  int32_t user_factors[DRB_DMF_MAX_LAYERS], item_factors[DRB_DMF_MAX_LAYERS];
+  float* params;
+  float* adam_m;
+  float* adam_v;
+  float* grads;
+  /* device CSR (user rows over items) and CSC (item rows over users) of ALL stored interactions with raw
+   * values (duplicates summed), column-sorted; row_scale = rsqrt(max(sum v^2, 1e-12)) per row when
+   * l2_norm_vectors (dmf.py:82-84), else NULL */
+  const int64_t* csr_indptr; const int32_t* csr_indices; const float* csr_values; const float* csr_row_scale;
+  const int64_t* csc_indptr; const int32_t* csc_indices; const float* csc_values; const float* csc_row_scale;
+  void* workspace;
+  int64_t workspace_bytes;
+  int32_t max_batch;
+} drb_dmf_desc;
+
+typedef struct {
+  float learning_rate, beta1, beta2, epsilon;
+  float reg_rate;
+  int32_t t[2];            /* Adam step counter per tower [user_nn, item_nn] (Q2: 2(s-1)+g+1) */
+} drb_dmf_step_args;
+
+int drb_dmf_create(drb_ctx* ctx, const drb_dmf_desc* desc, drb_dmf** out);
+int drb_dmf_destroy(drb_dmf* m);
+/* replaces: recommender_abc.py:190-205 with dmf.py:64-99 inside.  uids/iids/labels: device [batch]. */
+int drb_dmf_step(drb_dmf* m, const int32_t* uids, const int32_t* iids, const float* labels, int32_t batch,
+                 const drb_dmf_step_args* args, float* loss_out);
+int drb_dmf_step_host(drb_dmf* m, const int32_t* uids, const int32_t* iids, const float* labels, int32_t batch,
+                      const drb_dmf_step_args* args, float* loss_host);
+/* p[n] = max(1e-6, cos(user tower(uid), item tower(iid))) for n pairs (dmf.py:88-96, un-rescaled). device. */
+int drb_dmf_forward_pairs(drb_dmf* m, const int32_t* uids, const int32_t* iids, int32_t n, float* p_out);
+/* replaces: recommender_abc.py:454-461 (one _predict per candidate + nlargest).  Same contract as
+ * drb_cdae_rank_candidates; scores are the un-rescaled p (rescaling is monotone, done by the host). */
+int drb_dmf_rank_candidates(drb_dmf* m, const int32_t* uids, int32_t n, const int32_t* cand,
+                            const int32_t* cand_count, int32_t max_cand, int32_t novelty,
+                            int32_t* out_iid, float* out_score, int32_t* n_out);
+
+/* ------------------------------------------------------------------ ranking_evaluation candidate generation
+ * replaces: DRecPy/Evaluation/Processes/ranking_evaluation.py:108-116,163-219 -- per-user
+ * random.Random(seed+idx), rng.sample of positives / negatives, randint generation of extra negatives,
+ * rng.shuffle.  Test rows are grouped by user in evaluation order (row order inside a user preserved):
+ * test_indptr[n_users+1], test_item (raw ids), test_val.  black_indptr/black_item: per evaluated user, sorted
+ * raw item ids of its training-set positives (ignored when train_evaluation != 0).
+ * n_pos < 0 / n_neg < 0 mean "None"; user u is seeded with abs(seed + u); n_neg_is_frac != 0 means n_neg = int(frac * n_positives).
+ * Outputs: cand_off[n_users+1] (caller passes capacity via cand_capacity), cand (raw ids, shuffled),
+ * n_pos_out[u] (number of sampled positives), pos (raw ids of the sampled positives, pos_off[n_users+1]),
+ * skipped[u] != 0 when the reference returns early for that user. */
+int drb_eval_candidates(int64_t n_users, const int64_t* test_indptr, const int64_t* test_item,
+                        const double* test_val, const int64_t* black_indptr, const int64_t* black_item,
+                        int32_t train_evaluation, int64_t n_items, double threshold, int64_t n_pos,
+                        double n_neg, int32_t n_neg_is_frac, int32_t generate_negative_pairs, int64_t seed,
+                        int64_t cand_capacity, int64_t* cand_off, int64_t* cand, int64_t* pos_off, int64_t* pos,
+                        uint8_t* skipped);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DRB_H */

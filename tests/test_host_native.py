@@ -1,0 +1,169 @@
+"""Host-side pieces of libdrb (no GPU needed): library loads and exports every symbol of include/drb.h, the
+CPython RNG replay, PointSampler vs the live-reference goldens, corruption mask vs the oracle, and the
+ranking_evaluation protocol vs the live-reference goldens."""
+import ctypes as C
+import json
+import os
+import random
+import re
+
+import numpy as np
+import pytest
+
+import drecpy_b200 as drb
+from drecpy_b200 import _lib
+from oracle.cdae import corruption_keep_mt
+from oracle.sampler import PointSamplerOracle
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = _lib.load()
+    header = open(os.path.join(ROOT, 'include', 'drb.h')).read()
+    declared = set(re.findall(r'\b(drb_[a-z0-9_]+)\s*\(', header))
+    assert declared, 'no declarations parsed'
+    for name in declared:
+        assert hasattr(lib, name), f'{name} declared in drb.h but not exported'
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    assert lib.drb_version() == 100
+
+
+def test_no_cpu_fallback_without_device():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip('GPU present')
+    h = _lib.vp()
+    assert _lib.load().drb_ctx_create(0, C.byref(h)) == -2
+    assert b'no CPU fallback' in _lib.load().drb_last_error()
+    u, i, v = drb.synthetic_interactions(30, 40, 300)
+    with pytest.raises(RuntimeError):
+        drb.CDAE(hidden_factors=8, verbose=False, seed=1).fit(drb.InteractionData(u, i, v), epochs=1)
+
+
+@pytest.mark.parametrize('seed', [0, 10, 23, 2 ** 31 + 7, 2 ** 45 + 3])
+def test_rng_replays_cpython(seed):
+    lib = _lib.load()
+    g = _lib.HostRng(seed)
+    r = random.Random(seed)
+    assert [g.random() for _ in range(1500)] == [r.random() for _ in range(1500)]
+    for n in [1, 2, 3, 7, 943, 1682, 10 ** 6, 2 ** 32, 2 ** 40 + 11]:
+        assert [g.randbelow(n) for _ in range(40)] == [r._randbelow(n) for _ in range(40)]
+    for k in [1, 7, 31, 32, 33, 53, 64]:
+        assert lib.drb_rng_getrandbits(g.handle, k) == r.getrandbits(k)
+    st = r.getstate()[1]
+    assert np.array_equal(g.getstate(), np.array(st, np.uint32))
+    # sample / shuffle (CPython 3.12 algorithms)
+    for n, k in [(5, 3), (21, 6), (100, 7), (101, 100), (1000, 100), (4000, 21), (30, 0)]:
+        out = np.zeros(max(k, 1), np.int64)
+        _lib.check(lib.drb_rng_sample_indices(g.handle, n, k, _lib.np_ptr(out)))
+        assert out[:k].tolist() == r.sample(range(n), k), (n, k)
+    x = np.arange(101, dtype=np.int64)
+    y = list(range(101))
+    _lib.check(lib.drb_rng_shuffle_i64(g.handle, 101, _lib.np_ptr(x)))
+    r.shuffle(y)
+    assert x.tolist() == y
+
+
+@pytest.mark.parametrize('name', ['small_zero_rows', 'small_dups', 'small_float', 'thr3'])
+def test_native_sampler_and_csr_vs_live_reference(golden_dir, name):
+    g = np.load(os.path.join(golden_dir, f'sampler_{name}.npz'))
+    ds = drb.InteractionData(g['user'], g['item'], g['interaction'])
+    ds.assign_internal_ids()
+    assert np.array_equal(ds.uid, g['uid']) and np.array_equal(ds.iid, g['iid'])
+    for got, want in zip(ds.csr(), (g['csr_indptr'], g['csr_indices'], g['csr_data'])):
+        assert np.array_equal(got, want)
+    for got, want in zip(ds.csc(), (g['csc_indptr'], g['csc_indices'], g['csc_data'])):
+        assert np.array_equal(got, want)
+    assert np.array_equal(ds.select_user_interaction_vec(0).toarray().ravel(), g['dense_user0'])
+    assert np.array_equal(ds.select_item_interaction_vec(0).toarray().ravel(), g['dense_item0'])
+    for key in g.files:
+        if key.startswith('triples_seed'):
+            seed = int(key[len('triples_seed'):])
+            s = drb.PointSampler(ds, int(g['neg_ratio']), float(g['thr']), seed)
+            u, i, v = s.sample_arrays(len(g[key]))
+            assert np.array_equal(np.stack([u, i, v], 1).astype(np.float64), g[key]), (name, seed)
+
+
+def test_native_sampler_vs_oracle_c1_shape_and_state_roundtrip():
+    u, i, v = drb.synthetic_interactions(943, 1682, 100000, seed=10)
+    ds = drb.InteractionData(u, i, v)
+    ds.assign_internal_ids()
+    assert ds.count_unique('uid') == 943 and ds.count_unique('iid') == 1682
+    s = drb.PointSampler(ds, 5, 0.001, 10)
+    o = PointSamplerOracle(ds.uid, ds.iid, ds.interaction, 5, 0.001, 10)
+    assert s.sample(640) == [(a, b, int(c)) for a, b, c in o.sample(640)]
+    st = s.getstate()
+    a = s.sample(50)
+    s.setstate(st)
+    assert s.sample(50) == a
+
+
+def test_corruption_mask_matches_python_stream():
+    """cdae.py:63-64: n_items draws per sampled user, in item order; the native replay skips unused draws."""
+    u, i, v = drb.synthetic_interactions(60, 97, 900, seed=3)
+    ds = drb.InteractionData(u, i, v)
+    ds.assign_internal_ids()
+    indptr, indices, _ = ds.csr(0.001)
+    uids = np.array([5, 17, 5, 0, 59, 33], np.int32)
+    rng = _lib.HostRng(10)
+    off = np.zeros(len(uids) + 1, np.int32)
+    keep = np.zeros(int(np.diff(indptr).max()) * len(uids), np.uint8)
+    _lib.check(_lib.load().drb_cdae_corruption_keep_mt(rng.handle, _lib.np_ptr(uids), len(uids), 97, 0.2,
+                                                       _lib.np_ptr(indptr), _lib.np_ptr(indices), _lib.np_ptr(off),
+                                                       _lib.np_ptr(keep)))
+    pr = random.Random(10)
+    for b, uid in enumerate(uids):
+        dense = corruption_keep_mt(pr, 97, 0.2)
+        items = indices[indptr[uid]:indptr[uid + 1]]
+        assert np.array_equal(keep[off[b]:off[b + 1]].astype(bool), dense[items])
+    assert rng.random() == pr.random()          # both streams consumed exactly len(uids) * n_items draws
+
+
+class FakeModel:
+    def __init__(self, train):
+        self.interaction_dataset = self._data = train
+        self.interaction_threshold = 0.001
+        self.n_items = train.count_unique('iid')
+
+    def rank(self, user, items, novelty=True, skip_invalid_items=True, **kw):
+        t = self._data
+        uid = t.user_to_uid(user)
+        cand = set(x for x in (t.item_to_iid(it) for it in items) if x is not None)
+        if novelty:
+            cand -= set(t.user_items(uid).tolist())
+        r = sorted([(float((uid * 7919 + i * 104729) % 97) / 97.0, i) for i in cand], reverse=True)
+        return [(s, t.iid_to_item(i)) for s, i in r]
+
+
+def test_ranking_evaluation_protocol_vs_live_reference(golden_dir):
+    with open(os.path.join(golden_dir, 'ranking.json')) as f:
+        g = json.load(f)
+    tr, te = np.array(g['train_rows']), np.array(g['test_rows'])
+    train = drb.InteractionData(*[tr[:, c].astype(np.int64) for c in range(3)])
+    train.assign_internal_ids()
+    test = drb.InteractionData(*[te[:, c].astype(np.int64) for c in range(3)])
+    for name, case in g['cases'].items():
+        rec = []
+        res = drb.ranking_evaluation(FakeModel(train), test, record=rec, **case['kwargs'])
+        assert res == case['result'], name
+        assert len(rec) == len(case['per_user'])
+        for user, cands, ranked in rec:
+            ref = case['per_user'][str(user)]
+            assert cands == ref['candidates'] and ranked == ref['ranked'], (name, user)
+
+
+def test_ranking_evaluation_argument_errors():
+    """error behaviour of ranking_evaluation.py:63-71 (reference tests test_ranking_evaluation.py:127-250)."""
+    u, i, v = drb.synthetic_interactions(20, 30, 200)
+    train = drb.InteractionData(u, i, v)
+    train.assign_internal_ids()
+    m = FakeModel(train)
+    with pytest.raises(AssertionError, match=r'The number of test users \(0\) should be > 0.'):
+        drb.ranking_evaluation(m, train, n_test_users=0)
+    with pytest.raises(AssertionError, match=r'k \(0\) should be > 0.'):
+        drb.ranking_evaluation(m, train, k=0)
+    with pytest.raises(Exception, match='Cannot generate negative interaction pairs'):
+        drb.ranking_evaluation(m, train, generate_negative_pairs=True)
+    with pytest.raises(AssertionError, match='Expected "metrics" argument to be a list'):
+        drb.ranking_evaluation(m, train, metrics=drb.NDCG())
