@@ -69,6 +69,8 @@ SIGNATURES = {
     'drb_ctx_set_stream': (C.c_int, [vp, vp]),
     'drb_ctx_synchronize': (C.c_int, [vp]),
     'drb_ctx_launch_count': (i64, [vp]),
+    'drb_ctx_profile_enable': (C.c_int, [vp, C.c_int]),
+    'drb_ctx_profile_read': (C.c_int, [vp, C.c_char_p, i64, vp, vp, i32, P(i32)]),
     'drb_rng_create': (C.c_int, [u64, P(vp)]),
     'drb_rng_destroy': (C.c_int, [vp]),
     'drb_rng_seed': (C.c_int, [vp, u64]),
@@ -176,3 +178,14 @@ class HostRng:
     @property
     def handle(self):
         return self._h
+
+
+def profile_read(ctx):
+    """{kernel name: (total ms, launches)} accumulated since profiling was enabled / last read."""
+    names = C.create_string_buffer(4096)
+    ms = np.zeros(64, np.float64)
+    cnt = np.zeros(64, np.int64)
+    n = i32(0)
+    check(load().drb_ctx_profile_read(ctx, names, 4096, np_ptr(ms), np_ptr(cnt), 64, C.byref(n)))
+    keys = names.value.decode().split('\n')[:n.value]
+    return {k: (float(ms[j]), int(cnt[j])) for j, k in enumerate(keys)}

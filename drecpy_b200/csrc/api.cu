@@ -65,6 +65,7 @@ int drb_ctx_create(int device, drb_ctx** out) {
   c->stream = nullptr;
   c->launches = 0;
   c->sticky = 0;
+  c->profile = 0;
   if (cudaSetDevice(device) != cudaSuccess) {
     delete c;
     return drb_fail(DRB_E_CUDA, "cudaSetDevice(%d) failed", device);
@@ -84,6 +85,48 @@ int drb_ctx_synchronize(drb_ctx* ctx) {
   return DRB_OK;
 }
 int64_t drb_ctx_launch_count(const drb_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int drb_ctx_profile_enable(drb_ctx* ctx, int on) {
+  if (!ctx) return drb_fail(DRB_E_INVALID, "ctx is NULL");
+  ctx->profile = on ? 1 : 0;
+  return DRB_OK;
+}
+
+int drb_ctx_profile_read(drb_ctx* ctx, char* names, int64_t names_cap, double* total_ms, int64_t* counts,
+                         int32_t max_entries, int32_t* n_entries) {
+  if (!ctx || !names || !total_ms || !counts || !n_entries || names_cap < 1)
+    return drb_fail(DRB_E_INVALID, "drb_ctx_profile_read: bad argument");
+  DRB_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  std::vector<const char*> keys;
+  std::vector<double> ms;
+  std::vector<int64_t> cnt;
+  for (auto& r : ctx->recs) {
+    float t = 0.f;
+    cudaEventElapsedTime(&t, r.beg, r.end);
+    cudaEventDestroy(r.beg);
+    cudaEventDestroy(r.end);
+    size_t k = 0;
+    for (; k < keys.size(); k++) if (!std::strcmp(keys[k], r.name)) break;
+    if (k == keys.size()) { keys.push_back(r.name); ms.push_back(0.0); cnt.push_back(0); }
+    ms[k] += t; cnt[k] += 1;
+  }
+  ctx->recs.clear();
+  names[0] = 0;
+  int n = 0;
+  int64_t used = 0;
+  for (size_t k = 0; k < keys.size() && n < max_entries; k++) {
+    const int64_t len = (int64_t)std::strlen(keys[k]);
+    if (used + len + 2 > names_cap) break;
+    std::memcpy(names + used, keys[k], len);
+    names[used + len] = '\n';
+    used += len + 1;
+    names[used] = 0;
+    total_ms[n] = ms[k]; counts[n] = cnt[k];
+    n++;
+  }
+  *n_entries = n;
+  return DRB_OK;
+}
 
 }  // extern "C"
 

@@ -64,6 +64,7 @@ __global__ void __launch_bounds__(128) k_dmf_head(DmfHeadArgs h) {
 int launch_dmf_head(drb_ctx* ctx, const DmfHeadArgs& a) {
   if (a.n <= 0) return DRB_OK;
   const int blocks = (a.n * 32 + 127) / 128;
+  drb_prof_scope prof_(ctx, "k_dmf_head");
   k_dmf_head<<<blocks, 128, 0, ctx->stream>>>(a);
   DRB_LAUNCH_CHECK(ctx, "k_dmf_head");
   return DRB_OK;

@@ -17,12 +17,34 @@ static inline int64_t drb_round_up(int64_t x, int64_t m) { return (x + m - 1) / 
 #ifdef __CUDACC__
 #include <cuda_runtime.h>
 
+#include <vector>
+
+struct drb_prof_rec { const char* name; cudaEvent_t beg, end; };
+
 struct drb_ctx {
   int device;
   int sm_count;
   cudaStream_t stream;
   int64_t launches;
   int sticky;  // first CUDA error seen (sticky)
+  int profile; // when set, every kernel launch is bracketed by CUDA events on `stream` (bench.py roofline leg)
+  std::vector<drb_prof_rec> recs;
+};
+
+// RAII bracket around one kernel launch: records events on the launching stream when profiling is enabled
+struct drb_prof_scope {
+  drb_ctx* ctx; cudaEvent_t end = nullptr;
+  drb_prof_scope(drb_ctx* c, const char* name) : ctx(c) {
+    if (!c->profile) return;
+    cudaEvent_t beg;
+    cudaEventCreate(&beg);
+    cudaEventCreate(&end);
+    cudaEventRecord(beg, c->stream);
+    c->recs.push_back({name, beg, end});
+  }
+  ~drb_prof_scope() {
+    if (end) cudaEventRecord(end, ctx->stream);
+  }
 };
 
 #define DRB_CUDA_TRY(ctx, expr)                                                                        \

@@ -262,6 +262,8 @@ int run(drb_ctx* ctx, const GemmArgs& g, int* n_mtiles_out, int* n_blocks_out) {
   if (grid.y > 65535 || grid.z > 65535) return drb_fail(DRB_E_INVALID, "gemm: grid too large");
   if (n_mtiles_out) *n_mtiles_out = grid.y;
   if (n_blocks_out) *n_blocks_out = grid.x * grid.y;
+  drb_prof_scope prof_(ctx, LAYOUT == LAYOUT_KK ? (EPI == EPI_CDAE_LOSS ? "k_sgemm_kk_loss" : "k_sgemm_kk")
+                             : (LAYOUT == LAYOUT_MN ? "k_sgemm_mn" : "k_sgemm_kn"));
   k_sgemm<BN, LAYOUT, EPI><<<grid, THREADS, 0, ctx->stream>>>(g);
   DRB_LAUNCH_CHECK(ctx, "k_sgemm");
   return DRB_OK;

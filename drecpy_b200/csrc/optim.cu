@@ -87,6 +87,7 @@ int launch_adam(drb_ctx* ctx, const AdamArgs& a, int* n_blocks_out) {
   int blocks = (int)std::min<int64_t>(want, (int64_t)ctx->sm_count * 16);
   if (blocks < 1) blocks = 1;
   *n_blocks_out = blocks;
+  drb_prof_scope prof_(ctx, "k_adam");
   k_adam<<<blocks, kAdamThreads, 0, ctx->stream>>>(a, total4);
   DRB_LAUNCH_CHECK(ctx, "k_adam");
   return DRB_OK;
@@ -94,6 +95,7 @@ int launch_adam(drb_ctx* ctx, const AdamArgs& a, int* n_blocks_out) {
 
 int launch_finalize_loss(drb_ctx* ctx, const float* loss_part, int n_loss, float scale, const float* reg_part,
                          int n_reg, float* loss_out) {
+  drb_prof_scope prof_(ctx, "k_finalize_loss");
   k_finalize_loss<<<1, 256, 0, ctx->stream>>>(loss_part, n_loss, scale, reg_part, n_reg, loss_out);
   DRB_LAUNCH_CHECK(ctx, "k_finalize_loss");
   return DRB_OK;

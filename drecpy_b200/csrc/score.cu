@@ -232,6 +232,7 @@ int launch_rank_candidates(drb_ctx* ctx, const CandScoreArgs& a, int n) {
   if (n <= 0) return DRB_OK;
   if (a.max_cand < 1 || a.max_cand > 4096) return drb_fail(DRB_E_INVALID, "rank_candidates: max_cand must be in [1, 4096]");
   const int P = next_pow2(a.max_cand);
+  drb_prof_scope prof_(ctx, "k_rank_candidates");
   k_rank_candidates<<<n, 128, (size_t)P * sizeof(uint64_t), ctx->stream>>>(a, P);
   DRB_LAUNCH_CHECK(ctx, "k_rank_candidates");
   return DRB_OK;
@@ -241,6 +242,7 @@ int launch_topk(drb_ctx* ctx, const TopkArgs& a, int n) {
   if (n <= 0) return DRB_OK;
   if (a.k < 1 || a.k > 2048) return drb_fail(DRB_E_INVALID, "topk: k must be in [1, 2048]");
   const int P = next_pow2(a.k);
+  drb_prof_scope prof_(ctx, "k_topk");
   k_topk<<<n, kTopkThreads, (size_t)P * sizeof(uint64_t), ctx->stream>>>(a, P);
   DRB_LAUNCH_CHECK(ctx, "k_topk");
   return DRB_OK;

@@ -240,6 +240,7 @@ template <int LPR, int NV>
 struct GatherLauncher {
   static int run(drb_ctx* ctx, const GatherArgs& a, int n, const char* name) {
     const size_t smem = (size_t)kWarps * (32 / LPR) * a.ld * sizeof(float);
+    drb_prof_scope prof_(ctx, "k_gather");
     k_gather<LPR, NV><<<n, kGatherThreads, smem, ctx->stream>>>(a);
     DRB_LAUNCH_CHECK(ctx, name);
     return DRB_OK;
@@ -248,6 +249,7 @@ struct GatherLauncher {
 template <int LPR, int NV>
 struct ScatterLauncher {
   static int run(drb_ctx* ctx, const ScatterArgs& a, int n, const char* name) {
+    drb_prof_scope prof_(ctx, "k_scatter");
     k_scatter<LPR, NV><<<n, kGatherThreads, 0, ctx->stream>>>(a);
     DRB_LAUNCH_CHECK(ctx, name);
     return DRB_OK;
@@ -270,6 +272,7 @@ int launch_scatter(drb_ctx* ctx, const ScatterArgs& a, int n) {
 
 int launch_batch_prep(drb_ctx* ctx, const BatchPrepArgs& a, int n) {
   if (n <= 0) return DRB_OK;
+  drb_prof_scope prof_(ctx, "k_batch_prep");
   k_batch_prep<<<n, 128, 0, ctx->stream>>>(a);
   DRB_LAUNCH_CHECK(ctx, "k_batch_prep");
   return DRB_OK;
@@ -278,6 +281,7 @@ int launch_batch_prep(drb_ctx* ctx, const BatchPrepArgs& a, int n) {
 int launch_dz1(drb_ctx* ctx, const float* dh_part, int splits, const float* h, float* dz1, int n, int ld,
                float* colpart) {
   const int nblk = (n + kRowsPerBlock - 1) / kRowsPerBlock;
+  drb_prof_scope prof_(ctx, "k_dz1");
   k_dz1<<<nblk, min(512, (int)drb_round_up(ld, 32)), 0, ctx->stream>>>(dh_part, splits, h, dz1, n, ld, colpart);
   DRB_LAUNCH_CHECK(ctx, "k_dz1");
   return nblk;
@@ -285,6 +289,7 @@ int launch_dz1(drb_ctx* ctx, const float* dh_part, int splits, const float* h, f
 
 int launch_colpart(drb_ctx* ctx, const float* x, int n, int ld, float* colpart) {
   const int nblk = (n + kRowsPerBlock - 1) / kRowsPerBlock;
+  drb_prof_scope prof_(ctx, "k_colpart");
   k_colpart<<<nblk, min(512, (int)drb_round_up(ld, 32)), 0, ctx->stream>>>(x, n, ld, colpart);
   DRB_LAUNCH_CHECK(ctx, "k_colpart");
   return nblk;
@@ -292,6 +297,7 @@ int launch_colpart(drb_ctx* ctx, const float* x, int n, int ld, float* colpart) 
 
 int launch_reduce_partials(drb_ctx* ctx, const float* part, int nparts, int ld, float* out, int n) {
   if (n <= 0) return DRB_OK;
+  drb_prof_scope prof_(ctx, "k_reduce_partials");
   k_reduce_partials<<<(n + 255) / 256, 256, 0, ctx->stream>>>(part, nparts, ld, out, n);
   DRB_LAUNCH_CHECK(ctx, "k_reduce_partials");
   return DRB_OK;

@@ -60,6 +60,12 @@ int drb_ctx_set_stream(drb_ctx* ctx, void* stream);
 int drb_ctx_synchronize(drb_ctx* ctx);
 /* number of kernel launches this context has enqueued so far (bench.py's gpu_launches claim) */
 int64_t drb_ctx_launch_count(const drb_ctx* ctx);
+/* Per-kernel device timing for the roofline report: when enabled, every kernel launch is bracketed by CUDA
+ * events on the context's stream.  drb_ctx_profile_read synchronises, aggregates by kernel name and clears the
+ * records: names = '\n'-separated list, total_ms[i] / counts[i] per name.  Never enable it inside a timed run. */
+int drb_ctx_profile_enable(drb_ctx* ctx, int on);
+int drb_ctx_profile_read(drb_ctx* ctx, char* names, int64_t names_cap, double* total_ms, int64_t* counts,
+                         int32_t max_entries, int32_t* n_entries);
 
 /* ------------------------------------------------------------------ host RNG: CPython random.Random replay
  * replaces: the three `random.Random(seed)` streams of DRecPy/Sampler/point_sampler.py:30,
