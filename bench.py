@@ -240,7 +240,8 @@ def run_native(args, cfg):
     P = 5
     _lib.check(lib.drb_ctx_profile_enable(m._ctx, 1))
     for s in range(P):
-        m.step_device(batches[s][0], batches[s][1], None, cfg['reg'], loss_dev)
+        bt = batches[s % len(batches)]
+        m.step_device(bt[0], bt[1], None, cfg['reg'], loss_dev)
     prof = _lib.profile_read(m._ctx)
     _lib.check(lib.drb_ctx_profile_enable(m._ctx, 0))
     kernels = {k: round(v[0] / P, 4) for k, v in prof.items()}
