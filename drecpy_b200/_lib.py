@@ -13,6 +13,7 @@ LIB_PATH = os.path.join(HERE, 'libdrb.so')
 
 DRB_LOSS = {'bce': 0, 'mse': 1}
 DRB_LABEL = {'batch_mean': 0, 'per_user': 1}
+DRB_GEMM = {'auto': 0, 'ffma': 1, 'tcgen05': 2}
 DMF_MAX_LAYERS = 8
 
 vp = C.c_void_p
@@ -29,7 +30,7 @@ class CdaeDesc(C.Structure):
                 ('params', vp), ('adam_m', vp), ('adam_v', vp), ('grads', vp),
                 ('csr_indptr', vp), ('csr_indices', vp), ('seen_indptr', vp), ('seen_indices', vp),
                 ('corruption_level', f32), ('loss_kind', i32), ('label_mode', i32),
-                ('workspace', vp), ('workspace_bytes', i64), ('max_batch', i32)]
+                ('workspace', vp), ('workspace_bytes', i64), ('max_batch', i32), ('gemm_path', i32)]
 
 
 class CdaeStepArgs(C.Structure):

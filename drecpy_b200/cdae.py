@@ -13,6 +13,7 @@ New keywords, all with reference-faithful defaults:
                             deviation for throughput configurations)
   adam_t='per_variable'     Adam step counter advances once per variable (Q2); 'per_step' = textbook Adam
   init_weights=None         dict with any of W, W_, V, b, b_ (reference shapes) to inject initial weights
+  gemm='auto'               'tcgen05' = 3xTF32 tensor-core GEMMs (fp32-accurate), 'ffma' = exact-fp32 CUDA-core GEMMs
 """
 import ctypes as C
 import random
@@ -37,6 +38,8 @@ class CDAE(DeepRecommenderABC):
         self.label_mode = kwds.get('label_mode', 'batch_mean')
         self.rng_mode = kwds.get('rng_mode', 'mt19937')
         self.adam_t = kwds.get('adam_t', 'per_variable')
+        self.gemm = kwds.get('gemm', 'auto')
+        assert self.gemm in _lib.DRB_GEMM
         assert self.label_mode in _lib.DRB_LABEL and self.rng_mode in ('mt19937', 'philox')
         assert self.adam_t in ('per_variable', 'per_step')
         self._native = None
@@ -117,6 +120,7 @@ class CDAE(DeepRecommenderABC):
         d.loss_kind = _lib.DRB_LOSS[self.loss]
         d.label_mode = _lib.DRB_LABEL[self.label_mode]
         d.workspace, d.workspace_bytes, d.max_batch = self._workspace.data_ptr(), ws_bytes, self._max_batch
+        d.gemm_path = _lib.DRB_GEMM[self.gemm]
         self._native = _lib.vp()
         _lib.check(lib.drb_cdae_create(self._ctx, C.byref(d), C.byref(self._native)))
 

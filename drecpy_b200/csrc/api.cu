@@ -133,6 +133,9 @@ int drb_ctx_profile_read(drb_ctx* ctx, char* names, int64_t names_cap, double* t
 // ========================================================================================== CDAE
 struct CdaeWs {
   float *h, *dz, *dh_part, *dz1, *col_b2, *col_b, *loss_part, *reg_part, *label_count, *loss_scalar;
+  // tcgen05 path: tf32 hi/lo operand splits (dz doubles as dz_hi)
+  float *h_hi, *h_lo, *hT_hi, *hT_lo, *w2t_hi, *w2t_lo, *wT_hi, *wT_lo, *dz_lo;
+  int64_t hT_floats, wT_floats;
   uint32_t* label_bits;
   int32_t *uids, *keep_off, *aux_i32;
   uint8_t* keep;
@@ -146,17 +149,21 @@ struct drb_cdae {
   CdaeWs ws;
   int splits, words_per_row;
   int64_t keep_cap;
+  bool use_umma;
+  int n2, batch_pad;   // tcgen05 path: N of the backward GEMMs (hidden + ones feature, rounded to 16), padded batch
 };
+
+static int cdae_n2(int hidden) { return (int)drb_round_up(hidden + 1, 16); }
 
 static int64_t cdae_keep_cap(int32_t n_items, int32_t max_batch) {
   // every sampled user can hold at most n_items positives; cap the staging buffer at 1 GiB
   return std::min<int64_t>((int64_t)max_batch * n_items, (int64_t)1 << 30);
 }
 
-static CdaeWs cdae_carve(void* base, const drb_cdae_layout_t& L, int n_items, int max_batch, int label_mode,
-                         int splits, int sm_count) {
+static CdaeWs cdae_carve(void* base, const drb_cdae_layout_t& L, int n_items, int hidden, int max_batch,
+                         int label_mode, int splits, int sm_count, bool umma) {
   Carver c(base);
-  CdaeWs w;
+  CdaeWs w{};
   const int64_t B = max_batch;
   const int mt = (max_batch + 127) / 128;
   w.h = c.take<float>(B * L.ld);
@@ -175,6 +182,20 @@ static CdaeWs cdae_carve(void* base, const drb_cdae_layout_t& L, int n_items, in
   w.keep_off = c.take<int32_t>(B + 1);
   w.aux_i32 = c.take<int32_t>(3 * B + 64);
   w.keep = c.take<uint8_t>(cdae_keep_cap(n_items, max_batch));
+  if (umma) {
+    const int64_t n2 = cdae_n2(hidden), bp = drb_round_up(max_batch, 4);
+    w.h_hi = c.take<float>(B * L.ld);
+    w.h_lo = c.take<float>(B * L.ld);
+    w.hT_floats = n2 * bp;
+    w.hT_hi = c.take<float>(w.hT_floats);
+    w.hT_lo = c.take<float>(w.hT_floats);
+    w.w2t_hi = c.take<float>((int64_t)n_items * L.ld);
+    w.w2t_lo = c.take<float>((int64_t)n_items * L.ld);
+    w.wT_floats = n2 * (int64_t)L.items_pad;
+    w.wT_hi = c.take<float>(w.wT_floats);
+    w.wT_lo = c.take<float>(w.wT_floats);
+    w.dz_lo = c.take<float>(B * L.items_pad);
+  }
   w.bytes = c.off;
   return w;
 }
@@ -200,7 +221,7 @@ int64_t drb_cdae_workspace_bytes(int32_t n_users, int32_t n_items, int32_t hidde
   drb_cdae_layout_t L;
   if (drb_cdae_layout(n_users, n_items, hidden, &L) || max_batch <= 0) return -1;
   // worst case over label modes and split counts (splits <= 32, 148+ SMs -> use 256 as an upper bound)
-  return cdae_carve(nullptr, L, n_items, max_batch, DRB_LABEL_PER_USER, 32, 256).bytes;
+  return cdae_carve(nullptr, L, n_items, hidden, max_batch, DRB_LABEL_PER_USER, 32, 256, true).bytes;
 }
 
 int drb_cdae_create(drb_ctx* ctx, const drb_cdae_desc* desc, drb_cdae** out) {
@@ -225,14 +246,32 @@ int drb_cdae_create(drb_ctx* ctx, const drb_cdae_desc* desc, drb_cdae** out) {
   m->L = L;
   m->splits = gemm_splits(ctx, desc->max_batch, L.ld, desc->n_items);
   m->words_per_row = (L.items_pad + 31) / 32;
-  m->ws = cdae_carve(desc->workspace, L, desc->n_items, desc->max_batch, desc->label_mode, m->splits,
-                     ctx->sm_count);
+  m->n2 = cdae_n2(desc->hidden);
+  m->batch_pad = (int)drb_round_up(desc->max_batch, 4);
+  const bool umma_ok = umma_available() && m->n2 <= 256;
+  if (desc->gemm_path == DRB_GEMM_TCGEN05 && !umma_ok) {
+    delete m;
+    return drb_fail(DRB_E_INVALID, "drb_cdae_create: the tcgen05 path needs hidden < 256 and a driver with TMA support");
+  }
+  m->use_umma = umma_ok && desc->gemm_path != DRB_GEMM_FFMA;
+  m->ws = cdae_carve(desc->workspace, L, desc->n_items, desc->hidden, desc->max_batch, desc->label_mode, m->splits,
+                     ctx->sm_count, m->use_umma);
   m->keep_cap = cdae_keep_cap(desc->n_items, desc->max_batch);
   if (m->ws.bytes > desc->workspace_bytes) {
     int64_t need = m->ws.bytes;
     delete m;
     return drb_fail(DRB_E_INVALID, "drb_cdae_create: workspace too small (%lld < %lld bytes)",
                     (long long)desc->workspace_bytes, (long long)need);
+  }
+  if (m->use_umma) {   // transposed operand buffers: rows >= hidden stay zero (the ones row is rewritten every step)
+    cudaError_t e = cudaMemsetAsync(m->ws.hT_hi, 0, (size_t)m->ws.hT_floats * 4, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(m->ws.hT_lo, 0, (size_t)m->ws.hT_floats * 4, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(m->ws.wT_hi, 0, (size_t)m->ws.wT_floats * 4, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(m->ws.wT_lo, 0, (size_t)m->ws.wT_floats * 4, ctx->stream);
+    if (e != cudaSuccess) {
+      delete m;
+      return drb_fail(DRB_E_CUDA, "drb_cdae_create: workspace clear failed: %s", cudaGetErrorString(e));
+    }
   }
   *out = m;
   return DRB_OK;
@@ -291,6 +330,27 @@ int drb_cdae_step(drb_cdae* m, const int32_t* uids, const int32_t* keep_off, con
   const float s = (float)(1.0 / (1.0 - (double)m->d.corruption_level));
   if ((r = cdae_hidden_into(m, uids, batch, keep_off, keep_used, s, w.h))) return r;
 
+  const float inv_count = (float)(1.0 / ((double)batch * (double)I));
+  int n_blocks = 0;
+  if (m->use_umma) {
+    // 3-5 on the tensor cores (umma.cu): 3xTF32 split products, TMA-fed, TMEM accumulators
+    const int n2 = m->n2, bp = m->batch_pad;
+    if ((r = launch_split_tf32(ctx, w.h, batch, ld, ld, w.h_hi, w.h_lo, w.hT_hi, w.hT_lo, bp, m->d.hidden))) return r;
+    if ((r = launch_split_tf32(ctx, P + L.off_w2t, I, ld, ld, w.w2t_hi, w.w2t_lo, w.wT_hi, w.wT_lo, L.items_pad, -1)))
+      return r;
+    UmmaOperands o1{w.h_hi, w.h_lo, ld, w.w2t_hi, w.w2t_lo, ld, I};
+    if ((r = launch_umma_cdae_loss(ctx, o1, batch, I, ld, w.dz, w.dz_lo, L.items_pad, P + L.off_b2,
+                                   per_user ? nullptr : w.label_count, per_user ? w.label_bits : nullptr,
+                                   m->words_per_row, m->d.loss_kind, inv_count, batch, w.loss_part, &n_blocks)))
+      return r;
+    // dW'^T = dz^T h (I x K); the constant-one feature at column `hidden` yields db' = colsum(dz)
+    UmmaOperands o2{w.dz, w.dz_lo, L.items_pad, w.hT_hi, w.hT_lo, bp, n2};
+    if ((r = launch_umma_store(ctx, o2, true, I, n2, batch, 1, G + L.off_w2t, ld, ld, G + L.off_b2, m->d.hidden)))
+      return r;
+    // dh = dz W'^T (B x K), split over the item range
+    UmmaOperands o3{w.dz, w.dz_lo, L.items_pad, w.wT_hi, w.wT_lo, L.items_pad, n2};
+    if ((r = launch_umma_store(ctx, o3, false, batch, n2, I, m->splits, w.dh_part, ld, ld, nullptr, -1))) return r;
+  } else {
   // 3. K2: z2 = h W'^T + b', p = sigmoid, loss terms, dL/dz2 (never materialises p)
   GemmArgs g1{};
   g1.A = w.h; g1.lda = ld; g1.B = P + L.off_w2t; g1.ldb = ld; g1.C = w.dz; g1.ldc = L.items_pad;
@@ -298,9 +358,9 @@ int drb_cdae_step(drb_cdae* m, const int32_t* uids, const int32_t* keep_off, con
   g1.bias = P + L.off_b2;
   g1.label_count = per_user ? nullptr : w.label_count;
   g1.label_bits = per_user ? w.label_bits : nullptr; g1.words_per_row = m->words_per_row;
-  g1.loss_kind = m->d.loss_kind; g1.inv_count = (float)(1.0 / ((double)batch * (double)I)); g1.batch = batch;
+  g1.loss_kind = m->d.loss_kind; g1.inv_count = inv_count; g1.batch = batch;
   g1.loss_part = w.loss_part; g1.col_part = w.col_b2;
-  int n_mtiles = 0, n_blocks = 0;
+  int n_mtiles = 0;
   if ((r = launch_gemm(ctx, LAYOUT_KK, EPI_CDAE_LOSS, g1, &n_mtiles, &n_blocks))) return r;
   if ((r = launch_reduce_partials(ctx, w.col_b2, n_mtiles, L.items_pad, G + L.off_b2, L.items_pad))) return r;
 
@@ -315,6 +375,7 @@ int drb_cdae_step(drb_cdae* m, const int32_t* uids, const int32_t* keep_off, con
   g3.A = w.dz; g3.lda = L.items_pad; g3.B = P + L.off_w2t; g3.ldb = ld; g3.C = w.dh_part; g3.ldc = ld;
   g3.M = batch; g3.N = ld; g3.Kred = I; g3.splits = m->splits;
   if ((r = launch_gemm(ctx, LAYOUT_KN, EPI_STORE, g3))) return r;
+  }
   int nb = launch_dz1(ctx, w.dh_part, m->splits, w.h, w.dz1, batch, ld, w.col_b);
   if (nb < 0) return nb;
   if ((r = launch_reduce_partials(ctx, w.col_b, nb, ld, G + L.off_b, ld))) return r;
@@ -345,7 +406,7 @@ int drb_cdae_step(drb_cdae* m, const int32_t* uids, const int32_t* keep_off, con
   int n_reg = 0;
   if ((r = launch_adam(ctx, ad, &n_reg))) return r;
   (void)U;
-  return launch_finalize_loss(ctx, w.loss_part, n_blocks, g1.inv_count, w.reg_part, n_reg, loss_out);
+  return launch_finalize_loss(ctx, w.loss_part, n_blocks, inv_count, w.reg_part, n_reg, loss_out);
 }
 
 int drb_cdae_step_host(drb_cdae* m, const int32_t* uids, const int32_t* keep_off, const uint8_t* keep,

@@ -73,6 +73,24 @@ struct GemmArgs {
 int launch_gemm(drb_ctx* ctx, int layout, int epi, const GemmArgs& a, int* n_mtiles_out = nullptr,
                 int* n_blocks_out = nullptr);
 
+// ------------------------------------------------------------------ umma.cu (tcgen05 / TMA / TMEM path)
+struct UmmaOperands {
+  const float* a_hi; const float* a_lo; int lda;   // K-major: A[m][k]; MN-major: G[k][m]
+  const float* b_hi; const float* b_lo; int ldb;   // B[n][k], k contiguous
+  int b_rows;                                       // rows of B that exist in memory (>= logical N is fine)
+};
+bool umma_available();
+// src [rows][ld] -> tf32 hi / lo split, optionally also transposed ([cols..][ldt]); ones_row >= 0 sets that
+// transposed row to 1 (constant feature used to fold the output-bias gradient into the dW' GEMM)
+int launch_split_tf32(drb_ctx* ctx, const float* src, int rows, int cols, int ld, float* hi, float* lo, float* t_hi,
+                      float* t_lo, int ldt, int ones_row);
+int launch_umma_cdae_loss(drb_ctx* ctx, const UmmaOperands& o, int M, int N, int Kred, float* dz_hi, float* dz_lo,
+                          int ldc, const float* bias, const float* label_count, const uint32_t* label_bits,
+                          int words_per_row, int loss_kind, float inv_count, int batch, float* loss_part,
+                          int* n_blocks_out);
+int launch_umma_store(drb_ctx* ctx, const UmmaOperands& o, bool a_mn_major, int M, int N, int Kred, int splits,
+                      float* C, int ldc, int n_store, float* extra_col, int extra_col_index);
+
 // ------------------------------------------------------------------ optim.cu
 #define DRB_MAX_SEGS 40
 struct AdamSeg { int64_t off4, n4; float alpha, l2, regw; };

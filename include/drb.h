@@ -40,6 +40,7 @@ enum {
 enum { DRB_LOSS_BCE = 0, DRB_LOSS_MSE = 1 };
 enum { DRB_LABEL_BATCH_MEAN = 0, DRB_LABEL_PER_USER = 1 };
 enum { DRB_ACT_NONE = 0, DRB_ACT_SIGMOID = 1, DRB_ACT_RELU = 2 };
+enum { DRB_GEMM_AUTO = 0, DRB_GEMM_FFMA = 1, DRB_GEMM_TCGEN05 = 2 };
 
 typedef struct drb_ctx drb_ctx;
 typedef struct drb_rng drb_rng;
@@ -143,6 +144,7 @@ typedef struct {
   void* workspace;             /* device, >= drb_cdae_workspace_bytes(...) */
   int64_t workspace_bytes;
   int32_t max_batch;
+  int32_t gemm_path;           /* DRB_GEMM_AUTO (tcgen05 3xTF32 when hidden < 256), DRB_GEMM_FFMA, DRB_GEMM_TCGEN05 */
 } drb_cdae_desc;
 
 typedef struct {
