@@ -128,6 +128,23 @@ int drb_ctx_profile_read(drb_ctx* ctx, char* names, int64_t names_cap, double* t
   return DRB_OK;
 }
 
+int drb_debug_split_tf32(drb_ctx* ctx, const float* src, int32_t rows, int32_t cols, int32_t ld, float* hi, float* lo,
+                         float* t_hi, float* t_lo, int32_t ldt, int32_t ones_row) {
+  if (!ctx || !src) return drb_fail(DRB_E_INVALID, "drb_debug_split_tf32: NULL argument");
+  return launch_split_tf32(ctx, src, rows, cols, ld, hi, lo, t_hi, t_lo, ldt, ones_row);
+}
+
+int drb_debug_umma_gemm(drb_ctx* ctx, const float* a_hi, const float* a_lo, int32_t lda, const float* b_hi,
+                        const float* b_lo, int32_t ldb, int32_t b_rows, int32_t a_mn_major, int32_t M, int32_t N,
+                        int32_t Kred, int32_t splits, float* C, int32_t ldc, int32_t n_store, float* extra_col,
+                        int32_t extra_col_index) {
+  if (!ctx || !a_hi || !a_lo || !b_hi || !b_lo || !C) return drb_fail(DRB_E_INVALID, "drb_debug_umma_gemm: NULL argument");
+  if (!umma_available()) return drb_fail(DRB_E_NODEVICE, "tcgen05/TMA path unavailable");
+  UmmaOperands o{a_hi, a_lo, lda, b_hi, b_lo, ldb, b_rows};
+  return launch_umma_store(ctx, o, a_mn_major != 0, M, N, Kred, splits, C, ldc, n_store, n_store, extra_col,
+                           extra_col_index);
+}
+
 }  // extern "C"
 
 // ========================================================================================== CDAE
@@ -345,11 +362,13 @@ int drb_cdae_step(drb_cdae* m, const int32_t* uids, const int32_t* keep_off, con
       return r;
     // dW'^T = dz^T h (I x K); the constant-one feature at column `hidden` yields db' = colsum(dz)
     UmmaOperands o2{w.dz, w.dz_lo, L.items_pad, w.hT_hi, w.hT_lo, bp, n2};
-    if ((r = launch_umma_store(ctx, o2, true, I, n2, batch, 1, G + L.off_w2t, ld, ld, G + L.off_b2, m->d.hidden)))
+    if ((r = launch_umma_store(ctx, o2, true, I, n2, batch, 1, G + L.off_w2t, ld, ld, m->d.hidden, G + L.off_b2,
+                               m->d.hidden)))
       return r;
     // dh = dz W'^T (B x K), split over the item range
     UmmaOperands o3{w.dz, w.dz_lo, L.items_pad, w.wT_hi, w.wT_lo, L.items_pad, n2};
-    if ((r = launch_umma_store(ctx, o3, false, batch, n2, I, m->splits, w.dh_part, ld, ld, nullptr, -1))) return r;
+    if ((r = launch_umma_store(ctx, o3, false, batch, n2, I, m->splits, w.dh_part, ld, ld, m->d.hidden, nullptr, -1)))
+      return r;
   } else {
   // 3. K2: z2 = h W'^T + b', p = sigmoid, loss terms, dL/dz2 (never materialises p)
   GemmArgs g1{};

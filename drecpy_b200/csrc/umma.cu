@@ -72,10 +72,13 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
 }
 
 // shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start>>4 [0,14), LBO>>4 [16,30), SBO>>4 [32,46),
-// version=1 [46,48), layout_type [61,64) (2 = SWIZZLE_128B)
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+// version=1 [46,48), layout_type [61,64): 2 = SWIZZLE_128B (K-major tiles), 1 = SWIZZLE_128B_BASE32B -- the only
+// layout the hardware accepts for MN-major 32-bit (tf32) operands: 128-byte rows swizzled in 32-byte units over
+// 4-row atoms (cute::UMMA::Layout_MN_SW128_32B_Atom, TMA CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes,
+                                              uint64_t layout_type = 2) {
   return (uint64_t)((saddr >> 4) & 0x3fff) | ((uint64_t)((lbo_bytes >> 4) & 0x3fff) << 16) |
-         ((uint64_t)((sbo_bytes >> 4) & 0x3fff) << 32) | (1ull << 46) | (2ull << 61);
+         ((uint64_t)((sbo_bytes >> 4) & 0x3fff) << 32) | (1ull << 46) | (layout_type << 61);
 }
 
 template <int BN>
@@ -91,7 +94,7 @@ struct UmmaParams {
   int M, N, Kred;           // logical problem; N <= BN * grid.x
   int splits;               // reduction split over blockIdx.z, partial z stored at C + z * M * ldc
   float* C; int ldc;        // EPI_STORE: C[m][n] for n < n_store
-  int n_store;
+  int n_store; int n_valid;  // columns in [n_valid, n_store) are written as 0 (row padding of C)
   float* extra_col; int extra_col_index;   // EPI_STORE: column `extra_col_index` of the product goes to extra_col[m]
   // EPI_CDAE_LOSS
   float* dz_hi; float* dz_lo;              // [M][ldc]
@@ -185,9 +188,10 @@ k_umma_gemm(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
 #pragma unroll
         for (int kk = 0; kk < BK / UMMA_K; kk++) {
           uint64_t a_hi, a_lo;
-          if (A_MN) {   // MN-major: 8 k-rows = one 1024-byte K atom; MN atoms (32 floats) are 4096 bytes apart
-            a_hi = make_desc(sa_hi + kk * 1024, 4096, 1024);
-            a_lo = make_desc(sa_lo + kk * 1024, 4096, 1024);
+          if (A_MN) {   // MN-major: rows = k (128 B = 32 m each); K atoms of 4 rows are 512 B apart, one MMA (K=8)
+                        // spans two of them; MN atoms (32 floats, one TMA box) are 4096 B apart
+            a_hi = make_desc(sa_hi + kk * 1024, 4096, 512, 1);
+            a_lo = make_desc(sa_lo + kk * 1024, 4096, 512, 1);
           } else {      // K-major: 8-row groups 1024 bytes apart; advance 32 bytes per UMMA_K inside the swizzle row
             a_hi = make_desc(sa_hi + kk * 32, 16, 1024);
             a_lo = make_desc(sa_lo + kk * 32, 16, 1024);
@@ -228,8 +232,10 @@ k_umma_gemm(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
           const int nn = n + j4 * 4;
           if (nn < p.n_store)   // n_store % 4 == 0
             *reinterpret_cast<float4*>(crow + nn) =
-                make_float4(__uint_as_float(r[j4 * 4]), __uint_as_float(r[j4 * 4 + 1]),
-                            __uint_as_float(r[j4 * 4 + 2]), __uint_as_float(r[j4 * 4 + 3]));
+                make_float4(nn + 0 < p.n_valid ? __uint_as_float(r[j4 * 4]) : 0.f,
+                            nn + 1 < p.n_valid ? __uint_as_float(r[j4 * 4 + 1]) : 0.f,
+                            nn + 2 < p.n_valid ? __uint_as_float(r[j4 * 4 + 2]) : 0.f,
+                            nn + 3 < p.n_valid ? __uint_as_float(r[j4 * 4 + 3]) : 0.f);
         }
         if (p.extra_col && p.extra_col_index >= n && p.extra_col_index < n + 16 && blockIdx.z == 0) {
 #pragma unroll
@@ -359,7 +365,7 @@ EncodeTiledFn get_encode() {
 
 // 2-D fp32 tensor [outer][inner] with row pitch `pitch_floats`; box {box_inner, box_outer}; 128-byte swizzle; OOB = 0
 int make_map(CUtensorMap* map, const float* ptr, int64_t inner, int64_t outer, int64_t pitch_floats, int box_inner,
-             int box_outer) {
+             int box_outer, bool atom32 = false) {
   EncodeTiledFn enc = get_encode();
   if (!enc) return drb_fail(DRB_E_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
   cuuint64_t dims[2] = {(cuuint64_t)inner, (cuuint64_t)outer};
@@ -367,7 +373,8 @@ int make_map(CUtensorMap* map, const float* ptr, int64_t inner, int64_t outer, i
   cuuint32_t box[2] = {(cuuint32_t)box_inner, (cuuint32_t)box_outer};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(ptr), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return drb_fail(DRB_E_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
   return DRB_OK;
@@ -378,8 +385,8 @@ int run_umma(drb_ctx* ctx, const UmmaOperands& o, const UmmaParams& p, int* n_bl
   CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
   int r;
   if (A_MN) {   // A given as G[k][m]
-    if ((r = make_map(&ma_hi, o.a_hi, p.M, p.Kred, o.lda, 32, 32))) return r;
-    if ((r = make_map(&ma_lo, o.a_lo, p.M, p.Kred, o.lda, 32, 32))) return r;
+    if ((r = make_map(&ma_hi, o.a_hi, p.M, p.Kred, o.lda, 32, 32, true))) return r;
+    if ((r = make_map(&ma_lo, o.a_lo, p.M, p.Kred, o.lda, 32, 32, true))) return r;
   } else {      // A given as G[m][k]
     if ((r = make_map(&ma_hi, o.a_hi, p.Kred, p.M, o.lda, BK, BM))) return r;
     if ((r = make_map(&ma_lo, o.a_lo, p.Kred, p.M, o.lda, BK, BM))) return r;
@@ -426,9 +433,9 @@ int launch_umma_cdae_loss(drb_ctx* ctx, const UmmaOperands& o, int M, int N, int
 }
 
 int launch_umma_store(drb_ctx* ctx, const UmmaOperands& o, bool a_mn_major, int M, int N, int Kred, int splits,
-                      float* C, int ldc, int n_store, float* extra_col, int extra_col_index) {
+                      float* C, int ldc, int n_store, int n_valid, float* extra_col, int extra_col_index) {
   UmmaParams p{};
-  p.M = M; p.N = N; p.Kred = Kred; p.splits = splits; p.C = C; p.ldc = ldc; p.n_store = n_store;
+  p.M = M; p.N = N; p.Kred = Kred; p.splits = splits; p.C = C; p.ldc = ldc; p.n_store = n_store; p.n_valid = n_valid;
   p.extra_col = extra_col; p.extra_col_index = extra_col_index;
   if (N > 256) return drb_fail(DRB_E_INVALID, "umma store GEMM: N must be <= 256 (hidden width)");
 #define DRB_UMMA_CASE(BN)                                                        \

@@ -240,6 +240,22 @@ int drb_dmf_rank_candidates(drb_dmf* m, const int32_t* uids, int32_t n, const in
                             const int32_t* cand_count, int32_t max_cand, int32_t novelty,
                             int32_t* out_iid, float* out_score, int32_t* n_out);
 
+/* ------------------------------------------------------------------ kernel-level test hooks (tests/ only)
+ * The tcgen05 GEMM building blocks of the CDAE step, exposed so that tests can check them in isolation against
+ * a float64 product.  All pointers are device pointers.
+ * drb_debug_split_tf32: src[rows][ld] -> hi/lo (same layout; may be NULL) and transposed t_hi/t_lo[cols][ldt]
+ * (may be NULL); ones_row >= 0 sets that transposed row to 1.
+ * drb_debug_umma_gemm: C[m][n] = sum_k A(m,k) B(n,k) as 3 TF32 products.  a_mn_major == 0: A stored [M][lda] (k
+ * contiguous); != 0: A stored [Kred][lda] (m contiguous).  B stored [b_rows][ldb] (k contiguous).  Partial z of a
+ * split reduction is written at C + z*M*ldc; columns >= n_store are dropped; column extra_col_index goes to
+ * extra_col[m] when extra_col != NULL. */
+int drb_debug_split_tf32(drb_ctx* ctx, const float* src, int32_t rows, int32_t cols, int32_t ld, float* hi, float* lo,
+                         float* t_hi, float* t_lo, int32_t ldt, int32_t ones_row);
+int drb_debug_umma_gemm(drb_ctx* ctx, const float* a_hi, const float* a_lo, int32_t lda, const float* b_hi,
+                        const float* b_lo, int32_t ldb, int32_t b_rows, int32_t a_mn_major, int32_t M, int32_t N,
+                        int32_t Kred, int32_t splits, float* C, int32_t ldc, int32_t n_store, float* extra_col,
+                        int32_t extra_col_index);
+
 /* ------------------------------------------------------------------ ranking_evaluation candidate generation
  * replaces: DRecPy/Evaluation/Processes/ranking_evaluation.py:108-116,163-219 -- per-user
  * random.Random(seed+idx), rng.sample of positives / negatives, randint generation of extra negatives,
