@@ -11,75 +11,11 @@
 // (one elected lane), warps 2..5 = epilogue (each owns the 32 TMEM lanes of its sub-partition).
 // Tile 128 x BN x 32 floats; operands are K-major [rows][32 floats] tiles in the canonical SWIZZLE_128B layout, or,
 // for the transposed use of dL/dz in dW' = dz^T h, MN-major tiles assembled from four 32x32 TMA boxes.
-#include <cuda.h>
-
-#include "kernels.h"
+#include "umma_common.cuh"
 
 namespace {
 
-constexpr int BM = 128, BK = 32, UMMA_K = 8;
 constexpr int THREADS = 192;
-constexpr float KERAS_EPS = 1e-7f;
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "WAIT_LOOP:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-      "@p bra WAIT_DONE;\n\t"
-      "bra WAIT_LOOP;\n\t"
-      "WAIT_DONE:\n\t"
-      "}\n" ::"r"(bar), "r"(parity)
-      : "memory");
-}
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
-      "l"(map), "r"(bar), "r"(c0), "r"(c1)
-      : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
-                                          uint32_t accumulate) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
-      "}\n" ::"r"(tmem_d),
-      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, "
-      "[%16];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-      : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
-
-// shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start>>4 [0,14), LBO>>4 [16,30), SBO>>4 [32,46),
-// version=1 [46,48), layout_type [61,64): 2 = SWIZZLE_128B (K-major tiles), 1 = SWIZZLE_128B_BASE32B -- the only
-// layout the hardware accepts for MN-major 32-bit (tf32) operands: 128-byte rows swizzled in 32-byte units over
-// 4-row atoms (cute::UMMA::Layout_MN_SW128_32B_Atom, TMA CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes,
-                                              uint64_t layout_type = 2) {
-  return (uint64_t)((saddr >> 4) & 0x3fff) | ((uint64_t)((lbo_bytes >> 4) & 0x3fff) << 16) |
-         ((uint64_t)((sbo_bytes >> 4) & 0x3fff) << 32) | (1ull << 46) | (layout_type << 61);
-}
 
 template <int BN>
 struct Smem {
@@ -87,7 +23,8 @@ struct Smem {
   static constexpr int A_BYTES = BM * BK * 4;           // one of A_hi / A_lo
   static constexpr int B_BYTES = BN * BK * 4;
   static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
-  static constexpr int TOTAL = STAGES * STAGE_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/;
+  static constexpr int TOTAL = STAGES * STAGE_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/ +
+                               2 * BN * 4 /*epilogue column constants*/;
 };
 
 struct UmmaParams {
@@ -210,6 +147,22 @@ k_umma_gemm(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
     // ------------------------------------------------------------------ epilogue (warps 2..5)
     const int q = warp & 3;                       // TMEM sub-partition of this warp
     const int m = m0 + q * 32 + lane;             // one accumulator row per thread
+    float* s_bias = reinterpret_cast<float*>(smem_raw + (bars + 256u - smem_u32(smem_raw)));
+    float* s_tgt = s_bias + BN;
+    uint32_t lbits[(BN + 31) / 32];
+    if (EPI == EPI_CDAE_LOSS) {
+      // per-column constants of this tile, fetched once while the main loop runs (b' and the batch-mean label)
+      for (int c = threadIdx.x - 64; c < BN; c += 128) {
+        const int nn = n0 + c;
+        s_bias[c] = (nn < p.N) ? __ldg(p.bias + nn) : 0.f;
+        s_tgt[c] = (p.label_count && nn < p.N) ? __ldg(p.label_count + nn) / (float)p.batch : 0.f;
+      }
+#pragma unroll
+      for (int wi = 0; wi < (BN + 31) / 32; wi++)
+        lbits[wi] = (p.label_bits && m < p.M && (n0 >> 5) + wi < p.words_per_row)
+                        ? __ldg(p.label_bits + (int64_t)m * p.words_per_row + (n0 >> 5) + wi) : 0u;
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+    }
     mbar_wait(tmem_full_bar, 0);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     float loss_local = 0.f;
@@ -244,16 +197,19 @@ k_umma_gemm(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
         }
       } else {  // EPI_CDAE_LOSS: z2 -> p -> loss term and dL/dz2, written as the hi/lo split the backward GEMMs read
         float hi[16], lo[16];
+        uint32_t wcur = 0;   // per-user label bits of this 16-column chunk (one 32-bit word covers it)
+#pragma unroll
+        for (int wi = 0; wi < (BN + 31) / 32; wi++)
+          if ((c >> 5) == wi) wcur = lbits[wi];
+        wcur >>= (c & 31);
 #pragma unroll
         for (int j = 0; j < 16; j++) {
           const int nn = n + j;
           float g = 0.f;
           if (nn < p.N) {
-            const float z = __uint_as_float(r[j]) + __ldg(p.bias + nn);
-            const float pr = 1.0f / (1.0f + __expf(-z));
-            float tgt;
-            if (p.label_count) tgt = __ldg(p.label_count + nn) / (float)p.batch;
-            else tgt = (float)((p.label_bits[(int64_t)m * p.words_per_row + (nn >> 5)] >> (nn & 31)) & 1u);
+            const float z = __uint_as_float(r[j]) + s_bias[c + j];
+            const float pr = __frcp_rn(1.0f + __expf(-z));
+            const float tgt = p.label_count ? s_tgt[c + j] : (float)((wcur >> j) & 1u);
             float dp;
             if (p.loss_kind == DRB_LOSS_BCE) {
               const float one_m = 1.0f - KERAS_EPS;
@@ -305,13 +261,6 @@ k_umma_gemm(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
 }
 
 // ------------------------------------------------------------------------------------------ operand preparation
-__device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
-  uint32_t h;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(x));
-  hi = __uint_as_float(h);
-  lo = x - hi;
-}
-
 // src [rows][ld] -> hi/lo [rows][ld] and, optionally, transposed hi/lo [ld_t rows >= cols][ldt] (tile transpose)
 __global__ void __launch_bounds__(256) k_split_tf32(const float* __restrict__ src, int rows, int cols, int ld,
                                                    float* __restrict__ hi, float* __restrict__ lo,
@@ -345,39 +294,6 @@ __global__ void __launch_bounds__(256) k_split_tf32(const float* __restrict__ sr
       t_lo[(int64_t)c * ldt + r] = 0.0f;
     }
   }
-}
-
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-EncodeTiledFn get_encode() {
-  static EncodeTiledFn fn = nullptr;
-  if (!fn) {
-    void* sym = nullptr;
-    cudaDriverEntryPointQueryResult qres;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) == cudaSuccess &&
-        qres == cudaDriverEntryPointSuccess)
-      fn = reinterpret_cast<EncodeTiledFn>(sym);
-  }
-  return fn;
-}
-
-// 2-D fp32 tensor [outer][inner] with row pitch `pitch_floats`; box {box_inner, box_outer}; 128-byte swizzle; OOB = 0
-int make_map(CUtensorMap* map, const float* ptr, int64_t inner, int64_t outer, int64_t pitch_floats, int box_inner,
-             int box_outer, bool atom32 = false) {
-  EncodeTiledFn enc = get_encode();
-  if (!enc) return drb_fail(DRB_E_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
-  cuuint64_t dims[2] = {(cuuint64_t)inner, (cuuint64_t)outer};
-  cuuint64_t strides[1] = {(cuuint64_t)pitch_floats * 4};
-  cuuint32_t box[2] = {(cuuint32_t)box_inner, (cuuint32_t)box_outer};
-  cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(ptr), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
-                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) return drb_fail(DRB_E_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
-  return DRB_OK;
 }
 
 template <int BN, bool A_MN, int EPI>
@@ -419,17 +335,6 @@ int launch_split_tf32(drb_ctx* ctx, const float* src, int rows, int cols, int ld
   k_split_tf32<<<grid, 256, 0, ctx->stream>>>(src, rows, cols, ld, hi, lo, t_hi, t_lo, ldt, ones_row);
   DRB_LAUNCH_CHECK(ctx, "k_split_tf32");
   return DRB_OK;
-}
-
-int launch_umma_cdae_loss(drb_ctx* ctx, const UmmaOperands& o, int M, int N, int Kred, float* dz_hi, float* dz_lo,
-                          int ldc, const float* bias, const float* label_count, const uint32_t* label_bits,
-                          int words_per_row, int loss_kind, float inv_count, int batch, float* loss_part,
-                          int* n_blocks_out) {
-  UmmaParams p{};
-  p.M = M; p.N = N; p.Kred = Kred; p.splits = 1; p.ldc = ldc; p.dz_hi = dz_hi; p.dz_lo = dz_lo; p.bias = bias;
-  p.label_count = label_count; p.label_bits = label_bits; p.words_per_row = words_per_row; p.loss_kind = loss_kind;
-  p.inv_count = inv_count; p.batch = batch; p.loss_part = loss_part;
-  return run_umma<128, false, EPI_CDAE_LOSS>(ctx, o, p, n_blocks_out);
 }
 
 int launch_umma_store(drb_ctx* ctx, const UmmaOperands& o, bool a_mn_major, int M, int N, int Kred, int splits,

@@ -1,0 +1,273 @@
+// K2 on the tensor cores, persistent form: z2 = h W'^T (3xTF32 tcgen05.mma, TMA-fed) with the fused
+// b' + sigmoid + Keras BCE/MSE + dL/dz2 epilogue of the CDAE training step.
+//
+// Replaces (reference, DRecPy/): Recommender/cdae.py:76 (tf.matmul(hidden, W_) + b_ + sigmoid) and cdae.py:78-79
+// (Keras loss on the (B,B,I) broadcast == batch-mean labels) plus d(loss)/d(z2) of tape.gradient.
+// p is never written to memory; the epilogue emits dL/dz2 already split into tf32 hi/lo for the backward GEMMs.
+//
+// One CTA per SM loops over output tiles (m fastest, so co-running CTAs share the W' tile in L2).  The K extent is
+// short (hidden <= 255 -> <= 8 k-blocks), so per-tile set-up and the exposed epilogue dominated the one-tile-per-CTA
+// version; here the TMA producer runs ahead across tiles, the accumulator is double-buffered in TMEM
+// (2 x BN columns) and the 4 epilogue warps drain tile t while the MMA warp fills tile t+1.
+// Epilogue stores go through a per-warp shared-memory transpose so every global store instruction writes full
+// 128-byte lines.
+#include "umma_common.cuh"
+
+namespace {
+
+constexpr int LOSS_THREADS = 192;
+
+template <int BN>
+struct LossSmem {
+  static constexpr int STAGES = (BN <= 128) ? 3 : 2;
+  static constexpr int A_BYTES = BM * BK * 4;
+  static constexpr int B_BYTES = BN * BK * 4;
+  static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
+  static constexpr int BAR_BYTES = 256;
+  static constexpr int CONST_BYTES = 2 * BN * 4;            // b' and batch-mean target of the current tile
+  static constexpr int XPOSE_BYTES = 4 * 32 * 33 * 4;       // one 32x32 (+1 pad) fp32 transpose buffer per epilogue warp
+  static constexpr int TOTAL = STAGES * STAGE_BYTES + 1024 + BAR_BYTES + CONST_BYTES + XPOSE_BYTES;
+};
+
+struct LossParams {
+  int M, N, Kred;                          // batch, n_items, hidden (padded to 4)
+  float* dz_hi; float* dz_lo; int ldc;     // [M][ldc]
+  const float* bias;                       // b' [N]
+  const float* label_count; const uint32_t* label_bits; int words_per_row;
+  int loss_kind; float inv_count; int batch;
+  float* loss_part;                        // [gridDim.x]
+  int m_tiles, n_tiles;
+};
+
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+
+template <int BN>
+__global__ void __launch_bounds__(LOSS_THREADS, 1)
+k_umma_cdae_loss(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
+                 const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
+                 LossParams p) {
+  using S = LossSmem<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  const uint32_t bars = base + S::STAGES * S::STAGE_BYTES;
+  auto full_bar = [&](int s) { return bars + 8u * s; };
+  auto empty_bar = [&](int s) { return bars + 8u * (S::STAGES + s); };
+  auto tfull_bar = [&](int a) { return bars + 8u * (2 * S::STAGES + a); };
+  auto tempty_bar = [&](int a) { return bars + 8u * (2 * S::STAGES + 2 + a); };
+  const uint32_t tmem_ptr_addr = bars + 8u * (2 * S::STAGES + 4);
+  volatile uint32_t* tmem_ptr_generic = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_ptr_addr - raw));
+  volatile float* lred = reinterpret_cast<volatile float*>(smem_raw + (bars + 8u * (2 * S::STAGES + 5) - raw));
+  float* s_bias = reinterpret_cast<float*>(smem_raw + (bars + S::BAR_BYTES - raw));
+  float* s_tgt = s_bias + BN;
+  float* s_xpose = s_tgt + BN;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nkb = (p.Kred + BK - 1) / BK;
+  const int n_tiles_total = p.m_tiles * p.n_tiles;
+  constexpr uint32_t TMEM_COLS = (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < S::STAGES; s++) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int a = 0; a < 2; a++) {
+      mbar_init(tfull_bar(a), 1);
+      mbar_init(tempty_bar(a), 4);     // one arrival per epilogue warp
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_ptr_addr), "r"(TMEM_COLS));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_ptr_generic;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer (runs ahead across tiles)
+    if (lane == 0) {
+      int it = 0;
+      for (int t = blockIdx.x; t < n_tiles_total; t += gridDim.x) {
+        const int m0 = (t % p.m_tiles) * BM, n0 = (t / p.m_tiles) * BN;
+        for (int kb = 0; kb < nkb; kb++, it++) {
+          const int s = it % S::STAGES;
+          const uint32_t ph = (it / S::STAGES) & 1;
+          mbar_wait(empty_bar(s), ph ^ 1);
+          mbar_expect_tx(full_bar(s), S::STAGE_BYTES);
+          const uint32_t sa_hi = base + s * S::STAGE_BYTES, sa_lo = sa_hi + S::A_BYTES;
+          const uint32_t sb_hi = sa_lo + S::A_BYTES, sb_lo = sb_hi + S::B_BYTES;
+          tma_load_2d(sa_hi, &map_a_hi, full_bar(s), kb * BK, m0);
+          tma_load_2d(sa_lo, &map_a_lo, full_bar(s), kb * BK, m0);
+          tma_load_2d(sb_hi, &map_b_hi, full_bar(s), kb * BK, n0);
+          tma_load_2d(sb_lo, &map_b_lo, full_bar(s), kb * BK, n0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+      int it = 0, tl = 0;
+      for (int t = blockIdx.x; t < n_tiles_total; t += gridDim.x, tl++) {
+        const int as = tl & 1;
+        mbar_wait(tempty_bar(as), ((tl >> 1) & 1) ^ 1);     // epilogue has drained this accumulator
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t tacc = tmem_base + (uint32_t)(as * BN);
+        for (int kb = 0; kb < nkb; kb++, it++) {
+          const int s = it % S::STAGES;
+          mbar_wait(full_bar(s), (it / S::STAGES) & 1);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t sa_hi = base + s * S::STAGE_BYTES, sa_lo = sa_hi + S::A_BYTES;
+          const uint32_t sb_hi = sa_lo + S::A_BYTES, sb_lo = sb_hi + S::B_BYTES;
+#pragma unroll
+          for (int kk = 0; kk < BK / UMMA_K; kk++) {
+            const uint64_t a_hi = make_desc(sa_hi + kk * 32, 16, 1024), a_lo = make_desc(sa_lo + kk * 32, 16, 1024);
+            const uint64_t b_hi = make_desc(sb_hi + kk * 32, 16, 1024), b_lo = make_desc(sb_lo + kk * 32, 16, 1024);
+            umma_tf32(tacc, a_lo, b_hi, idesc, (kb | kk) != 0);
+            umma_tf32(tacc, a_hi, b_lo, idesc, 1u);
+            umma_tf32(tacc, a_hi, b_hi, idesc, 1u);
+          }
+          umma_commit(empty_bar(s));
+        }
+        umma_commit(tfull_bar(as));
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue warps 2..5
+    const int q = warp & 3;
+    float* xp = s_xpose + q * (32 * 33);
+    float loss_local = 0.f;
+    int tl = 0;
+    for (int t = blockIdx.x; t < n_tiles_total; t += gridDim.x, tl++) {
+      const int m0 = (t % p.m_tiles) * BM, n0 = (t / p.m_tiles) * BN;
+      const int as = tl & 1;
+      const int m = m0 + q * 32 + lane;
+      // per-column constants of this tile (the previous tile's readers are done: barrier first)
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      for (int c = threadIdx.x - 64; c < BN; c += 128) {
+        const int nn = n0 + c;
+        s_bias[c] = (nn < p.N) ? __ldg(p.bias + nn) : 0.f;
+        s_tgt[c] = (p.label_count && nn < p.N) ? __ldg(p.label_count + nn) / (float)p.batch : 0.f;
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      mbar_wait(tfull_bar(as), (tl >> 1) & 1);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll 1
+      for (int c = 0; c < BN; c += 32) {
+        uint32_t r[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN + c), r);
+        uint32_t wcur = 0;     // per-user label bits of these 32 columns (n0 + c is a multiple of 32)
+        if (p.label_bits && m < p.M && ((n0 + c) >> 5) < p.words_per_row)
+          wcur = __ldg(p.label_bits + (int64_t)m * p.words_per_row + ((n0 + c) >> 5));
+        float lo[32];
+#pragma unroll
+        for (int j = 0; j < 32; j++) {
+          const int nn = n0 + c + j;
+          float g = 0.f;
+          if (nn < p.N && m < p.M) {
+            const float z = __uint_as_float(r[j]) + s_bias[c + j];
+            const float pr = __frcp_rn(1.0f + __expf(-z));
+            const float tgt = p.label_count ? s_tgt[c + j] : (float)((wcur >> j) & 1u);
+            float dp;
+            if (p.loss_kind == DRB_LOSS_BCE) {
+              const float one_m = 1.0f - KERAS_EPS;
+              const float pc = fminf(fmaxf(pr, KERAS_EPS), one_m);
+              const float da = pc + KERAS_EPS, db = 1.0f - pc + KERAS_EPS;
+              loss_local -= tgt * __logf(da) + (1.0f - tgt) * __logf(db);
+              const bool inside = (pr >= KERAS_EPS) && (pr <= one_m);
+              dp = inside ? -(tgt * db - (1.0f - tgt) * da) * __frcp_rn(da * db) * p.inv_count : 0.f;
+            } else {
+              if (p.label_count) loss_local += pr * pr - 2.0f * pr * tgt + tgt;
+              else loss_local += (pr - tgt) * (pr - tgt);
+              dp = 2.0f * (pr - tgt) * p.inv_count;
+            }
+            g = dp * pr * (1.0f - pr);
+          }
+          float h;
+          split_tf32(g, h, lo[j]);
+          r[j] = __float_as_uint(h);
+        }
+        // transpose through shared memory: lane = row when writing, lane = column when reading -> every global
+        // store instruction covers one full 128-byte line of dz
+        const int ncol = n0 + c + lane;
+#pragma unroll
+        for (int half = 0; half < 2; half++) {
+          __syncwarp();
+#pragma unroll
+          for (int j = 0; j < 32; j++) xp[lane * 33 + j] = half ? lo[j] : __uint_as_float(r[j]);
+          __syncwarp();
+          float* dst = half ? p.dz_lo : p.dz_hi;
+          if (ncol < p.ldc) {
+#pragma unroll 8
+            for (int rr = 0; rr < 32; rr++) {
+              const int mm = m0 + q * 32 + rr;
+              if (mm < p.M) dst[(int64_t)mm * p.ldc + ncol] = xp[rr * 33 + lane];
+            }
+          }
+        }
+      }
+      // this warp has finished reading accumulator `as`
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(as));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) loss_local += __shfl_xor_sync(0xffffffffu, loss_local, o);
+    if (lane == 0) lred[q] = loss_local;
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+    if (warp == 2 && lane == 0) p.loss_part[blockIdx.x] = lred[0] + lred[1] + lred[2] + lred[3];
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS));
+  }
+}
+
+template <int BN>
+int run_loss(drb_ctx* ctx, const UmmaOperands& o, LossParams p, int* n_blocks_out) {
+  CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
+  int r;
+  if ((r = make_map(&ma_hi, o.a_hi, p.Kred, p.M, o.lda, BK, BM))) return r;
+  if ((r = make_map(&ma_lo, o.a_lo, p.Kred, p.M, o.lda, BK, BM))) return r;
+  if ((r = make_map(&mb_hi, o.b_hi, p.Kred, o.b_rows, o.ldb, BK, BN))) return r;
+  if ((r = make_map(&mb_lo, o.b_lo, p.Kred, o.b_rows, o.ldb, BK, BN))) return r;
+  p.m_tiles = (p.M + BM - 1) / BM;
+  p.n_tiles = (p.N + BN - 1) / BN;
+  const int grid = std::min(p.m_tiles * p.n_tiles, ctx->sm_count);
+  *n_blocks_out = grid;
+  auto kern = k_umma_cdae_loss<BN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, LossSmem<BN>::TOTAL);
+    if (e != cudaSuccess)
+      return drb_fail(DRB_E_CUDA, "cudaFuncSetAttribute(smem=%d) failed: %s", LossSmem<BN>::TOTAL, cudaGetErrorString(e));
+    attr_set = true;
+  }
+  drb_prof_scope prof_(ctx, "k_umma_cdae_loss");
+  kern<<<grid, LOSS_THREADS, LossSmem<BN>::TOTAL, ctx->stream>>>(ma_hi, ma_lo, mb_hi, mb_lo, p);
+  DRB_LAUNCH_CHECK(ctx, "k_umma_cdae_loss");
+  return DRB_OK;
+}
+
+}  // namespace
+
+int launch_umma_cdae_loss(drb_ctx* ctx, const UmmaOperands& o, int M, int N, int Kred, float* dz_hi, float* dz_lo,
+                          int ldc, const float* bias, const float* label_count, const uint32_t* label_bits,
+                          int words_per_row, int loss_kind, float inv_count, int batch, float* loss_part,
+                          int* n_blocks_out) {
+  LossParams p{};
+  p.M = M; p.N = N; p.Kred = Kred; p.ldc = ldc; p.dz_hi = dz_hi; p.dz_lo = dz_lo; p.bias = bias;
+  p.label_count = label_count; p.label_bits = label_bits; p.words_per_row = words_per_row; p.loss_kind = loss_kind;
+  p.inv_count = inv_count; p.batch = batch; p.loss_part = loss_part;
+  const char* env = getenv("DRB_LOSS_BN");
+  if (env && atoi(env) == 256) return run_loss<256>(ctx, o, p, n_blocks_out);
+  return run_loss<128>(ctx, o, p, n_blocks_out);
+}
