@@ -15,7 +15,8 @@
 
 namespace {
 
-constexpr int LOSS_THREADS = 192;
+constexpr int LOSS_EPI_WARPS = 8;                       // two per TMEM sub-partition, each takes half of the columns
+constexpr int LOSS_THREADS = 64 + 32 * LOSS_EPI_WARPS;
 
 template <int BN>
 struct LossSmem {
@@ -25,7 +26,7 @@ struct LossSmem {
   static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
   static constexpr int BAR_BYTES = 256;
   static constexpr int CONST_BYTES = 2 * BN * 4;            // b' and batch-mean target of the current tile
-  static constexpr int XPOSE_BYTES = 4 * 32 * 33 * 4;       // one 32x32 (+1 pad) fp32 transpose buffer per epilogue warp
+  static constexpr int XPOSE_BYTES = LOSS_EPI_WARPS * 32 * 32 * 4;   // one XOR-swizzled 32x32 fp32 transpose buffer per epilogue warp
   static constexpr int TOTAL = STAGES * STAGE_BYTES + 1024 + BAR_BYTES + CONST_BYTES + XPOSE_BYTES;
 };
 
@@ -43,7 +44,7 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 
-template <int BN>
+template <int BN, int LOSS, bool PER_USER>
 __global__ void __launch_bounds__(LOSS_THREADS, 1)
 k_umma_cdae_loss(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                  const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
@@ -76,7 +77,7 @@ k_umma_cdae_loss(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
     }
     for (int a = 0; a < 2; a++) {
       mbar_init(tfull_bar(a), 1);
-      mbar_init(tempty_bar(a), 4);     // one arrival per epilogue warp
+      mbar_init(tempty_bar(a), LOSS_EPI_WARPS);     // one arrival per epilogue warp
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -139,76 +140,75 @@ k_umma_cdae_loss(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
       }
     }
   } else {
-    // ------------------------------------------------------------------ epilogue warps 2..5
-    const int q = warp & 3;
-    float* xp = s_xpose + q * (32 * 33);
+    // ------------------------------------------------------------------ epilogue warps 2..9
+    // warp w reads TMEM lanes 32*(w&3)..+31 (hardware sub-partition rule) and the column half (w-2)/4 of the tile
+    const int q = warp & 3, chalf = (warp - 2) >> 2;
+    const int ew = warp - 2;
+    float* xp = s_xpose + ew * (32 * 32);
     float loss_local = 0.f;
+    const float one_m = 1.0f - KERAS_EPS;
     int tl = 0;
     for (int t = blockIdx.x; t < n_tiles_total; t += gridDim.x, tl++) {
       const int m0 = (t % p.m_tiles) * BM, n0 = (t / p.m_tiles) * BN;
       const int as = tl & 1;
       const int m = m0 + q * 32 + lane;
+      const bool row_ok = m < p.M;
       // per-column constants of this tile (the previous tile's readers are done: barrier first)
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      for (int c = threadIdx.x - 64; c < BN; c += 128) {
+      asm volatile("bar.sync 1, %0;" ::"n"(32 * LOSS_EPI_WARPS) : "memory");
+      for (int c = threadIdx.x - 64; c < BN; c += 32 * LOSS_EPI_WARPS) {
         const int nn = n0 + c;
         s_bias[c] = (nn < p.N) ? __ldg(p.bias + nn) : 0.f;
-        s_tgt[c] = (p.label_count && nn < p.N) ? __ldg(p.label_count + nn) / (float)p.batch : 0.f;
+        s_tgt[c] = (!PER_USER && nn < p.N) ? __ldg(p.label_count + nn) / (float)p.batch : 0.f;
       }
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      asm volatile("bar.sync 1, %0;" ::"n"(32 * LOSS_EPI_WARPS) : "memory");
       mbar_wait(tfull_bar(as), (tl >> 1) & 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll 1
-      for (int c = 0; c < BN; c += 32) {
+      for (int c = chalf * (BN / 2); c < (chalf + 1) * (BN / 2); c += 32) {
         uint32_t r[32];
         tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN + c), r);
         uint32_t wcur = 0;     // per-user label bits of these 32 columns (n0 + c is a multiple of 32)
-        if (p.label_bits && m < p.M && ((n0 + c) >> 5) < p.words_per_row)
+        if (PER_USER && row_ok && ((n0 + c) >> 5) < p.words_per_row)
           wcur = __ldg(p.label_bits + (int64_t)m * p.words_per_row + ((n0 + c) >> 5));
         float lo[32];
+        // branch-free element math: 32 independent dependency chains the scheduler can interleave
 #pragma unroll
         for (int j = 0; j < 32; j++) {
-          const int nn = n0 + c + j;
-          float g = 0.f;
-          if (nn < p.N && m < p.M) {
-            const float z = __uint_as_float(r[j]) + s_bias[c + j];
-            const float pr = __frcp_rn(1.0f + __expf(-z));
-            const float tgt = p.label_count ? s_tgt[c + j] : (float)((wcur >> j) & 1u);
-            float dp;
-            if (p.loss_kind == DRB_LOSS_BCE) {
-              const float one_m = 1.0f - KERAS_EPS;
-              const float pc = fminf(fmaxf(pr, KERAS_EPS), one_m);
-              const float da = pc + KERAS_EPS, db = 1.0f - pc + KERAS_EPS;
-              loss_local -= tgt * __logf(da) + (1.0f - tgt) * __logf(db);
-              const bool inside = (pr >= KERAS_EPS) && (pr <= one_m);
-              dp = inside ? -(tgt * db - (1.0f - tgt) * da) * __frcp_rn(da * db) * p.inv_count : 0.f;
-            } else {
-              if (p.label_count) loss_local += pr * pr - 2.0f * pr * tgt + tgt;
-              else loss_local += (pr - tgt) * (pr - tgt);
-              dp = 2.0f * (pr - tgt) * p.inv_count;
-            }
-            g = dp * pr * (1.0f - pr);
+          const bool ok = row_ok && (n0 + c + j < p.N);
+          const float z = __uint_as_float(r[j]) + s_bias[c + j];
+          const float pr = __fdividef(1.0f, 1.0f + __expf(-z));
+          const float tgt = PER_USER ? (float)((wcur >> j) & 1u) : s_tgt[c + j];
+          float dp, lt;
+          if (LOSS == DRB_LOSS_BCE) {
+            const float pc = fminf(fmaxf(pr, KERAS_EPS), one_m);
+            const float da = pc + KERAS_EPS, db = 1.0f - pc + KERAS_EPS;
+            lt = -(tgt * __logf(da) + (1.0f - tgt) * __logf(db));
+            const bool inside = (pr >= KERAS_EPS) && (pr <= one_m);
+            dp = inside ? ((1.0f - tgt) * da - tgt * db) * __fdividef(p.inv_count, da * db) : 0.f;
+          } else {
+            lt = PER_USER ? (pr - tgt) * (pr - tgt) : (pr * pr - 2.0f * pr * tgt + tgt);
+            dp = 2.0f * (pr - tgt) * p.inv_count;
           }
+          loss_local += ok ? lt : 0.f;
+          const float g = ok ? dp * pr * (1.0f - pr) : 0.f;
           float h;
           split_tf32(g, h, lo[j]);
           r[j] = __float_as_uint(h);
         }
-        // transpose through shared memory: lane = row when writing, lane = column when reading -> every global
-        // store instruction covers one full 128-byte line of dz
+        // transpose through shared memory (XOR-swizzled 32x32): lane = row when writing, lane = column when
+        // reading, so every global store instruction covers one full 128-byte line of dz
         const int ncol = n0 + c + lane;
 #pragma unroll
         for (int half = 0; half < 2; half++) {
           __syncwarp();
 #pragma unroll
-          for (int j = 0; j < 32; j++) xp[lane * 33 + j] = half ? lo[j] : __uint_as_float(r[j]);
+          for (int j = 0; j < 32; j++) xp[lane * 32 + (j ^ lane)] = half ? lo[j] : __uint_as_float(r[j]);
           __syncwarp();
-          float* dst = half ? p.dz_lo : p.dz_hi;
+          float* dst = (half ? p.dz_lo : p.dz_hi) + (int64_t)(m0 + q * 32) * p.ldc + ncol;
           if (ncol < p.ldc) {
-#pragma unroll 8
-            for (int rr = 0; rr < 32; rr++) {
-              const int mm = m0 + q * 32 + rr;
-              if (mm < p.M) dst[(int64_t)mm * p.ldc + ncol] = xp[rr * 33 + lane];
-            }
+#pragma unroll
+            for (int rr = 0; rr < 32; rr++)
+              if (m0 + q * 32 + rr < p.M) dst[(int64_t)rr * p.ldc] = xp[rr * 32 + (lane ^ rr)];
           }
         }
       }
@@ -219,9 +219,14 @@ k_umma_cdae_loss(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) loss_local += __shfl_xor_sync(0xffffffffu, loss_local, o);
-    if (lane == 0) lred[q] = loss_local;
-    asm volatile("bar.sync 1, 128;" ::: "memory");
-    if (warp == 2 && lane == 0) p.loss_part[blockIdx.x] = lred[0] + lred[1] + lred[2] + lred[3];
+    if (lane == 0) lred[ew] = loss_local;
+    asm volatile("bar.sync 1, %0;" ::"n"(32 * LOSS_EPI_WARPS) : "memory");
+    if (warp == 2 && lane == 0) {
+      float tot = 0.f;
+#pragma unroll
+      for (int i = 0; i < LOSS_EPI_WARPS; i++) tot += lred[i];
+      p.loss_part[blockIdx.x] = tot;
+    }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
@@ -231,7 +236,7 @@ k_umma_cdae_loss(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
   }
 }
 
-template <int BN>
+template <int BN, int LOSS, bool PER_USER>
 int run_loss(drb_ctx* ctx, const UmmaOperands& o, LossParams p, int* n_blocks_out) {
   CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
   int r;
@@ -243,7 +248,7 @@ int run_loss(drb_ctx* ctx, const UmmaOperands& o, LossParams p, int* n_blocks_ou
   p.n_tiles = (p.N + BN - 1) / BN;
   const int grid = std::min(p.m_tiles * p.n_tiles, ctx->sm_count);
   *n_blocks_out = grid;
-  auto kern = k_umma_cdae_loss<BN>;
+  auto kern = k_umma_cdae_loss<BN, LOSS, PER_USER>;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, LossSmem<BN>::TOTAL);
@@ -267,7 +272,10 @@ int launch_umma_cdae_loss(drb_ctx* ctx, const UmmaOperands& o, int M, int N, int
   p.M = M; p.N = N; p.Kred = Kred; p.ldc = ldc; p.dz_hi = dz_hi; p.dz_lo = dz_lo; p.bias = bias;
   p.label_count = label_count; p.label_bits = label_bits; p.words_per_row = words_per_row; p.loss_kind = loss_kind;
   p.inv_count = inv_count; p.batch = batch; p.loss_part = loss_part;
-  const char* env = getenv("DRB_LOSS_BN");
-  if (env && atoi(env) == 256) return run_loss<256>(ctx, o, p, n_blocks_out);
-  return run_loss<128>(ctx, o, p, n_blocks_out);
+  const bool per_user = label_count == nullptr;
+  if (loss_kind == DRB_LOSS_BCE)
+    return per_user ? run_loss<128, DRB_LOSS_BCE, true>(ctx, o, p, n_blocks_out)
+                    : run_loss<128, DRB_LOSS_BCE, false>(ctx, o, p, n_blocks_out);
+  return per_user ? run_loss<128, DRB_LOSS_MSE, true>(ctx, o, p, n_blocks_out)
+                  : run_loss<128, DRB_LOSS_MSE, false>(ctx, o, p, n_blocks_out);
 }
