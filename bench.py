@@ -178,8 +178,10 @@ def run_native(args, cfg):
     B, K, W = cfg['batch'], args.steps, args.warmup
     m = drb.CDAE(hidden_factors=cfg['hidden'], corruption_level=cfg['q'], loss='bce', seed=cfg['seed'], verbose=False,
                  rng_mode='philox', device=str(dev))
+    from drecpy_b200.parallel import DataParallel
     m.fit(ds, epochs=0, batch_size=B, learning_rate=cfg['lr'], neg_ratio=cfg['neg_ratio'], reg_rate=cfg['reg'],
-          sampler=drb.PointSampler(ds, cfg['neg_ratio'], 1e-3, cfg['seed'] + rank), world=(dist, rank, world))
+          sampler=drb.PointSampler(ds, cfg['neg_ratio'], 1e-3, cfg['seed'] + rank),
+          data_parallel=DataParallel(dist), dp_sampler='independent')
 
     # ---- device-resident inputs for the `value` leg
     lib = _lib.load()
@@ -190,7 +192,7 @@ def run_native(args, cfg):
         off = np.zeros(B + 1, np.int32)
         _lib.check(lib.drb_batch_offsets(_lib.np_ptr(u), B, _lib.np_ptr(pos_indptr), _lib.np_ptr(off)))
         batches.append((torch.from_numpy(u.copy()).to(dev), torch.from_numpy(off).to(dev)))
-    loss_dev = torch.zeros(1, device=dev)
+    loss_dev = torch.zeros(2, device=dev)
 
     def barrier():
         if dist is not None:
@@ -212,7 +214,7 @@ def run_native(args, cfg):
     ms_total = e0.elapsed_time(e1)
     clock_info = clocks.stop()
     launches = m.launch_count() - launches0
-    loss_value = float(loss_dev.item())
+    loss_value = float(loss_dev[0].item())
     t = torch.tensor([ms_total], device=dev)
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)

@@ -21,6 +21,7 @@ import random
 import numpy as np
 
 from . import _lib
+from .parallel import DataParallel
 from .recommender import DeepRecommenderABC
 from .sampler import PointSampler
 
@@ -53,6 +54,9 @@ class CDAE(DeepRecommenderABC):
             raise RuntimeError('drecpy_b200 needs a CUDA device (sm_100a); there is no CPU fallback')
         self._dev = torch.device(self.device or f'cuda:{torch.cuda.current_device()}')
         self._max_batch = int(max(batch_size, min(1024, self.n_users), kwds.get('score_batch', 0)))
+        # data parallel over user mini-batches: batch_size is PER RANK, the step uses the global batch
+        self._dp = kwds.get('data_parallel') or DataParallel()
+        self._dp_sampler = kwds.get('dp_sampler', 'replay')
         self._alloc_and_init(kwds.get('init_weights', None))
         self._build_native()
         self._sampler = kwds.get('sampler') or PointSampler(self._data, neg_ratio, self.interaction_threshold, self.seed)
@@ -123,6 +127,10 @@ class CDAE(DeepRecommenderABC):
         d.gemm_path = _lib.DRB_GEMM[self.gemm]
         self._native = _lib.vp()
         _lib.check(lib.drb_cdae_create(self._ctx, C.byref(d), C.byref(self._native)))
+        ptr, cnt = _lib.vp(), _lib.i64()
+        _lib.check(lib.drb_cdae_label_count_buffer(self._native, C.byref(ptr), C.byref(cnt)))
+        off = ptr.value - self._workspace.data_ptr()
+        self._label_count = self._workspace[off:off + 4 * cnt.value].view(torch.float32)   # all-reduced when DP
 
     def _setup_staging(self, batch_size):
         torch = self._torch
@@ -178,12 +186,26 @@ class CDAE(DeepRecommenderABC):
             a.t[j] = 5 * (s - 1) + j + 1 if self.adam_t == 'per_variable' else s     # Q2
         a.philox_seed = self._mask_seed
         a.philox_step = s
+        dp = getattr(self, '_dp', None)
+        if dp is not None and dp.active:
+            a.global_batch = self._cur_batch * dp.world
+            a.slot_offset = self._cur_batch * dp.rank
         return a
 
     def prepare_batch(self, slot, batch_size):
         """Host side of one step: sample B triples (only uid is used, cdae.py:52) and build the mask inputs."""
         lib = _lib.load()
-        self._sampler.sample_arrays(batch_size, out=(slot['uid_np'], slot['iid'], slot['val']))
+        dp = self._dp
+        if dp.active and self._dp_sampler == 'replay':
+            # every rank replays the global stream and keeps its slice (== a single-process run with batch N*B)
+            gu, _, _ = self._sampler.sample_arrays(batch_size * dp.world)
+            lo, hi = dp.shard(batch_size * dp.world)
+            slot['uid_np'][:] = gu[lo:hi]
+            if self.rng_mode == 'mt19937':
+                raise NotImplementedError("data parallel training needs rng_mode='philox' (the MT19937 corruption "
+                                          "stream is sequential over the global batch)")
+        else:
+            self._sampler.sample_arrays(batch_size, out=(slot['uid_np'], slot['iid'], slot['val']))
         if self.rng_mode == 'mt19937':
             _lib.check(lib.drb_cdae_corruption_keep_mt(
                 self._mask_rng.handle, _lib.np_ptr(slot['uid_np']), batch_size, self.n_items,
@@ -202,6 +224,9 @@ class CDAE(DeepRecommenderABC):
             if slot['event'] is not None:
                 slot['event'].synchronize()          # the async H2D of the step that last used this slot is done
             keep_ptr = self.prepare_batch(slot, batch_size)
+            self._cur_batch = batch_size
+            if self._dp.active:
+                return self._train_step_dp(slot, batch_size, reg_rate, want_loss)
             args = self.step_args(reg_rate)
             loss_ptr = _lib.vp(self._loss_host.data_ptr()) if want_loss else None
             _lib.check(lib.drb_cdae_step_host(self._native, _lib.np_ptr(slot['uid_np']), _lib.np_ptr(slot['off_np']),
@@ -213,13 +238,44 @@ class CDAE(DeepRecommenderABC):
                 return None
             return float(self._loss_host[0])
 
+    def _train_step_dp(self, slot, batch_size, reg_rate, want_loss):
+        torch = self._torch
+        if not hasattr(self, '_dp_dev'):
+            self._dp_dev = {'uid': torch.empty(batch_size, dtype=torch.int32, device=self._dev),
+                            'off': torch.empty(batch_size + 1, dtype=torch.int32, device=self._dev),
+                            'loss': torch.zeros(2, dtype=torch.float32, device=self._dev)}
+        d = self._dp_dev
+        d['uid'].copy_(slot['uid'], non_blocking=True)
+        d['off'].copy_(slot['off'], non_blocking=True)
+        self._step -= 1                      # step_device advances it again
+        self.step_device(d['uid'], d['off'], None, reg_rate, d['loss'])
+        ev = torch.cuda.Event()
+        ev.record(self._stream)
+        slot['event'] = ev
+        if not want_loss:
+            return None
+        return float(self._dp.global_loss(d['loss']).item())
+
     def step_device(self, uids_dev, keep_off_dev, keep_dev, reg_rate, loss_dev):
-        """One step on device-resident inputs (torch tensors); keep_dev=None selects the philox mask."""
+        """One step on device-resident inputs (torch tensors); keep_dev=None selects the philox mask.
+        loss_dev: float32[2] device tensor ([0] reported loss, [1] its batch term of this rank)."""
         self._step += 1
+        self._cur_batch = uids_dev.numel()
         args = self.step_args(reg_rate)
-        _lib.check(_lib.load().drb_cdae_step(self._native, _lib.t_ptr(uids_dev), _lib.t_ptr(keep_off_dev),
-                                             _lib.t_ptr(keep_dev), uids_dev.numel(), C.byref(args),
-                                             _lib.t_ptr(loss_dev)))
+        lib = _lib.load()
+        ptrs = (self._native, _lib.t_ptr(uids_dev), _lib.t_ptr(keep_off_dev), _lib.t_ptr(keep_dev), uids_dev.numel(),
+                C.byref(args), _lib.t_ptr(loss_dev))
+        dp = getattr(self, '_dp', None)
+        if dp is None or not dp.active:
+            _lib.check(lib.drb_cdae_step(*ptrs))
+            return
+        # data parallel: PREP -> all-reduce label histogram -> GRADS -> all-reduce gradients -> UPDATE
+        _lib.check(lib.drb_cdae_step_phases(*ptrs, 1))
+        if self.label_mode == 'batch_mean':
+            dp.all_reduce_sum(self._label_count)
+        _lib.check(lib.drb_cdae_step_phases(*ptrs, 2))
+        dp.all_reduce_sum(self._grads)
+        _lib.check(lib.drb_cdae_step_phases(*ptrs, 4))
 
     def launch_count(self):
         return _lib.load().drb_ctx_launch_count(self._ctx)
@@ -311,7 +367,7 @@ class CDAE(DeepRecommenderABC):
     def __getstate__(self):
         st = {k: v for k, v in self.__dict__.items()
               if k not in ('_native', '_ctx', '_torch', '_workspace', '_slots', '_loss_host', '_stream', '_lock',
-                           '_mask_rng', '_sampler', '_d_indptr', '_d_indices', '_d_seen_indptr', '_d_seen_indices',
+                           '_mask_rng', '_sampler', '_dp', '_dp_dev', '_label_count', '_d_indptr', '_d_indices', '_d_seen_indptr', '_d_seen_indices',
                            '_logger', '_dev')}
         for k in ('_params', '_adam_m', '_adam_v', '_grads'):
             if k in st: st[k] = st[k].cpu()
@@ -327,6 +383,7 @@ class CDAE(DeepRecommenderABC):
         self._lock = threading.RLock()
         self._logger = logging.getLogger(f'{self.__class__.__name__}_CLOGGER')
         self._native = self._ctx = None
+        self._dp = DataParallel()
         if L is not None and self.fitted:
             import torch
             self._torch = torch

@@ -167,6 +167,7 @@ struct drb_cdae {
   int splits, words_per_row;
   int64_t keep_cap;
   bool use_umma;
+  int n_loss_blocks;
   int n2, batch_pad;   // tcgen05 path: N of the backward GEMMs (hidden + ones feature, rounded to 16), padded batch
 };
 
@@ -309,6 +310,18 @@ static int cdae_hidden_into(drb_cdae* m, const int32_t* uids, int n, const int32
 
 int drb_cdae_step(drb_cdae* m, const int32_t* uids, const int32_t* keep_off, const uint8_t* keep, int32_t batch,
                   const drb_cdae_step_args* a, float* loss_out) {
+  return drb_cdae_step_phases(m, uids, keep_off, keep, batch, a, loss_out, DRB_PHASE_ALL);
+}
+
+int drb_cdae_label_count_buffer(drb_cdae* m, float** ptr, int64_t* count) {
+  if (!m || !ptr || !count) return drb_fail(DRB_E_INVALID, "drb_cdae_label_count_buffer: NULL argument");
+  *ptr = m->ws.label_count;
+  *count = m->L.items_pad;
+  return DRB_OK;
+}
+
+int drb_cdae_step_phases(drb_cdae* m, const int32_t* uids, const int32_t* keep_off, const uint8_t* keep,
+                         int32_t batch, const drb_cdae_step_args* a, float* loss_out, int32_t phases) {
   if (!m || !uids || !keep_off || !a || !loss_out) return drb_fail(DRB_E_INVALID, "drb_cdae_step: NULL argument");
   if (batch <= 0 || batch > m->d.max_batch)
     return drb_fail(DRB_E_INVALID, "drb_cdae_step: batch %d outside (0, max_batch=%d]", batch, m->d.max_batch);
@@ -322,8 +335,14 @@ int drb_cdae_step(drb_cdae* m, const int32_t* uids, const int32_t* keep_off, con
   float* P = m->d.params;
   float* G = m->d.grads;
   const bool per_user = (m->d.label_mode == DRB_LABEL_PER_USER);
+  const int gbatch = a->global_batch > 0 ? a->global_batch : batch;   // data parallel: labels / loss / reg use it
+  if (gbatch < batch) return drb_fail(DRB_E_INVALID, "drb_cdae_step: global_batch %d < batch %d", gbatch, batch);
+  const uint8_t* keep_used = keep ? keep : w.keep;
+  if (m->d.corruption_level == 0.f) keep_used = nullptr;
+  const float s = (float)(1.0 / (1.0 - (double)m->d.corruption_level));
   int r;
 
+  if (phases & DRB_PHASE_PREP) {
   // 0. clear sparse-gradient regions [W | V | b | b2] (W2T's gradient is fully overwritten by the GEMM)
   DRB_CUDA_TRY(ctx, cudaMemsetAsync(G + L.off_w, 0, (size_t)(L.total - L.off_w) * sizeof(float), ctx->stream));
   if (per_user)
@@ -339,15 +358,15 @@ int drb_cdae_step(drb_cdae* m, const int32_t* uids, const int32_t* keep_off, con
   bp.words_per_row = m->words_per_row;
   bp.keep_out = keep ? nullptr : w.keep;
   bp.seed = a->philox_seed; bp.step = a->philox_step; bp.q = m->d.corruption_level;
+  bp.slot_offset = a->slot_offset;
   if ((r = launch_batch_prep(ctx, bp, batch))) return r;
-  const uint8_t* keep_used = keep ? keep : w.keep;
-  if (m->d.corruption_level == 0.f) keep_used = nullptr;
+  }  // PREP (data parallel: the caller all-reduces the label histogram here)
 
+  if (phases & DRB_PHASE_GRADS) {
   // 2. K1: h = sigmoid(s * sum_kept W[i] + V[u] + b)
-  const float s = (float)(1.0 / (1.0 - (double)m->d.corruption_level));
   if ((r = cdae_hidden_into(m, uids, batch, keep_off, keep_used, s, w.h))) return r;
 
-  const float inv_count = (float)(1.0 / ((double)batch * (double)I));
+  const float inv_count = (float)(1.0 / ((double)gbatch * (double)I));
   int n_blocks = 0;
   if (m->use_umma) {
     // 3-5 on the tensor cores (umma.cu): 3xTF32 split products, TMA-fed, TMEM accumulators
@@ -358,7 +377,7 @@ int drb_cdae_step(drb_cdae* m, const int32_t* uids, const int32_t* keep_off, con
     UmmaOperands o1{w.h_hi, w.h_lo, ld, w.w2t_hi, w.w2t_lo, ld, I};
     if ((r = launch_umma_cdae_loss(ctx, o1, batch, I, ld, w.dz, w.dz_lo, L.items_pad, P + L.off_b2,
                                    per_user ? nullptr : w.label_count, per_user ? w.label_bits : nullptr,
-                                   m->words_per_row, m->d.loss_kind, inv_count, batch, w.loss_part, &n_blocks)))
+                                   m->words_per_row, m->d.loss_kind, inv_count, gbatch, w.loss_part, &n_blocks)))
       return r;
     // dW'^T = dz^T h (I x K); the constant-one feature at column `hidden` yields db' = colsum(dz)
     UmmaOperands o2{w.dz, w.dz_lo, L.items_pad, w.hT_hi, w.hT_lo, bp, n2};
@@ -377,7 +396,7 @@ int drb_cdae_step(drb_cdae* m, const int32_t* uids, const int32_t* keep_off, con
   g1.bias = P + L.off_b2;
   g1.label_count = per_user ? nullptr : w.label_count;
   g1.label_bits = per_user ? w.label_bits : nullptr; g1.words_per_row = m->words_per_row;
-  g1.loss_kind = m->d.loss_kind; g1.inv_count = inv_count; g1.batch = batch;
+  g1.loss_kind = m->d.loss_kind; g1.inv_count = inv_count; g1.batch = gbatch;
   g1.loss_part = w.loss_part; g1.col_part = w.col_b2;
   int n_mtiles = 0;
   if ((r = launch_gemm(ctx, LAYOUT_KK, EPI_CDAE_LOSS, g1, &n_mtiles, &n_blocks))) return r;
@@ -405,12 +424,16 @@ int drb_cdae_step(drb_cdae* m, const int32_t* uids, const int32_t* keep_off, con
   sc.keep_off = keep_off; sc.keep = keep_used; sc.row_scale = nullptr; sc.scale = s;
   sc.d = w.dz1; sc.ld = ld; sc.gtable = G + L.off_w; sc.growbias = G + L.off_v;
   if ((r = launch_scatter(ctx, sc, batch))) return r;
+  m->n_loss_blocks = n_blocks;
+  }  // GRADS (data parallel: the caller all-reduces the gradient arena here)
 
+  if (!(phases & DRB_PHASE_UPDATE)) return DRB_OK;
+  const float inv_count_u = (float)(1.0 / ((double)gbatch * (double)I));
   // 7. K4: fused Adam + L2 over the arena; t per reference variable [W, W_, V, b, b_]
   AdamArgs ad{};
   ad.w = P; ad.m = m->d.adam_m; ad.v = m->d.adam_v; ad.g = G;
   ad.beta1 = a->beta1; ad.beta2 = a->beta2; ad.eps = a->epsilon;
-  const float c = a->reg_rate / (float)batch;                       // cdae.py:82
+  const float c = a->reg_rate / (float)gbatch;                      // cdae.py:82
   const int64_t offs[6] = {L.off_w2t, L.off_w, L.off_v, L.off_b, L.off_b2, L.total};
   const int tmap[5] = {1, 0, 2, 3, 4};
   for (int sidx = 0; sidx < 5; sidx++) {
@@ -425,7 +448,7 @@ int drb_cdae_step(drb_cdae* m, const int32_t* uids, const int32_t* keep_off, con
   int n_reg = 0;
   if ((r = launch_adam(ctx, ad, &n_reg))) return r;
   (void)U;
-  return launch_finalize_loss(ctx, w.loss_part, n_blocks, inv_count, w.reg_part, n_reg, loss_out);
+  return launch_finalize_loss(ctx, w.loss_part, m->n_loss_blocks, inv_count_u, w.reg_part, n_reg, loss_out);
 }
 
 int drb_cdae_step_host(drb_cdae* m, const int32_t* uids, const int32_t* keep_off, const uint8_t* keep,

@@ -39,6 +39,7 @@ struct BatchPrepArgs {
   int words_per_row;
   uint8_t* keep_out;       // may be NULL; philox keep bytes
   uint64_t seed, step; float q;
+  int slot_offset;         // global slot of local row 0 (data parallel), part of the philox counter
 };
 int launch_batch_prep(drb_ctx* ctx, const BatchPrepArgs& a, int n);
 

@@ -68,7 +68,10 @@ __global__ void __launch_bounds__(256) k_finalize_loss(const float* __restrict__
     }
     __syncthreads();
   }
-  if (threadIdx.x == 0) *loss_out = (float)(sa[0] * (double)scale) + (float)sb[0];
+  if (threadIdx.x == 0) {
+    loss_out[0] = (float)(sa[0] * (double)scale) + (float)sb[0];   // reported loss: batch term + regularisation
+    loss_out[1] = (float)(sa[0] * (double)scale);                  // batch term alone (summed over ranks when data parallel)
+  }
 }
 
 }  // namespace

@@ -173,7 +173,7 @@ __global__ void __launch_bounds__(128) k_batch_prep(BatchPrepArgs a) {
     if (a.count) atomicAdd(a.count + item, 1.0f);
     if (a.label_bits) atomicOr(a.label_bits + (int64_t)b * a.words_per_row + (item >> 5), 1u << (item & 31));
     if (a.keep_out) {
-      const uint32_t x = philox_first((uint32_t)item, (uint32_t)b, (uint32_t)a.step, (uint32_t)(a.step >> 32),
+      const uint32_t x = philox_first((uint32_t)item, (uint32_t)(b + a.slot_offset), (uint32_t)a.step, (uint32_t)(a.step >> 32),
                                       (uint32_t)a.seed, (uint32_t)(a.seed >> 32));
       const float u = (float)(x >> 8) * (1.0f / 16777216.0f);
       a.keep_out[koff + (j - lo)] = (u < a.q) ? 0 : 1;

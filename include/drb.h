@@ -153,16 +153,31 @@ typedef struct {
   int32_t t[5];            /* Adam step counter per variable [W, W_, V, b, b_] (Q2: 5(s-1)+j+1) */
   uint64_t philox_seed;    /* used only when keep == NULL */
   uint64_t philox_step;
+  int32_t global_batch;    /* data parallel: number of sampled users over all ranks (0 = batch) */
+  int32_t slot_offset;     /* data parallel: global batch slot of local row 0 (philox counter) */
 } drb_cdae_step_args;
+
+enum { DRB_PHASE_PREP = 1, DRB_PHASE_GRADS = 2, DRB_PHASE_UPDATE = 4, DRB_PHASE_ALL = 7 };
 
 int drb_cdae_create(drb_ctx* ctx, const drb_cdae_desc* desc, drb_cdae** out);
 int drb_cdae_destroy(drb_cdae* m);
 /* One training step on device-resident inputs.
  * replaces: recommender_abc.py:190-205 (tape, gradient, 5x apply_gradients) with cdae.py:50-82 inside.
  * uids[batch], keep_off[batch+1], keep[keep_off[batch]] are DEVICE pointers; keep == NULL selects the
- * counter-based mask (philox4x32-10 keyed by (seed, step, slot, item)).  loss_out: device float. */
+ * counter-based mask (philox4x32-10 keyed by (seed, step, slot, item)).  loss_out: device float[2]
+ * ([0] reported loss, [1] its batch term). */
 int drb_cdae_step(drb_cdae* m, const int32_t* uids, const int32_t* keep_off, const uint8_t* keep,
                   int32_t batch, const drb_cdae_step_args* args, float* loss_out);
+/* The same step in phases, for data parallelism over user mini-batches (one process per GPU, replicated weights):
+ *   PREP   -> label histogram of the local batch; the caller all-reduces drb_cdae_label_count_buffer()
+ *   GRADS  -> forward + backward with global_batch in the label mean / loss mean / L2 scale; the caller
+ *             all-reduces the gradient arena
+ *   UPDATE -> Adam + loss.  loss_out must hold TWO floats: [0] = batch term + regularisation, [1] = batch term of the
+ *             local shard (sum [1] over ranks and add [0]-[1] for the global reported loss).
+ * drb_cdae_step == all phases with loss_out[0..1]. */
+int drb_cdae_step_phases(drb_cdae* m, const int32_t* uids, const int32_t* keep_off, const uint8_t* keep,
+                         int32_t batch, const drb_cdae_step_args* args, float* loss_out, int32_t phases);
+int drb_cdae_label_count_buffer(drb_cdae* m, float** ptr, int64_t* count);
 /* Same step with HOST inputs: copies uids / keep_off / keep to the device (inside the call), runs the step,
  * and, if loss_host != NULL, copies the loss back and synchronises. */
 int drb_cdae_step_host(drb_cdae* m, const int32_t* uids, const int32_t* keep_off, const uint8_t* keep,
@@ -227,7 +242,8 @@ typedef struct {
 
 int drb_dmf_create(drb_ctx* ctx, const drb_dmf_desc* desc, drb_dmf** out);
 int drb_dmf_destroy(drb_dmf* m);
-/* replaces: recommender_abc.py:190-205 with dmf.py:64-99 inside.  uids/iids/labels: device [batch]. */
+/* replaces: recommender_abc.py:190-205 with dmf.py:64-99 inside.  uids/iids/labels: device [batch];
+ * loss_out: device float[2] ([0] reported loss, [1] its batch term). */
 int drb_dmf_step(drb_dmf* m, const int32_t* uids, const int32_t* iids, const float* labels, int32_t batch,
                  const drb_dmf_step_args* args, float* loss_out);
 int drb_dmf_step_host(drb_dmf* m, const int32_t* uids, const int32_t* iids, const float* labels, int32_t batch,

@@ -1,0 +1,70 @@
+"""Data-parallel CDAE step on 2 GPUs (NCCL) against the single-GPU step with the same global batch (P9)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(('127.0.0.1', 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _weights(U, I, K):
+    rng = np.random.default_rng(5)
+
+    def glorot(shape, fi, fo):
+        lim = np.sqrt(6.0 / (fi + fo))
+        return rng.uniform(-lim, lim, shape).astype(np.float32)
+    return {'W': glorot((I, K), I, K), 'W_': glorot((K, I), K, I), 'V': glorot((U, K), U, K),
+            'b': glorot((K,), K, K), 'b_': glorot((I,), I, I)}
+
+
+def _worker(rank, world, port, out):
+    import torch
+    import torch.distributed as dist
+    import drecpy_b200 as drb
+    from drecpy_b200.parallel import DataParallel
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group('nccl', rank=rank, world_size=world, device_id=torch.device(f'cuda:{rank}'))
+    U, I, K, B = 500, 900, 64, 96
+    u, i, v = drb.synthetic_interactions(U, I, 30000, seed=4)
+    ds = drb.InteractionData(u, i, v)
+    w = _weights(U, I, K)
+    m = drb.CDAE(hidden_factors=K, seed=10, verbose=False, rng_mode='philox', device=f'cuda:{rank}')
+    m.fit(ds, epochs=0, batch_size=B, init_weights=w, data_parallel=DataParallel(dist))
+    losses = []
+    for s in range(1, 7):
+        m._step = s
+        losses.append(m._train_step(B, 1e-3, want_loss=True))
+    if rank == 0:
+        ref = drb.CDAE(hidden_factors=K, seed=10, verbose=False, rng_mode='philox', device='cuda:0')
+        ref.fit(ds, epochs=0, batch_size=B * world, init_weights=w)
+        ref_losses = []
+        for s in range(1, 7):
+            ref._step = s
+            ref_losses.append(ref._train_step(B * world, 1e-3, want_loss=True))
+        np.savez(out, losses=losses, ref_losses=ref_losses, p=m._params.cpu().numpy(), p_ref=ref._params.cpu().numpy())
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_gpu_step_matches_single_gpu(tmp_path):
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip('needs 2 GPUs')
+    import torch.multiprocessing as mp
+    out = str(tmp_path / 'dp.npz')
+    mp.spawn(_worker, args=(2, _free_port(), out), nprocs=2, join=True)
+    r = np.load(out)
+    assert np.allclose(r['losses'], r['ref_losses'], rtol=1e-5), (r['losses'], r['ref_losses'])
+    scale = np.abs(r['p_ref']).max()
+    assert np.abs(r['p'] - r['p_ref']).max() < 2e-4 * scale

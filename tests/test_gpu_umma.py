@@ -47,11 +47,11 @@ def test_tcgen05_step_matches_ffma_and_oracle(U, I, K, B, nnz, label_mode, loss)
         losses = []
         for m in (m_tc, m_ff):
             m.corruption_level = 0.0
-            loss_dev = torch.zeros(1, device='cuda')
+            loss_dev = torch.zeros(2, device='cuda')
             d_u, d_o = torch.as_tensor(uids, device='cuda'), torch.as_tensor(off, device='cuda')
             # q=0.2 philox mask is identical in both models (same seed / step); compare them against each other
             m.step_device(d_u, d_o, None, 1e-3, loss_dev)
-            losses.append(loss_dev.item())
+            losses.append(loss_dev[0].item())
         assert abs(losses[0] - losses[1]) <= 2e-5 * abs(losses[1]), (step, losses)
         for name in ('W', 'V', 'b', 'b_'):
             a, b = getattr(m_tc, name).cpu().numpy(), getattr(m_ff, name).cpu().numpy()
