@@ -223,12 +223,12 @@ def run_native(args, cfg):
     # ---- e2e leg: the per-step body of fit(): host sampler -> pinned staging -> H2D -> step -> D2H loss
     for _ in range(2):
         m._step += 1
-        m._train_step(B, cfg['reg'], want_loss=True)
+        m._train_step(B, cfg['reg'], want_loss=True, prefetch=True)
     barrier()
     t0 = time.perf_counter()
     for _ in range(K):
         m._step += 1
-        loss_e2e = m._train_step(B, cfg['reg'], want_loss=True)
+        loss_e2e = m._train_step(B, cfg['reg'], want_loss=True, prefetch=True)   # exactly what fit() runs per epoch
     torch.cuda.synchronize()
     t_e2e = time.perf_counter() - t0
     te = torch.tensor([t_e2e], device=dev)
@@ -236,9 +236,8 @@ def run_native(args, cfg):
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     t_e2e = float(te.item())
 
-    if rank != 0:
-        return
-    # ---- roofline leg: per-kernel CUDA-event timing inside libdrb (separate pass, rank 0 only reports)
+    # ---- roofline leg: per-kernel CUDA-event timing inside libdrb (separate pass; every rank runs it because the
+    # step contains collectives, rank 0 reports)
     P = 5
     _lib.check(lib.drb_ctx_profile_enable(m._ctx, 1))
     for s in range(P):
@@ -246,6 +245,11 @@ def run_native(args, cfg):
         m.step_device(bt[0], bt[1], None, cfg['reg'], loss_dev)
     prof = _lib.profile_read(m._ctx)
     _lib.check(lib.drb_ctx_profile_enable(m._ctx, 0))
+    if rank != 0:
+        if dist is not None:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
     kernels = {k: round(v[0] / P, 4) for k, v in prof.items()}
     peaks = load_peaks()
     I, Hd, U = cfg['n_items'], cfg['hidden'], cfg['n_users']
@@ -278,6 +282,7 @@ def run_native(args, cfg):
             'loss_last': loss_value, 'loss_last_e2e': loss_e2e, 'data_gen_s': round(t_data, 1)}
     print(json.dumps(line), flush=True)
     if dist is not None:
+        dist.barrier()
         dist.destroy_process_group()
 
 

@@ -131,6 +131,12 @@ class CDAE(DeepRecommenderABC):
         _lib.check(lib.drb_cdae_label_count_buffer(self._native, C.byref(ptr), C.byref(cnt)))
         off = ptr.value - self._workspace.data_ptr()
         self._label_count = self._workspace[off:off + 4 * cnt.value].view(torch.float32)   # all-reduced when DP
+        _lib.check(lib.drb_cdae_loss_buffer(self._native, C.byref(ptr)))
+        off = ptr.value - self._workspace.data_ptr()
+        self._loss_dev = self._workspace[off:off + 8].view(torch.float32)
+        _lib.check(lib.drb_cdae_dz1_buffer(self._native, C.byref(ptr), C.byref(cnt)))
+        off = ptr.value - self._workspace.data_ptr()
+        self._dz1 = self._workspace[off:off + 4 * cnt.value].view(torch.float32).view(-1, L.ld)
 
     def _setup_staging(self, batch_size):
         torch = self._torch
@@ -146,7 +152,8 @@ class CDAE(DeepRecommenderABC):
             s['uid_np'], s['off_np'], s['keep_np'] = s['uid'].numpy(), s['off'].numpy(), s['keep'].numpy()
             self._slots.append(s)
         self._slot_idx = 0
-        self._loss_host = torch.zeros(1, dtype=torch.float32).pin_memory()
+        self._loss_host = torch.zeros(2, dtype=torch.float32).pin_memory()
+        self._next = None
 
     # ------------------------------------------------------------------ weights as reference-shaped views
     def _seg(self, off, rows, ld):
@@ -190,6 +197,7 @@ class CDAE(DeepRecommenderABC):
         if dp is not None and dp.active:
             a.global_batch = self._cur_batch * dp.world
             a.slot_offset = self._cur_batch * dp.rank
+            a.skip_user_grad = 1
         return a
 
     def prepare_batch(self, slot, batch_size):
@@ -216,26 +224,43 @@ class CDAE(DeepRecommenderABC):
                                          _lib.np_ptr(slot['off_np'])))
         return None
 
-    def _train_step(self, batch_size, reg_rate, want_loss=False, **kwds):
+    def _acquire_slot(self):
+        slot = self._slots[self._slot_idx]
+        self._slot_idx = (self._slot_idx + 1) % _RING
+        if slot['event'] is not None:
+            slot['event'].synchronize()          # the async H2D of the step that last used this slot is done
+        return slot
+
+    def _train_step(self, batch_size, reg_rate, want_loss=False, prefetch=False, **kwds):
+        """One optimizer step through the host-buffer C-ABI entry.  With prefetch=True the NEXT batch is sampled
+        and its mask built on the host while the GPU runs this step (the fit loop does this on every epoch but the
+        last, so the sampler streams end exactly where the reference's would)."""
         lib = _lib.load()
         with self._lock:
-            slot = self._slots[self._slot_idx]
-            self._slot_idx = (self._slot_idx + 1) % _RING
-            if slot['event'] is not None:
-                slot['event'].synchronize()          # the async H2D of the step that last used this slot is done
-            keep_ptr = self.prepare_batch(slot, batch_size)
+            nxt = getattr(self, '_next', None)
+            if nxt is not None and nxt[1] == batch_size:
+                slot, keep_ptr = nxt[0], nxt[2]
+            else:
+                slot = self._acquire_slot()
+                keep_ptr = self.prepare_batch(slot, batch_size)
+            self._next = None
             self._cur_batch = batch_size
             if self._dp.active:
                 return self._train_step_dp(slot, batch_size, reg_rate, want_loss)
             args = self.step_args(reg_rate)
-            loss_ptr = _lib.vp(self._loss_host.data_ptr()) if want_loss else None
             _lib.check(lib.drb_cdae_step_host(self._native, _lib.np_ptr(slot['uid_np']), _lib.np_ptr(slot['off_np']),
-                                              keep_ptr, batch_size, C.byref(args), loss_ptr))
+                                              keep_ptr, batch_size, C.byref(args), None))
+            if want_loss:
+                self._loss_host.copy_(self._loss_dev, non_blocking=True)
+            ev = self._torch.cuda.Event()
+            ev.record(self._stream)
+            slot['event'] = ev
+            if prefetch:
+                nslot = self._acquire_slot()
+                self._next = (nslot, batch_size, self.prepare_batch(nslot, batch_size))
             if not want_loss:
-                ev = self._torch.cuda.Event()
-                ev.record(self._stream)
-                slot['event'] = ev
                 return None
+            ev.synchronize()
             return float(self._loss_host[0])
 
     def _train_step_dp(self, slot, batch_size, reg_rate, want_loss):
@@ -274,7 +299,17 @@ class CDAE(DeepRecommenderABC):
         if self.label_mode == 'batch_mean':
             dp.all_reduce_sum(self._label_count)
         _lib.check(lib.drb_cdae_step_phases(*ptrs, 2))
-        dp.all_reduce_sum(self._grads)
+        # user-row gradients: all-gather the B x K rows (never the U x K table), add them locally
+        torch = self._torch
+        B = uids_dev.numel()
+        if not hasattr(self, '_dp_gather') or self._dp_gather[0].shape[0] != B * dp.world:
+            self._dp_gather = (torch.empty((B * dp.world, self._L.ld), dtype=torch.float32, device=self._dev),
+                               torch.empty(B * dp.world, dtype=torch.int32, device=self._dev))
+        rows_all, uids_all = self._dp_gather
+        dp.dist.all_gather_into_tensor(rows_all, self._dz1[:B], group=dp.group)
+        dp.dist.all_gather_into_tensor(uids_all, uids_dev, group=dp.group)
+        _lib.check(lib.drb_cdae_scatter_user_rows(self._native, _lib.t_ptr(uids_all), _lib.t_ptr(rows_all), B * dp.world))
+        dp.all_reduce_sum(self._grads[:self._L.off_v])       # W', W, b, b' gradients (dense)
         _lib.check(lib.drb_cdae_step_phases(*ptrs, 4))
 
     def launch_count(self):
@@ -367,7 +402,7 @@ class CDAE(DeepRecommenderABC):
     def __getstate__(self):
         st = {k: v for k, v in self.__dict__.items()
               if k not in ('_native', '_ctx', '_torch', '_workspace', '_slots', '_loss_host', '_stream', '_lock',
-                           '_mask_rng', '_sampler', '_dp', '_dp_dev', '_label_count', '_d_indptr', '_d_indices', '_d_seen_indptr', '_d_seen_indices',
+                           '_mask_rng', '_sampler', '_dp', '_dp_dev', '_dp_gather', '_label_count', '_dz1', '_loss_dev', '_next', '_d_indptr', '_d_indices', '_d_seen_indptr', '_d_seen_indices',
                            '_logger', '_dev')}
         for k in ('_params', '_adam_m', '_adam_v', '_grads'):
             if k in st: st[k] = st[k].cpu()

@@ -228,10 +228,10 @@ int drb_cdae_layout(int32_t n_users, int32_t n_items, int32_t hidden, drb_cdae_l
   out->items_pad = (int32_t)ip;
   out->off_w2t = 0;
   out->off_w = out->off_w2t + (int64_t)n_items * ld;
-  out->off_v = out->off_w + (int64_t)n_items * ld;
-  out->off_b = out->off_v + (int64_t)n_users * ld;
+  out->off_b = out->off_w + (int64_t)n_items * ld;
   out->off_b2 = out->off_b + ld;
-  out->total = out->off_b2 + ip;
+  out->off_v = out->off_b2 + ip;          // V last: everything before it is all-reduced densely when data parallel
+  out->total = out->off_v + (int64_t)n_users * ld;
   return DRB_OK;
 }
 
@@ -311,6 +311,24 @@ static int cdae_hidden_into(drb_cdae* m, const int32_t* uids, int n, const int32
 int drb_cdae_step(drb_cdae* m, const int32_t* uids, const int32_t* keep_off, const uint8_t* keep, int32_t batch,
                   const drb_cdae_step_args* a, float* loss_out) {
   return drb_cdae_step_phases(m, uids, keep_off, keep, batch, a, loss_out, DRB_PHASE_ALL);
+}
+
+int drb_cdae_loss_buffer(drb_cdae* m, float** ptr) {
+  if (!m || !ptr) return drb_fail(DRB_E_INVALID, "drb_cdae_loss_buffer: NULL argument");
+  *ptr = m->ws.loss_scalar;
+  return DRB_OK;
+}
+
+int drb_cdae_dz1_buffer(drb_cdae* m, float** ptr, int64_t* count) {
+  if (!m || !ptr || !count) return drb_fail(DRB_E_INVALID, "drb_cdae_dz1_buffer: NULL argument");
+  *ptr = m->ws.dz1;
+  *count = (int64_t)m->d.max_batch * m->L.ld;
+  return DRB_OK;
+}
+
+int drb_cdae_scatter_user_rows(drb_cdae* m, const int32_t* uids, const float* rows, int32_t n) {
+  if (!m || !uids || !rows || n < 0) return drb_fail(DRB_E_INVALID, "drb_cdae_scatter_user_rows: bad argument");
+  return launch_row_scatter(m->ctx, uids, rows, n, m->L.ld, m->d.grads + m->L.off_v);
 }
 
 int drb_cdae_label_count_buffer(drb_cdae* m, float** ptr, int64_t* count) {
@@ -422,7 +440,8 @@ int drb_cdae_step_phases(drb_cdae* m, const int32_t* uids, const int32_t* keep_o
   ScatterArgs sc{};
   sc.indptr = m->d.csr_indptr; sc.indices = m->d.csr_indices; sc.values = nullptr; sc.rows = uids;
   sc.keep_off = keep_off; sc.keep = keep_used; sc.row_scale = nullptr; sc.scale = s;
-  sc.d = w.dz1; sc.ld = ld; sc.gtable = G + L.off_w; sc.growbias = G + L.off_v;
+  sc.d = w.dz1; sc.ld = ld; sc.gtable = G + L.off_w;
+  sc.growbias = a->skip_user_grad ? nullptr : G + L.off_v;   // data parallel: user rows are exchanged instead
   if ((r = launch_scatter(ctx, sc, batch))) return r;
   m->n_loss_blocks = n_blocks;
   }  // GRADS (data parallel: the caller all-reduces the gradient arena here)
@@ -434,14 +453,15 @@ int drb_cdae_step_phases(drb_cdae* m, const int32_t* uids, const int32_t* keep_o
   ad.w = P; ad.m = m->d.adam_m; ad.v = m->d.adam_v; ad.g = G;
   ad.beta1 = a->beta1; ad.beta2 = a->beta2; ad.eps = a->epsilon;
   const float c = a->reg_rate / (float)gbatch;                      // cdae.py:82
-  const int64_t offs[6] = {L.off_w2t, L.off_w, L.off_v, L.off_b, L.off_b2, L.total};
-  const int tmap[5] = {1, 0, 2, 3, 4};
+  const int64_t offs[6] = {L.off_w2t, L.off_w, L.off_b, L.off_b2, L.off_v, L.total};   // arena order
+  const int tmap[5] = {1, 0, 3, 4, 2};                                                  // -> [W, W_, V, b, b_]
+  const bool l2seg[5] = {true, true, false, false, true};
   for (int sidx = 0; sidx < 5; sidx++) {
     ad.seg[sidx].off4 = offs[sidx] / 4;
     ad.seg[sidx].n4 = (offs[sidx + 1] - offs[sidx]) / 4;
     ad.seg[sidx].alpha = drb_adam_alpha(a->learning_rate, a->beta1, a->beta2, a->t[tmap[sidx]]);
-    ad.seg[sidx].l2 = (sidx < 3) ? c : 0.f;
-    ad.seg[sidx].regw = (sidx < 3) ? 0.5f * c : 0.f;
+    ad.seg[sidx].l2 = l2seg[sidx] ? c : 0.f;
+    ad.seg[sidx].regw = l2seg[sidx] ? 0.5f * c : 0.f;
   }
   ad.nseg = 5;
   ad.reg_part = w.reg_part;
@@ -768,6 +788,12 @@ int drb_dmf_step(drb_dmf* m, const int32_t* uids, const int32_t* iids, const flo
   int n_reg = 0;
   if ((r = launch_adam(ctx, ad, &n_reg))) return r;
   return launch_finalize_loss(ctx, m->loss_part, batch, 1.0f / (float)batch, m->reg_part, n_reg, loss_out);
+}
+
+int drb_dmf_loss_buffer(drb_dmf* m, float** ptr) {
+  if (!m || !ptr) return drb_fail(DRB_E_INVALID, "drb_dmf_loss_buffer: NULL argument");
+  *ptr = m->loss_scalar;
+  return DRB_OK;
 }
 
 int drb_dmf_step_host(drb_dmf* m, const int32_t* uids, const int32_t* iids, const float* labels, int32_t batch,

@@ -31,6 +31,9 @@ struct ScatterArgs {
 };
 int launch_scatter(drb_ctx* ctx, const ScatterArgs& a, int n);
 
+// gtable[ids[r]] += rows[r]  (one warp per row, vector atomics) -- data-parallel exchange of the user-row gradients
+int launch_row_scatter(drb_ctx* ctx, const int32_t* ids, const float* rows, int n, int ld, float* gtable);
+
 // per batch row: label histogram (batch_mean) or bitmap (per_user) and, in philox mode, the keep bytes
 struct BatchPrepArgs {
   const int64_t* indptr; const int32_t* indices; const int32_t* rows; const int32_t* keep_off;

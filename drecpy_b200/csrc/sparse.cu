@@ -181,6 +181,15 @@ __global__ void __launch_bounds__(128) k_batch_prep(BatchPrepArgs a) {
   }
 }
 
+__global__ void __launch_bounds__(128) k_row_scatter(const int32_t* __restrict__ ids, const float* __restrict__ rows,
+                                                     int n, int ld, float* __restrict__ gtable) {
+  const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (r >= n) return;
+  float4* dst = reinterpret_cast<float4*>(gtable + (int64_t)ids[r] * ld);
+  const float4* src = reinterpret_cast<const float4*>(rows + (int64_t)r * ld);
+  for (int c = lane; c < (ld >> 2); c += 32) atomicAdd(dst + c, __ldg(src + c));
+}
+
 constexpr int kRowsPerBlock = 32;
 
 // dz1 = dh * h * (1-h) with dh = sum over split-K partials; column partial sums for db (cdae.py b gradient)
@@ -268,6 +277,14 @@ int launch_scatter(drb_ctx* ctx, const ScatterArgs& a, int n) {
   if (n <= 0) return DRB_OK;
   if (a.ld % 4) return drb_fail(DRB_E_INVALID, "scatter: ld must be a multiple of 4");
   return dispatch_lpr<ScatterLauncher>(ctx, a, n, a.ld, "k_scatter");
+}
+
+int launch_row_scatter(drb_ctx* ctx, const int32_t* ids, const float* rows, int n, int ld, float* gtable) {
+  if (n <= 0) return DRB_OK;
+  drb_prof_scope prof_(ctx, "k_row_scatter");
+  k_row_scatter<<<(n * 32 + 127) / 128, 128, 0, ctx->stream>>>(ids, rows, n, ld, gtable);
+  DRB_LAUNCH_CHECK(ctx, "k_row_scatter");
+  return DRB_OK;
 }
 
 int launch_batch_prep(drb_ctx* ctx, const BatchPrepArgs& a, int n) {

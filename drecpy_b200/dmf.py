@@ -60,7 +60,8 @@ class DMF(DeepRecommenderABC):
             s['uid_np'], s['iid_np'], s['lab_np'] = s['uid'].numpy(), s['iid'].numpy(), s['lab'].numpy()
             self._slots.append(s)
         self._slot_idx = 0
-        self._loss_host = torch.zeros(1, dtype=torch.float32).pin_memory()
+        self._loss_host = torch.zeros(2, dtype=torch.float32).pin_memory()
+        self._next = None
 
     def _factor_arrays(self):
         uf = (C.c_int32 * len(self.user_factors))(*self.user_factors)
@@ -154,6 +155,10 @@ class DMF(DeepRecommenderABC):
         d.workspace, d.workspace_bytes, d.max_batch = self._workspace.data_ptr(), ws_bytes, self._max_batch
         self._native = _lib.vp()
         _lib.check(lib.drb_dmf_create(self._ctx, C.byref(d), C.byref(self._native)))
+        ptr = _lib.vp()
+        _lib.check(lib.drb_dmf_loss_buffer(self._native, C.byref(ptr)))
+        off = ptr.value - self._workspace.data_ptr()
+        self._loss_dev = self._workspace[off:off + 8].view(torch.float32)
 
     def _params_tensor(self):
         return self._params
@@ -178,24 +183,42 @@ class DMF(DeepRecommenderABC):
         out[:] = lab
         return out
 
-    def _train_step(self, batch_size, reg_rate, want_loss=False, **kwds):
+    def _acquire_slot(self):
+        slot = self._slots[self._slot_idx]
+        self._slot_idx = (self._slot_idx + 1) % _RING
+        if slot['event'] is not None:
+            slot['event'].synchronize()
+        return slot
+
+    def _prepare_batch(self, slot, batch_size):
+        self._sampler.sample_arrays(batch_size, out=(slot['uid_np'], slot['iid_np'], slot['val']))
+        self.labels_from_values(slot['val'], out=slot['lab_np'])
+
+    def _train_step(self, batch_size, reg_rate, want_loss=False, prefetch=False, **kwds):
         lib = _lib.load()
         with self._lock:
-            slot = self._slots[self._slot_idx]
-            self._slot_idx = (self._slot_idx + 1) % _RING
-            if slot['event'] is not None:
-                slot['event'].synchronize()
-            self._sampler.sample_arrays(batch_size, out=(slot['uid_np'], slot['iid_np'], slot['val']))
-            self.labels_from_values(slot['val'], out=slot['lab_np'])
+            nxt = getattr(self, '_next', None)
+            if nxt is not None and nxt[1] == batch_size:
+                slot = nxt[0]
+            else:
+                slot = self._acquire_slot()
+                self._prepare_batch(slot, batch_size)
+            self._next = None
             args = self.step_args(reg_rate)
-            loss_ptr = _lib.vp(self._loss_host.data_ptr()) if want_loss else None
             _lib.check(lib.drb_dmf_step_host(self._native, _lib.np_ptr(slot['uid_np']), _lib.np_ptr(slot['iid_np']),
-                                             _lib.np_ptr(slot['lab_np']), batch_size, C.byref(args), loss_ptr))
+                                             _lib.np_ptr(slot['lab_np']), batch_size, C.byref(args), None))
+            if want_loss:
+                self._loss_host.copy_(self._loss_dev, non_blocking=True)
+            ev = self._torch.cuda.Event()
+            ev.record(self._stream)
+            slot['event'] = ev
+            if prefetch:
+                nslot = self._acquire_slot()
+                self._prepare_batch(nslot, batch_size)
+                self._next = (nslot, batch_size)
             if not want_loss:
-                ev = self._torch.cuda.Event()
-                ev.record(self._stream)
-                slot['event'] = ev
                 return None
+            ev.synchronize()
             return float(self._loss_host[0])
 
     def step_device(self, uids_dev, iids_dev, labels_dev, reg_rate, loss_dev):

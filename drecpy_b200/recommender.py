@@ -118,7 +118,7 @@ class DeepRecommenderABC(ABC):
         e = 0
         for e in _iter:
             self._step = e
-            loss = self._train_step(batch_size, reg_rate, want_loss=track, **kwds)
+            loss = self._train_step(batch_size, reg_rate, want_loss=track, prefetch=(e < epochs), **kwds)
 
             if track:
                 self._loss_tracker.add_epoch_loss(loss)

@@ -116,7 +116,7 @@ int drb_batch_offsets(const int32_t* uids, int32_t batch, const int64_t* csr_ind
 
 /* ------------------------------------------------------------------ CDAE
  * Parameter arena layout (floats), all segments 16-byte aligned, row stride ld = K rounded up to a multiple of 4:
- *   [ W2T  n_items x ld | W  n_items x ld | V  n_users x ld | b  ld | b2  n_items rounded up to a multiple of 4 ]
+ *   [ W2T  n_items x ld | W  n_items x ld | b  ld | b2  n_items rounded up to a multiple of 4 | V  n_users x ld ]
  * W2T is the reference's W_ (cdae.py:37, [K, I]) stored item-major ([I, K]); pad columns k >= K stay zero.
  * params / adam_m / adam_v / grads share this layout.  Reference variable order for the per-variable Adam
  * step counters t[5] is [W, W_, V, b, b_] (cdae.py:43). */
@@ -155,6 +155,7 @@ typedef struct {
   uint64_t philox_step;
   int32_t global_batch;    /* data parallel: number of sampled users over all ranks (0 = batch) */
   int32_t slot_offset;     /* data parallel: global batch slot of local row 0 (philox counter) */
+  int32_t skip_user_grad;  /* data parallel: leave dV to drb_cdae_scatter_user_rows (rows are all-gathered) */
 } drb_cdae_step_args;
 
 enum { DRB_PHASE_PREP = 1, DRB_PHASE_GRADS = 2, DRB_PHASE_UPDATE = 4, DRB_PHASE_ALL = 7 };
@@ -171,18 +172,24 @@ int drb_cdae_step(drb_cdae* m, const int32_t* uids, const int32_t* keep_off, con
 /* The same step in phases, for data parallelism over user mini-batches (one process per GPU, replicated weights):
  *   PREP   -> label histogram of the local batch; the caller all-reduces drb_cdae_label_count_buffer()
  *   GRADS  -> forward + backward with global_batch in the label mean / loss mean / L2 scale; the caller
- *             all-reduces the gradient arena
+ *             all-reduces the gradient arena [0, off_v) and, with skip_user_grad, all-gathers the (uid, dz1 row)
+ *             pairs of drb_cdae_dz1_buffer() and adds them with drb_cdae_scatter_user_rows (rows of V never
+ *             travel, only B x K activations' gradients do)
  *   UPDATE -> Adam + loss.  loss_out must hold TWO floats: [0] = batch term + regularisation, [1] = batch term of the
  *             local shard (sum [1] over ranks and add [0]-[1] for the global reported loss).
  * drb_cdae_step == all phases with loss_out[0..1]. */
 int drb_cdae_step_phases(drb_cdae* m, const int32_t* uids, const int32_t* keep_off, const uint8_t* keep,
                          int32_t batch, const drb_cdae_step_args* args, float* loss_out, int32_t phases);
 int drb_cdae_label_count_buffer(drb_cdae* m, float** ptr, int64_t* count);
+int drb_cdae_dz1_buffer(drb_cdae* m, float** ptr, int64_t* count);   /* [max_batch][ld], rows 0..batch-1 valid */
+int drb_cdae_scatter_user_rows(drb_cdae* m, const int32_t* uids, const float* rows, int32_t n);
 /* Same step with HOST inputs: copies uids / keep_off / keep to the device (inside the call), runs the step,
  * and, if loss_host != NULL, copies the loss back and synchronises. */
 int drb_cdae_step_host(drb_cdae* m, const int32_t* uids, const int32_t* keep_off, const uint8_t* keep,
                        int32_t batch, const drb_cdae_step_args* args, float* loss_host);
 /* Hidden representations h[n, ld] for n users, no corruption (cdae.py:67-76 first line).  uids: device. */
+/* device float[2] that drb_cdae_step_host leaves the loss in (valid after the step's stream work) */
+int drb_cdae_loss_buffer(drb_cdae* m, float** ptr);
 int drb_cdae_hidden(drb_cdae* m, const int32_t* uids, int32_t n, float* h_out);
 /* Candidate scoring + ranking.  replaces: cdae.py:84-103 (_predict over all items, filter, heapq.nlargest).
  * cand[n x max_cand] internal item ids (device), cand_count[n]; entries beyond the count are ignored.
@@ -248,6 +255,7 @@ int drb_dmf_step(drb_dmf* m, const int32_t* uids, const int32_t* iids, const flo
                  const drb_dmf_step_args* args, float* loss_out);
 int drb_dmf_step_host(drb_dmf* m, const int32_t* uids, const int32_t* iids, const float* labels, int32_t batch,
                       const drb_dmf_step_args* args, float* loss_host);
+int drb_dmf_loss_buffer(drb_dmf* m, float** ptr);
 /* p[n] = max(1e-6, cos(user tower(uid), item tower(iid))) for n pairs (dmf.py:88-96, un-rescaled). device. */
 int drb_dmf_forward_pairs(drb_dmf* m, const int32_t* uids, const int32_t* iids, int32_t n, float* p_out);
 /* replaces: recommender_abc.py:454-461 (one _predict per candidate + nlargest).  Same contract as
