@@ -151,7 +151,7 @@ int drb_debug_umma_gemm(drb_ctx* ctx, const float* a_hi, const float* a_lo, int3
 struct CdaeWs {
   float *h, *dz, *dh_part, *dz1, *col_b2, *col_b, *loss_part, *reg_part, *label_count, *loss_scalar;
   // tcgen05 path: tf32 hi/lo operand splits (dz doubles as dz_hi)
-  float *h_hi, *h_lo, *hT_hi, *hT_lo, *w2t_hi, *w2t_lo, *wT_hi, *wT_lo, *dz_lo;
+  float *h_hi, *h_lo, *hT_hi, *hT_lo, *w2t_hi, *w2t_lo, *wT_hi, *wT_lo, *dzt_hi, *dzt_lo;   // dzt_*: tile-major dz
   int64_t hT_floats, wT_floats;
   uint32_t* label_bits;
   int32_t *uids, *keep_off, *aux_i32;
@@ -212,7 +212,8 @@ static CdaeWs cdae_carve(void* base, const drb_cdae_layout_t& L, int n_items, in
     w.wT_floats = n2 * (int64_t)L.items_pad;
     w.wT_hi = c.take<float>(w.wT_floats);
     w.wT_lo = c.take<float>(w.wT_floats);
-    w.dz_lo = c.take<float>(B * L.items_pad);
+    w.dzt_hi = c.take<float>(drb_dz_tiled_floats(max_batch, n_items));
+    w.dzt_lo = c.take<float>(drb_dz_tiled_floats(max_batch, n_items));
   }
   w.bytes = c.off;
   return w;
@@ -393,17 +394,21 @@ int drb_cdae_step_phases(drb_cdae* m, const int32_t* uids, const int32_t* keep_o
     if ((r = launch_split_tf32(ctx, P + L.off_w2t, I, ld, ld, w.w2t_hi, w.w2t_lo, w.wT_hi, w.wT_lo, L.items_pad, -1)))
       return r;
     UmmaOperands o1{w.h_hi, w.h_lo, ld, w.w2t_hi, w.w2t_lo, ld, I};
-    if ((r = launch_umma_cdae_loss(ctx, o1, batch, I, ld, w.dz, w.dz_lo, L.items_pad, P + L.off_b2,
+    if ((r = launch_umma_cdae_loss(ctx, o1, batch, I, ld, w.dzt_hi, w.dzt_lo, L.items_pad, P + L.off_b2,
                                    per_user ? nullptr : w.label_count, per_user ? w.label_bits : nullptr,
                                    m->words_per_row, m->d.loss_kind, inv_count, gbatch, w.loss_part, &n_blocks)))
       return r;
     // dW'^T = dz^T h (I x K); the constant-one feature at column `hidden` yields db' = colsum(dz)
-    UmmaOperands o2{w.dz, w.dz_lo, L.items_pad, w.hT_hi, w.hT_lo, bp, n2};
+    UmmaOperands o2{w.dzt_hi, w.dzt_lo, 32, w.hT_hi, w.hT_lo, bp, n2};
+    o2.a_tiled_nib = drb_dz_nib(I);
+    o2.a_tiled_rows = (int64_t)((m->d.max_batch + 127) / 128) * o2.a_tiled_nib * 128;
     if ((r = launch_umma_store(ctx, o2, true, I, n2, batch, 1, G + L.off_w2t, ld, ld, m->d.hidden, G + L.off_b2,
                                m->d.hidden)))
       return r;
     // dh = dz W'^T (B x K), split over the item range
-    UmmaOperands o3{w.dz, w.dz_lo, L.items_pad, w.wT_hi, w.wT_lo, L.items_pad, n2};
+    UmmaOperands o3{w.dzt_hi, w.dzt_lo, 32, w.wT_hi, w.wT_lo, L.items_pad, n2};
+    o3.a_tiled_nib = o2.a_tiled_nib;
+    o3.a_tiled_rows = o2.a_tiled_rows;
     if ((r = launch_umma_store(ctx, o3, false, batch, n2, I, m->splits, w.dh_part, ld, ld, m->d.hidden, nullptr, -1)))
       return r;
   } else {

@@ -82,12 +82,18 @@ struct UmmaOperands {
   const float* a_hi; const float* a_lo; int lda;   // K-major: A[m][k]; MN-major: G[k][m]
   const float* b_hi; const float* b_lo; int ldb;   // B[n][k], k contiguous
   int b_rows;                                       // rows of B that exist in memory (>= logical N is fine)
+  int a_tiled_nib = 0;                              // > 0: A is dz in the 128x32 tile-major layout (see umma_loss.cu)
+  int64_t a_tiled_rows = 0;                         //      total rows of the [rows, 32] view
 };
 bool umma_available();
 // src [rows][ld] -> tf32 hi / lo split, optionally also transposed ([cols..][ldt]); ones_row >= 0 sets that
 // transposed row to 1 (constant feature used to fold the output-bias gradient into the dW' GEMM)
 int launch_split_tf32(drb_ctx* ctx, const float* src, int rows, int cols, int ld, float* hi, float* lo, float* t_hi,
                       float* t_lo, int ldt, int ones_row);
+// dz_hi / dz_lo are written in the tile-major layout: tile (row tile rt, column block cb) of 128 x 32 floats at
+// float offset ((rt * nib + cb) * 128) * 32, nib = drb_dz_nib(N)
+inline int drb_dz_nib(int n_cols) { return 4 * ((n_cols + 127) / 128); }
+inline int64_t drb_dz_tiled_floats(int rows, int n_cols) { return (int64_t)((rows + 127) / 128) * drb_dz_nib(n_cols) * 4096; }
 int launch_umma_cdae_loss(drb_ctx* ctx, const UmmaOperands& o, int M, int N, int Kred, float* dz_hi, float* dz_lo,
                           int ldc, const float* bias, const float* label_count, const uint32_t* label_bits,
                           int words_per_row, int loss_kind, float inv_count, int batch, float* loss_part,

@@ -33,6 +33,7 @@ struct UmmaParams {
   float* C; int ldc;        // EPI_STORE: C[m][n] for n < n_store
   int n_store; int n_valid;  // columns in [n_valid, n_store) are written as 0 (row padding of C)
   float* extra_col; int extra_col_index;   // EPI_STORE: column `extra_col_index` of the product goes to extra_col[m]
+  int a_tiled_nib;          // > 0: A lives in the 128x32 tile-major dz layout with this many 32-column blocks per row tile
   // EPI_CDAE_LOSS
   float* dz_hi; float* dz_lo;              // [M][ldc]
   const float* bias;                       // b' [N]
@@ -93,7 +94,22 @@ k_umma_gemm(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
         const uint32_t sa_hi = base + s * S::STAGE_BYTES, sa_lo = sa_hi + S::A_BYTES;
         const uint32_t sb_hi = sa_lo + S::A_BYTES, sb_lo = sb_hi + S::B_BYTES;
         const int k0 = (kb_beg + i) * BK;
-        if (A_MN) {
+        if (p.a_tiled_nib > 0) {
+          // dz tile-major layout: tile (row tile rt, column block cb) = 128 rows x 32 floats, contiguous 16 KB at
+          // row ((rt * nib + cb) * 128) of a [*, 32] tensor
+          if (A_MN) {   // M runs over dz columns, K over dz rows: four 4 KB boxes {32 cols, 32 rows}
+#pragma unroll
+            for (int j = 0; j < BM / 32; j++) {
+              const int row = ((k0 >> 7) * p.a_tiled_nib + (m0 >> 5) + j) * 128 + (k0 & 127);
+              tma_load_2d(sa_hi + j * 4096, &map_a_hi, full_bar(s), 0, row);
+              tma_load_2d(sa_lo + j * 4096, &map_a_lo, full_bar(s), 0, row);
+            }
+          } else {      // M runs over dz rows, K over dz columns: one contiguous 16 KB tile
+            const int row = ((m0 >> 7) * p.a_tiled_nib + (k0 >> 5)) * 128;
+            tma_load_2d(sa_hi, &map_a_hi, full_bar(s), 0, row);
+            tma_load_2d(sa_lo, &map_a_lo, full_bar(s), 0, row);
+          }
+        } else if (A_MN) {
           // A[m][k] stored as G[k][m] (m contiguous): four boxes of {32 m, 32 k}, one per 32-wide MN atom column
 #pragma unroll
           for (int j = 0; j < BM / 32; j++) {
@@ -300,7 +316,10 @@ template <int BN, bool A_MN, int EPI>
 int run_umma(drb_ctx* ctx, const UmmaOperands& o, const UmmaParams& p, int* n_blocks_out) {
   CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
   int r;
-  if (A_MN) {   // A given as G[k][m]
+  if (o.a_tiled_nib > 0) {   // tile-major dz: a [tiles * 128, 32] tensor
+    if ((r = make_map(&ma_hi, o.a_hi, 32, o.a_tiled_rows, 32, 32, A_MN ? 32 : BM, A_MN))) return r;
+    if ((r = make_map(&ma_lo, o.a_lo, 32, o.a_tiled_rows, 32, 32, A_MN ? 32 : BM, A_MN))) return r;
+  } else if (A_MN) {   // A given as G[k][m]
     if ((r = make_map(&ma_hi, o.a_hi, p.M, p.Kred, o.lda, 32, 32, true))) return r;
     if ((r = make_map(&ma_lo, o.a_lo, p.M, p.Kred, o.lda, 32, 32, true))) return r;
   } else {      // A given as G[m][k]
@@ -342,6 +361,7 @@ int launch_umma_store(drb_ctx* ctx, const UmmaOperands& o, bool a_mn_major, int 
   UmmaParams p{};
   p.M = M; p.N = N; p.Kred = Kred; p.splits = splits; p.C = C; p.ldc = ldc; p.n_store = n_store; p.n_valid = n_valid;
   p.extra_col = extra_col; p.extra_col_index = extra_col_index;
+  p.a_tiled_nib = o.a_tiled_nib;
   if (N > 256) return drb_fail(DRB_E_INVALID, "umma store GEMM: N must be <= 256 (hidden width)");
 #define DRB_UMMA_CASE(BN)                                                        \
   if (N <= BN) {                                                                 \

@@ -9,13 +9,13 @@
 // short (hidden <= 255 -> <= 8 k-blocks), so per-tile set-up and the exposed epilogue dominated the one-tile-per-CTA
 // version; here the TMA producer runs ahead across tiles, the accumulator is double-buffered in TMEM
 // (2 x BN columns) and the 4 epilogue warps drain tile t while the MMA warp fills tile t+1.
-// Epilogue stores go through a per-warp shared-memory transpose so every global store instruction writes full
-// 128-byte lines.
+// dz is written in a 128 x 32 tile-major layout: an epilogue thread (= one accumulator row) owns a contiguous 64-byte
+// piece of a 16 KB tile, and the two backward GEMMs later fetch whole tiles / 4 KB sub-tiles with single TMA boxes.
 #include "umma_common.cuh"
 
 namespace {
 
-constexpr int LOSS_EPI_WARPS = 8;                       // two per TMEM sub-partition, each takes half of the columns
+constexpr int LOSS_EPI_WARPS = 16;                      // four per TMEM sub-partition, each takes a quarter of the columns
 constexpr int LOSS_THREADS = 64 + 32 * LOSS_EPI_WARPS;
 
 template <int BN>
@@ -26,13 +26,12 @@ struct LossSmem {
   static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
   static constexpr int BAR_BYTES = 256;
   static constexpr int CONST_BYTES = 2 * BN * 4;            // b' and batch-mean target of the current tile
-  static constexpr int XPOSE_BYTES = LOSS_EPI_WARPS * 32 * 32 * 4;   // one XOR-swizzled 32x32 fp32 transpose buffer per epilogue warp
-  static constexpr int TOTAL = STAGES * STAGE_BYTES + 1024 + BAR_BYTES + CONST_BYTES + XPOSE_BYTES;
+  static constexpr int TOTAL = STAGES * STAGE_BYTES + 1024 + BAR_BYTES + CONST_BYTES;
 };
 
 struct LossParams {
   int M, N, Kred;                          // batch, n_items, hidden (padded to 4)
-  float* dz_hi; float* dz_lo; int ldc;     // [M][ldc]
+  float* dz_hi; float* dz_lo; int nib;     // tile-major (kernels.h: drb_dz_nib), nib column blocks per row tile
   const float* bias;                       // b' [N]
   const float* label_count; const uint32_t* label_bits; int words_per_row;
   int loss_kind; float inv_count; int batch;
@@ -63,7 +62,6 @@ k_umma_cdae_loss(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
   volatile float* lred = reinterpret_cast<volatile float*>(smem_raw + (bars + 8u * (2 * S::STAGES + 5) - raw));
   float* s_bias = reinterpret_cast<float*>(smem_raw + (bars + S::BAR_BYTES - raw));
   float* s_tgt = s_bias + BN;
-  float* s_xpose = s_tgt + BN;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nkb = (p.Kred + BK - 1) / BK;
@@ -140,11 +138,10 @@ k_umma_cdae_loss(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
       }
     }
   } else {
-    // ------------------------------------------------------------------ epilogue warps 2..9
-    // warp w reads TMEM lanes 32*(w&3)..+31 (hardware sub-partition rule) and the column half (w-2)/4 of the tile
-    const int q = warp & 3, chalf = (warp - 2) >> 2;
+    // ------------------------------------------------------------------ epilogue warps 2..17
+    // warp w reads TMEM lanes 32*(w&3)..+31 (hardware sub-partition rule) and the column quarter (w-2)/4 of the tile
+    const int q = warp & 3, cq = (warp - 2) >> 2;
     const int ew = warp - 2;
-    float* xp = s_xpose + ew * (32 * 32);
     float loss_local = 0.f;
     const float one_m = 1.0f - KERAS_EPS;
     int tl = 0;
@@ -164,16 +161,16 @@ k_umma_cdae_loss(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
       mbar_wait(tfull_bar(as), (tl >> 1) & 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll 1
-      for (int c = chalf * (BN / 2); c < (chalf + 1) * (BN / 2); c += 32) {
-        uint32_t r[32];
-        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN + c), r);
-        uint32_t wcur = 0;     // per-user label bits of these 32 columns (n0 + c is a multiple of 32)
+      for (int c = cq * (BN / 4); c < (cq + 1) * (BN / 4); c += 16) {
+        uint32_t r[16];
+        tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN + c), r);
+        uint32_t wcur = 0;     // per-user label bits of these 16 columns
         if (PER_USER && row_ok && ((n0 + c) >> 5) < p.words_per_row)
-          wcur = __ldg(p.label_bits + (int64_t)m * p.words_per_row + ((n0 + c) >> 5));
-        float lo[32];
-        // branch-free element math: 32 independent dependency chains the scheduler can interleave
+          wcur = __ldg(p.label_bits + (int64_t)m * p.words_per_row + ((n0 + c) >> 5)) >> ((n0 + c) & 31);
+        float lo[16];
+        // branch-free element math: 16 independent dependency chains the scheduler can interleave
 #pragma unroll
-        for (int j = 0; j < 32; j++) {
+        for (int j = 0; j < 16; j++) {
           const bool ok = row_ok && (n0 + c + j < p.N);
           const float z = __uint_as_float(r[j]) + s_bias[c + j];
           const float pr = __fdividef(1.0f, 1.0f + __expf(-z));
@@ -195,21 +192,16 @@ k_umma_cdae_loss(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
           split_tf32(g, h, lo[j]);
           r[j] = __float_as_uint(h);
         }
-        // transpose through shared memory (XOR-swizzled 32x32): lane = row when writing, lane = column when
-        // reading, so every global store instruction covers one full 128-byte line of dz
-        const int ncol = n0 + c + lane;
+        // tile-major store: this thread's 16 columns are 64 contiguous bytes of tile (m0/128, (n0+c)/32); every row
+        // and column of the tile is written (zeros outside the matrix) because the backward GEMMs read whole tiles
+        const int64_t off = ((int64_t)((m0 >> 7) * p.nib + ((n0 + c) >> 5)) * 128 + (q * 32 + lane)) * 32 + ((n0 + c) & 31);
 #pragma unroll
-        for (int half = 0; half < 2; half++) {
-          __syncwarp();
-#pragma unroll
-          for (int j = 0; j < 32; j++) xp[lane * 32 + (j ^ lane)] = half ? lo[j] : __uint_as_float(r[j]);
-          __syncwarp();
-          float* dst = (half ? p.dz_lo : p.dz_hi) + (int64_t)(m0 + q * 32) * p.ldc + ncol;
-          if (ncol < p.ldc) {
-#pragma unroll
-            for (int rr = 0; rr < 32; rr++)
-              if (m0 + q * 32 + rr < p.M) dst[(int64_t)rr * p.ldc] = xp[rr * 32 + (lane ^ rr)];
-          }
+        for (int j4 = 0; j4 < 4; j4++) {
+          *reinterpret_cast<float4*>(p.dz_hi + off + j4 * 4) =
+              make_float4(__uint_as_float(r[j4 * 4]), __uint_as_float(r[j4 * 4 + 1]), __uint_as_float(r[j4 * 4 + 2]),
+                          __uint_as_float(r[j4 * 4 + 3]));
+          *reinterpret_cast<float4*>(p.dz_lo + off + j4 * 4) =
+              make_float4(lo[j4 * 4], lo[j4 * 4 + 1], lo[j4 * 4 + 2], lo[j4 * 4 + 3]);
         }
       }
       // this warp has finished reading accumulator `as`
@@ -269,7 +261,8 @@ int launch_umma_cdae_loss(drb_ctx* ctx, const UmmaOperands& o, int M, int N, int
                           int words_per_row, int loss_kind, float inv_count, int batch, float* loss_part,
                           int* n_blocks_out) {
   LossParams p{};
-  p.M = M; p.N = N; p.Kred = Kred; p.ldc = ldc; p.dz_hi = dz_hi; p.dz_lo = dz_lo; p.bias = bias;
+  p.M = M; p.N = N; p.Kred = Kred; p.nib = drb_dz_nib(N); p.dz_hi = dz_hi; p.dz_lo = dz_lo; p.bias = bias;
+  (void)ldc;
   p.label_count = label_count; p.label_bits = label_bits; p.words_per_row = words_per_row; p.loss_kind = loss_kind;
   p.inv_count = inv_count; p.batch = batch; p.loss_part = loss_part;
   const bool per_user = label_count == nullptr;
