@@ -273,6 +273,12 @@ int drb_cdae_create(drb_ctx* ctx, const drb_cdae_desc* desc, drb_cdae** out) {
     return drb_fail(DRB_E_INVALID, "drb_cdae_create: the tcgen05 path needs hidden < 256 and a driver with TMA support");
   }
   m->use_umma = umma_ok && desc->gemm_path != DRB_GEMM_FFMA;
+  if (m->use_umma) {
+    // dh = dz W'^T on the tensor cores has one 128 x n2 tile per 128 users: split the item range so that the grid
+    // is ~2 waves of the SM count (the kernel is L2/HBM bandwidth bound, one CTA per SM)
+    const int mt = (desc->max_batch + 127) / 128;
+    m->splits = std::max(1, std::min(32, std::min((2 * ctx->sm_count) / mt, desc->n_items / 256)));
+  }
   m->ws = cdae_carve(desc->workspace, L, desc->n_items, desc->hidden, desc->max_batch, desc->label_mode, m->splits,
                      ctx->sm_count, m->use_umma);
   m->keep_cap = cdae_keep_cap(desc->n_items, desc->max_batch);

@@ -25,7 +25,7 @@ struct LossSmem {
   static constexpr int B_BYTES = BN * BK * 4;
   static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
   static constexpr int BAR_BYTES = 256;
-  static constexpr int CONST_BYTES = 2 * BN * 4;            // b' and batch-mean target of the current tile
+  static constexpr int CONST_BYTES = LOSS_EPI_WARPS * 2 * (BN / 4) * 4;   // per epilogue warp: b' and target of its columns
   static constexpr int TOTAL = STAGES * STAGE_BYTES + 1024 + BAR_BYTES + CONST_BYTES;
 };
 
@@ -61,7 +61,6 @@ k_umma_cdae_loss(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
   volatile uint32_t* tmem_ptr_generic = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_ptr_addr - raw));
   volatile float* lred = reinterpret_cast<volatile float*>(smem_raw + (bars + 8u * (2 * S::STAGES + 5) - raw));
   float* s_bias = reinterpret_cast<float*>(smem_raw + (bars + S::BAR_BYTES - raw));
-  float* s_tgt = s_bias + BN;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nkb = (p.Kred + BK - 1) / BK;
@@ -150,20 +149,30 @@ k_umma_cdae_loss(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
       const int as = tl & 1;
       const int m = m0 + q * 32 + lane;
       const bool row_ok = m < p.M;
-      // per-column constants of this tile (the previous tile's readers are done: barrier first)
-      asm volatile("bar.sync 1, %0;" ::"n"(32 * LOSS_EPI_WARPS) : "memory");
-      for (int c = threadIdx.x - 64; c < BN; c += 32 * LOSS_EPI_WARPS) {
-        const int nn = n0 + c;
-        s_bias[c] = (nn < p.N) ? __ldg(p.bias + nn) : 0.f;
-        s_tgt[c] = (!PER_USER && nn < p.N) ? __ldg(p.label_count + nn) / (float)p.batch : 0.f;
+      // per-column constants of this warp's column quarter (private shared-memory slice: no block barrier)
+      constexpr int CW = BN / 4;
+      float* wb = s_bias + ew * 2 * CW;
+      float* wt = wb + CW;
+      __syncwarp();
+      for (int c = lane; c < CW; c += 32) {
+        const int nn = n0 + cq * CW + c;
+        wb[c] = (nn < p.N) ? __ldg(p.bias + nn) : 0.f;
+        wt[c] = (!PER_USER && nn < p.N) ? __ldg(p.label_count + nn) / (float)p.batch : 0.f;
       }
-      asm volatile("bar.sync 1, %0;" ::"n"(32 * LOSS_EPI_WARPS) : "memory");
+      __syncwarp();
       mbar_wait(tfull_bar(as), (tl >> 1) & 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN + cq * CW);
+      uint32_t rn[16];
+      tmem_ld16_issue(tbase, rn);
 #pragma unroll 1
-      for (int c = cq * (BN / 4); c < (cq + 1) * (BN / 4); c += 16) {
+      for (int cl = 0; cl < CW; cl += 16) {
+        const int c = cq * CW + cl;
         uint32_t r[16];
-        tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN + c), r);
+        tmem_ld16_wait(rn);
+#pragma unroll
+        for (int j = 0; j < 16; j++) r[j] = rn[j];
+        if (cl + 16 < CW) tmem_ld16_issue(tbase + cl + 16, rn);      // prefetch the next chunk behind the math
         uint32_t wcur = 0;     // per-user label bits of these 16 columns
         if (PER_USER && row_ok && ((n0 + c) >> 5) < p.words_per_row)
           wcur = __ldg(p.label_bits + (int64_t)m * p.words_per_row + ((n0 + c) >> 5)) >> ((n0 + c) & 31);
@@ -172,9 +181,9 @@ k_umma_cdae_loss(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
 #pragma unroll
         for (int j = 0; j < 16; j++) {
           const bool ok = row_ok && (n0 + c + j < p.N);
-          const float z = __uint_as_float(r[j]) + s_bias[c + j];
+          const float z = __uint_as_float(r[j]) + wb[cl + j];
           const float pr = __fdividef(1.0f, 1.0f + __expf(-z));
-          const float tgt = PER_USER ? (float)((wcur >> j) & 1u) : s_tgt[c + j];
+          const float tgt = PER_USER ? (float)((wcur >> j) & 1u) : wt[cl + j];
           float dp, lt;
           if (LOSS == DRB_LOSS_BCE) {
             const float pc = fminf(fmaxf(pr, KERAS_EPS), one_m);
@@ -195,6 +204,7 @@ k_umma_cdae_loss(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
         // tile-major store: this thread's 16 columns are 64 contiguous bytes of tile (m0/128, (n0+c)/32); every row
         // and column of the tile is written (zeros outside the matrix) because the backward GEMMs read whole tiles
         const int64_t off = ((int64_t)((m0 >> 7) * p.nib + ((n0 + c) >> 5)) * 128 + (q * 32 + lane)) * 32 + ((n0 + c) & 31);
+        if (((n0 + c) >> 5) < p.nib) {   // 256-wide tiles can overhang the last 128-column group
 #pragma unroll
         for (int j4 = 0; j4 < 4; j4++) {
           *reinterpret_cast<float4*>(p.dz_hi + off + j4 * 4) =
@@ -202,6 +212,7 @@ k_umma_cdae_loss(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
                           __uint_as_float(r[j4 * 4 + 3]));
           *reinterpret_cast<float4*>(p.dz_lo + off + j4 * 4) =
               make_float4(lo[j4 * 4], lo[j4 * 4 + 1], lo[j4 * 4 + 2], lo[j4 * 4 + 3]);
+        }
         }
       }
       // this warp has finished reading accumulator `as`
@@ -266,9 +277,16 @@ int launch_umma_cdae_loss(drb_ctx* ctx, const UmmaOperands& o, int M, int N, int
   p.label_count = label_count; p.label_bits = label_bits; p.words_per_row = words_per_row; p.loss_kind = loss_kind;
   p.inv_count = inv_count; p.batch = batch; p.loss_part = loss_part;
   const bool per_user = label_count == nullptr;
-  if (loss_kind == DRB_LOSS_BCE)
-    return per_user ? run_loss<128, DRB_LOSS_BCE, true>(ctx, o, p, n_blocks_out)
-                    : run_loss<128, DRB_LOSS_BCE, false>(ctx, o, p, n_blocks_out);
-  return per_user ? run_loss<128, DRB_LOSS_MSE, true>(ctx, o, p, n_blocks_out)
-                  : run_loss<128, DRB_LOSS_MSE, false>(ctx, o, p, n_blocks_out);
+  static const int bn_env = getenv("DRB_LOSS_BN") ? atoi(getenv("DRB_LOSS_BN")) : 0;
+  // 256-wide tiles halve the re-reads of the h tile (the main loop is L2->SM bandwidth bound); keep 128 for small N
+  const bool wide = bn_env ? (bn_env == 256) : (N >= 4096);
+#define DRB_LOSS_CASE(BN_)                                                                          \
+  if (loss_kind == DRB_LOSS_BCE)                                                                    \
+    return per_user ? run_loss<BN_, DRB_LOSS_BCE, true>(ctx, o, p, n_blocks_out)                    \
+                    : run_loss<BN_, DRB_LOSS_BCE, false>(ctx, o, p, n_blocks_out);                  \
+  return per_user ? run_loss<BN_, DRB_LOSS_MSE, true>(ctx, o, p, n_blocks_out)                      \
+                  : run_loss<BN_, DRB_LOSS_MSE, false>(ctx, o, p, n_blocks_out);
+  if (wide) { DRB_LOSS_CASE(256) }
+  DRB_LOSS_CASE(128)
+#undef DRB_LOSS_CASE
 }
