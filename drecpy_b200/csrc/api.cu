@@ -369,7 +369,9 @@ int drb_cdae_step_phases(drb_cdae* m, const int32_t* uids, const int32_t* keep_o
 
   if (phases & DRB_PHASE_PREP) {
   // 0. clear sparse-gradient regions [W | V | b | b2] (W2T's gradient is fully overwritten by the GEMM)
-  DRB_CUDA_TRY(ctx, cudaMemsetAsync(G + L.off_w, 0, (size_t)(L.total - L.off_w) * sizeof(float), ctx->stream));
+  // (the tcgen05 path accumulates dW'^T from two reduction halves with vector atomics, so it clears that too)
+  const int64_t clear_from = m->use_umma ? 0 : L.off_w;
+  DRB_CUDA_TRY(ctx, cudaMemsetAsync(G + clear_from, 0, (size_t)(L.total - clear_from) * sizeof(float), ctx->stream));
   if (per_user)
     DRB_CUDA_TRY(ctx, cudaMemsetAsync(w.label_bits, 0, (size_t)batch * m->words_per_row * 4, ctx->stream));
   else
@@ -408,8 +410,10 @@ int drb_cdae_step_phases(drb_cdae* m, const int32_t* uids, const int32_t* keep_o
     UmmaOperands o2{w.dzt_hi, w.dzt_lo, 32, w.hT_hi, w.hT_lo, bp, n2};
     o2.a_tiled_nib = drb_dz_nib(I);
     o2.a_tiled_rows = (int64_t)((m->d.max_batch + 127) / 128) * o2.a_tiled_nib * 128;
-    if ((r = launch_umma_store(ctx, o2, true, I, n2, batch, 1, G + L.off_w2t, ld, ld, m->d.hidden, G + L.off_b2,
-                               m->d.hidden)))
+    // 209 item tiles on 148 SMs would run as two uneven waves; two reduction halves (3 even waves) accumulate atomically
+    const int s2 = batch >= 1024 ? 2 : 1;
+    if ((r = launch_umma_store(ctx, o2, true, I, n2, batch, s2, G + L.off_w2t, ld, ld, m->d.hidden, G + L.off_b2,
+                               m->d.hidden, s2 > 1)))
       return r;
     // dh = dz W'^T (B x K), split over the item range
     UmmaOperands o3{w.dzt_hi, w.dzt_lo, 32, w.wT_hi, w.wT_lo, L.items_pad, n2};

@@ -99,7 +99,8 @@ int launch_umma_cdae_loss(drb_ctx* ctx, const UmmaOperands& o, int M, int N, int
                           int words_per_row, int loss_kind, float inv_count, int batch, float* loss_part,
                           int* n_blocks_out);
 int launch_umma_store(drb_ctx* ctx, const UmmaOperands& o, bool a_mn_major, int M, int N, int Kred, int splits,
-                      float* C, int ldc, int n_store, int n_valid, float* extra_col, int extra_col_index);
+                      float* C, int ldc, int n_store, int n_valid, float* extra_col, int extra_col_index,
+                      bool atomic_out = false);
 
 // ------------------------------------------------------------------ optim.cu
 #define DRB_MAX_SEGS 40

@@ -33,6 +33,7 @@ struct UmmaParams {
   float* C; int ldc;        // EPI_STORE: C[m][n] for n < n_store
   int n_store; int n_valid;  // columns in [n_valid, n_store) are written as 0 (row padding of C)
   float* extra_col; int extra_col_index;   // EPI_STORE: column `extra_col_index` of the product goes to extra_col[m]
+  int atomic_out;           // splits > 1: accumulate all partials into C / extra_col with vector atomics (C pre-zeroed)
   int a_tiled_nib;          // > 0: A lives in the 128x32 tile-major dz layout with this many 32-column blocks per row tile
   // EPI_CDAE_LOSS
   float* dz_hi; float* dz_lo;              // [M][ldc]
@@ -183,7 +184,7 @@ k_umma_gemm(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     float loss_local = 0.f;
     float* crow = nullptr;
-    if (EPI == EPI_STORE) crow = p.C + (int64_t)blockIdx.z * p.M * p.ldc + (int64_t)m * p.ldc;
+    if (EPI == EPI_STORE) crow = p.C + (p.atomic_out ? 0 : (int64_t)blockIdx.z * p.M * p.ldc) + (int64_t)m * p.ldc;
 #pragma unroll 1
     for (int c = 0; c < BN; c += 16) {
       uint32_t r[16];
@@ -199,17 +200,22 @@ k_umma_gemm(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
 #pragma unroll
         for (int j4 = 0; j4 < 4; j4++) {
           const int nn = n + j4 * 4;
-          if (nn < p.n_store)   // n_store % 4 == 0
-            *reinterpret_cast<float4*>(crow + nn) =
-                make_float4(nn + 0 < p.n_valid ? __uint_as_float(r[j4 * 4]) : 0.f,
-                            nn + 1 < p.n_valid ? __uint_as_float(r[j4 * 4 + 1]) : 0.f,
-                            nn + 2 < p.n_valid ? __uint_as_float(r[j4 * 4 + 2]) : 0.f,
-                            nn + 3 < p.n_valid ? __uint_as_float(r[j4 * 4 + 3]) : 0.f);
+          if (nn < p.n_store) {   // n_store % 4 == 0
+            const float4 v = make_float4(nn + 0 < p.n_valid ? __uint_as_float(r[j4 * 4]) : 0.f,
+                                         nn + 1 < p.n_valid ? __uint_as_float(r[j4 * 4 + 1]) : 0.f,
+                                         nn + 2 < p.n_valid ? __uint_as_float(r[j4 * 4 + 2]) : 0.f,
+                                         nn + 3 < p.n_valid ? __uint_as_float(r[j4 * 4 + 3]) : 0.f);
+            if (p.atomic_out) atomicAdd(reinterpret_cast<float4*>(crow + nn), v);
+            else *reinterpret_cast<float4*>(crow + nn) = v;
+          }
         }
-        if (p.extra_col && p.extra_col_index >= n && p.extra_col_index < n + 16 && blockIdx.z == 0) {
+        if (p.extra_col && p.extra_col_index >= n && p.extra_col_index < n + 16 && (p.atomic_out || blockIdx.z == 0)) {
 #pragma unroll
           for (int j = 0; j < 16; j++)
-            if (n + j == p.extra_col_index) p.extra_col[m] = __uint_as_float(r[j]);
+            if (n + j == p.extra_col_index) {
+              if (p.atomic_out) atomicAdd(p.extra_col + m, __uint_as_float(r[j]));
+              else p.extra_col[m] = __uint_as_float(r[j]);
+            }
         }
       } else {  // EPI_CDAE_LOSS: z2 -> p -> loss term and dL/dz2, written as the hi/lo split the backward GEMMs read
         float hi[16], lo[16];
@@ -357,11 +363,13 @@ int launch_split_tf32(drb_ctx* ctx, const float* src, int rows, int cols, int ld
 }
 
 int launch_umma_store(drb_ctx* ctx, const UmmaOperands& o, bool a_mn_major, int M, int N, int Kred, int splits,
-                      float* C, int ldc, int n_store, int n_valid, float* extra_col, int extra_col_index) {
+                      float* C, int ldc, int n_store, int n_valid, float* extra_col, int extra_col_index,
+                      bool atomic_out) {
   UmmaParams p{};
   p.M = M; p.N = N; p.Kred = Kred; p.splits = splits; p.C = C; p.ldc = ldc; p.n_store = n_store; p.n_valid = n_valid;
   p.extra_col = extra_col; p.extra_col_index = extra_col_index;
   p.a_tiled_nib = o.a_tiled_nib;
+  p.atomic_out = atomic_out ? 1 : 0;
   if (N > 256) return drb_fail(DRB_E_INVALID, "umma store GEMM: N must be <= 256 (hidden width)");
 #define DRB_UMMA_CASE(BN)                                                        \
   if (N <= BN) {                                                                 \
