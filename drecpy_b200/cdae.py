@@ -246,12 +246,14 @@ class CDAE(DeepRecommenderABC):
             self._next = None
             self._cur_batch = batch_size
             if self._dp.active:
-                return self._train_step_dp(slot, batch_size, reg_rate, want_loss)
-            args = self.step_args(reg_rate)
-            _lib.check(lib.drb_cdae_step_host(self._native, _lib.np_ptr(slot['uid_np']), _lib.np_ptr(slot['off_np']),
-                                              keep_ptr, batch_size, C.byref(args), None))
-            if want_loss:
-                self._loss_host.copy_(self._loss_dev, non_blocking=True)
+                self._enqueue_step_dp(slot, batch_size, reg_rate)
+            else:
+                args = self.step_args(reg_rate)
+                _lib.check(lib.drb_cdae_step_host(self._native, _lib.np_ptr(slot['uid_np']),
+                                                  _lib.np_ptr(slot['off_np']), keep_ptr, batch_size, C.byref(args),
+                                                  None))
+                if want_loss:
+                    self._loss_host.copy_(self._loss_dev, non_blocking=True)
             ev = self._torch.cuda.Event()
             ev.record(self._stream)
             slot['event'] = ev
@@ -260,10 +262,12 @@ class CDAE(DeepRecommenderABC):
                 self._next = (nslot, batch_size, self.prepare_batch(nslot, batch_size))
             if not want_loss:
                 return None
+            if self._dp.active:
+                return float(self._dp.global_loss(self._dp_dev['loss']).item())
             ev.synchronize()
             return float(self._loss_host[0])
 
-    def _train_step_dp(self, slot, batch_size, reg_rate, want_loss):
+    def _enqueue_step_dp(self, slot, batch_size, reg_rate):
         torch = self._torch
         if not hasattr(self, '_dp_dev'):
             self._dp_dev = {'uid': torch.empty(batch_size, dtype=torch.int32, device=self._dev),
@@ -274,12 +278,6 @@ class CDAE(DeepRecommenderABC):
         d['off'].copy_(slot['off'], non_blocking=True)
         self._step -= 1                      # step_device advances it again
         self.step_device(d['uid'], d['off'], None, reg_rate, d['loss'])
-        ev = torch.cuda.Event()
-        ev.record(self._stream)
-        slot['event'] = ev
-        if not want_loss:
-            return None
-        return float(self._dp.global_loss(d['loss']).item())
 
     def step_device(self, uids_dev, keep_off_dev, keep_dev, reg_rate, loss_dev):
         """One step on device-resident inputs (torch tensors); keep_dev=None selects the philox mask.

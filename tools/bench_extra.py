@@ -1,0 +1,90 @@
+#!/usr/bin/env python
+"""Secondary measurements on one GPU (not the driver's bench contract): DMF training samples/s at config 2 and
+ranked users/s at config 4 (sampled leave-1-out protocol and full-catalog top-100).  Prints one JSON line."""
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+
+def dmf_c2(steps=200):
+    import torch
+    import drecpy_b200 as drb
+    u, i, v = drb.synthetic_interactions(6040, 3706, 1_000_000, seed=10)
+    ds = drb.InteractionData(u, i, v)
+    m = drb.DMF(user_factors=[64, 32], item_factors=[64, 32], seed=10, verbose=False)
+    B = 256
+    m.fit(ds, epochs=0, batch_size=B, learning_rate=1e-3, neg_ratio=5, reg_rate=1e-4)
+    dev = torch.device('cuda')
+    batches = []
+    for _ in range(steps + 20):
+        uu, ii, vv = m._sampler.sample_arrays(B)
+        batches.append((torch.from_numpy(uu.copy()).to(dev), torch.from_numpy(ii.copy()).to(dev),
+                        torch.from_numpy(m.labels_from_values(vv)).to(dev)))
+    loss = torch.zeros(2, device=dev)
+    for s in range(20):
+        m.step_device(*batches[s], 1e-4, loss)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    l0 = m.launch_count()
+    e0.record()
+    for s in range(20, 20 + steps):
+        m.step_device(*batches[s], 1e-4, loss)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    launches = (m.launch_count() - l0) / steps
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        m._step += 1
+        m._train_step(B, 1e-4, want_loss=True, prefetch=True)
+    t_e2e = (time.perf_counter() - t0) / steps
+    return {'dmf_c2_samples_per_s': B / (ms * 1e-3), 'dmf_c2_ms_per_step': ms, 'dmf_c2_launches_per_step': launches,
+            'dmf_c2_e2e_samples_per_s': B / t_e2e, 'dmf_loss': float(loss[0])}
+
+
+def eval_c4(n_users=138493, n_items=26744, nnz=20_000_000, K=200):
+    import torch
+    import drecpy_b200 as drb
+    u, i, v = drb.synthetic_interactions(n_users, n_items, nnz, seed=10, zipf_a=1.0)
+    rng = np.random.default_rng(3)
+    order = np.argsort(u, kind='stable')
+    first = np.flatnonzero(np.concatenate(([True], u[order][1:] != u[order][:-1])))
+    counts = np.diff(np.concatenate((first, [len(u)])))
+    pick = order[first + rng.integers(0, counts)]            # one held-out interaction per user (leave-1-out shape)
+    mask = np.zeros(len(u), bool)
+    mask[pick[counts > 1]] = True
+    train = drb.InteractionData(u[~mask], i[~mask], v[~mask])
+    test = drb.InteractionData(u[mask], i[mask], v[mask])
+    m = drb.CDAE(hidden_factors=K, seed=10, verbose=False, rng_mode='philox')
+    m.fit(train, epochs=2, batch_size=4096)
+    out = {'eval_users': int(mask.sum())}
+    t0 = time.perf_counter()
+    res = drb.ranking_evaluation(m, test, k=10, n_pos_interactions=1, n_neg_interactions=100,
+                                 generate_negative_pairs=True, novelty=True, seed=10,
+                                 metrics=[drb.HitRatio(), drb.NDCG()], verbose=False)
+    dt = time.perf_counter() - t0
+    out.update({'sampled_ranking_users_per_s': out['eval_users'] / dt, 'sampled_ranking_s': dt, 'metrics': res})
+    uids = torch.arange(m.n_users, dtype=torch.int32, device='cuda')
+    m.topk_batch(uids[:4096], 100, novelty=True, return_device=True)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    oi, os_, on = m.topk_batch(uids, 100, novelty=True, return_device=True)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    out.update({'full_catalog_top100_users_per_s': m.n_users / dt, 'full_catalog_s': dt})
+    return out
+
+
+if __name__ == '__main__':
+    res = {}
+    what = sys.argv[1:] or ['dmf', 'eval']
+    if 'dmf' in what:
+        res.update(dmf_c2())
+    if 'eval' in what:
+        res.update(eval_c4())
+    print(json.dumps(res))
