@@ -258,6 +258,7 @@ def run_native(args, cfg):
     achieved = flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else None
     tc_path = any(k.startswith('k_umma') for k in kernels)
     n_params = 2 * I * m._L.ld + U * m._L.ld + m._L.ld + m._L.items_pad
+    launches_total = int(launches)
     adam_gbs = 28.0 * n_params / (kernels.get('k_adam', float('nan')) * 1e-3) / 1e9
     roofline = {'kernel': ('k_umma_cdae_loss + k_umma_gemm x2 (tcgen05 3xTF32: output layer fwd + fused loss epilogue, '
                            'dW\'^T and dh)') if tc_path else 'k_sgemm x3 (fp32 FFMA path)',
@@ -277,15 +278,29 @@ def run_native(args, cfg):
         cpu = {'value': r['samples_per_s'], 'unit': 'samples/s', 'cores': os.cpu_count(), 'kind': 'port',
                'sample': f"2 timed oracle steps of {r['batch']} sampled users on the full shape (numpy/BLAS, all cores)"}
 
+    extras = None
+    if world == 1 and not args.no_extras:
+        # the other two legs of BASELINE.json's metric, measured after the headline (not part of `value`):
+        # DMF training samples/s at configs[1] and ranked users/s at configs[3] (tools/bench_extra.py)
+        try:
+            sys.path.insert(0, os.path.join(ROOT, 'tools'))
+            import bench_extra
+            del m, batches
+            torch.cuda.empty_cache()
+            extras = bench_extra.dmf_c2(steps=100)
+            extras.update(bench_extra.eval_c4(K=cfg['hidden'], arrays=(ds.user, ds.item, ds.interaction)))
+        except Exception as exc:          # never lose the headline line because of a secondary measurement
+            extras = {'error': repr(exc)}
+
     value = B * world * K / (ms_total * 1e-3)
     line = {'metric': 'cdae_training_samples_per_sec', 'value': value, 'unit': 'samples/s', 'n_gpus': world,
             'steps': K, 'warmup': W, 'ms_per_step': ms_total / K, 'higher_is_better': True, 'scaling': 'weak',
             'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic', 'config': workload_config(cfg, world),
-            'clocks': clock_info, 'gpu_launches': int(launches),
+            'clocks': clock_info, 'gpu_launches': launches_total,
             'e2e': {'value': B * world * K / t_e2e, 'unit': 'samples/s', 'h2d_bytes_per_step': 4 * B + 4 * (B + 1),
                     'd2h_bytes_per_step': 4, 'ms_per_step': 1e3 * t_e2e / K},
             'roofline': roofline, 'cpu_baseline': cpu, 'kernels_ms_per_step': kernels,
-            'loss_last': loss_value, 'loss_last_e2e': loss_e2e, 'data_gen_s': round(t_data, 1)}
+            'loss_last': loss_value, 'loss_last_e2e': loss_e2e, 'data_gen_s': round(t_data, 1), 'extras': extras}
     print(json.dumps(line), flush=True)
     if dist is not None:
         dist.barrier()
@@ -300,6 +315,7 @@ def main():
     ap.add_argument('--impl', default='native', choices=['native', 'reference'])
     ap.add_argument('--workload', default='c3', choices=['c3', 'small'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-extras', action='store_true')
     args = ap.parse_args()
     cfg = dict(C3 if args.workload == 'c3' else SMALL)
     if args.impl == 'reference':

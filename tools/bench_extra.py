@@ -47,10 +47,10 @@ def dmf_c2(steps=200):
             'dmf_c2_e2e_samples_per_s': B / t_e2e, 'dmf_loss': float(loss[0])}
 
 
-def eval_c4(n_users=138493, n_items=26744, nnz=20_000_000, K=200):
+def eval_c4(n_users=138493, n_items=26744, nnz=20_000_000, K=200, arrays=None):
     import torch
     import drecpy_b200 as drb
-    u, i, v = drb.synthetic_interactions(n_users, n_items, nnz, seed=10, zipf_a=1.0)
+    u, i, v = arrays if arrays is not None else drb.synthetic_interactions(n_users, n_items, nnz, seed=10, zipf_a=1.0)
     rng = np.random.default_rng(3)
     order = np.argsort(u, kind='stable')
     first = np.flatnonzero(np.concatenate(([True], u[order][1:] != u[order][:-1])))
