@@ -257,13 +257,18 @@ def run_native(args, cfg):
     flops = 6.0 * Hd * I * B                                     # 2KI fwd + 4KI bwd per sampled user
     achieved = flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else None
     tc_path = any(k.startswith('k_umma') for k in kernels)
+    traffic = None
+    tpath = os.path.join(ROOT, 'profiles', 'r1_traffic.json')
+    if tc_path and os.path.exists(tpath) and cfg['name'] == C3['name']:
+        tb = json.load(open(tpath))['dram_bytes_per_launch']      # ncu --set full capture of the same command
+        traffic = tb['k_umma_cdae_loss'] + tb['k_umma_gemm_mn'] + tb['k_umma_gemm_kk']
     n_params = 2 * I * m._L.ld + U * m._L.ld + m._L.ld + m._L.items_pad
     launches_total = int(launches)
     adam_gbs = 28.0 * n_params / (kernels.get('k_adam', float('nan')) * 1e-3) / 1e9
     roofline = {'kernel': ('k_umma_cdae_loss + k_umma_gemm x2 (tcgen05 3xTF32: output layer fwd + fused loss epilogue, '
                            'dW\'^T and dh)') if tc_path else 'k_sgemm x3 (fp32 FFMA path)',
                 'bound': 'tensor', 'achieved': achieved, 'peak': peaks['tf'], 'unit': 'TFLOP/s',
-                'frac': (achieved / peaks['tf']) if achieved else None, 'traffic': None,
+                'frac': (achieved / peaks['tf']) if achieved else None, 'traffic': traffic,
                 'note': 'achieved counts the algorithmic fp32 flops (6*K*I per sampled user); every product is issued '
                         'as 3 TF32 MMAs (half the bf16 rate each), so the issued-MMA rate is 3x achieved against a '
                         'TF32 peak of half the bf16 peak' if tc_path else 'CUDA-core path',
