@@ -6,6 +6,8 @@
 #include <algorithm>
 #include <cmath>
 #include <cstring>
+#include <functional>
+#include <thread>
 #include <unordered_set>
 #include <vector>
 
@@ -287,61 +289,81 @@ int drb_cdae_corruption_keep_mt(drb_rng* rng, const int32_t* uids, int32_t batch
   return DRB_OK;
 }
 
+}  // extern "C"
+
 // ------------------------------------------------------------------------------------------ evaluation candidates
-int drb_eval_candidates(int64_t n_users, const int64_t* test_indptr, const int64_t* test_item,
-                        const double* test_val, const int64_t* black_indptr, const int64_t* black_item,
-                        int32_t train_evaluation, int64_t n_items, double threshold, int64_t n_pos, double n_neg,
-                        int32_t n_neg_is_frac, int32_t generate_negative_pairs, int64_t seed,
-                        int64_t cand_capacity, int64_t* cand_off, int64_t* cand, int64_t* pos_off, int64_t* pos,
-                        uint8_t* skipped) {
-  if (n_users < 0 || !test_indptr || !cand_off || !pos_off || !skipped)
-    return drb_fail(DRB_E_INVALID, "drb_eval_candidates: bad argument");
-  const int64_t seed_i = seed;
+namespace {
+
+struct EvalShared {
+  const int64_t* test_indptr; const int64_t* test_item; const double* test_val;
+  const int64_t* black_row; const int64_t* black_indptr; const int32_t* black_iid;
+  const int64_t* raw_sorted; const int32_t* raw_to_iid; int64_t n_map;
+  int train_evaluation; int64_t n_items; double threshold; int64_t n_pos; double n_neg; int n_neg_is_frac;
+  int generate; int64_t seed;
+};
+
+struct EvalChunk {   // output of one worker: users [lo, hi)
+  int64_t lo, hi;
+  std::vector<int64_t> cand, pos, cand_len, pos_len;
+  std::vector<uint8_t> skipped;
+};
+
+// is raw item `it` one of the training positives of evaluated user u?
+inline bool in_train(const EvalShared& S, int64_t u, int64_t it) {
+  if (!S.black_row || S.black_row[u] < 0) return false;
+  const int64_t* p = std::lower_bound(S.raw_sorted, S.raw_sorted + S.n_map, it);
+  if (p == S.raw_sorted + S.n_map || *p != it) return false;
+  const int32_t iid = S.raw_to_iid[p - S.raw_sorted];
+  const int64_t r = S.black_row[u];
+  return std::binary_search(S.black_iid + S.black_indptr[r], S.black_iid + S.black_indptr[r + 1], iid);
+}
+
+void eval_worker(const EvalShared& S, EvalChunk& C) {
   drb_rng g;
-  std::vector<int64_t> p_items, n_pool, negs, picked, all;
-  int64_t co = 0, po = 0;
-  cand_off[0] = 0; pos_off[0] = 0;
-  for (int64_t u = 0; u < n_users; u++) {
-    int64_t s = seed_i + u;  // ranking_evaluation.py:111-116
+  std::vector<int64_t> p_items, n_pool, negs, picked, all, chosen;
+  for (int64_t u = C.lo; u < C.hi; u++) {
+    int64_t s = S.seed + u;  // ranking_evaluation.py:111-116
     g.seed((uint64_t)(s < 0 ? -s : s));
-    skipped[u] = 1;
-    cand_off[u + 1] = co; pos_off[u + 1] = po;
-    const int64_t lo = test_indptr[u], hi = test_indptr[u + 1];
-    p_items.clear(); n_pool.clear();
-    for (int64_t r = lo; r < hi; r++) (test_val[r] >= threshold ? p_items : n_pool).push_back(test_item[r]);
-    std::vector<int64_t> chosen;
-    if (n_pos < 0) {
+    C.skipped.push_back(1); C.cand_len.push_back(0); C.pos_len.push_back(0);
+    const int64_t lo = S.test_indptr[u], hi = S.test_indptr[u + 1];
+    p_items.clear(); n_pool.clear(); chosen.clear();
+    for (int64_t r = lo; r < hi; r++) (S.test_val[r] >= S.threshold ? p_items : n_pool).push_back(S.test_item[r]);
+    if (S.n_pos < 0) {
       chosen = p_items;
     } else {
-      if ((int64_t)p_items.size() < n_pos) continue;  // :175-176
-      picked.resize(n_pos);
-      sample_indices(g, (int64_t)p_items.size(), n_pos, picked.data());
+      if ((int64_t)p_items.size() < S.n_pos) continue;  // :175-176
+      picked.resize(S.n_pos);
+      sample_indices(g, (int64_t)p_items.size(), S.n_pos, picked.data());
       for (int64_t i : picked) chosen.push_back(p_items[i]);
     }
     negs.clear();
-    if (n_neg < 0) {
+    if (S.n_neg < 0) {
       negs = n_pool;
     } else {
-      int64_t want = n_neg_is_frac ? (int64_t)(n_neg * (double)chosen.size()) : (int64_t)n_neg;  // :187-188
-      int64_t take = std::min<int64_t>(want, (int64_t)n_pool.size());
+      const int64_t want = S.n_neg_is_frac ? (int64_t)(S.n_neg * (double)chosen.size()) : (int64_t)S.n_neg;  // :187-188
+      const int64_t take = std::min<int64_t>(want, (int64_t)n_pool.size());
       picked.resize(take);
       sample_indices(g, (int64_t)n_pool.size(), take, picked.data());
       for (int64_t i : picked) negs.push_back(n_pool[i]);
-      if ((int64_t)negs.size() < want && generate_negative_pairs) {
+      if ((int64_t)negs.size() < want && S.generate) {
         // blacklist = train positives (unless evaluating on train) U test positives  (:193-201)
-        std::vector<int64_t> black(p_items);
-        if (!train_evaluation && black_indptr)
-          black.insert(black.end(), black_item + black_indptr[u], black_item + black_indptr[u + 1]);
-        std::sort(black.begin(), black.end());
-        black.erase(std::unique(black.begin(), black.end()), black.end());
-        if (n_items - (int64_t)black.size() < want) continue;  // :202-207
+        std::vector<int64_t> tp(p_items);
+        std::sort(tp.begin(), tp.end());
+        tp.erase(std::unique(tp.begin(), tp.end()), tp.end());
+        int64_t black_size = (int64_t)tp.size();
+        if (!S.train_evaluation && S.black_row && S.black_row[u] >= 0) {
+          const int64_t r = S.black_row[u];
+          black_size = S.black_indptr[r + 1] - S.black_indptr[r];
+          for (int64_t it : tp) black_size += in_train(S, u, it) ? 0 : 1;
+        }
+        if (S.n_items - black_size < want) continue;  // :202-207
         std::unordered_set<int64_t> in_negs(negs.begin(), negs.end());
         while ((int64_t)negs.size() < want) {
-          int64_t it = g.randint(0, n_items - 1);  // :211 (raw/internal id confusion kept)
-          if (!std::binary_search(black.begin(), black.end(), it) && !in_negs.count(it)) {
-            negs.push_back(it);
-            in_negs.insert(it);
-          }
+          const int64_t it = g.randint(0, S.n_items - 1);  // :211 (raw/internal id confusion kept)
+          if (std::binary_search(tp.begin(), tp.end(), it) || in_negs.count(it)) continue;
+          if (!S.train_evaluation && in_train(S, u, it)) continue;
+          negs.push_back(it);
+          in_negs.insert(it);
         }
       }
     }
@@ -349,13 +371,58 @@ int drb_eval_candidates(int64_t n_users, const int64_t* test_indptr, const int64
     all.insert(all.end(), negs.begin(), negs.end());
     if (all.empty()) continue;  // :217-218
     shuffle_i64(g, (int64_t)all.size(), all.data());
-    if (co + (int64_t)all.size() > cand_capacity)
+    C.cand.insert(C.cand.end(), all.begin(), all.end());
+    C.pos.insert(C.pos.end(), chosen.begin(), chosen.end());
+    C.cand_len.back() = (int64_t)all.size();
+    C.pos_len.back() = (int64_t)chosen.size();
+    C.skipped.back() = 0;
+  }
+}
+
+}  // namespace
+
+extern "C" {
+
+int drb_eval_candidates(int64_t n_users, const int64_t* test_indptr, const int64_t* test_item,
+                        const double* test_val, const int64_t* black_row, const int64_t* black_indptr,
+                        const int32_t* black_iid, const int64_t* raw_sorted, const int32_t* raw_to_iid,
+                        int64_t n_map, int32_t train_evaluation, int64_t n_items, double threshold, int64_t n_pos,
+                        double n_neg, int32_t n_neg_is_frac, int32_t generate_negative_pairs, int64_t seed,
+                        int32_t n_threads, int64_t cand_capacity, int64_t* cand_off, int64_t* cand, int64_t* pos_off,
+                        int64_t* pos, uint8_t* skipped) {
+  if (n_users < 0 || !test_indptr || !cand_off || !pos_off || !skipped)
+    return drb_fail(DRB_E_INVALID, "drb_eval_candidates: bad argument");
+  if (black_row && (!black_indptr || !black_iid || (n_map > 0 && (!raw_sorted || !raw_to_iid))))
+    return drb_fail(DRB_E_INVALID, "drb_eval_candidates: incomplete training-positives description");
+  EvalShared S{test_indptr, test_item, test_val, black_row, black_indptr, black_iid, raw_sorted, raw_to_iid, n_map,
+               train_evaluation, n_items, threshold, n_pos, n_neg, n_neg_is_frac, generate_negative_pairs, seed};
+  int nt = std::max(1, std::min<int>(n_threads, 64));
+  if (n_users < 256) nt = 1;
+  std::vector<EvalChunk> chunks(nt);
+  const int64_t per = (n_users + nt - 1) / nt;
+  for (int t = 0; t < nt; t++) {
+    chunks[t].lo = std::min<int64_t>(n_users, t * per);
+    chunks[t].hi = std::min<int64_t>(n_users, (t + 1) * per);
+  }
+  if (nt == 1) {
+    eval_worker(S, chunks[0]);
+  } else {   // users are independent (each has its own Random(seed + idx)): one contiguous block per thread
+    std::vector<std::thread> th;
+    for (int t = 0; t < nt; t++) th.emplace_back(eval_worker, std::cref(S), std::ref(chunks[t]));
+    for (auto& x : th) x.join();
+  }
+  int64_t co = 0, po = 0;
+  cand_off[0] = 0; pos_off[0] = 0;
+  for (auto& C : chunks) {
+    if (co + (int64_t)C.cand.size() > cand_capacity)
       return drb_fail(DRB_E_INVALID, "drb_eval_candidates: candidate buffer too small");
-    if (cand) std::copy(all.begin(), all.end(), cand + co);
-    if (pos) std::copy(chosen.begin(), chosen.end(), pos + po);
-    co += (int64_t)all.size(); po += (int64_t)chosen.size();
-    cand_off[u + 1] = co; pos_off[u + 1] = po;
-    skipped[u] = 0;
+    if (cand) std::copy(C.cand.begin(), C.cand.end(), cand + co);
+    if (pos) std::copy(C.pos.begin(), C.pos.end(), pos + po);
+    for (int64_t u = C.lo; u < C.hi; u++) {
+      co += C.cand_len[u - C.lo]; po += C.pos_len[u - C.lo];
+      cand_off[u + 1] = co; pos_off[u + 1] = po;
+      skipped[u] = C.skipped[u - C.lo];
+    }
   }
   return DRB_OK;
 }

@@ -92,6 +92,7 @@ __global__ void __launch_bounds__(128) k_rank_candidates(CandScoreArgs a, int P)
   }
   for (int c = warp; c < cnt; c += 4) {
     const int iid = a.cand[(int64_t)u * a.max_cand + c];
+    if (iid < 0) continue;                                       // unknown raw item (skip_invalid_items)
     if (a.novelty && row_contains(seen, nseen, iid)) continue;   // warp-uniform
     const float* tr = a.table + (int64_t)iid * a.ld_t;
     float dot = 0.f, tss = 0.f;

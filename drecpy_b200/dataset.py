@@ -103,6 +103,16 @@ class InteractionData:
         pos = np.clip(pos, 0, len(s) - 1)
         return np.where(s[pos] == items, order[pos], -1)
 
+    def users_to_uids(self, users):
+        """Vectorised raw -> internal user ids; unknown ids map to -1."""
+        users = np.asarray(users)
+        if 'sorted_users' not in self._cache:
+            order = np.argsort(self._users, kind='stable')
+            self._cache['sorted_users'] = (self._users[order], order.astype(np.int64))
+        s, order = self._cache['sorted_users']
+        pos = np.clip(np.searchsorted(s, users), 0, len(s) - 1)
+        return np.where(s[pos] == users, order[pos], -1)
+
     @property
     def raw_items(self):
         return self._items

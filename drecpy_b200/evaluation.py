@@ -8,6 +8,7 @@ are scored in one batched GPU call (model.rank_batch) instead of 4 Python thread
 Models without rank_batch (any object with .rank) and non-integer raw ids go through the same protocol in Python.
 """
 import math
+import os
 import random
 
 import numpy as np
@@ -90,21 +91,17 @@ def _group_by_user(data):
 
 
 def _train_positive_items(model, users, thr):
-    """per evaluated user: raw item ids of its training rows with interaction >= thr
-    (ranking_evaluation.py:196-199), as CSR-like (indptr, sorted items)."""
+    """What drb_eval_candidates needs to test `raw item in training positives of user` without copying anything:
+    the training CSR of positives over internal ids, the training row of every evaluated user, and the sorted
+    raw-item -> internal-id map (ranking_evaluation.py:196-199)."""
     data = model._data if hasattr(model, '_data') else InteractionData.from_dataset(model.interaction_dataset)
     data.assign_internal_ids()
-    p_indptr, p_iid, _ = data.rows_by_user(thr)
-    uids = np.array([(-1 if (u := data.user_to_uid(x)) is None else u) for x in users.tolist()], np.int64)
-    lens = np.where(uids >= 0, p_indptr[np.maximum(uids, 0) + 1] - p_indptr[np.maximum(uids, 0)], 0)
-    indptr = np.zeros(len(users) + 1, np.int64)
-    np.cumsum(lens, out=indptr[1:])
-    items = np.empty(indptr[-1], np.int64)
-    raw = data.raw_items
-    for r in np.flatnonzero(lens):
-        u = uids[r]
-        items[indptr[r]:indptr[r + 1]] = np.sort(raw[p_iid[p_indptr[u]:p_indptr[u + 1]]])
-    return indptr, items
+    indptr, indices, _ = data.csr(thr)
+    rows = np.ascontiguousarray(data.users_to_uids(users).astype(np.int64))
+    data.items_to_iids(np.zeros(0, np.int64))          # builds the cached sorted map
+    raw_sorted, order = data._cache['sorted_items']
+    return (rows, np.ascontiguousarray(indptr), np.ascontiguousarray(indices),
+            np.ascontiguousarray(raw_sorted.astype(np.int64)), np.ascontiguousarray(order.astype(np.int32)))
 
 
 def generate_candidates(model, data, users, t_indptr, t_order, thr, n_pos, n_neg, generate_negative_pairs,
@@ -114,11 +111,9 @@ def generate_candidates(model, data, users, t_indptr, t_order, thr, n_pos, n_neg
     n_users = len(users)
     t_item = np.ascontiguousarray(data.item[t_order].astype(np.int64))
     t_val = np.ascontiguousarray(data.interaction[t_order].astype(np.float64))
-    if train_evaluation or not generate_negative_pairs:
-        b_indptr, b_item = np.zeros(n_users + 1, np.int64), np.zeros(1, np.int64)
-    else:
-        b_indptr, b_item = _train_positive_items(model, users, thr)
-        if len(b_item) == 0: b_item = np.zeros(1, np.int64)
+    black = None
+    if not train_evaluation and generate_negative_pairs:
+        black = _train_positive_items(model, users, thr)
     is_frac = isinstance(n_neg, float)
     per_user_neg = 0 if n_neg is None else (int(np.ceil(n_neg * np.diff(t_indptr).max())) if is_frac else int(n_neg))
     cap = int(len(t_item) + n_users * per_user_neg + 16)
@@ -127,12 +122,13 @@ def generate_candidates(model, data, users, t_indptr, t_order, thr, n_pos, n_neg
     cand = np.empty(cap, np.int64)
     pos = np.empty(cap, np.int64)
     skipped = np.zeros(n_users, np.uint8)
+    bp = [_lib.np_ptr(a) for a in black] if black is not None else [None] * 5
     _lib.check(_lib.load().drb_eval_candidates(
-        n_users, _lib.np_ptr(t_indptr), _lib.np_ptr(t_item), _lib.np_ptr(t_val), _lib.np_ptr(b_indptr),
-        _lib.np_ptr(b_item), int(bool(train_evaluation)), int(model.n_items), float(thr),
+        n_users, _lib.np_ptr(t_indptr), _lib.np_ptr(t_item), _lib.np_ptr(t_val), bp[0], bp[1], bp[2], bp[3], bp[4],
+        len(black[3]) if black is not None else 0, int(bool(train_evaluation)), int(model.n_items), float(thr),
         -1 if n_pos is None else int(n_pos), -1.0 if n_neg is None else float(n_neg), int(is_frac),
-        int(bool(generate_negative_pairs)), int(seed), cap, _lib.np_ptr(cand_off), _lib.np_ptr(cand),
-        _lib.np_ptr(pos_off), _lib.np_ptr(pos), _lib.np_ptr(skipped)))
+        int(bool(generate_negative_pairs)), int(seed), min(16, os.cpu_count() or 1), cap, _lib.np_ptr(cand_off),
+        _lib.np_ptr(cand), _lib.np_ptr(pos_off), _lib.np_ptr(pos), _lib.np_ptr(skipped)))
     return cand_off, cand[:cand_off[-1]], pos_off, pos[:pos_off[-1]], skipped, t_item, t_val
 
 
@@ -163,6 +159,97 @@ def _candidates_python(rng, test_rows, train_pos_items, test_pos_items, n_items,
     if len(all_items) == 0: return None
     rng.shuffle(all_items)
     return all_items, positives
+
+
+# ------------------------------------------------------------------------------------------ vectorised protocol
+def _fast_evaluation(model, data, users, t_indptr, t_order, thr, n_pos, n_neg, generate, train_evaluation, seed,
+                     novelty, metrics, ks):
+    """Same protocol as the per-user loop below for the built-in metrics, with every per-user Python step replaced
+    by array operations that perform the SAME float64 operations in the SAME order per user (sequential DCG sums,
+    sequential sum over users), so the rounded results are identical.  Returns None when a corner case needs the
+    general path (duplicate items inside one user's candidate / positive list)."""
+    cand_off, cand, pos_off, pos, skipped, t_item, t_val = generate_candidates(
+        model, data, users, t_indptr, t_order, thr, n_pos, n_neg, generate, train_evaluation, seed)
+    active = np.flatnonzero(skipped == 0)
+    t_item, t_val = t_item[:t_indptr[-1]], t_val[:t_indptr[-1]]    # rows of the evaluated users only
+    metric_sums = {(m.name, k_): [0, 0] for m in metrics for k_ in ks}
+    if len(active):
+        known = model._data.users_to_uids(users[active]) >= 0       # model.rank asserts the user is known -> skipped
+        active = active[known]
+    if len(active):
+        n = len(active)
+        c_lens = (cand_off[active + 1] - cand_off[active]).astype(np.int64)
+        p_lens = (pos_off[active + 1] - pos_off[active]).astype(np.int64)
+        c_off = np.zeros(n + 1, np.int64); np.cumsum(c_lens, out=c_off[1:])
+        p_off = np.zeros(n + 1, np.int64); np.cumsum(p_lens, out=p_off[1:])
+        c_src = np.arange(c_off[-1]) - np.repeat(c_off[:-1], c_lens) + np.repeat(cand_off[active], c_lens)
+        p_src = np.arange(p_off[-1]) - np.repeat(p_off[:-1], p_lens) + np.repeat(pos_off[active], p_lens)
+        c_flat, p_flat = cand[c_src], pos[p_src]
+        c_seg, p_seg = np.repeat(np.arange(n), c_lens), np.repeat(np.arange(n), p_lens)
+        big = int(max(c_flat.max(initial=0), t_item.max(initial=0), p_flat.max(initial=0))) + 2
+        if big * (len(users) + 1) >= 2 ** 62 or c_flat.min(initial=0) < 0 or t_item.min(initial=0) < 0:
+            return None
+        # corner case: duplicate items inside one candidate or positive list -> general path
+        ck = np.sort(c_seg * big + c_flat)
+        pk = np.sort(p_seg * big + p_flat)
+        if (len(ck) > 1 and (ck[1:] == ck[:-1]).any()) or (len(pk) > 1 and (pk[1:] == pk[:-1]).any()):
+            return None
+        ranked, n_out = model.rank_arrays(users[active], c_flat, c_off, novelty=novelty)
+        c_max, L = int(c_lens.max()), ranked.shape[1]
+        # relevancy lookup: first test row of (user, item), else 0  (ranking_evaluation.py:223)
+        t_seg = np.repeat(np.arange(len(users)), np.diff(t_indptr))
+        remap = np.full(len(users), -1, np.int64); remap[active] = np.arange(n)
+        t_keep = remap[t_seg] >= 0
+        t_key = remap[t_seg[t_keep]] * big + t_item[t_keep]
+        u_key, first = np.unique(t_key, return_index=True)
+        u_val = t_val[t_keep][first]
+
+        def relevancy(seg, items):
+            key = seg * big + items
+            pos_ = np.clip(np.searchsorted(u_key, key), 0, max(len(u_key) - 1, 0))
+            hit = (u_key[pos_] == key) if len(u_key) else np.zeros(len(key), bool)
+            return np.where(hit, u_val[pos_], 0.0) if len(u_key) else np.zeros(len(key))
+        rel_rank = np.zeros((n, L))
+        valid = np.arange(L)[None, :] < n_out[:, None]
+        rr, cc = np.nonzero(valid)
+        rel_rank[rr, cc] = relevancy(rr, ranked[rr, cc])
+        rel_cand = np.full((n, c_max), -np.inf)
+        rel_cand[c_seg, np.arange(c_off[-1]) - np.repeat(c_off[:-1], c_lens)] = relevancy(c_seg, c_flat)
+        ideal = -np.sort(-rel_cand, axis=1)                       # relevancies of the ideal list, descending
+        # hits: ranked item is one of the user's sampled positives
+        p_key = np.sort(p_seg * big + p_flat)
+        rk = np.where(valid, np.arange(n)[:, None] * big + np.maximum(ranked, 0), -1)
+        pp = np.clip(np.searchsorted(p_key, rk), 0, max(len(p_key) - 1, 0))
+        is_pos = valid & (p_key[pp] == rk) if len(p_key) else np.zeros_like(valid)
+        for m in metrics:
+            for k_ in ks:
+                kk = min(k_, L)
+                n_rec = np.minimum(n_out, k_)
+                if type(m) is NDCG:
+                    cur = np.zeros(n); best = np.zeros(n)
+                    for i in range(min(k_, max(L, c_max))):       # sequential sums, position by position
+                        d = math.log2(2 + i)
+                        if i < L:
+                            cur = np.where(i < n_rec, cur + (2 ** rel_rank[:, i] - 1) / d, cur)
+                        if i < c_max:
+                            ok = (i < c_lens)
+                            best = np.where(ok, best + (2 ** np.where(ok, ideal[:, i], 0.0) - 1) / d, best)
+                    good = best != 0                                # ZeroDivisionError -> metric skipped for the user
+                    vals = (cur[good] / best[good]).tolist()
+                else:
+                    hits = is_pos[:, :kk].sum(axis=1)
+                    if type(m) is Precision:
+                        good = n_rec > 0
+                        vals = (hits[good] / n_rec[good]).tolist()
+                    else:                                           # HitRatio, Recall: / number of positives
+                        good = p_lens > 0
+                        vals = (hits[good] / p_lens[good]).tolist()
+                acc = 0
+                for v in vals:                                      # same left-to-right float additions as the loop
+                    acc += v
+                metric_sums[(m.name, k_)] = [acc, len(vals)]
+    return {m + f'@{k_}': round(metric_sums[(m, k_)][0] / metric_sums[(m, k_)][1], 4)
+            if metric_sums[(m, k_)][1] > 0 else 0 for m, k_ in metric_sums}
 
 
 # ------------------------------------------------------------------------------------------ the protocol
@@ -199,6 +286,14 @@ def ranking_evaluation(model, ds_test=None, n_test_users=None, k=10, n_pos_inter
     record = kwds.get('record', None)      # optional list collecting (user, candidates, ranked) for tests
 
     native_ids = np.issubdtype(data.item.dtype, np.integer)
+    fast = (native_ids and hasattr(model, 'rank_arrays') and record is None and not kwds.get('force_python', False)
+            and all(type(m) in (HitRatio, NDCG, Precision, Recall) and getattr(m, 'strong_relevancy', True)
+                    for m in metrics))
+    if fast:
+        res = _fast_evaluation(model, data, users, t_indptr, t_order, interaction_threshold, n_pos_interactions,
+                               n_neg_interactions, generate_negative_pairs, train_evaluation, seed, novelty, metrics, k)
+        if res is not None:
+            return res
     if native_ids:
         cand_off, cand, pos_off, pos, skipped, t_item, t_val = generate_candidates(
             model, data, users, t_indptr, t_order, interaction_threshold, n_pos_interactions, n_neg_interactions,

@@ -283,6 +283,32 @@ class DeepRecommenderABC(ABC):
         items = self._data.raw_items
         return [items[out_i[r, :n_out[r]]].tolist() for r in range(len(uids))], out_s, n_out
 
+    def rank_arrays(self, user_ids, cand, cand_off, novelty=True, chunk=32768):
+        """Batched rank() over flat arrays: user_ids [n] raw, cand raw item ids with offsets cand_off [n+1].
+        Returns (ranked raw items [n, Cmax] padded with -1, n_out [n]).  Unknown items are skipped
+        (skip_invalid_items=True); users must be known."""
+        data = self._data
+        uids = data.users_to_uids(user_ids).astype(np.int32)
+        assert (uids >= 0).all(), 'unknown user in rank_arrays'
+        n = len(uids)
+        lens = np.diff(cand_off).astype(np.int64)
+        c_max = int(max(1, lens.max() if n else 1))
+        iids = data.items_to_iids(cand).astype(np.int32)
+        padded = np.full((n, c_max), -1, np.int32)
+        rows = np.repeat(np.arange(n), lens)
+        cols = np.arange(len(cand)) - np.repeat(cand_off[:-1], lens)
+        padded[rows, cols] = iids
+        out_items = np.full((n, c_max), -1, np.int64)
+        n_out = np.zeros(n, np.int32)
+        raw = data.raw_items
+        for o in range(0, n, chunk):
+            oi, _, on = self._rank_batch(uids[o:o + chunk], padded[o:o + chunk], lens[o:o + chunk].astype(np.int32),
+                                         novelty)
+            valid = np.arange(c_max)[None, :] < on[:, None]
+            out_items[o:o + chunk] = np.where(valid, raw[np.where(valid, oi, 0)], -1)
+            n_out[o:o + chunk] = on
+        return out_items, n_out
+
     def _standardize_value(self, value):
         return (value - self.min_interaction) / (self.max_interaction - self.min_interaction)
 

@@ -284,18 +284,22 @@ int drb_debug_umma_gemm(drb_ctx* ctx, const float* a_hi, const float* a_lo, int3
  * replaces: DRecPy/Evaluation/Processes/ranking_evaluation.py:108-116,163-219 -- per-user
  * random.Random(seed+idx), rng.sample of positives / negatives, randint generation of extra negatives,
  * rng.shuffle.  Test rows are grouped by user in evaluation order (row order inside a user preserved):
- * test_indptr[n_users+1], test_item (raw ids), test_val.  black_indptr/black_item: per evaluated user, sorted
- * raw item ids of its training-set positives (ignored when train_evaluation != 0).
- * n_pos < 0 / n_neg < 0 mean "None"; user u is seeded with abs(seed + u); n_neg_is_frac != 0 means n_neg = int(frac * n_positives).
+ * test_indptr[n_users+1], test_item (raw ids), test_val.  Training positives (ignored when train_evaluation != 0
+ * or black_row == NULL): black_row[u] = training-set row (internal uid) of evaluated user u or -1;
+ * black_indptr / black_iid = the training CSR of positives over internal item ids (sorted per row);
+ * raw_sorted[n_map] / raw_to_iid[n_map] = sorted raw item ids and their internal ids.
+ * n_pos < 0 / n_neg < 0 mean "None"; user u is seeded with abs(seed + u); n_neg_is_frac != 0 means
+ * n_neg = int(frac * n_positives).  Users are independent, so the work is split over n_threads host threads.
  * Outputs: cand_off[n_users+1] (caller passes capacity via cand_capacity), cand (raw ids, shuffled),
- * n_pos_out[u] (number of sampled positives), pos (raw ids of the sampled positives, pos_off[n_users+1]),
- * skipped[u] != 0 when the reference returns early for that user. */
+ * pos (raw ids of the sampled positives, pos_off[n_users+1]), skipped[u] != 0 when the reference returns early
+ * for that user. */
 int drb_eval_candidates(int64_t n_users, const int64_t* test_indptr, const int64_t* test_item,
-                        const double* test_val, const int64_t* black_indptr, const int64_t* black_item,
-                        int32_t train_evaluation, int64_t n_items, double threshold, int64_t n_pos,
+                        const double* test_val, const int64_t* black_row, const int64_t* black_indptr,
+                        const int32_t* black_iid, const int64_t* raw_sorted, const int32_t* raw_to_iid,
+                        int64_t n_map, int32_t train_evaluation, int64_t n_items, double threshold, int64_t n_pos,
                         double n_neg, int32_t n_neg_is_frac, int32_t generate_negative_pairs, int64_t seed,
-                        int64_t cand_capacity, int64_t* cand_off, int64_t* cand, int64_t* pos_off, int64_t* pos,
-                        uint8_t* skipped);
+                        int32_t n_threads, int64_t cand_capacity, int64_t* cand_off, int64_t* cand, int64_t* pos_off,
+                        int64_t* pos, uint8_t* skipped);
 
 #ifdef __cplusplus
 }

@@ -167,3 +167,48 @@ def test_ranking_evaluation_argument_errors():
         drb.ranking_evaluation(m, train, generate_negative_pairs=True)
     with pytest.raises(AssertionError, match='Expected "metrics" argument to be a list'):
         drb.ranking_evaluation(m, train, metrics=drb.NDCG())
+
+
+class FakeBatchModel(FakeModel):
+    """FakeModel plus the batched rank_arrays() entry the vectorised evaluator uses."""
+
+    def rank_arrays(self, user_ids, cand, cand_off, novelty=True, chunk=0):
+        n = len(user_ids)
+        c_max = int(np.diff(cand_off).max())
+        out = np.full((n, c_max), -1, np.int64)
+        n_out = np.zeros(n, np.int32)
+        for r, user in enumerate(np.asarray(user_ids).tolist()):
+            ranked = [it for _, it in self.rank(user, cand[cand_off[r]:cand_off[r + 1]].tolist(), novelty=novelty)]
+            out[r, :len(ranked)] = ranked
+            n_out[r] = len(ranked)
+        return out, n_out
+
+
+def test_vectorised_evaluation_equals_per_user_protocol(golden_dir):
+    with open(os.path.join(golden_dir, 'ranking.json')) as f:
+        g = json.load(f)
+    tr, te = np.array(g['train_rows']), np.array(g['test_rows'])
+    train = drb.InteractionData(*[tr[:, c].astype(np.int64) for c in range(3)])
+    train.assign_internal_ids()
+    test = drb.InteractionData(*[te[:, c].astype(np.int64) for c in range(3)])
+    model = FakeBatchModel(train)
+    for name, case in g['cases'].items():
+        fast = drb.ranking_evaluation(model, test, **case['kwargs'])
+        assert fast == case['result'], name                       # the live reference's own result
+    # random protocol settings on a bigger synthetic split: fast path == general path
+    u, i, v = drb.synthetic_interactions(300, 400, 9000, seed=21)
+    v = v - 1                                                     # include zero-valued (sub-threshold) rows
+    rng = np.random.default_rng(5)
+    mask = rng.random(len(u)) < 0.2
+    train = drb.InteractionData(u[~mask], i[~mask], v[~mask])
+    train.assign_internal_ids()
+    test = drb.InteractionData(u[mask], i[mask], v[mask])
+    model = FakeBatchModel(train)
+    for kw in [dict(k=[1, 5, 10], n_pos_interactions=1, n_neg_interactions=100, generate_negative_pairs=True,
+                    novelty=True, seed=10),
+               dict(k=3, n_pos_interactions=None, n_neg_interactions=None, novelty=False),
+               dict(k=[2, 7], n_pos_interactions=2, n_neg_interactions=0.5, generate_negative_pairs=True, seed=4),
+               dict(k=10, n_pos_interactions=None, n_neg_interactions=5, novelty=True, n_test_users=50)]:
+        fast = drb.ranking_evaluation(model, test, verbose=False, **kw)
+        slow = drb.ranking_evaluation(model, test, verbose=False, force_python=True, **kw)
+        assert fast == slow, (kw, fast, slow)
