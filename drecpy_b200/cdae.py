@@ -292,23 +292,34 @@ class CDAE(DeepRecommenderABC):
         if dp is None or not dp.active:
             _lib.check(lib.drb_cdae_step(*ptrs))
             return
-        # data parallel: PREP -> all-reduce label histogram -> GRADS -> all-reduce gradients -> UPDATE
-        _lib.check(lib.drb_cdae_step_phases(*ptrs, 1))
-        if self.label_mode == 'batch_mean':
-            dp.all_reduce_sum(self._label_count)
-        _lib.check(lib.drb_cdae_step_phases(*ptrs, 2))
-        # user-row gradients: all-gather the B x K rows (never the U x K table), add them locally
+        # data parallel: the collectives run on NCCL's stream while the next phase computes
+        #   PREP | all-reduce(label histogram) || GRADS_A | GRADS_B | all-reduce(dW'^T) || GRADS_C |
+        #   all-gather(uids, dz1 rows) -> dV | all-reduce(dW, db, db') | UPDATE
         torch = self._torch
+        dist, L = dp.dist, self._L
+        PREP, GA, UPD, GB, GC = 1, 2, 4, 8, 16
+        _lib.check(lib.drb_cdae_step_phases(*ptrs, PREP))
+        h_lab = None
+        if self.label_mode == 'batch_mean':
+            h_lab = dist.all_reduce(self._label_count, op=dist.ReduceOp.SUM, group=dp.group, async_op=True)
+        _lib.check(lib.drb_cdae_step_phases(*ptrs, GA))
+        if h_lab is not None:
+            h_lab.wait()
+        _lib.check(lib.drb_cdae_step_phases(*ptrs, GB))
+        h_w2t = dist.all_reduce(self._grads[:L.off_w], op=dist.ReduceOp.SUM, group=dp.group, async_op=True)
+        _lib.check(lib.drb_cdae_step_phases(*ptrs, GC))
+        # user-row gradients: all-gather the B x K rows (never the U x K table), add them locally
         B = uids_dev.numel()
         if not hasattr(self, '_dp_gather') or self._dp_gather[0].shape[0] != B * dp.world:
-            self._dp_gather = (torch.empty((B * dp.world, self._L.ld), dtype=torch.float32, device=self._dev),
+            self._dp_gather = (torch.empty((B * dp.world, L.ld), dtype=torch.float32, device=self._dev),
                                torch.empty(B * dp.world, dtype=torch.int32, device=self._dev))
         rows_all, uids_all = self._dp_gather
-        dp.dist.all_gather_into_tensor(rows_all, self._dz1[:B], group=dp.group)
-        dp.dist.all_gather_into_tensor(uids_all, uids_dev, group=dp.group)
+        dist.all_gather_into_tensor(rows_all, self._dz1[:B], group=dp.group)
+        dist.all_gather_into_tensor(uids_all, uids_dev, group=dp.group)
         _lib.check(lib.drb_cdae_scatter_user_rows(self._native, _lib.t_ptr(uids_all), _lib.t_ptr(rows_all), B * dp.world))
-        dp.all_reduce_sum(self._grads[:self._L.off_v])       # W', W, b, b' gradients (dense)
-        _lib.check(lib.drb_cdae_step_phases(*ptrs, 4))
+        dp.all_reduce_sum(self._grads[L.off_w:L.off_v])      # dW, db, db' (dense)
+        h_w2t.wait()
+        _lib.check(lib.drb_cdae_step_phases(*ptrs, UPD))
 
     def launch_count(self):
         return _lib.load().drb_ctx_launch_count(self._ctx)

@@ -389,37 +389,35 @@ int drb_cdae_step_phases(drb_cdae* m, const int32_t* uids, const int32_t* keep_o
   if ((r = launch_batch_prep(ctx, bp, batch))) return r;
   }  // PREP (data parallel: the caller all-reduces the label histogram here)
 
-  if (phases & DRB_PHASE_GRADS) {
-  // 2. K1: h = sigmoid(s * sum_kept W[i] + V[u] + b)
-  if ((r = cdae_hidden_into(m, uids, batch, keep_off, keep_used, s, w.h))) return r;
-
   const float inv_count = (float)(1.0 / ((double)gbatch * (double)I));
-  int n_blocks = 0;
-  if (m->use_umma) {
-    // 3-5 on the tensor cores (umma.cu): 3xTF32 split products, TMA-fed, TMEM accumulators
-    const int n2 = m->n2, bp = m->batch_pad;
+  const int n2 = m->n2, bp = m->batch_pad;
+  if (phases & DRB_PHASE_GRADS_A) {
+  // 2. K1: h = sigmoid(s * sum_kept W[i] + V[u] + b)   (needs no labels: overlaps the label all-reduce when DP)
+  if ((r = cdae_hidden_into(m, uids, batch, keep_off, keep_used, s, w.h))) return r;
+  if (m->use_umma) {   // tf32 hi/lo operand splits for the tensor-core GEMMs (umma.cu)
     if ((r = launch_split_tf32(ctx, w.h, batch, ld, ld, w.h_hi, w.h_lo, w.hT_hi, w.hT_lo, bp, m->d.hidden))) return r;
     if ((r = launch_split_tf32(ctx, P + L.off_w2t, I, ld, ld, w.w2t_hi, w.w2t_lo, w.wT_hi, w.wT_lo, L.items_pad, -1)))
       return r;
+  }
+  }
+
+  UmmaOperands o2{w.dzt_hi, w.dzt_lo, 32, w.hT_hi, w.hT_lo, bp, n2};
+  o2.a_tiled_nib = drb_dz_nib(I);
+  o2.a_tiled_rows = (int64_t)((m->d.max_batch + 127) / 128) * o2.a_tiled_nib * 128;
+  if (phases & DRB_PHASE_GRADS_B) {
+  int n_blocks = 0;
+  if (m->use_umma) {
+    // 3-4 on the tensor cores: 3xTF32 split products, TMA-fed, TMEM accumulators
     UmmaOperands o1{w.h_hi, w.h_lo, ld, w.w2t_hi, w.w2t_lo, ld, I};
     if ((r = launch_umma_cdae_loss(ctx, o1, batch, I, ld, w.dzt_hi, w.dzt_lo, L.items_pad, P + L.off_b2,
                                    per_user ? nullptr : w.label_count, per_user ? w.label_bits : nullptr,
                                    m->words_per_row, m->d.loss_kind, inv_count, gbatch, w.loss_part, &n_blocks)))
       return r;
     // dW'^T = dz^T h (I x K); the constant-one feature at column `hidden` yields db' = colsum(dz)
-    UmmaOperands o2{w.dzt_hi, w.dzt_lo, 32, w.hT_hi, w.hT_lo, bp, n2};
-    o2.a_tiled_nib = drb_dz_nib(I);
-    o2.a_tiled_rows = (int64_t)((m->d.max_batch + 127) / 128) * o2.a_tiled_nib * 128;
     // 209 item tiles on 148 SMs would run as two uneven waves; two reduction halves (3 even waves) accumulate atomically
     const int s2 = batch >= 1024 ? 2 : 1;
     if ((r = launch_umma_store(ctx, o2, true, I, n2, batch, s2, G + L.off_w2t, ld, ld, m->d.hidden, G + L.off_b2,
                                m->d.hidden, s2 > 1)))
-      return r;
-    // dh = dz W'^T (B x K), split over the item range
-    UmmaOperands o3{w.dzt_hi, w.dzt_lo, 32, w.wT_hi, w.wT_lo, L.items_pad, n2};
-    o3.a_tiled_nib = o2.a_tiled_nib;
-    o3.a_tiled_rows = o2.a_tiled_rows;
-    if ((r = launch_umma_store(ctx, o3, false, batch, n2, I, m->splits, w.dh_part, ld, ld, m->d.hidden, nullptr, -1)))
       return r;
   } else {
   // 3. K2: z2 = h W'^T + b', p = sigmoid, loss terms, dL/dz2 (never materialises p)
@@ -440,8 +438,19 @@ int drb_cdae_step_phases(drb_cdae* m, const int32_t* uids, const int32_t* keep_o
   g2.A = w.dz; g2.lda = L.items_pad; g2.B = w.h; g2.ldb = ld; g2.C = G + L.off_w2t; g2.ldc = ld;
   g2.M = I; g2.N = ld; g2.Kred = batch; g2.splits = 1;
   if ((r = launch_gemm(ctx, LAYOUT_MN, EPI_STORE, g2))) return r;
+  }
+  m->n_loss_blocks = n_blocks;
+  }  // GRADS_B (data parallel: dW'^T and db' can be all-reduced from here on)
 
+  if (phases & DRB_PHASE_GRADS_C) {
   // 5. K3: dh = dz W'^T  (B x K), split over the item range, partials reduced by the dz1 kernel
+  if (m->use_umma) {
+    UmmaOperands o3{w.dzt_hi, w.dzt_lo, 32, w.wT_hi, w.wT_lo, L.items_pad, n2};
+    o3.a_tiled_nib = o2.a_tiled_nib;
+    o3.a_tiled_rows = o2.a_tiled_rows;
+    if ((r = launch_umma_store(ctx, o3, false, batch, n2, I, m->splits, w.dh_part, ld, ld, m->d.hidden, nullptr, -1)))
+      return r;
+  } else {
   GemmArgs g3{};
   g3.A = w.dz; g3.lda = L.items_pad; g3.B = P + L.off_w2t; g3.ldb = ld; g3.C = w.dh_part; g3.ldc = ld;
   g3.M = batch; g3.N = ld; g3.Kred = I; g3.splits = m->splits;
@@ -458,8 +467,7 @@ int drb_cdae_step_phases(drb_cdae* m, const int32_t* uids, const int32_t* keep_o
   sc.d = w.dz1; sc.ld = ld; sc.gtable = G + L.off_w;
   sc.growbias = a->skip_user_grad ? nullptr : G + L.off_v;   // data parallel: user rows are exchanged instead
   if ((r = launch_scatter(ctx, sc, batch))) return r;
-  m->n_loss_blocks = n_blocks;
-  }  // GRADS (data parallel: the caller all-reduces the gradient arena here)
+  }  // GRADS_C (data parallel: the caller exchanges dz1 rows and all-reduces dW, db here)
 
   if (!(phases & DRB_PHASE_UPDATE)) return DRB_OK;
   const float inv_count_u = (float)(1.0 / ((double)gbatch * (double)I));

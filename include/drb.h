@@ -158,7 +158,15 @@ typedef struct {
   int32_t skip_user_grad;  /* data parallel: leave dV to drb_cdae_scatter_user_rows (rows are all-gathered) */
 } drb_cdae_step_args;
 
-enum { DRB_PHASE_PREP = 1, DRB_PHASE_GRADS = 2, DRB_PHASE_UPDATE = 4, DRB_PHASE_ALL = 7 };
+enum {
+  DRB_PHASE_PREP = 1,      /* clear gradients, label histogram / bitmap, philox mask */
+  DRB_PHASE_GRADS_A = 2,   /* hidden layer (gather) + tf32 operand splits: needs no labels */
+  DRB_PHASE_UPDATE = 4,    /* Adam + loss */
+  DRB_PHASE_GRADS_B = 8,   /* output layer + loss epilogue, dW'^T, db' */
+  DRB_PHASE_GRADS_C = 16,  /* dh, dz1, db, scatter into dW (and dV unless skip_user_grad) */
+  DRB_PHASE_GRADS = 2 | 8 | 16,
+  DRB_PHASE_ALL = 31
+};
 
 int drb_cdae_create(drb_ctx* ctx, const drb_cdae_desc* desc, drb_cdae** out);
 int drb_cdae_destroy(drb_cdae* m);
@@ -171,7 +179,8 @@ int drb_cdae_step(drb_cdae* m, const int32_t* uids, const int32_t* keep_off, con
                   int32_t batch, const drb_cdae_step_args* args, float* loss_out);
 /* The same step in phases, for data parallelism over user mini-batches (one process per GPU, replicated weights):
  *   PREP   -> label histogram of the local batch; the caller all-reduces drb_cdae_label_count_buffer()
- *   GRADS  -> forward + backward with global_batch in the label mean / loss mean / L2 scale; the caller
+ *             (GRADS_A can run while that all-reduce is in flight, GRADS_C while dW'^T is being all-reduced)
+ *   GRADS  -> (= GRADS_A | GRADS_B | GRADS_C) forward + backward with global_batch in the label mean / loss mean / L2 scale; the caller
  *             all-reduces the gradient arena [0, off_v) and, with skip_user_grad, all-gathers the (uid, dz1 row)
  *             pairs of drb_cdae_dz1_buffer() and adds them with drb_cdae_scatter_user_rows (rows of V never
  *             travel, only B x K activations' gradients do)
