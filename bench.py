@@ -214,7 +214,7 @@ def run_native(args, cfg):
     ms_total = e0.elapsed_time(e1)
     clock_info = clocks.stop()
     launches = m.launch_count() - launches0
-    loss_value = float(loss_dev[0].item())
+    loss_value = float(m._dp.global_loss(loss_dev).item())      # collective when data parallel: every rank calls it
     t = torch.tensor([ms_total], device=dev)
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)

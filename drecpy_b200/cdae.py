@@ -406,33 +406,3 @@ class CDAE(DeepRecommenderABC):
         if threshold is None:
             return ranked
         return [x for x in ranked if x[0] >= threshold]
-
-    # ------------------------------------------------------------------ persistence
-    def __getstate__(self):
-        st = {k: v for k, v in self.__dict__.items()
-              if k not in ('_native', '_ctx', '_torch', '_workspace', '_slots', '_loss_host', '_stream', '_lock',
-                           '_mask_rng', '_sampler', '_dp', '_dp_dev', '_dp_gather', '_label_count', '_dz1', '_loss_dev', '_next', '_d_indptr', '_d_indices', '_d_seen_indptr', '_d_seen_indices',
-                           '_logger', '_dev')}
-        for k in ('_params', '_adam_m', '_adam_v', '_grads'):
-            if k in st: st[k] = st[k].cpu()
-        st['_L'] = {f: getattr(self._L, f) for f, _ in _lib.CdaeLayout._fields_} if getattr(self, '_L', None) is not None else None
-        st['epoch_weights'] = {}
-        return st
-
-    def __setstate__(self, st):
-        import logging
-        import threading
-        L = st.pop('_L', None)
-        self.__dict__.update(st)
-        self._lock = threading.RLock()
-        self._logger = logging.getLogger(f'{self.__class__.__name__}_CLOGGER')
-        self._native = self._ctx = None
-        self._dp = DataParallel()
-        if L is not None and self.fitted:
-            import torch
-            self._torch = torch
-            self._L = _lib.CdaeLayout(**L)
-            self._dev = torch.device(self.device or f'cuda:{torch.cuda.current_device()}')
-            for k in ('_params', '_adam_m', '_adam_v', '_grads'):
-                setattr(self, k, getattr(self, k).to(self._dev))
-            self._build_native()

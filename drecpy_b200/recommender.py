@@ -333,6 +333,45 @@ class DeepRecommenderABC(ABC):
         if self.verbose: self._logger.warning(msg)
 
     # ------------------------------------------------------------------ persistence (recommender_abc.py:503-524)
+    _TRANSIENT = ('_native', '_ctx', '_torch', '_workspace', '_slots', '_loss_host', '_loss_dev', '_stream', '_lock',
+                  '_mask_rng', '_sampler', '_dp', '_dp_dev', '_dp_gather', '_label_count', '_dz1', '_next',
+                  '_d_indptr', '_d_indices', '_d_seen_indptr', '_d_seen_indices', '_dev_sparse', '_logger', '_dev')
+
+    def __getstate__(self):
+        """joblib/pickle: device arenas go to host tensors, native handles are dropped and rebuilt on load."""
+        st = {k: v for k, v in self.__dict__.items() if k not in self._TRANSIENT}
+        for k in ('_params', '_adam_m', '_adam_v', '_grads'):
+            if k in st: st[k] = st[k].cpu()
+        L = getattr(self, '_L', None)
+        st['_L'] = (type(L), {f: (list(getattr(L, f)) if hasattr(getattr(L, f), '__len__') else getattr(L, f))
+                              for f, _ in L._fields_}) if L is not None else None
+        st['epoch_weights'] = {}
+        return st
+
+    def __setstate__(self, st):
+        L = st.pop('_L', None)
+        self.__dict__.update(st)
+        self._lock = threading.RLock()
+        self._logger = logging.getLogger(f'{self.__class__.__name__}_CLOGGER')
+        self._native = self._ctx = None
+        if L is not None and self.fitted:
+            import torch
+            from .parallel import DataParallel
+            self._torch = torch
+            cls, fields = L
+            self._L = cls()
+            for f, v in fields.items():
+                if isinstance(v, list):
+                    arr = getattr(self._L, f)
+                    for j, x in enumerate(v): arr[j] = x
+                else:
+                    setattr(self._L, f, v)
+            self._dp = DataParallel()
+            self._dev = torch.device(self.device or f'cuda:{torch.cuda.current_device()}')
+            for k in ('_params', '_adam_m', '_adam_v', '_grads'):
+                setattr(self, k, getattr(self, k).to(self._dev))
+            self._build_native()
+
     def save(self, save_path):
         from joblib import dump
         dump(self, save_path)

