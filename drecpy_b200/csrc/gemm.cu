@@ -17,8 +17,6 @@ namespace {
 constexpr int BM = 128, BK = 16, THREADS = 256, PAD = 4;
 constexpr float KERAS_EPS = 1e-7f;
 
-struct Frag4 { float4 v[2]; };
-
 template <int BN, int LAYOUT, int EPI>
 __global__ void __launch_bounds__(THREADS) k_sgemm(GemmArgs g) {
   constexpr int TN = BN / 16;  // 8 (BN=128) or 4 (BN=64)

@@ -1,16 +1,19 @@
-// K2 / K3 on the 5th-generation tensor cores (sm_100a): fp32-accurate GEMM as 3 x TF32 split products
-// (A_hi*B_hi + A_hi*B_lo + A_lo*B_hi) issued with tcgen05.mma.kind::tf32, operands staged in shared memory by TMA
-// (cp.async.bulk.tensor, 128-byte swizzle), accumulator in TMEM, epilogue through tcgen05.ld.
+// K3 on the 5th-generation tensor cores (sm_100a): the two backward products of the CDAE output layer,
+// dW'^T = dz^T h and dh = dz W'^T, as fp32-accurate 3 x TF32 split GEMMs (A_lo*B_hi + A_hi*B_lo + A_hi*B_hi) issued
+// with tcgen05.mma.kind::tf32, operands staged in shared memory by TMA (cp.async.bulk.tensor, 128-byte swizzle),
+// accumulator in TMEM, epilogue through tcgen05.ld.  (The forward product with the fused loss epilogue is the
+// persistent kernel in umma_loss.cu.)
 //
-// Replaces the same reference call sites as gemm.cu (DRecPy/Recommender/cdae.py:76,78-79 and the matching
-// tape.gradient products, recommender_abc.py:203).  Why 3xTF32: north_star asks for forward scores within 1e-5
-// relative of the reference's fp32 TensorFlow path, which a single TF32/BF16 MMA (2^-11 / 2^-8 operand rounding)
-// cannot give; splitting every fp32 operand into hi = rna_tf32(x), lo = x - hi keeps ~22 mantissa bits.
+// Replaces the tape.gradient products of DRecPy/Recommender/recommender_abc.py:203 for cdae.py:76.  Why 3xTF32:
+// north_star asks for fp32 parity (forward scores within 1e-5 relative); a single TF32/BF16 MMA rounds operands to
+// 2^-11 / 2^-8.  Splitting every fp32 operand into hi = rna_tf32(x), lo = x - hi keeps ~22 mantissa bits.
 //
 // Warp roles (192 threads, one output tile per CTA): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer
 // (one elected lane), warps 2..5 = epilogue (each owns the 32 TMEM lanes of its sub-partition).
-// Tile 128 x BN x 32 floats; operands are K-major [rows][32 floats] tiles in the canonical SWIZZLE_128B layout, or,
-// for the transposed use of dL/dz in dW' = dz^T h, MN-major tiles assembled from four 32x32 TMA boxes.
+// Tile 128 x BN x 32 floats.  B is K-major ([rows][32 floats], SWIZZLE_128B).  A is dz: K-major for dh, or -- for the
+// transposed use in dW'^T -- MN-major, which tcgen05 accepts for 32-bit operands only in the SWIZZLE_128B_BASE32B
+// layout (four 32x32 TMA boxes per tile).  dz normally arrives in the 128x32 tile-major layout written by the loss
+// kernel, so every box is one contiguous 16 KB / 4 KB read.
 #include "umma_common.cuh"
 
 namespace {
@@ -23,8 +26,7 @@ struct Smem {
   static constexpr int A_BYTES = BM * BK * 4;           // one of A_hi / A_lo
   static constexpr int B_BYTES = BN * BK * 4;
   static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
-  static constexpr int TOTAL = STAGES * STAGE_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/ +
-                               2 * BN * 4 /*epilogue column constants*/;
+  static constexpr int TOTAL = STAGES * STAGE_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/;
 };
 
 struct UmmaParams {
@@ -35,15 +37,9 @@ struct UmmaParams {
   float* extra_col; int extra_col_index;   // EPI_STORE: column `extra_col_index` of the product goes to extra_col[m]
   int atomic_out;           // splits > 1: accumulate all partials into C / extra_col with vector atomics (C pre-zeroed)
   int a_tiled_nib;          // > 0: A lives in the 128x32 tile-major dz layout with this many 32-column blocks per row tile
-  // EPI_CDAE_LOSS
-  float* dz_hi; float* dz_lo;              // [M][ldc]
-  const float* bias;                       // b' [N]
-  const float* label_count; const uint32_t* label_bits; int words_per_row;
-  int loss_kind; float inv_count; int batch;
-  float* loss_part;                        // [grid.x * grid.y]
 };
 
-template <int BN, bool A_MN, int EPI>
+template <int BN, bool A_MN>
 __global__ void __launch_bounds__(THREADS, 1)
 k_umma_gemm(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
             const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo, UmmaParams p) {
@@ -164,27 +160,9 @@ k_umma_gemm(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
     // ------------------------------------------------------------------ epilogue (warps 2..5)
     const int q = warp & 3;                       // TMEM sub-partition of this warp
     const int m = m0 + q * 32 + lane;             // one accumulator row per thread
-    float* s_bias = reinterpret_cast<float*>(smem_raw + (bars + 256u - smem_u32(smem_raw)));
-    float* s_tgt = s_bias + BN;
-    uint32_t lbits[(BN + 31) / 32];
-    if (EPI == EPI_CDAE_LOSS) {
-      // per-column constants of this tile, fetched once while the main loop runs (b' and the batch-mean label)
-      for (int c = threadIdx.x - 64; c < BN; c += 128) {
-        const int nn = n0 + c;
-        s_bias[c] = (nn < p.N) ? __ldg(p.bias + nn) : 0.f;
-        s_tgt[c] = (p.label_count && nn < p.N) ? __ldg(p.label_count + nn) / (float)p.batch : 0.f;
-      }
-#pragma unroll
-      for (int wi = 0; wi < (BN + 31) / 32; wi++)
-        lbits[wi] = (p.label_bits && m < p.M && (n0 >> 5) + wi < p.words_per_row)
-                        ? __ldg(p.label_bits + (int64_t)m * p.words_per_row + (n0 >> 5) + wi) : 0u;
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-    }
     mbar_wait(tmem_full_bar, 0);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    float loss_local = 0.f;
-    float* crow = nullptr;
-    if (EPI == EPI_STORE) crow = p.C + (p.atomic_out ? 0 : (int64_t)blockIdx.z * p.M * p.ldc) + (int64_t)m * p.ldc;
+    float* crow = p.C + (p.atomic_out ? 0 : (int64_t)blockIdx.z * p.M * p.ldc) + (int64_t)m * p.ldc;
 #pragma unroll 1
     for (int c = 0; c < BN; c += 16) {
       uint32_t r[16];
@@ -196,82 +174,26 @@ k_umma_gemm(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
       }
       const int n = n0 + c;
       if (m >= p.M) continue;
-      if (EPI == EPI_STORE) {
 #pragma unroll
-        for (int j4 = 0; j4 < 4; j4++) {
-          const int nn = n + j4 * 4;
-          if (nn < p.n_store) {   // n_store % 4 == 0
-            const float4 v = make_float4(nn + 0 < p.n_valid ? __uint_as_float(r[j4 * 4]) : 0.f,
-                                         nn + 1 < p.n_valid ? __uint_as_float(r[j4 * 4 + 1]) : 0.f,
-                                         nn + 2 < p.n_valid ? __uint_as_float(r[j4 * 4 + 2]) : 0.f,
-                                         nn + 3 < p.n_valid ? __uint_as_float(r[j4 * 4 + 3]) : 0.f);
-            if (p.atomic_out) atomicAdd(reinterpret_cast<float4*>(crow + nn), v);
-            else *reinterpret_cast<float4*>(crow + nn) = v;
-          }
-        }
-        if (p.extra_col && p.extra_col_index >= n && p.extra_col_index < n + 16 && (p.atomic_out || blockIdx.z == 0)) {
-#pragma unroll
-          for (int j = 0; j < 16; j++)
-            if (n + j == p.extra_col_index) {
-              if (p.atomic_out) atomicAdd(p.extra_col + m, __uint_as_float(r[j]));
-              else p.extra_col[m] = __uint_as_float(r[j]);
-            }
-        }
-      } else {  // EPI_CDAE_LOSS: z2 -> p -> loss term and dL/dz2, written as the hi/lo split the backward GEMMs read
-        float hi[16], lo[16];
-        uint32_t wcur = 0;   // per-user label bits of this 16-column chunk (one 32-bit word covers it)
-#pragma unroll
-        for (int wi = 0; wi < (BN + 31) / 32; wi++)
-          if ((c >> 5) == wi) wcur = lbits[wi];
-        wcur >>= (c & 31);
-#pragma unroll
-        for (int j = 0; j < 16; j++) {
-          const int nn = n + j;
-          float g = 0.f;
-          if (nn < p.N) {
-            const float z = __uint_as_float(r[j]) + s_bias[c + j];
-            const float pr = __frcp_rn(1.0f + __expf(-z));
-            const float tgt = p.label_count ? s_tgt[c + j] : (float)((wcur >> j) & 1u);
-            float dp;
-            if (p.loss_kind == DRB_LOSS_BCE) {
-              const float one_m = 1.0f - KERAS_EPS;
-              const float pc = fminf(fmaxf(pr, KERAS_EPS), one_m);
-              const float da = pc + KERAS_EPS, db = 1.0f - pc + KERAS_EPS;
-              loss_local -= tgt * __logf(da) + (1.0f - tgt) * __logf(db);
-              const bool inside = (pr >= KERAS_EPS) && (pr <= one_m);
-              dp = inside ? -(tgt * db - (1.0f - tgt) * da) * __frcp_rn(da * db) * p.inv_count : 0.f;
-            } else {
-              if (p.label_count) loss_local += pr * pr - 2.0f * pr * tgt + tgt;
-              else loss_local += (pr - tgt) * (pr - tgt);
-              dp = 2.0f * (pr - tgt) * p.inv_count;
-            }
-            g = dp * pr * (1.0f - pr);
-          }
-          uint32_t h;
-          asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(g));
-          hi[j] = __uint_as_float(h);
-          lo[j] = g - hi[j];
-        }
-#pragma unroll
-        for (int j4 = 0; j4 < 4; j4++) {
-          const int nn = n + j4 * 4;
-          if (nn < p.ldc) {
-            const int64_t o = (int64_t)m * p.ldc + nn;
-            *reinterpret_cast<float4*>(p.dz_hi + o) = make_float4(hi[j4 * 4], hi[j4 * 4 + 1], hi[j4 * 4 + 2], hi[j4 * 4 + 3]);
-            *reinterpret_cast<float4*>(p.dz_lo + o) = make_float4(lo[j4 * 4], lo[j4 * 4 + 1], lo[j4 * 4 + 2], lo[j4 * 4 + 3]);
-          }
+      for (int j4 = 0; j4 < 4; j4++) {
+        const int nn = n + j4 * 4;
+        if (nn < p.n_store) {   // n_store % 4 == 0
+          const float4 v = make_float4(nn + 0 < p.n_valid ? __uint_as_float(r[j4 * 4]) : 0.f,
+                                       nn + 1 < p.n_valid ? __uint_as_float(r[j4 * 4 + 1]) : 0.f,
+                                       nn + 2 < p.n_valid ? __uint_as_float(r[j4 * 4 + 2]) : 0.f,
+                                       nn + 3 < p.n_valid ? __uint_as_float(r[j4 * 4 + 3]) : 0.f);
+          if (p.atomic_out) atomicAdd(reinterpret_cast<float4*>(crow + nn), v);
+          else *reinterpret_cast<float4*>(crow + nn) = v;
         }
       }
-    }
-    if (EPI == EPI_CDAE_LOSS) {
+      if (p.extra_col && p.extra_col_index >= n && p.extra_col_index < n + 16 && (p.atomic_out || blockIdx.z == 0)) {
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) loss_local += __shfl_xor_sync(0xffffffffu, loss_local, o);
-      // four epilogue warps -> one partial per CTA through shared memory (reuse the tail of the barrier block)
-      volatile float* lred = reinterpret_cast<volatile float*>(smem_raw + (bars + 8u * (2 * S::STAGES + 2) - smem_u32(smem_raw)));
-      if (lane == 0) lred[q] = loss_local;
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      if (warp == 2 && lane == 0)
-        p.loss_part[blockIdx.y * gridDim.x + blockIdx.x] = lred[0] + lred[1] + lred[2] + lred[3];
+        for (int j = 0; j < 16; j++)
+          if (n + j == p.extra_col_index) {
+            if (p.atomic_out) atomicAdd(p.extra_col + m, __uint_as_float(r[j]));
+            else p.extra_col[m] = __uint_as_float(r[j]);
+          }
+      }
     }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -318,7 +240,7 @@ __global__ void __launch_bounds__(256) k_split_tf32(const float* __restrict__ sr
   }
 }
 
-template <int BN, bool A_MN, int EPI>
+template <int BN, bool A_MN>
 int run_umma(drb_ctx* ctx, const UmmaOperands& o, const UmmaParams& p, int* n_blocks_out) {
   CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
   int r;
@@ -336,14 +258,14 @@ int run_umma(drb_ctx* ctx, const UmmaOperands& o, const UmmaParams& p, int* n_bl
   if ((r = make_map(&mb_lo, o.b_lo, p.Kred, o.b_rows, o.ldb, BK, BN))) return r;
   dim3 grid((p.N + BN - 1) / BN, (p.M + BM - 1) / BM, p.splits);
   if (n_blocks_out) *n_blocks_out = grid.x * grid.y;
-  auto kern = k_umma_gemm<BN, A_MN, EPI>;
+  auto kern = k_umma_gemm<BN, A_MN>;
   static bool attr_set = false;   // per template instantiation
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem<BN>::TOTAL);
     if (e != cudaSuccess) return drb_fail(DRB_E_CUDA, "cudaFuncSetAttribute(smem=%d) failed: %s", Smem<BN>::TOTAL, cudaGetErrorString(e));
     attr_set = true;
   }
-  drb_prof_scope prof_(ctx, A_MN ? "k_umma_gemm_mn" : (EPI == EPI_CDAE_LOSS ? "k_umma_gemm_loss" : "k_umma_gemm_kk"));
+  drb_prof_scope prof_(ctx, A_MN ? "k_umma_gemm_mn" : "k_umma_gemm_kk");
   kern<<<grid, THREADS, Smem<BN>::TOTAL, ctx->stream>>>(ma_hi, ma_lo, mb_hi, mb_lo, p);
   DRB_LAUNCH_CHECK(ctx, "k_umma_gemm");
   return DRB_OK;
@@ -373,8 +295,8 @@ int launch_umma_store(drb_ctx* ctx, const UmmaOperands& o, bool a_mn_major, int 
   if (N > 256) return drb_fail(DRB_E_INVALID, "umma store GEMM: N must be <= 256 (hidden width)");
 #define DRB_UMMA_CASE(BN)                                                        \
   if (N <= BN) {                                                                 \
-    if (a_mn_major) return run_umma<BN, true, EPI_STORE>(ctx, o, p, nullptr);    \
-    return run_umma<BN, false, EPI_STORE>(ctx, o, p, nullptr);                   \
+    if (a_mn_major) return run_umma<BN, true>(ctx, o, p, nullptr);               \
+    return run_umma<BN, false>(ctx, o, p, nullptr);                              \
   }
   DRB_UMMA_CASE(64)
   DRB_UMMA_CASE(128)
