@@ -36,7 +36,8 @@ class CdaeDesc(C.Structure):
 class CdaeStepArgs(C.Structure):
     _fields_ = [('learning_rate', f32), ('beta1', f32), ('beta2', f32), ('epsilon', f32), ('reg_rate', f32),
                 ('t', i32 * 5), ('philox_seed', u64), ('philox_step', u64), ('global_batch', i32),
-                ('slot_offset', i32), ('skip_user_grad', i32)]
+                ('slot_offset', i32), ('skip_user_grad', i32), ('shard_items', i32), ('item_offset', i32),
+                ('n_items_global', i64), ('v_rows', vp)]
 
 
 class DmfLayout(C.Structure):
@@ -101,6 +102,7 @@ SIGNATURES = {
     'drb_cdae_loss_buffer': (C.c_int, [vp, P(vp)]),
     'drb_dmf_loss_buffer': (C.c_int, [vp, P(vp)]),
     'drb_cdae_dz1_buffer': (C.c_int, [vp, P(vp), P(i64)]),
+    'drb_cdae_h_buffer': (C.c_int, [vp, P(vp), P(i64)]),
     'drb_cdae_scatter_user_rows': (C.c_int, [vp, vp, vp, i32]),
     'drb_cdae_step_host': (C.c_int, [vp, vp, vp, vp, i32, P(CdaeStepArgs), vp]),
     'drb_cdae_hidden': (C.c_int, [vp, vp, i32, vp]),

@@ -57,6 +57,22 @@ class CDAE(DeepRecommenderABC):
         # data parallel over user mini-batches: batch_size is PER RANK, the step uses the global batch
         self._dp = kwds.get('data_parallel') or DataParallel()
         self._dp_sampler = kwds.get('dp_sampler', 'replay')
+        # parallel_mode='data'  : replicated weights, the mini-batch is split over ranks (gradients all-reduced)
+        # parallel_mode='items' : W, W', b' sharded by item range and V by user range; every rank runs the whole
+        #                         global batch against its items and only batch x hidden activations are exchanged
+        self._parallel_mode = kwds.get('parallel_mode', 'data')
+        assert self._parallel_mode in ('data', 'items')
+        self._sharded = self._parallel_mode == 'items' and self._dp.active
+        if self._sharded:
+            w, r = self._dp.world, self._dp.rank
+            per_i, per_u = -(-self.n_items // w), -(-self.n_users // w)
+            self._ilo, self._ihi = min(self.n_items, r * per_i), min(self.n_items, (r + 1) * per_i)
+            self._ulo, self._uhi = min(self.n_users, r * per_u), min(self.n_users, (r + 1) * per_u)
+            assert self._ihi > self._ilo and self._uhi > self._ulo, 'more ranks than items / users'
+            self._max_batch = int(max(batch_size * w, kwds.get('score_batch', 0)))
+        else:
+            self._ilo, self._ihi, self._ulo, self._uhi = 0, self.n_items, 0, self.n_users
+        self._nI, self._nU = self._ihi - self._ilo, self._uhi - self._ulo
         self._alloc_and_init(kwds.get('init_weights', None))
         self._build_native()
         self._sampler = kwds.get('sampler') or PointSampler(self._data, neg_ratio, self.interaction_threshold, self.seed)
@@ -69,7 +85,7 @@ class CDAE(DeepRecommenderABC):
         torch = self._torch
         lib = _lib.load()
         L = _lib.CdaeLayout()
-        _lib.check(lib.drb_cdae_layout(self.n_users, self.n_items, self.hidden_factors, C.byref(L)))
+        _lib.check(lib.drb_cdae_layout(self._nU, self._nI, self.hidden_factors, C.byref(L)))
         self._L = L
         dev = self._dev
         self._params = torch.zeros(L.total, dtype=torch.float32, device=dev)
@@ -89,11 +105,12 @@ class CDAE(DeepRecommenderABC):
             v = torch.as_tensor(np.asarray(v), dtype=torch.float32)
             assert tuple(v.shape) == tuple(init[k].shape), f'{k}: expected shape {tuple(init[k].shape)}'
             init[k] = v
-        self.W.copy_(init['W'])
-        self.W_.copy_(init['W_'])
-        self.V.copy_(init['V'])
+        il, ih, ul, uh = self._ilo, self._ihi, self._ulo, self._uhi      # the whole range unless item-sharded
+        self.W.copy_(init['W'][il:ih])
+        self.W_.copy_(init['W_'][:, il:ih])
+        self.V.copy_(init['V'][ul:uh])
         self.b.copy_(init['b'])
-        self.b_.copy_(init['b_'])
+        self.b_.copy_(init['b_'][il:ih])
 
     def _build_native(self):
         torch = self._torch
@@ -105,17 +122,19 @@ class CDAE(DeepRecommenderABC):
         _lib.check(lib.drb_ctx_set_stream(self._ctx, _lib.vp(self._stream.cuda_stream)))
         pos = self._data.csr(self.interaction_threshold)     # positives: cdae.py:61
         seen = self._data.csr()                              # every stored row: cdae.py:93-98
+        if self._sharded:                                    # keep the columns of this rank's item range, re-based
+            pos, seen = [self._restrict_columns(c, self._ilo, self._ihi) for c in (pos, seen)]
         self._h_indptr = np.ascontiguousarray(pos[0])
         self._h_indices = np.ascontiguousarray(pos[1])
         self._d_indptr = torch.from_numpy(self._h_indptr).to(dev)
         self._d_indices = torch.from_numpy(self._h_indices).to(dev)
         self._d_seen_indptr = torch.from_numpy(np.ascontiguousarray(seen[0])).to(dev)
         self._d_seen_indices = torch.from_numpy(np.ascontiguousarray(seen[1])).to(dev)
-        ws_bytes = lib.drb_cdae_workspace_bytes(self.n_users, self.n_items, self.hidden_factors, self._max_batch)
+        ws_bytes = lib.drb_cdae_workspace_bytes(self._nU, self._nI, self.hidden_factors, self._max_batch)
         assert ws_bytes > 0
         self._workspace = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
         d = _lib.CdaeDesc()
-        d.n_users, d.n_items, d.hidden = self.n_users, self.n_items, self.hidden_factors
+        d.n_users, d.n_items, d.hidden = self._nU, self._nI, self.hidden_factors
         d.params, d.adam_m, d.adam_v, d.grads = (self._params.data_ptr(), self._adam_m.data_ptr(),
                                                  self._adam_v.data_ptr(), self._grads.data_ptr())
         d.csr_indptr, d.csr_indices = self._d_indptr.data_ptr(), self._d_indices.data_ptr()
@@ -134,11 +153,25 @@ class CDAE(DeepRecommenderABC):
         _lib.check(lib.drb_cdae_loss_buffer(self._native, C.byref(ptr)))
         off = ptr.value - self._workspace.data_ptr()
         self._loss_dev = self._workspace[off:off + 8].view(torch.float32)
+        _lib.check(lib.drb_cdae_h_buffer(self._native, C.byref(ptr), C.byref(cnt)))
+        off = ptr.value - self._workspace.data_ptr()
+        self._h_buf = self._workspace[off:off + 4 * cnt.value].view(torch.float32).view(-1, L.ld)
         _lib.check(lib.drb_cdae_dz1_buffer(self._native, C.byref(ptr), C.byref(cnt)))
         off = ptr.value - self._workspace.data_ptr()
         self._dz1 = self._workspace[off:off + 4 * cnt.value].view(torch.float32).view(-1, L.ld)
 
+    @staticmethod
+    def _restrict_columns(csr, lo, hi):
+        indptr, indices, data = csr
+        keep = (indices >= lo) & (indices < hi)
+        rows = np.repeat(np.arange(len(indptr) - 1), np.diff(indptr))[keep]
+        out = np.zeros(len(indptr), np.int64)
+        np.cumsum(np.bincount(rows, minlength=len(indptr) - 1), out=out[1:])
+        return out, (indices[keep] - lo).astype(np.int32), data[keep]
+
     def _setup_staging(self, batch_size):
+        if self._sharded:
+            batch_size = batch_size * self._dp.world
         torch = self._torch
         deg = np.diff(self._h_indptr)
         cap = int(np.sort(deg)[::-1][:batch_size].sum()) if len(deg) else 0   # exact bound on a batch's nnz
@@ -161,15 +194,15 @@ class CDAE(DeepRecommenderABC):
 
     @property
     def W(self):
-        return self._seg(self._L.off_w, self.n_items, self._L.ld)[:, :self.hidden_factors]
+        return self._seg(self._L.off_w, self._nI, self._L.ld)[:, :self.hidden_factors]
 
     @property
     def W_(self):     # reference layout [K, I]; stored item-major
-        return self._seg(self._L.off_w2t, self.n_items, self._L.ld)[:, :self.hidden_factors].t()
+        return self._seg(self._L.off_w2t, self._nI, self._L.ld)[:, :self.hidden_factors].t()
 
     @property
     def V(self):
-        return self._seg(self._L.off_v, self.n_users, self._L.ld)[:, :self.hidden_factors]
+        return self._seg(self._L.off_v, self._nU, self._L.ld)[:, :self.hidden_factors]
 
     @property
     def b(self):
@@ -177,7 +210,7 @@ class CDAE(DeepRecommenderABC):
 
     @property
     def b_(self):
-        return self._params[self._L.off_b2:self._L.off_b2 + self.n_items]
+        return self._params[self._L.off_b2:self._L.off_b2 + self._nI]
 
     def _params_tensor(self):
         return self._params
@@ -194,7 +227,9 @@ class CDAE(DeepRecommenderABC):
         a.philox_seed = self._mask_seed
         a.philox_step = s
         dp = getattr(self, '_dp', None)
-        if dp is not None and dp.active:
+        if dp is not None and dp.active and getattr(self, '_sharded', False):
+            a.shard_items, a.item_offset, a.n_items_global = 1, self._ilo, self.n_items
+        elif dp is not None and dp.active:
             a.global_batch = self._cur_batch * dp.world
             a.slot_offset = self._cur_batch * dp.rank
             a.skip_user_grad = 1
@@ -204,7 +239,14 @@ class CDAE(DeepRecommenderABC):
         """Host side of one step: sample B triples (only uid is used, cdae.py:52) and build the mask inputs."""
         lib = _lib.load()
         dp = self._dp
-        if dp.active and self._dp_sampler == 'replay':
+        if self._sharded:
+            # every rank replays the same stream and processes the WHOLE global batch against its own items
+            n = batch_size * dp.world
+            self._sampler.sample_arrays(n, out=(slot['uid_np'], slot['iid'], slot['val']))
+            if self.rng_mode == 'mt19937':
+                raise NotImplementedError("item-sharded training needs rng_mode='philox'")
+            batch_size = n
+        elif dp.active and self._dp_sampler == 'replay':
             # every rank replays the global stream and keeps its slice (== a single-process run with batch N*B)
             gu, _, _ = self._sampler.sample_arrays(batch_size * dp.world)
             lo, hi = dp.shard(batch_size * dp.world)
@@ -246,7 +288,7 @@ class CDAE(DeepRecommenderABC):
             self._next = None
             self._cur_batch = batch_size
             if self._dp.active:
-                self._enqueue_step_dp(slot, batch_size, reg_rate)
+                self._enqueue_step_dp(slot, batch_size * (self._dp.world if self._sharded else 1), reg_rate)
             else:
                 args = self.step_args(reg_rate)
                 _lib.check(lib.drb_cdae_step_host(self._native, _lib.np_ptr(slot['uid_np']),
@@ -263,7 +305,7 @@ class CDAE(DeepRecommenderABC):
             if not want_loss:
                 return None
             if self._dp.active:
-                return float(self._dp.global_loss(self._dp_dev['loss']).item())
+                return self.global_loss(self._dp_dev['loss'])
             ev.synchronize()
             return float(self._loss_host[0])
 
@@ -274,10 +316,21 @@ class CDAE(DeepRecommenderABC):
                             'off': torch.empty(batch_size + 1, dtype=torch.int32, device=self._dev),
                             'loss': torch.zeros(2, dtype=torch.float32, device=self._dev)}
         d = self._dp_dev
-        d['uid'].copy_(slot['uid'], non_blocking=True)
-        d['off'].copy_(slot['off'], non_blocking=True)
+        d['uid'].copy_(slot['uid'][:batch_size], non_blocking=True)
+        d['off'].copy_(slot['off'][:batch_size + 1], non_blocking=True)
         self._step -= 1                      # step_device advances it again
         self.step_device(d['uid'], d['off'], None, reg_rate, d['loss'])
+
+    def global_loss(self, loss2):
+        """Reported loss of the global batch from this rank's [loss, batch term] pair (a collective when parallel)."""
+        dp = self._dp
+        if not dp.active:
+            return float(loss2[0].item())
+        if self._sharded:                     # every rank holds the terms of its items and its share of the L2 sum
+            t = loss2[0:1].clone()
+            dp.all_reduce_sum(t)
+            return float(t.item())
+        return float(dp.global_loss(loss2).item())
 
     def step_device(self, uids_dev, keep_off_dev, keep_dev, reg_rate, loss_dev):
         """One step on device-resident inputs (torch tensors); keep_dev=None selects the philox mask.
@@ -292,6 +345,8 @@ class CDAE(DeepRecommenderABC):
         if dp is None or not dp.active:
             _lib.check(lib.drb_cdae_step(*ptrs))
             return
+        if self._sharded:
+            return self._step_device_sharded(uids_dev, args, ptrs)
         # data parallel: the collectives run on NCCL's stream while the next phase computes
         #   PREP | all-reduce(label histogram) || GRADS_A | GRADS_B | all-reduce(dW'^T) || GRADS_C |
         #   all-gather(uids, dz1 rows) -> dV | all-reduce(dW, db, db') | UPDATE
@@ -320,6 +375,44 @@ class CDAE(DeepRecommenderABC):
         dp.all_reduce_sum(self._grads[L.off_w:L.off_v])      # dW, db, db' (dense)
         h_w2t.wait()
         _lib.check(lib.drb_cdae_step_phases(*ptrs, UPD))
+
+    def _step_device_sharded(self, uids_dev, args, ptrs):
+        """Item-sharded step: rows of W / W' / V never travel; the two exchanges are all-reduces of batch x hidden
+        activations (the partial pre-activation of the hidden layer and the partial dh)."""
+        torch, lib, dp = self._torch, _lib.load(), self._dp
+        n = uids_dev.numel()
+        owned = (uids_dev >= self._ulo) & (uids_dev < self._uhi)
+        v_rows = torch.where(owned, uids_dev - self._ulo, torch.full_like(uids_dev, -1)).contiguous()
+        args.v_rows = v_rows.data_ptr()
+        PREP, GA, UPD, GB, GC, GA2, GC2 = 1, 2, 4, 8, 16, 32, 64
+        _lib.check(lib.drb_cdae_step_phases(*ptrs, PREP | GA))
+        dp.all_reduce_sum(self._h_buf[:n])
+        _lib.check(lib.drb_cdae_step_phases(*ptrs, GA2 | GB | GC))
+        dp.all_reduce_sum(self._dz1[:n])
+        _lib.check(lib.drb_cdae_step_phases(*ptrs, GC2 | UPD))
+        self._keepalive = v_rows             # the kernels read it asynchronously
+
+    def gather_full_weights(self):
+        """Reference-shaped full weights {W, W_, V, b, b_} on every rank (all-gather of the shards)."""
+        torch, dp = self._torch, self._dp
+        out = {'b': self.b.clone()}
+        if not getattr(self, '_sharded', False):
+            out.update(W=self.W.clone(), W_=self.W_.clone(), V=self.V.clone(), b_=self.b_.clone())
+            return out
+        K = self.hidden_factors
+
+        def gather_rows(local, total, per):
+            pad = torch.zeros((per, local.shape[1]), dtype=torch.float32, device=self._dev)
+            pad[:local.shape[0]] = local
+            full = torch.empty((per * dp.world, local.shape[1]), dtype=torch.float32, device=self._dev)
+            dp.dist.all_gather_into_tensor(full, pad, group=dp.group)
+            return full[:total]
+        per_i, per_u = -(-self.n_items // dp.world), -(-self.n_users // dp.world)
+        out['W'] = gather_rows(self.W.contiguous(), self.n_items, per_i)
+        out['W_'] = gather_rows(self.W_.t().contiguous(), self.n_items, per_i).t()
+        out['V'] = gather_rows(self.V.contiguous(), self.n_users, per_u)
+        out['b_'] = gather_rows(self.b_.reshape(-1, 1).contiguous(), self.n_items, per_i).reshape(-1)
+        return out
 
     def launch_count(self):
         return _lib.load().drb_ctx_launch_count(self._ctx)

@@ -304,13 +304,14 @@ int drb_cdae_create(drb_ctx* ctx, const drb_cdae_desc* desc, drb_cdae** out) {
 int drb_cdae_destroy(drb_cdae* m) { delete m; return DRB_OK; }
 
 static int cdae_hidden_into(drb_cdae* m, const int32_t* uids, int n, const int32_t* keep_off, const uint8_t* keep,
-                            float scale, float* h) {
+                            float scale, float* h, int act = DRB_ACT_SIGMOID, const int32_t* bias_rows = nullptr) {
   GatherArgs g{};
   g.indptr = m->d.csr_indptr; g.indices = m->d.csr_indices; g.values = nullptr;
   g.rows = uids; g.keep_off = keep_off; g.keep = keep;
   g.table = m->d.params + m->L.off_w; g.ld = m->L.ld;
   g.rowbias = m->d.params + m->L.off_v; g.bias = m->d.params + m->L.off_b;
-  g.row_scale = nullptr; g.scale = scale; g.act = DRB_ACT_SIGMOID; g.width = m->d.hidden;
+  g.row_scale = nullptr; g.scale = scale; g.act = act; g.width = m->d.hidden;
+  g.bias_rows = bias_rows;
   g.out = h;
   return launch_gather(m->ctx, g, n);
 }
@@ -323,6 +324,13 @@ int drb_cdae_step(drb_cdae* m, const int32_t* uids, const int32_t* keep_off, con
 int drb_cdae_loss_buffer(drb_cdae* m, float** ptr) {
   if (!m || !ptr) return drb_fail(DRB_E_INVALID, "drb_cdae_loss_buffer: NULL argument");
   *ptr = m->ws.loss_scalar;
+  return DRB_OK;
+}
+
+int drb_cdae_h_buffer(drb_cdae* m, float** ptr, int64_t* count) {
+  if (!m || !ptr || !count) return drb_fail(DRB_E_INVALID, "drb_cdae_h_buffer: NULL argument");
+  *ptr = m->ws.h;
+  *count = (int64_t)m->d.max_batch * m->L.ld;
   return DRB_OK;
 }
 
@@ -365,6 +373,9 @@ int drb_cdae_step_phases(drb_cdae* m, const int32_t* uids, const int32_t* keep_o
   const uint8_t* keep_used = keep ? keep : w.keep;
   if (m->d.corruption_level == 0.f) keep_used = nullptr;
   const float s = (float)(1.0 / (1.0 - (double)m->d.corruption_level));
+  const bool sharded = a->shard_items != 0;       // item-sharded weights: this model holds items [item_offset, +I)
+  const double items_global = sharded && a->n_items_global > 0 ? (double)a->n_items_global : (double)I;
+  const float inv_count = (float)(1.0 / ((double)gbatch * items_global));
   int r;
 
   if (phases & DRB_PHASE_PREP) {
@@ -386,14 +397,21 @@ int drb_cdae_step_phases(drb_cdae* m, const int32_t* uids, const int32_t* keep_o
   bp.keep_out = keep ? nullptr : w.keep;
   bp.seed = a->philox_seed; bp.step = a->philox_step; bp.q = m->d.corruption_level;
   bp.slot_offset = a->slot_offset;
+  bp.item_offset = sharded ? a->item_offset : 0;
   if ((r = launch_batch_prep(ctx, bp, batch))) return r;
   }  // PREP (data parallel: the caller all-reduces the label histogram here)
 
-  const float inv_count = (float)(1.0 / ((double)gbatch * (double)I));
   const int n2 = m->n2, bp = m->batch_pad;
   if (phases & DRB_PHASE_GRADS_A) {
-  // 2. K1: h = sigmoid(s * sum_kept W[i] + V[u] + b)   (needs no labels: overlaps the label all-reduce when DP)
-  if ((r = cdae_hidden_into(m, uids, batch, keep_off, keep_used, s, w.h))) return r;
+  // 2. K1: h = sigmoid(s * sum_kept W[i] + V[u] + b)   (needs no labels: overlaps the label all-reduce when DP).
+  //    Item-sharded: the partial pre-activation over the local items (+ V_u + b on the user's owner rank); the caller
+  //    all-reduces drb_cdae_h_buffer() and GRADS_A2 applies the sigmoid.
+  if ((r = cdae_hidden_into(m, uids, batch, keep_off, keep_used, s, w.h, sharded ? DRB_ACT_NONE : DRB_ACT_SIGMOID,
+                            sharded ? a->v_rows : nullptr)))
+    return r;
+  }
+  if ((phases & DRB_PHASE_GRADS_A2) || ((phases & DRB_PHASE_GRADS_A) && !sharded)) {
+  if (sharded && (r = launch_sigmoid_rows(ctx, w.h, batch, ld, m->d.hidden))) return r;
   if (m->use_umma) {   // tf32 hi/lo operand splits for the tensor-core GEMMs (umma.cu)
     if ((r = launch_split_tf32(ctx, w.h, batch, ld, ld, w.h_hi, w.h_lo, w.hT_hi, w.hT_lo, bp, m->d.hidden))) return r;
     if ((r = launch_split_tf32(ctx, P + L.off_w2t, I, ld, ld, w.w2t_hi, w.w2t_lo, w.wT_hi, w.wT_lo, L.items_pad, -1)))
@@ -456,7 +474,13 @@ int drb_cdae_step_phases(drb_cdae* m, const int32_t* uids, const int32_t* keep_o
   g3.M = batch; g3.N = ld; g3.Kred = I; g3.splits = m->splits;
   if ((r = launch_gemm(ctx, LAYOUT_KN, EPI_STORE, g3))) return r;
   }
-  int nb = launch_dz1(ctx, w.dh_part, m->splits, w.h, w.dz1, batch, ld, w.col_b);
+  if (sharded) {   // dh partial over the local items -> one plane; the caller all-reduces drb_cdae_dz1_buffer()
+    if ((r = launch_sum_planes(ctx, w.dh_part, m->splits, (int64_t)batch * ld, w.dz1))) return r;
+  }
+  }
+  if ((phases & DRB_PHASE_GRADS_C2) || ((phases & DRB_PHASE_GRADS_C) && !sharded)) {
+  int nb = sharded ? launch_dz1(ctx, w.dz1, 1, w.h, w.dz1, batch, ld, w.col_b)
+                   : launch_dz1(ctx, w.dh_part, m->splits, w.h, w.dz1, batch, ld, w.col_b);
   if (nb < 0) return nb;
   if ((r = launch_reduce_partials(ctx, w.col_b, nb, ld, G + L.off_b, ld))) return r;
 
@@ -466,11 +490,12 @@ int drb_cdae_step_phases(drb_cdae* m, const int32_t* uids, const int32_t* keep_o
   sc.keep_off = keep_off; sc.keep = keep_used; sc.row_scale = nullptr; sc.scale = s;
   sc.d = w.dz1; sc.ld = ld; sc.gtable = G + L.off_w;
   sc.growbias = a->skip_user_grad ? nullptr : G + L.off_v;   // data parallel: user rows are exchanged instead
+  sc.bias_rows = sharded ? a->v_rows : nullptr;              // item-sharded: only owned users' rows of V
   if ((r = launch_scatter(ctx, sc, batch))) return r;
-  }  // GRADS_C (data parallel: the caller exchanges dz1 rows and all-reduces dW, db here)
+  }  // GRADS_C / GRADS_C2 (data parallel: the caller exchanges dz1 rows and all-reduces dW, db here)
 
   if (!(phases & DRB_PHASE_UPDATE)) return DRB_OK;
-  const float inv_count_u = (float)(1.0 / ((double)gbatch * (double)I));
+  const float inv_count_u = inv_count;
   // 7. K4: fused Adam + L2 over the arena; t per reference variable [W, W_, V, b, b_]
   AdamArgs ad{};
   ad.w = P; ad.m = m->d.adam_m; ad.v = m->d.adam_v; ad.g = G;

@@ -13,6 +13,8 @@ struct GatherArgs {
   const int32_t* keep_off; const uint8_t* keep;                         // may be NULL (keep everything)
   const float* table; int ld;                                           // gathered table [*, ld]
   const float* rowbias;                                                 // may be NULL; [*, ld] indexed by rows[b]
+  const int32_t* bias_rows;                                             // may be NULL; else rowbias row per output row,
+                                                                        // -1 = add neither rowbias nor bias (item-sharded)
   const float* bias;                                                    // may be NULL; [ld]
   const float* row_scale;                                               // may be NULL; per CSR row
   float scale; int act; int width;                                      // columns >= width are forced to 0
@@ -28,6 +30,7 @@ struct ScatterArgs {
   const float* d; int ld;             // [n, ld] row gradients
   float* gtable;                      // [*, ld] += w * d[b]   (vector atomics)
   float* growbias;                    // may be NULL; [*, ld] += d[b] at rows[b]
+  const int32_t* bias_rows;           // may be NULL; else the growbias row per batch row, -1 = skip (item-sharded)
 };
 int launch_scatter(drb_ctx* ctx, const ScatterArgs& a, int n);
 
@@ -43,6 +46,7 @@ struct BatchPrepArgs {
   uint8_t* keep_out;       // may be NULL; philox keep bytes
   uint64_t seed, step; float q;
   int slot_offset;         // global slot of local row 0 (data parallel), part of the philox counter
+  int item_offset;         // global id of local item 0 (item-sharded), part of the philox counter
 };
 int launch_batch_prep(drb_ctx* ctx, const BatchPrepArgs& a, int n);
 
@@ -51,6 +55,9 @@ int launch_dz1(drb_ctx* ctx, const float* dh_part, int splits, const float* h, f
                float* colpart);
 // column partials of x[n, ld] per 32-row block (generic bias gradient)
 int launch_colpart(drb_ctx* ctx, const float* x, int n, int ld, float* colpart);
+// out[e] = sum_s part[s][e] (e < n_elems); in-place sigmoid of x[n][ld] with columns >= width forced to 0
+int launch_sum_planes(drb_ctx* ctx, const float* part, int planes, int64_t n_elems, float* out);
+int launch_sigmoid_rows(drb_ctx* ctx, float* x, int n, int ld, int width);
 // out[j] = sum_p part[p, ld + j]
 int launch_reduce_partials(drb_ctx* ctx, const float* part, int nparts, int ld, float* out, int n);
 

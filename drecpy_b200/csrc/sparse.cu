@@ -13,6 +13,8 @@
 // L2-resident on B200, so this kernel is bound by L2->SM bandwidth and load issue, not HBM.
 #include "kernels.h"
 
+#include <algorithm>
+
 namespace {
 
 constexpr int kGatherThreads = 128;
@@ -89,8 +91,11 @@ __global__ void __launch_bounds__(kGatherThreads) k_gather(GatherArgs a) {
 #pragma unroll
     for (int p = 0; p < kWarps * G; p++) s += redf[p * a.ld + col];
     float z = s * rs;
-    if (a.rowbias) z += a.rowbias[(int64_t)row * a.ld + col];
-    if (a.bias) z += a.bias[col];
+    const int brow = a.bias_rows ? a.bias_rows[b] : row;     // item-sharded: only the user's owner adds V_u + b
+    if (brow >= 0) {
+      if (a.rowbias) z += a.rowbias[(int64_t)brow * a.ld + col];
+      if (a.bias) z += a.bias[col];
+    }
     a.out[(int64_t)b * a.ld + col] = (col < a.width) ? apply_act(z, a.act) : 0.f;
   }
 }
@@ -115,11 +120,12 @@ __global__ void __launch_bounds__(kGatherThreads) k_scatter(ScatterArgs a) {
     const int c4 = c + v * LPR;
     d[v] = (c4 < ld4) ? ldg4(a.d + (int64_t)b * a.ld + c4 * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
   }
-  if (a.growbias && warp == 0 && sub == 0) {
+  const int brow = a.bias_rows ? a.bias_rows[b] : row;
+  if (a.growbias && brow >= 0 && warp == 0 && sub == 0) {
 #pragma unroll
     for (int v = 0; v < NV; v++) {
       const int c4 = c + v * LPR;
-      if (c4 < ld4) atomicAdd(reinterpret_cast<float4*>(a.growbias + (int64_t)row * a.ld) + c4, d[v]);
+      if (c4 < ld4) atomicAdd(reinterpret_cast<float4*>(a.growbias + (int64_t)brow * a.ld) + c4, d[v]);
     }
   }
   for (int base = warp * 32; base < deg; base += kWarps * 32) {
@@ -173,7 +179,7 @@ __global__ void __launch_bounds__(128) k_batch_prep(BatchPrepArgs a) {
     if (a.count) atomicAdd(a.count + item, 1.0f);
     if (a.label_bits) atomicOr(a.label_bits + (int64_t)b * a.words_per_row + (item >> 5), 1u << (item & 31));
     if (a.keep_out) {
-      const uint32_t x = philox_first((uint32_t)item, (uint32_t)(b + a.slot_offset), (uint32_t)a.step, (uint32_t)(a.step >> 32),
+      const uint32_t x = philox_first((uint32_t)(item + a.item_offset), (uint32_t)(b + a.slot_offset), (uint32_t)a.step, (uint32_t)(a.step >> 32),
                                       (uint32_t)a.seed, (uint32_t)(a.seed >> 32));
       const float u = (float)(x >> 8) * (1.0f / 16777216.0f);
       a.keep_out[koff + (j - lo)] = (u < a.q) ? 0 : 1;
@@ -220,6 +226,25 @@ __global__ void k_colpart(const float* __restrict__ x, int n, int ld, float* __r
     float cs = 0.f;
     for (int r = r0; r < r1; r++) cs += x[(int64_t)r * ld + col];
     colpart[(int64_t)blockIdx.x * ld + col] = cs;
+  }
+}
+
+__global__ void k_sum_planes(const float* __restrict__ part, int planes, int64_t n4, float* __restrict__ out) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int s = 0; s < planes; s++) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(part) + s * n4 + i);
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+    reinterpret_cast<float4*>(out)[i] = acc;
+  }
+}
+
+__global__ void k_sigmoid_rows(float* __restrict__ x, int n, int ld, int width) {
+  const int64_t total = (int64_t)n * ld;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int col = (int)(i % ld);
+    x[i] = (col < width) ? 1.0f / (1.0f + expf(-x[i])) : 0.f;
   }
 }
 
@@ -310,6 +335,24 @@ int launch_colpart(drb_ctx* ctx, const float* x, int n, int ld, float* colpart) 
   k_colpart<<<nblk, min(512, (int)drb_round_up(ld, 32)), 0, ctx->stream>>>(x, n, ld, colpart);
   DRB_LAUNCH_CHECK(ctx, "k_colpart");
   return nblk;
+}
+
+int launch_sum_planes(drb_ctx* ctx, const float* part, int planes, int64_t n_elems, float* out) {
+  const int64_t n4 = n_elems / 4;   // n_elems % 4 == 0 (ld is a multiple of 4)
+  const int blocks = (int)std::min<int64_t>((n4 + 255) / 256, (int64_t)ctx->sm_count * 8);
+  drb_prof_scope prof_(ctx, "k_sum_planes");
+  k_sum_planes<<<std::max(1, blocks), 256, 0, ctx->stream>>>(part, planes, n4, out);
+  DRB_LAUNCH_CHECK(ctx, "k_sum_planes");
+  return DRB_OK;
+}
+
+int launch_sigmoid_rows(drb_ctx* ctx, float* x, int n, int ld, int width) {
+  const int64_t total = (int64_t)n * ld;
+  const int blocks = (int)std::min<int64_t>((total + 255) / 256, (int64_t)ctx->sm_count * 8);
+  drb_prof_scope prof_(ctx, "k_sigmoid_rows");
+  k_sigmoid_rows<<<std::max(1, blocks), 256, 0, ctx->stream>>>(x, n, ld, width);
+  DRB_LAUNCH_CHECK(ctx, "k_sigmoid_rows");
+  return DRB_OK;
 }
 
 int launch_reduce_partials(drb_ctx* ctx, const float* part, int nparts, int ld, float* out, int n) {

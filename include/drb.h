@@ -156,6 +156,11 @@ typedef struct {
   int32_t global_batch;    /* data parallel: number of sampled users over all ranks (0 = batch) */
   int32_t slot_offset;     /* data parallel: global batch slot of local row 0 (philox counter) */
   int32_t skip_user_grad;  /* data parallel: leave dV to drb_cdae_scatter_user_rows (rows are all-gathered) */
+  /* item-sharded weights (this model holds items [item_offset, item_offset + n_items) and a slice of V): */
+  int32_t shard_items;     /* != 0 selects the item-sharded step */
+  int32_t item_offset;     /* global id of local item 0 (philox counter) */
+  int64_t n_items_global;  /* loss normalisation 1 / (global_batch * n_items_global) */
+  const int32_t* v_rows;   /* device [batch]: local row of V for users this rank owns, -1 otherwise */
 } drb_cdae_step_args;
 
 enum {
@@ -165,7 +170,12 @@ enum {
   DRB_PHASE_GRADS_B = 8,   /* output layer + loss epilogue, dW'^T, db' */
   DRB_PHASE_GRADS_C = 16,  /* dh, dz1, db, scatter into dW (and dV unless skip_user_grad) */
   DRB_PHASE_GRADS = 2 | 8 | 16,
-  DRB_PHASE_ALL = 31
+  DRB_PHASE_ALL = 31,
+  /* item-sharded step only: GRADS_A leaves the partial pre-activation in drb_cdae_h_buffer() (all-reduce it), then
+   * GRADS_A2 applies the sigmoid; GRADS_C leaves the partial dh in drb_cdae_dz1_buffer() (all-reduce it), then
+   * GRADS_C2 forms dz1 and scatters.  Rows of W / W' / V never travel, only batch x hidden activations do. */
+  DRB_PHASE_GRADS_A2 = 32,
+  DRB_PHASE_GRADS_C2 = 64
 };
 
 int drb_cdae_create(drb_ctx* ctx, const drb_cdae_desc* desc, drb_cdae** out);
@@ -191,6 +201,7 @@ int drb_cdae_step_phases(drb_cdae* m, const int32_t* uids, const int32_t* keep_o
                          int32_t batch, const drb_cdae_step_args* args, float* loss_out, int32_t phases);
 int drb_cdae_label_count_buffer(drb_cdae* m, float** ptr, int64_t* count);
 int drb_cdae_dz1_buffer(drb_cdae* m, float** ptr, int64_t* count);   /* [max_batch][ld], rows 0..batch-1 valid */
+int drb_cdae_h_buffer(drb_cdae* m, float** ptr, int64_t* count);     /* [max_batch][ld] hidden activations */
 int drb_cdae_scatter_user_rows(drb_cdae* m, const int32_t* uids, const float* rows, int32_t n);
 /* Same step with HOST inputs: copies uids / keep_off / keep to the device (inside the call), runs the step,
  * and, if loss_host != NULL, copies the loss back and synchronises. */

@@ -68,3 +68,54 @@ def test_two_gpu_step_matches_single_gpu(tmp_path):
     assert np.allclose(r['losses'], r['ref_losses'], rtol=1e-5), (r['losses'], r['ref_losses'])
     scale = np.abs(r['p_ref']).max()
     assert np.abs(r['p'] - r['p_ref']).max() < 2e-4 * scale
+
+
+def _worker_items(rank, world, port, out):
+    import torch
+    import torch.distributed as dist
+    import drecpy_b200 as drb
+    from drecpy_b200.parallel import DataParallel
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group('nccl', rank=rank, world_size=world, device_id=torch.device(f'cuda:{rank}'))
+    U, I, K, B = 501, 903, 64, 96          # odd sizes: uneven shards
+    u, i, v = drb.synthetic_interactions(U, I, 30000, seed=4)
+    ds = drb.InteractionData(u, i, v)
+    w = _weights(U, I, K)
+    m = drb.CDAE(hidden_factors=K, seed=10, verbose=False, rng_mode='philox', device=f'cuda:{rank}')
+    m.fit(ds, epochs=0, batch_size=B, init_weights=w, data_parallel=DataParallel(dist), parallel_mode='items')
+    assert m.W.shape[0] < I and m.V.shape[0] < U          # weights really are sharded
+    losses = []
+    for s in range(1, 7):
+        m._step = s
+        losses.append(m._train_step(B, 1e-3, want_loss=True))
+    full = m.gather_full_weights()
+    if rank == 0:
+        ref = drb.CDAE(hidden_factors=K, seed=10, verbose=False, rng_mode='philox', device='cuda:0')
+        ref.fit(ds, epochs=0, batch_size=B * world, init_weights=w)
+        ref_losses = []
+        for s in range(1, 7):
+            ref._step = s
+            ref_losses.append(ref._train_step(B * world, 1e-3, want_loss=True))
+        np.savez(out, losses=losses, ref_losses=ref_losses,
+                 **{k: t.cpu().numpy() for k, t in full.items()},
+                 **{'ref_' + k: getattr(ref, k).cpu().numpy() for k in ('W', 'W_', 'V', 'b', 'b_')})
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_item_sharded_step_matches_single_gpu(tmp_path):
+    """W, W', b' sharded by item range and V by user range over 2 GPUs; only batch x hidden activations travel."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip('needs 2 GPUs')
+    import torch.multiprocessing as mp
+    out = str(tmp_path / 'items.npz')
+    mp.spawn(_worker_items, args=(2, _free_port(), out), nprocs=2, join=True)
+    r = np.load(out)
+    assert np.allclose(r['losses'], r['ref_losses'], rtol=1e-5), (r['losses'], r['ref_losses'])
+    for k in ('W', 'W_', 'V', 'b', 'b_'):
+        scale = np.abs(r['ref_' + k]).max()
+        assert r[k].shape == r['ref_' + k].shape
+        assert np.abs(r[k] - r['ref_' + k]).max() < 2e-4 * scale, k
