@@ -151,12 +151,13 @@ def run_reference(args, cfg):
     print(json.dumps(line), flush=True)
 
 
-def workload_config(cfg, n_gpus):
+def workload_config(cfg, n_gpus, parallelism=None):
+    parallelism = parallelism or f'dp{n_gpus}'
     return {'workload': f"{cfg['name']}: CDAE hidden_factors={cfg['hidden']} bce q={cfg['q']} on synthetic "
                         f"{cfg['n_users']}x{cfg['n_items']} / {cfg['nnz']} interactions (BASELINE.json configs[2])",
             'batch_per_gpu': cfg['batch'], 'global_batch': cfg['batch'] * n_gpus, 'neg_ratio': cfg['neg_ratio'],
             'label_mode': 'batch_mean', 'adam': 'dense, per-variable step counter', 'mask_rng': 'philox (device)',
-            'item_popularity': f"zipf a={cfg['zipf_a']}", 'parallelism': f'dp{n_gpus}',
+            'item_popularity': f"zipf a={cfg['zipf_a']}", 'parallelism': parallelism,
             'l2': 'per-step working set (params + Adam state + dz ~ 2.7 GB) exceeds the 126 MB L2; no flush needed'}
 
 
@@ -181,16 +182,21 @@ def run_native(args, cfg):
     from drecpy_b200.parallel import DataParallel
     m.fit(ds, epochs=0, batch_size=B, learning_rate=cfg['lr'], neg_ratio=cfg['neg_ratio'], reg_rate=cfg['reg'],
           sampler=drb.PointSampler(ds, cfg['neg_ratio'], 1e-3, cfg['seed'] + rank),
-          data_parallel=DataParallel(dist), dp_sampler='independent')
+          data_parallel=DataParallel(dist), dp_sampler='independent', parallel_mode=args.parallel)
+    items_mode = args.parallel == 'items' and world > 1
+    Bs = B * world if items_mode else B          # item-sharded: every rank steps the whole global batch
 
     # ---- device-resident inputs for the `value` leg
     lib = _lib.load()
     pos_indptr = np.ascontiguousarray(ds.csr(1e-3)[0])
     batches = []
+    pos_indptr = m._h_indptr                      # the (possibly item-sharded) CSR the model gathers from
+    if items_mode:                                # all ranks must step the same users
+        m._sampler = drb.PointSampler(ds, cfg['neg_ratio'], 1e-3, cfg['seed'])
     for _ in range(K + W):
-        u = m._sampler.sample_arrays(B)[0]
-        off = np.zeros(B + 1, np.int32)
-        _lib.check(lib.drb_batch_offsets(_lib.np_ptr(u), B, _lib.np_ptr(pos_indptr), _lib.np_ptr(off)))
+        u = m._sampler.sample_arrays(Bs)[0]
+        off = np.zeros(Bs + 1, np.int32)
+        _lib.check(lib.drb_batch_offsets(_lib.np_ptr(u), Bs, _lib.np_ptr(pos_indptr), _lib.np_ptr(off)))
         batches.append((torch.from_numpy(u.copy()).to(dev), torch.from_numpy(off).to(dev)))
     loss_dev = torch.zeros(2, device=dev)
 
@@ -214,7 +220,7 @@ def run_native(args, cfg):
     ms_total = e0.elapsed_time(e1)
     clock_info = clocks.stop()
     launches = m.launch_count() - launches0
-    loss_value = float(m._dp.global_loss(loss_dev).item())      # collective when data parallel: every rank calls it
+    loss_value = m.global_loss(loss_dev)                        # collective when parallel: every rank calls it
     t = torch.tensor([ms_total], device=dev)
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -262,7 +268,7 @@ def run_native(args, cfg):
     if tc_path and os.path.exists(tpath) and cfg['name'] == C3['name']:
         tb = json.load(open(tpath))['dram_bytes_per_launch']      # ncu --set full capture of the same command
         traffic = tb['k_umma_cdae_loss'] + tb['k_umma_gemm_mn'] + tb['k_umma_gemm_kk']
-    n_params = 2 * I * m._L.ld + U * m._L.ld + m._L.ld + m._L.items_pad
+    n_params = int(m._L.total)                                   # parameters this rank updates (its shard when item-sharded)
     launches_total = int(launches)
     adam_gbs = 28.0 * n_params / (kernels.get('k_adam', float('nan')) * 1e-3) / 1e9
     roofline = {'kernel': ('k_umma_cdae_loss + k_umma_gemm x2 (tcgen05 3xTF32: output layer fwd + fused loss epilogue, '
@@ -300,7 +306,8 @@ def run_native(args, cfg):
     value = B * world * K / (ms_total * 1e-3)
     line = {'metric': 'cdae_training_samples_per_sec', 'value': value, 'unit': 'samples/s', 'n_gpus': world,
             'steps': K, 'warmup': W, 'ms_per_step': ms_total / K, 'higher_is_better': True, 'scaling': 'weak',
-            'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic', 'config': workload_config(cfg, world),
+            'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+            'config': workload_config(cfg, world, f'item-sharded x{world}' if items_mode else f'dp{world}'),
             'clocks': clock_info, 'gpu_launches': launches_total,
             'e2e': {'value': B * world * K / t_e2e, 'unit': 'samples/s', 'h2d_bytes_per_step': 4 * B + 4 * (B + 1),
                     'd2h_bytes_per_step': 4, 'ms_per_step': 1e3 * t_e2e / K},
@@ -321,6 +328,8 @@ def main():
     ap.add_argument('--workload', default='c3', choices=['c3', 'small'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-extras', action='store_true')
+    ap.add_argument('--parallel', default='data', choices=['data', 'items'],
+                    help='N>1: data = replicated weights + gradient all-reduce; items = item-sharded weights')
     args = ap.parse_args()
     cfg = dict(C3 if args.workload == 'c3' else SMALL)
     if args.impl == 'reference':

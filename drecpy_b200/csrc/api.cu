@@ -432,8 +432,10 @@ int drb_cdae_step_phases(drb_cdae* m, const int32_t* uids, const int32_t* keep_o
                                    m->words_per_row, m->d.loss_kind, inv_count, gbatch, w.loss_part, &n_blocks)))
       return r;
     // dW'^T = dz^T h (I x K); the constant-one feature at column `hidden` yields db' = colsum(dz)
-    // 209 item tiles on 148 SMs would run as two uneven waves; two reduction halves (3 even waves) accumulate atomically
-    const int s2 = batch >= 1024 ? 2 : 1;
+    // e.g. 209 item tiles on 148 SMs would run as two uneven waves: split the batch reduction so the grid is ~2 waves
+    // (the partial products accumulate with vector atomics into the pre-zeroed gradient)
+    const int mt2 = (I + 127) / 128;
+    const int s2 = batch >= 1024 ? std::max(1, std::min({16, (2 * ctx->sm_count + mt2 - 1) / mt2, batch / 512})) : 1;
     if ((r = launch_umma_store(ctx, o2, true, I, n2, batch, s2, G + L.off_w2t, ld, ld, m->d.hidden, G + L.off_b2,
                                m->d.hidden, s2 > 1)))
       return r;
