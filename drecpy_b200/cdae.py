@@ -459,20 +459,30 @@ class CDAE(DeepRecommenderABC):
             return o_i.cpu().numpy(), o_s.cpu().numpy(), o_n.cpu().numpy()
 
     def _rank_batch_dense(self, uids, cand, cand_count, novelty):
-        """Candidate lists longer than the in-CTA sorter handles: dense scores from the GPU, ordering on the host
-        with the same (score desc, iid desc) rule."""
+        """Candidate lists longer than the in-CTA sorter handles (e.g. recommend(n=None) over the whole catalog):
+        dense scores from drb_cdae_predict_all, then a device-side sort of the same 64-bit (orderable(score), iid)
+        keys the ranking kernels use, so the (score desc, iid desc) order is identical."""
+        torch = self._torch
         n, max_c = cand.shape
         o_i = np.zeros((n, max_c), np.int32)
         o_s = np.zeros((n, max_c), np.float32)
         o_n = np.zeros(n, np.int32)
+        seen_indptr, seen_indices = self._d_seen_indptr, self._d_seen_indices
         for r in range(n):
-            p = self._predict(int(uids[r]))
-            c = np.unique(cand[r, :cand_count[r]])
+            u = torch.tensor([int(uids[r])], dtype=torch.int32, device=self._dev)
+            scores = torch.empty(self._L.items_pad, dtype=torch.float32, device=self._dev)
+            _lib.check(_lib.load().drb_cdae_predict_all(self._native, _lib.t_ptr(u), 1, _lib.t_ptr(scores)))
+            c = torch.as_tensor(np.ascontiguousarray(cand[r, :cand_count[r]], np.int64), device=self._dev)
+            c = torch.unique(c[c >= 0])
             if novelty:
-                c = np.setdiff1d(c, self._data.user_items(int(uids[r])))
-            order = np.lexsort((c, p[c]))[::-1]
+                lo, hi = int(seen_indptr[int(uids[r])]), int(seen_indptr[int(uids[r]) + 1])
+                c = c[~torch.isin(c, seen_indices[lo:hi].long())]
+            bits = scores[c].view(torch.int32).long()
+            ordv = torch.where(bits < 0, (~bits) & 0xFFFFFFFF, (bits & 0xFFFFFFFF) | 0x80000000)
+            order = torch.argsort(((ordv - 0x80000000) << 32) + c, descending=True)   # signed (ord, iid) key
             c = c[order]
-            o_i[r, :len(c)], o_s[r, :len(c)], o_n[r] = c, p[c], len(c)
+            k = c.numel()
+            o_i[r, :k], o_s[r, :k], o_n[r] = c.cpu().numpy(), scores[c].cpu().numpy(), k
         return o_i, o_s, o_n
 
     def topk_batch(self, uids, k, novelty=True, return_device=False):

@@ -212,6 +212,17 @@ def test_rank_order_ties_and_novelty():
     for uid in range(0, U, 13):
         want = o.rank(uid, range(I), 100, True)
         assert oi[uid, :on[uid]].tolist() == [i for _, i in want]
+    # whole-catalog ranking longer than the in-CTA sorter (recommend(n=None)): same order, device-side sort
+    I_big = 5000
+    ds2 = _dataset(60, I_big, 3000, seed=7)
+    w2 = _cdae_weights(60, I_big, 8)
+    w2['W_'][:, 10:30] = w2['W_'][:, 10:11]
+    w2['b_'][10:30] = w2['b_'][10]
+    m2 = _make_cdae(ds2, 8, 8, w2)
+    o2 = _oracle_cdae(ds2, w2)
+    got = m2.recommend(ds2.uid_to_user(5))
+    want = o2.rank(5, range(I_big), I_big, True)
+    assert [ds2.item_to_iid(it) for _, it in got] == [i for _, i in want]
     # k larger than the number of eligible items
     got = m.rank(ds.uid_to_user(3), [ds.iid_to_item(x) for x in (1, 2, 3)], novelty=False)
     assert len(got) == 3
