@@ -30,6 +30,9 @@ struct Carver {  // bump allocator over the caller-provided workspace (256-byte 
   }
 };
 
+// upper bound on the row blocks k_dz1 / k_colpart use for any batch <= max_batch (32 rows per block, 4 below 2048 rows)
+int colpart_blocks(int max_batch) { return std::max((max_batch + 31) / 32, (std::min(max_batch, 2047) + 3) / 4); }
+
 int gemm_splits(const drb_ctx* ctx, int M, int N, int Kred) {
   const int tiles = ((M + 127) / 128) * ((N + 127) / 128);
   int s = (2 * ctx->sm_count + tiles - 1) / tiles;
@@ -189,7 +192,7 @@ static CdaeWs cdae_carve(void* base, const drb_cdae_layout_t& L, int n_items, in
   w.dh_part = c.take<float>((int64_t)splits * B * L.ld);
   w.dz1 = c.take<float>(B * L.ld);
   w.col_b2 = c.take<float>((int64_t)mt * L.items_pad);
-  w.col_b = c.take<float>((int64_t)((max_batch + 31) / 32) * L.ld);
+  w.col_b = c.take<float>((int64_t)colpart_blocks(max_batch) * L.ld);
   w.loss_part = c.take<float>((int64_t)mt * ((L.items_pad + 63) / 64));
   w.reg_part = c.take<float>((int64_t)sm_count * 16);
   w.label_count = c.take<float>(L.items_pad);
@@ -670,7 +673,7 @@ static int64_t dmf_carve(drb_dmf* m, void* base, const drb_dmf_layout_t& L, int 
     }
   }
   const int ldl = L.ld_user[L.n_layers_user - 1];
-  float* col = c.take<float>((int64_t)((max_batch + 31) / 32) * maxld);
+  float* col = c.take<float>((int64_t)colpart_blocks(max_batch) * maxld);
   float* lp = c.take<float>(B);
   float* rp = c.take<float>((int64_t)sm_count * 16);
   float* ls = c.take<float>(64);

@@ -196,13 +196,14 @@ __global__ void __launch_bounds__(128) k_row_scatter(const int32_t* __restrict__
   for (int c = lane; c < (ld >> 2); c += 32) atomicAdd(dst + c, __ldg(src + c));
 }
 
-constexpr int kRowsPerBlock = 32;
+constexpr int kRowsPerBlock = 32;   // large batches; small ones use 4 so that more than a couple of CTAs run
+__host__ __device__ inline int rows_per_block(int n) { return n >= 2048 ? kRowsPerBlock : 4; }
 
 // dz1 = dh * h * (1-h) with dh = sum over split-K partials; column partial sums for db (cdae.py b gradient)
 __global__ void k_dz1(const float* __restrict__ dh_part, int splits, const float* __restrict__ h,
                       float* __restrict__ dz1, int n, int ld, float* __restrict__ colpart) {
-  const int r0 = blockIdx.x * kRowsPerBlock;
-  const int r1 = min(n, r0 + kRowsPerBlock);
+  const int r0 = blockIdx.x * rows_per_block(n);
+  const int r1 = min(n, r0 + rows_per_block(n));
   const int64_t plane = (int64_t)n * ld;
   for (int col = threadIdx.x; col < ld; col += blockDim.x) {
     float cs = 0.f;
@@ -220,8 +221,8 @@ __global__ void k_dz1(const float* __restrict__ dh_part, int splits, const float
 }
 
 __global__ void k_colpart(const float* __restrict__ x, int n, int ld, float* __restrict__ colpart) {
-  const int r0 = blockIdx.x * kRowsPerBlock;
-  const int r1 = min(n, r0 + kRowsPerBlock);
+  const int r0 = blockIdx.x * rows_per_block(n);
+  const int r1 = min(n, r0 + rows_per_block(n));
   for (int col = threadIdx.x; col < ld; col += blockDim.x) {
     float cs = 0.f;
     for (int r = r0; r < r1; r++) cs += x[(int64_t)r * ld + col];
@@ -322,7 +323,7 @@ int launch_batch_prep(drb_ctx* ctx, const BatchPrepArgs& a, int n) {
 
 int launch_dz1(drb_ctx* ctx, const float* dh_part, int splits, const float* h, float* dz1, int n, int ld,
                float* colpart) {
-  const int nblk = (n + kRowsPerBlock - 1) / kRowsPerBlock;
+  const int nblk = (n + rows_per_block(n) - 1) / rows_per_block(n);
   drb_prof_scope prof_(ctx, "k_dz1");
   k_dz1<<<nblk, min(512, (int)drb_round_up(ld, 32)), 0, ctx->stream>>>(dh_part, splits, h, dz1, n, ld, colpart);
   DRB_LAUNCH_CHECK(ctx, "k_dz1");
@@ -330,7 +331,7 @@ int launch_dz1(drb_ctx* ctx, const float* dh_part, int splits, const float* h, f
 }
 
 int launch_colpart(drb_ctx* ctx, const float* x, int n, int ld, float* colpart) {
-  const int nblk = (n + kRowsPerBlock - 1) / kRowsPerBlock;
+  const int nblk = (n + rows_per_block(n) - 1) / rows_per_block(n);
   drb_prof_scope prof_(ctx, "k_colpart");
   k_colpart<<<nblk, min(512, (int)drb_round_up(ld, 32)), 0, ctx->stream>>>(x, n, ld, colpart);
   DRB_LAUNCH_CHECK(ctx, "k_colpart");

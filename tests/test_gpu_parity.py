@@ -124,6 +124,36 @@ def test_cdae_step_modes(case):
     assert rel_err(m.V.cpu().numpy(), o.V) < 2e-3
 
 
+def test_cdae_empty_rows_duplicate_rows_and_batch_of_one():
+    """interaction_threshold=4 leaves many users without a single positive (empty CSR rows); the raw data also holds
+    duplicated (user, item) rows, which the reference sums before thresholding (mem_dataset.py:495, cdae.py:61)."""
+    import torch
+    rng = np.random.default_rng(3)
+    u, i, v = drb.synthetic_interactions(90, 140, 700, seed=11)
+    dup = rng.choice(len(u), 60, replace=False)
+    u, i, v = np.concatenate([u, u[dup]]), np.concatenate([i, i[dup]]), np.concatenate([v, rng.integers(1, 3, 60)])
+    ds = drb.InteractionData(u, i, v)
+    ds.assign_internal_ids()
+    U, I, K = ds.count_unique('uid'), ds.count_unique('iid'), 12
+    w = _cdae_weights(U, I, K)
+    m = drb.CDAE(hidden_factors=K, corruption_level=0.0, seed=10, verbose=False, interaction_threshold=4,
+                 rng_mode='philox')
+    m.fit(ds, epochs=0, batch_size=8, init_weights=w)
+    o = CDAEOracle(w['W'], w['W_'], w['V'], w['b'], w['b_'], ds.csr(), interaction_threshold=4, corruption_level=0.0,
+                   learning_rate=1e-3)
+    deg = np.diff(ds.csr(4)[0])
+    assert (deg == 0).any() and (deg > 0).any()
+    empty, full = int(np.flatnonzero(deg == 0)[0]), int(deg.argmax())
+    for uids in (np.array([empty], np.int32), np.array([full, empty, empty, 3, full], np.int32)):
+        off = np.concatenate([[0], np.cumsum(deg[uids])]).astype(np.int32)
+        loss = torch.zeros(2, device='cuda')
+        m.step_device(torch.as_tensor(uids, device='cuda'), torch.as_tensor(off, device='cuda'), None, 1e-3, loss)
+        lo = o.step(uids, np.ones((len(uids), I), bool), 1e-3)
+        assert abs(loss[0].item() - lo) / abs(lo) < 1e-5
+    assert rel_err(m.V.cpu().numpy(), o.V) < 1e-4 and rel_err(m.W.cpu().numpy(), o.W) < 1e-4
+    assert np.max(np.abs(m._predict(empty) - o.predict(empty)) / o.predict(empty)) < 1e-5
+
+
 def test_cdae_duplicate_users_and_ragged_rows():
     """batch with repeated users, a user with a single interaction and the largest-degree user."""
     ds = _dataset(150, 260, 5000, seed=8)
