@@ -252,7 +252,13 @@ def test_rank_order_ties_and_novelty():
     o2 = _oracle_cdae(ds2, w2)
     got = m2.recommend(ds2.uid_to_user(5))
     want = o2.rank(5, range(I_big), I_big, True)
-    assert [ds2.item_to_iid(it) for _, it in got] == [i for _, i in want]
+    got_i = [ds2.item_to_iid(it) for _, it in got]
+    assert sorted(got_i) == sorted(i for _, i in want)
+    po = o2.predict(5)
+    so = po[got_i]                              # oracle scores in the GPU's order: non-increasing up to fp32 noise,
+    assert np.all(so[:-1] >= so[1:] * (1 - 1e-6))
+    exact = so[:-1] == so[1:]                   # ... and exact ties (the forced ones) by item id descending
+    assert np.all(np.array(got_i[:-1])[exact] > np.array(got_i[1:])[exact]) and exact.sum() >= 10
     # k larger than the number of eligible items
     got = m.rank(ds.uid_to_user(3), [ds.iid_to_item(x) for x in (1, 2, 3)], novelty=False)
     assert len(got) == 3
