@@ -30,8 +30,8 @@ struct Carver {  // bump allocator over the caller-provided workspace (256-byte 
   }
 };
 
-// upper bound on the row blocks k_dz1 / k_colpart use for any batch <= max_batch (32 rows per block, 4 below 2048 rows)
-int colpart_blocks(int max_batch) { return std::max((max_batch + 31) / 32, (std::min(max_batch, 2047) + 3) / 4); }
+// upper bound on the row blocks k_dz1 / k_colpart use for any batch <= max_batch (8 rows per block, 4 below 2048 rows)
+int colpart_blocks(int max_batch) { return std::max((max_batch + 7) / 8, (std::min(max_batch, 2047) + 3) / 4); }
 
 int gemm_splits(const drb_ctx* ctx, int M, int N, int Kred) {
   const int tiles = ((M + 127) / 128) * ((N + 127) / 128);
@@ -170,6 +170,7 @@ struct drb_cdae {
   int splits, words_per_row;
   int64_t keep_cap;
   bool use_umma;
+  bool v_grad_clean;   // the dV region of the gradient arena is known to be all zero
   int n_loss_blocks;
   int n2, batch_pad;   // tcgen05 path: N of the backward GEMMs (hidden + ones feature, rounded to 16), padded batch
 };
@@ -276,6 +277,7 @@ int drb_cdae_create(drb_ctx* ctx, const drb_cdae_desc* desc, drb_cdae** out) {
     return drb_fail(DRB_E_INVALID, "drb_cdae_create: the tcgen05 path needs hidden < 256 and a driver with TMA support");
   }
   m->use_umma = umma_ok && desc->gemm_path != DRB_GEMM_FFMA;
+  m->v_grad_clean = false;
   if (m->use_umma) {
     // dh = dz W'^T on the tensor cores has one 128 x n2 tile per 128 users: split the item range so that the grid
     // is ~2 waves of the SM count (the kernel is L2/HBM bandwidth bound, one CTA per SM)
@@ -367,7 +369,7 @@ int drb_cdae_step_phases(drb_cdae* m, const int32_t* uids, const int32_t* keep_o
   if (ctx->sticky) return drb_fail(DRB_E_CUDA, "context has a sticky CUDA error (%d)", ctx->sticky);
   const drb_cdae_layout_t& L = m->L;
   CdaeWs& w = m->ws;
-  const int I = m->d.n_items, U = m->d.n_users, ld = L.ld;
+  const int I = m->d.n_items, ld = L.ld;
   float* P = m->d.params;
   float* G = m->d.grads;
   const bool per_user = (m->d.label_mode == DRB_LABEL_PER_USER);
@@ -385,7 +387,12 @@ int drb_cdae_step_phases(drb_cdae* m, const int32_t* uids, const int32_t* keep_o
   // 0. clear sparse-gradient regions [W | V | b | b2] (W2T's gradient is fully overwritten by the GEMM)
   // (the tcgen05 path accumulates dW'^T from two reduction halves with vector atomics, so it clears that too)
   const int64_t clear_from = m->use_umma ? 0 : L.off_w;
-  DRB_CUDA_TRY(ctx, cudaMemsetAsync(G + clear_from, 0, (size_t)(L.total - clear_from) * sizeof(float), ctx->stream));
+  // dV (U x K, the largest gradient) is only touched in the rows of the sampled users: on the plain single-process
+  // step those rows are re-zeroed after the update (k_zero_rows) instead of clearing the whole table every step
+  const bool sparse_clear_v = !a->skip_user_grad && !sharded && m->v_grad_clean;
+  const int64_t clear_to = sparse_clear_v ? L.off_v : L.total;
+  DRB_CUDA_TRY(ctx, cudaMemsetAsync(G + clear_from, 0, (size_t)(clear_to - clear_from) * sizeof(float), ctx->stream));
+  m->v_grad_clean = false;
   if (per_user)
     DRB_CUDA_TRY(ctx, cudaMemsetAsync(w.label_bits, 0, (size_t)batch * m->words_per_row * 4, ctx->stream));
   else
@@ -520,7 +527,10 @@ int drb_cdae_step_phases(drb_cdae* m, const int32_t* uids, const int32_t* keep_o
   ad.reg_part = w.reg_part;
   int n_reg = 0;
   if ((r = launch_adam(ctx, ad, &n_reg))) return r;
-  (void)U;
+  if (!a->skip_user_grad && !sharded) {   // leave dV all-zero again for the next step (see PREP)
+    if ((r = launch_zero_rows(ctx, G + L.off_v, uids, batch, ld))) return r;
+    m->v_grad_clean = true;
+  }
   return launch_finalize_loss(ctx, w.loss_part, m->n_loss_blocks, inv_count_u, w.reg_part, n_reg, loss_out);
 }
 
@@ -891,15 +901,11 @@ int drb_dmf_rank_candidates(drb_dmf* m, const int32_t* uids, int32_t n, const in
   drb_ctx* ctx = m->ctx;
   const int lu = m->tw[0].n_layers - 1, li = m->tw[1].n_layers - 1;
   const int ldl = m->tw[1].ld[li];
-  // item tower for every item: ids 0..n_items-1 are generated on the device by a strided memcpy-free trick:
-  // the id list is simply the identity, staged through the iids buffer chunk by chunk from the host.
-  std::vector<int32_t> ident(m->d.max_batch);
+  // item tower once for every item of the catalog (the weights are fixed during scoring), chunk by chunk
   int r;
   for (int32_t o = 0; o < m->d.n_items; o += m->d.max_batch) {
     const int c = std::min(m->d.max_batch, m->d.n_items - o);
-    for (int i = 0; i < c; i++) ident[i] = o + i;
-    DRB_CUDA_TRY(ctx, cudaMemcpyAsync(m->iids, ident.data(), (size_t)c * 4, cudaMemcpyHostToDevice, ctx->stream));
-    DRB_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));  // `ident` is reused by the next chunk
+    if ((r = launch_iota(ctx, m->iids, c, o))) return r;
     if ((r = dmf_tower_fwd(m, 1, m->iids, c))) return r;
     DRB_CUDA_TRY(ctx, cudaMemcpyAsync(m->item_rep + (int64_t)o * ldl, m->tw[1].act[li], (size_t)c * ldl * 4,
                                       cudaMemcpyDeviceToDevice, ctx->stream));

@@ -55,6 +55,10 @@ int launch_dz1(drb_ctx* ctx, const float* dh_part, int splits, const float* h, f
                float* colpart);
 // column partials of x[n, ld] per 32-row block (generic bias gradient)
 int launch_colpart(drb_ctx* ctx, const float* x, int n, int ld, float* colpart);
+// table[ids[r]][:] = 0 for r < n
+int launch_zero_rows(drb_ctx* ctx, float* table, const int32_t* ids, int n, int ld);
+// out[i] = start + i
+int launch_iota(drb_ctx* ctx, int32_t* out, int n, int start);
 // out[e] = sum_s part[s][e] (e < n_elems); in-place sigmoid of x[n][ld] with columns >= width forced to 0
 int launch_sum_planes(drb_ctx* ctx, const float* part, int planes, int64_t n_elems, float* out);
 int launch_sigmoid_rows(drb_ctx* ctx, float* x, int n, int ld, int width);

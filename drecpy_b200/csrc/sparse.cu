@@ -196,7 +196,7 @@ __global__ void __launch_bounds__(128) k_row_scatter(const int32_t* __restrict__
   for (int c = lane; c < (ld >> 2); c += 32) atomicAdd(dst + c, __ldg(src + c));
 }
 
-constexpr int kRowsPerBlock = 32;   // large batches; small ones use 4 so that more than a couple of CTAs run
+constexpr int kRowsPerBlock = 8;    // large batches; small ones use 4 so that more than a couple of CTAs run
 __host__ __device__ inline int rows_per_block(int n) { return n >= 2048 ? kRowsPerBlock : 4; }
 
 // dz1 = dh * h * (1-h) with dh = sum over split-K partials; column partial sums for db (cdae.py b gradient)
@@ -230,6 +230,19 @@ __global__ void k_colpart(const float* __restrict__ x, int n, int ld, float* __r
   }
 }
 
+__global__ void __launch_bounds__(128) k_zero_rows(float* __restrict__ table, const int32_t* __restrict__ ids, int n,
+                                                   int ld) {
+  const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (r >= n) return;
+  float4* dst = reinterpret_cast<float4*>(table + (int64_t)ids[r] * ld);
+  for (int c = lane; c < (ld >> 2); c += 32) dst[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+}
+
+__global__ void k_iota(int32_t* __restrict__ out, int n, int start) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = start + i;
+}
+
 __global__ void k_sum_planes(const float* __restrict__ part, int planes, int64_t n4, float* __restrict__ out) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -249,13 +262,23 @@ __global__ void k_sigmoid_rows(float* __restrict__ x, int n, int ld, int width) 
   }
 }
 
-__global__ void k_reduce_partials(const float* __restrict__ part, int nparts, int ld, float* __restrict__ out,
-                                  int n) {
-  const int j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= n) return;
+// out[j] = sum_p part[p][j]: 32 columns per block, 8 thread rows stride over the partials, fixed-order final sum
+__global__ void __launch_bounds__(256) k_reduce_partials(const float* __restrict__ part, int nparts, int ld,
+                                                         float* __restrict__ out, int n) {
+  __shared__ float sm[8][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int j = blockIdx.x * 32 + tx;
   float s = 0.f;
-  for (int p = 0; p < nparts; p++) s += part[(int64_t)p * ld + j];
-  out[j] = s;
+  if (j < n)
+    for (int p = ty; p < nparts; p += 8) s += part[(int64_t)p * ld + j];
+  sm[ty][tx] = s;
+  __syncthreads();
+  if (ty == 0 && j < n) {
+    float t = 0.f;
+#pragma unroll
+    for (int r = 0; r < 8; r++) t += sm[r][tx];
+    out[j] = t;
+  }
 }
 
 template <template <int, int> class Launcher, typename Args>
@@ -338,6 +361,22 @@ int launch_colpart(drb_ctx* ctx, const float* x, int n, int ld, float* colpart) 
   return nblk;
 }
 
+int launch_zero_rows(drb_ctx* ctx, float* table, const int32_t* ids, int n, int ld) {
+  if (n <= 0) return DRB_OK;
+  drb_prof_scope prof_(ctx, "k_zero_rows");
+  k_zero_rows<<<(n * 32 + 127) / 128, 128, 0, ctx->stream>>>(table, ids, n, ld);
+  DRB_LAUNCH_CHECK(ctx, "k_zero_rows");
+  return DRB_OK;
+}
+
+int launch_iota(drb_ctx* ctx, int32_t* out, int n, int start) {
+  if (n <= 0) return DRB_OK;
+  drb_prof_scope prof_(ctx, "k_iota");
+  k_iota<<<(n + 255) / 256, 256, 0, ctx->stream>>>(out, n, start);
+  DRB_LAUNCH_CHECK(ctx, "k_iota");
+  return DRB_OK;
+}
+
 int launch_sum_planes(drb_ctx* ctx, const float* part, int planes, int64_t n_elems, float* out) {
   const int64_t n4 = n_elems / 4;   // n_elems % 4 == 0 (ld is a multiple of 4)
   const int blocks = (int)std::min<int64_t>((n4 + 255) / 256, (int64_t)ctx->sm_count * 8);
@@ -359,7 +398,7 @@ int launch_sigmoid_rows(drb_ctx* ctx, float* x, int n, int ld, int width) {
 int launch_reduce_partials(drb_ctx* ctx, const float* part, int nparts, int ld, float* out, int n) {
   if (n <= 0) return DRB_OK;
   drb_prof_scope prof_(ctx, "k_reduce_partials");
-  k_reduce_partials<<<(n + 255) / 256, 256, 0, ctx->stream>>>(part, nparts, ld, out, n);
+  k_reduce_partials<<<(n + 31) / 32, 256, 0, ctx->stream>>>(part, nparts, ld, out, n);
   DRB_LAUNCH_CHECK(ctx, "k_reduce_partials");
   return DRB_OK;
 }
