@@ -39,6 +39,10 @@ struct LossParams {
   int m_tiles, n_tiles;
 };
 
+__device__ __forceinline__ float fast_ex2(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float fast_lg2(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float fast_rcp(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
@@ -177,26 +181,33 @@ k_umma_cdae_loss(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
         if (PER_USER && row_ok && ((n0 + c) >> 5) < p.words_per_row)
           wcur = __ldg(p.label_bits + (int64_t)m * p.words_per_row + ((n0 + c) >> 5)) >> ((n0 + c) & 31);
         float lo[16];
-        // branch-free element math: 16 independent dependency chains the scheduler can interleave
+        // branch-free element math: 16 independent dependency chains the scheduler can interleave.  MUFU ops are
+        // issued directly (ex2 / rcp / lg2 .approx.ftz: no denormal fix-up sequences), 5 per element.
+        //   p = 1 / (1 + 2^(-z log2 e));  pc = clip(p, eps, 1-eps);  da = pc + eps;  db = 1 - pc + eps
+        //   bce term   = -(t ln da + (1-t) ln db) = -ln2 (lg2 db + t (lg2 da - lg2 db))
+        //   dL/dp      = ((1-t) da - t db) / (da db) / (B I) = (da - t (da + db)) / (da db) / (B I)   [p inside the clip]
+        //   dL/dz      = dL/dp * p (1-p)
 #pragma unroll
         for (int j = 0; j < 16; j++) {
           const bool ok = row_ok && (n0 + c + j < p.N);
           const float z = __uint_as_float(r[j]) + wb[cl + j];
-          const float pr = __fdividef(1.0f, 1.0f + __expf(-z));
+          const float pr = fast_rcp(1.0f + fast_ex2(z * -1.4426950408889634f));
           const float tgt = PER_USER ? (float)((wcur >> j) & 1u) : wt[cl + j];
-          float dp, lt;
+          float gz, lt;
           if (LOSS == DRB_LOSS_BCE) {
             const float pc = fminf(fmaxf(pr, KERAS_EPS), one_m);
             const float da = pc + KERAS_EPS, db = 1.0f - pc + KERAS_EPS;
-            lt = -(tgt * __logf(da) + (1.0f - tgt) * __logf(db));
+            const float la = fast_lg2(da), lb = fast_lg2(db);
+            lt = -0.6931471805599453f * fmaf(tgt, la - lb, lb);
             const bool inside = (pr >= KERAS_EPS) && (pr <= one_m);
-            dp = inside ? ((1.0f - tgt) * da - tgt * db) * __fdividef(p.inv_count, da * db) : 0.f;
+            const float num = fmaf(-tgt, da + db, da);
+            gz = inside ? num * (pr * (1.0f - pr)) * (fast_rcp(da * db) * p.inv_count) : 0.f;
           } else {
-            lt = PER_USER ? (pr - tgt) * (pr - tgt) : (pr * pr - 2.0f * pr * tgt + tgt);
-            dp = 2.0f * (pr - tgt) * p.inv_count;
+            lt = PER_USER ? (pr - tgt) * (pr - tgt) : fmaf(pr, pr - 2.0f * tgt, tgt);
+            gz = 2.0f * (pr - tgt) * p.inv_count * (pr * (1.0f - pr));
           }
           loss_local += ok ? lt : 0.f;
-          const float g = ok ? dp * pr * (1.0f - pr) : 0.f;
+          const float g = ok ? gz : 0.f;
           float h;
           split_tf32(g, h, lo[j]);
           r[j] = __float_as_uint(h);
