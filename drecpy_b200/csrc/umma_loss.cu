@@ -5,12 +5,17 @@
 // (Keras loss on the (B,B,I) broadcast == batch-mean labels) plus d(loss)/d(z2) of tape.gradient.
 // p is never written to memory; the epilogue emits dL/dz2 already split into tf32 hi/lo for the backward GEMMs.
 //
-// One CTA per SM loops over output tiles (m fastest, so co-running CTAs share the W' tile in L2).  The K extent is
-// short (hidden <= 255 -> <= 8 k-blocks), so per-tile set-up and the exposed epilogue dominated the one-tile-per-CTA
-// version; here the TMA producer runs ahead across tiles, the accumulator is double-buffered in TMEM
-// (2 x BN columns) and the 4 epilogue warps drain tile t while the MMA warp fills tile t+1.
-// dz is written in a 128 x 32 tile-major layout: an epilogue thread (= one accumulator row) owns a contiguous 64-byte
-// piece of a 16 KB tile, and the two backward GEMMs later fetch whole tiles / 4 KB sub-tiles with single TMA boxes.
+// The product is formed transposed, z2^T = W' h^T: MMA M = 128 items (TMEM lanes), N = up to 256 batch rows (TMEM
+// columns).  An epilogue warp therefore holds 32 consecutive items of one batch row across its lanes, which is one
+// 128-byte line of the dz layout below: every dz store instruction writes one full line.  (With batch rows on the
+// lanes each store touched 32 lines, 16 bytes each, and the kernel was bound by the store path: 0.49 -> see DESIGN.md.)
+//
+// One CTA per SM loops over output tiles (batch tiles fastest, so co-running CTAs share the W' tile in L2).  The K
+// extent is short (hidden <= 255 -> <= 8 k-blocks), so per-tile set-up and the exposed epilogue dominated the
+// one-tile-per-CTA version; here the TMA producer runs ahead across tiles, the accumulator is double-buffered in TMEM
+// (2 x BN columns) and the 16 epilogue warps drain tile t while the MMA warp fills tile t+1.
+// dz is written in a 128 x 32 tile-major layout (128 batch rows x 32 items = 16 KB contiguous), and the two backward
+// GEMMs later fetch whole tiles / 4 KB sub-tiles with single TMA boxes.
 #include "umma_common.cuh"
 
 namespace {
@@ -25,8 +30,7 @@ struct LossSmem {
   static constexpr int B_BYTES = BN * BK * 4;
   static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
   static constexpr int BAR_BYTES = 256;
-  static constexpr int CONST_BYTES = LOSS_EPI_WARPS * 2 * (BN / 4) * 4;   // per epilogue warp: b' and target of its columns
-  static constexpr int TOTAL = STAGES * STAGE_BYTES + 1024 + BAR_BYTES + CONST_BYTES;
+  static constexpr int TOTAL = STAGES * STAGE_BYTES + 1024 + BAR_BYTES;
 };
 
 struct LossParams {
@@ -36,7 +40,9 @@ struct LossParams {
   const float* label_count; const uint32_t* label_bits; int words_per_row;
   int loss_kind; float inv_count; int batch;
   float* loss_part;                        // [gridDim.x]
-  int m_tiles, n_tiles;
+  int m_tiles, n_tiles, row_tiles;         // item tiles (128), batch tiles (BN), 128-row tiles of the dz layout
+  int debug;   // DRB_LOSS_DEBUG bit mask (profiling experiments only, results are wrong): 1 = first 16-column chunk of
+               // each epilogue warp only, 2 = skip TMA + MMA, 4 = skip the dz stores
 };
 
 __device__ __forceinline__ float fast_ex2(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
@@ -64,10 +70,9 @@ k_umma_cdae_loss(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
   const uint32_t tmem_ptr_addr = bars + 8u * (2 * S::STAGES + 4);
   volatile uint32_t* tmem_ptr_generic = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_ptr_addr - raw));
   volatile float* lred = reinterpret_cast<volatile float*>(smem_raw + (bars + 8u * (2 * S::STAGES + 5) - raw));
-  float* s_bias = reinterpret_cast<float*>(smem_raw + (bars + S::BAR_BYTES - raw));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int nkb = (p.Kred + BK - 1) / BK;
+  const int nkb = (p.debug & 2) ? 0 : (p.Kred + BK - 1) / BK;
   const int n_tiles_total = p.m_tiles * p.n_tiles;
   constexpr uint32_t TMEM_COLS = (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
 
@@ -96,7 +101,7 @@ k_umma_cdae_loss(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
     if (lane == 0) {
       int it = 0;
       for (int t = blockIdx.x; t < n_tiles_total; t += gridDim.x) {
-        const int m0 = (t % p.m_tiles) * BM, n0 = (t / p.m_tiles) * BN;
+        const int i0 = (t / p.n_tiles) * BM, r0 = (t % p.n_tiles) * BN;   // batch tiles fastest: co-running CTAs share W'
         for (int kb = 0; kb < nkb; kb++, it++) {
           const int s = it % S::STAGES;
           const uint32_t ph = (it / S::STAGES) & 1;
@@ -104,10 +109,10 @@ k_umma_cdae_loss(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
           mbar_expect_tx(full_bar(s), S::STAGE_BYTES);
           const uint32_t sa_hi = base + s * S::STAGE_BYTES, sa_lo = sa_hi + S::A_BYTES;
           const uint32_t sb_hi = sa_lo + S::A_BYTES, sb_lo = sb_hi + S::B_BYTES;
-          tma_load_2d(sa_hi, &map_a_hi, full_bar(s), kb * BK, m0);
-          tma_load_2d(sa_lo, &map_a_lo, full_bar(s), kb * BK, m0);
-          tma_load_2d(sb_hi, &map_b_hi, full_bar(s), kb * BK, n0);
-          tma_load_2d(sb_lo, &map_b_lo, full_bar(s), kb * BK, n0);
+          tma_load_2d(sa_hi, &map_a_hi, full_bar(s), kb * BK, i0);
+          tma_load_2d(sa_lo, &map_a_lo, full_bar(s), kb * BK, i0);
+          tma_load_2d(sb_hi, &map_b_hi, full_bar(s), kb * BK, r0);
+          tma_load_2d(sb_lo, &map_b_lo, full_bar(s), kb * BK, r0);
         }
       }
     }
@@ -142,44 +147,46 @@ k_umma_cdae_loss(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
     }
   } else {
     // ------------------------------------------------------------------ epilogue warps 2..17
-    // warp w reads TMEM lanes 32*(w&3)..+31 (hardware sub-partition rule) and the column quarter (w-2)/4 of the tile
+    // The accumulator holds z2^T: TMEM lane = item, column = batch row.  Warp w reads lanes 32*(w&3)..+31 (hardware
+    // sub-partition rule) = one 32-item block of the dz layout, and the column quarter (w-2)/4 of the tile.  For one
+    // batch row the 32 lanes of a warp then own 128 contiguous bytes of a dz tile: every store is one full line.
     const int q = warp & 3, cq = (warp - 2) >> 2;
     const int ew = warp - 2;
     float loss_local = 0.f;
     const float one_m = 1.0f - KERAS_EPS;
+    constexpr int CW = BN / 4;                    // batch rows of this warp per tile
+    const float fbatch = (float)p.batch;
+    // per-item constants (b', batch-mean label) live in registers and are fetched one tile ahead
+    float nbias, ncount;
+    auto fetch_consts = [&](int t) {
+      const int item = (t / p.n_tiles) * BM + q * 32 + lane;
+      const bool in = (t < n_tiles_total) && (item < p.N);
+      nbias = in ? __ldg(p.bias + item) : 0.f;
+      ncount = (!PER_USER && in) ? __ldg(p.label_count + item) : 0.f;
+    };
+    fetch_consts(blockIdx.x);
     int tl = 0;
     for (int t = blockIdx.x; t < n_tiles_total; t += gridDim.x, tl++) {
-      const int m0 = (t % p.m_tiles) * BM, n0 = (t / p.m_tiles) * BN;
+      const int i0 = (t / p.n_tiles) * BM, r0 = (t % p.n_tiles) * BN;
       const int as = tl & 1;
-      const int m = m0 + q * 32 + lane;
-      const bool row_ok = m < p.M;
-      // per-column constants of this warp's column quarter (private shared-memory slice: no block barrier)
-      constexpr int CW = BN / 4;
-      float* wb = s_bias + ew * 2 * CW;
-      float* wt = wb + CW;
-      __syncwarp();
-      for (int c = lane; c < CW; c += 32) {
-        const int nn = n0 + cq * CW + c;
-        wb[c] = (nn < p.N) ? __ldg(p.bias + nn) : 0.f;
-        wt[c] = (!PER_USER && nn < p.N) ? __ldg(p.label_count + nn) / (float)p.batch : 0.f;
-      }
-      __syncwarp();
+      const int item = i0 + q * 32 + lane;
+      const bool item_ok = item < p.N;
+      const int ib = (i0 >> 5) + q;               // 32-item block of this warp
+      const float bias = nbias, tgt_c = ncount / fbatch;
+      fetch_consts(t + gridDim.x);
       mbar_wait(tfull_bar(as), (tl >> 1) & 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN + cq * CW);
       uint32_t rn[16];
       tmem_ld16_issue(tbase, rn);
 #pragma unroll 1
-      for (int cl = 0; cl < CW; cl += 16) {
-        const int c = cq * CW + cl;
+      for (int cl = 0; cl < ((p.debug & 1) ? 16 : CW); cl += 16) {
+        const int row = r0 + cq * CW + cl;        // first of this chunk's 16 batch rows (same 128-row tile: 16 | 128)
         uint32_t r[16];
         tmem_ld16_wait(rn);
 #pragma unroll
         for (int j = 0; j < 16; j++) r[j] = rn[j];
         if (cl + 16 < CW) tmem_ld16_issue(tbase + cl + 16, rn);      // prefetch the next chunk behind the math
-        uint32_t wcur = 0;     // per-user label bits of these 16 columns
-        if (PER_USER && row_ok && ((n0 + c) >> 5) < p.words_per_row)
-          wcur = __ldg(p.label_bits + (int64_t)m * p.words_per_row + ((n0 + c) >> 5)) >> ((n0 + c) & 31);
         float lo[16];
         // branch-free element math: 16 independent dependency chains the scheduler can interleave.  MUFU ops are
         // issued directly (ex2 / rcp / lg2 .approx.ftz: no denormal fix-up sequences), 5 per element.
@@ -189,10 +196,15 @@ k_umma_cdae_loss(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
         //   dL/dz      = dL/dp * p (1-p)
 #pragma unroll
         for (int j = 0; j < 16; j++) {
-          const bool ok = row_ok && (n0 + c + j < p.N);
-          const float z = __uint_as_float(r[j]) + wb[cl + j];
+          const bool ok = item_ok && (row + j < p.M);
+          const float z = __uint_as_float(r[j]) + bias;
           const float pr = fast_rcp(1.0f + fast_ex2(z * -1.4426950408889634f));
-          const float tgt = PER_USER ? (float)((wcur >> j) & 1u) : wt[cl + j];
+          float tgt = tgt_c;
+          if (PER_USER) {   // one broadcast word per batch row: bit `lane` of word ib
+            const uint32_t w = (row + j < p.M && ib < p.words_per_row)
+                                   ? __ldg(p.label_bits + (int64_t)(row + j) * p.words_per_row + ib) : 0u;
+            tgt = (float)((w >> lane) & 1u);
+          }
           float gz, lt;
           if (LOSS == DRB_LOSS_BCE) {
             const float pc = fminf(fmaxf(pr, KERAS_EPS), one_m);
@@ -212,18 +224,17 @@ k_umma_cdae_loss(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
           split_tf32(g, h, lo[j]);
           r[j] = __float_as_uint(h);
         }
-        // tile-major store: this thread's 16 columns are 64 contiguous bytes of tile (m0/128, (n0+c)/32); every row
-        // and column of the tile is written (zeros outside the matrix) because the backward GEMMs read whole tiles
-        const int64_t off = ((int64_t)((m0 >> 7) * p.nib + ((n0 + c) >> 5)) * 128 + (q * 32 + lane)) * 32 + ((n0 + c) & 31);
-        if (((n0 + c) >> 5) < p.nib) {   // 256-wide tiles can overhang the last 128-column group
+        // tile-major store: row j of this chunk is the 128-byte line ((row tile, item block), row in tile) and the
+        // lanes are its 32 floats.  Every row and column of an existing tile is written (zeros outside the matrix)
+        // because the backward GEMMs read whole tiles.
+        const int rt = row >> 7;
+        if (rt < p.row_tiles && ib < p.nib && !(p.debug & 4)) {   // wide tiles can overhang the last 128-row tile
+          const int64_t off = ((int64_t)(rt * p.nib + ib) * 128 + (row & 127)) * 32 + lane;
 #pragma unroll
-        for (int j4 = 0; j4 < 4; j4++) {
-          *reinterpret_cast<float4*>(p.dz_hi + off + j4 * 4) =
-              make_float4(__uint_as_float(r[j4 * 4]), __uint_as_float(r[j4 * 4 + 1]), __uint_as_float(r[j4 * 4 + 2]),
-                          __uint_as_float(r[j4 * 4 + 3]));
-          *reinterpret_cast<float4*>(p.dz_lo + off + j4 * 4) =
-              make_float4(lo[j4 * 4], lo[j4 * 4 + 1], lo[j4 * 4 + 2], lo[j4 * 4 + 3]);
-        }
+          for (int j = 0; j < 16; j++) {
+            p.dz_hi[off + j * 32] = __uint_as_float(r[j]);
+            p.dz_lo[off + j * 32] = lo[j];
+          }
         }
       }
       // this warp has finished reading accumulator `as`
@@ -254,12 +265,15 @@ template <int BN, int LOSS, bool PER_USER>
 int run_loss(drb_ctx* ctx, const UmmaOperands& o, LossParams p, int* n_blocks_out) {
   CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
   int r;
-  if ((r = make_map(&ma_hi, o.a_hi, p.Kred, p.M, o.lda, BK, BM))) return r;
-  if ((r = make_map(&ma_lo, o.a_lo, p.Kred, p.M, o.lda, BK, BM))) return r;
-  if ((r = make_map(&mb_hi, o.b_hi, p.Kred, o.b_rows, o.ldb, BK, BN))) return r;
-  if ((r = make_map(&mb_lo, o.b_lo, p.Kred, o.b_rows, o.ldb, BK, BN))) return r;
-  p.m_tiles = (p.M + BM - 1) / BM;
-  p.n_tiles = (p.N + BN - 1) / BN;
+  // MMA roles are swapped with respect to the caller's z = h W'^T: A (M side, 128 TMEM lanes) = W' rows = items,
+  // B (N side, BN TMEM columns) = h rows = batch rows
+  if ((r = make_map(&ma_hi, o.b_hi, p.Kred, o.b_rows, o.ldb, BK, BM))) return r;
+  if ((r = make_map(&ma_lo, o.b_lo, p.Kred, o.b_rows, o.ldb, BK, BM))) return r;
+  if ((r = make_map(&mb_hi, o.a_hi, p.Kred, p.M, o.lda, BK, BN))) return r;
+  if ((r = make_map(&mb_lo, o.a_lo, p.Kred, p.M, o.lda, BK, BN))) return r;
+  p.m_tiles = (p.N + BM - 1) / BM;      // item tiles
+  p.n_tiles = (p.M + BN - 1) / BN;      // batch tiles
+  p.row_tiles = (p.M + 127) / 128;
   const int grid = std::min(p.m_tiles * p.n_tiles, ctx->sm_count);
   *n_blocks_out = grid;
   auto kern = k_umma_cdae_loss<BN, LOSS, PER_USER>;
@@ -287,10 +301,12 @@ int launch_umma_cdae_loss(drb_ctx* ctx, const UmmaOperands& o, int M, int N, int
   (void)ldc;
   p.label_count = label_count; p.label_bits = label_bits; p.words_per_row = words_per_row; p.loss_kind = loss_kind;
   p.inv_count = inv_count; p.batch = batch; p.loss_part = loss_part;
+  static const int dbg_env = getenv("DRB_LOSS_DEBUG") ? atoi(getenv("DRB_LOSS_DEBUG")) : 0;
+  p.debug = dbg_env;
   const bool per_user = label_count == nullptr;
   static const int bn_env = getenv("DRB_LOSS_BN") ? atoi(getenv("DRB_LOSS_BN")) : 0;
-  // 256-wide tiles halve the re-reads of the h tile (the main loop is L2->SM bandwidth bound); keep 128 for small N
-  const bool wide = bn_env ? (bn_env == 256) : (N >= 4096);
+  // 256 batch rows per tile halve the re-reads of the W' tile (the main loop is L2->SM bandwidth bound)
+  const bool wide = bn_env ? (bn_env == 256) : (M > 128);
 #define DRB_LOSS_CASE(BN_)                                                                          \
   if (loss_kind == DRB_LOSS_BCE)                                                                    \
     return per_user ? run_loss<BN_, DRB_LOSS_BCE, true>(ctx, o, p, n_blocks_out)                    \
