@@ -20,11 +20,14 @@ namespace {
 
 constexpr int THREADS = 192;
 
-template <int BN>
+// KB = floats of the reduction dimension per pipeline stage.  Wide tiles (BN > 128) use 16: with 32 only two ~90 KB
+// stages fit, one in flight while the other is consumed, and the tensor pipe idled half the time waiting for TMA
+// (ncu: sm__pipe_tensor_cycles_active 53 %); 16-deep stages give five stages of the same shared memory.
+template <int BN, int KB>
 struct Smem {
-  static constexpr int STAGES = (BN <= 128) ? 3 : 2;
-  static constexpr int A_BYTES = BM * BK * 4;           // one of A_hi / A_lo
-  static constexpr int B_BYTES = BN * BK * 4;
+  static constexpr int A_BYTES = BM * KB * 4;           // one of A_hi / A_lo
+  static constexpr int B_BYTES = BN * KB * 4;
+  static constexpr int STAGES = (KB == 32) ? ((BN <= 128) ? 3 : 2) : ((BN <= 128) ? 6 : (BN <= 208) ? 5 : 4);
   static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
   static constexpr int TOTAL = STAGES * STAGE_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/;
 };
@@ -39,11 +42,12 @@ struct UmmaParams {
   int a_tiled_nib;          // > 0: A lives in the 128x32 tile-major dz layout with this many 32-column blocks per row tile
 };
 
-template <int BN, bool A_MN>
+template <int BN, bool A_MN, int KB>
 __global__ void __launch_bounds__(THREADS, 1)
 k_umma_gemm(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
             const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo, UmmaParams p) {
-  using S = Smem<BN>;
+  using S = Smem<BN, KB>;
+  constexpr int BK = KB;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;   // SWIZZLE_128B atoms need 1024-byte alignment
   const uint32_t bars = base + S::STAGES * S::STAGE_BYTES;       // full[STAGES], empty[STAGES], tmem_full, tmem_ptr
@@ -94,24 +98,24 @@ k_umma_gemm(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
         if (p.a_tiled_nib > 0) {
           // dz tile-major layout: tile (row tile rt, column block cb) = 128 rows x 32 floats, contiguous 16 KB at
           // row ((rt * nib + cb) * 128) of a [*, 32] tensor
-          if (A_MN) {   // M runs over dz columns, K over dz rows: four 4 KB boxes {32 cols, 32 rows}
+          if (A_MN) {   // M runs over dz columns, K over dz rows: four boxes {32 cols, BK rows}
 #pragma unroll
             for (int j = 0; j < BM / 32; j++) {
               const int row = ((k0 >> 7) * p.a_tiled_nib + (m0 >> 5) + j) * 128 + (k0 & 127);
-              tma_load_2d(sa_hi + j * 4096, &map_a_hi, full_bar(s), 0, row);
-              tma_load_2d(sa_lo + j * 4096, &map_a_lo, full_bar(s), 0, row);
+              tma_load_2d(sa_hi + j * (BK * 128), &map_a_hi, full_bar(s), 0, row);
+              tma_load_2d(sa_lo + j * (BK * 128), &map_a_lo, full_bar(s), 0, row);
             }
-          } else {      // M runs over dz rows, K over dz columns: one contiguous 16 KB tile
+          } else {      // M runs over dz rows, K over dz columns: a whole 16 KB tile (BK = 32) or its left / right half
             const int row = ((m0 >> 7) * p.a_tiled_nib + (k0 >> 5)) * 128;
-            tma_load_2d(sa_hi, &map_a_hi, full_bar(s), 0, row);
-            tma_load_2d(sa_lo, &map_a_lo, full_bar(s), 0, row);
+            tma_load_2d(sa_hi, &map_a_hi, full_bar(s), k0 & 31, row);
+            tma_load_2d(sa_lo, &map_a_lo, full_bar(s), k0 & 31, row);
           }
         } else if (A_MN) {
-          // A[m][k] stored as G[k][m] (m contiguous): four boxes of {32 m, 32 k}, one per 32-wide MN atom column
+          // A[m][k] stored as G[k][m] (m contiguous): four boxes of {32 m, BK k}, one per 32-wide MN atom column
 #pragma unroll
           for (int j = 0; j < BM / 32; j++) {
-            tma_load_2d(sa_hi + j * 4096, &map_a_hi, full_bar(s), m0 + 32 * j, k0);
-            tma_load_2d(sa_lo + j * 4096, &map_a_lo, full_bar(s), m0 + 32 * j, k0);
+            tma_load_2d(sa_hi + j * (BK * 128), &map_a_hi, full_bar(s), m0 + 32 * j, k0);
+            tma_load_2d(sa_lo + j * (BK * 128), &map_a_lo, full_bar(s), m0 + 32 * j, k0);
           }
         } else {
           tma_load_2d(sa_hi, &map_a_hi, full_bar(s), k0, m0);
@@ -139,15 +143,15 @@ k_umma_gemm(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
         for (int kk = 0; kk < BK / UMMA_K; kk++) {
           uint64_t a_hi, a_lo;
           if (A_MN) {   // MN-major: rows = k (128 B = 32 m each); K atoms of 4 rows are 512 B apart, one MMA (K=8)
-                        // spans two of them; MN atoms (32 floats, one TMA box) are 4096 B apart
-            a_hi = make_desc(sa_hi + kk * 1024, 4096, 512, 1);
-            a_lo = make_desc(sa_lo + kk * 1024, 4096, 512, 1);
-          } else {      // K-major: 8-row groups 1024 bytes apart; advance 32 bytes per UMMA_K inside the swizzle row
-            a_hi = make_desc(sa_hi + kk * 32, 16, 1024);
-            a_lo = make_desc(sa_lo + kk * 32, 16, 1024);
+                        // spans two of them; MN atoms (32 floats, one TMA box of BK rows) are BK * 128 B apart
+            a_hi = make_desc(sa_hi + kk * 1024, BK * 128, 512, 1);
+            a_lo = make_desc(sa_lo + kk * 1024, BK * 128, 512, 1);
+          } else {
+            a_hi = make_desc_kmajor<BK>(sa_hi, kk);
+            a_lo = make_desc_kmajor<BK>(sa_lo, kk);
           }
-          const uint64_t b_hi = make_desc(sb_hi + kk * 32, 16, 1024);
-          const uint64_t b_lo = make_desc(sb_lo + kk * 32, 16, 1024);
+          const uint64_t b_hi = make_desc_kmajor<BK>(sb_hi, kk);
+          const uint64_t b_lo = make_desc_kmajor<BK>(sb_lo, kk);
           umma_tf32(tmem_base, a_lo, b_hi, idesc, (i | kk) != 0);   // small terms first
           umma_tf32(tmem_base, a_hi, b_lo, idesc, 1u);
           umma_tf32(tmem_base, a_hi, b_hi, idesc, 1u);
@@ -240,16 +244,17 @@ __global__ void __launch_bounds__(256) k_split_tf32(const float* __restrict__ sr
   }
 }
 
-template <int BN, bool A_MN>
+template <int BN, bool A_MN, int KB>
 int run_umma(drb_ctx* ctx, const UmmaOperands& o, const UmmaParams& p, int* n_blocks_out) {
+  constexpr int BK = KB;
   CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
   int r;
   if (o.a_tiled_nib > 0) {   // tile-major dz: a [tiles * 128, 32] tensor
-    if ((r = make_map(&ma_hi, o.a_hi, 32, o.a_tiled_rows, 32, 32, A_MN ? 32 : BM, A_MN))) return r;
-    if ((r = make_map(&ma_lo, o.a_lo, 32, o.a_tiled_rows, 32, 32, A_MN ? 32 : BM, A_MN))) return r;
+    if ((r = make_map(&ma_hi, o.a_hi, 32, o.a_tiled_rows, 32, A_MN ? 32 : BK, A_MN ? BK : BM, A_MN))) return r;
+    if ((r = make_map(&ma_lo, o.a_lo, 32, o.a_tiled_rows, 32, A_MN ? 32 : BK, A_MN ? BK : BM, A_MN))) return r;
   } else if (A_MN) {   // A given as G[k][m]
-    if ((r = make_map(&ma_hi, o.a_hi, p.M, p.Kred, o.lda, 32, 32, true))) return r;
-    if ((r = make_map(&ma_lo, o.a_lo, p.M, p.Kred, o.lda, 32, 32, true))) return r;
+    if ((r = make_map(&ma_hi, o.a_hi, p.M, p.Kred, o.lda, 32, BK, true))) return r;
+    if ((r = make_map(&ma_lo, o.a_lo, p.M, p.Kred, o.lda, 32, BK, true))) return r;
   } else {      // A given as G[m][k]
     if ((r = make_map(&ma_hi, o.a_hi, p.Kred, p.M, o.lda, BK, BM))) return r;
     if ((r = make_map(&ma_lo, o.a_lo, p.Kred, p.M, o.lda, BK, BM))) return r;
@@ -258,15 +263,15 @@ int run_umma(drb_ctx* ctx, const UmmaOperands& o, const UmmaParams& p, int* n_bl
   if ((r = make_map(&mb_lo, o.b_lo, p.Kred, o.b_rows, o.ldb, BK, BN))) return r;
   dim3 grid((p.N + BN - 1) / BN, (p.M + BM - 1) / BM, p.splits);
   if (n_blocks_out) *n_blocks_out = grid.x * grid.y;
-  auto kern = k_umma_gemm<BN, A_MN>;
+  auto kern = k_umma_gemm<BN, A_MN, KB>;
   static bool attr_set = false;   // per template instantiation
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem<BN>::TOTAL);
-    if (e != cudaSuccess) return drb_fail(DRB_E_CUDA, "cudaFuncSetAttribute(smem=%d) failed: %s", Smem<BN>::TOTAL, cudaGetErrorString(e));
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem<BN, KB>::TOTAL);
+    if (e != cudaSuccess) return drb_fail(DRB_E_CUDA, "cudaFuncSetAttribute(smem=%d) failed: %s", Smem<BN, KB>::TOTAL, cudaGetErrorString(e));
     attr_set = true;
   }
   drb_prof_scope prof_(ctx, A_MN ? "k_umma_gemm_mn" : "k_umma_gemm_kk");
-  kern<<<grid, THREADS, Smem<BN>::TOTAL, ctx->stream>>>(ma_hi, ma_lo, mb_hi, mb_lo, p);
+  kern<<<grid, THREADS, Smem<BN, KB>::TOTAL, ctx->stream>>>(ma_hi, ma_lo, mb_hi, mb_lo, p);
   DRB_LAUNCH_CHECK(ctx, "k_umma_gemm");
   return DRB_OK;
 }
@@ -293,15 +298,20 @@ int launch_umma_store(drb_ctx* ctx, const UmmaOperands& o, bool a_mn_major, int 
   p.a_tiled_nib = o.a_tiled_nib;
   p.atomic_out = atomic_out ? 1 : 0;
   if (N > 256) return drb_fail(DRB_E_INVALID, "umma store GEMM: N must be <= 256 (hidden width)");
-#define DRB_UMMA_CASE(BN)                                                        \
+  static const int bk_env = getenv("DRB_UMMA_BK") ? atoi(getenv("DRB_UMMA_BK")) : 0;   // profiling override: 16 | 32
+#define DRB_UMMA_CASE(BN, KB_DEFAULT)                                            \
   if (N <= BN) {                                                                 \
-    if (a_mn_major) return run_umma<BN, true>(ctx, o, p, nullptr);               \
-    return run_umma<BN, false>(ctx, o, p, nullptr);                              \
+    if ((bk_env ? bk_env : KB_DEFAULT) == 16) {                                  \
+      if (a_mn_major) return run_umma<BN, true, 16>(ctx, o, p, nullptr);         \
+      return run_umma<BN, false, 16>(ctx, o, p, nullptr);                        \
+    }                                                                            \
+    if (a_mn_major) return run_umma<BN, true, 32>(ctx, o, p, nullptr);           \
+    return run_umma<BN, false, 32>(ctx, o, p, nullptr);                          \
   }
-  DRB_UMMA_CASE(64)
-  DRB_UMMA_CASE(128)
-  DRB_UMMA_CASE(208)
-  DRB_UMMA_CASE(256)
+  DRB_UMMA_CASE(64, 32)
+  DRB_UMMA_CASE(128, 32)
+  DRB_UMMA_CASE(208, 16)
+  DRB_UMMA_CASE(256, 16)
 #undef DRB_UMMA_CASE
   return drb_fail(DRB_E_INVALID, "umma store GEMM: unsupported N");
 }

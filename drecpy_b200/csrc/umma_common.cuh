@@ -12,7 +12,7 @@
 
 namespace {
 
-constexpr int BM = 128, BK = 32, UMMA_K = 8;
+constexpr int BM = 128, UMMA_K = 8;   // the k-block depth (32 or 16 floats per stage) is a kernel template parameter
 constexpr float KERAS_EPS = 1e-7f;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -104,6 +104,13 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes
          ((uint64_t)((sbo_bytes >> 4) & 0x3fff) << 32) | (1ull << 46) | (layout_type << 61);
 }
 
+// K-major operand tile [rows][KB floats] as written by TMA: 128-byte rows / SWIZZLE_128B for KB = 32, 64-byte rows /
+// SWIZZLE_64B (layout_type 4) for KB = 16; 8-row groups are 8 * row bytes apart, one MMA (K = 8) advances 32 bytes
+template <int KB>
+__device__ __forceinline__ uint64_t make_desc_kmajor(uint32_t saddr, int kk) {
+  return KB == 32 ? make_desc(saddr + kk * 32, 16, 1024, 2) : make_desc(saddr + kk * 32, 16, 512, 4);
+}
+
 __device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
   uint32_t h;
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(x));
@@ -127,9 +134,12 @@ EncodeTiledFn get_encode() {
   return fn;
 }
 
-// 2-D fp32 tensor [outer][inner] with row pitch `pitch_floats`; box {box_inner, box_outer}; 128-byte swizzle; OOB = 0
+// 2-D fp32 tensor [outer][inner] with row pitch `pitch_floats`; box {box_inner, box_outer}; OOB = 0.  Swizzle: 128-byte
+// (16-byte units) for 32-float box rows, 64-byte for 16-float box rows, or the 32-byte-unit 128-byte form (atom32)
 int make_map(CUtensorMap* map, const float* ptr, int64_t inner, int64_t outer, int64_t pitch_floats, int box_inner,
              int box_outer, bool atom32 = false) {
+  const CUtensorMapSwizzle swz = atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B
+                                        : (box_inner == 16 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B);
   EncodeTiledFn enc = get_encode();
   if (!enc) return drb_fail(DRB_E_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
   cuuint64_t dims[2] = {(cuuint64_t)inner, (cuuint64_t)outer};
@@ -137,7 +147,7 @@ int make_map(CUtensorMap* map, const float* ptr, int64_t inner, int64_t outer, i
   cuuint32_t box[2] = {(cuuint32_t)box_inner, (cuuint32_t)box_outer};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(ptr), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return drb_fail(DRB_E_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
