@@ -23,17 +23,22 @@ constexpr int THREADS = 192;
 // KB = floats of the reduction dimension per pipeline stage.  Wide tiles (BN > 128) use 16: with 32 only two ~90 KB
 // stages fit, one in flight while the other is consumed, and the tensor pipe idled half the time waiting for TMA
 // (ncu: sm__pipe_tensor_cycles_active 53 %); 16-deep stages give five stages of the same shared memory.
-template <int BN, int KB>
+//
+// CL = 2 runs two adjacent row tiles (blockIdx.x even / odd) as one CTA pair with cta_group::2 MMAs (M = 256): every CTA stages its
+// own 128 rows of A but only half of the B rows, which cuts the shared-memory traffic of the MMAs (A + B read per
+// instruction, 96 B/clk at full rate with N = 256, next to the TMA writes) -- the actual limit of the one-CTA form.
+template <int BN, int KB, int CL>
 struct Smem {
   static constexpr int A_BYTES = BM * KB * 4;           // one of A_hi / A_lo
-  static constexpr int B_BYTES = BN * KB * 4;
-  static constexpr int STAGES = (KB == 32) ? ((BN <= 128) ? 3 : 2) : ((BN <= 128) ? 6 : (BN <= 208) ? 5 : 4);
+  static constexpr int B_BYTES = (BN / CL) * KB * 4;    // this CTA's rows of B
+  static constexpr int STAGES = (CL == 2) ? ((KB == 32) ? 3 : (BN <= 208 ? 7 : 6))
+                              : (KB == 32) ? ((BN <= 128) ? 3 : 2) : ((BN <= 128) ? 6 : (BN <= 208) ? 5 : 4);
   static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
   static constexpr int TOTAL = STAGES * STAGE_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/;
 };
 
 struct UmmaParams {
-  int M, N, Kred;           // logical problem; N <= BN * grid.x
+  int M, N, Kred;           // logical problem; N <= BN * grid.y
   int splits;               // reduction split over blockIdx.z, partial z stored at C + z * M * ldc
   float* C; int ldc;        // EPI_STORE: C[m][n] for n < n_store
   int n_store; int n_valid;  // columns in [n_valid, n_store) are written as 0 (row padding of C)
@@ -42,12 +47,14 @@ struct UmmaParams {
   int a_tiled_nib;          // > 0: A lives in the 128x32 tile-major dz layout with this many 32-column blocks per row tile
 };
 
-template <int BN, bool A_MN, int KB>
+template <int BN, bool A_MN, int KB, int CL>
 __global__ void __launch_bounds__(THREADS, 1)
 k_umma_gemm(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
             const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo, UmmaParams p) {
-  using S = Smem<BN, KB>;
+  using S = Smem<BN, KB, CL>;
   constexpr int BK = KB;
+  const uint32_t cta_rank = (CL > 1) ? cluster_ctarank() : 0u;
+  const bool leader = cta_rank == 0;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;   // SWIZZLE_128B atoms need 1024-byte alignment
   const uint32_t bars = base + S::STAGES * S::STAGE_BYTES;       // full[STAGES], empty[STAGES], tmem_full, tmem_ptr
@@ -59,7 +66,7 @@ k_umma_gemm(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
       reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_ptr_addr - smem_u32(smem_raw)));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+  const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;   // row tiles along x: a CTA pair (cluster {2,1,1}) is two adjacent row tiles
   const int nkb_total = (p.Kred + BK - 1) / BK;
   const int kb_per = (nkb_total + p.splits - 1) / p.splits;
   const int kb_beg = blockIdx.z * kb_per;
@@ -76,13 +83,23 @@ k_umma_gemm(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_ptr_addr), "r"(TMEM_COLS));
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    if (CL > 1) {   // collective: the same warp of both CTAs
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_ptr_addr), "r"(TMEM_COLS));
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_ptr_addr), "r"(TMEM_COLS));
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  __syncthreads();
+  if (CL > 1) cluster_sync_all(); else __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_ptr_generic;
+  // every TMA load of the pair reports to the even CTA's full barrier (only that CTA issues MMAs)
+  auto load = [&](uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+    if (CL > 1) tma_load_2d_pair(dst, map, mapa_rank(bar, 0), c0, c1);
+    else tma_load_2d(dst, map, bar, c0, c1);
+  };
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
@@ -91,7 +108,7 @@ k_umma_gemm(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
         const int s = i % S::STAGES;
         const uint32_t ph = (i / S::STAGES) & 1;
         mbar_wait(empty_bar(s), ph ^ 1);
-        mbar_expect_tx(full_bar(s), S::STAGE_BYTES);
+        if (leader) mbar_expect_tx(full_bar(s), CL * S::STAGE_BYTES);
         const uint32_t sa_hi = base + s * S::STAGE_BYTES, sa_lo = sa_hi + S::A_BYTES;
         const uint32_t sb_hi = sa_lo + S::A_BYTES, sb_lo = sb_hi + S::B_BYTES;
         const int k0 = (kb_beg + i) * BK;
@@ -102,36 +119,36 @@ k_umma_gemm(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
 #pragma unroll
             for (int j = 0; j < BM / 32; j++) {
               const int row = ((k0 >> 7) * p.a_tiled_nib + (m0 >> 5) + j) * 128 + (k0 & 127);
-              tma_load_2d(sa_hi + j * (BK * 128), &map_a_hi, full_bar(s), 0, row);
-              tma_load_2d(sa_lo + j * (BK * 128), &map_a_lo, full_bar(s), 0, row);
+              load(sa_hi + j * (BK * 128), &map_a_hi, full_bar(s), 0, row);
+              load(sa_lo + j * (BK * 128), &map_a_lo, full_bar(s), 0, row);
             }
           } else {      // M runs over dz rows, K over dz columns: a whole 16 KB tile (BK = 32) or its left / right half
             const int row = ((m0 >> 7) * p.a_tiled_nib + (k0 >> 5)) * 128;
-            tma_load_2d(sa_hi, &map_a_hi, full_bar(s), k0 & 31, row);
-            tma_load_2d(sa_lo, &map_a_lo, full_bar(s), k0 & 31, row);
+            load(sa_hi, &map_a_hi, full_bar(s), k0 & 31, row);
+            load(sa_lo, &map_a_lo, full_bar(s), k0 & 31, row);
           }
         } else if (A_MN) {
           // A[m][k] stored as G[k][m] (m contiguous): four boxes of {32 m, BK k}, one per 32-wide MN atom column
 #pragma unroll
           for (int j = 0; j < BM / 32; j++) {
-            tma_load_2d(sa_hi + j * (BK * 128), &map_a_hi, full_bar(s), m0 + 32 * j, k0);
-            tma_load_2d(sa_lo + j * (BK * 128), &map_a_lo, full_bar(s), m0 + 32 * j, k0);
+            load(sa_hi + j * (BK * 128), &map_a_hi, full_bar(s), m0 + 32 * j, k0);
+            load(sa_lo + j * (BK * 128), &map_a_lo, full_bar(s), m0 + 32 * j, k0);
           }
         } else {
-          tma_load_2d(sa_hi, &map_a_hi, full_bar(s), k0, m0);
-          tma_load_2d(sa_lo, &map_a_lo, full_bar(s), k0, m0);
+          load(sa_hi, &map_a_hi, full_bar(s), k0, m0);
+          load(sa_lo, &map_a_lo, full_bar(s), k0, m0);
         }
-        tma_load_2d(sb_hi, &map_b_hi, full_bar(s), k0, n0);
-        tma_load_2d(sb_lo, &map_b_lo, full_bar(s), k0, n0);
+        load(sb_hi, &map_b_hi, full_bar(s), k0, n0 + (int)cta_rank * (BN / CL));
+        load(sb_lo, &map_b_lo, full_bar(s), k0, n0 + (int)cta_rank * (BN / CL));
       }
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer (single thread)
-    if (lane == 0) {
+    if (lane == 0 && leader) {
       // instruction descriptor (cute::UMMA::InstrDescriptor): D=F32 [4,6)=1, A=TF32 [7,10)=2, B=TF32 [10,13)=2,
       // a_major [15], b_major [16], N>>3 [17,23), M>>4 [24,29)
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((A_MN ? 1u : 0u) << 15) | (0u << 16) |
-                             ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+                             ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((BM * CL) >> 4) << 24);
       for (int i = 0; i < nkb; i++) {
         const int s = i % S::STAGES;
         const uint32_t ph = (i / S::STAGES) & 1;
@@ -152,13 +169,21 @@ k_umma_gemm(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
           }
           const uint64_t b_hi = make_desc_kmajor<BK>(sb_hi, kk);
           const uint64_t b_lo = make_desc_kmajor<BK>(sb_lo, kk);
-          umma_tf32(tmem_base, a_lo, b_hi, idesc, (i | kk) != 0);   // small terms first
-          umma_tf32(tmem_base, a_hi, b_lo, idesc, 1u);
-          umma_tf32(tmem_base, a_hi, b_hi, idesc, 1u);
+          if (CL > 1) {
+            umma_tf32_pair(tmem_base, a_lo, b_hi, idesc, (i | kk) != 0);
+            umma_tf32_pair(tmem_base, a_hi, b_lo, idesc, 1u);
+            umma_tf32_pair(tmem_base, a_hi, b_hi, idesc, 1u);
+          } else {
+            umma_tf32(tmem_base, a_lo, b_hi, idesc, (i | kk) != 0);   // small terms first
+            umma_tf32(tmem_base, a_hi, b_lo, idesc, 1u);
+            umma_tf32(tmem_base, a_hi, b_hi, idesc, 1u);
+          }
         }
-        umma_commit(empty_bar(s));       // frees the smem stage once these MMAs have read it
+        if (CL > 1) umma_commit_pair(empty_bar(s));   // frees the smem stage (both CTAs) once these MMAs have read it
+        else umma_commit(empty_bar(s));
       }
-      umma_commit(tmem_full_bar);        // accumulator complete
+      if (CL > 1) umma_commit_pair(tmem_full_bar);    // accumulator complete
+      else umma_commit(tmem_full_bar);
     }
   } else {
     // ------------------------------------------------------------------ epilogue (warps 2..5)
@@ -201,10 +226,11 @@ k_umma_gemm(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
     }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  __syncthreads();
+  if (CL > 1) cluster_sync_all(); else __syncthreads();
   if (warp == 1) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS));
+    if (CL > 1) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS));
+    else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS));
   }
 }
 
@@ -244,9 +270,10 @@ __global__ void __launch_bounds__(256) k_split_tf32(const float* __restrict__ sr
   }
 }
 
-template <int BN, bool A_MN, int KB>
+template <int BN, bool A_MN, int KB, int CL>
 int run_umma(drb_ctx* ctx, const UmmaOperands& o, const UmmaParams& p, int* n_blocks_out) {
   constexpr int BK = KB;
+  constexpr int SMEM = Smem<BN, KB, CL>::TOTAL;
   CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
   int r;
   if (o.a_tiled_nib > 0) {   // tile-major dz: a [tiles * 128, 32] tensor
@@ -259,19 +286,30 @@ int run_umma(drb_ctx* ctx, const UmmaOperands& o, const UmmaParams& p, int* n_bl
     if ((r = make_map(&ma_hi, o.a_hi, p.Kred, p.M, o.lda, BK, BM))) return r;
     if ((r = make_map(&ma_lo, o.a_lo, p.Kred, p.M, o.lda, BK, BM))) return r;
   }
-  if ((r = make_map(&mb_hi, o.b_hi, p.Kred, o.b_rows, o.ldb, BK, BN))) return r;
-  if ((r = make_map(&mb_lo, o.b_lo, p.Kred, o.b_rows, o.ldb, BK, BN))) return r;
-  dim3 grid((p.N + BN - 1) / BN, (p.M + BM - 1) / BM, p.splits);
+  if ((r = make_map(&mb_hi, o.b_hi, p.Kred, o.b_rows, o.ldb, BK, BN / CL))) return r;
+  if ((r = make_map(&mb_lo, o.b_lo, p.Kred, o.b_rows, o.ldb, BK, BN / CL))) return r;
+  dim3 grid(((p.M + BM - 1) / BM + CL - 1) / CL * CL, (p.N + BN - 1) / BN, p.splits);   // whole pairs of row tiles
   if (n_blocks_out) *n_blocks_out = grid.x * grid.y;
-  auto kern = k_umma_gemm<BN, A_MN, KB>;
+  auto kern = k_umma_gemm<BN, A_MN, KB, CL>;
   static bool attr_set = false;   // per template instantiation
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem<BN, KB>::TOTAL);
-    if (e != cudaSuccess) return drb_fail(DRB_E_CUDA, "cudaFuncSetAttribute(smem=%d) failed: %s", Smem<BN, KB>::TOTAL, cudaGetErrorString(e));
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
+    if (e != cudaSuccess) return drb_fail(DRB_E_CUDA, "cudaFuncSetAttribute(smem=%d) failed: %s", SMEM, cudaGetErrorString(e));
     attr_set = true;
   }
   drb_prof_scope prof_(ctx, A_MN ? "k_umma_gemm_mn" : "k_umma_gemm_kk");
-  kern<<<grid, THREADS, Smem<BN, KB>::TOTAL, ctx->stream>>>(ma_hi, ma_lo, mb_hi, mb_lo, p);
+  if (CL > 1) {
+    cudaLaunchConfig_t cfg{};
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = CL; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.gridDim = grid; cfg.blockDim = dim3(THREADS); cfg.dynamicSmemBytes = SMEM; cfg.stream = ctx->stream;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, ma_hi, ma_lo, mb_hi, mb_lo, p);
+    if (e != cudaSuccess) return drb_fail(DRB_E_CUDA, "cluster launch of k_umma_gemm failed: %s", cudaGetErrorString(e));
+  } else {
+    kern<<<grid, THREADS, SMEM, ctx->stream>>>(ma_hi, ma_lo, mb_hi, mb_lo, p);
+  }
   DRB_LAUNCH_CHECK(ctx, "k_umma_gemm");
   return DRB_OK;
 }
@@ -299,19 +337,24 @@ int launch_umma_store(drb_ctx* ctx, const UmmaOperands& o, bool a_mn_major, int 
   p.atomic_out = atomic_out ? 1 : 0;
   if (N > 256) return drb_fail(DRB_E_INVALID, "umma store GEMM: N must be <= 256 (hidden width)");
   static const int bk_env = getenv("DRB_UMMA_BK") ? atoi(getenv("DRB_UMMA_BK")) : 0;   // profiling override: 16 | 32
-#define DRB_UMMA_CASE(BN, KB_DEFAULT)                                            \
+  static const int cl_env = getenv("DRB_UMMA_CLUSTER") ? atoi(getenv("DRB_UMMA_CLUSTER")) : 0;   // override: 1 | 2
+#define DRB_UMMA_CASE(BN, KB_DEFAULT, CL_DEFAULT)                                \
   if (N <= BN) {                                                                 \
     if ((bk_env ? bk_env : KB_DEFAULT) == 16) {                                  \
-      if (a_mn_major) return run_umma<BN, true, 16>(ctx, o, p, nullptr);         \
-      return run_umma<BN, false, 16>(ctx, o, p, nullptr);                        \
+      if ((cl_env ? cl_env : CL_DEFAULT) == 2) {                                 \
+        if (a_mn_major) return run_umma<BN, true, 16, 2>(ctx, o, p, nullptr);    \
+        return run_umma<BN, false, 16, 2>(ctx, o, p, nullptr);                   \
+      }                                                                          \
+      if (a_mn_major) return run_umma<BN, true, 16, 1>(ctx, o, p, nullptr);      \
+      return run_umma<BN, false, 16, 1>(ctx, o, p, nullptr);                     \
     }                                                                            \
-    if (a_mn_major) return run_umma<BN, true, 32>(ctx, o, p, nullptr);           \
-    return run_umma<BN, false, 32>(ctx, o, p, nullptr);                          \
+    if (a_mn_major) return run_umma<BN, true, 32, 1>(ctx, o, p, nullptr);        \
+    return run_umma<BN, false, 32, 1>(ctx, o, p, nullptr);                       \
   }
-  DRB_UMMA_CASE(64, 32)
-  DRB_UMMA_CASE(128, 32)
-  DRB_UMMA_CASE(208, 16)
-  DRB_UMMA_CASE(256, 16)
+  DRB_UMMA_CASE(64, 32, 1)
+  DRB_UMMA_CASE(128, 32, 1)
+  DRB_UMMA_CASE(208, 16, 2)
+  DRB_UMMA_CASE(256, 16, 2)
 #undef DRB_UMMA_CASE
   return drb_fail(DRB_E_INVALID, "umma store GEMM: unsupported N");
 }

@@ -20,14 +20,17 @@
 
 namespace {
 
+constexpr int DRB_LOSS_CLUSTER_DEFAULT = 2;              // 2 = CTA pairs, cta_group::2 MMAs (env DRB_LOSS_CLUSTER)
 constexpr int LOSS_EPI_WARPS = 16;                      // four per TMEM sub-partition, each takes a quarter of the columns
 constexpr int LOSS_THREADS = 64 + 32 * LOSS_EPI_WARPS;
 
-template <int BN, int KB>   // KB: floats of the hidden dimension per pipeline stage (see umma.cu: Smem)
+// KB: floats of the hidden dimension per pipeline stage; CL = 2: CTA pair, each CTA stages half of the h rows (see
+// umma.cu: Smem)
+template <int BN, int KB, int CL>
 struct LossSmem {
-  static constexpr int STAGES = (KB == 32) ? ((BN <= 128) ? 3 : 2) : ((BN <= 128) ? 6 : 4);
   static constexpr int A_BYTES = BM * KB * 4;
-  static constexpr int B_BYTES = BN * KB * 4;
+  static constexpr int B_BYTES = (BN / CL) * KB * 4;
+  static constexpr int STAGES = 192 * 1024 / (2 * A_BYTES + 2 * B_BYTES);
   static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
   static constexpr int BAR_BYTES = 256;
   static constexpr int TOTAL = STAGES * STAGE_BYTES + 1024 + BAR_BYTES;
@@ -53,12 +56,20 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 
-template <int BN, int LOSS, bool PER_USER, int KB>
+__device__ __forceinline__ void mbar_arrive_rank(uint32_t bar, uint32_t rank) {   // same barrier offset in CTA `rank`
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(mapa_rank(bar, rank)) : "memory");
+}
+
+// CL = 2: the two CTAs of a cluster (one TPC) work on two item tiles of the same batch tile as a CTA pair: the even
+// CTA issues cta_group::2 MMAs (M = 256) that read each CTA's own W' tile and each CTA's half of the shared h tile and
+// write each CTA's own accumulator, so the h tile is staged once per pair and the MMAs read a third less shared memory.
+// (TMA multicast of the h tile with one-CTA MMAs was measured first: no gain, 0.299 vs 0.302 ms.)
+template <int BN, int LOSS, bool PER_USER, int KB, int CL>
 __global__ void __launch_bounds__(LOSS_THREADS, 1)
 k_umma_cdae_loss(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                  const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
                  LossParams p) {
-  using S = LossSmem<BN, KB>;
+  using S = LossSmem<BN, KB, CL>;
   constexpr int BK = KB;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
@@ -74,7 +85,14 @@ k_umma_cdae_loss(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nkb = (p.debug & 2) ? 0 : (p.Kred + BK - 1) / BK;
-  const int n_tiles_total = p.m_tiles * p.n_tiles;
+  // work units: CL = 1 -> one tile per CTA per iteration; CL = 2 -> one pair of item tiles per cluster per iteration.
+  // Batch tiles run fastest, so co-running CTAs share W' tiles in L2.
+  const uint32_t cta_rank = (CL > 1) ? cluster_ctarank() : 0u;
+  const bool leader = cta_rank == 0;
+  const int unit0 = blockIdx.x / CL, unit_stride = gridDim.x / CL;
+  const int n_units = ((p.m_tiles + CL - 1) / CL) * p.n_tiles;
+  auto unit_item0 = [&](int u) { return ((u / p.n_tiles) * CL + (int)cta_rank) * BM; };
+  auto unit_row0 = [&](int u) { return (u % p.n_tiles) * BN; };
   constexpr uint32_t TMEM_COLS = (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
 
   if (threadIdx.x == 0) {
@@ -84,16 +102,21 @@ k_umma_cdae_loss(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
     }
     for (int a = 0; a < 2; a++) {
       mbar_init(tfull_bar(a), 1);
-      mbar_init(tempty_bar(a), LOSS_EPI_WARPS);     // one arrival per epilogue warp
+      mbar_init(tempty_bar(a), CL * LOSS_EPI_WARPS);   // one arrival per epilogue warp of the pair (even CTA's is used)
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_ptr_addr), "r"(TMEM_COLS));
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    if (CL > 1) {   // collective: the same warp of both CTAs
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_ptr_addr), "r"(TMEM_COLS));
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_ptr_addr), "r"(TMEM_COLS));
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  __syncthreads();
+  if (CL > 1) cluster_sync_all(); else __syncthreads();   // peers' barriers are initialised before anything is sent
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_ptr_generic;
 
@@ -101,28 +124,39 @@ k_umma_cdae_loss(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
     // ------------------------------------------------------------------ TMA producer (runs ahead across tiles)
     if (lane == 0) {
       int it = 0;
-      for (int t = blockIdx.x; t < n_tiles_total; t += gridDim.x) {
-        const int i0 = (t / p.n_tiles) * BM, r0 = (t % p.n_tiles) * BN;   // batch tiles fastest: co-running CTAs share W'
+      for (int t = unit0; t < n_units; t += unit_stride) {
+        const int i0 = unit_item0(t), r0 = unit_row0(t);
         for (int kb = 0; kb < nkb; kb++, it++) {
           const int s = it % S::STAGES;
           const uint32_t ph = (it / S::STAGES) & 1;
           mbar_wait(empty_bar(s), ph ^ 1);
-          mbar_expect_tx(full_bar(s), S::STAGE_BYTES - ((p.debug & 8) ? S::B_BYTES : 0));
           const uint32_t sa_hi = base + s * S::STAGE_BYTES, sa_lo = sa_hi + S::A_BYTES;
           const uint32_t sb_hi = sa_lo + S::A_BYTES, sb_lo = sb_hi + S::B_BYTES;
-          tma_load_2d(sa_hi, &map_a_hi, full_bar(s), kb * BK, i0);
-          tma_load_2d(sa_lo, &map_a_lo, full_bar(s), kb * BK, i0);
-          tma_load_2d(sb_hi, &map_b_hi, full_bar(s), kb * BK, r0);
-          if (!(p.debug & 8)) tma_load_2d(sb_lo, &map_b_lo, full_bar(s), kb * BK, r0);
+          if (CL > 1) {   // both CTAs' loads report to the even CTA's barrier; this CTA stages its half of the h rows
+            if (leader) mbar_expect_tx(full_bar(s), CL * S::STAGE_BYTES);
+            const uint32_t fb = mapa_rank(full_bar(s), 0);
+            const int rh = r0 + (int)cta_rank * (BN / CL);
+            tma_load_2d_pair(sa_hi, &map_a_hi, fb, kb * BK, i0);
+            tma_load_2d_pair(sa_lo, &map_a_lo, fb, kb * BK, i0);
+            tma_load_2d_pair(sb_hi, &map_b_hi, fb, kb * BK, rh);
+            tma_load_2d_pair(sb_lo, &map_b_lo, fb, kb * BK, rh);
+          } else {
+            mbar_expect_tx(full_bar(s), S::STAGE_BYTES - ((p.debug & 8) ? S::B_BYTES : 0));
+            tma_load_2d(sa_hi, &map_a_hi, full_bar(s), kb * BK, i0);
+            tma_load_2d(sa_lo, &map_a_lo, full_bar(s), kb * BK, i0);
+            tma_load_2d(sb_hi, &map_b_hi, full_bar(s), kb * BK, r0);
+            if (!(p.debug & 8)) tma_load_2d(sb_lo, &map_b_lo, full_bar(s), kb * BK, r0);
+          }
         }
       }
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
-      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+    if (lane == 0 && leader) {
+      const uint32_t idesc =
+          (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((BM * CL) >> 4) << 24);
       int it = 0, tl = 0;
-      for (int t = blockIdx.x; t < n_tiles_total; t += gridDim.x, tl++) {
+      for (int t = unit0; t < n_units; t += unit_stride, tl++) {
         const int as = tl & 1;
         mbar_wait(tempty_bar(as), ((tl >> 1) & 1) ^ 1);     // epilogue has drained this accumulator
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -137,13 +171,21 @@ k_umma_cdae_loss(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
           for (int kk = 0; kk < ((p.debug & 16) ? 0 : BK / UMMA_K); kk++) {
             const uint64_t a_hi = make_desc_kmajor<BK>(sa_hi, kk), a_lo = make_desc_kmajor<BK>(sa_lo, kk);
             const uint64_t b_hi = make_desc_kmajor<BK>(sb_hi, kk), b_lo = make_desc_kmajor<BK>(sb_lo, kk);
-            umma_tf32(tacc, a_lo, b_hi, idesc, (kb | kk) != 0);
-            umma_tf32(tacc, a_hi, b_lo, idesc, 1u);
-            umma_tf32(tacc, a_hi, b_hi, idesc, 1u);
+            if (CL > 1) {
+              umma_tf32_pair(tacc, a_lo, b_hi, idesc, (kb | kk) != 0);
+              umma_tf32_pair(tacc, a_hi, b_lo, idesc, 1u);
+              umma_tf32_pair(tacc, a_hi, b_hi, idesc, 1u);
+            } else {
+              umma_tf32(tacc, a_lo, b_hi, idesc, (kb | kk) != 0);
+              umma_tf32(tacc, a_hi, b_lo, idesc, 1u);
+              umma_tf32(tacc, a_hi, b_hi, idesc, 1u);
+            }
           }
-          umma_commit(empty_bar(s));
+          if (CL > 1) umma_commit_pair(empty_bar(s));   // frees the stage in both CTAs' producers
+          else umma_commit(empty_bar(s));
         }
-        umma_commit(tfull_bar(as));
+        if (CL > 1) umma_commit_pair(tfull_bar(as));
+        else umma_commit(tfull_bar(as));
       }
     }
   } else {
@@ -160,21 +202,21 @@ k_umma_cdae_loss(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
     // per-item constants (b', batch-mean label) live in registers and are fetched one tile ahead
     float nbias, ncount;
     auto fetch_consts = [&](int t) {
-      const int item = (t / p.n_tiles) * BM + q * 32 + lane;
-      const bool in = (t < n_tiles_total) && (item < p.N);
+      const int item = unit_item0(t) + q * 32 + lane;
+      const bool in = (t < n_units) && (item < p.N);
       nbias = in ? __ldg(p.bias + item) : 0.f;
       ncount = (!PER_USER && in) ? __ldg(p.label_count + item) : 0.f;
     };
-    fetch_consts(blockIdx.x);
+    fetch_consts(unit0);
     int tl = 0;
-    for (int t = blockIdx.x; t < n_tiles_total; t += gridDim.x, tl++) {
-      const int i0 = (t / p.n_tiles) * BM, r0 = (t % p.n_tiles) * BN;
+    for (int t = unit0; t < n_units; t += unit_stride, tl++) {
+      const int i0 = unit_item0(t), r0 = unit_row0(t);
       const int as = tl & 1;
       const int item = i0 + q * 32 + lane;
       const bool item_ok = item < p.N;
       const int ib = (i0 >> 5) + q;               // 32-item block of this warp
       const float bias = nbias, tgt_c = ncount / fbatch;
-      fetch_consts(t + gridDim.x);
+      fetch_consts(t + unit_stride);
       mbar_wait(tfull_bar(as), (tl >> 1) & 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN + cq * CW);
@@ -241,7 +283,10 @@ k_umma_cdae_loss(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
       // this warp has finished reading accumulator `as`
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
-      if (lane == 0) mbar_arrive(tempty_bar(as));
+      if (lane == 0) {
+        if (CL > 1) mbar_arrive_rank(tempty_bar(as), 0);
+        else mbar_arrive(tempty_bar(as));
+      }
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) loss_local += __shfl_xor_sync(0xffffffffu, loss_local, o);
@@ -255,14 +300,15 @@ k_umma_cdae_loss(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
     }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  __syncthreads();
+  if (CL > 1) cluster_sync_all(); else __syncthreads();   // no CTA leaves while its peer can still write to it
   if (warp == 1) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS));
+    if (CL > 1) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS));
+    else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS));
   }
 }
 
-template <int BN, int LOSS, bool PER_USER, int KB>
+template <int BN, int LOSS, bool PER_USER, int KB, int CL>
 int run_loss(drb_ctx* ctx, const UmmaOperands& o, LossParams p, int* n_blocks_out) {
   constexpr int BK = KB;
   CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
@@ -271,23 +317,48 @@ int run_loss(drb_ctx* ctx, const UmmaOperands& o, LossParams p, int* n_blocks_ou
   // B (N side, BN TMEM columns) = h rows = batch rows
   if ((r = make_map(&ma_hi, o.b_hi, p.Kred, o.b_rows, o.ldb, BK, BM))) return r;
   if ((r = make_map(&ma_lo, o.b_lo, p.Kred, o.b_rows, o.ldb, BK, BM))) return r;
-  if ((r = make_map(&mb_hi, o.a_hi, p.Kred, p.M, o.lda, BK, BN))) return r;
-  if ((r = make_map(&mb_lo, o.a_lo, p.Kred, p.M, o.lda, BK, BN))) return r;
+  if ((r = make_map(&mb_hi, o.a_hi, p.Kred, p.M, o.lda, BK, BN / CL))) return r;
+  if ((r = make_map(&mb_lo, o.a_lo, p.Kred, p.M, o.lda, BK, BN / CL))) return r;
   p.m_tiles = (p.N + BM - 1) / BM;      // item tiles
   p.n_tiles = (p.M + BN - 1) / BN;      // batch tiles
   p.row_tiles = (p.M + 127) / 128;
-  const int grid = std::min(p.m_tiles * p.n_tiles, ctx->sm_count);
-  *n_blocks_out = grid;
-  auto kern = k_umma_cdae_loss<BN, LOSS, PER_USER, KB>;
-  static bool attr_set = false;
+  auto kern = k_umma_cdae_loss<BN, LOSS, PER_USER, KB, CL>;
+  constexpr int SMEM = LossSmem<BN, KB, CL>::TOTAL;
+  static bool attr_set = false;       // per template instantiation
+  static int max_clusters = 0;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, LossSmem<BN, KB>::TOTAL);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
     if (e != cudaSuccess)
-      return drb_fail(DRB_E_CUDA, "cudaFuncSetAttribute(smem=%d) failed: %s", LossSmem<BN, KB>::TOTAL, cudaGetErrorString(e));
+      return drb_fail(DRB_E_CUDA, "cudaFuncSetAttribute(smem=%d) failed: %s", SMEM, cudaGetErrorString(e));
+    if (CL > 1) {   // clusters are placed inside a GPC: ask how many fit at once, the kernel is persistent
+      cudaLaunchConfig_t qc{};
+      cudaLaunchAttribute qa[1];
+      qa[0].id = cudaLaunchAttributeClusterDimension;
+      qa[0].val.clusterDim.x = CL; qa[0].val.clusterDim.y = 1; qa[0].val.clusterDim.z = 1;
+      qc.gridDim = dim3(ctx->sm_count / CL * CL); qc.blockDim = dim3(LOSS_THREADS); qc.dynamicSmemBytes = SMEM;
+      qc.attrs = qa; qc.numAttrs = 1;
+      e = cudaOccupancyMaxActiveClusters(&max_clusters, kern, &qc);
+      if (e != cudaSuccess || max_clusters < 1)
+        return drb_fail(DRB_E_CUDA, "cudaOccupancyMaxActiveClusters failed: %s", cudaGetErrorString(e));
+    }
     attr_set = true;
   }
+  const int n_units = ((p.m_tiles + CL - 1) / CL) * p.n_tiles;
+  const int grid = CL * std::min(n_units, CL > 1 ? max_clusters : ctx->sm_count);
+  *n_blocks_out = grid;
   drb_prof_scope prof_(ctx, "k_umma_cdae_loss");
-  kern<<<grid, LOSS_THREADS, LossSmem<BN, KB>::TOTAL, ctx->stream>>>(ma_hi, ma_lo, mb_hi, mb_lo, p);
+  if (CL > 1) {
+    cudaLaunchConfig_t cfg{};
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = CL; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(LOSS_THREADS); cfg.dynamicSmemBytes = SMEM; cfg.stream = ctx->stream;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, ma_hi, ma_lo, mb_hi, mb_lo, p);
+    if (e != cudaSuccess) return drb_fail(DRB_E_CUDA, "cluster launch of k_umma_cdae_loss failed: %s", cudaGetErrorString(e));
+  } else {
+    kern<<<grid, LOSS_THREADS, SMEM, ctx->stream>>>(ma_hi, ma_lo, mb_hi, mb_lo, p);
+  }
   DRB_LAUNCH_CHECK(ctx, "k_umma_cdae_loss");
   return DRB_OK;
 }
@@ -310,20 +381,22 @@ int launch_umma_cdae_loss(drb_ctx* ctx, const UmmaOperands& o, int M, int N, int
   // 256 batch rows per tile halve the re-reads of the W' tile (the main loop is L2->SM bandwidth bound)
   const bool wide = bn_env ? (bn_env == 256) : (M > 128);
   static const int bk_env = getenv("DRB_UMMA_BK") ? atoi(getenv("DRB_UMMA_BK")) : 0;   // profiling override: 16 | 32
-#define DRB_LOSS_CASE(BN_, KB_)                                                                     \
+  static const int cl_env = getenv("DRB_LOSS_CLUSTER") ? atoi(getenv("DRB_LOSS_CLUSTER")) : 0;   // override: 1 | 2
+#define DRB_LOSS_CASE(BN_, KB_, CL_)                                                                \
   {                                                                                                 \
     if (loss_kind == DRB_LOSS_BCE)                                                                  \
-      return per_user ? run_loss<BN_, DRB_LOSS_BCE, true, KB_>(ctx, o, p, n_blocks_out)             \
-                      : run_loss<BN_, DRB_LOSS_BCE, false, KB_>(ctx, o, p, n_blocks_out);           \
-    return per_user ? run_loss<BN_, DRB_LOSS_MSE, true, KB_>(ctx, o, p, n_blocks_out)               \
-                    : run_loss<BN_, DRB_LOSS_MSE, false, KB_>(ctx, o, p, n_blocks_out);             \
+      return per_user ? run_loss<BN_, DRB_LOSS_BCE, true, KB_, CL_>(ctx, o, p, n_blocks_out)        \
+                      : run_loss<BN_, DRB_LOSS_BCE, false, KB_, CL_>(ctx, o, p, n_blocks_out);      \
+    return per_user ? run_loss<BN_, DRB_LOSS_MSE, true, KB_, CL_>(ctx, o, p, n_blocks_out)          \
+                    : run_loss<BN_, DRB_LOSS_MSE, false, KB_, CL_>(ctx, o, p, n_blocks_out);        \
   }
   if (wide) {
+    if ((cl_env ? cl_env : DRB_LOSS_CLUSTER_DEFAULT) == 2) DRB_LOSS_CASE(256, 32, 2)
     // the persistent loop already keeps TMA ahead across tiles: 32-deep stages measured 0.30 ms, 16-deep 0.31 ms
-    if ((bk_env ? bk_env : 32) == 16) DRB_LOSS_CASE(256, 16)
-    DRB_LOSS_CASE(256, 32)
+    if ((bk_env ? bk_env : 32) == 16) DRB_LOSS_CASE(256, 16, 1)
+    DRB_LOSS_CASE(256, 32, 1)
   }
-  if ((bk_env ? bk_env : 32) == 16) DRB_LOSS_CASE(128, 16)
-  DRB_LOSS_CASE(128, 32)
+  if ((bk_env ? bk_env : 32) == 16) DRB_LOSS_CASE(128, 16, 1)
+  DRB_LOSS_CASE(128, 32, 1)
 #undef DRB_LOSS_CASE
 }
