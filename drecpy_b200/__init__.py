@@ -9,11 +9,12 @@ from .recommender import DeepRecommenderABC
 from .cdae import CDAE
 from .dmf import DMF
 from .evaluation import ranking_evaluation, HitRatio, NDCG, DCG, Precision, Recall
+from .splits import leave_k_out
 from .early_stopping import MaxValidationValueRule
 from .loss_tracker import LossTracker
 
 InteractionDataset = InteractionData
 
-__all__ = ['InteractionData', 'InteractionDataset', 'synthetic_interactions', 'PointSampler', 'DeepRecommenderABC',
+__all__ = ['InteractionData', 'InteractionDataset', 'synthetic_interactions', 'PointSampler', 'DeepRecommenderABC', 'leave_k_out',
            'CDAE', 'DMF', 'ranking_evaluation', 'HitRatio', 'NDCG', 'DCG', 'Precision', 'Recall',
            'MaxValidationValueRule', 'LossTracker']

@@ -175,7 +175,11 @@ struct drb_cdae {
   int n2, batch_pad;   // tcgen05 path: N of the backward GEMMs (hidden + ones feature, rounded to 16), padded batch
 };
 
-static int cdae_n2(int hidden) { return (int)drb_round_up(hidden + 1, 16); }
+// N of the backward GEMMs: hidden plus the constant-one feature that folds db' = colsum(dz) into dW'^T, rounded to 16.
+// tcgen05 tiles are at most 256 wide: for hidden in 241..256 the feature does not fit and the loss kernel accumulates
+// db' itself (cdae_colsum_in_loss).
+static bool cdae_colsum_in_loss(int hidden) { return drb_round_up(hidden + 1, 16) > 256 && hidden <= 256; }
+static int cdae_n2(int hidden) { return (int)drb_round_up(hidden + (cdae_colsum_in_loss(hidden) ? 0 : 1), 16); }
 
 static int64_t cdae_keep_cap(int32_t n_items, int32_t max_batch) {
   // every sampled user can hold at most n_items positives; cap the staging buffer at 1 GiB
@@ -274,7 +278,7 @@ int drb_cdae_create(drb_ctx* ctx, const drb_cdae_desc* desc, drb_cdae** out) {
   const bool umma_ok = umma_available() && m->n2 <= 256;
   if (desc->gemm_path == DRB_GEMM_TCGEN05 && !umma_ok) {
     delete m;
-    return drb_fail(DRB_E_INVALID, "drb_cdae_create: the tcgen05 path needs hidden < 256 and a driver with TMA support");
+    return drb_fail(DRB_E_INVALID, "drb_cdae_create: the tcgen05 path needs hidden <= 256 and a driver with TMA support");
   }
   m->use_umma = umma_ok && desc->gemm_path != DRB_GEMM_FFMA;
   m->v_grad_clean = false;
@@ -423,7 +427,9 @@ int drb_cdae_step_phases(drb_cdae* m, const int32_t* uids, const int32_t* keep_o
   if ((phases & DRB_PHASE_GRADS_A2) || ((phases & DRB_PHASE_GRADS_A) && !sharded)) {
   if (sharded && (r = launch_sigmoid_rows(ctx, w.h, batch, ld, m->d.hidden))) return r;
   if (m->use_umma) {   // tf32 hi/lo operand splits for the tensor-core GEMMs (umma.cu)
-    if ((r = launch_split_tf32(ctx, w.h, batch, ld, ld, w.h_hi, w.h_lo, w.hT_hi, w.hT_lo, bp, m->d.hidden))) return r;
+    if ((r = launch_split_tf32(ctx, w.h, batch, ld, ld, w.h_hi, w.h_lo, w.hT_hi, w.hT_lo, bp,
+                               cdae_colsum_in_loss(m->d.hidden) ? -1 : m->d.hidden)))
+      return r;
     if ((r = launch_split_tf32(ctx, P + L.off_w2t, I, ld, ld, w.w2t_hi, w.w2t_lo, w.wT_hi, w.wT_lo, L.items_pad, -1)))
       return r;
   }
@@ -439,15 +445,17 @@ int drb_cdae_step_phases(drb_cdae* m, const int32_t* uids, const int32_t* keep_o
     UmmaOperands o1{w.h_hi, w.h_lo, ld, w.w2t_hi, w.w2t_lo, ld, I};
     if ((r = launch_umma_cdae_loss(ctx, o1, batch, I, ld, w.dzt_hi, w.dzt_lo, L.items_pad, P + L.off_b2,
                                    per_user ? nullptr : w.label_count, per_user ? w.label_bits : nullptr,
-                                   m->words_per_row, m->d.loss_kind, inv_count, gbatch, w.loss_part, &n_blocks)))
+                                   m->words_per_row, m->d.loss_kind, inv_count, gbatch, w.loss_part,
+                                   cdae_colsum_in_loss(m->d.hidden) ? G + L.off_b2 : nullptr, &n_blocks)))
       return r;
     // dW'^T = dz^T h (I x K); the constant-one feature at column `hidden` yields db' = colsum(dz)
     // e.g. 209 item tiles on 148 SMs would run as two uneven waves: split the batch reduction so the grid is ~2 waves
     // (the partial products accumulate with vector atomics into the pre-zeroed gradient)
     const int mt2 = (I + 127) / 128;
     const int s2 = batch >= 1024 ? std::max(1, std::min({16, (2 * ctx->sm_count + mt2 - 1) / mt2, batch / 512})) : 1;
-    if ((r = launch_umma_store(ctx, o2, true, I, n2, batch, s2, G + L.off_w2t, ld, ld, m->d.hidden, G + L.off_b2,
-                               m->d.hidden, s2 > 1)))
+    const bool colsum = cdae_colsum_in_loss(m->d.hidden);
+    if ((r = launch_umma_store(ctx, o2, true, I, n2, batch, s2, G + L.off_w2t, ld, ld, m->d.hidden,
+                               colsum ? nullptr : G + L.off_b2, colsum ? -1 : m->d.hidden, s2 > 1)))
       return r;
   } else {
   // 3. K2: z2 = h W'^T + b', p = sigmoid, loss terms, dL/dz2 (never materialises p)
@@ -639,6 +647,19 @@ struct drb_dmf {
   float *col_part, *loss_part, *reg_part, *loss_scalar, *labels, *p_tmp, *item_rep, *user_rep;
   int32_t *uids, *iids;
   int64_t ws_bytes;
+  // CUDA-graph replay of the training step (the C2 step is ~20 launches of a few microseconds each: launch bound).
+  // One instantiated graph per distinct argument set; the Adam step sizes -- the only per-step scalars -- are read
+  // from step_scalars, which a one-thread kernel refreshes before every replay.
+  // The graph always reads the batch from the model's own uids / iids / labels buffers (a caller's device arrays are
+  // copied there first), so there is one graph per (batch size, loss pointer, hyper-parameters).
+  struct Graph {
+    const void* loss_out;
+    int32_t batch; float beta1, beta2, eps, reg;
+    cudaGraphExec_t exec; int64_t launches;
+  } graphs[8];
+  int n_graphs, graph_next, graph_off, n_captures;
+  cudaStream_t cap_stream;     // capture happens here (the caller's stream may be the legacy default stream)
+  float* step_scalars;
 };
 
 static int dmf_fill_layout(int32_t n_users, int32_t n_items, const int32_t* uf, int32_t nu, const int32_t* itf,
@@ -696,6 +717,7 @@ static int64_t dmf_carve(drb_dmf* m, void* base, const drb_dmf_layout_t& L, int 
   if (m) {
     m->col_part = col; m->loss_part = lp; m->reg_part = rp; m->loss_scalar = ls; m->labels = lab; m->p_tmp = pt;
     m->item_rep = irep; m->user_rep = urep; m->uids = u; m->iids = i;
+    m->step_scalars = ls + 16;   // inside the 64-float scalar block, clear of the loss outputs
   }
   (void)n_users;
   return c.off;
@@ -780,6 +802,7 @@ int drb_dmf_create(drb_ctx* ctx, const drb_dmf_desc* d, drb_dmf** out) {
   if (!m) return drb_fail(DRB_E_NOMEM, "out of memory");
   std::memset(m, 0, sizeof(*m));
   m->ctx = ctx; m->d = *d; m->L = L;
+  { const char* ge = getenv("DRB_GRAPH"); m->graph_off = (ge && atoi(ge) == 0) ? 1 : 0; }   // DRB_GRAPH=0: direct launches
   for (int t = 0; t < 2; t++) {
     DmfTower& T = m->tw[t];
     T.n_layers = t ? L.n_layers_item : L.n_layers_user;
@@ -805,17 +828,20 @@ int drb_dmf_create(drb_ctx* ctx, const drb_dmf_desc* d, drb_dmf** out) {
   *out = m;
   return DRB_OK;
 }
-int drb_dmf_destroy(drb_dmf* m) { delete m; return DRB_OK; }
+int drb_dmf_destroy(drb_dmf* m) {
+  if (m) {
+    for (int i = 0; i < 8; i++)
+      if (m->graphs[i].exec) cudaGraphExecDestroy(m->graphs[i].exec);
+    if (m->cap_stream) cudaStreamDestroy(m->cap_stream);
+  }
+  delete m;
+  return DRB_OK;
+}
 
-int drb_dmf_step(drb_dmf* m, const int32_t* uids, const int32_t* iids, const float* labels, int32_t batch,
-                 const drb_dmf_step_args* a, float* loss_out) {
-  if (!m || !uids || !iids || !labels || !a || !loss_out) return drb_fail(DRB_E_INVALID, "drb_dmf_step: NULL argument");
-  if (batch <= 0 || batch > m->d.max_batch)
-    return drb_fail(DRB_E_INVALID, "drb_dmf_step: batch %d outside (0, max_batch=%d]", batch, m->d.max_batch);
-  if (!m->d.adam_m || !m->d.adam_v || !m->d.grads)
-    return drb_fail(DRB_E_STATE, "drb_dmf_step: model was created without optimizer arenas");
+// one training step enqueued on ctx->stream; alpha_dev != NULL: Adam step sizes come from device memory (graph capture)
+static int dmf_step_body(drb_dmf* m, const int32_t* uids, const int32_t* iids, const float* labels, int32_t batch,
+                         const drb_dmf_step_args* a, float* loss_out, const float* alpha_dev) {
   drb_ctx* ctx = m->ctx;
-  if (ctx->sticky) return drb_fail(DRB_E_CUDA, "context has a sticky CUDA error (%d)", ctx->sticky);
   int r;
   DRB_CUDA_TRY(ctx, cudaMemsetAsync(m->d.grads, 0, (size_t)m->L.total * sizeof(float), ctx->stream));
   if ((r = dmf_tower_fwd(m, 0, uids, batch))) return r;
@@ -831,6 +857,7 @@ int drb_dmf_step(drb_dmf* m, const int32_t* uids, const int32_t* iids, const flo
   AdamArgs ad{};
   ad.w = m->d.params; ad.m = m->d.adam_m; ad.v = m->d.adam_v; ad.g = m->d.grads;
   ad.beta1 = a->beta1; ad.beta2 = a->beta2; ad.eps = a->epsilon;
+  ad.alpha_dev = alpha_dev;
   int ns = 0;
   for (int t = 0; t < 2; t++) {
     const float alpha = drb_adam_alpha(a->learning_rate, a->beta1, a->beta2, a->t[t]);
@@ -838,9 +865,11 @@ int drb_dmf_step(drb_dmf* m, const int32_t* uids, const int32_t* iids, const flo
     int64_t in = T.in_dim;
     for (int l = 0; l < T.n_layers; l++) {
       ad.seg[ns].off4 = T.off_k[l] / 4; ad.seg[ns].n4 = in * T.ld[l] / 4; ad.seg[ns].alpha = alpha;
+      ad.seg[ns].alpha_idx = t;
       ad.seg[ns].l2 = 2.0f * a->reg_rate; ad.seg[ns].regw = a->reg_rate;       // regularizers.l2: reg * sum(w^2)
       ns++;
       ad.seg[ns].off4 = T.off_b[l] / 4; ad.seg[ns].n4 = T.ld[l] / 4; ad.seg[ns].alpha = alpha;
+      ad.seg[ns].alpha_idx = t;
       ad.seg[ns].l2 = 0.f; ad.seg[ns].regw = 0.f;
       ns++;
       in = T.width[l];
@@ -851,6 +880,76 @@ int drb_dmf_step(drb_dmf* m, const int32_t* uids, const int32_t* iids, const flo
   int n_reg = 0;
   if ((r = launch_adam(ctx, ad, &n_reg))) return r;
   return launch_finalize_loss(ctx, m->loss_part, batch, 1.0f / (float)batch, m->reg_part, n_reg, loss_out);
+}
+
+int drb_dmf_step(drb_dmf* m, const int32_t* uids, const int32_t* iids, const float* labels, int32_t batch,
+                 const drb_dmf_step_args* a, float* loss_out) {
+  if (!m || !uids || !iids || !labels || !a || !loss_out) return drb_fail(DRB_E_INVALID, "drb_dmf_step: NULL argument");
+  if (batch <= 0 || batch > m->d.max_batch)
+    return drb_fail(DRB_E_INVALID, "drb_dmf_step: batch %d outside (0, max_batch=%d]", batch, m->d.max_batch);
+  if (!m->d.adam_m || !m->d.adam_v || !m->d.grads)
+    return drb_fail(DRB_E_STATE, "drb_dmf_step: model was created without optimizer arenas");
+  drb_ctx* ctx = m->ctx;
+  if (ctx->sticky) return drb_fail(DRB_E_CUDA, "context has a sticky CUDA error (%d)", ctx->sticky);
+  if (m->graph_off || ctx->profile)    // per-kernel profiling brackets every launch with events: direct launches
+    return dmf_step_body(m, uids, iids, labels, batch, a, loss_out, nullptr);
+
+  if (uids != m->uids) DRB_CUDA_TRY(ctx, cudaMemcpyAsync(m->uids, uids, (size_t)batch * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+  if (iids != m->iids) DRB_CUDA_TRY(ctx, cudaMemcpyAsync(m->iids, iids, (size_t)batch * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+  if (labels != m->labels)
+    DRB_CUDA_TRY(ctx, cudaMemcpyAsync(m->labels, labels, (size_t)batch * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+  drb_dmf::Graph* g = nullptr;
+  for (int i = 0; i < m->n_graphs; i++) {
+    drb_dmf::Graph& c = m->graphs[i];
+    if (c.loss_out == loss_out && c.batch == batch && c.beta1 == a->beta1 && c.beta2 == a->beta2 && c.eps == a->epsilon && c.reg == a->reg_rate) { g = &c; break; }
+  }
+  if (!g) {
+    // capture the step once for this argument set (nothing executes during capture); a caller that keeps changing
+    // the argument set would pay a capture per step: give up on graphs after 32 captures
+    if (++m->n_captures > 32) {
+      m->graph_off = 1;
+      return dmf_step_body(m, m->uids, m->iids, m->labels, batch, a, loss_out, nullptr);
+    }
+    if (!m->cap_stream && cudaStreamCreateWithFlags(&m->cap_stream, cudaStreamNonBlocking) != cudaSuccess) {
+      cudaGetLastError();
+      m->graph_off = 1;
+      return dmf_step_body(m, uids, iids, labels, batch, a, loss_out, nullptr);
+    }
+    cudaStream_t user = ctx->stream;
+    const int64_t before = ctx->launches;
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t exec = nullptr;
+    int r = DRB_OK;
+    cudaError_t e = cudaStreamBeginCapture(m->cap_stream, cudaStreamCaptureModeThreadLocal);
+    if (e == cudaSuccess) {
+      ctx->stream = m->cap_stream;
+      r = dmf_step_body(m, m->uids, m->iids, m->labels, batch, a, loss_out, m->step_scalars);
+      ctx->stream = user;
+      e = cudaStreamEndCapture(m->cap_stream, &graph);
+    }
+    if (e == cudaSuccess && r == DRB_OK) e = cudaGraphInstantiate(&exec, graph, 0);
+    if (graph) cudaGraphDestroy(graph);
+    const int64_t captured = ctx->launches - before;
+    ctx->launches = before;
+    if (e != cudaSuccess || r != DRB_OK) {   // e.g. a driver without capture support for some node: run directly from now on
+      cudaGetLastError();
+      ctx->sticky = 0;
+      m->graph_off = 1;
+      return dmf_step_body(m, uids, iids, labels, batch, a, loss_out, nullptr);
+    }
+    const int slot = m->n_graphs < 8 ? m->n_graphs++ : (m->graph_next++ & 7);
+    if (m->graphs[slot].exec) cudaGraphExecDestroy(m->graphs[slot].exec);
+    m->graphs[slot] = drb_dmf::Graph{loss_out, batch, a->beta1, a->beta2, a->epsilon, a->reg_rate,
+                                     exec, captured};
+    g = &m->graphs[slot];
+  }
+  const float alphas[2] = {drb_adam_alpha(a->learning_rate, a->beta1, a->beta2, a->t[0]),
+                           drb_adam_alpha(a->learning_rate, a->beta1, a->beta2, a->t[1])};
+  int r = launch_set_scalars(ctx, m->step_scalars, alphas, 2);
+  if (r) return r;
+  DRB_CUDA_TRY(ctx, cudaGraphLaunch(g->exec, ctx->stream));
+  ctx->launches += g->launches;
+  return DRB_OK;
 }
 
 int drb_dmf_loss_buffer(drb_dmf* m, float** ptr) {

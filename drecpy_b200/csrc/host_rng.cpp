@@ -427,4 +427,45 @@ int drb_eval_candidates(int64_t n_users, const int64_t* test_indptr, const int64
   return DRB_OK;
 }
 
+// ---------------------------------------------------------------------------------------------- leave-k-out split
+// DRecPy/Evaluation/Splits/leave_k_out.py:14-135 for every user at once.  User idx (order of first appearance) draws
+// from random.Random(seed + idx + 1) -- the reference increments the seed *before* creating each user's generator
+// (leave_k_out.py:68-69) -- and rng.sample(rids, k) picks k of the user's rows, which are given here as positions
+// user_indptr[idx] .. user_indptr[idx+1] of the caller's "rows grouped by user, in DataFrame order" permutation.
+// flags[pos]: 0 = train, 1 = test, 2 = removed (user with fewer than min_user_interactions rows).
+int drb_leave_k_out(int64_t n_users, const int64_t* user_indptr, int64_t k_fixed, double k_ratio, int32_t is_ratio,
+                    int64_t min_user_interactions, int64_t seed, int32_t n_threads, uint8_t* flags) {
+  if (n_users < 0 || !user_indptr || !flags) return drb_fail(DRB_E_INVALID, "drb_leave_k_out: bad argument");
+  if (!is_ratio && k_fixed <= 0) return drb_fail(DRB_E_INVALID, "The value of k (%lld) must be > 0.", (long long)k_fixed);
+  auto worker = [&](int64_t lo, int64_t hi) {
+    drb_rng g;
+    std::vector<int64_t> picked;
+    for (int64_t u = lo; u < hi; u++) {
+      const int64_t beg = user_indptr[u], n = user_indptr[u + 1] - beg;
+      const int64_t k = is_ratio ? (int64_t)((double)n * k_ratio) : k_fixed;   // int(len * k)
+      if (n < min_user_interactions) {
+        std::fill(flags + beg, flags + beg + n, (uint8_t)2);
+      } else if (n > k && k > 0) {
+        const int64_t s = seed + u + 1;
+        g.seed((uint64_t)(s < 0 ? -s : s));
+        picked.resize(k);
+        sample_indices(g, n, k, picked.data());
+        for (int64_t j = 0; j < k; j++) flags[beg + picked[j]] = 1;
+      }
+    }
+  };
+  int nt = std::max(1, std::min<int>(n_threads, 64));
+  if (n_users < 1024) nt = 1;
+  if (nt == 1) {
+    worker(0, n_users);
+  } else {
+    std::vector<std::thread> th;
+    const int64_t per = (n_users + nt - 1) / nt;
+    for (int t = 0; t < nt; t++)
+      th.emplace_back(worker, std::min<int64_t>(n_users, t * per), std::min<int64_t>(n_users, (t + 1) * per));
+    for (auto& x : th) x.join();
+  }
+  return DRB_OK;
+}
+
 }  // extern "C"

@@ -108,20 +108,24 @@ inline int64_t drb_dz_tiled_floats(int rows, int n_cols) { return (int64_t)((row
 int launch_umma_cdae_loss(drb_ctx* ctx, const UmmaOperands& o, int M, int N, int Kred, float* dz_hi, float* dz_lo,
                           int ldc, const float* bias, const float* label_count, const uint32_t* label_bits,
                           int words_per_row, int loss_kind, float inv_count, int batch, float* loss_part,
-                          int* n_blocks_out);
+                          float* dz_colsum /* may be NULL: [N] += colsum(dz), i.e. db' */, int* n_blocks_out);
 int launch_umma_store(drb_ctx* ctx, const UmmaOperands& o, bool a_mn_major, int M, int N, int Kred, int splits,
                       float* C, int ldc, int n_store, int n_valid, float* extra_col, int extra_col_index,
                       bool atomic_out = false);
 
 // ------------------------------------------------------------------ optim.cu
 #define DRB_MAX_SEGS 40
-struct AdamSeg { int64_t off4, n4; float alpha, l2, regw; };
+struct AdamSeg { int64_t off4, n4; float alpha, l2, regw; int alpha_idx; };
 struct AdamArgs {
   float* w; float* m; float* v; const float* g;
   AdamSeg seg[DRB_MAX_SEGS]; int nseg;
   float beta1, beta2, eps;
   float* reg_part;                    // [blocks] partial sums of regw * w^2 (pre-update weights)
+  const float* alpha_dev;             // may be NULL; else alpha of segment s = alpha_dev[seg[s].alpha_idx] (graph replay:
+                                      // the step sizes are the only scalars of a step that change from step to step)
 };
+// dst[i] = vals[i], i < n <= 8 (one tiny launch; the values travel as kernel arguments)
+int launch_set_scalars(drb_ctx* ctx, float* dst, const float* vals, int n);
 int launch_adam(drb_ctx* ctx, const AdamArgs& a, int* n_blocks_out);
 // loss_out = sum(loss_part) * scale + sum(reg_part)
 int launch_finalize_loss(drb_ctx* ctx, const float* loss_part, int n_loss, float scale, const float* reg_part,

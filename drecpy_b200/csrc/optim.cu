@@ -23,7 +23,8 @@ __global__ void __launch_bounds__(kAdamThreads) k_adam(AdamArgs a, int64_t total
 #pragma unroll 1
     while (s + 1 < a.nseg && i >= a.seg[s + 1].off4) s++;
     if (i >= a.seg[s].off4 + a.seg[s].n4) continue;  // alignment gap between segments
-    const float alpha = a.seg[s].alpha, l2 = a.seg[s].l2, regw = a.seg[s].regw;
+    const float alpha = a.alpha_dev ? __ldg(a.alpha_dev + a.seg[s].alpha_idx) : a.seg[s].alpha;
+    const float l2 = a.seg[s].l2, regw = a.seg[s].regw;
     float4 w = reinterpret_cast<float4*>(a.w)[i];
     float4 m = reinterpret_cast<float4*>(a.m)[i];
     float4 v = reinterpret_cast<float4*>(a.v)[i];
@@ -74,7 +75,21 @@ __global__ void __launch_bounds__(256) k_finalize_loss(const float* __restrict__
   }
 }
 
+struct Scalars8 { float v[8]; };
+__global__ void k_set_scalars(float* __restrict__ dst, Scalars8 s, int n) {
+  if ((int)threadIdx.x < n) dst[threadIdx.x] = s.v[threadIdx.x];
+}
+
 }  // namespace
+
+int launch_set_scalars(drb_ctx* ctx, float* dst, const float* vals, int n) {
+  if (n < 0 || n > 8) return drb_fail(DRB_E_INVALID, "launch_set_scalars: n must be in [0, 8]");
+  Scalars8 s{};
+  for (int i = 0; i < n; i++) s.v[i] = vals[i];
+  k_set_scalars<<<1, 32, 0, ctx->stream>>>(dst, s, n);
+  DRB_LAUNCH_CHECK(ctx, "k_set_scalars");
+  return DRB_OK;
+}
 
 float drb_adam_alpha(float lr, float beta1, float beta2, int t) {
   // Keras computes this in fp32: lr * sqrt(1 - beta2^t) / (1 - beta1^t)

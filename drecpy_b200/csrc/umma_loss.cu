@@ -43,6 +43,7 @@ struct LossParams {
   const float* label_count; const uint32_t* label_bits; int words_per_row;
   int loss_kind; float inv_count; int batch;
   float* loss_part;                        // [gridDim.x]
+  float* colsum;                           // NULL, or [N]: db' += column sums of dz (hidden = 241..256: no room for the ones feature)
   int m_tiles, n_tiles, row_tiles;         // item tiles (128), batch tiles (BN), 128-row tiles of the dz layout
   int debug;   // DRB_LOSS_DEBUG bit mask (profiling experiments only, results are wrong): 1 = first 16-row chunk of
                // each epilogue warp only, 2 = skip TMA + MMA, 4 = skip the dz stores, 8 = skip the B_lo loads, 16 = skip the MMAs
@@ -222,6 +223,7 @@ k_umma_cdae_loss(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
       const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN + cq * CW);
       uint32_t rn[16];
       tmem_ld16_issue(tbase, rn);
+      float csum = 0.f;                           // this lane's item: sum of dL/dz2 over the warp's batch rows
 #pragma unroll 1
       for (int cl = 0; cl < ((p.debug & 1) ? 16 : CW); cl += 16) {
         const int row = r0 + cq * CW + cl;        // first of this chunk's 16 batch rows (same 128-row tile: 16 | 128)
@@ -267,6 +269,10 @@ k_umma_cdae_loss(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
           split_tf32(g, h, lo[j]);
           r[j] = __float_as_uint(h);
         }
+        if (p.colsum) {
+#pragma unroll
+          for (int j = 0; j < 16; j++) csum += __uint_as_float(r[j]) + lo[j];
+        }
         // tile-major store: row j of this chunk is the 128-byte line ((row tile, item block), row in tile) and the
         // lanes are its 32 floats.  Every row and column of an existing tile is written (zeros outside the matrix)
         // because the backward GEMMs read whole tiles.
@@ -280,6 +286,7 @@ k_umma_cdae_loss(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
           }
         }
       }
+      if (p.colsum && item_ok) atomicAdd(p.colsum + item, csum);
       // this warp has finished reading accumulator `as`
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
@@ -368,12 +375,12 @@ int run_loss(drb_ctx* ctx, const UmmaOperands& o, LossParams p, int* n_blocks_ou
 int launch_umma_cdae_loss(drb_ctx* ctx, const UmmaOperands& o, int M, int N, int Kred, float* dz_hi, float* dz_lo,
                           int ldc, const float* bias, const float* label_count, const uint32_t* label_bits,
                           int words_per_row, int loss_kind, float inv_count, int batch, float* loss_part,
-                          int* n_blocks_out) {
+                          float* dz_colsum, int* n_blocks_out) {
   LossParams p{};
   p.M = M; p.N = N; p.Kred = Kred; p.nib = drb_dz_nib(N); p.dz_hi = dz_hi; p.dz_lo = dz_lo; p.bias = bias;
   (void)ldc;
   p.label_count = label_count; p.label_bits = label_bits; p.words_per_row = words_per_row; p.loss_kind = loss_kind;
-  p.inv_count = inv_count; p.batch = batch; p.loss_part = loss_part;
+  p.inv_count = inv_count; p.batch = batch; p.loss_part = loss_part; p.colsum = dz_colsum;
   static const int dbg_env = getenv("DRB_LOSS_DEBUG") ? atoi(getenv("DRB_LOSS_DEBUG")) : 0;
   p.debug = dbg_env;
   const bool per_user = label_count == nullptr;

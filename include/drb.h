@@ -144,7 +144,7 @@ typedef struct {
   void* workspace;             /* device, >= drb_cdae_workspace_bytes(...) */
   int64_t workspace_bytes;
   int32_t max_batch;
-  int32_t gemm_path;           /* DRB_GEMM_AUTO (tcgen05 3xTF32 when hidden < 256), DRB_GEMM_FFMA, DRB_GEMM_TCGEN05 */
+  int32_t gemm_path;           /* DRB_GEMM_AUTO (tcgen05 3xTF32 when hidden <= 256), DRB_GEMM_FFMA, DRB_GEMM_TCGEN05 */
 } drb_cdae_desc;
 
 typedef struct {
@@ -320,6 +320,16 @@ int drb_eval_candidates(int64_t n_users, const int64_t* test_indptr, const int64
                         double n_neg, int32_t n_neg_is_frac, int32_t generate_negative_pairs, int64_t seed,
                         int32_t n_threads, int64_t cand_capacity, int64_t* cand_off, int64_t* cand, int64_t* pos_off,
                         int64_t* pos, uint8_t* skipped);
+
+/* Leave-k-out split for every user at once (replaces DRecPy/Evaluation/Splits/leave_k_out.py:58-135: one
+ * interaction_dataset.select('user == ...') plus rng.sample per user on a thread pool).  Rows are given grouped by
+ * user in order of first appearance, each group in DataFrame order: group idx spans user_indptr[idx]..[idx+1].  User
+ * idx draws from random.Random(seed + idx + 1) (the reference increments the seed before creating the generator,
+ * leave_k_out.py:68-69).  k_fixed rows per user go to the test set (is_ratio: int(len * k_ratio), :98-99) when the
+ * user has more than k rows (:119); users with fewer than min_user_interactions rows are removed (:115-117).
+ * flags[pos] = 0 train, 1 test, 2 removed; the caller zero-fills flags.  The last_timestamps variant stays in Python. */
+int drb_leave_k_out(int64_t n_users, const int64_t* user_indptr, int64_t k_fixed, double k_ratio, int32_t is_ratio,
+                    int64_t min_user_interactions, int64_t seed, int32_t n_threads, uint8_t* flags);
 
 #ifdef __cplusplus
 }

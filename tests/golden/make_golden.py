@@ -9,6 +9,9 @@ none of the code exercised here touches TensorFlow.  Outputs (committed):
   ranking.json         candidate lists handed to model.rank and the final metric dicts of the live
                        ranking_evaluation (DRecPy/Evaluation/Processes/ranking_evaluation.py:19-246) on the
                        reference's own fixture (tests/Evaluation/Processes/test_ranking_evaluation.py:12-19)
+  splits.json          train / test row ids of the live leave_k_out (DRecPy/Evaluation/Splits/leave_k_out.py:14-135):
+                       fixed k, ratio k, min_user_interactions, k larger than some users' histories,
+                       last_timestamps
   ref_kat_check.json   record that the oracle protocol driven by the live UserKNN reproduces the reference's
                        own expected metric dicts (test_ranking_evaluation.py:30-60)
 """
@@ -182,9 +185,44 @@ def ranking_golden():
     assert all(c['equal'] for c in check.values()), 'oracle protocol does not reproduce the reference KATs'
 
 
+def splits_golden():
+    rng = np.random.default_rng(21)
+    n = 4000
+    user = rng.integers(0, 120, n) * 7 + 3          # raw ids out of order, not contiguous
+    item = rng.integers(0, 300, n)
+    key = np.unique(user * 1000 + item)
+    rng.shuffle(key)
+    user, item = key // 1000, key % 1000
+    val = rng.integers(1, 6, len(key))
+    ts = rng.integers(0, 50, len(key))               # many ties: (timestamp, rid) ordering matters
+    df = pd.DataFrame({'user': user, 'item': item, 'interaction': val, 'timestamp': ts})
+    cases = {
+        'k3_seed10': dict(k=3, seed=10),
+        'k1_seed0': dict(k=1, seed=0),
+        'ratio_0.2_seed5': dict(k=0.2, seed=5),
+        'k30_min25_seed7': dict(k=30, min_user_interactions=25, seed=7),     # k above some users' row counts
+        'ratio_0.5_min20_seed1': dict(k=0.5, min_user_interactions=20, seed=1),
+        'k2_last_timestamps': dict(k=2, last_timestamps=True, seed=3),
+        'ratio_0.3_last_timestamps_min28': dict(k=0.3, last_timestamps=True, min_user_interactions=28, seed=3),
+    }
+    out = {'rows': df.values.tolist(), 'cases': {}}
+    for name, kw in cases.items():
+        ds = InteractionDataset.read_df(df, verbose=False)
+        train, test = leave_k_out(ds, verbose=False, **kw)
+        out['cases'][name] = {'kwargs': kw, 'train_rid': sorted(train.values_list('rid', to_list=True)),
+                              'test_rid': sorted(test.values_list('rid', to_list=True))}
+        print(name, len(train), len(test))
+    with open(os.path.join(HERE, 'splits.json'), 'w') as f:
+        json.dump(out, f)
+
+
 if __name__ == '__main__':
+    if sys.argv[1:] == ['splits']:
+        splits_golden()
+        sys.exit(0)
     sampler_golden('small_zero_rows', 300, 500, 6000, data_seed=10, seeds=[10, 23, 0], n=1500, zero_frac=0.15)
     sampler_golden('small_dups', 120, 90, 2500, data_seed=11, seeds=[10], n=600, dup=200)
     sampler_golden('small_float', 200, 400, 8000, data_seed=12, seeds=[10, 7], n=800, float_vals=True)
     sampler_golden('thr3', 150, 250, 5000, data_seed=13, seeds=[10], n=600, thr=3)
     ranking_golden()
+    splits_golden()

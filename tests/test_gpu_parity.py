@@ -217,6 +217,31 @@ def test_dmf_steps_and_scores(uf, itf, l2n, nce):
         assert rel_err(b.cpu().numpy(), bo) < 2e-3
 
 
+def test_dmf_graph_replay_equals_direct_launches(monkeypatch):
+    """drb_dmf_step replays an instantiated CUDA graph (the step is launch bound); DRB_GRAPH=0 launches every kernel
+    directly.  Same kernels in the same order: losses and weights agree to the last bits (the scatter kernels add
+    with atomics, so not bit for bit) and the launch counts match."""
+    U, I, B = 300, 500, 64
+    ds = _dataset(U, I, 15000, seed=8)
+    w = _dmf_weights(U, I, [64, 32], [64, 32])
+    runs = []
+    for graph in ('1', '0'):
+        monkeypatch.setenv('DRB_GRAPH', graph)
+        m = drb.DMF(user_factors=[64, 32], item_factors=[64, 32], seed=10, verbose=False)
+        m.fit(ds, epochs=0, batch_size=B, learning_rate=1e-3, neg_ratio=5, reg_rate=1e-4, init_weights=w)
+        n0 = m.launch_count()
+        losses = []
+        for s in range(1, 13):
+            m._step = s
+            losses.append(m._train_step(B if s % 5 else B // 2, 1e-4, want_loss=True))   # a second batch size: second graph
+        runs.append((losses, m.launch_count() - n0, [k.cpu().numpy() for k, _ in m.tower_weights('user_nn')]))
+    assert np.allclose(runs[0][0], runs[1][0], rtol=2e-6, atol=0)
+    # graph mode adds one k_set_scalars launch per step
+    assert runs[0][1] == runs[1][1] + 12
+    for a, b in zip(runs[0][2], runs[1][2]):
+        assert rel_err(a, b) < 1e-5
+
+
 def test_rank_order_ties_and_novelty():
     """(score desc, iid desc) == heapq.nlargest on (score, iid) tuples (cdae.py:102-103), duplicates collapsed,
     training items dropped when novelty."""

@@ -212,3 +212,45 @@ def test_vectorised_evaluation_equals_per_user_protocol(golden_dir):
         fast = drb.ranking_evaluation(model, test, verbose=False, **kw)
         slow = drb.ranking_evaluation(model, test, verbose=False, force_python=True, **kw)
         assert fast == slow, (kw, fast, slow)
+
+
+# ------------------------------------------------------------------------------------------------ leave_k_out
+def test_leave_k_out_matches_live_reference_goldens():
+    """drecpy_b200.leave_k_out (native per-user Random(seed + idx + 1).sample replay) against the row ids the live
+    reference produced (tests/golden/splits.json <- DRecPy/Evaluation/Splits/leave_k_out.py:14-135): fixed and ratio
+    k, min_user_interactions, k above some users' history length, last_timestamps."""
+    import json
+    g = json.load(open(os.path.join(os.path.dirname(__file__), 'golden', 'splits.json')))
+    rows = np.array(g['rows'], dtype=np.int64)
+    ds = drb.InteractionData(rows[:, 0], rows[:, 1], rows[:, 2])
+    key = {(int(u), int(i)): r for r, (u, i) in enumerate(zip(rows[:, 0], rows[:, 1]))}    # (user, item) pairs are unique
+    for name, case in g['cases'].items():
+        kw = dict(case['kwargs'])
+        train, test = drb.leave_k_out(ds, timestamps=rows[:, 3], verbose=False, **kw)
+        tr = [key[(int(u), int(i))] for u, i in zip(train.user, train.item)]
+        te = [key[(int(u), int(i))] for u, i in zip(test.user, test.item)]
+        assert tr == sorted(tr) and te == sorted(te), name              # input row order is preserved
+        assert tr == case['train_rid'], name
+        assert te == case['test_rid'], name
+
+
+def test_leave_k_out_reference_fixture_and_errors():
+    """The reference's own evaluation fixture (tests/Evaluation/Processes/test_ranking_evaluation.py:12-19): the split
+    stored in ranking.json came from the live leave_k_out(k=5, seed=10)."""
+    import json, random
+    g = json.load(open(os.path.join(os.path.dirname(__file__), 'golden', 'ranking.json')))
+    rng = random.Random(0)
+    rows = np.array([[u, i, rng.randint(-1, 5)] for u in range(50) for i in range(200) if rng.randint(0, 4) == 0])
+    train, test = drb.leave_k_out(drb.InteractionData(rows[:, 0], rows[:, 1], rows[:, 2]), k=5, seed=10, verbose=False)
+    assert np.stack([train.user, train.item, train.interaction], 1).tolist() == g['train_rows']
+    assert np.stack([test.user, test.item, test.interaction], 1).tolist() == g['test_rows']
+    # multi-threaded path (>= 1024 users) equals the single-threaded one: users are independent
+    rs = np.random.default_rng(0)
+    u = np.repeat(np.arange(3000), 12); i = rs.integers(0, 10**6, len(u)); v = np.ones(len(u), np.int64)
+    a = drb.leave_k_out(drb.InteractionData(u, i, v), k=2, seed=4, max_concurrent_threads=8, verbose=False)
+    b = drb.leave_k_out(drb.InteractionData(u, i, v), k=2, seed=4, max_concurrent_threads=1, verbose=False)
+    assert np.array_equal(a[1].item, b[1].item) and len(a[1]) == 6000 and len(a[0]) == 30000
+    with pytest.raises(AssertionError):
+        drb.leave_k_out(drb.InteractionData(u, i, v), k=0)
+    with pytest.raises(Exception, match='should be in the'):
+        drb.leave_k_out(drb.InteractionData(u, i, v), k=1.5)
