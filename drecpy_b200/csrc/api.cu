@@ -157,7 +157,7 @@ struct CdaeWs {
   float *h_hi, *h_lo, *hT_hi, *hT_lo, *w2t_hi, *w2t_lo, *wT_hi, *wT_lo, *dzt_hi, *dzt_lo;   // dzt_*: tile-major dz
   int64_t hT_floats, wT_floats;
   uint32_t* label_bits;
-  int32_t *uids, *keep_off, *aux_i32;
+  int32_t *uids, *keep_off, *aux_i32, *chunk_off;
   uint8_t* keep;
   int64_t bytes;
 };
@@ -207,6 +207,7 @@ static CdaeWs cdae_carve(void* base, const drb_cdae_layout_t& L, int n_items, in
   w.uids = c.take<int32_t>(B);
   w.keep_off = c.take<int32_t>(B + 1);
   w.aux_i32 = c.take<int32_t>(3 * B + 64);
+  w.chunk_off = c.take<int32_t>(B + 64);
   w.keep = c.take<uint8_t>(cdae_keep_cap(n_items, max_batch));
   if (umma) {
     const int64_t n2 = cdae_n2(hidden), bp = drb_round_up(max_batch, 4);
@@ -313,7 +314,8 @@ int drb_cdae_create(drb_ctx* ctx, const drb_cdae_desc* desc, drb_cdae** out) {
 int drb_cdae_destroy(drb_cdae* m) { delete m; return DRB_OK; }
 
 static int cdae_hidden_into(drb_cdae* m, const int32_t* uids, int n, const int32_t* keep_off, const uint8_t* keep,
-                            float scale, float* h, int act = DRB_ACT_SIGMOID, const int32_t* bias_rows = nullptr) {
+                            float scale, float* h, int act = DRB_ACT_SIGMOID, const int32_t* bias_rows = nullptr,
+                            const int32_t* chunk_off = nullptr) {
   GatherArgs g{};
   g.indptr = m->d.csr_indptr; g.indices = m->d.csr_indices; g.values = nullptr;
   g.rows = uids; g.keep_off = keep_off; g.keep = keep;
@@ -322,6 +324,7 @@ static int cdae_hidden_into(drb_cdae* m, const int32_t* uids, int n, const int32
   g.row_scale = nullptr; g.scale = scale; g.act = act; g.width = m->d.hidden;
   g.bias_rows = bias_rows;
   g.out = h;
+  g.chunk_off = chunk_off;
   return launch_gather(m->ctx, g, n);
 }
 
@@ -420,8 +423,11 @@ int drb_cdae_step_phases(drb_cdae* m, const int32_t* uids, const int32_t* keep_o
   // 2. K1: h = sigmoid(s * sum_kept W[i] + V[u] + b)   (needs no labels: overlaps the label all-reduce when DP).
   //    Item-sharded: the partial pre-activation over the local items (+ V_u + b on the user's owner rank); the caller
   //    all-reduces drb_cdae_h_buffer() and GRADS_A2 applies the sigmoid.
+  //    Balanced over 256-entry pieces of the users' rows (training only; k_chunk_scan builds the piece map that the
+  //    scatter of this step reuses).
+  if ((r = launch_chunk_scan(ctx, m->d.csr_indptr, uids, batch, w.chunk_off))) return r;
   if ((r = cdae_hidden_into(m, uids, batch, keep_off, keep_used, s, w.h, sharded ? DRB_ACT_NONE : DRB_ACT_SIGMOID,
-                            sharded ? a->v_rows : nullptr)))
+                            sharded ? a->v_rows : nullptr, w.chunk_off)))
     return r;
   }
   if ((phases & DRB_PHASE_GRADS_A2) || ((phases & DRB_PHASE_GRADS_A) && !sharded)) {
@@ -511,6 +517,7 @@ int drb_cdae_step_phases(drb_cdae* m, const int32_t* uids, const int32_t* keep_o
   sc.d = w.dz1; sc.ld = ld; sc.gtable = G + L.off_w;
   sc.growbias = a->skip_user_grad ? nullptr : G + L.off_v;   // data parallel: user rows are exchanged instead
   sc.bias_rows = sharded ? a->v_rows : nullptr;              // item-sharded: only owned users' rows of V
+  sc.chunk_off = w.chunk_off;                                // piece map of this batch (built in GRADS_A)
   if ((r = launch_scatter(ctx, sc, batch))) return r;
   }  // GRADS_C / GRADS_C2 (data parallel: the caller exchanges dz1 rows and all-reduces dW, db here)
 

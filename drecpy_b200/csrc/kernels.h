@@ -19,8 +19,13 @@ struct GatherArgs {
   const float* row_scale;                                               // may be NULL; per CSR row
   float scale; int act; int width;                                      // columns >= width are forced to 0
   float* out;                                                           // [n, ld]
+  const int32_t* chunk_off;                                             // may be NULL; [n + 1] from launch_chunk_scan:
+                                                                        // balanced form (pieces of 256 CSR entries,
+                                                                        // atomics into out, then a finishing pass)
 };
 int launch_gather(drb_ctx* ctx, const GatherArgs& a, int n);
+// chunk_off[b] = number of 256-entry pieces of the CSR rows rows[0..b), chunk_off[n] = total
+int launch_chunk_scan(drb_ctx* ctx, const int64_t* indptr, const int32_t* rows, int n, int32_t* chunk_off);
 
 struct ScatterArgs {
   const int64_t* indptr; const int32_t* indices; const float* values;
@@ -31,6 +36,7 @@ struct ScatterArgs {
   float* gtable;                      // [*, ld] += w * d[b]   (vector atomics)
   float* growbias;                    // may be NULL; [*, ld] += d[b] at rows[b]
   const int32_t* bias_rows;           // may be NULL; else the growbias row per batch row, -1 = skip (item-sharded)
+  const int32_t* chunk_off;           // may be NULL; balanced form, see GatherArgs
 };
 int launch_scatter(drb_ctx* ctx, const ScatterArgs& a, int n);
 

@@ -28,6 +28,58 @@ __device__ __forceinline__ float apply_act(float x, int act) {
   return x;
 }
 
+// Inner loop of the gathers: the warp walks `deg` CSR entries starting at `lo`, 32 (index, weight) pairs at a time,
+// broadcast by shuffle.  The table-row loads of kGatherRows entries are issued back to back (predicated, no branch)
+// before the first FMA consumes one: with one row per iteration the FMAs of row t stalled in front of the loads of
+// row t+1 and every warp had a single row in flight (SASS), which left the kernel latency bound at ~5 TB/s from L2.
+constexpr int kGatherRows = 4;
+template <int LPR, int NV>
+__device__ __forceinline__ void gather_accumulate(const GatherArgs& a, int64_t lo, int deg, const uint8_t* keep, int warp,
+                                                  int lane, float4 (&acc)[NV]) {
+  constexpr int G = 32 / LPR;
+  const int sub = lane / LPR, c = lane % LPR;
+  const int ld4 = a.ld >> 2;
+  for (int base = warp * 32; base < deg; base += kWarps * 32) {
+    const int j = base + lane;
+    int my_idx = 0;
+    float my_w = 0.f;
+    if (j < deg) {
+      my_idx = a.indices[lo + j];
+      my_w = a.values ? a.values[lo + j] : 1.0f;
+      if (keep && keep[j] == 0) my_w = 0.f;
+    }
+    const int cnt = min(32, deg - base);
+    for (int t = 0; t < cnt; t += G * kGatherRows) {
+      float4 x[kGatherRows][NV];
+      float w[kGatherRows];
+#pragma unroll
+      for (int u = 0; u < kGatherRows; u++) {
+        const int src = t + u * G + sub;
+        const int idx = __shfl_sync(0xffffffffu, my_idx, src & 31);
+        const float ww = __shfl_sync(0xffffffffu, my_w, src & 31);
+        const bool ok = src < cnt && ww != 0.f;       // dropped (corrupted) entries are never loaded
+        w[u] = ok ? ww : 0.f;
+        const float* rp = a.table + (int64_t)idx * a.ld;
+#pragma unroll
+        for (int v = 0; v < NV; v++) {
+          const int c4 = c + v * LPR;
+          x[u][v] = (ok && c4 < ld4) ? ldg4(rp + c4 * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < kGatherRows; u++) {
+#pragma unroll
+        for (int v = 0; v < NV; v++) {
+          acc[v].x = fmaf(w[u], x[u][v].x, acc[v].x);
+          acc[v].y = fmaf(w[u], x[u][v].y, acc[v].y);
+          acc[v].z = fmaf(w[u], x[u][v].z, acc[v].z);
+          acc[v].w = fmaf(w[u], x[u][v].w, acc[v].w);
+        }
+      }
+    }
+  }
+}
+
 template <int LPR, int NV>
 __global__ void __launch_bounds__(kGatherThreads) k_gather(GatherArgs a) {
   constexpr int G = 32 / LPR;  // table rows streamed concurrently by one warp
@@ -45,37 +97,7 @@ __global__ void __launch_bounds__(kGatherThreads) k_gather(GatherArgs a) {
 #pragma unroll
   for (int v = 0; v < NV; v++) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
 
-  for (int base = warp * 32; base < deg; base += kWarps * 32) {
-    const int j = base + lane;
-    int my_idx = 0;
-    float my_w = 0.f;
-    if (j < deg) {
-      my_idx = a.indices[lo + j];
-      my_w = a.values ? a.values[lo + j] : 1.0f;
-      if (keep && keep[j] == 0) my_w = 0.f;
-    }
-    const int cnt = min(32, deg - base);
-#pragma unroll 4
-    for (int t = 0; t < cnt; t += G) {
-      const int src = t + sub;
-      const int idx = __shfl_sync(0xffffffffu, my_idx, src & 31);
-      const float w = __shfl_sync(0xffffffffu, my_w, src & 31);
-      if (src < cnt && w != 0.f) {
-        const float* rp = a.table + (int64_t)idx * a.ld;
-#pragma unroll
-        for (int v = 0; v < NV; v++) {
-          const int c4 = c + v * LPR;
-          if (c4 < ld4) {
-            const float4 x = ldg4(rp + c4 * 4);
-            acc[v].x = fmaf(w, x.x, acc[v].x);
-            acc[v].y = fmaf(w, x.y, acc[v].y);
-            acc[v].z = fmaf(w, x.z, acc[v].z);
-            acc[v].w = fmaf(w, x.w, acc[v].w);
-          }
-        }
-      }
-    }
-  }
+  gather_accumulate<LPR, NV>(a, lo, deg, keep, warp, lane, acc);
 #pragma unroll
   for (int v = 0; v < NV; v++) {
     const int c4 = c + v * LPR;
@@ -281,6 +303,192 @@ __global__ void __launch_bounds__(256) k_reduce_partials(const float* __restrict
   }
 }
 
+// ------------------------------------------------------------------------------------------ chunked (balanced) forms
+// One CTA per sampled row leaves the kernel waiting for its longest row: with log-normal user activity the heaviest
+// row of a 4096-user batch has ~35x the median degree, and ncu showed the SMs busy 46 % of the gather's duration.
+// The chunked forms cut every CSR row into pieces of kChunk entries and let a persistent grid walk the pieces:
+//   k_chunk_scan     chunk_off[b] = sum_{b' < b} ceil(deg(b') / kChunk)           (one CTA, running carry)
+//   k_gather_chunks  partial sum of one piece, added to acc[b] with vector atomics (acc zeroed by the caller)
+//   k_gather_finish  out = act(acc * scale + rowbias + bias)                      (in place)
+//   k_scatter_chunks the scatter of one piece (atomics anyway)
+// The piece -> row map is a binary search in a shared-memory copy of chunk_off.  Used by the CDAE training step;
+// scoring and the DMF towers keep the one-CTA-per-row kernels (deterministic summation order).
+constexpr int kChunk = 256;
+constexpr int kMaxChunkRows = 16384;   // chunk_off is staged in shared memory: 64 KB at most
+
+__global__ void __launch_bounds__(1024) k_chunk_scan(const int64_t* __restrict__ indptr, const int32_t* __restrict__ rows,
+                                                     int n, int32_t* __restrict__ chunk_off) {
+  __shared__ int wsum[32];
+  __shared__ int carry_s;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) carry_s = 0;
+  __syncthreads();
+  for (int base = 0; base < n; base += 1024) {
+    const int b = base + threadIdx.x;
+    int v = 0;
+    if (b < n) {
+      const int row = rows[b];
+      v = max(1, (int)((indptr[row + 1] - indptr[row] + kChunk - 1) / kChunk));   // >= 1: an empty row still owns dV[u]
+    }
+    int x = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int y = __shfl_up_sync(0xffffffffu, x, o);
+      if (lane >= o) x += y;
+    }
+    if (lane == 31) wsum[warp] = x;
+    __syncthreads();
+    if (warp == 0) {
+      int w = wsum[lane];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int y = __shfl_up_sync(0xffffffffu, w, o);
+        if (lane >= o) w += y;
+      }
+      wsum[lane] = w;
+    }
+    __syncthreads();
+    const int carry = carry_s;
+    const int incl = carry + x + (warp ? wsum[warp - 1] : 0);
+    if (b < n) chunk_off[b] = incl - v;
+    __syncthreads();
+    if (threadIdx.x == 1023) carry_s = incl;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) chunk_off[n] = carry_s;
+}
+
+// largest b with coff[b] <= c  (coff non-decreasing, coff[0] = 0, c < coff[n])
+__device__ __forceinline__ int chunk_row(const int32_t* coff, int n, int c) {
+  int lo = 0, hi = n;
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (coff[mid] <= c) lo = mid; else hi = mid;
+  }
+  return lo;
+}
+
+template <int LPR, int NV>
+__global__ void __launch_bounds__(kGatherThreads) k_gather_chunks(GatherArgs a, const int32_t* __restrict__ chunk_off,
+                                                                  int n) {
+  constexpr int G = 32 / LPR;
+  extern __shared__ float4 red[];  // [kWarps * G][ld4], then coff[n + 1]
+  const int ld4 = a.ld >> 2;
+  int32_t* coff = reinterpret_cast<int32_t*>(red + kWarps * G * ld4);
+  for (int i = threadIdx.x; i <= n; i += kGatherThreads) coff[i] = chunk_off[i];
+  __syncthreads();
+  const int total = coff[n];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int sub = lane / LPR, c = lane % LPR;
+  for (int ch = blockIdx.x; ch < total; ch += gridDim.x) {
+    const int b = chunk_row(coff, n, ch);
+    const int first = (ch - coff[b]) * kChunk;
+    const int row = a.rows[b];
+    const int64_t lo = a.indptr[row] + first;
+    const int deg = (int)min((int64_t)kChunk, (int64_t)(a.indptr[row + 1] - lo));
+    const uint8_t* keep = a.keep ? a.keep + a.keep_off[b] + first : nullptr;
+    float4 acc[NV];
+#pragma unroll
+    for (int v = 0; v < NV; v++) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+    gather_accumulate<LPR, NV>(a, lo, deg, keep, warp, lane, acc);
+#pragma unroll
+    for (int v = 0; v < NV; v++) {
+      const int c4 = c + v * LPR;
+      if (c4 < ld4) red[(warp * G + sub) * ld4 + c4] = acc[v];
+    }
+    __syncthreads();
+    for (int c4 = threadIdx.x; c4 < ld4; c4 += kGatherThreads) {
+      float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int p = 0; p < kWarps * G; p++) {
+        const float4 x = red[p * ld4 + c4];
+        s.x += x.x; s.y += x.y; s.z += x.z; s.w += x.w;
+      }
+      atomicAdd(reinterpret_cast<float4*>(a.out + (int64_t)b * a.ld) + c4, s);
+    }
+    __syncthreads();
+  }
+}
+
+__global__ void __launch_bounds__(256) k_gather_finish(GatherArgs a, int n) {
+  const int64_t total = (int64_t)n * a.ld;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int b = (int)(i / a.ld), col = (int)(i % a.ld);
+    const int row = a.rows[b];
+    float rs = a.scale;
+    if (a.row_scale) rs *= a.row_scale[row];
+    float z = a.out[i] * rs;
+    const int brow = a.bias_rows ? a.bias_rows[b] : row;
+    if (brow >= 0) {
+      if (a.rowbias) z += a.rowbias[(int64_t)brow * a.ld + col];
+      if (a.bias) z += a.bias[col];
+    }
+    a.out[i] = (col < a.width) ? apply_act(z, a.act) : 0.f;
+  }
+}
+
+template <int LPR, int NV>
+__global__ void __launch_bounds__(kGatherThreads) k_scatter_chunks(ScatterArgs a, const int32_t* __restrict__ chunk_off,
+                                                                   int n) {
+  constexpr int G = 32 / LPR;
+  extern __shared__ int32_t coff_s[];  // [n + 1]
+  for (int i = threadIdx.x; i <= n; i += kGatherThreads) coff_s[i] = chunk_off[i];
+  __syncthreads();
+  const int total = coff_s[n];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int sub = lane / LPR, c = lane % LPR;
+  const int ld4 = a.ld >> 2;
+  for (int ch = blockIdx.x; ch < total; ch += gridDim.x) {
+    const int b = chunk_row(coff_s, n, ch);
+    const int piece = ch - coff_s[b];
+    const int first = piece * kChunk;
+    const int row = a.rows[b];
+    const int64_t lo = a.indptr[row] + first;
+    const int deg = (int)min((int64_t)kChunk, (int64_t)(a.indptr[row + 1] - lo));
+    const uint8_t* keep = a.keep ? a.keep + a.keep_off[b] + first : nullptr;
+    float rs = a.scale;
+    if (a.row_scale) rs *= a.row_scale[row];
+    float4 d[NV];
+#pragma unroll
+    for (int v = 0; v < NV; v++) {
+      const int c4 = c + v * LPR;
+      d[v] = (c4 < ld4) ? ldg4(a.d + (int64_t)b * a.ld + c4 * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    const int brow = a.bias_rows ? a.bias_rows[b] : row;
+    if (a.growbias && brow >= 0 && piece == 0 && warp == 0 && sub == 0) {
+#pragma unroll
+      for (int v = 0; v < NV; v++) {
+        const int c4 = c + v * LPR;
+        if (c4 < ld4) atomicAdd(reinterpret_cast<float4*>(a.growbias + (int64_t)brow * a.ld) + c4, d[v]);
+      }
+    }
+    for (int base = warp * 32; base < deg; base += kWarps * 32) {
+      const int j = base + lane;
+      int my_idx = 0;
+      float my_w = 0.f;
+      if (j < deg) {
+        my_idx = a.indices[lo + j];
+        my_w = (a.values ? a.values[lo + j] : 1.0f) * rs;
+        if (keep && keep[j] == 0) my_w = 0.f;
+      }
+      const int cnt = min(32, deg - base);
+      for (int t = 0; t < cnt; t += G) {
+        const int src = t + sub;
+        const int idx = __shfl_sync(0xffffffffu, my_idx, src & 31);
+        const float w = __shfl_sync(0xffffffffu, my_w, src & 31);
+        if (src < cnt && w != 0.f) {
+          float4* gp = reinterpret_cast<float4*>(a.gtable + (int64_t)idx * a.ld);
+#pragma unroll
+          for (int v = 0; v < NV; v++) {
+            const int c4 = c + v * LPR;
+            if (c4 < ld4) atomicAdd(gp + c4, make_float4(w * d[v].x, w * d[v].y, w * d[v].z, w * d[v].w));
+          }
+        }
+      }
+    }
+  }
+}
+
 template <template <int, int> class Launcher, typename Args>
 int dispatch_lpr(drb_ctx* ctx, const Args& a, int n, int ld, const char* name) {
   const int ld4 = ld >> 2;
@@ -316,15 +524,67 @@ struct ScatterLauncher {
 
 }  // namespace
 
+template <int LPR, int NV>
+struct GatherChunksLauncher {
+  static int run(drb_ctx* ctx, const GatherArgs& a, int n, const char* name) {
+    const size_t smem = (size_t)kWarps * (32 / LPR) * a.ld * sizeof(float) + (size_t)(n + 1) * sizeof(int32_t);
+    auto kern = k_gather_chunks<LPR, NV>;
+    if (smem > 48 * 1024) {
+      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return drb_fail(DRB_E_CUDA, "%s: %zu bytes of shared memory: %s", name, smem, cudaGetErrorString(e));
+    }
+    drb_prof_scope prof_(ctx, "k_gather");
+    kern<<<ctx->sm_count * 8, kGatherThreads, smem, ctx->stream>>>(a, a.chunk_off, n);
+    DRB_LAUNCH_CHECK(ctx, name);
+    return DRB_OK;
+  }
+};
+template <int LPR, int NV>
+struct ScatterChunksLauncher {
+  static int run(drb_ctx* ctx, const ScatterArgs& a, int n, const char* name) {
+    const size_t smem = (size_t)(n + 1) * sizeof(int32_t);
+    auto kern = k_scatter_chunks<LPR, NV>;
+    if (smem > 48 * 1024) {
+      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return drb_fail(DRB_E_CUDA, "%s: %zu bytes of shared memory: %s", name, smem, cudaGetErrorString(e));
+    }
+    drb_prof_scope prof_(ctx, "k_scatter");
+    kern<<<ctx->sm_count * 8, kGatherThreads, smem, ctx->stream>>>(a, a.chunk_off, n);
+    DRB_LAUNCH_CHECK(ctx, name);
+    return DRB_OK;
+  }
+};
+
+int launch_chunk_scan(drb_ctx* ctx, const int64_t* indptr, const int32_t* rows, int n, int32_t* chunk_off) {
+  if (n <= 0) return DRB_OK;
+  drb_prof_scope prof_(ctx, "k_chunk_scan");
+  k_chunk_scan<<<1, 1024, 0, ctx->stream>>>(indptr, rows, n, chunk_off);
+  DRB_LAUNCH_CHECK(ctx, "k_chunk_scan");
+  return DRB_OK;
+}
+
 int launch_gather(drb_ctx* ctx, const GatherArgs& a, int n) {
   if (n <= 0) return DRB_OK;
   if (a.ld % 4) return drb_fail(DRB_E_INVALID, "gather: ld must be a multiple of 4");
+  if (a.chunk_off && n <= kMaxChunkRows) {   // balanced form: zero, accumulate pieces, finish
+    cudaError_t e = cudaMemsetAsync(a.out, 0, (size_t)n * a.ld * sizeof(float), ctx->stream);
+    if (e != cudaSuccess) { ctx->sticky = (int)e; return drb_fail(DRB_E_CUDA, "gather: memset failed: %s", cudaGetErrorString(e)); }
+    int r = dispatch_lpr<GatherChunksLauncher>(ctx, a, n, a.ld, "k_gather_chunks");
+    if (r) return r;
+    const int64_t total = (int64_t)n * a.ld;
+    const int blocks = (int)std::min<int64_t>((total + 255) / 256, (int64_t)ctx->sm_count * 8);
+    drb_prof_scope prof_(ctx, "k_gather_finish");
+    k_gather_finish<<<blocks, 256, 0, ctx->stream>>>(a, n);
+    DRB_LAUNCH_CHECK(ctx, "k_gather_finish");
+    return DRB_OK;
+  }
   return dispatch_lpr<GatherLauncher>(ctx, a, n, a.ld, "k_gather");
 }
 
 int launch_scatter(drb_ctx* ctx, const ScatterArgs& a, int n) {
   if (n <= 0) return DRB_OK;
   if (a.ld % 4) return drb_fail(DRB_E_INVALID, "scatter: ld must be a multiple of 4");
+  if (a.chunk_off && n <= kMaxChunkRows) return dispatch_lpr<ScatterChunksLauncher>(ctx, a, n, a.ld, "k_scatter_chunks");
   return dispatch_lpr<ScatterLauncher>(ctx, a, n, a.ld, "k_scatter");
 }
 

@@ -173,6 +173,27 @@ def test_cdae_duplicate_users_and_ragged_rows():
     assert rel_err(m.W.cpu().numpy(), o.W) < 1e-4
 
 
+@pytest.mark.parametrize('mask', ['mt19937', 'philox'])
+def test_cdae_heavy_rows_span_several_pieces(mask):
+    """Users with 300..1400 interactions: the balanced gather / scatter of the training step cut their CSR rows into
+    256-entry pieces (sparse.cu: k_gather_chunks / k_scatter_chunks); the corruption mask bytes of a piece start at
+    keep_off[b] + 256 * piece.  Loss and weights against the oracle, every step."""
+    rng = np.random.default_rng(5)
+    U, I = 40, 1500
+    deg = rng.integers(300, 1400, U)
+    deg[:3] = [1, 256, 257]                               # piece boundaries
+    u = np.repeat(np.arange(U), deg)
+    i = np.concatenate([rng.choice(I, d, replace=False) for d in deg])
+    perm = rng.permutation(len(u))
+    ds = drb.InteractionData(u[perm] + 1, i[perm] + 1, rng.integers(1, 6, len(u)))
+    ds.assign_internal_ids()
+    m, o, l, lo = _run_cdae_steps(ds, 24, 32, 6, {}, {}, mask=mask)
+    assert np.max(np.abs(l - lo) / np.abs(lo)) < 1e-4, (l, lo)
+    for name in ('W', 'V', 'b', 'b_'):
+        assert rel_err(getattr(m, name).cpu().numpy(), getattr(o, name)) < 5e-4, name
+    assert rel_err(m.W_.cpu().numpy(), o.W_) < 5e-4
+
+
 def _dmf_weights(U, I, uf, itf, seed=2):
     rng = np.random.default_rng(seed)
 
