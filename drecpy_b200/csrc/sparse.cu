@@ -323,14 +323,19 @@ __global__ void __launch_bounds__(1024) k_chunk_scan(const int64_t* __restrict__
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   if (threadIdx.x == 0) carry_s = 0;
   __syncthreads();
-  for (int base = 0; base < n; base += 1024) {
-    const int b = base + threadIdx.x;
-    int v = 0;
-    if (b < n) {
-      const int row = rows[b];
-      v = max(1, (int)((indptr[row + 1] - indptr[row] + kChunk - 1) / kChunk));   // >= 1: an empty row still owns dV[u]
+  for (int base = 0; base < n; base += 4096) {     // four consecutive rows per thread: their loads overlap
+    const int b0 = base + 4 * threadIdx.x;
+    int v[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      v[k] = 0;
+      if (b0 + k < n) {
+        const int row = rows[b0 + k];
+        v[k] = max(1, (int)((indptr[row + 1] - indptr[row] + kChunk - 1) / kChunk));   // >= 1: an empty row still owns dV[u]
+      }
     }
-    int x = v;
+    const int mine = v[0] + v[1] + v[2] + v[3];
+    int x = mine;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
       const int y = __shfl_up_sync(0xffffffffu, x, o);
@@ -348,9 +353,13 @@ __global__ void __launch_bounds__(1024) k_chunk_scan(const int64_t* __restrict__
       wsum[lane] = w;
     }
     __syncthreads();
-    const int carry = carry_s;
-    const int incl = carry + x + (warp ? wsum[warp - 1] : 0);
-    if (b < n) chunk_off[b] = incl - v;
+    const int incl = carry_s + x + (warp ? wsum[warp - 1] : 0);
+    int run = incl - mine;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      if (b0 + k < n) chunk_off[b0 + k] = run;
+      run += v[k];
+    }
     __syncthreads();
     if (threadIdx.x == 1023) carry_s = incl;
     __syncthreads();

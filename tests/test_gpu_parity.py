@@ -173,6 +173,15 @@ def test_cdae_duplicate_users_and_ragged_rows():
     assert rel_err(m.W.cpu().numpy(), o.W) < 1e-4
 
 
+def test_cdae_batch_larger_than_one_scan_tile():
+    """B = 4500 sampled users: the piece-map scan (k_chunk_scan) walks more than one 4096-row tile and carries the
+    running total across; loss and weights against the oracle."""
+    ds = _dataset(211, 389, 9000, seed=4)
+    m, o, l, lo = _run_cdae_steps(ds, 16, 4500, 2, {}, {}, mask='philox')
+    assert np.max(np.abs(l - lo) / np.abs(lo)) < 1e-4, (l, lo)
+    assert rel_err(m.W.cpu().numpy(), o.W) < 5e-4 and rel_err(m.V.cpu().numpy(), o.V) < 5e-4
+
+
 @pytest.mark.parametrize('mask', ['mt19937', 'philox'])
 def test_cdae_heavy_rows_span_several_pieces(mask):
     """Users with 300..1400 interactions: the balanced gather / scatter of the training step cut their CSR rows into
