@@ -254,3 +254,31 @@ def test_leave_k_out_reference_fixture_and_errors():
         drb.leave_k_out(drb.InteractionData(u, i, v), k=0)
     with pytest.raises(Exception, match='should be in the'):
         drb.leave_k_out(drb.InteractionData(u, i, v), k=1.5)
+
+
+# ------------------------------------------------------------------------------------------------ repo contracts
+def test_product_package_never_imports_the_oracle():
+    """oracle/ is test infrastructure: nothing under drecpy_b200/ may import or execute it."""
+    root = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'drecpy_b200')
+    for name in os.listdir(root):
+        if name.endswith('.py'):
+            src = open(os.path.join(root, name)).read()
+            assert not re.search(r'^\s*(from|import)\s+oracle\b', src, re.M), name
+
+
+def test_committed_bench_lines_carry_the_contract_keys():
+    """profiles/r1_bench_n*.json are bench.py's own output lines: every key the bench contract names is present."""
+    prof = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'profiles')
+    for n in (1, 2, 4, 8):
+        j = json.load(open(os.path.join(prof, f'r1_bench_n{n}.json')))
+        for k in ('metric', 'value', 'unit', 'n_gpus', 'steps', 'warmup', 'ms_per_step', 'higher_is_better', 'scaling',
+                  'vs_baseline', 'dtype', 'data', 'config', 'clocks', 'gpu_launches', 'e2e', 'roofline'):
+            assert k in j, (n, k)
+        assert j['n_gpus'] == n and j['warmup'] >= 3 and j['vs_baseline'] is None and 'workload' in j['config']
+        assert set(j['e2e']) >= {'value', 'unit', 'h2d_bytes_per_step', 'd2h_bytes_per_step'}
+        assert set(j['roofline']) >= {'bound', 'achieved', 'peak', 'unit', 'frac', 'traffic'}
+        assert j['gpu_launches'] > 0 and j['e2e']['value'] < j['value']
+        assert not set(j['clocks']['reasons']) & {'hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown'}
+        if n == 1:
+            assert set(j['cpu_baseline']) >= {'value', 'unit', 'cores', 'kind', 'sample'}
+            assert abs(j['roofline']['frac'] - j['roofline']['achieved'] / j['roofline']['peak']) < 1e-9
