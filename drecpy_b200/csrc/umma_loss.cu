@@ -398,7 +398,10 @@ int launch_umma_cdae_loss(drb_ctx* ctx, const UmmaOperands& o, int M, int N, int
                     : run_loss<BN_, DRB_LOSS_MSE, false, KB_, CL_>(ctx, o, p, n_blocks_out);        \
   }
   if (wide) {
-    if ((cl_env ? cl_env : DRB_LOSS_CLUSTER_DEFAULT) == 2) DRB_LOSS_CASE(256, 32, 2)
+    if ((cl_env ? cl_env : DRB_LOSS_CLUSTER_DEFAULT) == 2) {
+      if ((bk_env ? bk_env : 32) == 16) DRB_LOSS_CASE(256, 16, 2)
+      DRB_LOSS_CASE(256, 32, 2)
+    }
     // the persistent loop already keeps TMA ahead across tiles: 32-deep stages measured 0.30 ms, 16-deep 0.31 ms
     if ((bk_env ? bk_env : 32) == 16) DRB_LOSS_CASE(256, 16, 1)
     DRB_LOSS_CASE(256, 32, 1)
