@@ -122,6 +122,7 @@ SIGNATURES = {
     'drb_eval_candidates': (C.c_int, [i64, vp, vp, vp, vp, vp, vp, vp, vp, i64, i32, i64, f64, i64, f64, i32, i32, i64,
                                       i32, i64, vp, vp, vp, vp, vp]),
     'drb_leave_k_out': (C.c_int, [i64, vp, i64, f64, i32, i64, i64, i32, vp]),
+    'drb_eval_lookup': (C.c_int, [i64, vp, vp, vp, vp, vp, vp, vp, f64, i32, vp]),
 }
 
 _lib = None

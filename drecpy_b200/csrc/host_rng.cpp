@@ -7,6 +7,7 @@
 #include <cmath>
 #include <cstring>
 #include <functional>
+#include <cstdint>
 #include <thread>
 #include <unordered_set>
 #include <vector>
@@ -423,6 +424,55 @@ int drb_eval_candidates(int64_t n_users, const int64_t* test_indptr, const int64
       cand_off[u + 1] = co; pos_off[u + 1] = po;
       skipped[u] = C.skipped[u - C.lo];
     }
+  }
+  return DRB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------- grouped key lookup
+// For every group g (one evaluated user): out[q] = value of the FIRST table row of the group whose key equals
+// q_key[q], else `miss`, for q in [q_beg[g], q_end[g]).  The table rows of group g are [tab_beg[g], tab_end[g]) of
+// tab_key / tab_val (tab_val NULL: every row counts 1.0).  This is the per-candidate `ds_test.select_one(uid, iid)`
+// of ranking_evaluation.py:222-223 (relevancy of a ranked / candidate item = the first matching test row, else 0) and
+// the `item in positives` test of the metrics (Metrics/ranking.py:32-56), for all users in one call.
+int drb_eval_lookup(int64_t n_groups, const int64_t* tab_beg, const int64_t* tab_end, const int64_t* tab_key,
+                    const double* tab_val, const int64_t* q_beg, const int64_t* q_end, const int64_t* q_key,
+                    double miss, int32_t n_threads, double* out) {
+  if (n_groups < 0 || !tab_beg || !tab_end || !q_beg || !q_end || !out)
+    return drb_fail(DRB_E_INVALID, "drb_eval_lookup: bad argument");
+  auto worker = [&](int64_t lo, int64_t hi) {
+    std::vector<std::pair<int64_t, int64_t>> idx;   // (key, first row) of a long table, sorted by key
+    for (int64_t g = lo; g < hi; g++) {
+      const int64_t tb = tab_beg[g], te = tab_end[g], nt = te - tb;
+      const bool longtab = nt > 16;
+      if (longtab) {
+        idx.clear();
+        for (int64_t r = tb; r < te; r++) idx.emplace_back(tab_key[r], r);
+        std::sort(idx.begin(), idx.end());          // pairs: equal keys ordered by row, so the first row comes first
+      }
+      for (int64_t q = q_beg[g]; q < q_end[g]; q++) {
+        const int64_t key = q_key[q];
+        int64_t hit = -1;
+        if (longtab) {
+          auto it = std::lower_bound(idx.begin(), idx.end(), std::make_pair(key, (int64_t)INT64_MIN));
+          if (it != idx.end() && it->first == key) hit = it->second;
+        } else {
+          for (int64_t r = tb; r < te; r++)
+            if (tab_key[r] == key) { hit = r; break; }
+        }
+        out[q] = hit < 0 ? miss : (tab_val ? tab_val[hit] : 1.0);
+      }
+    }
+  };
+  int nt = std::max(1, std::min<int>(n_threads, 64));
+  if (n_groups < 1024) nt = 1;
+  if (nt == 1) {
+    worker(0, n_groups);
+  } else {
+    std::vector<std::thread> th;
+    const int64_t per = (n_groups + nt - 1) / nt;
+    for (int t = 0; t < nt; t++)
+      th.emplace_back(worker, std::min<int64_t>(n_groups, t * per), std::min<int64_t>(n_groups, (t + 1) * per));
+    for (auto& x : th) x.join();
   }
   return DRB_OK;
 }

@@ -102,26 +102,38 @@ class InteractionData:
     def iid_to_item(self, iid):
         return self._items[iid].item() if 0 <= iid < len(self._items) else None
 
+    def _id_lookup(self, which, ids):
+        """Vectorised raw -> internal ids; unknown ids map to -1.  Non-negative integer ids in a compact range go
+        through a direct table (one gather), anything else through a binary search in the sorted raw ids."""
+        raw = self._items if which == 'items' else self._users
+        ids = np.asarray(ids)
+        key = 'lut_' + which
+        if key not in self._cache:
+            lut = None
+            if raw.dtype.kind in 'iu' and len(raw) and raw.min() >= 0 and raw.max() <= max(1 << 24, 8 * len(raw)):
+                lut = np.full(int(raw.max()) + 2, -1, np.int64)       # last slot: everything out of range
+                lut[raw] = np.arange(len(raw))
+            self._cache[key] = lut
+            order = np.argsort(raw, kind='stable')
+            self._cache['sorted_' + which] = (raw[order], order.astype(np.int64))
+        lut = self._cache[key]
+        if lut is not None and ids.dtype.kind in 'iu':
+            top = len(lut) - 1
+            safe = np.where((ids >= 0) & (ids < top), ids, top) if len(ids) else ids
+            return lut[safe]
+        s_, order = self._cache['sorted_' + which]
+        if not len(s_):
+            return np.full(len(ids), -1, np.int64)
+        pos = np.clip(np.searchsorted(s_, ids), 0, len(s_) - 1)
+        return np.where(s_[pos] == ids, order[pos], -1)
+
     def items_to_iids(self, items):
         """Vectorised raw -> internal item ids; unknown ids map to -1."""
-        items = np.asarray(items)
-        if 'sorted_items' not in self._cache:
-            order = np.argsort(self._items, kind='stable')
-            self._cache['sorted_items'] = (self._items[order], order.astype(np.int64))
-        s, order = self._cache['sorted_items']
-        pos = np.searchsorted(s, items)
-        pos = np.clip(pos, 0, len(s) - 1)
-        return np.where(s[pos] == items, order[pos], -1)
+        return self._id_lookup('items', items)
 
     def users_to_uids(self, users):
         """Vectorised raw -> internal user ids; unknown ids map to -1."""
-        users = np.asarray(users)
-        if 'sorted_users' not in self._cache:
-            order = np.argsort(self._users, kind='stable')
-            self._cache['sorted_users'] = (self._users[order], order.astype(np.int64))
-        s, order = self._cache['sorted_users']
-        pos = np.clip(np.searchsorted(s, users), 0, len(s) - 1)
-        return np.where(s[pos] == users, order[pos], -1)
+        return self._id_lookup('users', users)
 
     @property
     def raw_items(self):

@@ -196,31 +196,35 @@ def _fast_evaluation(model, data, users, t_indptr, t_order, thr, n_pos, n_neg, g
             return None
         ranked, n_out = model.rank_arrays(users[active], c_flat, c_off, novelty=novelty)
         c_max, L = int(c_lens.max()), ranked.shape[1]
-        # relevancy lookup: first test row of (user, item), else 0  (ranking_evaluation.py:223)
-        t_seg = np.repeat(np.arange(len(users)), np.diff(t_indptr))
-        remap = np.full(len(users), -1, np.int64); remap[active] = np.arange(n)
-        t_keep = remap[t_seg] >= 0
-        t_key = remap[t_seg[t_keep]] * big + t_item[t_keep]
-        u_key, first = np.unique(t_key, return_index=True)
-        u_val = t_val[t_keep][first]
+        # relevancy lookup: first test row of (user, item), else 0  (ranking_evaluation.py:223); hits: the ranked item
+        # is one of the user's sampled positives.  Both are grouped first-match lookups done natively for all users.
+        lib, nthr = _lib.load(), min(16, os.cpu_count() or 1)
+        t_beg = np.ascontiguousarray(t_indptr[:-1][active].astype(np.int64))
+        t_end = np.ascontiguousarray(t_indptr[1:][active].astype(np.int64))
+        t_item_c, t_val_c = np.ascontiguousarray(t_item, np.int64), np.ascontiguousarray(t_val, np.float64)
 
-        def relevancy(seg, items):
-            key = seg * big + items
-            pos_ = np.clip(np.searchsorted(u_key, key), 0, max(len(u_key) - 1, 0))
-            hit = (u_key[pos_] == key) if len(u_key) else np.zeros(len(key), bool)
-            return np.where(hit, u_val[pos_], 0.0) if len(u_key) else np.zeros(len(key))
-        rel_rank = np.zeros((n, L))
+        def lookup(tab_beg, tab_end, tab_key, tab_val, q_beg, q_end, q_key, out):
+            _lib.check(lib.drb_eval_lookup(n, _lib.np_ptr(tab_beg), _lib.np_ptr(tab_end), _lib.np_ptr(tab_key),
+                                           _lib.np_ptr(tab_val) if tab_val is not None else None, _lib.np_ptr(q_beg),
+                                           _lib.np_ptr(q_end), _lib.np_ptr(q_key), 0.0, nthr, _lib.np_ptr(out)))
         valid = np.arange(L)[None, :] < n_out[:, None]
-        rr, cc = np.nonzero(valid)
-        rel_rank[rr, cc] = relevancy(rr, ranked[rr, cc])
+        ranked_c = np.ascontiguousarray(ranked, np.int64)
+        r_beg = np.arange(n, dtype=np.int64) * L
+        r_end = r_beg + n_out.astype(np.int64)
+        rel_rank = np.zeros((n, L))
+        lookup(t_beg, t_end, t_item_c, t_val_c, r_beg, r_end, ranked_c.reshape(-1), rel_rank.reshape(-1))
+        c_flat_c = np.ascontiguousarray(c_flat, np.int64)
+        rel_flat = np.zeros(len(c_flat_c))
+        c_beg, c_end = np.ascontiguousarray(c_off[:-1]), np.ascontiguousarray(c_off[1:])
+        lookup(t_beg, t_end, t_item_c, t_val_c, c_beg, c_end, c_flat_c, rel_flat)
         rel_cand = np.full((n, c_max), -np.inf)
-        rel_cand[c_seg, np.arange(c_off[-1]) - np.repeat(c_off[:-1], c_lens)] = relevancy(c_seg, c_flat)
+        rel_cand[c_seg, np.arange(c_off[-1]) - np.repeat(c_off[:-1], c_lens)] = rel_flat
         ideal = -np.sort(-rel_cand, axis=1)                       # relevancies of the ideal list, descending
-        # hits: ranked item is one of the user's sampled positives
-        p_key = np.sort(p_seg * big + p_flat)
-        rk = np.where(valid, np.arange(n)[:, None] * big + np.maximum(ranked, 0), -1)
-        pp = np.clip(np.searchsorted(p_key, rk), 0, max(len(p_key) - 1, 0))
-        is_pos = valid & (p_key[pp] == rk) if len(p_key) else np.zeros_like(valid)
+        hit = np.zeros((n, L))
+        p_flat_c = np.ascontiguousarray(p_flat, np.int64)
+        lookup(np.ascontiguousarray(p_off[:-1]), np.ascontiguousarray(p_off[1:]), p_flat_c, None, r_beg, r_end,
+               ranked_c.reshape(-1), hit.reshape(-1))
+        is_pos = valid & (hit > 0.5)
         for m in metrics:
             for k_ in ks:
                 kk = min(k_, L)

@@ -321,6 +321,15 @@ int drb_eval_candidates(int64_t n_users, const int64_t* test_indptr, const int64
                         int32_t n_threads, int64_t cand_capacity, int64_t* cand_off, int64_t* cand, int64_t* pos_off,
                         int64_t* pos, uint8_t* skipped);
 
+/* Grouped first-match lookup (replaces the per-candidate ds_test.select_one('uid == .., iid == ..') of
+ * DRecPy/Evaluation/Processes/ranking_evaluation.py:222-223 and the `item in positives` tests of
+ * Evaluation/Metrics/ranking.py:32-56).  For group g, out[q] = tab_val of the first row r in [tab_beg[g], tab_end[g])
+ * with tab_key[r] == q_key[q] (1.0 when tab_val is NULL), else `miss`, for every q in [q_beg[g], q_end[g]).
+ * Positions of `out` outside every query range are left untouched. */
+int drb_eval_lookup(int64_t n_groups, const int64_t* tab_beg, const int64_t* tab_end, const int64_t* tab_key,
+                    const double* tab_val, const int64_t* q_beg, const int64_t* q_end, const int64_t* q_key,
+                    double miss, int32_t n_threads, double* out);
+
 /* Leave-k-out split for every user at once (replaces DRecPy/Evaluation/Splits/leave_k_out.py:58-135: one
  * interaction_dataset.select('user == ...') plus rng.sample per user on a thread pool).  Rows are given grouped by
  * user in order of first appearance, each group in DataFrame order: group idx spans user_indptr[idx]..[idx+1].  User
