@@ -321,7 +321,18 @@ inline bool in_train(const EvalShared& S, int64_t u, int64_t it) {
 
 void eval_worker(const EvalShared& S, EvalChunk& C) {
   drb_rng g;
-  std::vector<int64_t> p_items, n_pool, negs, picked, all, chosen;
+  std::vector<int64_t> p_items, n_pool, negs, picked, all, chosen, tp;
+  // Generated negatives are integers in [0, n_items): two byte maps over that range replace a hash set of the
+  // negatives drawn so far and the two binary searches per draw of `in_train` (both cleared per user by walking
+  // what was set).  iid_raw = inverse of the sorted raw-id map, built once per worker.
+  std::vector<uint8_t> neg_mark((size_t)std::max<int64_t>(S.n_items, 0), 0), train_mark(neg_mark.size(), 0);
+  std::vector<int64_t> iid_raw, train_set;
+  if (S.black_row && S.n_map > 0) {
+    int32_t max_iid = -1;
+    for (int64_t k = 0; k < S.n_map; k++) max_iid = std::max(max_iid, S.raw_to_iid[k]);
+    iid_raw.assign((size_t)max_iid + 1, -1);
+    for (int64_t k = 0; k < S.n_map; k++) iid_raw[S.raw_to_iid[k]] = S.raw_sorted[k];
+  }
   for (int64_t u = C.lo; u < C.hi; u++) {
     int64_t s = S.seed + u;  // ranking_evaluation.py:111-116
     g.seed((uint64_t)(s < 0 ? -s : s));
@@ -348,7 +359,7 @@ void eval_worker(const EvalShared& S, EvalChunk& C) {
       for (int64_t i : picked) negs.push_back(n_pool[i]);
       if ((int64_t)negs.size() < want && S.generate) {
         // blacklist = train positives (unless evaluating on train) U test positives  (:193-201)
-        std::vector<int64_t> tp(p_items);
+        tp = p_items;
         std::sort(tp.begin(), tp.end());
         tp.erase(std::unique(tp.begin(), tp.end()), tp.end());
         int64_t black_size = (int64_t)tp.size();
@@ -358,14 +369,28 @@ void eval_worker(const EvalShared& S, EvalChunk& C) {
           for (int64_t it : tp) black_size += in_train(S, u, it) ? 0 : 1;
         }
         if (S.n_items - black_size < want) continue;  // :202-207
-        std::unordered_set<int64_t> in_negs(negs.begin(), negs.end());
+        const size_t first_generated = negs.size();
+        for (int64_t it : negs)                          // sampled test negatives that fall inside the drawn range
+          if (it >= 0 && it < S.n_items) neg_mark[(size_t)it] = 1;
+        train_set.clear();
+        if (!S.train_evaluation && S.black_row && S.black_row[u] >= 0) {
+          const int64_t r = S.black_row[u];
+          for (int64_t k = S.black_indptr[r]; k < S.black_indptr[r + 1]; k++) {
+            const int32_t iid = S.black_iid[k];
+            const int64_t raw = (iid >= 0 && (size_t)iid < iid_raw.size()) ? iid_raw[iid] : -1;
+            if (raw >= 0 && raw < S.n_items) { train_mark[(size_t)raw] = 1; train_set.push_back(raw); }
+          }
+        }
         while ((int64_t)negs.size() < want) {
           const int64_t it = g.randint(0, S.n_items - 1);  // :211 (raw/internal id confusion kept)
-          if (std::binary_search(tp.begin(), tp.end(), it) || in_negs.count(it)) continue;
-          if (!S.train_evaluation && in_train(S, u, it)) continue;
+          if (neg_mark[(size_t)it] || train_mark[(size_t)it] || std::binary_search(tp.begin(), tp.end(), it)) continue;
           negs.push_back(it);
-          in_negs.insert(it);
+          neg_mark[(size_t)it] = 1;
         }
+        for (size_t k = 0; k < first_generated; k++)
+          if (negs[k] >= 0 && negs[k] < S.n_items) neg_mark[(size_t)negs[k]] = 0;
+        for (size_t k = first_generated; k < negs.size(); k++) neg_mark[(size_t)negs[k]] = 0;
+        for (int64_t raw : train_set) train_mark[(size_t)raw] = 0;
       }
     }
     all = chosen;

@@ -294,18 +294,24 @@ class DeepRecommenderABC(ABC):
         lens = np.diff(cand_off).astype(np.int64)
         c_max = int(max(1, lens.max() if n else 1))
         iids = data.items_to_iids(cand).astype(np.int32)
-        padded = np.full((n, c_max), -1, np.int32)
-        rows = np.repeat(np.arange(n), lens)
-        cols = np.arange(len(cand)) - np.repeat(cand_off[:-1], lens)
-        padded[rows, cols] = iids
+        if n and (lens == c_max).all() and cand_off[0] == 0:          # uniform lists (the sampled protocol): a reshape
+            padded = np.ascontiguousarray(iids.reshape(n, c_max))
+        else:
+            padded = np.full((n, c_max), -1, np.int32)
+            rows = np.repeat(np.arange(n), lens)
+            cols = np.arange(len(cand)) - np.repeat(cand_off[:-1], lens)
+            padded[rows, cols] = iids
         out_items = np.full((n, c_max), -1, np.int64)
         n_out = np.zeros(n, np.int32)
         raw = data.raw_items
         for o in range(0, n, chunk):
             oi, _, on = self._rank_batch(uids[o:o + chunk], padded[o:o + chunk], lens[o:o + chunk].astype(np.int32),
                                          novelty)
-            valid = np.arange(c_max)[None, :] < on[:, None]
-            out_items[o:o + chunk] = np.where(valid, raw[np.where(valid, oi, 0)], -1)
+            if (on == oi.shape[1]).all():                                # nothing filtered: every slot is valid
+                out_items[o:o + chunk, :oi.shape[1]] = raw[oi]
+            else:
+                valid = np.arange(oi.shape[1])[None, :] < on[:, None]
+                out_items[o:o + chunk, :oi.shape[1]] = np.where(valid, raw[np.where(valid, oi, 0)], -1)
             n_out[o:o + chunk] = on
         return out_items, n_out
 

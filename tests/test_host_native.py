@@ -282,3 +282,58 @@ def test_committed_bench_lines_carry_the_contract_keys():
         if n == 1:
             assert set(j['cpu_baseline']) >= {'value', 'unit', 'cores', 'kind', 'sample'}
             assert abs(j['roofline']['frac'] - j['roofline']['achieved'] / j['roofline']['peak']) < 1e-9
+
+
+def test_rank_arrays_uniform_and_ragged_paths_agree():
+    """DeepRecommenderABC.rank_arrays (host side of the batched scorer): the reshape fast path for equally long
+    candidate lists and the padded path for ragged ones hand the same lists to _rank_batch and map the same raw ids
+    back, including unknown items (-1) and rows shortened by the novelty filter."""
+    from drecpy_b200.recommender import DeepRecommenderABC
+
+    class Scorer(DeepRecommenderABC):
+        def __init__(self, data):
+            self._data = data
+            self.n_items = data.count_unique('iid')
+
+        def _pre_fit(self, *a, **k): pass
+        def _predict(self, *a, **k): pass
+        def _train_step(self, *a, **k): pass
+
+        def _rank_batch(self, uids, cand, cand_count, novelty):
+            n, c = cand.shape
+            oi, on = np.full((n, c), -1, np.int32), np.zeros(n, np.int32)
+            for r in range(n):
+                items = [int(x) for x in cand[r, :cand_count[r]] if x >= 0]
+                if novelty:
+                    seen = set(self._data.user_items(int(uids[r])).tolist())
+                    items = [x for x in items if x not in seen]
+                items = sorted(set(items), key=lambda x: ((x * 2654435761 + int(uids[r])) % 1009, x), reverse=True)
+                oi[r, :len(items)] = items
+                on[r] = len(items)
+            return oi, np.zeros((n, c), np.float32), on
+
+    u, i, v = drb.synthetic_interactions(40, 60, 600, seed=2)
+    data = drb.InteractionData(u, i, v)
+    data.assign_internal_ids()
+    m = Scorer(data)
+    rng = np.random.default_rng(1)
+    users = data.raw_users[rng.permutation(40)[:25]]
+    for novelty in (False, True):
+        uniform = rng.integers(1, 61, (25, 12)).astype(np.int64)
+        uniform[3, 5] = 10_000                                       # unknown raw item
+        off = np.arange(26, dtype=np.int64) * 12
+        got, n_out = m.rank_arrays(users, uniform.reshape(-1), off, novelty=novelty, chunk=7)
+        # the same lists, made ragged by appending one extra list of a different length
+        cand2 = np.concatenate([uniform.reshape(-1), np.array([5, 6, 7], np.int64)])
+        off2 = np.concatenate([off, [off[-1] + 3]])
+        got2, n_out2 = m.rank_arrays(np.concatenate([users, users[:1]]), cand2, off2, novelty=novelty, chunk=7)
+        assert np.array_equal(n_out, n_out2[:25]) and np.array_equal(got, got2[:25, :12])
+        for r in range(25):
+            uid = data.user_to_uid(users[r].item())
+            iids = [data.item_to_iid(int(x)) for x in uniform[r]]
+            iids = [x for x in iids if x is not None]
+            if novelty:
+                iids = [x for x in iids if x not in set(data.user_items(uid).tolist())]
+            exp = sorted(set(iids), key=lambda x: ((x * 2654435761 + uid) % 1009, x), reverse=True)
+            assert got[r, :n_out[r]].tolist() == [data.iid_to_item(x) for x in exp]
+            assert (got[r, n_out[r]:] == -1).all()
