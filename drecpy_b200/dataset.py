@@ -20,7 +20,7 @@ def _build_csr(rows, cols, vals, n_rows, n_cols):
     if len(rows) == 0:
         return np.zeros(n_rows + 1, np.int64), np.zeros(0, np.int32), np.zeros(0, np.float64)
     key = rows * n_cols + cols
-    order = np.argsort(key, kind='stable')
+    order = _argsort_stable(key)
     key_s = key[order]
     starts = np.flatnonzero(np.concatenate(([True], key_s[1:] != key_s[:-1])))
     data = np.add.reduceat(vals[order], starts)          # duplicates summed (scipy csr_matrix semantics)
@@ -29,6 +29,16 @@ def _build_csr(rows, cols, vals, n_rows, n_cols):
     indptr = np.zeros(n_rows + 1, np.int64)
     np.cumsum(np.bincount(r, minlength=n_rows), out=indptr[1:])
     return indptr, (ukey % n_cols).astype(np.int32), data
+
+
+def _argsort_stable(keys):
+    """np.argsort(kind='stable') for large integer arrays through torch's multi-threaded CPU sort (same permutation:
+    both are stable); ~6x faster at 2e7 keys, which is the whole cost of building the CSR views of an ml-20m table."""
+    keys = np.ascontiguousarray(keys)
+    if len(keys) < 1_000_000 or keys.dtype.kind not in 'iu':
+        return np.argsort(keys, kind='stable')
+    import torch
+    return torch.sort(torch.from_numpy(keys.astype(np.int64, copy=False)), stable=True).indices.numpy()
 
 
 def _unique_sorted(keys):
@@ -189,7 +199,7 @@ class InteractionData:
             assert self.has_internal_ids
             U = self.count_unique('uid')
             sel = np.arange(len(self)) if threshold is None else np.flatnonzero(self.interaction >= threshold)
-            order = sel[np.argsort(self.uid[sel], kind='stable')]
+            order = sel[_argsort_stable(self.uid[sel])]
             indptr = np.zeros(U + 1, np.int64)
             np.cumsum(np.bincount(self.uid[sel], minlength=U), out=indptr[1:])
             self._cache[key] = (indptr, np.ascontiguousarray(self.iid[order]),

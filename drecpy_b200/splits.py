@@ -13,13 +13,13 @@ import numpy as np
 import pandas as pd
 
 from . import _lib
-from .dataset import InteractionData
+from .dataset import InteractionData, _argsort_stable
 
 
 def _group_rows_by_user(users):
     """Row positions grouped by user in order of first appearance, each group in row order."""
     codes, uniques = pd.factorize(np.asarray(users))
-    order = np.argsort(codes, kind='stable')
+    order = _argsort_stable(codes)
     indptr = np.zeros(len(uniques) + 1, np.int64)
     np.cumsum(np.bincount(codes, minlength=len(uniques)), out=indptr[1:])
     return order.astype(np.int64), indptr
