@@ -337,3 +337,18 @@ def test_rank_arrays_uniform_and_ragged_paths_agree():
             exp = sorted(set(iids), key=lambda x: ((x * 2654435761 + uid) % 1009, x), reverse=True)
             assert got[r, :n_out[r]].tolist() == [data.iid_to_item(x) for x in exp]
             assert (got[r, n_out[r]:] == -1).all()
+
+
+def test_config4_flow_split_then_evaluate_small():
+    """Config 4's host flow end to end at a small shape: leave_k_out(k=1) -> ranking_evaluation with 1 positive and
+    generated negatives; the vectorised evaluator (native candidates + grouped lookups) equals the per-user protocol."""
+    u, i, v = drb.synthetic_interactions(250, 320, 7000, seed=9)
+    train, test = drb.leave_k_out(drb.InteractionData(u, i, v), k=1, seed=10, verbose=False)
+    assert len(test) == 250 and len(train) == 7000 - 250
+    train.assign_internal_ids()
+    model = FakeBatchModel(train)
+    kw = dict(k=[5, 10], n_pos_interactions=1, n_neg_interactions=100, generate_negative_pairs=True, novelty=True,
+              seed=10, metrics=[drb.HitRatio(), drb.NDCG(), drb.Precision(), drb.Recall()])
+    fast = drb.ranking_evaluation(model, test, verbose=False, **kw)
+    slow = drb.ranking_evaluation(model, test, verbose=False, force_python=True, **kw)
+    assert fast == slow and 0 < fast['HitRatio@10'] <= 1
