@@ -36,6 +36,40 @@ def load_peaks():
     return dict(hbm=6650.0, tf=1400.0, tf_burst=1590.0, src='fallback')
 
 
+def build_roofline(kernels, hidden, n_items, batch, n_params, peaks, traffic_table=None):
+    """The `roofline` object of the bench line from the per-kernel CUDA-event times (ms per step).
+
+    Dominant kernels: the three output-layer GEMMs (forward + fused loss epilogue, dW'^T, dh), tensor bound.
+    `achieved` = ALGORITHMIC flops (6*K*I per sampled user) / their time; `peak` = the measured sustained
+    bf16 rate.  Every fp32-accurate product is issued as three TF32 MMAs and TF32 runs at half the bf16 rate, so this
+    design can reach at most peak / 6 of algorithmic flops (`cap_3xtf32`); `frac_of_cap` says how close the kernels are
+    to that."""
+    gemm_ms = sum(v for k, v in kernels.items() if k.startswith('k_sgemm') or k.startswith('k_umma'))
+    flops = 6.0 * hidden * n_items * batch
+    achieved = flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else None
+    tc_path = any(k.startswith('k_umma') for k in kernels)
+    traffic = None
+    if tc_path and traffic_table:
+        traffic = sum(traffic_table[k] for k in ('k_umma_cdae_loss', 'k_umma_gemm_mn', 'k_umma_gemm_kk'))
+    adam_ms = kernels.get('k_adam', float('nan'))
+    adam_gbs = 28.0 * n_params / (adam_ms * 1e-3) / 1e9
+    cap = peaks['tf'] / 6.0 if tc_path else None
+    return {'kernel': ('k_umma_cdae_loss + k_umma_gemm x2 (tcgen05 3xTF32: output layer fwd + fused loss epilogue, '
+                       'dW\'^T and dh)') if tc_path else 'k_sgemm x3 (fp32 FFMA path)',
+            'bound': 'tensor', 'achieved': achieved, 'peak': peaks['tf'], 'unit': 'TFLOP/s',
+            'frac': (achieved / peaks['tf']) if achieved else None, 'traffic': traffic,
+            'note': ('achieved counts the algorithmic fp32 flops (6*K*I per sampled user); every product is issued '
+                     'as 3 TF32 MMAs (half the bf16 rate each), so the issued-MMA rate is 3x achieved against a '
+                     'TF32 peak of half the bf16 peak: at most peak/6 of algorithmic flops') if tc_path
+            else 'CUDA-core path',
+            'achieved_issued_tf32': 3 * achieved if (achieved and tc_path) else None,
+            'cap_3xtf32': cap, 'frac_of_cap': (achieved / cap) if (achieved and cap) else None,
+            'peak_source': f"{peaks['src']} bf16 sustained",
+            'share_of_step': gemm_ms / sum(kernels.values()) if kernels else None,
+            'secondary': {'k_adam': {'bound': 'hbm', 'achieved': adam_gbs, 'peak': peaks['hbm'], 'unit': 'GB/s',
+                                     'frac': adam_gbs / peaks['hbm']}}}
+
+
 def make_data(cfg):
     import drecpy_b200 as drb
     t = time.time()
@@ -259,29 +293,13 @@ def run_native(args, cfg):
     kernels = {k: round(v[0] / P, 4) for k, v in prof.items()}
     peaks = load_peaks()
     I, Hd, U = cfg['n_items'], cfg['hidden'], cfg['n_users']
-    gemm_ms = sum(v for k, v in kernels.items() if k.startswith('k_sgemm') or k.startswith('k_umma'))
-    flops = 6.0 * Hd * I * B                                     # 2KI fwd + 4KI bwd per sampled user
-    achieved = flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else None
-    tc_path = any(k.startswith('k_umma') for k in kernels)
-    traffic = None
+    traffic_table = None
     tpath = os.path.join(ROOT, 'profiles', 'r1_traffic.json')
-    if tc_path and os.path.exists(tpath) and cfg['name'] == C3['name']:
-        tb = json.load(open(tpath))['dram_bytes_per_launch']      # ncu --set full capture of the same command
-        traffic = tb['k_umma_cdae_loss'] + tb['k_umma_gemm_mn'] + tb['k_umma_gemm_kk']
+    if os.path.exists(tpath) and cfg['name'] == C3['name']:
+        traffic_table = json.load(open(tpath))['dram_bytes_per_launch']   # ncu --set full capture of the same command
     n_params = int(m._L.total)                                   # parameters this rank updates (its shard when item-sharded)
     launches_total = int(launches)
-    adam_gbs = 28.0 * n_params / (kernels.get('k_adam', float('nan')) * 1e-3) / 1e9
-    roofline = {'kernel': ('k_umma_cdae_loss + k_umma_gemm x2 (tcgen05 3xTF32: output layer fwd + fused loss epilogue, '
-                           'dW\'^T and dh)') if tc_path else 'k_sgemm x3 (fp32 FFMA path)',
-                'bound': 'tensor', 'achieved': achieved, 'peak': peaks['tf'], 'unit': 'TFLOP/s',
-                'frac': (achieved / peaks['tf']) if achieved else None, 'traffic': traffic,
-                'note': 'achieved counts the algorithmic fp32 flops (6*K*I per sampled user); every product is issued '
-                        'as 3 TF32 MMAs (half the bf16 rate each), so the issued-MMA rate is 3x achieved against a '
-                        'TF32 peak of half the bf16 peak' if tc_path else 'CUDA-core path',
-                'achieved_issued_tf32': 3 * achieved if (achieved and tc_path) else None,
-                'peak_source': f"{peaks['src']} bf16 sustained", 'share_of_step': gemm_ms / sum(kernels.values()),
-                'secondary': {'k_adam': {'bound': 'hbm', 'achieved': adam_gbs, 'peak': peaks['hbm'], 'unit': 'GB/s',
-                                         'frac': adam_gbs / peaks['hbm']}}}
+    roofline = build_roofline(kernels, Hd, I, B, n_params, peaks, traffic_table)
 
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
