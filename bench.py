@@ -187,12 +187,14 @@ def run_reference(args, cfg):
 
 def workload_config(cfg, n_gpus, parallelism=None):
     parallelism = parallelism or f'dp{n_gpus}'
+    origin = 'BASELINE.json configs[2]' if cfg['name'] == C3['name'] else 'debug shape, not a BASELINE.json config'
     return {'workload': f"{cfg['name']}: CDAE hidden_factors={cfg['hidden']} bce q={cfg['q']} on synthetic "
-                        f"{cfg['n_users']}x{cfg['n_items']} / {cfg['nnz']} interactions (BASELINE.json configs[2])",
+                        f"{cfg['n_users']}x{cfg['n_items']} / {cfg['nnz']} interactions ({origin})",
             'batch_per_gpu': cfg['batch'], 'global_batch': cfg['batch'] * n_gpus, 'neg_ratio': cfg['neg_ratio'],
             'label_mode': 'batch_mean', 'adam': 'dense, per-variable step counter', 'mask_rng': 'philox (device)',
             'item_popularity': f"zipf a={cfg['zipf_a']}", 'parallelism': parallelism,
-            'l2': 'per-step working set (params + Adam state + dz ~ 2.7 GB) exceeds the 126 MB L2; no flush needed'}
+            'l2': ('per-step working set (params + Adam state + dz ~ 2.7 GB) exceeds the 126 MB L2; no flush needed'
+                   if cfg['name'] == C3['name'] else 'debug shape: the working set is L2 resident')}
 
 
 # ------------------------------------------------------------------------------------------ GPU arm
