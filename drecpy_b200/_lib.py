@@ -90,7 +90,7 @@ SIGNATURES = {
     'drb_sampler_sample': (C.c_int, [vp, i64, vp, vp, vp]),
     'drb_sampler_getstate': (C.c_int, [vp, vp]),
     'drb_sampler_setstate': (C.c_int, [vp, vp]),
-    'drb_cdae_corruption_keep_mt': (C.c_int, [vp, vp, i32, i32, f64, vp, vp, vp, vp]),
+    'drb_cdae_corruption_keep_mt': (C.c_int, [vp, vp, i32, i32, f64, vp, vp, vp, vp, i64]),
     'drb_batch_offsets': (C.c_int, [vp, i32, vp, vp]),
     'drb_cdae_layout': (C.c_int, [i32, i32, i32, P(CdaeLayout)]),
     'drb_cdae_workspace_bytes': (i64, [i32, i32, i32, i32]),
@@ -117,6 +117,7 @@ SIGNATURES = {
     'drb_dmf_step_host': (C.c_int, [vp, vp, vp, vp, i32, P(DmfStepArgs), vp]),
     'drb_dmf_forward_pairs': (C.c_int, [vp, vp, vp, i32, vp]),
     'drb_dmf_rank_candidates': (C.c_int, [vp, vp, i32, vp, vp, i32, i32, vp, vp, vp]),
+    'drb_dmf_invalidate_cache': (C.c_int, [vp]),
     'drb_debug_split_tf32': (C.c_int, [vp, vp, i32, i32, i32, vp, vp, vp, vp, i32, i32]),
     'drb_debug_umma_gemm': (C.c_int, [vp, vp, vp, i32, vp, vp, i32, i32, i32, i32, i32, i32, i32, vp, i32, i32, vp, i32]),
     'drb_eval_candidates': (C.c_int, [i64, vp, vp, vp, vp, vp, vp, vp, vp, i64, i32, i64, f64, i64, f64, i32, i32, i64,

@@ -174,7 +174,9 @@ class CDAE(DeepRecommenderABC):
             batch_size = batch_size * self._dp.world
         torch = self._torch
         deg = np.diff(self._h_indptr)
-        cap = int(np.sort(deg)[::-1][:batch_size].sum()) if len(deg) else 0   # exact bound on a batch's nnz
+        # users are drawn WITH replacement, so no sum over distinct users bounds a batch's positives; start from a
+        # typical batch and let prepare_batch grow the slot when drb_batch_offsets reports more (_ensure_keep)
+        cap = int(min(batch_size * int(deg.max(initial=0)), 4 * batch_size * float(deg.mean()) + 4096)) if len(deg) else 0
         self._slots = []
         for _ in range(_RING):
             s = {'uid': torch.empty(batch_size, dtype=torch.int32).pin_memory(),
@@ -256,15 +258,26 @@ class CDAE(DeepRecommenderABC):
                                           "stream is sequential over the global batch)")
         else:
             self._sampler.sample_arrays(batch_size, out=(slot['uid_np'], slot['iid'], slot['val']))
+        _lib.check(lib.drb_batch_offsets(_lib.np_ptr(slot['uid_np']), batch_size, _lib.np_ptr(self._h_indptr),
+                                         _lib.np_ptr(slot['off_np'])))
         if self.rng_mode == 'mt19937':
+            self._ensure_keep(slot, int(slot['off_np'][batch_size]))
             _lib.check(lib.drb_cdae_corruption_keep_mt(
                 self._mask_rng.handle, _lib.np_ptr(slot['uid_np']), batch_size, self.n_items,
                 float(self.corruption_level), _lib.np_ptr(self._h_indptr), _lib.np_ptr(self._h_indices),
-                _lib.np_ptr(slot['off_np']), _lib.np_ptr(slot['keep_np'])))
+                _lib.np_ptr(slot['off_np']), _lib.np_ptr(slot['keep_np']), len(slot['keep_np'])))
             return _lib.np_ptr(slot['keep_np'])
-        _lib.check(lib.drb_batch_offsets(_lib.np_ptr(slot['uid_np']), batch_size, _lib.np_ptr(self._h_indptr),
-                                         _lib.np_ptr(slot['off_np'])))
         return None
+
+    def _ensure_keep(self, slot, nnz):
+        """The pinned keep buffer of a staging slot holds one byte per positive of the batch; grow it when a batch
+        (users repeat: sampling is with replacement) holds more than any batch so far."""
+        if nnz <= len(slot['keep_np']):
+            return
+        if slot['event'] is not None:
+            slot['event'].synchronize()               # an H2D copy out of the old buffer may still be in flight
+        slot['keep'] = self._torch.empty(int(nnz * 1.25) + 4096, dtype=self._torch.uint8).pin_memory()
+        slot['keep_np'] = slot['keep'].numpy()
 
     def _acquire_slot(self):
         slot = self._slots[self._slot_idx]
@@ -445,8 +458,6 @@ class CDAE(DeepRecommenderABC):
         torch = self._torch
         with self._lock:
             n, max_c = cand.shape
-            if max_c > 4096:
-                return self._rank_batch_dense(uids, cand, cand_count, novelty)
             d_u = torch.as_tensor(np.ascontiguousarray(uids, np.int32), device=self._dev)
             d_c = torch.as_tensor(np.ascontiguousarray(cand, np.int32), device=self._dev)
             d_n = torch.as_tensor(np.ascontiguousarray(cand_count, np.int32), device=self._dev)
@@ -457,33 +468,6 @@ class CDAE(DeepRecommenderABC):
                                                             _lib.t_ptr(d_n), max_c, int(bool(novelty)),
                                                             _lib.t_ptr(o_i), _lib.t_ptr(o_s), _lib.t_ptr(o_n)))
             return o_i.cpu().numpy(), o_s.cpu().numpy(), o_n.cpu().numpy()
-
-    def _rank_batch_dense(self, uids, cand, cand_count, novelty):
-        """Candidate lists longer than the in-CTA sorter handles (e.g. recommend(n=None) over the whole catalog):
-        dense scores from drb_cdae_predict_all, then a device-side sort of the same 64-bit (orderable(score), iid)
-        keys the ranking kernels use, so the (score desc, iid desc) order is identical."""
-        torch = self._torch
-        n, max_c = cand.shape
-        o_i = np.zeros((n, max_c), np.int32)
-        o_s = np.zeros((n, max_c), np.float32)
-        o_n = np.zeros(n, np.int32)
-        seen_indptr, seen_indices = self._d_seen_indptr, self._d_seen_indices
-        for r in range(n):
-            u = torch.tensor([int(uids[r])], dtype=torch.int32, device=self._dev)
-            scores = torch.empty(self._L.items_pad, dtype=torch.float32, device=self._dev)
-            _lib.check(_lib.load().drb_cdae_predict_all(self._native, _lib.t_ptr(u), 1, _lib.t_ptr(scores)))
-            c = torch.as_tensor(np.ascontiguousarray(cand[r, :cand_count[r]], np.int64), device=self._dev)
-            c = torch.unique(c[c >= 0])
-            if novelty:
-                lo, hi = int(seen_indptr[int(uids[r])]), int(seen_indptr[int(uids[r]) + 1])
-                c = c[~torch.isin(c, seen_indices[lo:hi].long())]
-            bits = scores[c].view(torch.int32).long()
-            ordv = torch.where(bits < 0, (~bits) & 0xFFFFFFFF, (bits & 0xFFFFFFFF) | 0x80000000)
-            order = torch.argsort(((ordv - 0x80000000) << 32) + c, descending=True)   # signed (ord, iid) key
-            c = c[order]
-            k = c.numel()
-            o_i[r, :k], o_s[r, :k], o_n[r] = c.cpu().numpy(), scores[c].cpu().numpy(), k
-        return o_i, o_s, o_n
 
     def topk_batch(self, uids, k, novelty=True, return_device=False):
         """Full-catalog top-k for many users: (iids [n,k], scores [n,k], n_out [n])."""

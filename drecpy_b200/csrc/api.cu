@@ -600,10 +600,19 @@ int drb_cdae_predict_all(drb_cdae* m, const int32_t* uids, int32_t n, float* out
 int drb_cdae_rank_candidates(drb_cdae* m, const int32_t* uids, int32_t n, const int32_t* cand,
                              const int32_t* cand_count, int32_t max_cand, int32_t novelty, int32_t* out_iid,
                              float* out_score, int32_t* n_out) {
-  if (!m || !uids || !cand || !cand_count || !out_iid || !out_score || !n_out || n < 0)
+  if (!m || !uids || !cand || !cand_count || !out_iid || !out_score || !n_out || n < 0 || max_cand < 1)
     return drb_fail(DRB_E_INVALID, "drb_cdae_rank_candidates: bad argument");
-  for (int32_t o = 0; o < n; o += m->d.max_batch) {
-    const int c = std::min(m->d.max_batch, n - o);
+  // lists longer than the shared-memory sorter takes (recommend(n=None): the whole catalog) sort their keys in the
+  // dz workspace, as many users per launch as fit there
+  void* scratch = m->ws.dz;
+  const int64_t scratch_bytes = (int64_t)m->d.max_batch * m->L.items_pad * 4;
+  int64_t per = m->d.max_batch;
+  if (max_cand > 4096) {
+    per = std::min<int64_t>(per, rank_scratch_rows(scratch_bytes, max_cand));
+    if (per < 1) return drb_fail(DRB_E_INVALID, "drb_cdae_rank_candidates: max_cand %d does not fit the workspace", max_cand);
+  }
+  for (int32_t o = 0; o < n; o += (int32_t)per) {
+    const int c = (int)std::min<int64_t>(per, n - o);
     int r = cdae_hidden_into(m, uids + o, c, nullptr, nullptr, 1.0f, m->ws.h);
     if (r) return r;
     CandScoreArgs a{};
@@ -612,7 +621,7 @@ int drb_cdae_rank_candidates(drb_cdae* m, const int32_t* uids, int32_t n, const 
     a.uids = uids + o; a.cand = cand + (int64_t)o * max_cand; a.cand_count = cand_count + o; a.max_cand = max_cand;
     a.seen_indptr = m->d.seen_indptr; a.seen_indices = m->d.seen_indices; a.novelty = novelty;
     a.out_iid = out_iid + (int64_t)o * max_cand; a.out_score = out_score + (int64_t)o * max_cand; a.n_out = n_out + o;
-    if ((r = launch_rank_candidates(m->ctx, a, c))) return r;
+    if ((r = launch_rank_candidates(m->ctx, a, c, scratch, scratch_bytes))) return r;
   }
   return DRB_OK;
 }
@@ -653,6 +662,8 @@ struct drb_dmf {
   DmfTower tw[2];  // 0 = user tower (rows over items), 1 = item tower (rows over users)
   float *col_part, *loss_part, *reg_part, *loss_scalar, *labels, *p_tmp, *item_rep, *user_rep;
   int32_t *uids, *iids;
+  void* rank_scratch; int64_t rank_scratch_bytes;   // sort keys of candidate lists longer than 4096 (score.cu)
+  bool item_rep_valid;                               // item_rep holds the item tower of the CURRENT weights
   int64_t ws_bytes;
   // CUDA-graph replay of the training step (the C2 step is ~20 launches of a few microseconds each: launch bound).
   // One instantiated graph per distinct argument set; the Adam step sizes -- the only per-step scalars -- are read
@@ -721,6 +732,12 @@ static int64_t dmf_carve(drb_dmf* m, void* base, const drb_dmf_layout_t& L, int 
   float* urep = c.take<float>(B * ldl);
   int32_t* u = c.take<int32_t>(B);
   int32_t* i = c.take<int32_t>(B);
+  // key scratch for catalog-long candidate lists: 8 users x next_pow2(n_items) 64-bit keys
+  int64_t p2 = 32;
+  while (p2 < n_items) p2 <<= 1;
+  const int64_t rs_bytes = 8 * p2 * 8;
+  void* rs = c.take<uint8_t>(rs_bytes);
+  if (m) { m->rank_scratch = rs; m->rank_scratch_bytes = rs_bytes; }
   if (m) {
     m->col_part = col; m->loss_part = lp; m->reg_part = rp; m->loss_scalar = ls; m->labels = lab; m->p_tmp = pt;
     m->item_rep = irep; m->user_rep = urep; m->uids = u; m->iids = i;
@@ -898,6 +915,7 @@ int drb_dmf_step(drb_dmf* m, const int32_t* uids, const int32_t* iids, const flo
     return drb_fail(DRB_E_STATE, "drb_dmf_step: model was created without optimizer arenas");
   drb_ctx* ctx = m->ctx;
   if (ctx->sticky) return drb_fail(DRB_E_CUDA, "context has a sticky CUDA error (%d)", ctx->sticky);
+  m->item_rep_valid = false;           // the weights are about to change
   if (m->graph_off || ctx->profile)    // per-kernel profiling brackets every launch with events: direct launches
     return dmf_step_body(m, uids, iids, labels, batch, a, loss_out, nullptr);
 
@@ -1002,22 +1020,31 @@ int drb_dmf_forward_pairs(drb_dmf* m, const int32_t* uids, const int32_t* iids, 
 int drb_dmf_rank_candidates(drb_dmf* m, const int32_t* uids, int32_t n, const int32_t* cand,
                             const int32_t* cand_count, int32_t max_cand, int32_t novelty, int32_t* out_iid,
                             float* out_score, int32_t* n_out) {
-  if (!m || !uids || !cand || !cand_count || !out_iid || !out_score || !n_out || n < 0)
+  if (!m || !uids || !cand || !cand_count || !out_iid || !out_score || !n_out || n < 0 || max_cand < 1)
     return drb_fail(DRB_E_INVALID, "drb_dmf_rank_candidates: bad argument");
   drb_ctx* ctx = m->ctx;
   const int lu = m->tw[0].n_layers - 1, li = m->tw[1].n_layers - 1;
   const int ldl = m->tw[1].ld[li];
-  // item tower once for every item of the catalog (the weights are fixed during scoring), chunk by chunk
+  // item tower once for every item of the catalog, chunk by chunk; the representations stay valid until the next
+  // training step or drb_dmf_invalidate_cache (a single-user rank() no longer recomputes the whole catalog)
   int r;
-  for (int32_t o = 0; o < m->d.n_items; o += m->d.max_batch) {
-    const int c = std::min(m->d.max_batch, m->d.n_items - o);
-    if ((r = launch_iota(ctx, m->iids, c, o))) return r;
-    if ((r = dmf_tower_fwd(m, 1, m->iids, c))) return r;
-    DRB_CUDA_TRY(ctx, cudaMemcpyAsync(m->item_rep + (int64_t)o * ldl, m->tw[1].act[li], (size_t)c * ldl * 4,
-                                      cudaMemcpyDeviceToDevice, ctx->stream));
+  if (!m->item_rep_valid) {
+    for (int32_t o = 0; o < m->d.n_items; o += m->d.max_batch) {
+      const int c = std::min(m->d.max_batch, m->d.n_items - o);
+      if ((r = launch_iota(ctx, m->iids, c, o))) return r;
+      if ((r = dmf_tower_fwd(m, 1, m->iids, c))) return r;
+      DRB_CUDA_TRY(ctx, cudaMemcpyAsync(m->item_rep + (int64_t)o * ldl, m->tw[1].act[li], (size_t)c * ldl * 4,
+                                        cudaMemcpyDeviceToDevice, ctx->stream));
+    }
+    m->item_rep_valid = true;
   }
-  for (int32_t o = 0; o < n; o += m->d.max_batch) {
-    const int c = std::min(m->d.max_batch, n - o);
+  int64_t per = m->d.max_batch;
+  if (max_cand > 4096) {
+    per = std::min<int64_t>(per, rank_scratch_rows(m->rank_scratch_bytes, max_cand));
+    if (per < 1) return drb_fail(DRB_E_INVALID, "drb_dmf_rank_candidates: max_cand %d exceeds the catalog-sized key scratch", max_cand);
+  }
+  for (int32_t o = 0; o < n; o += (int32_t)per) {
+    const int c = (int)std::min<int64_t>(per, n - o);
     if ((r = dmf_tower_fwd(m, 0, uids + o, c))) return r;
     CandScoreArgs a{};
     a.urep = m->tw[0].act[lu]; a.ld_u = m->tw[0].ld[lu]; a.table = m->item_rep; a.ld_t = ldl; a.bias = nullptr;
@@ -1025,8 +1052,14 @@ int drb_dmf_rank_candidates(drb_dmf* m, const int32_t* uids, int32_t n, const in
     a.uids = uids + o; a.cand = cand + (int64_t)o * max_cand; a.cand_count = cand_count + o; a.max_cand = max_cand;
     a.seen_indptr = m->d.csr_indptr; a.seen_indices = m->d.csr_indices; a.novelty = novelty;
     a.out_iid = out_iid + (int64_t)o * max_cand; a.out_score = out_score + (int64_t)o * max_cand; a.n_out = n_out + o;
-    if ((r = launch_rank_candidates(ctx, a, c))) return r;
+    if ((r = launch_rank_candidates(ctx, a, c, m->rank_scratch, m->rank_scratch_bytes))) return r;
   }
+  return DRB_OK;
+}
+
+int drb_dmf_invalidate_cache(drb_dmf* m) {
+  if (!m) return drb_fail(DRB_E_INVALID, "drb_dmf_invalidate_cache: NULL argument");
+  m->item_rep_valid = false;
   return DRB_OK;
 }
 

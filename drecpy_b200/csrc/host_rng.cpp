@@ -268,11 +268,16 @@ int drb_batch_offsets(const int32_t* uids, int32_t batch, const int64_t* csr_ind
 
 int drb_cdae_corruption_keep_mt(drb_rng* rng, const int32_t* uids, int32_t batch, int32_t n_items, double q,
                                 const int64_t* csr_indptr, const int32_t* csr_indices, int32_t* keep_off,
-                                uint8_t* keep) {
-  if (!rng || !uids || !csr_indptr || !csr_indices || !keep_off || batch < 0 || n_items <= 0)
+                                uint8_t* keep, int64_t keep_capacity) {
+  if (!rng || !uids || !csr_indptr || !csr_indices || !keep_off || !keep || batch < 0 || n_items <= 0)
     return drb_fail(DRB_E_INVALID, "drb_cdae_corruption_keep_mt: bad argument");
   int r = drb_batch_offsets(uids, batch, csr_indptr, keep_off);
   if (r) return r;
+  // users are sampled with replacement, so a batch can hold more positives than any set of distinct users: the
+  // caller states how much room `keep` has and nothing is written (and no draw consumed) when it is too small
+  if ((int64_t)keep_off[batch] > keep_capacity)
+    return drb_fail(DRB_E_INVALID, "drb_cdae_corruption_keep_mt: batch holds %lld positives, keep has room for %lld",
+                    (long long)keep_off[batch], (long long)keep_capacity);
   for (int32_t b = 0; b < batch; b++) {
     // cdae.py:63-64: draw i of this user decides item i; every draw is rng.uniform(0,1) = two MT outputs.
     const int64_t lo = csr_indptr[uids[b]], hi = csr_indptr[uids[b] + 1];

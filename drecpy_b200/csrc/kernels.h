@@ -161,7 +161,10 @@ struct CandScoreArgs {
   const int64_t* seen_indptr; const int32_t* seen_indices; int novelty;
   int32_t* out_iid; float* out_score; int32_t* n_out;     // [n, max_cand], [n]
 };
-int launch_rank_candidates(drb_ctx* ctx, const CandScoreArgs& a, int n);
+// max_cand <= 4096: keys sorted in shared memory.  Longer lists (up to the whole catalog) sort in `scratch`
+// (next_pow2(max_cand) 64-bit keys per user); rank_scratch_rows = users one call can take with that much scratch
+int launch_rank_candidates(drb_ctx* ctx, const CandScoreArgs& a, int n, void* scratch = nullptr, int64_t scratch_bytes = 0);
+int64_t rank_scratch_rows(int64_t scratch_bytes, int max_cand);
 
 struct TopkArgs {
   const float* scores; int ld; int n_items;   // [n, ld]

@@ -70,8 +70,13 @@ __device__ void emit_sorted(const uint64_t* keys, int P, int limit, int32_t* out
   if (lane == 0) *n_out = min(running, limit);
 }
 
-__global__ void __launch_bounds__(128) k_rank_candidates(CandScoreArgs a, int P) {
-  extern __shared__ uint64_t keys[];  // [P]
+// keys_global == NULL: the P keys of a user live in shared memory (P <= 4096, 128 threads); otherwise in the caller's
+// scratch row keys_global[blockIdx.x * P ..) and the same bitonic network runs on global memory with 1024 threads
+// (candidate lists as long as the catalog: recommend(n=None), recommender_abc.py:391-419)
+__global__ void __launch_bounds__(1024) k_rank_candidates(CandScoreArgs a, int P, uint64_t* keys_global) {
+  extern __shared__ uint64_t keys_smem[];  // [P] when keys_global == NULL
+  uint64_t* keys = keys_global ? keys_global + (int64_t)blockIdx.x * P : keys_smem;
+  const int nwarps = blockDim.x >> 5;
   const int u = blockIdx.x;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int uid = a.uids[u];
@@ -90,7 +95,7 @@ __global__ void __launch_bounds__(128) k_rank_candidates(CandScoreArgs a, int P)
     for (int k = lane; k < a.width; k += 32) uss = fmaf(ur[k], ur[k], uss);
     uss = warp_sum(uss);
   }
-  for (int c = warp; c < cnt; c += 4) {
+  for (int c = warp; c < cnt; c += nwarps) {
     const int iid = a.cand[(int64_t)u * a.max_cand + c];
     if (iid < 0) continue;                                       // unknown raw item (skip_invalid_items)
     if (a.novelty && row_contains(seen, nseen, iid)) continue;   // warp-uniform
@@ -229,12 +234,23 @@ int next_pow2(int x) {
 
 }  // namespace
 
-int launch_rank_candidates(drb_ctx* ctx, const CandScoreArgs& a, int n) {
+int64_t rank_scratch_rows(int64_t scratch_bytes, int max_cand) {
+  return scratch_bytes / ((int64_t)next_pow2(max_cand) * (int64_t)sizeof(uint64_t));
+}
+
+int launch_rank_candidates(drb_ctx* ctx, const CandScoreArgs& a, int n, void* scratch, int64_t scratch_bytes) {
   if (n <= 0) return DRB_OK;
-  if (a.max_cand < 1 || a.max_cand > 4096) return drb_fail(DRB_E_INVALID, "rank_candidates: max_cand must be in [1, 4096]");
+  if (a.max_cand < 1) return drb_fail(DRB_E_INVALID, "rank_candidates: max_cand must be >= 1");
   const int P = next_pow2(a.max_cand);
   drb_prof_scope prof_(ctx, "k_rank_candidates");
-  k_rank_candidates<<<n, 128, (size_t)P * sizeof(uint64_t), ctx->stream>>>(a, P);
+  if (a.max_cand <= 4096) {
+    k_rank_candidates<<<n, 128, (size_t)P * sizeof(uint64_t), ctx->stream>>>(a, P, nullptr);
+  } else {
+    if (!scratch || rank_scratch_rows(scratch_bytes, a.max_cand) < n)
+      return drb_fail(DRB_E_INVALID, "rank_candidates: %d lists of %d candidates need %lld bytes of key scratch", n,
+                      a.max_cand, (long long)n * P * 8);
+    k_rank_candidates<<<n, 1024, 0, ctx->stream>>>(a, P, static_cast<uint64_t*>(scratch));
+  }
   DRB_LAUNCH_CHECK(ctx, "k_rank_candidates");
   return DRB_OK;
 }

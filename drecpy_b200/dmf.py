@@ -254,7 +254,11 @@ class DMF(DeepRecommenderABC):
         torch = self._torch
         with self._lock:
             n, max_c = cand.shape
-            assert max_c <= 4096, 'DMF candidate lists longer than 4096 are not supported yet'
+            # the library caches the item tower of the whole catalog between steps; in-place writes to the arena
+            # from Python (weight injection, _revert_weights) bump the tensor version -> tell it
+            if getattr(self, '_params_version', None) != self._params._version:
+                _lib.check(_lib.load().drb_dmf_invalidate_cache(self._native))
+                self._params_version = self._params._version
             d_u = torch.as_tensor(np.ascontiguousarray(uids, np.int32), device=self._dev)
             d_c = torch.as_tensor(np.ascontiguousarray(cand, np.int32), device=self._dev)
             d_n = torch.as_tensor(np.ascontiguousarray(cand_count, np.int32), device=self._dev)

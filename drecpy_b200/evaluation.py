@@ -303,6 +303,10 @@ def ranking_evaluation(model, ds_test=None, n_test_users=None, k=10, n_pos_inter
             model, data, users, t_indptr, t_order, interaction_threshold, n_pos_interactions, n_neg_interactions,
             generate_negative_pairs, train_evaluation, seed)
         active = np.flatnonzero(skipped == 0)
+        if len(active) and hasattr(model, '_data'):
+            # model.rank asserts the user is known; the reference logs that failure and skips the user
+            # (ranking_evaluation.py:222 inside the per-user try) -- same filter as the vectorised path
+            active = active[model._data.users_to_uids(users[active]) >= 0]
         cand_lists = [cand[cand_off[u]:cand_off[u + 1]] for u in active]
         pos_lists = [pos[pos_off[u]:pos_off[u + 1]].tolist() for u in active]
         rows = [(t_item[t_indptr[u]:t_indptr[u + 1]], t_val[t_indptr[u]:t_indptr[u + 1]]) for u in active]

@@ -79,7 +79,7 @@ class DeepRecommenderABC(ABC):
         self.n_items = self._data.count_unique('iid')
         self.n_rows = len(self._data)
 
-        self._loss_tracker = LossTracker()
+        self._loss_tracker = kwds.get('loss_tracker') or LossTracker()
         self._log_initial_info()
         self._info('Creating auxiliary structures...')
 
@@ -137,6 +137,8 @@ class DeepRecommenderABC(ABC):
                     epoch_callback_res_registered = True
 
             if early_stopping_rule is not None and e % early_stopping_freq == 0:
+                if e not in self.epoch_weights:
+                    self._store_epoch_weights(e)           # a rule may name any epoch it was evaluated on
                 try:
                     early_stopping_best_epoch = early_stopping_rule.compute(
                         self._loss_tracker.epoch_losses, self._loss_tracker.epoch_callback_results,
@@ -198,9 +200,15 @@ class DeepRecommenderABC(ABC):
         self.epoch_weights[epoch] = p.detach().clone() if p.numel() < (1 << 27) else p.detach().cpu()
 
     def _revert_weights(self, epoch):
-        if epoch == 0 or epoch not in self.epoch_weights:
+        if epoch == 0 or epoch == self._step:
             # reference: epoch_weights[0 - 1] == the last step's weights, i.e. a no-op revert
             self._info(f'Network weights reverted from epoch {self._step} to epoch {epoch}.')
+            return
+        if epoch not in self.epoch_weights:
+            # snapshots exist on callback / early-stopping epochs only (Q3); a rule that names any other epoch cannot
+            # be honoured -- say so instead of claiming a revert
+            self._logger.warning(f'No weight snapshot for epoch {epoch} (snapshots: {sorted(self.epoch_weights)}); '
+                                 f'network weights stay at epoch {self._step}.')
             return
         p = self._params_tensor()
         p.copy_(self.epoch_weights[epoch].to(p.device))
@@ -264,8 +272,10 @@ class DeepRecommenderABC(ABC):
         return [(out_s[0, j], int(out_i[0, j])) for j in range(k)]
 
     def rank_batch(self, user_ids, item_id_lists, novelty=True):
-        """Batched rank() over raw ids: returns one ranked raw-item list per user (invalid items skipped)."""
-        uids = np.array([self._data.user_to_uid(u) for u in user_ids], np.int32)
+        """Batched rank() over raw ids: returns one ranked raw-item list per user (invalid items skipped).  A user
+        the model was not trained on gets an empty list (rank() would assert; per-user callers skip such users)."""
+        uids = self._data.users_to_uids(np.asarray(user_ids)).astype(np.int32)
+        known = uids >= 0
         lens = [len(x) for x in item_id_lists]
         flat = np.concatenate([np.asarray(x) for x in item_id_lists]) if sum(lens) else np.zeros(0, np.int64)
         iids = self._data.items_to_iids(flat)
@@ -277,9 +287,9 @@ class DeepRecommenderABC(ABC):
             v = iids[o:o + ln]
             v = v[v >= 0]
             cand[r, :len(v)] = v
-            cnt[r] = len(v)
+            cnt[r] = len(v) if known[r] else 0
             o += ln
-        out_i, out_s, n_out = self._rank_batch(uids, cand, cnt, novelty)
+        out_i, out_s, n_out = self._rank_batch(np.where(known, uids, 0).astype(np.int32), cand, cnt, novelty)
         items = self._data.raw_items
         return [items[out_i[r, :n_out[r]]].tolist() for r in range(len(uids))], out_s, n_out
 

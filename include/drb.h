@@ -110,7 +110,8 @@ int drb_sampler_setstate(drb_sampler* s, const uint32_t state[3 * 625]);
  * column-sorted, host copy). */
 int drb_cdae_corruption_keep_mt(drb_rng* rng, const int32_t* uids, int32_t batch, int32_t n_items, double q,
                                 const int64_t* csr_indptr, const int32_t* csr_indices,
-                                int32_t* keep_off /* [batch+1] */, uint8_t* keep /* [sum deg] */);
+                                int32_t* keep_off /* [batch+1] */, uint8_t* keep /* [sum deg] */,
+                                int64_t keep_capacity /* bytes available in keep; DRB_E_INVALID if too small */);
 /* keep_off only (prefix of the sampled users' degrees), for the counter-based (philox) mask mode */
 int drb_batch_offsets(const int32_t* uids, int32_t batch, const int64_t* csr_indptr, int32_t* keep_off);
 
@@ -283,6 +284,9 @@ int drb_dmf_forward_pairs(drb_dmf* m, const int32_t* uids, const int32_t* iids, 
 int drb_dmf_rank_candidates(drb_dmf* m, const int32_t* uids, int32_t n, const int32_t* cand,
                             const int32_t* cand_count, int32_t max_cand, int32_t novelty,
                             int32_t* out_iid, float* out_score, int32_t* n_out);
+/* drb_dmf_rank_candidates keeps the item tower's output for the whole catalog until the next drb_dmf_step; a caller
+ * that writes the parameter arena itself (weight injection, _revert_weights: recommender_abc.py:346-352) says so. */
+int drb_dmf_invalidate_cache(drb_dmf* m);
 
 /* ------------------------------------------------------------------ kernel-level test hooks (tests/ only)
  * The tcgen05 GEMM building blocks of the CDAE step, exposed so that tests can check them in isolation against

@@ -111,13 +111,39 @@ def test_corruption_mask_matches_python_stream():
     keep = np.zeros(int(np.diff(indptr).max()) * len(uids), np.uint8)
     _lib.check(_lib.load().drb_cdae_corruption_keep_mt(rng.handle, _lib.np_ptr(uids), len(uids), 97, 0.2,
                                                        _lib.np_ptr(indptr), _lib.np_ptr(indices), _lib.np_ptr(off),
-                                                       _lib.np_ptr(keep)))
+                                                       _lib.np_ptr(keep), len(keep)))
     pr = random.Random(10)
     for b, uid in enumerate(uids):
         dense = corruption_keep_mt(pr, 97, 0.2)
         items = indices[indptr[uid]:indptr[uid + 1]]
         assert np.array_equal(keep[off[b]:off[b + 1]].astype(bool), dense[items])
     assert rng.random() == pr.random()          # both streams consumed exactly len(uids) * n_items draws
+
+
+def test_corruption_mask_refuses_a_short_keep_buffer():
+    """Users repeat inside a batch (sampling is with replacement), so batch nnz is not bounded by any set of distinct
+    users: the native replay takes the buffer capacity, fails without writing and without consuming draws."""
+    u, i, v = drb.synthetic_interactions(20, 50, 400, seed=3)
+    ds = drb.InteractionData(u, i, v)
+    ds.assign_internal_ids()
+    indptr, indices, _ = ds.csr(0.001)
+    heavy = int(np.argmax(np.diff(indptr)))
+    uids = np.full(64, heavy, np.int32)                      # batch_size > n_users, one user repeated
+    nnz = int(np.diff(indptr)[heavy]) * len(uids)
+    assert nnz > int(np.diff(indptr).sum())                  # more than the whole dataset holds
+    rng = _lib.HostRng(10)
+    off = np.zeros(len(uids) + 1, np.int32)
+    guard = np.full(nnz + 64, 0xAB, np.uint8)
+    rc = _lib.load().drb_cdae_corruption_keep_mt(rng.handle, _lib.np_ptr(uids), len(uids), 50, 0.2,
+                                                 _lib.np_ptr(indptr), _lib.np_ptr(indices), _lib.np_ptr(off),
+                                                 _lib.np_ptr(guard), nnz - 1)
+    assert rc == -1 and b'room for' in _lib.load().drb_last_error()
+    assert (guard == 0xAB).all() and rng.random() == random.Random(10).random()
+    rng = _lib.HostRng(10)
+    _lib.check(_lib.load().drb_cdae_corruption_keep_mt(rng.handle, _lib.np_ptr(uids), len(uids), 50, 0.2,
+                                                       _lib.np_ptr(indptr), _lib.np_ptr(indices), _lib.np_ptr(off),
+                                                       _lib.np_ptr(guard), nnz))
+    assert off[-1] == nnz and (guard[nnz:] == 0xAB).all() and set(np.unique(guard[:nnz])) <= {0, 1}
 
 
 class FakeModel:
