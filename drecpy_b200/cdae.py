@@ -454,19 +454,28 @@ class CDAE(DeepRecommenderABC):
                 _lib.check(_lib.load().drb_cdae_hidden(self._native, _lib.t_ptr(u[o:]), n, _lib.t_ptr(out[o:])))
             return out[:, :self.hidden_factors].cpu().numpy()
 
-    def _rank_batch(self, uids, cand, cand_count, novelty):
+    def rank_candidates_device(self, d_u, d_c, d_n, novelty, out=None):
+        """drb_cdae_rank_candidates on device tensors: uids [n] int32, cand [n, max_c] int32 internal ids, counts [n].
+        Returns device tensors (iids [n, max_c], scores [n, max_c], n_out [n]); `out` reuses a previous result."""
         torch = self._torch
+        n, max_c = d_c.shape
         with self._lock:
-            n, max_c = cand.shape
-            d_u = torch.as_tensor(np.ascontiguousarray(uids, np.int32), device=self._dev)
-            d_c = torch.as_tensor(np.ascontiguousarray(cand, np.int32), device=self._dev)
-            d_n = torch.as_tensor(np.ascontiguousarray(cand_count, np.int32), device=self._dev)
-            o_i = torch.empty((n, max_c), dtype=torch.int32, device=self._dev)
-            o_s = torch.empty((n, max_c), dtype=torch.float32, device=self._dev)
-            o_n = torch.empty(n, dtype=torch.int32, device=self._dev)
+            o_i, o_s, o_n = out if out is not None else (
+                torch.empty((n, max_c), dtype=torch.int32, device=self._dev),
+                torch.empty((n, max_c), dtype=torch.float32, device=self._dev),
+                torch.empty(n, dtype=torch.int32, device=self._dev))
             _lib.check(_lib.load().drb_cdae_rank_candidates(self._native, _lib.t_ptr(d_u), n, _lib.t_ptr(d_c),
                                                             _lib.t_ptr(d_n), max_c, int(bool(novelty)),
                                                             _lib.t_ptr(o_i), _lib.t_ptr(o_s), _lib.t_ptr(o_n)))
+        return o_i, o_s, o_n
+
+    def _rank_batch(self, uids, cand, cand_count, novelty):
+        torch = self._torch
+        with self._lock:
+            d_u = torch.as_tensor(np.ascontiguousarray(uids, np.int32), device=self._dev)
+            d_c = torch.as_tensor(np.ascontiguousarray(cand, np.int32), device=self._dev)
+            d_n = torch.as_tensor(np.ascontiguousarray(cand_count, np.int32), device=self._dev)
+            o_i, o_s, o_n = self.rank_candidates_device(d_u, d_c, d_n, novelty)
             return o_i.cpu().numpy(), o_s.cpu().numpy(), o_n.cpu().numpy()
 
     def topk_batch(self, uids, k, novelty=True, return_device=False):

@@ -173,6 +173,7 @@ struct drb_cdae {
   bool v_grad_clean;   // the dV region of the gradient arena is known to be all zero
   int n_loss_blocks;
   int n2, batch_pad;   // tcgen05 path: N of the backward GEMMs (hidden + ones feature, rounded to 16), padded batch
+  float* z_dbg;        // tests only: drb_debug_cdae_capture_logits
 };
 
 // N of the backward GEMMs: hidden plus the constant-one feature that folds db' = colsum(dz) into dW'^T, rounded to 16.
@@ -283,6 +284,7 @@ int drb_cdae_create(drb_ctx* ctx, const drb_cdae_desc* desc, drb_cdae** out) {
   }
   m->use_umma = umma_ok && desc->gemm_path != DRB_GEMM_FFMA;
   m->v_grad_clean = false;
+  m->z_dbg = nullptr;
   if (m->use_umma) {
     // dh = dz W'^T on the tensor cores has one 128 x n2 tile per 128 users: split the item range so that the grid
     // is ~2 waves of the SM count (the kernel is L2/HBM bandwidth bound, one CTA per SM)
@@ -356,6 +358,13 @@ int drb_cdae_dz1_buffer(drb_cdae* m, float** ptr, int64_t* count) {
 int drb_cdae_scatter_user_rows(drb_cdae* m, const int32_t* uids, const float* rows, int32_t n) {
   if (!m || !uids || !rows || n < 0) return drb_fail(DRB_E_INVALID, "drb_cdae_scatter_user_rows: bad argument");
   return launch_row_scatter(m->ctx, uids, rows, n, m->L.ld, m->d.grads + m->L.off_v);
+}
+
+int drb_debug_cdae_capture_logits(drb_cdae* m, float* z_out) {
+  if (!m) return drb_fail(DRB_E_INVALID, "drb_debug_cdae_capture_logits: NULL argument");
+  if (z_out && !m->use_umma) return drb_fail(DRB_E_STATE, "drb_debug_cdae_capture_logits: the model runs the FFMA path");
+  m->z_dbg = z_out;
+  return DRB_OK;
 }
 
 int drb_cdae_label_count_buffer(drb_cdae* m, float** ptr, int64_t* count) {
@@ -452,7 +461,8 @@ int drb_cdae_step_phases(drb_cdae* m, const int32_t* uids, const int32_t* keep_o
     if ((r = launch_umma_cdae_loss(ctx, o1, batch, I, ld, w.dzt_hi, w.dzt_lo, L.items_pad, P + L.off_b2,
                                    per_user ? nullptr : w.label_count, per_user ? w.label_bits : nullptr,
                                    m->words_per_row, m->d.loss_kind, inv_count, gbatch, w.loss_part,
-                                   cdae_colsum_in_loss(m->d.hidden) ? G + L.off_b2 : nullptr, &n_blocks)))
+                                   cdae_colsum_in_loss(m->d.hidden) ? G + L.off_b2 : nullptr, &n_blocks, m->z_dbg,
+                                   L.items_pad)))
       return r;
     // dW'^T = dz^T h (I x K); the constant-one feature at column `hidden` yields db' = colsum(dz)
     // e.g. 209 item tiles on 148 SMs would run as two uneven waves: split the batch reduction so the grid is ~2 waves

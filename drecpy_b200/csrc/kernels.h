@@ -114,7 +114,8 @@ inline int64_t drb_dz_tiled_floats(int rows, int n_cols) { return (int64_t)((row
 int launch_umma_cdae_loss(drb_ctx* ctx, const UmmaOperands& o, int M, int N, int Kred, float* dz_hi, float* dz_lo,
                           int ldc, const float* bias, const float* label_count, const uint32_t* label_bits,
                           int words_per_row, int loss_kind, float inv_count, int batch, float* loss_part,
-                          float* dz_colsum /* may be NULL: [N] += colsum(dz), i.e. db' */, int* n_blocks_out);
+                          float* dz_colsum /* may be NULL: [N] += colsum(dz), i.e. db' */, int* n_blocks_out,
+                          float* z_dbg = nullptr /* tests: logits as formed by the kernel, [M][ldz] */, int ldz = 0);
 int launch_umma_store(drb_ctx* ctx, const UmmaOperands& o, bool a_mn_major, int M, int N, int Kred, int splits,
                       float* C, int ldc, int n_store, int n_valid, float* extra_col, int extra_col_index,
                       bool atomic_out = false);

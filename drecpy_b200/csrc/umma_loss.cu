@@ -45,6 +45,8 @@ struct LossParams {
   float* loss_part;                        // [gridDim.x]
   float* colsum;                           // NULL, or [N]: db' += column sums of dz (hidden = 241..256: no room for the ones feature)
   int m_tiles, n_tiles, row_tiles;         // item tiles (128), batch tiles (BN), 128-row tiles of the dz layout
+  float* z_dbg; int ldz;                   // tests only (drb_debug_cdae_capture_logits): z2 = h W'^T + b' as this kernel
+                                           // formed it, row-major [M][ldz]; NULL in production
   int debug;   // DRB_LOSS_DEBUG bit mask (profiling experiments only, results are wrong): 1 = first 16-row chunk of
                // each epilogue warp only, 2 = skip TMA + MMA, 4 = skip the dz stores, 8 = skip the B_lo loads, 16 = skip the MMAs
 };
@@ -243,6 +245,7 @@ k_umma_cdae_loss(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
         for (int j = 0; j < 16; j++) {
           const bool ok = item_ok && (row + j < p.M);
           const float z = __uint_as_float(r[j]) + bias;
+          if (p.z_dbg && ok) p.z_dbg[(int64_t)(row + j) * p.ldz + item] = z;
           const float pr = fast_rcp(1.0f + fast_ex2(z * -1.4426950408889634f));
           float tgt = tgt_c;
           if (PER_USER) {   // one broadcast word per batch row: bit `lane` of word ib
@@ -375,8 +378,9 @@ int run_loss(drb_ctx* ctx, const UmmaOperands& o, LossParams p, int* n_blocks_ou
 int launch_umma_cdae_loss(drb_ctx* ctx, const UmmaOperands& o, int M, int N, int Kred, float* dz_hi, float* dz_lo,
                           int ldc, const float* bias, const float* label_count, const uint32_t* label_bits,
                           int words_per_row, int loss_kind, float inv_count, int batch, float* loss_part,
-                          float* dz_colsum, int* n_blocks_out) {
+                          float* dz_colsum, int* n_blocks_out, float* z_dbg, int ldz) {
   LossParams p{};
+  p.z_dbg = z_dbg; p.ldz = ldz;
   p.M = M; p.N = N; p.Kred = Kred; p.nib = drb_dz_nib(N); p.dz_hi = dz_hi; p.dz_lo = dz_lo; p.bias = bias;
   (void)ldc;
   p.label_count = label_count; p.label_bits = label_bits; p.words_per_row = words_per_row; p.loss_kind = loss_kind;

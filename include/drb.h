@@ -297,6 +297,10 @@ int drb_dmf_invalidate_cache(drb_dmf* m);
  * contiguous); != 0: A stored [Kred][lda] (m contiguous).  B stored [b_rows][ldb] (k contiguous).  Partial z of a
  * split reduction is written at C + z*M*ldc; columns >= n_store are dropped; column extra_col_index goes to
  * extra_col[m] when extra_col != NULL. */
+/* drb_debug_cdae_capture_logits: while z_out != NULL every following training step also stores the output-layer
+ * logits z2 = h W'^T + b' (cdae.py:76 before the sigmoid) exactly as the tcgen05 loss kernel formed them, row-major
+ * [batch][items_pad] floats at z_out (device).  NULL switches the capture off.  Only the tensor-core path. */
+int drb_debug_cdae_capture_logits(drb_cdae* m, float* z_out);
 int drb_debug_split_tf32(drb_ctx* ctx, const float* src, int32_t rows, int32_t cols, int32_t ld, float* hi, float* lo,
                          float* t_hi, float* t_lo, int32_t ldt, int32_t ones_row);
 int drb_debug_umma_gemm(drb_ctx* ctx, const float* a_hi, const float* a_lo, int32_t lda, const float* b_hi,

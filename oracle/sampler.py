@@ -54,3 +54,48 @@ class PointSamplerOracle:
             null_pair = self.rng.uniform(0, self.neg_ratio + 1) > 1
             out.append(self.sample_negative() if null_pair else self.sample_positive())
         return out
+
+
+class PointSamplerOracleCSR(PointSamplerOracle):
+    """The same three streams and the same draws as PointSamplerOracle, with array storage instead of a Python set of
+    all (uid, iid) pairs and a dict of row lists, so that it can be built for the 20 M-row shape in seconds (the CPU
+    arm of bench.py samples with it).  Membership of mem_dataset.py:161 = binary search in the user's sorted item
+    list; positives = the user's rows in DataFrame order (mem_dataset.py:119-129)."""
+
+    def __init__(self, uid, iid, val, neg_ratio, interaction_threshold=None, seed=None):
+        uid = np.asarray(uid).astype(np.int64)
+        iid = np.asarray(iid).astype(np.int64)
+        val = np.asarray(val)
+        self.neg_ratio = neg_ratio
+        self.rng = random.Random(seed)
+        self.null_rng = random.Random(seed)
+        self.pos_rng = random.Random(seed)
+        self.max_uid = int(uid.max())
+        self.max_iid = int(iid.max())
+        n_u = self.max_uid + 1
+        order = np.lexsort((iid, uid))                                   # all rows: by user, items ascending
+        self.all_indptr = np.concatenate(([0], np.cumsum(np.bincount(uid, minlength=n_u))))
+        self.all_iid = iid[order]
+        sel = np.arange(len(uid)) if interaction_threshold is None else np.flatnonzero(val >= interaction_threshold)
+        o2 = sel[np.argsort(uid[sel], kind='stable')]                    # filtered rows: by user, DataFrame order kept
+        self.pos_indptr = np.concatenate(([0], np.cumsum(np.bincount(uid[sel], minlength=n_u))))
+        self.pos_iid = iid[o2]
+        self.pos_val = val[o2]
+
+    def sample_negative(self):
+        while True:
+            u = self.null_rng.randint(0, self.max_uid)
+            i = self.null_rng.randint(0, self.max_iid)
+            lo, hi = self.all_indptr[u], self.all_indptr[u + 1]
+            p = lo + np.searchsorted(self.all_iid[lo:hi], i)
+            if p == hi or self.all_iid[p] != i:
+                return u, i, 0
+
+    def sample_positive(self):
+        while True:
+            u = self.pos_rng.randint(0, self.max_uid)
+            lo, hi = int(self.pos_indptr[u]), int(self.pos_indptr[u + 1])
+            if hi == lo:
+                continue
+            j = self.pos_rng.randint(0, hi - lo - 1)
+            return u, int(self.pos_iid[lo + j]), self.pos_val[lo + j]

@@ -11,7 +11,7 @@ import pytest
 
 from oracle import dataset as ods
 from oracle import ranking as orank
-from oracle.sampler import PointSamplerOracle
+from oracle.sampler import PointSamplerOracle, PointSamplerOracleCSR
 
 SAMPLER_CASES = ['small_zero_rows', 'small_dups', 'small_float', 'thr3']
 
@@ -42,9 +42,10 @@ def test_point_sampler_vs_live_reference(golden_dir, name):
             continue
         seed = int(key[len('triples_seed'):])
         want = g[key]
-        s = PointSamplerOracle(g['uid'], g['iid'], g['interaction'], int(g['neg_ratio']), float(g['thr']), seed)
-        got = np.array([[u, i, float(v)] for u, i, v in s.sample(len(want))])
-        assert np.array_equal(got, want), f'{name} seed {seed}'
+        for cls in (PointSamplerOracle, PointSamplerOracleCSR):      # dict / set storage and the array storage
+            s = cls(g['uid'], g['iid'], g['interaction'], int(g['neg_ratio']), float(g['thr']), seed)
+            got = np.array([[u, i, float(v)] for u, i, v in s.sample(len(want))])
+            assert np.array_equal(got, want), f'{name} seed {seed} {cls.__name__}'
 
 
 def test_generators_reference_kats():
