@@ -381,7 +381,7 @@ def test_config4_flow_split_then_evaluate_small():
 
 
 def test_bench_roofline_object_from_committed_kernel_times():
-    """bench.build_roofline is the pure part of the bench line: fed with the kernel times of the committed one-GPU
+    """bench.cdae_roofline is the pure part of the bench line: fed with the kernel times of the committed round-1 one-GPU
     line and the committed ncu traffic table it reproduces that line's roofline numbers."""
     import importlib.util
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -392,14 +392,17 @@ def test_bench_roofline_object_from_committed_kernel_times():
     table = json.load(open(os.path.join(root, 'profiles', 'r1_traffic.json')))['dram_bytes_per_launch']
     peaks = dict(hbm=j['roofline']['secondary']['k_adam']['peak'], tf=j['roofline']['peak'], tf_burst=0.0, src='measured')
     n_params = 2 * 26744 * 200 + 138493 * 200 + 200 + 26744                 # W, W', V, b, b' (ld == hidden == 200)
-    r = bench.build_roofline(j['kernels_ms_per_step'], 200, 26744, 4096, n_params, peaks, table)
+    r = bench.cdae_roofline(j['kernels_ms_per_step'], bench.C3, n_params, peaks, table)
     assert r['bound'] == 'tensor' and r['unit'] == 'TFLOP/s'
     assert abs(r['achieved'] - j['roofline']['achieved']) < 1e-6 * r['achieved']
     assert abs(r['frac'] - r['achieved'] / r['peak']) < 1e-12
     assert r['traffic'] == table['k_umma_cdae_loss'] + table['k_umma_gemm_mn'] + table['k_umma_gemm_kk']
-    assert abs(r['frac_of_cap'] - 6 * r['frac']) < 1e-9 and 0.5 < r['frac_of_cap'] < 1.0
+    assert abs(r['algorithmic_flops_per_step'] - 6.0 * 200 * 26744 * 4096) < 1
     assert 0.8 < r['secondary']['k_adam']['frac'] < 1.0
-    # FFMA path: no tensor-core cap, no traffic
-    r2 = bench.build_roofline({'k_sgemm_kk_loss': 2.5, 'k_sgemm_mn': 1.7, 'k_sgemm_kn': 2.8, 'k_adam': 0.17}, 200, 26744,
-                              4096, n_params, peaks, table)
-    assert r2['cap_3xtf32'] is None and r2['traffic'] is None and r2['achieved'] > 0
+    # FFMA path: no traffic claim
+    r2 = bench.cdae_roofline({'k_sgemm_kk_loss': 2.5, 'k_sgemm_mn': 1.7, 'k_sgemm_kn': 2.8, 'k_adam': 0.17}, bench.C3,
+                             n_params, peaks, table)
+    assert r2['traffic'] is None and r2['achieved'] > 0
+    # every workload has a native and a reference runner
+    for name, cfg in bench.WORKLOADS.items():
+        assert cfg['model'] in bench.RUNNERS and len(bench.RUNNERS[cfg['model']]) == 2, name
