@@ -108,6 +108,7 @@ SIGNATURES = {
     'drb_cdae_hidden': (C.c_int, [vp, vp, i32, vp]),
     'drb_cdae_rank_candidates': (C.c_int, [vp, vp, i32, vp, vp, i32, i32, vp, vp, vp]),
     'drb_cdae_topk': (C.c_int, [vp, vp, i32, i32, i32, vp, vp, vp]),
+    'drb_cdae_topk_exact': (C.c_int, [vp, vp, i32, i32, i32, vp, vp, vp]),
     'drb_cdae_predict_all': (C.c_int, [vp, vp, i32, vp]),
     'drb_dmf_layout': (C.c_int, [i32, i32, vp, i32, vp, i32, P(DmfLayout)]),
     'drb_dmf_workspace_bytes': (i64, [i32, i32, vp, i32, vp, i32, i32]),

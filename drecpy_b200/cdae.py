@@ -478,17 +478,31 @@ class CDAE(DeepRecommenderABC):
             o_i, o_s, o_n = self.rank_candidates_device(d_u, d_c, d_n, novelty)
             return o_i.cpu().numpy(), o_s.cpu().numpy(), o_n.cpu().numpy()
 
-    def topk_batch(self, uids, k, novelty=True, return_device=False):
-        """Full-catalog top-k for many users: (iids [n,k], scores [n,k], n_out [n])."""
+    def topk_batch(self, uids, k, novelty=True, return_device=False, exact=False):
+        """Full-catalog top-k for many users: (iids [n,k], scores [n,k], n_out [n]).  exact=True forces the exact-fp32
+        score rows + radix select instead of the tensor-core path."""
         torch = self._torch
+        lib = _lib.load()
         with self._lock:
             d_u = uids if torch.is_tensor(uids) else torch.as_tensor(np.ascontiguousarray(uids, np.int32), device=self._dev)
             n = d_u.numel()
             o_i = torch.empty((n, k), dtype=torch.int32, device=self._dev)
             o_s = torch.empty((n, k), dtype=torch.float32, device=self._dev)
             o_n = torch.empty(n, dtype=torch.int32, device=self._dev)
-            _lib.check(_lib.load().drb_cdae_topk(self._native, _lib.t_ptr(d_u), n, k, int(bool(novelty)),
-                                                 _lib.t_ptr(o_i), _lib.t_ptr(o_s), _lib.t_ptr(o_n)))
+            fn = lib.drb_cdae_topk_exact if exact else lib.drb_cdae_topk
+            _lib.check(fn(self._native, _lib.t_ptr(d_u), n, k, int(bool(novelty)), _lib.t_ptr(o_i), _lib.t_ptr(o_s),
+                          _lib.t_ptr(o_n)))
+            if not exact and n and int(o_n.min()) < 0:
+                # more candidate lists of one block overflowed than the device-side fallback has rows for (only
+                # possible with adversarial score distributions): those users go through the exact path
+                bad = torch.nonzero(o_n < 0).flatten()
+                b_i = torch.empty((bad.numel(), k), dtype=torch.int32, device=self._dev)
+                b_s = torch.empty((bad.numel(), k), dtype=torch.float32, device=self._dev)
+                b_n = torch.empty(bad.numel(), dtype=torch.int32, device=self._dev)
+                b_u = d_u[bad].contiguous()
+                _lib.check(lib.drb_cdae_topk_exact(self._native, _lib.t_ptr(b_u), bad.numel(), k, int(bool(novelty)),
+                                                   _lib.t_ptr(b_i), _lib.t_ptr(b_s), _lib.t_ptr(b_n)))
+                o_i[bad], o_s[bad], o_n[bad] = b_i, b_s, b_n
             if return_device:
                 return o_i, o_s, o_n
             return o_i.cpu().numpy(), o_s.cpu().numpy(), o_n.cpu().numpy()

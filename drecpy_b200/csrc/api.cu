@@ -636,14 +636,101 @@ int drb_cdae_rank_candidates(drb_cdae* m, const int32_t* uids, int32_t n, const 
   return DRB_OK;
 }
 
-int drb_cdae_topk(drb_cdae* m, const int32_t* uids, int32_t n, int32_t k, int32_t novelty, int32_t* out_iid,
-                  float* out_score, int32_t* n_out) {
+// Scratch of the tensor-core top-k, carved from the dz workspace (max_batch x items_pad floats):
+//   lists [B][cap] u64 | seen bitmap [B][words] u32 | cnt [B] | tau [B] | fallback: count, users [FB], rows [FB][items_pad]
+struct TopkScratch {
+  uint64_t* lists; uint32_t* bits; int32_t* cnt; uint32_t* tau; int32_t* fb_count; int32_t* fb_users; float* fb_rows;
+  int cap, fb_max; bool ok;
+};
+static constexpr int kTopkFallbackRows = 32;
+
+static TopkScratch topk_scratch(drb_cdae* m, int cap) {
+  TopkScratch t{};
+  const int64_t B = m->d.max_batch, words = m->words_per_row;
+  Carver c(m->ws.dz);
+  t.lists = c.take<uint64_t>(B * cap);
+  t.bits = c.take<uint32_t>(B * words);
+  t.cnt = c.take<int32_t>(B);
+  t.tau = c.take<uint32_t>(B);
+  t.fb_count = c.take<int32_t>(64);
+  t.fb_users = c.take<int32_t>(kTopkFallbackRows);
+  t.fb_rows = c.take<float>((int64_t)kTopkFallbackRows * m->L.items_pad);
+  t.cap = cap; t.fb_max = kTopkFallbackRows;
+  t.ok = c.off <= B * (int64_t)m->L.items_pad * 4;
+  return t;
+}
+
+// Full-catalog top-k on the tensor cores for one block of users (see umma_score.cu for the selection scheme).
+static int cdae_topk_umma_chunk(drb_cdae* m, const TopkScratch& S, int n_s, const int32_t* uids, int c, int k, int novelty,
+                                int32_t* out_iid, float* out_score, int32_t* n_out) {
+  drb_ctx* ctx = m->ctx;
+  CdaeWs& w = m->ws;
+  const int I = m->d.n_items, ld = m->L.ld, words = m->words_per_row;
+  int r;
+  if ((r = cdae_hidden_into(m, uids, c, nullptr, nullptr, 1.0f, w.h))) return r;
+  if ((r = launch_split_tf32(ctx, w.h, c, ld, ld, w.h_hi, w.h_lo, nullptr, nullptr, 0, -1))) return r;
+  DRB_CUDA_TRY(ctx, cudaMemsetAsync(S.cnt, 0, (size_t)c * 4, ctx->stream));
+  DRB_CUDA_TRY(ctx, cudaMemsetAsync(S.tau, 0, (size_t)c * 4, ctx->stream));
+  DRB_CUDA_TRY(ctx, cudaMemsetAsync(S.fb_count, 0, 4, ctx->stream));
+  const uint32_t* bits = nullptr;
+  if (novelty) {     // the user's stored items as a bitmap (cdae.py:93-98): built like the per-user label bitmap
+    DRB_CUDA_TRY(ctx, cudaMemsetAsync(S.bits, 0, (size_t)c * words * 4, ctx->stream));
+    BatchPrepArgs bp{};
+    bp.indptr = m->d.seen_indptr; bp.indices = m->d.seen_indices; bp.rows = uids;
+    bp.label_bits = S.bits; bp.words_per_row = words;
+    if ((r = launch_batch_prep(ctx, bp, c))) return r;
+    bits = S.bits;
+  }
+  UmmaOperands o{w.h_hi, w.h_lo, ld, w.w2t_hi, w.w2t_lo, ld, I};
+  const float* b2 = m->d.params + m->L.off_b2;
+  // pass 1: the first n_s items, everything unseen is listed; tau = k-th best of the slice
+  if ((r = launch_umma_score_filter(ctx, o, c, I, 0, n_s, ld, b2, bits, words, S.tau, S.cnt, S.lists, S.cap))) return r;
+  if ((r = launch_select_lists(ctx, S.lists, S.cap, S.cnt, S.tau, k, false, nullptr, nullptr, nullptr, c))) return r;
+  // pass 2: the rest of the catalog, only scores >= tau are listed; then the final order
+  if ((r = launch_umma_score_filter(ctx, o, c, I, n_s, I, ld, b2, bits, words, S.tau, S.cnt, S.lists, S.cap))) return r;
+  if ((r = launch_select_lists(ctx, S.lists, S.cap, S.cnt, S.tau, k, true, out_iid, out_score, n_out, c))) return r;
+  // users whose list overflowed (n_out == -1): exact fp32 scores + radix select, on the device, no host round trip
+  TopkArgs t{};
+  t.ld = m->L.items_pad; t.n_items = I; t.uids = uids;
+  t.seen_indptr = m->d.seen_indptr; t.seen_indices = m->d.seen_indices; t.novelty = novelty; t.k = k;
+  t.out_iid = out_iid; t.out_score = out_score; t.n_out = n_out;
+  return launch_topk_fallback(ctx, t, c, w.h, ld, m->d.params + m->L.off_w2t, ld, b2, m->d.hidden, S.fb_rows, S.fb_users,
+                              S.fb_count, S.fb_max);
+}
+
+static int cdae_topk_impl(drb_cdae* m, const int32_t* uids, int32_t n, int32_t k, int32_t novelty, int32_t* out_iid,
+                          float* out_score, int32_t* n_out, bool exact_only) {
   if (!m || !uids || !out_iid || !out_score || !n_out || n < 0)
     return drb_fail(DRB_E_INVALID, "drb_cdae_topk: bad argument");
+  if (k < 1 || k > 2048) return drb_fail(DRB_E_INVALID, "drb_cdae_topk: k must be in [1, 2048]");
+  // Tensor-core path: wide catalogs, blocks of >= 128 users.  DRB_TOPK_PATH=ffma forces the exact-fp32 GEMM + radix
+  // select path, DRB_TOPK_CAP / DRB_TOPK_NS shrink the list capacity / first slice (tests of the overflow fallback).
+  const char* path_env = getenv("DRB_TOPK_PATH");
+  const int cap_env = getenv("DRB_TOPK_CAP") ? atoi(getenv("DRB_TOPK_CAP")) : 0;
+  const int ns_env = getenv("DRB_TOPK_NS") ? atoi(getenv("DRB_TOPK_NS")) : 0;
+  const int I = m->d.n_items;
+  const int cap = cap_env ? cap_env : 4096;
+  int n_s = ns_env ? ns_env : (int)drb_round_up(std::max<int64_t>(2048, 3ll * k * I / cap), 256);
+  TopkScratch S{};
+  bool fast = !exact_only && m->use_umma && n >= 128 && !(path_env && !strcmp(path_env, "ffma")) && (cap & (cap - 1)) == 0 &&
+              n_s + k <= cap && n_s < I;
+  if (fast && !ns_env && !cap_env) fast = I >= 8192 && n_s <= I / 3;
+  if (fast) { S = topk_scratch(m, cap); fast = S.ok; }
+  if (fast) {   // tf32 hi/lo split of W' once per call (the weights do not change while scoring)
+    int r = launch_split_tf32(m->ctx, m->d.params + m->L.off_w2t, I, m->L.ld, m->L.ld, m->ws.w2t_hi, m->ws.w2t_lo, nullptr,
+                              nullptr, 0, -1);
+    if (r) return r;
+  }
   for (int32_t o = 0; o < n; o += m->d.max_batch) {
     const int c = std::min(m->d.max_batch, n - o);
-    int r = cdae_scores_chunk(m, uids + o, c, m->ws.dz);
-    if (r) return r;
+    int r;
+    if (fast && c >= 128) {
+      if ((r = cdae_topk_umma_chunk(m, S, n_s, uids + o, c, k, novelty, out_iid + (int64_t)o * k,
+                                    out_score + (int64_t)o * k, n_out + o)))
+        return r;
+      continue;
+    }
+    if ((r = cdae_scores_chunk(m, uids + o, c, m->ws.dz))) return r;
     TopkArgs t{};
     t.scores = m->ws.dz; t.ld = m->L.items_pad; t.n_items = m->d.n_items; t.uids = uids + o;
     t.seen_indptr = m->d.seen_indptr; t.seen_indices = m->d.seen_indices; t.novelty = novelty; t.k = k;
@@ -651,6 +738,16 @@ int drb_cdae_topk(drb_cdae* m, const int32_t* uids, int32_t n, int32_t k, int32_
     if ((r = launch_topk(m->ctx, t, c))) return r;
   }
   return DRB_OK;
+}
+
+int drb_cdae_topk(drb_cdae* m, const int32_t* uids, int32_t n, int32_t k, int32_t novelty, int32_t* out_iid,
+                  float* out_score, int32_t* n_out) {
+  return cdae_topk_impl(m, uids, n, k, novelty, out_iid, out_score, n_out, false);
+}
+
+int drb_cdae_topk_exact(drb_cdae* m, const int32_t* uids, int32_t n, int32_t k, int32_t novelty, int32_t* out_iid,
+                        float* out_score, int32_t* n_out) {
+  return cdae_topk_impl(m, uids, n, k, novelty, out_iid, out_score, n_out, true);
 }
 
 }  // extern "C"

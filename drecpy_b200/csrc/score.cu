@@ -157,10 +157,16 @@ __global__ void __launch_bounds__(kTopkThreads) k_topk(TopkArgs a, int P) {
   __shared__ int hist[256];
   __shared__ SelectState st;
   __shared__ int n_sel;
-  const int u = blockIdx.x;
+  // direct: block b ranks score row b for user b.  Indirect (the exact fallback of the tensor-core path): block b ranks
+  // score row b for user fb_users[b], for the first *fb_count rows only.
+  int u = blockIdx.x;
+  if (a.fb_users) {
+    if (u >= min(*a.fb_count, a.fb_max)) return;
+    u = a.fb_users[blockIdx.x];
+  }
   const int uid = a.uids[u];
   // the score row is scratch: knock out the user's training items (cdae.py:93-98) in place
-  float* row = const_cast<float*>(a.scores) + (int64_t)u * a.ld;
+  float* row = const_cast<float*>(a.scores) + (int64_t)blockIdx.x * a.ld;
   if (a.novelty) {
     const int64_t lo = a.seen_indptr[uid], hi = a.seen_indptr[uid + 1];
     for (int64_t j = lo + threadIdx.x; j < hi; j += blockDim.x) row[a.seen_indices[j]] = -INFINITY;
@@ -226,6 +232,68 @@ __global__ void __launch_bounds__(kTopkThreads) k_topk(TopkArgs a, int P) {
   emit_sorted(keys, P, a.k, a.out_iid + (int64_t)u * a.k, a.out_score + (int64_t)u * a.k, a.n_out + u);
 }
 
+
+// ---------------------------------------------------------------- candidate lists of the tensor-core top-k (umma_score.cu)
+// One CTA per user: sorts the user's list of 64-bit keys (descending) in shared memory.
+//   final == 0: keeps the best k at the head of the list and publishes tau = orderable score of the k-th (0 while
+//               fewer than k exist: the next pass then takes everything);
+//   final != 0: emits the answer.  A list that overflowed its capacity marks the user (n_out = -1) for the fallback.
+__global__ void __launch_bounds__(256) k_select_lists(uint64_t* lists, int cap, int32_t* cnt, uint32_t* tau_ord, int k,
+                                                      int final, int32_t* out_iid, float* out_score, int32_t* n_out) {
+  extern __shared__ uint64_t keys[];
+  const int u = blockIdx.x;
+  const int c = cnt[u];
+  uint64_t* list = lists + (int64_t)u * cap;
+  if (c > cap) {                    // overflow: the list is incomplete, this user goes through the exact fallback
+    if (threadIdx.x == 0) {
+      if (final) n_out[u] = -1;
+      else tau_ord[u] = 0xffffffffu;         // nothing more is appended for this user; cnt stays > cap
+    }
+    return;
+  }
+  int P = 32;
+  while (P < c) P <<= 1;
+  for (int i = threadIdx.x; i < P; i += blockDim.x) keys[i] = i < c ? list[i] : 0ull;
+  __syncthreads();
+  bitonic_desc(keys, P);
+  if (final) {
+    emit_sorted(keys, P, k, out_iid + (int64_t)u * k, out_score + (int64_t)u * k, n_out + u);
+    return;
+  }
+  const int kk = min(c, k);
+  for (int i = threadIdx.x; i < kk; i += blockDim.x) list[i] = keys[i];
+  if (threadIdx.x == 0) {
+    cnt[u] = kk;
+    tau_ord[u] = (c >= k) ? (uint32_t)(keys[k - 1] >> 32) : 0u;
+  }
+}
+
+// Exact fallback for users whose candidate list overflowed: claims a scratch row, fills it with the user's scores
+// sigmoid(h_u . W'_i + b'_i) over the whole catalog (one warp per item, fp32 FMA); k_topk (indirect) then ranks the row.
+__global__ void __launch_bounds__(256) k_fallback_scores(const int32_t* n_out, int n_users, const float* h, int ld_h,
+                                                         const float* table, int ld_t, const float* bias, int width,
+                                                         int n_items, float* rows, int ld_rows, int32_t* fb_users,
+                                                         int32_t* fb_count, int fb_max) {
+  __shared__ int slot_s;
+  const int u = blockIdx.x;
+  if (u >= n_users || n_out[u] != -1) return;
+  if (threadIdx.x == 0) slot_s = atomicAdd(fb_count, 1);
+  __syncthreads();
+  const int slot = slot_s;
+  if (slot >= fb_max) return;      // more overflows than scratch rows: n_out stays -1 and the host reports it
+  if (threadIdx.x == 0) fb_users[slot] = u;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const float* ur = h + (int64_t)u * ld_h;
+  float* row = rows + (int64_t)slot * ld_rows;
+  for (int i = warp; i < n_items; i += 8) {
+    const float* tr = table + (int64_t)i * ld_t;
+    float dot = 0.f;
+    for (int kx = lane; kx < width; kx += 32) dot = fmaf(ur[kx], tr[kx], dot);
+    dot = warp_sum(dot);
+    if (lane == 0) row[i] = 1.0f / (1.0f + expf(-(dot + bias[i])));
+  }
+}
+
 int next_pow2(int x) {
   int p = 32;
   while (p < x) p <<= 1;
@@ -263,4 +331,35 @@ int launch_topk(drb_ctx* ctx, const TopkArgs& a, int n) {
   k_topk<<<n, kTopkThreads, (size_t)P * sizeof(uint64_t), ctx->stream>>>(a, P);
   DRB_LAUNCH_CHECK(ctx, "k_topk");
   return DRB_OK;
+}
+
+int launch_select_lists(drb_ctx* ctx, uint64_t* lists, int cap, int32_t* cnt, uint32_t* tau_ord, int k, bool final,
+                        int32_t* out_iid, float* out_score, int32_t* n_out, int n) {
+  if (n <= 0) return DRB_OK;
+  if (cap < 32 || (cap & (cap - 1)) || cap > 8192) return drb_fail(DRB_E_INVALID, "select_lists: cap must be a power of two in [32, 8192]");
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(k_select_lists, cudaFuncAttributeMaxDynamicSharedMemorySize, 8192 * 8);
+    if (e != cudaSuccess) return drb_fail(DRB_E_CUDA, "cudaFuncSetAttribute(k_select_lists) failed: %s", cudaGetErrorString(e));
+    attr_set = true;
+  }
+  drb_prof_scope prof_(ctx, "k_select_lists");
+  k_select_lists<<<n, 256, (size_t)cap * sizeof(uint64_t), ctx->stream>>>(lists, cap, cnt, tau_ord, k, final ? 1 : 0, out_iid,
+                                                                         out_score, n_out);
+  DRB_LAUNCH_CHECK(ctx, "k_select_lists");
+  return DRB_OK;
+}
+
+int launch_topk_fallback(drb_ctx* ctx, const TopkArgs& a, int n, const float* h, int ld_h, const float* table, int ld_t,
+                         const float* bias, int width, float* rows, int32_t* fb_users, int32_t* fb_count, int fb_max) {
+  if (n <= 0) return DRB_OK;
+  {
+    drb_prof_scope prof_(ctx, "k_fallback_scores");
+    k_fallback_scores<<<n, 256, 0, ctx->stream>>>(a.n_out, n, h, ld_h, table, ld_t, bias, width, a.n_items, rows, a.ld,
+                                                  fb_users, fb_count, fb_max);
+    DRB_LAUNCH_CHECK(ctx, "k_fallback_scores");
+  }
+  TopkArgs t = a;
+  t.scores = rows; t.fb_users = fb_users; t.fb_count = fb_count; t.fb_max = fb_max;
+  return launch_topk(ctx, t, fb_max);
 }

@@ -1,0 +1,346 @@
+// Full-catalog scoring on the tensor cores with the top-k selection kept on chip: scores = sigmoid(h W'^T + b') for a
+// block of users against a range of items (3xTF32 tcgen05.mma, TMA-fed, TMEM accumulators -- the persistent CTA-pair
+// skeleton of umma_loss.cu), and an epilogue that never writes a score to memory.  It compares every score with the
+// user's current threshold and appends the few that pass to that user's candidate list.
+//
+// Replaces (reference, DRecPy/): Recommender/recommender_abc.py:413-419 (_recommend = _rank over range(n_items)) ->
+// Recommender/cdae.py:84-103 (_predict over all items, drop the user's training items when novelty, heapq.nlargest on
+// (score, iid)), as driven for every user by Evaluation/Processes/recommendation_evaluation.py:164.
+//
+// Selection scheme (drb_cdae_topk in api.cu drives it):
+//   1. items [0, n_S): threshold 0, i.e. every unseen item of that slice lands in the list; k_select_lists sorts the
+//      list, keeps its best k and publishes tau = the k-th best score.  The k-th best of ANY subset is a lower bound of
+//      the final k-th best, so nothing below tau can be in the answer;
+//   2. items [n_S, I): only scores >= tau are appended (a few per cent of the catalog at worst, far less when the
+//      slice already holds popular items); k_select_lists then sorts k + appended keys and emits the answer in the
+//      reference's order (score desc, iid desc).
+// Keys are 64-bit (orderable(score) << 32 | iid) as everywhere in score.cu.  The novelty filter is a per-user bitmap
+// of the user's stored items (built by k_batch_prep from the `seen` CSR): one broadcast 32-bit load covers the 32 items
+// a warp holds for one user.  A list that overflows its capacity is detected by k_select_lists and that user is
+// re-done by the exact fallback (score.cu), so the scheme is exact for any data.
+//
+// Orientation as in umma_loss.cu: MMA M = 128 items on the TMEM lanes, N = 256 users on the TMEM columns; an epilogue
+// warp holds 32 consecutive items of one user across its lanes, so one ballot says which of them pass and one atomicAdd
+// per (warp, user) reserves their slots.
+#include "umma_common.cuh"
+
+namespace {
+
+constexpr int SC_EPI_WARPS = 16;
+constexpr int SC_THREADS = 64 + 32 * SC_EPI_WARPS;
+
+template <int BN, int KB, int CL>
+struct ScoreSmem {
+  static constexpr int A_BYTES = BM * KB * 4;
+  static constexpr int B_BYTES = (BN / CL) * KB * 4;
+  static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
+  static constexpr int STAGES = 192 * 1024 / STAGE_BYTES;
+  static constexpr int BAR_BYTES = 256;
+  static constexpr int TAU_BYTES = SC_EPI_WARPS * (BN / 4) * 4;   // per epilogue warp: thresholds of its users
+  static constexpr int TOTAL = STAGES * STAGE_BYTES + 1024 + BAR_BYTES + TAU_BYTES;
+};
+
+struct ScoreParams {
+  int M;                                   // users of this block
+  int item_begin, item_end;                // item range of this pass (item_begin % 128 == 0, item_end <= n_items)
+  int Kred;                                // hidden (padded to 4)
+  const float* bias;                       // b' [n_items]
+  const uint32_t* seen_bits; int words_per_row;   // NULL (no novelty filter) or [M][words_per_row]
+  const uint32_t* tau_ord;                 // [M] orderable-score threshold per user (0 = take everything)
+  int32_t* cnt;                            // [M] entries appended so far (may exceed cap: overflow)
+  uint64_t* lists; int cap;                // [M][cap]
+  int m_tiles, n_tiles;
+};
+
+__device__ __forceinline__ float sc_ex2(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float sc_rcp(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ void sc_mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void sc_mbar_arrive_rank(uint32_t bar, uint32_t rank) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(mapa_rank(bar, rank)) : "memory");
+}
+
+template <int BN, int KB, int CL>
+__global__ void __launch_bounds__(SC_THREADS, 1)
+k_umma_score_filter(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
+                    const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
+                    ScoreParams p) {
+  using S = ScoreSmem<BN, KB, CL>;
+  constexpr int BK = KB;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  const uint32_t bars = base + S::STAGES * S::STAGE_BYTES;
+  auto full_bar = [&](int s) { return bars + 8u * s; };
+  auto empty_bar = [&](int s) { return bars + 8u * (S::STAGES + s); };
+  auto tfull_bar = [&](int a) { return bars + 8u * (2 * S::STAGES + a); };
+  auto tempty_bar = [&](int a) { return bars + 8u * (2 * S::STAGES + 2 + a); };
+  const uint32_t tmem_ptr_addr = bars + 8u * (2 * S::STAGES + 4);
+  volatile uint32_t* tmem_ptr_generic = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_ptr_addr - raw));
+  uint32_t* tau_smem = reinterpret_cast<uint32_t*>(smem_raw + (bars + S::BAR_BYTES - raw));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nkb = (p.Kred + BK - 1) / BK;
+  const uint32_t cta_rank = (CL > 1) ? cluster_ctarank() : 0u;
+  const bool leader = cta_rank == 0;
+  const int unit0 = blockIdx.x / CL, unit_stride = gridDim.x / CL;
+  const int n_units = ((p.m_tiles + CL - 1) / CL) * p.n_tiles;
+  auto unit_item0 = [&](int u) { return p.item_begin + ((u / p.n_tiles) * CL + (int)cta_rank) * BM; };
+  auto unit_row0 = [&](int u) { return (u % p.n_tiles) * BN; };
+  constexpr uint32_t TMEM_COLS = (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < S::STAGES; s++) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int a = 0; a < 2; a++) {
+      mbar_init(tfull_bar(a), 1);
+      mbar_init(tempty_bar(a), CL * SC_EPI_WARPS);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    if (CL > 1) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_ptr_addr), "r"(TMEM_COLS));
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_ptr_addr), "r"(TMEM_COLS));
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  if (CL > 1) cluster_sync_all(); else __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_ptr_generic;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer (runs ahead across tiles)
+    if (lane == 0) {
+      int it = 0;
+      for (int t = unit0; t < n_units; t += unit_stride) {
+        const int i0 = unit_item0(t), r0 = unit_row0(t);
+        for (int kb = 0; kb < nkb; kb++, it++) {
+          const int s = it % S::STAGES;
+          const uint32_t ph = (it / S::STAGES) & 1;
+          mbar_wait(empty_bar(s), ph ^ 1);
+          const uint32_t sa_hi = base + s * S::STAGE_BYTES, sa_lo = sa_hi + S::A_BYTES;
+          const uint32_t sb_hi = sa_lo + S::A_BYTES, sb_lo = sb_hi + S::B_BYTES;
+          if (CL > 1) {
+            if (leader) mbar_expect_tx(full_bar(s), CL * S::STAGE_BYTES);
+            const uint32_t fb = mapa_rank(full_bar(s), 0);
+            const int rh = r0 + (int)cta_rank * (BN / CL);
+            tma_load_2d_pair(sa_hi, &map_a_hi, fb, kb * BK, i0);
+            tma_load_2d_pair(sa_lo, &map_a_lo, fb, kb * BK, i0);
+            tma_load_2d_pair(sb_hi, &map_b_hi, fb, kb * BK, rh);
+            tma_load_2d_pair(sb_lo, &map_b_lo, fb, kb * BK, rh);
+          } else {
+            mbar_expect_tx(full_bar(s), S::STAGE_BYTES);
+            tma_load_2d(sa_hi, &map_a_hi, full_bar(s), kb * BK, i0);
+            tma_load_2d(sa_lo, &map_a_lo, full_bar(s), kb * BK, i0);
+            tma_load_2d(sb_hi, &map_b_hi, full_bar(s), kb * BK, r0);
+            tma_load_2d(sb_lo, &map_b_lo, full_bar(s), kb * BK, r0);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0 && leader) {
+      const uint32_t idesc =
+          (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((BM * CL) >> 4) << 24);
+      int it = 0, tl = 0;
+      for (int t = unit0; t < n_units; t += unit_stride, tl++) {
+        const int as = tl & 1;
+        mbar_wait(tempty_bar(as), ((tl >> 1) & 1) ^ 1);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t tacc = tmem_base + (uint32_t)(as * BN);
+        for (int kb = 0; kb < nkb; kb++, it++) {
+          const int s = it % S::STAGES;
+          mbar_wait(full_bar(s), (it / S::STAGES) & 1);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t sa_hi = base + s * S::STAGE_BYTES, sa_lo = sa_hi + S::A_BYTES;
+          const uint32_t sb_hi = sa_lo + S::A_BYTES, sb_lo = sb_hi + S::B_BYTES;
+#pragma unroll
+          for (int kk = 0; kk < BK / UMMA_K; kk++) {
+            const uint64_t a_hi = make_desc_kmajor<BK>(sa_hi, kk), a_lo = make_desc_kmajor<BK>(sa_lo, kk);
+            const uint64_t b_hi = make_desc_kmajor<BK>(sb_hi, kk), b_lo = make_desc_kmajor<BK>(sb_lo, kk);
+            if (CL > 1) {
+              umma_tf32_pair(tacc, a_lo, b_hi, idesc, (kb | kk) != 0);
+              umma_tf32_pair(tacc, a_hi, b_lo, idesc, 1u);
+              umma_tf32_pair(tacc, a_hi, b_hi, idesc, 1u);
+            } else {
+              umma_tf32(tacc, a_lo, b_hi, idesc, (kb | kk) != 0);
+              umma_tf32(tacc, a_hi, b_lo, idesc, 1u);
+              umma_tf32(tacc, a_hi, b_hi, idesc, 1u);
+            }
+          }
+          if (CL > 1) umma_commit_pair(empty_bar(s));
+          else umma_commit(empty_bar(s));
+        }
+        if (CL > 1) umma_commit_pair(tfull_bar(as));
+        else umma_commit(tfull_bar(as));
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue warps 2..17
+    // TMEM lane = item, column = user.  Warp w reads lanes 32*(w&3)..+31 (its sub-partition) = one 32-item block and the
+    // column quarter (w-2)/4 of the tile: for one user the 32 lanes of a warp hold 32 consecutive items.
+    const int q = warp & 3, cq = (warp - 2) >> 2;
+    constexpr int CW = BN / 4;                    // users of this warp per tile
+    uint32_t* my_tau = tau_smem + (warp - 2) * CW;
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    float nbias;
+    auto fetch_bias = [&](int t) {
+      const int item = unit_item0(t) + q * 32 + lane;
+      nbias = ((t < n_units) && (item < p.item_end)) ? __ldg(p.bias + item) : 0.f;
+    };
+    fetch_bias(unit0);
+    int tl = 0;
+    for (int t = unit0; t < n_units; t += unit_stride, tl++) {
+      const int i0 = unit_item0(t), r0 = unit_row0(t);
+      const int as = tl & 1;
+      const int item = i0 + q * 32 + lane;
+      const bool item_ok = item < p.item_end;
+      const int ib = (i0 >> 5) + q;               // 32-item block of this warp == word of the seen bitmap
+      const float bias = nbias;
+      fetch_bias(t + unit_stride);
+      // thresholds of this warp's users (users beyond the block never pass)
+      __syncwarp();
+#pragma unroll
+      for (int c = lane; c < CW; c += 32) {
+        const int row = r0 + cq * CW + c;
+        my_tau[c] = (row < p.M) ? __ldg(p.tau_ord + row) : 0xffffffffu;
+      }
+      __syncwarp();
+      mbar_wait(tfull_bar(as), (tl >> 1) & 1);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN + cq * CW);
+      uint32_t rn[16];
+      tmem_ld16_issue(tbase, rn);
+#pragma unroll 1
+      for (int cl = 0; cl < CW; cl += 16) {
+        const int row = r0 + cq * CW + cl;        // first of this chunk's 16 users
+        uint32_t r[16];
+        tmem_ld16_wait(rn);
+#pragma unroll
+        for (int j = 0; j < 16; j++) r[j] = rn[j];
+        if (cl + 16 < CW) tmem_ld16_issue(tbase + cl + 16, rn);
+        uint32_t bal[16];
+        // 1. score, knock-out, threshold test: r[j] becomes the orderable score, bal[j] the lanes that pass for user j
+#pragma unroll
+        for (int j = 0; j < 16; j++) {
+          const float z = __uint_as_float(r[j]) + bias;
+          const float pr = sc_rcp(1.0f + sc_ex2(z * -1.4426950408889634f));     // sigmoid, > 0
+          const uint32_t ord = __float_as_uint(pr) | 0x80000000u;               // f2ord of a non-negative float
+          uint32_t seen = 0u;
+          if (p.seen_bits && row + j < p.M && ib < p.words_per_row)
+            seen = __ldg(p.seen_bits + (int64_t)(row + j) * p.words_per_row + ib);
+          const bool pass = item_ok && !((seen >> lane) & 1u) && (ord >= my_tau[cl + j]);
+          r[j] = ord;
+          bal[j] = __ballot_sync(0xffffffffu, pass);
+        }
+        // 2. one atomicAdd per (warp, user) reserves the slots of the passing lanes (all issued before any is consumed)
+        int slot[16];
+#pragma unroll
+        for (int j = 0; j < 16; j++) {
+          slot[j] = 0;
+          if (bal[j] != 0u && lane == 0) slot[j] = atomicAdd(p.cnt + row + j, __popc(bal[j]));
+        }
+        // 3. append
+#pragma unroll
+        for (int j = 0; j < 16; j++) {
+          if (bal[j] != 0u) {                      // warp-uniform
+            const int b0 = __shfl_sync(0xffffffffu, slot[j], 0);
+            if ((bal[j] >> lane) & 1u) {
+              const int pos = b0 + __popc(bal[j] & lt_mask);
+              if (pos < p.cap) p.lists[(int64_t)(row + j) * p.cap + pos] = ((uint64_t)r[j] << 32) | (uint32_t)item;
+            }
+          }
+        }
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) {
+        if (CL > 1) sc_mbar_arrive_rank(tempty_bar(as), 0);
+        else sc_mbar_arrive(tempty_bar(as));
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  if (CL > 1) cluster_sync_all(); else __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    if (CL > 1) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS));
+    else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS));
+  }
+}
+
+template <int BN, int KB, int CL>
+int run_score(drb_ctx* ctx, const UmmaOperands& o, ScoreParams p, int n_items) {
+  constexpr int BK = KB;
+  CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
+  int r;
+  // A (M side, TMEM lanes) = W' rows = items; B (N side, TMEM columns) = h rows = users.  Rows past the end of either
+  // matrix read as zeros (TMA out-of-bounds fill) and are masked in the epilogue.
+  if ((r = make_map(&ma_hi, o.b_hi, p.Kred, n_items, o.ldb, BK, BM))) return r;
+  if ((r = make_map(&ma_lo, o.b_lo, p.Kred, n_items, o.ldb, BK, BM))) return r;
+  if ((r = make_map(&mb_hi, o.a_hi, p.Kred, p.M, o.lda, BK, BN / CL))) return r;
+  if ((r = make_map(&mb_lo, o.a_lo, p.Kred, p.M, o.lda, BK, BN / CL))) return r;
+  p.m_tiles = (p.item_end - p.item_begin + BM - 1) / BM;
+  p.n_tiles = (p.M + BN - 1) / BN;
+  auto kern = k_umma_score_filter<BN, KB, CL>;
+  constexpr int SMEM = ScoreSmem<BN, KB, CL>::TOTAL;
+  static bool attr_set = false;
+  static int max_clusters = 0;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
+    if (e != cudaSuccess)
+      return drb_fail(DRB_E_CUDA, "cudaFuncSetAttribute(smem=%d) failed: %s", SMEM, cudaGetErrorString(e));
+    if (CL > 1) {
+      cudaLaunchConfig_t qc{};
+      cudaLaunchAttribute qa[1];
+      qa[0].id = cudaLaunchAttributeClusterDimension;
+      qa[0].val.clusterDim.x = CL; qa[0].val.clusterDim.y = 1; qa[0].val.clusterDim.z = 1;
+      qc.gridDim = dim3(ctx->sm_count / CL * CL); qc.blockDim = dim3(SC_THREADS); qc.dynamicSmemBytes = SMEM;
+      qc.attrs = qa; qc.numAttrs = 1;
+      e = cudaOccupancyMaxActiveClusters(&max_clusters, kern, &qc);
+      if (e != cudaSuccess || max_clusters < 1)
+        return drb_fail(DRB_E_CUDA, "cudaOccupancyMaxActiveClusters failed: %s", cudaGetErrorString(e));
+    }
+    attr_set = true;
+  }
+  const int n_units = ((p.m_tiles + CL - 1) / CL) * p.n_tiles;
+  if (n_units <= 0) return DRB_OK;
+  const int grid = CL * std::min(n_units, CL > 1 ? max_clusters : ctx->sm_count);
+  drb_prof_scope prof_(ctx, "k_umma_score_filter");
+  if (CL > 1) {
+    cudaLaunchConfig_t cfg{};
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = CL; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(SC_THREADS); cfg.dynamicSmemBytes = SMEM; cfg.stream = ctx->stream;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, ma_hi, ma_lo, mb_hi, mb_lo, p);
+    if (e != cudaSuccess) return drb_fail(DRB_E_CUDA, "cluster launch of k_umma_score_filter failed: %s", cudaGetErrorString(e));
+  } else {
+    kern<<<grid, SC_THREADS, SMEM, ctx->stream>>>(ma_hi, ma_lo, mb_hi, mb_lo, p);
+  }
+  DRB_LAUNCH_CHECK(ctx, "k_umma_score_filter");
+  return DRB_OK;
+}
+
+}  // namespace
+
+int launch_umma_score_filter(drb_ctx* ctx, const UmmaOperands& o, int n_users, int n_items, int item_begin, int item_end,
+                             int Kred, const float* bias, const uint32_t* seen_bits, int words_per_row,
+                             const uint32_t* tau_ord, int32_t* cnt, uint64_t* lists, int cap) {
+  if (item_begin % 128 != 0 || item_end > n_items || item_begin >= item_end)
+    return drb_fail(DRB_E_INVALID, "score_filter: bad item range [%d, %d) of %d", item_begin, item_end, n_items);
+  ScoreParams p{};
+  p.M = n_users; p.item_begin = item_begin; p.item_end = item_end; p.Kred = Kred; p.bias = bias;
+  p.seen_bits = seen_bits; p.words_per_row = words_per_row; p.tau_ord = tau_ord; p.cnt = cnt; p.lists = lists; p.cap = cap;
+  if (n_users > 128) return run_score<256, 32, 2>(ctx, o, p, n_items);
+  return run_score<128, 32, 1>(ctx, o, p, n_items);
+}

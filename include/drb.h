@@ -219,10 +219,18 @@ int drb_cdae_hidden(drb_cdae* m, const int32_t* uids, int32_t n, float* h_out);
 int drb_cdae_rank_candidates(drb_cdae* m, const int32_t* uids, int32_t n, const int32_t* cand,
                              const int32_t* cand_count, int32_t max_cand, int32_t novelty,
                              int32_t* out_iid, float* out_score, int32_t* n_out);
-/* Full-catalog top-k.  replaces: recommender_abc.py:413-419 -> cdae.py:90-103 with iids = range(n_items).
- * out_iid / out_score: [n x k]; n_out[u] <= k. */
+/* Full-catalog top-k.  replaces: recommender_abc.py:413-419 -> cdae.py:90-103 with iids = range(n_items), i.e. what
+ * Evaluation/Processes/recommendation_evaluation.py:164 asks of the model for every user.
+ * out_iid / out_score: [n x k]; n_out[u] <= k entries ordered by (score desc, iid desc).
+ * Wide catalogs and blocks of >= 128 users run on the tensor cores (tcgen05 h W'^T tiles whose epilogue keeps only the
+ * scores above a per-user threshold; no score is written to memory).  Its per-user candidate lists are bounded: a user
+ * whose list overflowed is re-done on the device by the exact path; if more than 32 users of one block overflow, the
+ * remaining ones are reported with n_out[u] == -1 and the caller re-runs them through drb_cdae_topk_exact. */
 int drb_cdae_topk(drb_cdae* m, const int32_t* uids, int32_t n, int32_t k, int32_t novelty,
                   int32_t* out_iid, float* out_score, int32_t* n_out);
+/* Same contract, always the exact-fp32 score rows + radix select (any catalog size, any number of users). */
+int drb_cdae_topk_exact(drb_cdae* m, const int32_t* uids, int32_t n, int32_t k, int32_t novelty,
+                        int32_t* out_iid, float* out_score, int32_t* n_out);
 /* Dense scores for n users over all items: out[n x items_pad] (cdae.py:84-88 with iid=None). */
 int drb_cdae_predict_all(drb_cdae* m, const int32_t* uids, int32_t n, float* out);
 

@@ -1,7 +1,7 @@
 """Full-size checks at BASELINE.json's configs[2] shape (synthetic ml-20m: 138,493 x 26,744, 20 M interactions,
 K = 200, B = 4096) through size-independent properties: the tcgen05 3xTF32 path against the exact-fp32 FFMA path on
 the same inputs, padding invariants, (score desc, iid desc) order / novelty / idempotence of the full-catalog top-k,
-sampler membership properties.  The oracle itself is too slow for this size (1 k samples/s)."""
+sampler membership properties.  (Parity against the oracle at this size: tests/test_gpu_baseline_shapes.py.)"""
 import numpy as np
 import pytest
 
@@ -80,6 +80,6 @@ def test_full_size_topk_properties(c3):
         seen = indices[indptr[uids[r]]:indptr[uids[r] + 1]]
         assert len(np.intersect1d(seen, oi[r])) == 0
         p = m._predict(int(uids[r]))                         # scores are the dense predictions, and they are the top ones
-        assert np.allclose(p[oi[r]], os_[r], rtol=1e-6)
+        assert np.allclose(p[oi[r]], os_[r], rtol=1e-5)      # tensor-core scores vs the exact-fp32 predict path
         p[seen] = -1
-        assert np.sort(p)[-100] <= os_[r, -1] + 1e-7
+        assert np.sort(p)[-100] <= os_[r, -1] * (1 + 1e-5)

@@ -1,0 +1,125 @@
+"""Full-catalog top-k on the tensor cores (umma_score.cu) against the oracle's heapq.nlargest over (score, iid) tuples
+(cdae.py:102-103): index lists equal except checked near-ties, exact score ties broken by item id, novelty filter,
+users with nothing / little left to recommend, and the overflow fallback of the bounded candidate lists."""
+import heapq
+
+import numpy as np
+import pytest
+
+import drecpy_b200 as drb
+from oracle.cdae import CDAEOracle
+
+pytestmark = pytest.mark.gpu
+
+
+def _weights(U, I, K, seed=1, scale=3.0):
+    rng = np.random.default_rng(seed)
+
+    def g(shape, fi, fo):
+        lim = np.sqrt(6.0 / (fi + fo)) * scale
+        return rng.uniform(-lim, lim, shape).astype(np.float32)
+    return {'W': g((I, K), I, K), 'W_': g((K, I), K, I), 'V': g((U, K), U, K), 'b': g((K,), K, K), 'b_': g((I,), I, I)}
+
+
+def _setup(U=700, I=9000, K=48, nnz=60000, heavy_user=True):
+    u, i, v = drb.synthetic_interactions(U, I, nnz, seed=6)
+    if heavy_user:                      # user 1 has seen almost everything: fewer than k items are left for it
+        extra = np.arange(1, I - 40 + 1)
+        u = np.concatenate([u, np.full(len(extra), 1)])
+        i = np.concatenate([i, extra])
+        v = np.concatenate([v, np.full(len(extra), 3)])
+        key = np.unique(u.astype(np.int64) * (I + 1) + i, return_index=True)[1]
+        u, i, v = u[np.sort(key)], i[np.sort(key)], v[np.sort(key)]
+    ds = drb.InteractionData(u, i, v)
+    ds.assign_internal_ids()
+    U, I = ds.count_unique('uid'), ds.count_unique('iid')
+    w = _weights(U, I, K)
+    # exact score ties: identical output rows inside the first slice, across the slice boundary (item 2048) and far out
+    for lo, hi in ((100, 140), (2040, 2060), (7000, 7012)):
+        w['W_'][:, lo:hi] = w['W_'][:, lo:lo + 1]
+        w['b_'][lo:hi] = w['b_'][lo]
+    m = drb.CDAE(hidden_factors=K, seed=10, verbose=False)
+    m.fit(ds, epochs=0, batch_size=256, init_weights=w)
+    o = CDAEOracle(w['W'], w['W_'], w['V'], w['b'], w['b_'], ds.csr(), interaction_threshold=1e-3)
+    return ds, m, o
+
+
+def _oracle_topk(o, ds, uid, k, novelty):
+    p = o.predict(uid)
+    alive = np.ones(len(p), bool)
+    if novelty:
+        seen = ds.csr()
+        alive[seen[1][seen[0][uid]:seen[0][uid + 1]]] = False
+    idx = np.flatnonzero(alive)
+    return p, heapq.nlargest(k, zip(p[idx].tolist(), idx.tolist()))
+
+
+def _check(m, o, ds, uids, k, novelty, oi, os_, on, tol=2e-6):
+    near = 0
+    for r, uid in enumerate(uids):
+        p, want = _oracle_topk(o, ds, int(uid), k, novelty)
+        assert on[r] == len(want), (uid, on[r], len(want))
+        got = oi[r, :on[r]].tolist()
+        if got != [i for _, i in want]:
+            near += 1
+            for a, (sb, b) in zip(got, want):
+                if a != b:
+                    assert abs(p[a] - sb) <= tol * max(abs(p[a]), abs(sb)), (uid, a, b, p[a], sb)
+        if on[r]:
+            assert np.max(np.abs(os_[r, :on[r]] - p[got]) / p[got]) < 1e-5
+    return near
+
+
+@pytest.mark.parametrize('novelty', [True, False])
+def test_tensor_core_topk_matches_oracle(novelty):
+    ds, m, o = _setup()
+    U = m.n_users
+    uids = np.arange(U, dtype=np.int32)
+    oi, os_, on = m.topk_batch(uids, 100, novelty=novelty)
+    assert m.launch_count() > 0
+    ex_i, ex_s, ex_n = m.topk_batch(uids, 100, novelty=novelty, exact=True)
+    assert np.array_equal(on, ex_n)
+    heavy = ds.user_to_uid(1)
+    if novelty:
+        assert 0 < on[heavy] < 100          # only ~40 unseen items are left for the heavy user
+    sample = np.concatenate([np.arange(0, U, 23), [heavy]]).astype(np.int32)
+    near = _check(m, o, ds, sample, 100, novelty, oi[sample], os_[sample], on[sample])
+    assert near <= 3
+    # the forced exact ties come out by item id descending wherever they appear together
+    for r in range(U):
+        got = oi[r, :on[r]]
+        for lo, hi in ((100, 140), (2040, 2060), (7000, 7012)):
+            t = got[(got >= lo) & (got < hi)]
+            assert list(t) == sorted(t, reverse=True)
+    # the tensor-core answer and the exact-fp32 answer agree except for near-ties
+    diff = np.flatnonzero((oi != ex_i).any(axis=1))
+    assert len(diff) <= U // 20
+    # k = 1 and a k that is not a multiple of anything
+    for k in (1, 37):
+        ki, ks, kn = m.topk_batch(uids, k, novelty=novelty)
+        assert _check(m, o, ds, sample[:8], k, novelty, ki[sample[:8]], ks[sample[:8]], kn[sample[:8]]) <= 1
+
+
+def test_tensor_core_topk_overflow_fallback(monkeypatch):
+    """Candidate lists are bounded.  With a tiny capacity (256 keys, first slice 128 items) most users overflow: up to
+    32 per block are re-done on the device by the exact path, the rest come back flagged and topk_batch re-runs them
+    through drb_cdae_topk_exact.  The answer does not change."""
+    ds, m, o = _setup(heavy_user=False)
+    uids = np.arange(m.n_users, dtype=np.int32)
+    ref_i, ref_s, ref_n = m.topk_batch(uids, 100, novelty=True, exact=True)
+    monkeypatch.setenv('DRB_TOPK_CAP', '256')
+    monkeypatch.setenv('DRB_TOPK_NS', '128')
+    l0 = m.launch_count()
+    oi, os_, on = m.topk_batch(uids, 100, novelty=True)
+    assert m.launch_count() > l0
+    assert np.array_equal(on, ref_n) and (on == 100).all()
+    sample = np.arange(0, m.n_users, 31).astype(np.int32)
+    assert _check(m, o, ds, sample, 100, True, oi[sample], os_[sample], on[sample]) <= 2
+    assert len(np.flatnonzero((oi != ref_i).any(axis=1))) <= m.n_users // 20
+    # default capacity (4096) but a first slice of only 256 items: tau = the 100th best of 256, so about 3,500 +- 350
+    # keys pass per user and a few per cent of the lists overflow -- handled entirely on the device
+    monkeypatch.delenv('DRB_TOPK_CAP')
+    monkeypatch.setenv('DRB_TOPK_NS', '256')
+    oi, os_, on = m.topk_batch(uids, 100, novelty=True)
+    assert np.array_equal(on, ref_n)
+    assert _check(m, o, ds, sample, 100, True, oi[sample], os_[sample], on[sample]) <= 2
