@@ -237,7 +237,7 @@ k_umma_score_filter(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
           uint32_t seen = 0u;
           if (p.seen_bits && row + j < p.M && ib < p.words_per_row)
             seen = __ldg(p.seen_bits + (int64_t)(row + j) * p.words_per_row + ib);
-          const bool pass = item_ok && !((seen >> lane) & 1u) && (ord >= my_tau[cl + j]);
+          const bool pass = item_ok && (row + j < p.M) && !((seen >> lane) & 1u) && (ord >= my_tau[cl + j]);
           r[j] = ord;
           bal[j] = __ballot_sync(0xffffffffu, pass);
         }
