@@ -32,6 +32,8 @@ __device__ __forceinline__ bool row_contains(const int32_t* lo, int n, int32_t x
   return a < n && lo[a] == x;
 }
 
+struct SelectState { uint32_t prefix; int need; int bucket_count; };
+
 // descending bitonic sort of P (power of two) 64-bit keys in shared memory
 __device__ void bitonic_desc(uint64_t* keys, int P) {
   for (int k = 2; k <= P; k <<= 1) {
@@ -126,7 +128,6 @@ __global__ void __launch_bounds__(1024) k_rank_candidates(CandScoreArgs a, int P
 // ---------------------------------------------------------------- full-catalog top-k (radix select + sort)
 constexpr int kTopkThreads = 256;
 
-struct SelectState { uint32_t prefix; int need; int bucket_count; };
 
 // one MSB-first 8-bit radix pass over `value(i)` for elements accepted by `live(i)`
 template <typename KeyFn>
@@ -234,13 +235,70 @@ __global__ void __launch_bounds__(kTopkThreads) k_topk(TopkArgs a, int P) {
 
 
 // ---------------------------------------------------------------- candidate lists of the tensor-core top-k (umma_score.cu)
-// One CTA per user: sorts the user's list of 64-bit keys (descending) in shared memory.
-//   final == 0: keeps the best k at the head of the list and publishes tau = orderable score of the k-th (0 while
-//               fewer than k exist: the next pass then takes everything);
-//   final != 0: emits the answer.  A list that overflowed its capacity marks the user (n_out = -1) for the fallback.
+// Finds, among hist[0..256), the largest digit d with sum_{b >= d} hist[b] >= need (need >= 1, total >= need).
+// Executed by warp 0; results through `st` (need = rank wanted inside bucket d, bucket_count = hist[d]).
+__device__ __forceinline__ void pick_digit_warp(const int* hist, uint32_t prefix, int shift, SelectState* st) {
+  const int lane = threadIdx.x & 31;
+  int local = 0;
+#pragma unroll
+  for (int b = 0; b < 8; b++) local += hist[lane * 8 + b];
+  int v = local;                                   // inclusive suffix sum over lanes >= lane
+#pragma unroll
+  for (int off = 1; off < 32; off <<= 1) {
+    const int t = __shfl_down_sync(0xffffffffu, v, off);
+    if (lane + off < 32) v += t;
+  }
+  const int need = st->need;
+  const uint32_t ge = __ballot_sync(0xffffffffu, v >= need);
+  const int L = 31 - __clz(ge);                    // v decreases with the lane: the last lane that still reaches `need`
+  if (lane == L) {
+    int rem = need - (v - local), d = lane * 8 + 7;
+    for (; d > lane * 8; d--) {
+      if (hist[d] >= rem) break;
+      rem -= hist[d];
+    }
+    st->need = rem;
+    st->bucket_count = hist[d];
+    st->prefix = prefix | ((uint32_t)d << shift);
+  }
+}
+
+// k-th largest (need = k) of the 32-bit values value(i), i < n, accepted by the functor: 4 MSB-first 8-bit passes over
+// shared-memory keys.  On return st->prefix = that value, st->need = how many of the values equal to it belong to the
+// top `need`, st->bucket_count = how many values equal it.  All threads of the CTA call it.
+template <typename KeyFn>
+__device__ void radix_select_u32(int n, int need, KeyFn key, int* hist, SelectState* st) {
+  if (threadIdx.x == 0) { st->need = need; st->prefix = 0; }
+  __syncthreads();
+  uint32_t pm = 0;
+  for (int shift = 24; shift >= 0; shift -= 8) {
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) hist[i] = 0;
+    __syncthreads();
+    const uint32_t prefix = st->prefix;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+      uint32_t kx;
+      if (key(i, &kx) && (kx & pm) == prefix) atomicAdd(&hist[(kx >> shift) & 0xff], 1);
+    }
+    __syncthreads();
+    if (threadIdx.x < 32) pick_digit_warp(hist, prefix, shift, st);
+    __syncthreads();
+    pm |= 0xffu << shift;
+  }
+}
+
+// One CTA per user over the user's list of 64-bit keys (orderable score << 32 | iid), copied to shared memory once.
+//   final == 0 (after the first item slice): radix-selects tau = the k-th best score, keeps the keys >= tau at the head
+//               of the list (unordered) and publishes tau (0 while fewer than k exist: the next pass takes everything);
+//   final != 0: radix-selects the k best keys -- score first, item id among equal scores, i.e. heapq.nlargest on
+//               (score, iid) tuples (cdae.py:102-103) -- sorts those k and emits them.
+// A list that overflowed its capacity marks the user (n_out = -1) for the exact fallback.
 __global__ void __launch_bounds__(256) k_select_lists(uint64_t* lists, int cap, int32_t* cnt, uint32_t* tau_ord, int k,
-                                                      int final, int32_t* out_iid, float* out_score, int32_t* n_out) {
-  extern __shared__ uint64_t keys[];
+                                                      int final, int P, int32_t* out_iid, float* out_score,
+                                                      int32_t* n_out) {
+  extern __shared__ uint64_t sm_keys[];            // [cap] the list, then [P] the selected keys (final)
+  __shared__ int hist[256];
+  __shared__ SelectState st;
+  __shared__ int n_sel;
   const int u = blockIdx.x;
   const int c = cnt[u];
   uint64_t* list = lists + (int64_t)u * cap;
@@ -251,21 +309,59 @@ __global__ void __launch_bounds__(256) k_select_lists(uint64_t* lists, int cap, 
     }
     return;
   }
-  int P = 32;
-  while (P < c) P <<= 1;
-  for (int i = threadIdx.x; i < P; i += blockDim.x) keys[i] = i < c ? list[i] : 0ull;
+  for (int i = threadIdx.x; i < c; i += blockDim.x) sm_keys[i] = list[i];
+  if (threadIdx.x == 0) n_sel = 0;
   __syncthreads();
-  bitonic_desc(keys, P);
-  if (final) {
-    emit_sorted(keys, P, k, out_iid + (int64_t)u * k, out_score + (int64_t)u * k, n_out + u);
+  auto ord_key = [&](int i, uint32_t* out) { *out = (uint32_t)(sm_keys[i] >> 32); return true; };
+  if (!final) {
+    if (c < k) {                    // fewer than k so far: keep everything, no threshold yet
+      if (threadIdx.x == 0) tau_ord[u] = 0u;
+      return;
+    }
+    radix_select_u32(c, k, ord_key, hist, &st);
+    const uint32_t t32 = st.prefix;
+    for (int i = threadIdx.x; i < c; i += blockDim.x) {
+      const uint64_t key = sm_keys[i];
+      if ((uint32_t)(key >> 32) >= t32) list[atomicAdd(&n_sel, 1)] = key;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) { cnt[u] = n_sel; tau_ord[u] = t32; }
     return;
   }
-  const int kk = min(c, k);
-  for (int i = threadIdx.x; i < kk; i += blockDim.x) list[i] = keys[i];
-  if (threadIdx.x == 0) {
-    cnt[u] = kk;
-    tau_ord[u] = (c >= k) ? (uint32_t)(keys[k - 1] >> 32) : 0u;
+  uint64_t* sel = sm_keys + cap;
+  for (int i = threadIdx.x; i < P; i += blockDim.x) sel[i] = 0ull;
+  const int kk = min(k, c);
+  if (kk == 0) {
+    if (threadIdx.x == 0) n_out[u] = 0;
+    return;
   }
+  uint32_t t32 = 0, tiid = 0;
+  if (kk < c) {
+    radix_select_u32(c, kk, ord_key, hist, &st);
+    t32 = st.prefix;
+    const int need_eq = st.need, count_eq = st.bucket_count;
+    __syncthreads();
+    if (need_eq < count_eq) {       // ties on the threshold score: the need_eq largest item ids among them
+      auto iid_key = [&](int i, uint32_t* out) {
+        *out = (uint32_t)(sm_keys[i] & 0xffffffffu);
+        return (uint32_t)(sm_keys[i] >> 32) == t32;
+      };
+      radix_select_u32(c, need_eq, iid_key, hist, &st);
+      tiid = st.prefix;
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < c; i += blockDim.x) {
+    const uint64_t key = sm_keys[i];
+    const uint32_t o = (uint32_t)(key >> 32), id = (uint32_t)(key & 0xffffffffu);
+    if (kk == c || o > t32 || (o == t32 && id >= tiid)) {
+      const int pos = atomicAdd(&n_sel, 1);
+      if (pos < P) sel[pos] = key;
+    }
+  }
+  __syncthreads();
+  bitonic_desc(sel, P);
+  emit_sorted(sel, P, k, out_iid + (int64_t)u * k, out_score + (int64_t)u * k, n_out + u);
 }
 
 // Exact fallback for users whose candidate list overflowed: claims a scratch row, fills it with the user's scores
@@ -337,15 +433,17 @@ int launch_select_lists(drb_ctx* ctx, uint64_t* lists, int cap, int32_t* cnt, ui
                         int32_t* out_iid, float* out_score, int32_t* n_out, int n) {
   if (n <= 0) return DRB_OK;
   if (cap < 32 || (cap & (cap - 1)) || cap > 8192) return drb_fail(DRB_E_INVALID, "select_lists: cap must be a power of two in [32, 8192]");
+  if (k < 1 || k > 2048) return drb_fail(DRB_E_INVALID, "select_lists: k must be in [1, 2048]");
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(k_select_lists, cudaFuncAttributeMaxDynamicSharedMemorySize, 8192 * 8);
+    cudaError_t e = cudaFuncSetAttribute(k_select_lists, cudaFuncAttributeMaxDynamicSharedMemorySize, (8192 + 2048) * 8);
     if (e != cudaSuccess) return drb_fail(DRB_E_CUDA, "cudaFuncSetAttribute(k_select_lists) failed: %s", cudaGetErrorString(e));
     attr_set = true;
   }
-  drb_prof_scope prof_(ctx, "k_select_lists");
-  k_select_lists<<<n, 256, (size_t)cap * sizeof(uint64_t), ctx->stream>>>(lists, cap, cnt, tau_ord, k, final ? 1 : 0, out_iid,
-                                                                         out_score, n_out);
+  const int P = next_pow2(k);
+  drb_prof_scope prof_(ctx, final ? "k_select_lists_final" : "k_select_lists_tau");
+  k_select_lists<<<n, 256, (size_t)(cap + (final ? P : 0)) * sizeof(uint64_t), ctx->stream>>>(
+      lists, cap, cnt, tau_ord, k, final ? 1 : 0, P, out_iid, out_score, n_out);
   DRB_LAUNCH_CHECK(ctx, "k_select_lists");
   return DRB_OK;
 }

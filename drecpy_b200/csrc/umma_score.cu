@@ -50,6 +50,8 @@ struct ScoreParams {
   int32_t* cnt;                            // [M] entries appended so far (may exceed cap: overflow)
   uint64_t* lists; int cap;                // [M][cap]
   int m_tiles, n_tiles;
+  int debug;   // DRB_SCORE_DEBUG bit mask (profiling experiments only, results are wrong): 1 = no appends, 2 = no seen
+               // bitmap loads, 4 = no MMAs, 8 = no sigmoid
 };
 
 __device__ __forceinline__ float sc_ex2(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
@@ -163,7 +165,7 @@ k_umma_score_filter(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
           const uint32_t sa_hi = base + s * S::STAGE_BYTES, sa_lo = sa_hi + S::A_BYTES;
           const uint32_t sb_hi = sa_lo + S::A_BYTES, sb_lo = sb_hi + S::B_BYTES;
 #pragma unroll
-          for (int kk = 0; kk < BK / UMMA_K; kk++) {
+          for (int kk = 0; kk < ((p.debug & 4) ? 0 : BK / UMMA_K); kk++) {
             const uint64_t a_hi = make_desc_kmajor<BK>(sa_hi, kk), a_lo = make_desc_kmajor<BK>(sa_lo, kk);
             const uint64_t b_hi = make_desc_kmajor<BK>(sb_hi, kk), b_lo = make_desc_kmajor<BK>(sb_lo, kk);
             if (CL > 1) {
@@ -232,14 +234,14 @@ k_umma_score_filter(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
 #pragma unroll
         for (int j = 0; j < 16; j++) {
           const float z = __uint_as_float(r[j]) + bias;
-          const float pr = sc_rcp(1.0f + sc_ex2(z * -1.4426950408889634f));     // sigmoid, > 0
+          const float pr = (p.debug & 8) ? fabsf(z) : sc_rcp(1.0f + sc_ex2(z * -1.4426950408889634f));   // sigmoid, > 0
           const uint32_t ord = __float_as_uint(pr) | 0x80000000u;               // f2ord of a non-negative float
           uint32_t seen = 0u;
-          if (p.seen_bits && row + j < p.M && ib < p.words_per_row)
+          if (p.seen_bits && !(p.debug & 2) && row + j < p.M && ib < p.words_per_row)
             seen = __ldg(p.seen_bits + (int64_t)(row + j) * p.words_per_row + ib);
           const bool pass = item_ok && (row + j < p.M) && !((seen >> lane) & 1u) && (ord >= my_tau[cl + j]);
           r[j] = ord;
-          bal[j] = __ballot_sync(0xffffffffu, pass);
+          bal[j] = (p.debug & 1) ? 0u : __ballot_sync(0xffffffffu, pass);
         }
         // 2. one atomicAdd per (warp, user) reserves the slots of the passing lanes (all issued before any is consumed)
         int slot[16];
@@ -314,7 +316,7 @@ int run_score(drb_ctx* ctx, const UmmaOperands& o, ScoreParams p, int n_items) {
   const int n_units = ((p.m_tiles + CL - 1) / CL) * p.n_tiles;
   if (n_units <= 0) return DRB_OK;
   const int grid = CL * std::min(n_units, CL > 1 ? max_clusters : ctx->sm_count);
-  drb_prof_scope prof_(ctx, "k_umma_score_filter");
+  drb_prof_scope prof_(ctx, p.item_begin == 0 ? "k_umma_score_filter_slice" : "k_umma_score_filter_rest");
   if (CL > 1) {
     cudaLaunchConfig_t cfg{};
     cudaLaunchAttribute at[1];
@@ -341,6 +343,7 @@ int launch_umma_score_filter(drb_ctx* ctx, const UmmaOperands& o, int n_users, i
   ScoreParams p{};
   p.M = n_users; p.item_begin = item_begin; p.item_end = item_end; p.Kred = Kred; p.bias = bias;
   p.seen_bits = seen_bits; p.words_per_row = words_per_row; p.tau_ord = tau_ord; p.cnt = cnt; p.lists = lists; p.cap = cap;
+  p.debug = getenv("DRB_SCORE_DEBUG") ? atoi(getenv("DRB_SCORE_DEBUG")) : 0;
   if (n_users > 128) return run_score<256, 32, 2>(ctx, o, p, n_items);
   return run_score<128, 32, 1>(ctx, o, p, n_items);
 }
