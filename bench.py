@@ -455,7 +455,7 @@ def run_cdae_native(args, cfg, D, arrays=None):
     value = B * world * K / (ms_total * 1e-3)
     line = base_line(cfg, 'cdae_training_samples_per_sec', 'samples/s', value, world, K, W, ms_total,
                      cdae_config(cfg, world, f'item-sharded x{world}' if items_mode else f'dp{world}', flush),
-                     clock_info, launches)
+                     clock_info, launches, scaling='strong' if cfg.get('strong') else 'weak')
     line.update({'e2e': {'value': B * world * K / t_e2e, 'unit': 'samples/s', 'h2d_bytes_per_step': h2d,
                          'd2h_bytes_per_step': 4, 'ms_per_step': 1e3 * t_e2e / K},
                  'roofline': roofline, 'cpu_baseline': cpu, 'kernels_ms_per_step': kernels,
@@ -878,10 +878,17 @@ def main():
     ap.add_argument('--no-extras', action='store_true')
     ap.add_argument('--no-flush', action='store_true', help='c1 / c2: back-to-back steps instead of an L2 flush per step')
     ap.add_argument('--no-dp-parity', action='store_true')
+    ap.add_argument('--scaling', default='weak', choices=['weak', 'strong'],
+                    help='c3, N>1: weak = 4096 users per GPU (default, the driver\'s curve); strong = 4096 users globally')
     ap.add_argument('--parallel', default='data', choices=['data', 'items'],
                     help='N>1: data = replicated weights + gradient all-reduce; items = item-sharded weights')
     args = ap.parse_args()
     cfg = dict(WORKLOADS[args.workload])
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    if args.scaling == 'strong' and cfg['model'] == 'cdae' and world > 1:
+        assert cfg['batch'] % world == 0
+        cfg['batch'] //= world                        # the global batch stays what BASELINE.json names
+        cfg['strong'] = True
     native, reference = RUNNERS[cfg['model']]
     if args.impl == 'reference':
         if int(os.environ.get('RANK', '0')) == 0:

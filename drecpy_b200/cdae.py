@@ -21,7 +21,7 @@ import random
 import numpy as np
 
 from . import _lib
-from .parallel import DataParallel
+from .parallel import DataParallel, data_parallel_step
 from .recommender import DeepRecommenderABC
 from .sampler import PointSampler
 
@@ -360,34 +360,22 @@ class CDAE(DeepRecommenderABC):
             return
         if self._sharded:
             return self._step_device_sharded(uids_dev, args, ptrs)
-        # data parallel: the collectives run on NCCL's stream while the next phase computes
-        #   PREP | all-reduce(label histogram) || GRADS_A | GRADS_B | all-reduce(dW'^T) || GRADS_C |
-        #   all-gather(uids, dz1 rows) -> dV | all-reduce(dW, db, db') | UPDATE
+        # data parallel: drecpy_b200.parallel.data_parallel_step runs the phases with the collectives between them
         torch = self._torch
-        dist, L = dp.dist, self._L
-        PREP, GA, UPD, GB, GC = 1, 2, 4, 8, 16
-        _lib.check(lib.drb_cdae_step_phases(*ptrs, PREP))
-        h_lab = None
-        if self.label_mode == 'batch_mean':
-            h_lab = dist.all_reduce(self._label_count, op=dist.ReduceOp.SUM, group=dp.group, async_op=True)
-        _lib.check(lib.drb_cdae_step_phases(*ptrs, GA))
-        if h_lab is not None:
-            h_lab.wait()
-        _lib.check(lib.drb_cdae_step_phases(*ptrs, GB))
-        h_w2t = dist.all_reduce(self._grads[:L.off_w], op=dist.ReduceOp.SUM, group=dp.group, async_op=True)
-        _lib.check(lib.drb_cdae_step_phases(*ptrs, GC))
-        # user-row gradients: all-gather the B x K rows (never the U x K table), add them locally
+        L = self._L
         B = uids_dev.numel()
         if not hasattr(self, '_dp_gather') or self._dp_gather[0].shape[0] != B * dp.world:
             self._dp_gather = (torch.empty((B * dp.world, L.ld), dtype=torch.float32, device=self._dev),
                                torch.empty(B * dp.world, dtype=torch.int32, device=self._dev))
         rows_all, uids_all = self._dp_gather
-        dist.all_gather_into_tensor(rows_all, self._dz1[:B], group=dp.group)
-        dist.all_gather_into_tensor(uids_all, uids_dev, group=dp.group)
-        _lib.check(lib.drb_cdae_scatter_user_rows(self._native, _lib.t_ptr(uids_all), _lib.t_ptr(rows_all), B * dp.world))
-        dp.all_reduce_sum(self._grads[L.off_w:L.off_v])      # dW, db, db' (dense)
-        h_w2t.wait()
-        _lib.check(lib.drb_cdae_step_phases(*ptrs, UPD))
+
+        def run_phase(mask):
+            _lib.check(lib.drb_cdae_step_phases(*ptrs, mask))
+
+        def add_user_rows(u_all, r_all):       # user-row gradients: B x K rows travel, never the U x K table
+            _lib.check(lib.drb_cdae_scatter_user_rows(self._native, _lib.t_ptr(u_all), _lib.t_ptr(r_all), u_all.numel()))
+        data_parallel_step(dp, run_phase, self._label_count if self.label_mode == 'batch_mean' else None, self._grads,
+                           L.off_w, L.off_v, self._dz1[:B], uids_dev, rows_all, uids_all, add_user_rows)
 
     def _step_device_sharded(self, uids_dev, args, ptrs):
         """Item-sharded step: rows of W / W' / V never travel; the two exchanges are all-reduces of batch x hidden

@@ -172,6 +172,8 @@ struct drb_cdae {
   bool use_umma;
   bool v_grad_clean;   // the dV region of the gradient arena is known to be all zero
   int n_loss_blocks;
+  const int32_t* rows_uids; int rows_n;   // user rows added by the last drb_cdae_scatter_user_rows (re-zeroed after Adam)
+  bool reg_slots_clear;                   // the three reg_part slots were zeroed in PREP (split UPDATE of this step)
   int n2, batch_pad;   // tcgen05 path: N of the backward GEMMs (hidden + ones feature, rounded to 16), padded batch
   float* z_dbg;        // tests only: drb_debug_cdae_capture_logits
 };
@@ -200,7 +202,7 @@ static CdaeWs cdae_carve(void* base, const drb_cdae_layout_t& L, int n_items, in
   w.col_b2 = c.take<float>((int64_t)mt * L.items_pad);
   w.col_b = c.take<float>((int64_t)colpart_blocks(max_batch) * L.ld);
   w.loss_part = c.take<float>((int64_t)mt * ((L.items_pad + 63) / 64));
-  w.reg_part = c.take<float>((int64_t)sm_count * 16);
+  w.reg_part = c.take<float>((int64_t)sm_count * 16 * 3);   // three slots: split UPDATE launches (data parallel)
   w.label_count = c.take<float>(L.items_pad);
   w.loss_scalar = c.take<float>(64);
   const int64_t words = (L.items_pad + 31) / 32;
@@ -285,6 +287,7 @@ int drb_cdae_create(drb_ctx* ctx, const drb_cdae_desc* desc, drb_cdae** out) {
   m->use_umma = umma_ok && desc->gemm_path != DRB_GEMM_FFMA;
   m->v_grad_clean = false;
   m->z_dbg = nullptr;
+  m->rows_uids = nullptr; m->rows_n = 0; m->reg_slots_clear = false;
   if (m->use_umma) {
     // dh = dz W'^T on the tensor cores has one 128 x n2 tile per 128 users: split the item range so that the grid
     // is ~2 waves of the SM count (the kernel is L2/HBM bandwidth bound, one CTA per SM)
@@ -357,6 +360,7 @@ int drb_cdae_dz1_buffer(drb_cdae* m, float** ptr, int64_t* count) {
 
 int drb_cdae_scatter_user_rows(drb_cdae* m, const int32_t* uids, const float* rows, int32_t n) {
   if (!m || !uids || !rows || n < 0) return drb_fail(DRB_E_INVALID, "drb_cdae_scatter_user_rows: bad argument");
+  m->rows_uids = uids; m->rows_n = n;     // borrowed until the UPDATE of this step: those rows are re-zeroed after Adam
   return launch_row_scatter(m->ctx, uids, rows, n, m->L.ld, m->d.grads + m->L.off_v);
 }
 
@@ -405,10 +409,12 @@ int drb_cdae_step_phases(drb_cdae* m, const int32_t* uids, const int32_t* keep_o
   const int64_t clear_from = m->use_umma ? 0 : L.off_w;
   // dV (U x K, the largest gradient) is only touched in the rows of the sampled users: on the plain single-process
   // step those rows are re-zeroed after the update (k_zero_rows) instead of clearing the whole table every step
-  const bool sparse_clear_v = !a->skip_user_grad && !sharded && m->v_grad_clean;
+  const bool sparse_clear_v = !sharded && m->v_grad_clean;
   const int64_t clear_to = sparse_clear_v ? L.off_v : L.total;
   DRB_CUDA_TRY(ctx, cudaMemsetAsync(G + clear_from, 0, (size_t)(clear_to - clear_from) * sizeof(float), ctx->stream));
   m->v_grad_clean = false;
+  m->rows_uids = nullptr; m->rows_n = 0;
+  m->reg_slots_clear = false;
   if (per_user)
     DRB_CUDA_TRY(ctx, cudaMemsetAsync(w.label_bits, 0, (size_t)batch * m->words_per_row * 4, ctx->stream));
   else
@@ -531,9 +537,12 @@ int drb_cdae_step_phases(drb_cdae* m, const int32_t* uids, const int32_t* keep_o
   if ((r = launch_scatter(ctx, sc, batch))) return r;
   }  // GRADS_C / GRADS_C2 (data parallel: the caller exchanges dz1 rows and all-reduces dW, db here)
 
-  if (!(phases & DRB_PHASE_UPDATE)) return DRB_OK;
-  const float inv_count_u = inv_count;
-  // 7. K4: fused Adam + L2 over the arena; t per reference variable [W, W_, V, b, b_]
+  const int upd = phases & (DRB_PHASE_UPDATE | DRB_PHASE_UPDATE_V | DRB_PHASE_UPDATE_W2T | DRB_PHASE_UPDATE_REST);
+  if (!upd) return DRB_OK;
+  // 7. K4: fused Adam + L2 over the arena; t per reference variable [W, W_, V, b, b_].  DRB_PHASE_UPDATE = one launch
+  //    over everything.  Data parallel: three launches, each as soon as ITS gradient is final -- V after the user rows
+  //    have been added, W2T after its all-reduce, the rest (W, b, b2) after theirs -- so the last all-reduce runs under
+  //    the V update (72 % of the Adam bytes at the ml-20m shape).
   AdamArgs ad{};
   ad.w = P; ad.m = m->d.adam_m; ad.v = m->d.adam_v; ad.g = G;
   ad.beta1 = a->beta1; ad.beta2 = a->beta2; ad.eps = a->epsilon;
@@ -541,22 +550,53 @@ int drb_cdae_step_phases(drb_cdae* m, const int32_t* uids, const int32_t* keep_o
   const int64_t offs[6] = {L.off_w2t, L.off_w, L.off_b, L.off_b2, L.off_v, L.total};   // arena order
   const int tmap[5] = {1, 0, 3, 4, 2};                                                  // -> [W, W_, V, b, b_]
   const bool l2seg[5] = {true, true, false, false, true};
-  for (int sidx = 0; sidx < 5; sidx++) {
-    ad.seg[sidx].off4 = offs[sidx] / 4;
-    ad.seg[sidx].n4 = (offs[sidx + 1] - offs[sidx]) / 4;
-    ad.seg[sidx].alpha = drb_adam_alpha(a->learning_rate, a->beta1, a->beta2, a->t[tmap[sidx]]);
-    ad.seg[sidx].l2 = l2seg[sidx] ? c : 0.f;
-    ad.seg[sidx].regw = l2seg[sidx] ? 0.5f * c : 0.f;
-  }
-  ad.nseg = 5;
-  ad.reg_part = w.reg_part;
+  const int R = ctx->sm_count * 16;                                  // one reg_part slot
+  auto run_adam = [&](int first, int last, int slot, int* n_out) -> int {   // arena segments [first, last]
+    int ns = 0;
+    for (int sidx = first; sidx <= last; sidx++, ns++) {
+      ad.seg[ns].off4 = offs[sidx] / 4;
+      ad.seg[ns].n4 = (offs[sidx + 1] - offs[sidx]) / 4;
+      ad.seg[ns].alpha = drb_adam_alpha(a->learning_rate, a->beta1, a->beta2, a->t[tmap[sidx]]);
+      ad.seg[ns].l2 = l2seg[sidx] ? c : 0.f;
+      ad.seg[ns].regw = l2seg[sidx] ? 0.5f * c : 0.f;
+    }
+    ad.nseg = ns;
+    ad.reg_part = w.reg_part + (int64_t)slot * R;
+    return launch_adam(ctx, ad, n_out);
+  };
+  auto rezero_user_rows = [&]() -> int {      // leave dV all-zero again for the next step (see PREP)
+    if (sharded) return DRB_OK;
+    if (!a->skip_user_grad) {
+      if ((r = launch_zero_rows(ctx, G + L.off_v, uids, batch, ld))) return r;
+      m->v_grad_clean = true;
+    } else if (m->rows_uids) {                // data parallel: the rows every rank added from the all-gathered list
+      if ((r = launch_zero_rows(ctx, G + L.off_v, m->rows_uids, m->rows_n, ld))) return r;
+      m->v_grad_clean = true;
+    }
+    return DRB_OK;
+  };
   int n_reg = 0;
-  if ((r = launch_adam(ctx, ad, &n_reg))) return r;
-  if (!a->skip_user_grad && !sharded) {   // leave dV all-zero again for the next step (see PREP)
-    if ((r = launch_zero_rows(ctx, G + L.off_v, uids, batch, ld))) return r;
-    m->v_grad_clean = true;
+  if (phases & DRB_PHASE_UPDATE) {
+    if ((r = run_adam(0, 4, 0, &n_reg))) return r;
+    if ((r = rezero_user_rows())) return r;
+    return launch_finalize_loss(ctx, w.loss_part, m->n_loss_blocks, inv_count, w.reg_part, n_reg, loss_out);
   }
-  return launch_finalize_loss(ctx, w.loss_part, m->n_loss_blocks, inv_count_u, w.reg_part, n_reg, loss_out);
+  if (!m->reg_slots_clear) {   // split form: unused entries of the three partial-sum slots must read as zero
+    DRB_CUDA_TRY(ctx, cudaMemsetAsync(w.reg_part, 0, (size_t)3 * R * sizeof(float), ctx->stream));
+    m->reg_slots_clear = true;
+  }
+  if (phases & DRB_PHASE_UPDATE_V) {
+    if ((r = run_adam(4, 4, 0, &n_reg))) return r;
+    if ((r = rezero_user_rows())) return r;
+  }
+  if (phases & DRB_PHASE_UPDATE_W2T) {
+    if ((r = run_adam(0, 0, 1, &n_reg))) return r;
+  }
+  if (phases & DRB_PHASE_UPDATE_REST) {
+    if ((r = run_adam(1, 3, 2, &n_reg))) return r;
+    return launch_finalize_loss(ctx, w.loss_part, m->n_loss_blocks, inv_count, w.reg_part, 3 * R, loss_out);
+  }
+  return DRB_OK;
 }
 
 int drb_cdae_step_host(drb_cdae* m, const int32_t* uids, const int32_t* keep_off, const uint8_t* keep,

@@ -17,7 +17,7 @@ __global__ void __launch_bounds__(kAdamThreads) k_adam(AdamArgs a, int64_t total
   __shared__ float sred[kAdamThreads];
   float reg = 0.f;
   const float omb1 = 1.0f - a.beta1, omb2 = 1.0f - a.beta2;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total4;
+  for (int64_t i = a.seg[0].off4 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total4;
        i += (int64_t)gridDim.x * blockDim.x) {
     int s = 0;
 #pragma unroll 1
@@ -99,8 +99,8 @@ float drb_adam_alpha(float lr, float beta1, float beta2, int t) {
 
 int launch_adam(drb_ctx* ctx, const AdamArgs& a, int* n_blocks_out) {
   if (a.nseg < 1 || a.nseg > DRB_MAX_SEGS) return drb_fail(DRB_E_INVALID, "adam: bad segment count");
-  const int64_t total4 = a.seg[a.nseg - 1].off4 + a.seg[a.nseg - 1].n4;
-  int64_t want = (total4 + kAdamThreads - 1) / kAdamThreads;
+  const int64_t total4 = a.seg[a.nseg - 1].off4 + a.seg[a.nseg - 1].n4;      // the launch covers [seg[0].off4, total4)
+  int64_t want = (total4 - a.seg[0].off4 + kAdamThreads - 1) / kAdamThreads;
   // 16 float4 per thread in flight across the grid keeps HBM busy; grid is a multiple of the SM count
   int blocks = (int)std::min<int64_t>(want, (int64_t)ctx->sm_count * 16);
   if (blocks < 1) blocks = 1;

@@ -176,7 +176,14 @@ enum {
    * GRADS_A2 applies the sigmoid; GRADS_C leaves the partial dh in drb_cdae_dz1_buffer() (all-reduce it), then
    * GRADS_C2 forms dz1 and scatters.  Rows of W / W' / V never travel, only batch x hidden activations do. */
   DRB_PHASE_GRADS_A2 = 32,
-  DRB_PHASE_GRADS_C2 = 64
+  DRB_PHASE_GRADS_C2 = 64,
+  /* UPDATE in three launches (data parallel), each as soon as its gradient is final, so that the last gradient
+   * all-reduce runs under the update of V: UPDATE_V (after drb_cdae_scatter_user_rows), UPDATE_W2T (after the
+   * all-reduce of grads[0, off_w)), UPDATE_REST (W, b, b2 after the all-reduce of grads[off_w, off_v); writes the loss).
+   * All three must run, UPDATE_REST last. */
+  DRB_PHASE_UPDATE_V = 128,
+  DRB_PHASE_UPDATE_W2T = 256,
+  DRB_PHASE_UPDATE_REST = 512
 };
 
 int drb_cdae_create(drb_ctx* ctx, const drb_cdae_desc* desc, drb_cdae** out);
