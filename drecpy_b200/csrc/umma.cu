@@ -156,8 +156,10 @@ k_umma_gemm(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t sa_hi = base + s * S::STAGE_BYTES, sa_lo = sa_hi + S::A_BYTES;
         const uint32_t sb_hi = sa_lo + S::A_BYTES, sb_lo = sb_hi + S::B_BYTES;
-#pragma unroll
-        for (int kk = 0; kk < BK / UMMA_K; kk++) {
+        // last k-block of the reduction: MMAs over the zero-filled tail of the box are not issued
+        const int kk_n = min(BK / UMMA_K, (p.Kred - (kb_beg + i) * BK + UMMA_K - 1) / UMMA_K);
+#pragma unroll 1
+        for (int kk = 0; kk < kk_n; kk++) {
           uint64_t a_hi, a_lo;
           if (A_MN) {   // MN-major: rows = k (128 B = 32 m each); K atoms of 4 rows are 512 B apart, one MMA (K=8)
                         // spans two of them; MN atoms (32 floats, one TMA box of BK rows) are BK * 128 B apart

@@ -170,8 +170,11 @@ k_umma_cdae_loss(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           const uint32_t sa_hi = base + s * S::STAGE_BYTES, sa_lo = sa_hi + S::A_BYTES;
           const uint32_t sb_hi = sa_lo + S::A_BYTES, sb_lo = sb_hi + S::B_BYTES;
-#pragma unroll
-          for (int kk = 0; kk < ((p.debug & 16) ? 0 : BK / UMMA_K); kk++) {
+          // the last k-block holds fewer than BK real columns (K = 200: 6 full blocks + 8 columns): TMA zero-fills the
+          // rest of the box, the MMAs over those zeros are simply not issued
+          const int kk_n = (p.debug & 16) ? 0 : min(BK / UMMA_K, (p.Kred - kb * BK + UMMA_K - 1) / UMMA_K);
+#pragma unroll 1
+          for (int kk = 0; kk < kk_n; kk++) {
             const uint64_t a_hi = make_desc_kmajor<BK>(sa_hi, kk), a_lo = make_desc_kmajor<BK>(sa_lo, kk);
             const uint64_t b_hi = make_desc_kmajor<BK>(sb_hi, kk), b_lo = make_desc_kmajor<BK>(sb_lo, kk);
             if (CL > 1) {
