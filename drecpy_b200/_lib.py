@@ -13,7 +13,7 @@ LIB_PATH = os.path.join(HERE, 'libdrb.so')
 
 DRB_LOSS = {'bce': 0, 'mse': 1}
 DRB_LABEL = {'batch_mean': 0, 'per_user': 1}
-DRB_GEMM = {'auto': 0, 'ffma': 1, 'tcgen05': 2}
+DRB_GEMM = {'auto': 0, 'ffma': 1, 'tcgen05': 2, 'tcgen05_tf32': 3}
 DMF_MAX_LAYERS = 8
 
 vp = C.c_void_p
@@ -122,6 +122,8 @@ SIGNATURES = {
     'drb_debug_cdae_capture_logits': (C.c_int, [vp, vp]),
     'drb_debug_split_tf32': (C.c_int, [vp, vp, i32, i32, i32, vp, vp, vp, vp, i32, i32]),
     'drb_debug_umma_gemm': (C.c_int, [vp, vp, vp, i32, vp, vp, i32, i32, i32, i32, i32, i32, i32, vp, i32, i32, vp, i32]),
+    'drb_debug_split_f16': (C.c_int, [vp, vp, i32, i32, i32, f32, vp, vp, i32, vp, vp, i32, i32]),
+    'drb_debug_umma_gemm_f16': (C.c_int, [vp, vp, vp, i32, vp, vp, i32, i32, i32, i32, i32, i32, f32, vp, i32, i32, vp, i32]),
     'drb_eval_candidates': (C.c_int, [i64, vp, vp, vp, vp, vp, vp, vp, vp, i64, i32, i64, f64, i64, f64, i32, i32, i64,
                                       i32, i64, vp, vp, vp, vp, vp]),
     'drb_leave_k_out': (C.c_int, [i64, vp, i64, f64, i32, i64, i64, i32, vp]),

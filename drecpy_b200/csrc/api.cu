@@ -148,6 +148,23 @@ int drb_debug_umma_gemm(drb_ctx* ctx, const float* a_hi, const float* a_lo, int3
                            extra_col_index);
 }
 
+int drb_debug_split_f16(drb_ctx* ctx, const float* src, int32_t rows, int32_t cols, int32_t ld, float alpha, void* hi,
+                        void* lo, int32_t ldh, void* t_hi, void* t_lo, int32_t ldt, int32_t ones_row) {
+  if (!ctx || !src) return drb_fail(DRB_E_INVALID, "drb_debug_split_f16: NULL argument");
+  return launch_split_f16(ctx, src, rows, cols, ld, alpha, nullptr, hi, lo, ldh, t_hi, t_lo, ldt, ones_row);
+}
+
+int drb_debug_umma_gemm_f16(drb_ctx* ctx, const void* a_hi, const void* a_lo, int32_t lda, const void* b_hi,
+                            const void* b_lo, int32_t ldb, int32_t b_rows, int32_t M, int32_t N, int32_t Kred,
+                            int32_t splits, float out_scale, float* C, int32_t ldc, int32_t n_store, float* extra_col,
+                            int32_t extra_col_index) {
+  if (!ctx || !a_hi || !a_lo || !b_hi || !b_lo || !C) return drb_fail(DRB_E_INVALID, "drb_debug_umma_gemm_f16: NULL argument");
+  if (!umma_available()) return drb_fail(DRB_E_NODEVICE, "tcgen05/TMA path unavailable");
+  UmmaOperands o{a_hi, a_lo, lda, b_hi, b_lo, ldb, b_rows};
+  o.half = true; o.out_scale = out_scale;
+  return launch_umma_store(ctx, o, false, M, N, Kred, splits, C, ldc, n_store, n_store, extra_col, extra_col_index);
+}
+
 }  // extern "C"
 
 // ========================================================================================== CDAE
@@ -170,6 +187,8 @@ struct drb_cdae {
   int splits, words_per_row;
   int64_t keep_cap;
   bool use_umma;
+  bool half;           // tensor-core operands are fp16 hi/lo pairs (kind::f16, per-tensor power-of-two scaling); else tf32 hi/lo
+  int ldh, bp8, ip8;   // fp16 row pitches in halfs (multiples of 8): h / W' rows, transposed h, transposed W'
   bool v_grad_clean;   // the dV region of the gradient arena is known to be all zero
   int n_loss_blocks;
   const int32_t* rows_uids; int rows_n;   // user rows added by the last drb_cdae_scatter_user_rows (re-zeroed after Adam)
@@ -213,15 +232,16 @@ static CdaeWs cdae_carve(void* base, const drb_cdae_layout_t& L, int n_items, in
   w.chunk_off = c.take<int32_t>(B + 64);
   w.keep = c.take<uint8_t>(cdae_keep_cap(n_items, max_batch));
   if (umma) {
-    const int64_t n2 = cdae_n2(hidden), bp = drb_round_up(max_batch, 4);
-    w.h_hi = c.take<float>(B * L.ld);
-    w.h_lo = c.take<float>(B * L.ld);
+    // sized for tf32 hi/lo floats; the fp16 hi/lo forms (pitches rounded up to 8 halfs) need at most as many bytes
+    const int64_t n2 = cdae_n2(hidden), bp = drb_round_up(max_batch, 8);
+    w.h_hi = c.take<float>(B * (L.ld + 4));
+    w.h_lo = c.take<float>(B * (L.ld + 4));
     w.hT_floats = n2 * bp;
     w.hT_hi = c.take<float>(w.hT_floats);
     w.hT_lo = c.take<float>(w.hT_floats);
-    w.w2t_hi = c.take<float>((int64_t)n_items * L.ld);
-    w.w2t_lo = c.take<float>((int64_t)n_items * L.ld);
-    w.wT_floats = n2 * (int64_t)L.items_pad;
+    w.w2t_hi = c.take<float>((int64_t)n_items * (L.ld + 4));
+    w.w2t_lo = c.take<float>((int64_t)n_items * (L.ld + 4));
+    w.wT_floats = n2 * (int64_t)drb_round_up(L.items_pad, 8);
     w.wT_hi = c.take<float>(w.wT_floats);
     w.wT_lo = c.take<float>(w.wT_floats);
     w.dzt_hi = c.take<float>(drb_dz_tiled_floats(max_batch, n_items));
@@ -278,13 +298,20 @@ int drb_cdae_create(drb_ctx* ctx, const drb_cdae_desc* desc, drb_cdae** out) {
   m->splits = gemm_splits(ctx, desc->max_batch, L.ld, desc->n_items);
   m->words_per_row = (L.items_pad + 31) / 32;
   m->n2 = cdae_n2(desc->hidden);
-  m->batch_pad = (int)drb_round_up(desc->max_batch, 4);
+  m->batch_pad = (int)drb_round_up(desc->max_batch, 8);
   const bool umma_ok = umma_available() && m->n2 <= 256;
-  if (desc->gemm_path == DRB_GEMM_TCGEN05 && !umma_ok) {
+  if ((desc->gemm_path == DRB_GEMM_TCGEN05 || desc->gemm_path == DRB_GEMM_TCGEN05_TF32) && !umma_ok) {
     delete m;
     return drb_fail(DRB_E_INVALID, "drb_cdae_create: the tcgen05 path needs hidden <= 256 and a driver with TMA support");
   }
   m->use_umma = umma_ok && desc->gemm_path != DRB_GEMM_FFMA;
+  {   // DRB_GEMM_SPLIT=tf32 keeps the 3xTF32 products (profiling / comparison); default: 3xFP16 at twice the MMA rate
+    const char* se = getenv("DRB_GEMM_SPLIT");
+    m->half = m->use_umma && desc->gemm_path != DRB_GEMM_TCGEN05_TF32 && !(se && !strcmp(se, "tf32"));
+  }
+  m->ldh = (int)drb_round_up(L.ld, 8);
+  m->bp8 = (int)drb_round_up(desc->max_batch, 8);
+  m->ip8 = (int)drb_round_up(L.items_pad, 8);
   m->v_grad_clean = false;
   m->z_dbg = nullptr;
   m->rows_uids = nullptr; m->rows_n = 0; m->reg_slots_clear = false;
@@ -447,7 +474,19 @@ int drb_cdae_step_phases(drb_cdae* m, const int32_t* uids, const int32_t* keep_o
   }
   if ((phases & DRB_PHASE_GRADS_A2) || ((phases & DRB_PHASE_GRADS_A) && !sharded)) {
   if (sharded && (r = launch_sigmoid_rows(ctx, w.h, batch, ld, m->d.hidden))) return r;
-  if (m->use_umma) {   // tf32 hi/lo operand splits for the tensor-core GEMMs (umma.cu)
+  if (m->use_umma && m->half) {
+    // fp16 hi/lo operand splits.  h is in (0, 1): fixed scale 2^15.  W' is scaled by a power of two alpha_w that puts its
+    // largest magnitude in [2^14, 2^15) (k_absmax, then k_publish_scale: scales[0] = alpha_w, scales[1] = 1 / alpha_w).
+    float* scales = w.loss_scalar + 32;
+    const int ones = cdae_colsum_in_loss(m->d.hidden) ? -1 : m->d.hidden;
+    if ((r = launch_split_f16(ctx, w.h, batch, ld, ld, DRB_H_F16_SCALE, nullptr, w.h_hi, w.h_lo, m->ldh, w.hT_hi, w.hT_lo,
+                              m->bp8, ones)))
+      return r;
+    if ((r = launch_absmax_scale(ctx, P + L.off_w2t, I, m->d.hidden, ld, scales))) return r;
+    if ((r = launch_split_f16(ctx, P + L.off_w2t, I, ld, ld, 1.0f, scales, w.w2t_hi, w.w2t_lo, m->ldh, w.wT_hi, w.wT_lo,
+                              m->ip8, -1)))
+      return r;
+  } else if (m->use_umma) {   // tf32 hi/lo operand splits for the tensor-core GEMMs (umma.cu)
     if ((r = launch_split_tf32(ctx, w.h, batch, ld, ld, w.h_hi, w.h_lo, w.hT_hi, w.hT_lo, bp,
                                cdae_colsum_in_loss(m->d.hidden) ? -1 : m->d.hidden)))
       return r;
@@ -456,19 +495,33 @@ int drb_cdae_step_phases(drb_cdae* m, const int32_t* uids, const int32_t* keep_o
   }
   }
 
+  // fp16 dz: two tile-major copies inside the dzt buffers (kernels.h: DzHalf), hi in the first half, lo in the second
+  DzHalf dzh{};
+  const float* inv_alpha_w = w.loss_scalar + 33;
+  if (m->use_umma && m->half) {
+    const int64_t half_bytes = drb_dz_tiled_floats(m->d.max_batch, I) * 2;     // bytes of one hi (or lo) copy
+    dzh.row_tiles = (m->d.max_batch + 127) / 128; dzh.item_tiles = (I + 127) / 128;
+    dzh.nib64 = drb_dz_nib64(I); dzh.nub = 2 * dzh.row_tiles;
+    dzh.u_hi = w.dzt_hi; dzh.u_lo = reinterpret_cast<char*>(w.dzt_hi) + half_bytes;
+    dzh.i_hi = w.dzt_lo; dzh.i_lo = reinterpret_cast<char*>(w.dzt_lo) + half_bytes;
+  }
+  const float dz_unscale = inv_count / DRB_DZ_F16_SCALE;      // fp16 dz holds dL/dz2 * 2^14 / inv_count
+
   UmmaOperands o2{w.dzt_hi, w.dzt_lo, 32, w.hT_hi, w.hT_lo, bp, n2};
   o2.a_tiled_nib = drb_dz_nib(I);
   o2.a_tiled_rows = (int64_t)((m->d.max_batch + 127) / 128) * o2.a_tiled_nib * 128;
   if (phases & DRB_PHASE_GRADS_B) {
   int n_blocks = 0;
   if (m->use_umma) {
-    // 3-4 on the tensor cores: 3xTF32 split products, TMA-fed, TMEM accumulators
-    UmmaOperands o1{w.h_hi, w.h_lo, ld, w.w2t_hi, w.w2t_lo, ld, I};
+    // 3-4 on the tensor cores: fp32-accurate split products (3xFP16 or 3xTF32), TMA-fed, TMEM accumulators
+    UmmaOperands o1{w.h_hi, w.h_lo, m->half ? m->ldh : ld, w.w2t_hi, w.w2t_lo, m->half ? m->ldh : ld, I};
+    if (m->half) { o1.half = true; o1.out_scale = 1.0f / DRB_H_F16_SCALE; o1.out_scale_dev = inv_alpha_w; }
+    dzh.row_tiles = (batch + 127) / 128;        // row tiles that exist for THIS batch (the layout pitch is nub / nib64)
     if ((r = launch_umma_cdae_loss(ctx, o1, batch, I, ld, w.dzt_hi, w.dzt_lo, L.items_pad, P + L.off_b2,
                                    per_user ? nullptr : w.label_count, per_user ? w.label_bits : nullptr,
                                    m->words_per_row, m->d.loss_kind, inv_count, gbatch, w.loss_part,
                                    cdae_colsum_in_loss(m->d.hidden) ? G + L.off_b2 : nullptr, &n_blocks, m->z_dbg,
-                                   L.items_pad)))
+                                   L.items_pad, m->half ? &dzh : nullptr)))
       return r;
     // dW'^T = dz^T h (I x K); the constant-one feature at column `hidden` yields db' = colsum(dz)
     // e.g. 209 item tiles on 148 SMs would run as two uneven waves: split the batch reduction so the grid is ~2 waves
@@ -476,6 +529,14 @@ int drb_cdae_step_phases(drb_cdae* m, const int32_t* uids, const int32_t* keep_o
     const int mt2 = (I + 127) / 128;
     const int s2 = batch >= 1024 ? std::max(1, std::min({16, (2 * ctx->sm_count + mt2 - 1) / mt2, batch / 512})) : 1;
     const bool colsum = cdae_colsum_in_loss(m->d.hidden);
+    if (m->half) {      // A = the [item tile][user block] copy of dz (K-major over users), B = h^T
+      UmmaOperands oh{dzh.i_hi, dzh.i_lo, 64, w.hT_hi, w.hT_lo, m->bp8, n2};
+      oh.a_tiled_nib = dzh.nub; oh.a_tiled_rows = (int64_t)dzh.item_tiles * dzh.nub * 128;
+      oh.half = true; oh.out_scale = dz_unscale / DRB_H_F16_SCALE; oh.name = "k_umma_gemm_dw";
+      if ((r = launch_umma_store(ctx, oh, false, I, n2, batch, s2, G + L.off_w2t, ld, ld, m->d.hidden,
+                                 colsum ? nullptr : G + L.off_b2, colsum ? -1 : m->d.hidden, s2 > 1)))
+        return r;
+    } else
     if ((r = launch_umma_store(ctx, o2, true, I, n2, batch, s2, G + L.off_w2t, ld, ld, m->d.hidden,
                                colsum ? nullptr : G + L.off_b2, colsum ? -1 : m->d.hidden, s2 > 1)))
       return r;
@@ -504,7 +565,13 @@ int drb_cdae_step_phases(drb_cdae* m, const int32_t* uids, const int32_t* keep_o
 
   if (phases & DRB_PHASE_GRADS_C) {
   // 5. K3: dh = dz W'^T  (B x K), split over the item range, partials reduced by the dz1 kernel
-  if (m->use_umma) {
+  if (m->use_umma && m->half) {      // A = the [user tile][item block] copy of dz (K-major over items), B = W'^T
+    UmmaOperands o3{dzh.u_hi, dzh.u_lo, 64, w.wT_hi, w.wT_lo, m->ip8, n2};
+    o3.a_tiled_nib = dzh.nib64; o3.a_tiled_rows = (int64_t)((m->d.max_batch + 127) / 128) * dzh.nib64 * 128;
+    o3.half = true; o3.out_scale = dz_unscale; o3.out_scale_dev = inv_alpha_w; o3.name = "k_umma_gemm_dh";
+    if ((r = launch_umma_store(ctx, o3, false, batch, n2, I, m->splits, w.dh_part, ld, ld, m->d.hidden, nullptr, -1)))
+      return r;
+  } else if (m->use_umma) {
     UmmaOperands o3{w.dzt_hi, w.dzt_lo, 32, w.wT_hi, w.wT_lo, L.items_pad, n2};
     o3.a_tiled_nib = o2.a_tiled_nib;
     o3.a_tiled_rows = o2.a_tiled_rows;
@@ -708,7 +775,10 @@ static int cdae_topk_umma_chunk(drb_cdae* m, const TopkScratch& S, int n_s, cons
   const int I = m->d.n_items, ld = m->L.ld, words = m->words_per_row;
   int r;
   if ((r = cdae_hidden_into(m, uids, c, nullptr, nullptr, 1.0f, w.h))) return r;
-  if ((r = launch_split_tf32(ctx, w.h, c, ld, ld, w.h_hi, w.h_lo, nullptr, nullptr, 0, -1))) return r;
+  if (m->half) {
+    if ((r = launch_split_f16(ctx, w.h, c, ld, ld, DRB_H_F16_SCALE, nullptr, w.h_hi, w.h_lo, m->ldh, nullptr, nullptr, 0, -1)))
+      return r;
+  } else if ((r = launch_split_tf32(ctx, w.h, c, ld, ld, w.h_hi, w.h_lo, nullptr, nullptr, 0, -1))) return r;
   DRB_CUDA_TRY(ctx, cudaMemsetAsync(S.cnt, 0, (size_t)c * 4, ctx->stream));
   DRB_CUDA_TRY(ctx, cudaMemsetAsync(S.tau, 0, (size_t)c * 4, ctx->stream));
   DRB_CUDA_TRY(ctx, cudaMemsetAsync(S.fb_count, 0, 4, ctx->stream));
@@ -721,7 +791,8 @@ static int cdae_topk_umma_chunk(drb_cdae* m, const TopkScratch& S, int n_s, cons
     if ((r = launch_batch_prep(ctx, bp, c))) return r;
     bits = S.bits;
   }
-  UmmaOperands o{w.h_hi, w.h_lo, ld, w.w2t_hi, w.w2t_lo, ld, I};
+  UmmaOperands o{w.h_hi, w.h_lo, m->half ? m->ldh : ld, w.w2t_hi, w.w2t_lo, m->half ? m->ldh : ld, I};
+  if (m->half) { o.half = true; o.out_scale = 1.0f / DRB_H_F16_SCALE; o.out_scale_dev = w.loss_scalar + 33; }
   const float* b2 = m->d.params + m->L.off_b2;
   // pass 1: the first n_s items, everything unseen is listed; tau = k-th best of the slice
   if ((r = launch_umma_score_filter(ctx, o, c, I, 0, n_s, ld, b2, bits, words, S.tau, S.cnt, S.lists, S.cap))) return r;
@@ -756,9 +827,17 @@ static int cdae_topk_impl(drb_cdae* m, const int32_t* uids, int32_t n, int32_t k
               n_s + k <= cap && n_s < I;
   if (fast && !ns_env && !cap_env) fast = I >= 8192 && n_s <= I / 3;
   if (fast) { S = topk_scratch(m, cap); fast = S.ok; }
-  if (fast) {   // tf32 hi/lo split of W' once per call (the weights do not change while scoring)
-    int r = launch_split_tf32(m->ctx, m->d.params + m->L.off_w2t, I, m->L.ld, m->L.ld, m->ws.w2t_hi, m->ws.w2t_lo, nullptr,
-                              nullptr, 0, -1);
+  if (fast) {   // hi/lo split of W' once per call (the weights do not change while scoring)
+    int r;
+    if (m->half) {
+      float* scales = m->ws.loss_scalar + 32;
+      if ((r = launch_absmax_scale(m->ctx, m->d.params + m->L.off_w2t, I, m->d.hidden, m->L.ld, scales))) return r;
+      r = launch_split_f16(m->ctx, m->d.params + m->L.off_w2t, I, m->L.ld, m->L.ld, 1.0f, scales, m->ws.w2t_hi,
+                           m->ws.w2t_lo, m->ldh, nullptr, nullptr, 0, -1);
+    } else {
+      r = launch_split_tf32(m->ctx, m->d.params + m->L.off_w2t, I, m->L.ld, m->L.ld, m->ws.w2t_hi, m->ws.w2t_lo, nullptr,
+                            nullptr, 0, -1);
+    }
     if (r) return r;
   }
   for (int32_t o = 0; o < n; o += m->d.max_batch) {

@@ -96,26 +96,49 @@ int launch_gemm(drb_ctx* ctx, int layout, int epi, const GemmArgs& a, int* n_mti
 
 // ------------------------------------------------------------------ umma.cu (tcgen05 / TMA / TMEM path)
 struct UmmaOperands {
-  const float* a_hi; const float* a_lo; int lda;   // K-major: A[m][k]; MN-major: G[k][m]
-  const float* b_hi; const float* b_lo; int ldb;   // B[n][k], k contiguous
+  const void* a_hi; const void* a_lo; int lda;      // K-major: A[m][k]; MN-major (tf32 only): G[k][m]; pitch in elements
+  const void* b_hi; const void* b_lo; int ldb;      // B[n][k], k contiguous
   int b_rows;                                       // rows of B that exist in memory (>= logical N is fine)
-  int a_tiled_nib = 0;                              // > 0: A is dz in the 128x32 tile-major layout (see umma_loss.cu)
-  int64_t a_tiled_rows = 0;                         //      total rows of the [rows, 32] view
+  int a_tiled_nib = 0;                              // > 0: A is dz in a tile-major layout: 128-row tiles of 32 floats
+                                                    // (tf32, umma_loss.cu) or 64 halfs (fp16), nib column blocks per row tile
+  int64_t a_tiled_rows = 0;                         //      total rows of the [rows, 32 | 64] view
+  bool half = false;                                // operands are fp16 hi / lo pairs (kind::f16) instead of tf32 hi / lo
+  float out_scale = 1.f;                            // accumulators are multiplied by out_scale * (*out_scale_dev)
+  const float* out_scale_dev = nullptr;             //   (undoes the per-tensor power-of-two scaling of fp16 operands)
+  const char* name = nullptr;                       // profiling name of the launch (drb_ctx_profile_read)
 };
 bool umma_available();
 // src [rows][ld] -> tf32 hi / lo split, optionally also transposed ([cols..][ldt]); ones_row >= 0 sets that
 // transposed row to 1 (constant feature used to fold the output-bias gradient into the dW' GEMM)
 int launch_split_tf32(drb_ctx* ctx, const float* src, int rows, int cols, int ld, float* hi, float* lo, float* t_hi,
                       float* t_lo, int ldt, int ones_row);
+// fp16 form: x * alpha * (*alpha_dev) -> hi = rn_f16(.), lo = rn_f16(. - hi); hi / lo [rows][ldh halfs] (may be NULL),
+// transposed t_hi / t_lo [cols..][ldt halfs] (may be NULL).  alpha_dev may be NULL.  ones_row: that transposed row = alpha.
+int launch_split_f16(drb_ctx* ctx, const float* src, int rows, int cols, int ld, float alpha, const float* alpha_dev,
+                     void* hi, void* lo, int ldh, void* t_hi, void* t_lo, int ldt, int ones_row);
+// scales[0] = alpha = 2^(14 - floor(log2(max |x|))) (so that max |x| * alpha is in [2^14, 2^15)), scales[1] = 1 / alpha;
+// x [rows][ld], the first `cols` columns.  Two tiny launches (reduce, then publish).
+int launch_absmax_scale(drb_ctx* ctx, const float* x, int64_t rows, int cols, int ld, float* scales);
 // dz_hi / dz_lo are written in the tile-major layout: tile (row tile rt, column block cb) of 128 x 32 floats at
 // float offset ((rt * nib + cb) * 128) * 32, nib = drb_dz_nib(N)
 inline int drb_dz_nib(int n_cols) { return 4 * ((n_cols + 127) / 128); }
+// fp16 dz: two tile-major copies, tiles of 128 rows x 64 halfs (16 KB): U = [user tile][item block] feeds dh = dz W'^T,
+// I = [item tile][user block] feeds dW'^T = dz^T h; hi and lo of one copy share one buffer of drb_dz_tiled_floats floats
+inline int drb_dz_nib64(int n_cols) { return 2 * ((n_cols + 127) / 128); }
+struct DzHalf {
+  void* u_hi; void* u_lo; int nib64;      // [ceil(B/128)][nib64] tiles
+  void* i_hi; void* i_lo; int nub;        // [ceil(I/128)][nub] tiles, nub = 2 * ceil(B/128)
+  int row_tiles, item_tiles;
+};
 inline int64_t drb_dz_tiled_floats(int rows, int n_cols) { return (int64_t)((rows + 127) / 128) * drb_dz_nib(n_cols) * 4096; }
 int launch_umma_cdae_loss(drb_ctx* ctx, const UmmaOperands& o, int M, int N, int Kred, float* dz_hi, float* dz_lo,
                           int ldc, const float* bias, const float* label_count, const uint32_t* label_bits,
                           int words_per_row, int loss_kind, float inv_count, int batch, float* loss_part,
                           float* dz_colsum /* may be NULL: [N] += colsum(dz), i.e. db' */, int* n_blocks_out,
-                          float* z_dbg = nullptr /* tests: logits as formed by the kernel, [M][ldz] */, int ldz = 0);
+                          float* z_dbg = nullptr /* tests: logits as formed by the kernel, [M][ldz] */, int ldz = 0,
+                          const DzHalf* dzh = nullptr /* o.half: dz goes here (fp16 hi/lo, scaled by 2^14 / inv_count) */);
+constexpr float DRB_DZ_F16_SCALE = 16384.0f;   // |dL/dz2| / inv_count <= 1 -> scaled into [-2^14, 2^14]
+constexpr float DRB_H_F16_SCALE = 32768.0f;    // h in (0, 1)
 int launch_umma_store(drb_ctx* ctx, const UmmaOperands& o, bool a_mn_major, int M, int N, int Kred, int splits,
                       float* C, int ldc, int n_store, int n_valid, float* extra_col, int extra_col_index,
                       bool atomic_out = false);

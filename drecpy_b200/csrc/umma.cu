@@ -44,15 +44,20 @@ struct UmmaParams {
   int n_store; int n_valid;  // columns in [n_valid, n_store) are written as 0 (row padding of C)
   float* extra_col; int extra_col_index;   // EPI_STORE: column `extra_col_index` of the product goes to extra_col[m]
   int atomic_out;           // splits > 1: accumulate all partials into C / extra_col with vector atomics (C pre-zeroed)
-  int a_tiled_nib;          // > 0: A lives in the 128x32 tile-major dz layout with this many 32-column blocks per row tile
+  int a_tiled_nib;          // > 0: A lives in a tile-major dz layout (128-row tiles of 32 floats / 64 halfs) with this many
+                            // column blocks per row tile
+  float out_scale; const float* out_scale_dev;   // accumulators are multiplied by out_scale * (*out_scale_dev)
 };
 
-template <int BN, bool A_MN, int KB, int CL>
+template <int BN, bool A_MN, int KB, int CL, bool H>
 __global__ void __launch_bounds__(THREADS, 1)
 k_umma_gemm(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
             const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo, UmmaParams p) {
   using S = Smem<BN, KB, CL>;
-  constexpr int BK = KB;
+  static_assert(!(H && A_MN), "fp16 operands are K-major only (the loss kernel writes dz in both orientations)");
+  constexpr int BK = H ? 2 * KB : KB;            // elements of the reduction dimension per stage (KB: 4-byte units)
+  constexpr int UK = H ? 16 : UMMA_K;            // elements one MMA consumes (32 bytes either way)
+  constexpr int TW = H ? 64 : 32;                // width of a dz tile in elements (128 bytes)
   const uint32_t cta_rank = (CL > 1) ? cluster_ctarank() : 0u;
   const bool leader = cta_rank == 0;
   extern __shared__ uint8_t smem_raw[];
@@ -122,10 +127,10 @@ k_umma_gemm(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
               load(sa_hi + j * (BK * 128), &map_a_hi, full_bar(s), 0, row);
               load(sa_lo + j * (BK * 128), &map_a_lo, full_bar(s), 0, row);
             }
-          } else {      // M runs over dz rows, K over dz columns: a whole 16 KB tile (BK = 32) or its left / right half
-            const int row = ((m0 >> 7) * p.a_tiled_nib + (k0 >> 5)) * 128;
-            load(sa_hi, &map_a_hi, full_bar(s), k0 & 31, row);
-            load(sa_lo, &map_a_lo, full_bar(s), k0 & 31, row);
+          } else {      // M runs over dz rows, K over dz columns: a whole 16 KB tile (128-byte stages) or its left / right half
+            const int row = ((m0 >> 7) * p.a_tiled_nib + (k0 / TW)) * 128;
+            load(sa_hi, &map_a_hi, full_bar(s), k0 % TW, row);
+            load(sa_lo, &map_a_lo, full_bar(s), k0 % TW, row);
           }
         } else if (A_MN) {
           // A[m][k] stored as G[k][m] (m contiguous): four boxes of {32 m, BK k}, one per 32-wide MN atom column
@@ -147,8 +152,7 @@ k_umma_gemm(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
     if (lane == 0 && leader) {
       // instruction descriptor (cute::UMMA::InstrDescriptor): D=F32 [4,6)=1, A=TF32 [7,10)=2, B=TF32 [10,13)=2,
       // a_major [15], b_major [16], N>>3 [17,23), M>>4 [24,29)
-      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((A_MN ? 1u : 0u) << 15) | (0u << 16) |
-                             ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((BM * CL) >> 4) << 24);
+      const uint32_t idesc = make_idesc<H>(BM * CL, BN, A_MN);
       for (int i = 0; i < nkb; i++) {
         const int s = i % S::STAGES;
         const uint32_t ph = (i / S::STAGES) & 1;
@@ -157,29 +161,24 @@ k_umma_gemm(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
         const uint32_t sa_hi = base + s * S::STAGE_BYTES, sa_lo = sa_hi + S::A_BYTES;
         const uint32_t sb_hi = sa_lo + S::A_BYTES, sb_lo = sb_hi + S::B_BYTES;
         // last k-block of the reduction: MMAs over the zero-filled tail of the box are not issued
-        const int kk_n = min(BK / UMMA_K, (p.Kred - (kb_beg + i) * BK + UMMA_K - 1) / UMMA_K);
-#pragma unroll 1
-        for (int kk = 0; kk < kk_n; kk++) {
+        const int kk_n = min(BK / UK, (p.Kred - (kb_beg + i) * BK + UK - 1) / UK);
+#pragma unroll
+        for (int kk = 0; kk < BK / UK; kk++) {
+          if (kk >= kk_n) break;
           uint64_t a_hi, a_lo;
           if (A_MN) {   // MN-major: rows = k (128 B = 32 m each); K atoms of 4 rows are 512 B apart, one MMA (K=8)
                         // spans two of them; MN atoms (32 floats, one TMA box of BK rows) are BK * 128 B apart
-            a_hi = make_desc(sa_hi + kk * 1024, BK * 128, 512, 1);
-            a_lo = make_desc(sa_lo + kk * 1024, BK * 128, 512, 1);
+            a_hi = make_desc(sa_hi + kk * 1024, KB * 128, 512, 1);
+            a_lo = make_desc(sa_lo + kk * 1024, KB * 128, 512, 1);
           } else {
-            a_hi = make_desc_kmajor<BK>(sa_hi, kk);
-            a_lo = make_desc_kmajor<BK>(sa_lo, kk);
+            a_hi = make_desc_kmajor<KB>(sa_hi, kk);
+            a_lo = make_desc_kmajor<KB>(sa_lo, kk);
           }
-          const uint64_t b_hi = make_desc_kmajor<BK>(sb_hi, kk);
-          const uint64_t b_lo = make_desc_kmajor<BK>(sb_lo, kk);
-          if (CL > 1) {
-            umma_tf32_pair(tmem_base, a_lo, b_hi, idesc, (i | kk) != 0);
-            umma_tf32_pair(tmem_base, a_hi, b_lo, idesc, 1u);
-            umma_tf32_pair(tmem_base, a_hi, b_hi, idesc, 1u);
-          } else {
-            umma_tf32(tmem_base, a_lo, b_hi, idesc, (i | kk) != 0);   // small terms first
-            umma_tf32(tmem_base, a_hi, b_lo, idesc, 1u);
-            umma_tf32(tmem_base, a_hi, b_hi, idesc, 1u);
-          }
+          const uint64_t b_hi = make_desc_kmajor<KB>(sb_hi, kk);
+          const uint64_t b_lo = make_desc_kmajor<KB>(sb_lo, kk);
+          umma_split<H, CL>(tmem_base, a_lo, b_hi, idesc, (i | kk) != 0);   // small terms first
+          umma_split<H, CL>(tmem_base, a_hi, b_lo, idesc, 1u);
+          umma_split<H, CL>(tmem_base, a_hi, b_hi, idesc, 1u);
         }
         if (CL > 1) umma_commit_pair(empty_bar(s));   // frees the smem stage (both CTAs) once these MMAs have read it
         else umma_commit(empty_bar(s));
@@ -194,6 +193,7 @@ k_umma_gemm(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
     mbar_wait(tmem_full_bar, 0);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     float* crow = p.C + (p.atomic_out ? 0 : (int64_t)blockIdx.z * p.M * p.ldc) + (int64_t)m * p.ldc;
+    const float osc = p.out_scale * (p.out_scale_dev ? __ldg(p.out_scale_dev) : 1.0f);
 #pragma unroll 1
     for (int c = 0; c < BN; c += 16) {
       uint32_t r[16];
@@ -202,6 +202,10 @@ k_umma_gemm(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
       } else {
 #pragma unroll
         for (int j = 0; j < 16; j++) r[j] = 0u;
+      }
+      if (H) {
+#pragma unroll
+        for (int j = 0; j < 16; j++) r[j] = __float_as_uint(__uint_as_float(r[j]) * osc);
       }
       const int n = n0 + c;
       if (m >= p.M) continue;
@@ -272,34 +276,110 @@ __global__ void __launch_bounds__(256) k_split_tf32(const float* __restrict__ sr
   }
 }
 
-template <int BN, bool A_MN, int KB, int CL>
+
+// fp16 hi / lo split of a scaled fp32 matrix (see launch_split_f16 in kernels.h); same 32 x 32 tile transpose
+__global__ void __launch_bounds__(256) k_split_f16(const float* __restrict__ src, int rows, int cols, int ld, float alpha,
+                                                  const float* __restrict__ alpha_dev, __half* __restrict__ hi,
+                                                  __half* __restrict__ lo, int ldh, __half* __restrict__ t_hi,
+                                                  __half* __restrict__ t_lo, int ldt, int ones_row) {
+  __shared__ __half th[32][34], tl[32][34];
+  const float sc = alpha * (alpha_dev ? __ldg(alpha_dev) : 1.0f);
+  const int r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    const int r = r0 + ty + i * 8, c = c0 + tx;
+    __half h = __float2half_rn(0.f), l = h;
+    if (r < rows && c < cols) {
+      split_f16(src[(int64_t)r * ld + c] * sc, h, l);
+      if (hi) { hi[(int64_t)r * ldh + c] = h; lo[(int64_t)r * ldh + c] = l; }
+    }
+    th[ty + i * 8][tx] = h;
+    tl[ty + i * 8][tx] = l;
+  }
+  if (!t_hi) return;
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    const int c = c0 + ty + i * 8, r = r0 + tx;   // transposed: row index c, column index r
+    if (c < cols && r < rows) {
+      t_hi[(int64_t)c * ldt + r] = th[tx][ty + i * 8];
+      t_lo[(int64_t)c * ldt + r] = tl[tx][ty + i * 8];
+    }
+    if (ones_row >= 0 && c == ones_row && r < rows) {   // constant-one feature, in the scaled units of this operand
+      t_hi[(int64_t)c * ldt + r] = __float2half_rn(sc);
+      t_lo[(int64_t)c * ldt + r] = __float2half_rn(0.f);
+    }
+  }
+}
+
+// max |x| over the first `cols` columns of x[rows][ld], as the bit pattern of a non-negative float (atomicMax on uint)
+__global__ void __launch_bounds__(256) k_absmax(const float* __restrict__ x, int64_t rows, int cols, int ld,
+                                                uint32_t* __restrict__ out_bits) {
+  float m = 0.f;
+  const int64_t total = rows * (int64_t)ld;
+  (void)cols;   // pad columns of the arenas are exactly zero, so the whole pitch can be scanned
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x)
+    m = fmaxf(m, fabsf(x[i]));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(out_bits, __float_as_uint(m));
+}
+// scales[0] = alpha = 2^(14 - floor(log2 max)), scales[1] = 1 / alpha; max == 0 (or not finite) -> 1
+__global__ void k_publish_scale(const uint32_t* __restrict__ max_bits, float* __restrict__ scales) {
+  const float m = __uint_as_float(*max_bits);
+  float alpha = 1.0f;
+  if (m > 0.f && isfinite(m)) {
+    const int e = (int)((*max_bits >> 23) & 0xffu) - 127;     // floor(log2 m) for normal m
+    const int ea = max(-100, min(100, 14 - e));
+    alpha = exp2f((float)ea);
+  }
+  scales[0] = alpha;
+  scales[1] = 1.0f / alpha;
+}
+
+template <int BN, bool A_MN, int KB, int CL, bool H>
 int run_umma(drb_ctx* ctx, const UmmaOperands& o, const UmmaParams& p, int* n_blocks_out) {
   constexpr int BK = KB;
   constexpr int SMEM = Smem<BN, KB, CL>::TOTAL;
   CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
   int r;
+  if (H) {      // fp16 hi / lo operands, K-major; tile-major dz = a [tiles * 128, 64 halfs] tensor
+    if (o.a_tiled_nib > 0) {
+      if ((r = make_map_h(&ma_hi, o.a_hi, 64, o.a_tiled_rows, 64, 2 * KB, BM))) return r;
+      if ((r = make_map_h(&ma_lo, o.a_lo, 64, o.a_tiled_rows, 64, 2 * KB, BM))) return r;
+    } else {
+      if ((r = make_map_h(&ma_hi, o.a_hi, p.Kred, p.M, o.lda, 2 * KB, BM))) return r;
+      if ((r = make_map_h(&ma_lo, o.a_lo, p.Kred, p.M, o.lda, 2 * KB, BM))) return r;
+    }
+    if ((r = make_map_h(&mb_hi, o.b_hi, p.Kred, o.b_rows, o.ldb, 2 * KB, BN / CL))) return r;
+    if ((r = make_map_h(&mb_lo, o.b_lo, p.Kred, o.b_rows, o.ldb, 2 * KB, BN / CL))) return r;
+  } else {
+  const float* fa_hi = static_cast<const float*>(o.a_hi); const float* fa_lo = static_cast<const float*>(o.a_lo);
+  const float* fb_hi = static_cast<const float*>(o.b_hi); const float* fb_lo = static_cast<const float*>(o.b_lo);
   if (o.a_tiled_nib > 0) {   // tile-major dz: a [tiles * 128, 32] tensor
-    if ((r = make_map(&ma_hi, o.a_hi, 32, o.a_tiled_rows, 32, A_MN ? 32 : BK, A_MN ? BK : BM, A_MN))) return r;
-    if ((r = make_map(&ma_lo, o.a_lo, 32, o.a_tiled_rows, 32, A_MN ? 32 : BK, A_MN ? BK : BM, A_MN))) return r;
+    if ((r = make_map(&ma_hi, fa_hi, 32, o.a_tiled_rows, 32, A_MN ? 32 : BK, A_MN ? BK : BM, A_MN))) return r;
+    if ((r = make_map(&ma_lo, fa_lo, 32, o.a_tiled_rows, 32, A_MN ? 32 : BK, A_MN ? BK : BM, A_MN))) return r;
   } else if (A_MN) {   // A given as G[k][m]
-    if ((r = make_map(&ma_hi, o.a_hi, p.M, p.Kred, o.lda, 32, BK, true))) return r;
-    if ((r = make_map(&ma_lo, o.a_lo, p.M, p.Kred, o.lda, 32, BK, true))) return r;
+    if ((r = make_map(&ma_hi, fa_hi, p.M, p.Kred, o.lda, 32, BK, true))) return r;
+    if ((r = make_map(&ma_lo, fa_lo, p.M, p.Kred, o.lda, 32, BK, true))) return r;
   } else {      // A given as G[m][k]
-    if ((r = make_map(&ma_hi, o.a_hi, p.Kred, p.M, o.lda, BK, BM))) return r;
-    if ((r = make_map(&ma_lo, o.a_lo, p.Kred, p.M, o.lda, BK, BM))) return r;
+    if ((r = make_map(&ma_hi, fa_hi, p.Kred, p.M, o.lda, BK, BM))) return r;
+    if ((r = make_map(&ma_lo, fa_lo, p.Kred, p.M, o.lda, BK, BM))) return r;
   }
-  if ((r = make_map(&mb_hi, o.b_hi, p.Kred, o.b_rows, o.ldb, BK, BN / CL))) return r;
-  if ((r = make_map(&mb_lo, o.b_lo, p.Kred, o.b_rows, o.ldb, BK, BN / CL))) return r;
+  if ((r = make_map(&mb_hi, fb_hi, p.Kred, o.b_rows, o.ldb, BK, BN / CL))) return r;
+  if ((r = make_map(&mb_lo, fb_lo, p.Kred, o.b_rows, o.ldb, BK, BN / CL))) return r;
+  }
   dim3 grid(((p.M + BM - 1) / BM + CL - 1) / CL * CL, (p.N + BN - 1) / BN, p.splits);   // whole pairs of row tiles
   if (n_blocks_out) *n_blocks_out = grid.x * grid.y;
-  auto kern = k_umma_gemm<BN, A_MN, KB, CL>;
+  auto kern = k_umma_gemm<BN, A_MN, KB, CL, H>;
   static bool attr_set = false;   // per template instantiation
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
     if (e != cudaSuccess) return drb_fail(DRB_E_CUDA, "cudaFuncSetAttribute(smem=%d) failed: %s", SMEM, cudaGetErrorString(e));
     attr_set = true;
   }
-  drb_prof_scope prof_(ctx, A_MN ? "k_umma_gemm_mn" : "k_umma_gemm_kk");
+  drb_prof_scope prof_(ctx, o.name ? o.name : (A_MN ? "k_umma_gemm_mn" : "k_umma_gemm_kk"));
   if (CL > 1) {
     cudaLaunchConfig_t cfg{};
     cudaLaunchAttribute at[1];
@@ -329,6 +409,36 @@ int launch_split_tf32(drb_ctx* ctx, const float* src, int rows, int cols, int ld
   return DRB_OK;
 }
 
+int launch_split_f16(drb_ctx* ctx, const float* src, int rows, int cols, int ld, float alpha, const float* alpha_dev,
+                     void* hi, void* lo, int ldh, void* t_hi, void* t_lo, int ldt, int ones_row) {
+  if (rows <= 0 || cols <= 0) return DRB_OK;
+  int ccols = cols;
+  if (ones_row >= cols) ccols = ones_row + 1;   // make sure a block visits the ones row
+  dim3 grid((ccols + 31) / 32, (rows + 31) / 32);
+  drb_prof_scope prof_(ctx, "k_split_f16");
+  k_split_f16<<<grid, 256, 0, ctx->stream>>>(src, rows, cols, ld, alpha, alpha_dev, static_cast<__half*>(hi),
+                                             static_cast<__half*>(lo), ldh, static_cast<__half*>(t_hi),
+                                             static_cast<__half*>(t_lo), ldt, ones_row);
+  DRB_LAUNCH_CHECK(ctx, "k_split_f16");
+  return DRB_OK;
+}
+
+int launch_absmax_scale(drb_ctx* ctx, const float* x, int64_t rows, int cols, int ld, float* scales) {
+  uint32_t* bits = reinterpret_cast<uint32_t*>(scales + 2);
+  cudaError_t e = cudaMemsetAsync(bits, 0, 4, ctx->stream);
+  if (e != cudaSuccess) return drb_fail(DRB_E_CUDA, "absmax: memset failed: %s", cudaGetErrorString(e));
+  const int64_t total = rows * (int64_t)ld;
+  const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>((total + 255) / 256, (int64_t)ctx->sm_count * 8));
+  {
+    drb_prof_scope prof_(ctx, "k_absmax");
+    k_absmax<<<blocks, 256, 0, ctx->stream>>>(x, rows, cols, ld, bits);
+    DRB_LAUNCH_CHECK(ctx, "k_absmax");
+  }
+  k_publish_scale<<<1, 1, 0, ctx->stream>>>(bits, scales);
+  DRB_LAUNCH_CHECK(ctx, "k_publish_scale");
+  return DRB_OK;
+}
+
 int launch_umma_store(drb_ctx* ctx, const UmmaOperands& o, bool a_mn_major, int M, int N, int Kred, int splits,
                       float* C, int ldc, int n_store, int n_valid, float* extra_col, int extra_col_index,
                       bool atomic_out) {
@@ -337,26 +447,31 @@ int launch_umma_store(drb_ctx* ctx, const UmmaOperands& o, bool a_mn_major, int 
   p.extra_col = extra_col; p.extra_col_index = extra_col_index;
   p.a_tiled_nib = o.a_tiled_nib;
   p.atomic_out = atomic_out ? 1 : 0;
+  p.out_scale = o.out_scale; p.out_scale_dev = o.out_scale_dev;
   if (N > 256) return drb_fail(DRB_E_INVALID, "umma store GEMM: N must be <= 256 (hidden width)");
   static const int bk_env = getenv("DRB_UMMA_BK") ? atoi(getenv("DRB_UMMA_BK")) : 0;   // profiling override: 16 | 32
   static const int cl_env = getenv("DRB_UMMA_CLUSTER") ? atoi(getenv("DRB_UMMA_CLUSTER")) : 0;   // override: 1 | 2
-#define DRB_UMMA_CASE(BN, KB_DEFAULT, CL_DEFAULT)                                \
-  if (N <= BN) {                                                                 \
-    if ((bk_env ? bk_env : KB_DEFAULT) == 16) {                                  \
-      if ((cl_env ? cl_env : CL_DEFAULT) == 2) {                                 \
-        if (a_mn_major) return run_umma<BN, true, 16, 2>(ctx, o, p, nullptr);    \
-        return run_umma<BN, false, 16, 2>(ctx, o, p, nullptr);                   \
-      }                                                                          \
-      if (a_mn_major) return run_umma<BN, true, 16, 1>(ctx, o, p, nullptr);      \
-      return run_umma<BN, false, 16, 1>(ctx, o, p, nullptr);                     \
-    }                                                                            \
-    if (a_mn_major) return run_umma<BN, true, 32, 1>(ctx, o, p, nullptr);        \
-    return run_umma<BN, false, 32, 1>(ctx, o, p, nullptr);                       \
+#define DRB_UMMA_CASE(BN, KB_DEFAULT, CL_DEFAULT)                                       \
+  if (N <= BN) {                                                                        \
+    if (o.half) {   /* fp16 operands: K-major only */                                   \
+      if (a_mn_major) return drb_fail(DRB_E_INVALID, "umma store GEMM: fp16 operands are K-major only"); \
+      if ((bk_env ? bk_env : KB_DEFAULT) == 16) {                                       \
+        if ((cl_env ? cl_env : CL_DEFAULT) == 2) return run_umma<BN, false, 16, 2, true>(ctx, o, p, nullptr); \
+        return run_umma<BN, false, 16, 1, true>(ctx, o, p, nullptr);                    \
+      }                                                                                 \
+      return run_umma<BN, false, 32, 1, true>(ctx, o, p, nullptr);                      \
+    }                                                                                   \
+    if ((bk_env ? bk_env : KB_DEFAULT) == 16) {                                         \
+      if ((cl_env ? cl_env : CL_DEFAULT) == 2) {                                        \
+        if (a_mn_major) return run_umma<BN, true, 16, 2, false>(ctx, o, p, nullptr);    \
+        return run_umma<BN, false, 16, 2, false>(ctx, o, p, nullptr);                   \
+      }                                                                                 \
+      if (a_mn_major) return run_umma<BN, true, 16, 1, false>(ctx, o, p, nullptr);      \
+      return run_umma<BN, false, 16, 1, false>(ctx, o, p, nullptr);                     \
+    }                                                                                   \
+    if (a_mn_major) return run_umma<BN, true, 32, 1, false>(ctx, o, p, nullptr);        \
+    return run_umma<BN, false, 32, 1, false>(ctx, o, p, nullptr);                       \
   }
-  DRB_UMMA_CASE(64, 32, 1)
-  DRB_UMMA_CASE(128, 32, 1)
-  DRB_UMMA_CASE(208, 16, 2)
-  DRB_UMMA_CASE(256, 16, 2)
 #undef DRB_UMMA_CASE
   return drb_fail(DRB_E_INVALID, "umma store GEMM: unsupported N");
 }

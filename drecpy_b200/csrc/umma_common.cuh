@@ -4,6 +4,7 @@
 #define DRB_UMMA_COMMON_CUH
 
 #include <cuda.h>
+#include <cuda_fp16.h>
 
 #include <algorithm>
 #include <cstdlib>
@@ -94,6 +95,57 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint6
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// fp16 operands (kind::f16): the same shared-memory descriptors (byte based), one MMA covers K = 16 halfs = 32 bytes
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                         uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_f16_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                              uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// one split-precision MMA of either kind (H: fp16 hi/lo operands, else tf32 hi/lo), one CTA or a CTA pair
+template <bool H, int CL>
+__device__ __forceinline__ void umma_split(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                           uint32_t accumulate) {
+  if (H) {
+    if (CL > 1) umma_f16_pair(tmem_d, adesc, bdesc, idesc, accumulate);
+    else umma_f16(tmem_d, adesc, bdesc, idesc, accumulate);
+  } else {
+    if (CL > 1) umma_tf32_pair(tmem_d, adesc, bdesc, idesc, accumulate);
+    else umma_tf32(tmem_d, adesc, bdesc, idesc, accumulate);
+  }
+}
+// instruction descriptor (cute::UMMA::InstrDescriptor): D = F32 [4,6) = 1; A / B format [7,10) / [10,13): TF32 = 2
+// (kind::tf32), F16 = 0 (kind::f16); a_major [15] (1 = MN-major); N >> 3 [17,23); M >> 4 [24,29)
+template <bool H>
+__device__ __forceinline__ uint32_t make_idesc(int m, int n, bool a_mn_major = false) {
+  const uint32_t fmt = H ? 0u : 2u;
+  return (1u << 4) | (fmt << 7) | (fmt << 10) | ((a_mn_major ? 1u : 0u) << 15) | ((uint32_t)(n >> 3) << 17) |
+         ((uint32_t)(m >> 4) << 24);
+}
+
+// fp16 split of a value already scaled into the fp16 range: x = hi + lo up to ~2^-22 |x| (both round-to-nearest; lo is
+// a subnormal half only for elements 2^-11 below the tensor's maximum, where its absolute error is irrelevant)
+__device__ __forceinline__ void split_f16(float x, __half& hi, __half& lo) {
+  hi = __float2half_rn(x);
+  lo = __float2half_rn(x - __half2float(hi));
+}
+
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, "
@@ -191,6 +243,34 @@ int make_map(CUtensorMap* map, const float* ptr, int64_t inner, int64_t outer, i
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return drb_fail(DRB_E_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
   return DRB_OK;
+}
+
+// The same for an fp16 tensor [outer][inner halfs]: 128-byte box rows (64 halfs, SWIZZLE_128B) or 64-byte (32 halfs,
+// SWIZZLE_64B).  pitch_halfs must be a multiple of 8 (16-byte global strides).
+int make_map_h(CUtensorMap* map, const void* ptr, int64_t inner, int64_t outer, int64_t pitch_halfs, int box_inner,
+               int box_outer) {
+  const CUtensorMapSwizzle swz = (box_inner == 32) ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B;
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return drb_fail(DRB_E_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
+  if (pitch_halfs % 8) return drb_fail(DRB_E_INVALID, "fp16 tensor map: row pitch %lld is not a multiple of 8", (long long)pitch_halfs);
+  cuuint64_t dims[2] = {(cuuint64_t)inner, (cuuint64_t)outer};
+  cuuint64_t strides[1] = {(cuuint64_t)pitch_halfs * 2};
+  cuuint32_t box[2] = {(cuuint32_t)box_inner, (cuuint32_t)box_outer};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return drb_fail(DRB_E_CUDA, "cuTensorMapEncodeTiled (fp16) failed with CUresult %d", (int)r);
+  return DRB_OK;
+}
+
+// operand map of either kind: KB is the stage depth in 4-byte units (32 -> 128-byte rows, 16 -> 64-byte rows), i.e.
+// KB floats or 2*KB halfs; inner / pitch are in elements of the operand type
+template <bool H>
+int make_operand_map(CUtensorMap* map, const void* ptr, int64_t inner, int64_t outer, int64_t pitch, int KB,
+                     int box_outer) {
+  if (H) return make_map_h(map, ptr, inner, outer, pitch, 2 * KB, box_outer);
+  return make_map(map, static_cast<const float*>(ptr), inner, outer, pitch, KB, box_outer);
 }
 
 }  // namespace

@@ -45,6 +45,8 @@ struct LossParams {
   float* loss_part;                        // [gridDim.x]
   float* colsum;                           // NULL, or [N]: db' += column sums of dz (hidden = 241..256: no room for the ones feature)
   int m_tiles, n_tiles, row_tiles;         // item tiles (128), batch tiles (BN), 128-row tiles of the dz layout
+  DzHalf dzh;                              // H: fp16 dz copies (kernels.h), values scaled by DRB_DZ_F16_SCALE / inv_count
+  float out_scale; const float* out_scale_dev;   // H: accumulator -> logit (undoes the operand scaling)
   float* z_dbg; int ldz;                   // tests only (drb_debug_cdae_capture_logits): z2 = h W'^T + b' as this kernel
                                            // formed it, row-major [M][ldz]; NULL in production
   int debug;   // DRB_LOSS_DEBUG bit mask (profiling experiments only, results are wrong): 1 = first 16-row chunk of
@@ -67,13 +69,14 @@ __device__ __forceinline__ void mbar_arrive_rank(uint32_t bar, uint32_t rank) { 
 // CTA issues cta_group::2 MMAs (M = 256) that read each CTA's own W' tile and each CTA's half of the shared h tile and
 // write each CTA's own accumulator, so the h tile is staged once per pair and the MMAs read a third less shared memory.
 // (TMA multicast of the h tile with one-CTA MMAs was measured first: no gain, 0.299 vs 0.302 ms.)
-template <int BN, int LOSS, bool PER_USER, int KB, int CL>
+template <int BN, int LOSS, bool PER_USER, int KB, int CL, bool H>
 __global__ void __launch_bounds__(LOSS_THREADS, 1)
 k_umma_cdae_loss(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                  const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
                  LossParams p) {
   using S = LossSmem<BN, KB, CL>;
-  constexpr int BK = KB;
+  constexpr int BK = H ? 2 * KB : KB;            // elements of the hidden dimension per stage (KB is in 4-byte units)
+  constexpr int UK = H ? 16 : UMMA_K;            // elements one MMA consumes (32 bytes either way)
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
@@ -156,8 +159,7 @@ k_umma_cdae_loss(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
     if (lane == 0 && leader) {
-      const uint32_t idesc =
-          (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((BM * CL) >> 4) << 24);
+      const uint32_t idesc = make_idesc<H>(BM * CL, BN);
       int it = 0, tl = 0;
       for (int t = unit0; t < n_units; t += unit_stride, tl++) {
         const int as = tl & 1;
@@ -172,20 +174,15 @@ k_umma_cdae_loss(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
           const uint32_t sb_hi = sa_lo + S::A_BYTES, sb_lo = sb_hi + S::B_BYTES;
           // the last k-block holds fewer than BK real columns (K = 200: 6 full blocks + 8 columns): TMA zero-fills the
           // rest of the box, the MMAs over those zeros are simply not issued
-          const int kk_n = (p.debug & 16) ? 0 : min(BK / UMMA_K, (p.Kred - kb * BK + UMMA_K - 1) / UMMA_K);
-#pragma unroll 1
-          for (int kk = 0; kk < kk_n; kk++) {
-            const uint64_t a_hi = make_desc_kmajor<BK>(sa_hi, kk), a_lo = make_desc_kmajor<BK>(sa_lo, kk);
-            const uint64_t b_hi = make_desc_kmajor<BK>(sb_hi, kk), b_lo = make_desc_kmajor<BK>(sb_lo, kk);
-            if (CL > 1) {
-              umma_tf32_pair(tacc, a_lo, b_hi, idesc, (kb | kk) != 0);
-              umma_tf32_pair(tacc, a_hi, b_lo, idesc, 1u);
-              umma_tf32_pair(tacc, a_hi, b_hi, idesc, 1u);
-            } else {
-              umma_tf32(tacc, a_lo, b_hi, idesc, (kb | kk) != 0);
-              umma_tf32(tacc, a_hi, b_lo, idesc, 1u);
-              umma_tf32(tacc, a_hi, b_hi, idesc, 1u);
-            }
+          const int kk_n = (p.debug & 16) ? 0 : min(BK / UK, (p.Kred - kb * BK + UK - 1) / UK);
+#pragma unroll
+          for (int kk = 0; kk < BK / UK; kk++) {
+            if (kk >= kk_n) break;
+            const uint64_t a_hi = make_desc_kmajor<KB>(sa_hi, kk), a_lo = make_desc_kmajor<KB>(sa_lo, kk);
+            const uint64_t b_hi = make_desc_kmajor<KB>(sb_hi, kk), b_lo = make_desc_kmajor<KB>(sb_lo, kk);
+            umma_split<H, CL>(tacc, a_lo, b_hi, idesc, (kb | kk) != 0);
+            umma_split<H, CL>(tacc, a_hi, b_lo, idesc, 1u);
+            umma_split<H, CL>(tacc, a_hi, b_hi, idesc, 1u);
           }
           if (CL > 1) umma_commit_pair(empty_bar(s));   // frees the stage in both CTAs' producers
           else umma_commit(empty_bar(s));
@@ -205,6 +202,10 @@ k_umma_cdae_loss(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
     const float one_m = 1.0f - KERAS_EPS;
     constexpr int CW = BN / 4;                    // batch rows of this warp per tile
     const float fbatch = (float)p.batch;
+    // H: the operands were scaled into the fp16 range by powers of two; one multiply brings the accumulator back
+    const float osc = H ? p.out_scale * (p.out_scale_dev ? __ldg(p.out_scale_dev) : 1.0f) : 1.0f;
+    // H: dz leaves as fp16 hi/lo of (dL/dz2 / inv_count) * 2^14, a value in [-2^14, 2^14]; the backward GEMMs undo it
+    const float gsc = H ? DRB_DZ_F16_SCALE : p.inv_count;
     // per-item constants (b', batch-mean label) live in registers and are fetched one tile ahead
     float nbias, ncount;
     auto fetch_consts = [&](int t) {
@@ -247,7 +248,7 @@ k_umma_cdae_loss(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
 #pragma unroll
         for (int j = 0; j < 16; j++) {
           const bool ok = item_ok && (row + j < p.M);
-          const float z = __uint_as_float(r[j]) + bias;
+          const float z = H ? fmaf(__uint_as_float(r[j]), osc, bias) : __uint_as_float(r[j]) + bias;
           if (p.z_dbg && ok) p.z_dbg[(int64_t)(row + j) * p.ldz + item] = z;
           const float pr = fast_rcp(1.0f + fast_ex2(z * -1.4426950408889634f));
           float tgt = tgt_c;
@@ -264,21 +265,61 @@ k_umma_cdae_loss(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
             lt = -0.6931471805599453f * fmaf(tgt, la - lb, lb);
             const bool inside = (pr >= KERAS_EPS) && (pr <= one_m);
             const float num = fmaf(-tgt, da + db, da);
-            gz = inside ? num * (pr * (1.0f - pr)) * (fast_rcp(da * db) * p.inv_count) : 0.f;
+            gz = inside ? num * (pr * (1.0f - pr)) * (fast_rcp(da * db) * gsc) : 0.f;
           } else {
             lt = PER_USER ? (pr - tgt) * (pr - tgt) : fmaf(pr, pr - 2.0f * tgt, tgt);
-            gz = 2.0f * (pr - tgt) * p.inv_count * (pr * (1.0f - pr));
+            gz = 2.0f * (pr - tgt) * gsc * (pr * (1.0f - pr));
           }
           loss_local += ok ? lt : 0.f;
           const float g = ok ? gz : 0.f;
-          float h;
-          split_tf32(g, h, lo[j]);
-          r[j] = __float_as_uint(h);
+          if (H) {
+            __half hh, hl;
+            split_f16(g, hh, hl);
+            r[j] = (uint32_t)__half_as_ushort(hh) | ((uint32_t)__half_as_ushort(hl) << 16);   // hi | lo << 16
+            lo[j] = __half2float(hh) + __half2float(hl);
+          } else {
+            float h;
+            split_tf32(g, h, lo[j]);
+            r[j] = __float_as_uint(h);
+          }
         }
         if (p.colsum) {
 #pragma unroll
-          for (int j = 0; j < 16; j++) csum += __uint_as_float(r[j]) + lo[j];
+          for (int j = 0; j < 16; j++) csum += H ? lo[j] : __uint_as_float(r[j]) + lo[j];
         }
+        if (H) {
+          // two tile-major fp16 copies (tiles of 128 rows x 64 halfs).  U = [user tile][item block]: for one user the
+          // lanes of the warp are 32 consecutive items = 64 contiguous bytes.  I = [item tile][user block]: this
+          // thread's item row takes its 16 users = 32 contiguous bytes.  Every element of an existing tile is written
+          // (zeros outside the matrix): the backward GEMMs read whole tiles.
+          const int rt = row >> 7, cbu = (i0 >> 6) + (q >> 1);
+          if (rt < p.dzh.row_tiles && cbu < p.dzh.nib64 && !(p.debug & 4)) {
+            const int64_t off = ((int64_t)(rt * p.dzh.nib64 + cbu) * 128 + (row & 127)) * 64 + (q & 1) * 32 + lane;
+            unsigned short* uh = reinterpret_cast<unsigned short*>(p.dzh.u_hi) + off;
+            unsigned short* ul = reinterpret_cast<unsigned short*>(p.dzh.u_lo) + off;
+#pragma unroll
+            for (int j = 0; j < 16; j++) {
+              uh[j * 64] = (unsigned short)(r[j] & 0xffffu);
+              ul[j * 64] = (unsigned short)(r[j] >> 16);
+            }
+          }
+          const int itile = i0 >> 7, ub = row >> 6;
+          if (itile < p.dzh.item_tiles && ub < p.dzh.nub && !(p.debug & 4)) {
+            const int64_t off = ((int64_t)(itile * p.dzh.nub + ub) * 128 + q * 32 + lane) * 64 + (row & 63);
+            uint32_t ph[8], pl[8];
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+              ph[j] = (r[2 * j] & 0xffffu) | (r[2 * j + 1] << 16);
+              pl[j] = (r[2 * j] >> 16) | (r[2 * j + 1] & 0xffff0000u);
+            }
+            uint4* dh4 = reinterpret_cast<uint4*>(reinterpret_cast<unsigned short*>(p.dzh.i_hi) + off);
+            uint4* dl4 = reinterpret_cast<uint4*>(reinterpret_cast<unsigned short*>(p.dzh.i_lo) + off);
+            dh4[0] = make_uint4(ph[0], ph[1], ph[2], ph[3]);
+            dh4[1] = make_uint4(ph[4], ph[5], ph[6], ph[7]);
+            dl4[0] = make_uint4(pl[0], pl[1], pl[2], pl[3]);
+            dl4[1] = make_uint4(pl[4], pl[5], pl[6], pl[7]);
+          }
+        } else {
         // tile-major store: row j of this chunk is the 128-byte line ((row tile, item block), row in tile) and the
         // lanes are its 32 floats.  Every row and column of an existing tile is written (zeros outside the matrix)
         // because the backward GEMMs read whole tiles.
@@ -291,8 +332,9 @@ k_umma_cdae_loss(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
             p.dz_lo[off + j * 32] = lo[j];
           }
         }
+        }
       }
-      if (p.colsum && item_ok) atomicAdd(p.colsum + item, csum);
+      if (p.colsum && item_ok) atomicAdd(p.colsum + item, H ? csum * (p.inv_count / DRB_DZ_F16_SCALE) : csum);
       // this warp has finished reading accumulator `as`
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
@@ -321,21 +363,20 @@ k_umma_cdae_loss(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
   }
 }
 
-template <int BN, int LOSS, bool PER_USER, int KB, int CL>
+template <int BN, int LOSS, bool PER_USER, int KB, int CL, bool H>
 int run_loss(drb_ctx* ctx, const UmmaOperands& o, LossParams p, int* n_blocks_out) {
-  constexpr int BK = KB;
   CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
   int r;
   // MMA roles are swapped with respect to the caller's z = h W'^T: A (M side, 128 TMEM lanes) = W' rows = items,
   // B (N side, BN TMEM columns) = h rows = batch rows
-  if ((r = make_map(&ma_hi, o.b_hi, p.Kred, o.b_rows, o.ldb, BK, BM))) return r;
-  if ((r = make_map(&ma_lo, o.b_lo, p.Kred, o.b_rows, o.ldb, BK, BM))) return r;
-  if ((r = make_map(&mb_hi, o.a_hi, p.Kred, p.M, o.lda, BK, BN / CL))) return r;
-  if ((r = make_map(&mb_lo, o.a_lo, p.Kred, p.M, o.lda, BK, BN / CL))) return r;
+  if ((r = make_operand_map<H>(&ma_hi, o.b_hi, p.Kred, o.b_rows, o.ldb, KB, BM))) return r;
+  if ((r = make_operand_map<H>(&ma_lo, o.b_lo, p.Kred, o.b_rows, o.ldb, KB, BM))) return r;
+  if ((r = make_operand_map<H>(&mb_hi, o.a_hi, p.Kred, p.M, o.lda, KB, BN / CL))) return r;
+  if ((r = make_operand_map<H>(&mb_lo, o.a_lo, p.Kred, p.M, o.lda, KB, BN / CL))) return r;
   p.m_tiles = (p.N + BM - 1) / BM;      // item tiles
   p.n_tiles = (p.M + BN - 1) / BN;      // batch tiles
   p.row_tiles = (p.M + 127) / 128;
-  auto kern = k_umma_cdae_loss<BN, LOSS, PER_USER, KB, CL>;
+  auto kern = k_umma_cdae_loss<BN, LOSS, PER_USER, KB, CL, H>;
   constexpr int SMEM = LossSmem<BN, KB, CL>::TOTAL;
   static bool attr_set = false;       // per template instantiation
   static int max_clusters = 0;
@@ -381,9 +422,13 @@ int run_loss(drb_ctx* ctx, const UmmaOperands& o, LossParams p, int* n_blocks_ou
 int launch_umma_cdae_loss(drb_ctx* ctx, const UmmaOperands& o, int M, int N, int Kred, float* dz_hi, float* dz_lo,
                           int ldc, const float* bias, const float* label_count, const uint32_t* label_bits,
                           int words_per_row, int loss_kind, float inv_count, int batch, float* loss_part,
-                          float* dz_colsum, int* n_blocks_out, float* z_dbg, int ldz) {
+                          float* dz_colsum, int* n_blocks_out, float* z_dbg, int ldz, const DzHalf* dzh) {
   LossParams p{};
   p.z_dbg = z_dbg; p.ldz = ldz;
+  if (o.half) {
+    if (!dzh) return drb_fail(DRB_E_INVALID, "loss kernel: fp16 operands need the fp16 dz buffers");
+    p.dzh = *dzh; p.out_scale = o.out_scale; p.out_scale_dev = o.out_scale_dev;
+  }
   p.M = M; p.N = N; p.Kred = Kred; p.nib = drb_dz_nib(N); p.dz_hi = dz_hi; p.dz_lo = dz_lo; p.bias = bias;
   (void)ldc;
   p.label_count = label_count; p.label_bits = label_bits; p.words_per_row = words_per_row; p.loss_kind = loss_kind;
@@ -396,13 +441,18 @@ int launch_umma_cdae_loss(drb_ctx* ctx, const UmmaOperands& o, int M, int N, int
   const bool wide = bn_env ? (bn_env == 256) : (M > 128);
   static const int bk_env = getenv("DRB_UMMA_BK") ? atoi(getenv("DRB_UMMA_BK")) : 0;   // profiling override: 16 | 32
   static const int cl_env = getenv("DRB_LOSS_CLUSTER") ? atoi(getenv("DRB_LOSS_CLUSTER")) : 0;   // override: 1 | 2
-#define DRB_LOSS_CASE(BN_, KB_, CL_)                                                                \
+#define DRB_LOSS_CASE_H(BN_, KB_, CL_, H_)                                                          \
   {                                                                                                 \
     if (loss_kind == DRB_LOSS_BCE)                                                                  \
-      return per_user ? run_loss<BN_, DRB_LOSS_BCE, true, KB_, CL_>(ctx, o, p, n_blocks_out)        \
-                      : run_loss<BN_, DRB_LOSS_BCE, false, KB_, CL_>(ctx, o, p, n_blocks_out);      \
-    return per_user ? run_loss<BN_, DRB_LOSS_MSE, true, KB_, CL_>(ctx, o, p, n_blocks_out)          \
-                    : run_loss<BN_, DRB_LOSS_MSE, false, KB_, CL_>(ctx, o, p, n_blocks_out);        \
+      return per_user ? run_loss<BN_, DRB_LOSS_BCE, true, KB_, CL_, H_>(ctx, o, p, n_blocks_out)    \
+                      : run_loss<BN_, DRB_LOSS_BCE, false, KB_, CL_, H_>(ctx, o, p, n_blocks_out);  \
+    return per_user ? run_loss<BN_, DRB_LOSS_MSE, true, KB_, CL_, H_>(ctx, o, p, n_blocks_out)      \
+                    : run_loss<BN_, DRB_LOSS_MSE, false, KB_, CL_, H_>(ctx, o, p, n_blocks_out);    \
+  }
+#define DRB_LOSS_CASE(BN_, KB_, CL_)                                                                \
+  {                                                                                                 \
+    if (o.half) DRB_LOSS_CASE_H(BN_, KB_, CL_, true)                                                \
+    DRB_LOSS_CASE_H(BN_, KB_, CL_, false)                                                           \
   }
   if (wide) {
     if ((cl_env ? cl_env : DRB_LOSS_CLUSTER_DEFAULT) == 2) {
@@ -416,4 +466,5 @@ int launch_umma_cdae_loss(drb_ctx* ctx, const UmmaOperands& o, int M, int N, int
   if ((bk_env ? bk_env : 32) == 16) DRB_LOSS_CASE(128, 16, 1)
   DRB_LOSS_CASE(128, 32, 1)
 #undef DRB_LOSS_CASE
+#undef DRB_LOSS_CASE_H
 }

@@ -36,7 +36,7 @@ struct ScoreSmem {
   static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
   static constexpr int STAGES = 192 * 1024 / STAGE_BYTES;
   static constexpr int BAR_BYTES = 256;
-  static constexpr int TAU_BYTES = SC_EPI_WARPS * (BN / 4) * 4;   // per epilogue warp: thresholds of its users
+  static constexpr int TAU_BYTES = SC_EPI_WARPS * (BN / 4) * 8;   // per epilogue warp: (threshold, seen word) of its users
   static constexpr int TOTAL = STAGES * STAGE_BYTES + 1024 + BAR_BYTES + TAU_BYTES;
 };
 
@@ -50,6 +50,7 @@ struct ScoreParams {
   int32_t* cnt;                            // [M] entries appended so far (may exceed cap: overflow)
   uint64_t* lists; int cap;                // [M][cap]
   int m_tiles, n_tiles;
+  float out_scale; const float* out_scale_dev;   // H: accumulator -> logit (undoes the fp16 operand scaling)
   int debug;   // DRB_SCORE_DEBUG bit mask (profiling experiments only, results are wrong): 1 = no appends, 2 = no seen
                // bitmap loads, 4 = no MMAs, 8 = no sigmoid
 };
@@ -63,13 +64,14 @@ __device__ __forceinline__ void sc_mbar_arrive_rank(uint32_t bar, uint32_t rank)
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(mapa_rank(bar, rank)) : "memory");
 }
 
-template <int BN, int KB, int CL>
+template <int BN, int KB, int CL, bool H>
 __global__ void __launch_bounds__(SC_THREADS, 1)
 k_umma_score_filter(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                     const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
                     ScoreParams p) {
   using S = ScoreSmem<BN, KB, CL>;
-  constexpr int BK = KB;
+  constexpr int BK = H ? 2 * KB : KB;            // elements of the hidden dimension per stage (KB: 4-byte units)
+  constexpr int UK = H ? 16 : UMMA_K;            // elements one MMA consumes
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
@@ -80,7 +82,7 @@ k_umma_score_filter(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
   auto tempty_bar = [&](int a) { return bars + 8u * (2 * S::STAGES + 2 + a); };
   const uint32_t tmem_ptr_addr = bars + 8u * (2 * S::STAGES + 4);
   volatile uint32_t* tmem_ptr_generic = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_ptr_addr - raw));
-  uint32_t* tau_smem = reinterpret_cast<uint32_t*>(smem_raw + (bars + S::BAR_BYTES - raw));
+  uint2* tau_smem = reinterpret_cast<uint2*>(smem_raw + (bars + S::BAR_BYTES - raw));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nkb = (p.Kred + BK - 1) / BK;
@@ -150,8 +152,7 @@ k_umma_score_filter(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
     if (lane == 0 && leader) {
-      const uint32_t idesc =
-          (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((BM * CL) >> 4) << 24);
+      const uint32_t idesc = make_idesc<H>(BM * CL, BN);
       int it = 0, tl = 0;
       for (int t = unit0; t < n_units; t += unit_stride, tl++) {
         const int as = tl & 1;
@@ -165,20 +166,15 @@ k_umma_score_filter(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
           const uint32_t sa_hi = base + s * S::STAGE_BYTES, sa_lo = sa_hi + S::A_BYTES;
           const uint32_t sb_hi = sa_lo + S::A_BYTES, sb_lo = sb_hi + S::B_BYTES;
           // the last k-block holds fewer than BK real columns: the MMAs over the zero-filled rest are not issued
-          const int kk_n = (p.debug & 4) ? 0 : min(BK / UMMA_K, (p.Kred - kb * BK + UMMA_K - 1) / UMMA_K);
-#pragma unroll 1
-          for (int kk = 0; kk < kk_n; kk++) {
-            const uint64_t a_hi = make_desc_kmajor<BK>(sa_hi, kk), a_lo = make_desc_kmajor<BK>(sa_lo, kk);
-            const uint64_t b_hi = make_desc_kmajor<BK>(sb_hi, kk), b_lo = make_desc_kmajor<BK>(sb_lo, kk);
-            if (CL > 1) {
-              umma_tf32_pair(tacc, a_lo, b_hi, idesc, (kb | kk) != 0);
-              umma_tf32_pair(tacc, a_hi, b_lo, idesc, 1u);
-              umma_tf32_pair(tacc, a_hi, b_hi, idesc, 1u);
-            } else {
-              umma_tf32(tacc, a_lo, b_hi, idesc, (kb | kk) != 0);
-              umma_tf32(tacc, a_hi, b_lo, idesc, 1u);
-              umma_tf32(tacc, a_hi, b_hi, idesc, 1u);
-            }
+          const int kk_n = (p.debug & 4) ? 0 : min(BK / UK, (p.Kred - kb * BK + UK - 1) / UK);
+#pragma unroll
+          for (int kk = 0; kk < BK / UK; kk++) {
+            if (kk >= kk_n) break;
+            const uint64_t a_hi = make_desc_kmajor<KB>(sa_hi, kk), a_lo = make_desc_kmajor<KB>(sa_lo, kk);
+            const uint64_t b_hi = make_desc_kmajor<KB>(sb_hi, kk), b_lo = make_desc_kmajor<KB>(sb_lo, kk);
+            umma_split<H, CL>(tacc, a_lo, b_hi, idesc, (kb | kk) != 0);
+            umma_split<H, CL>(tacc, a_hi, b_lo, idesc, 1u);
+            umma_split<H, CL>(tacc, a_hi, b_hi, idesc, 1u);
           }
           if (CL > 1) umma_commit_pair(empty_bar(s));
           else umma_commit(empty_bar(s));
@@ -193,8 +189,9 @@ k_umma_score_filter(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
     // column quarter (w-2)/4 of the tile: for one user the 32 lanes of a warp hold 32 consecutive items.
     const int q = warp & 3, cq = (warp - 2) >> 2;
     constexpr int CW = BN / 4;                    // users of this warp per tile
-    uint32_t* my_tau = tau_smem + (warp - 2) * CW;
+    uint2* my_tau = tau_smem + (warp - 2) * CW;    // .x = threshold, .y = the user's seen-bitmap word for this item block
     const uint32_t lt_mask = (1u << lane) - 1u;
+    const float osc = H ? p.out_scale * (p.out_scale_dev ? __ldg(p.out_scale_dev) : 1.0f) : 1.0f;
     float nbias;
     auto fetch_bias = [&](int t) {
       const int item = unit_item0(t) + q * 32 + lane;
@@ -210,12 +207,19 @@ k_umma_score_filter(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
       const int ib = (i0 >> 5) + q;               // 32-item block of this warp == word of the seen bitmap
       const float bias = nbias;
       fetch_bias(t + unit_stride);
-      // thresholds of this warp's users (users beyond the block never pass)
+      // thresholds and seen-bitmap words of this warp's users, fetched before the accumulator is waited for (users
+      // beyond the block never pass)
       __syncwarp();
 #pragma unroll
       for (int c = lane; c < CW; c += 32) {
         const int row = r0 + cq * CW + c;
-        my_tau[c] = (row < p.M) ? __ldg(p.tau_ord + row) : 0xffffffffu;
+        uint2 v = make_uint2(0xffffffffu, 0u);
+        if (row < p.M) {
+          v.x = __ldg(p.tau_ord + row);
+          if (p.seen_bits && !(p.debug & 2) && ib < p.words_per_row)
+            v.y = __ldg(p.seen_bits + (int64_t)row * p.words_per_row + ib);
+        }
+        my_tau[c] = v;
       }
       __syncwarp();
       mbar_wait(tfull_bar(as), (tl >> 1) & 1);
@@ -235,13 +239,11 @@ k_umma_score_filter(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
         // 1. score, knock-out, threshold test: r[j] becomes the orderable score, bal[j] the lanes that pass for user j
 #pragma unroll
         for (int j = 0; j < 16; j++) {
-          const float z = __uint_as_float(r[j]) + bias;
+          const float z = H ? fmaf(__uint_as_float(r[j]), osc, bias) : __uint_as_float(r[j]) + bias;
           const float pr = (p.debug & 8) ? fabsf(z) : sc_rcp(1.0f + sc_ex2(z * -1.4426950408889634f));   // sigmoid, > 0
           const uint32_t ord = __float_as_uint(pr) | 0x80000000u;               // f2ord of a non-negative float
-          uint32_t seen = 0u;
-          if (p.seen_bits && !(p.debug & 2) && row + j < p.M && ib < p.words_per_row)
-            seen = __ldg(p.seen_bits + (int64_t)(row + j) * p.words_per_row + ib);
-          const bool pass = item_ok && (row + j < p.M) && !((seen >> lane) & 1u) && (ord >= my_tau[cl + j]);
+          const uint2 ts = my_tau[cl + j];                                      // broadcast read
+          const bool pass = item_ok && (row + j < p.M) && !((ts.y >> lane) & 1u) && (ord >= ts.x);
           r[j] = ord;
           bal[j] = (p.debug & 1) ? 0u : __ballot_sync(0xffffffffu, pass);
         }
@@ -281,20 +283,19 @@ k_umma_score_filter(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
   }
 }
 
-template <int BN, int KB, int CL>
+template <int BN, int KB, int CL, bool H>
 int run_score(drb_ctx* ctx, const UmmaOperands& o, ScoreParams p, int n_items) {
-  constexpr int BK = KB;
   CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
   int r;
   // A (M side, TMEM lanes) = W' rows = items; B (N side, TMEM columns) = h rows = users.  Rows past the end of either
   // matrix read as zeros (TMA out-of-bounds fill) and are masked in the epilogue.
-  if ((r = make_map(&ma_hi, o.b_hi, p.Kred, n_items, o.ldb, BK, BM))) return r;
-  if ((r = make_map(&ma_lo, o.b_lo, p.Kred, n_items, o.ldb, BK, BM))) return r;
-  if ((r = make_map(&mb_hi, o.a_hi, p.Kred, p.M, o.lda, BK, BN / CL))) return r;
-  if ((r = make_map(&mb_lo, o.a_lo, p.Kred, p.M, o.lda, BK, BN / CL))) return r;
+  if ((r = make_operand_map<H>(&ma_hi, o.b_hi, p.Kred, n_items, o.ldb, KB, BM))) return r;
+  if ((r = make_operand_map<H>(&ma_lo, o.b_lo, p.Kred, n_items, o.ldb, KB, BM))) return r;
+  if ((r = make_operand_map<H>(&mb_hi, o.a_hi, p.Kred, p.M, o.lda, KB, BN / CL))) return r;
+  if ((r = make_operand_map<H>(&mb_lo, o.a_lo, p.Kred, p.M, o.lda, KB, BN / CL))) return r;
   p.m_tiles = (p.item_end - p.item_begin + BM - 1) / BM;
   p.n_tiles = (p.M + BN - 1) / BN;
-  auto kern = k_umma_score_filter<BN, KB, CL>;
+  auto kern = k_umma_score_filter<BN, KB, CL, H>;
   constexpr int SMEM = ScoreSmem<BN, KB, CL>::TOTAL;
   static bool attr_set = false;
   static int max_clusters = 0;
@@ -346,6 +347,11 @@ int launch_umma_score_filter(drb_ctx* ctx, const UmmaOperands& o, int n_users, i
   p.M = n_users; p.item_begin = item_begin; p.item_end = item_end; p.Kred = Kred; p.bias = bias;
   p.seen_bits = seen_bits; p.words_per_row = words_per_row; p.tau_ord = tau_ord; p.cnt = cnt; p.lists = lists; p.cap = cap;
   p.debug = getenv("DRB_SCORE_DEBUG") ? atoi(getenv("DRB_SCORE_DEBUG")) : 0;
-  if (n_users > 128) return run_score<256, 32, 2>(ctx, o, p, n_items);
-  return run_score<128, 32, 1>(ctx, o, p, n_items);
+  p.out_scale = o.out_scale; p.out_scale_dev = o.out_scale_dev;
+  if (o.half) {
+    if (n_users > 128) return run_score<256, 32, 2, true>(ctx, o, p, n_items);
+    return run_score<128, 32, 1, true>(ctx, o, p, n_items);
+  }
+  if (n_users > 128) return run_score<256, 32, 2, false>(ctx, o, p, n_items);
+  return run_score<128, 32, 1, false>(ctx, o, p, n_items);
 }

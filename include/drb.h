@@ -40,7 +40,7 @@ enum {
 enum { DRB_LOSS_BCE = 0, DRB_LOSS_MSE = 1 };
 enum { DRB_LABEL_BATCH_MEAN = 0, DRB_LABEL_PER_USER = 1 };
 enum { DRB_ACT_NONE = 0, DRB_ACT_SIGMOID = 1, DRB_ACT_RELU = 2 };
-enum { DRB_GEMM_AUTO = 0, DRB_GEMM_FFMA = 1, DRB_GEMM_TCGEN05 = 2 };
+enum { DRB_GEMM_AUTO = 0, DRB_GEMM_FFMA = 1, DRB_GEMM_TCGEN05 = 2, DRB_GEMM_TCGEN05_TF32 = 3 };
 
 typedef struct drb_ctx drb_ctx;
 typedef struct drb_rng drb_rng;
@@ -145,7 +145,8 @@ typedef struct {
   void* workspace;             /* device, >= drb_cdae_workspace_bytes(...) */
   int64_t workspace_bytes;
   int32_t max_batch;
-  int32_t gemm_path;           /* DRB_GEMM_AUTO (tcgen05 3xTF32 when hidden <= 256), DRB_GEMM_FFMA, DRB_GEMM_TCGEN05 */
+  int32_t gemm_path;           /* DRB_GEMM_AUTO (tcgen05 when hidden <= 256), DRB_GEMM_FFMA (exact fp32 on the CUDA cores),
+                                  DRB_GEMM_TCGEN05 (fp32-accurate 3xFP16 split products), DRB_GEMM_TCGEN05_TF32 (3xTF32) */
 } drb_cdae_desc;
 
 typedef struct {
@@ -322,6 +323,16 @@ int drb_debug_umma_gemm(drb_ctx* ctx, const float* a_hi, const float* a_lo, int3
                         const float* b_lo, int32_t ldb, int32_t b_rows, int32_t a_mn_major, int32_t M, int32_t N,
                         int32_t Kred, int32_t splits, float* C, int32_t ldc, int32_t n_store, float* extra_col,
                         int32_t extra_col_index);
+
+/* The 3xFP16 forms of the same building blocks: x * alpha -> fp16 hi / lo ([rows][ldh halfs]; transposed [cols..][ldt
+ * halfs], ones_row set to alpha), and C = out_scale * sum_k A(m,k) B(n,k) from K-major fp16 hi / lo operands
+ * (A [M][lda halfs], B [b_rows][ldb halfs]; pitches are multiples of 8). */
+int drb_debug_split_f16(drb_ctx* ctx, const float* src, int32_t rows, int32_t cols, int32_t ld, float alpha, void* hi,
+                        void* lo, int32_t ldh, void* t_hi, void* t_lo, int32_t ldt, int32_t ones_row);
+int drb_debug_umma_gemm_f16(drb_ctx* ctx, const void* a_hi, const void* a_lo, int32_t lda, const void* b_hi,
+                            const void* b_lo, int32_t ldb, int32_t b_rows, int32_t M, int32_t N, int32_t Kred,
+                            int32_t splits, float out_scale, float* C, int32_t ldc, int32_t n_store, float* extra_col,
+                            int32_t extra_col_index);
 
 /* ------------------------------------------------------------------ ranking_evaluation candidate generation
  * replaces: DRecPy/Evaluation/Processes/ranking_evaluation.py:108-116,163-219 -- per-user

@@ -1,4 +1,5 @@
-"""tcgen05 (3xTF32, TMA, TMEM) GEMM path against the exact-fp32 FFMA path and the oracle (GPU only)."""
+"""tcgen05 (split-precision products, TMA, TMEM) GEMM paths -- 3xFP16 (default) and 3xTF32 -- against the exact-fp32 FFMA
+path and the oracle (GPU only)."""
 import numpy as np
 import pytest
 
@@ -35,9 +36,10 @@ def rel(a, b):
                                          # hidden 241..256: no room for the ones feature, db' summed in the loss epilogue
                                          (300, 900, 256, 200, 9000), (200, 600, 248, 64, 5000)])
 @pytest.mark.parametrize('label_mode,loss', [('batch_mean', 'bce'), ('per_user', 'mse')])
-def test_tcgen05_step_matches_ffma_and_oracle(U, I, K, B, nnz, label_mode, loss):
+@pytest.mark.parametrize('gemm', ['tcgen05', 'tcgen05_tf32'])
+def test_tcgen05_step_matches_ffma_and_oracle(U, I, K, B, nnz, label_mode, loss, gemm):
     import torch
-    ds, w, m_tc = _setup(U, I, K, B, nnz, 'tcgen05', label_mode=label_mode, loss=loss)
+    ds, w, m_tc = _setup(U, I, K, B, nnz, gemm, label_mode=label_mode, loss=loss)
     _, _, m_ff = _setup(U, I, K, B, nnz, 'ffma', label_mode=label_mode, loss=loss)
     o = CDAEOracle(w['W'], w['W_'], w['V'], w['b'], w['b_'], ds.csr(), corruption_level=0.0, loss=loss,
                    label_mode=label_mode, learning_rate=1e-3)

@@ -101,3 +101,54 @@ def test_umma_mnmajor_with_ones_column(ctx, M, N, K):
     assert ok, msg
     ok, msg = _report(extra[:, None], G[:, :M].double().sum(0)[:, None], 'ones column')
     assert ok, msg
+
+
+# ------------------------------------------------------------------------------------------------ 3xFP16 building blocks
+def _split_f16(ctx, x, alpha, transpose=False, ones_row=-1, t_rows=None):
+    import torch
+    lib = _lib.load()
+    rows, ld = x.shape
+    ldh = (ld + 7) // 8 * 8
+    hi = torch.zeros((rows, ldh), dtype=torch.float16, device='cuda')
+    lo = torch.zeros_like(hi)
+    t_hi = t_lo = None
+    ldt = 0
+    if transpose:
+        ldt = (rows + 7) // 8 * 8
+        t_hi = torch.zeros((t_rows or ld, ldt), dtype=torch.float16, device='cuda')
+        t_lo = torch.zeros_like(t_hi)
+    _lib.check(lib.drb_debug_split_f16(ctx, _lib.t_ptr(x), rows, ld, ld, alpha, _lib.t_ptr(hi), _lib.t_ptr(lo), ldh,
+                                       _lib.t_ptr(t_hi), _lib.t_ptr(t_lo), ldt, ones_row))
+    return hi, lo, t_hi, t_lo
+
+
+@pytest.mark.parametrize('M,N,K,splits', [(128, 64, 32, 1), (128, 128, 64, 1), (300, 208, 200, 1), (257, 56, 1000, 3),
+                                          (64, 256, 100, 1), (4096, 208, 2048, 4), (26744, 208, 512, 2)])
+def test_umma_f16_kmajor(ctx, M, N, K, splits):
+    """C = A B^T from fp16 hi/lo operands scaled into the fp16 range: within 1e-5 of the float64 product, i.e. the same
+    accuracy as the 3xTF32 form.  Operand magnitudes span what the CDAE step feeds (weights ~1e-2, activations in (0,1),
+    gradients with a wide dynamic range)."""
+    import torch
+    g = torch.Generator(device='cuda').manual_seed(M * 7 + N)
+    a = torch.rand((M, K), device='cuda', generator=g) * 0.999                       # activations
+    b = (torch.rand((N, K), device='cuda', generator=g) - 0.5) * 0.03               # weights
+    b = b * torch.pow(10.0, -3 * torch.rand((N, K), device='cuda', generator=g))     # with a wide dynamic range
+    alpha_a = 32768.0
+    alpha_b = float(2.0 ** (14 - np.floor(np.log2(b.abs().max().item()))))
+    a_hi, a_lo, _, _ = _split_f16(ctx, a, alpha_a)
+    b_hi, b_lo, _, _ = _split_f16(ctx, b, alpha_b)
+    assert float(a_hi.float().abs().max()) <= 32768 and float(b_hi.float().abs().max()) < 32768
+    # the split itself keeps ~22 bits of every element that matters
+    rec = (a_hi.double() + a_lo.double())[:, :K] / alpha_a
+    assert float((rec - a.double()).abs().max()) <= 2.0 ** -22
+    lib = _lib.load()
+    ldc = (N + 3) // 4 * 4
+    Cm = torch.full((splits, M, ldc), float('nan'), device='cuda')
+    _lib.check(lib.drb_debug_umma_gemm_f16(ctx, _lib.t_ptr(a_hi), _lib.t_ptr(a_lo), a_hi.shape[1], _lib.t_ptr(b_hi),
+                                           _lib.t_ptr(b_lo), b_hi.shape[1], N, M, N, K, splits,
+                                           1.0 / (alpha_a * alpha_b), _lib.t_ptr(Cm), ldc, N, None, -1))
+    torch.cuda.synchronize()
+    got = Cm.sum(0)[:, :N]
+    want = a.double() @ b.double().t()
+    ok, msg = _report(got, want, f'f16 kmajor {M}x{N}x{K}/{splits}')
+    assert ok, msg
