@@ -472,6 +472,10 @@ int launch_umma_store(drb_ctx* ctx, const UmmaOperands& o, bool a_mn_major, int 
     if (a_mn_major) return run_umma<BN, true, 32, 1, false>(ctx, o, p, nullptr);        \
     return run_umma<BN, false, 32, 1, false>(ctx, o, p, nullptr);                       \
   }
+  DRB_UMMA_CASE(64, 32, 1)
+  DRB_UMMA_CASE(128, 32, 1)
+  DRB_UMMA_CASE(208, 16, 2)
+  DRB_UMMA_CASE(256, 16, 2)
 #undef DRB_UMMA_CASE
   return drb_fail(DRB_E_INVALID, "umma store GEMM: unsupported N");
 }
