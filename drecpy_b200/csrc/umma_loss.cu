@@ -273,17 +273,30 @@ k_umma_cdae_loss(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
           loss_local += ok ? lt : 0.f;
           const float g = ok ? gz : 0.f;
           if (H) {
-            __half hh, hl;
-            split_f16(g, hh, hl);
-            r[j] = (uint32_t)__half_as_ushort(hh) | ((uint32_t)__half_as_ushort(hl) << 16);   // hi | lo << 16
-            lo[j] = __half2float(hh) + __half2float(hl);
+            lo[j] = g;                             // split below, two users at a time
           } else {
             float h;
             split_tf32(g, h, lo[j]);
             r[j] = __float_as_uint(h);
           }
         }
-        if (p.colsum) {
+        if (H) {
+          // fp16 hi/lo split of 16 values with 16 packed conversions (cvt.rn.f16x2.f32 handles two floats): hi is first
+          // rounded to 11 significant bits in fp32 (Dekker: c = g * (2^13 + 1), hi = c - (c - g)), so its conversion
+          // is exact and lo = g - hi needs no conversion back.  r[j] = hi | lo << 16.
+#pragma unroll
+          for (int j = 0; j < 16; j += 2) {
+            const float c0 = __fmul_rn(lo[j], 8193.0f), c1 = __fmul_rn(lo[j + 1], 8193.0f);   // no fma contraction
+            const float h0 = __fsub_rn(c0, __fsub_rn(c0, lo[j])), h1 = __fsub_rn(c1, __fsub_rn(c1, lo[j + 1]));
+            const float l0 = __fsub_rn(lo[j], h0), l1 = __fsub_rn(lo[j + 1], h1);
+            uint32_t hp, lp;                        // .x = user j (low half), .y = user j + 1
+            asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(hp) : "f"(h1), "f"(h0));
+            asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(lp) : "f"(l1), "f"(l0));
+            r[j] = (hp & 0xffffu) | (lp << 16);
+            r[j + 1] = (hp >> 16) | (lp & 0xffff0000u);
+          }
+        }
+        if (p.colsum) {                         // H: lo[] still holds the unsplit values
 #pragma unroll
           for (int j = 0; j < 16; j++) csum += H ? lo[j] : __uint_as_float(r[j]) + lo[j];
         }
