@@ -115,6 +115,8 @@ SIGNATURES = {
     'drb_dmf_create': (C.c_int, [vp, P(DmfDesc), P(vp)]),
     'drb_dmf_destroy': (C.c_int, [vp]),
     'drb_dmf_step': (C.c_int, [vp, vp, vp, vp, i32, P(DmfStepArgs), vp]),
+    'drb_dmf_step_phases': (C.c_int, [vp, vp, vp, vp, i32, P(DmfStepArgs), vp, i32, i32]),
+    'drb_dmf_grads_buffer': (C.c_int, [vp, P(vp), P(i64)]),
     'drb_dmf_step_host': (C.c_int, [vp, vp, vp, vp, i32, P(DmfStepArgs), vp]),
     'drb_dmf_forward_pairs': (C.c_int, [vp, vp, vp, i32, vp]),
     'drb_dmf_rank_candidates': (C.c_int, [vp, vp, i32, vp, vp, i32, i32, vp, vp, vp]),

@@ -330,6 +330,10 @@ int drb_cdae_create(drb_ctx* ctx, const drb_cdae_desc* desc, drb_cdae** out) {
     return drb_fail(DRB_E_INVALID, "drb_cdae_create: workspace too small (%lld < %lld bytes)",
                     (long long)desc->workspace_bytes, (long long)need);
   }
+  if (cudaMemsetAsync(m->ws.loss_scalar, 0, 64 * sizeof(float), ctx->stream) != cudaSuccess) {   // loss, scales, ticket
+    delete m;
+    return drb_fail(DRB_E_CUDA, "drb_cdae_create: workspace clear failed");
+  }
   if (m->use_umma) {   // transposed operand buffers: rows >= hidden stay zero (the ones row is rewritten every step)
     cudaError_t e = cudaMemsetAsync(m->ws.hT_hi, 0, (size_t)m->ws.hT_floats * 4, ctx->stream);
     if (e == cudaSuccess) e = cudaMemsetAsync(m->ws.hT_lo, 0, (size_t)m->ws.hT_floats * 4, ctx->stream);
@@ -643,10 +647,15 @@ int drb_cdae_step_phases(drb_cdae* m, const int32_t* uids, const int32_t* keep_o
     return DRB_OK;
   };
   int n_reg = 0;
+  auto fuse_finalize = [&](int n_regs) {      // the last Adam block also writes the loss (one launch less)
+    ad.fin_loss_part = w.loss_part; ad.fin_n_loss = m->n_loss_blocks; ad.fin_scale = inv_count; ad.fin_n_reg = n_regs;
+    ad.fin_reg_part = w.reg_part; ad.fin_loss_out = loss_out;
+    ad.fin_ticket = reinterpret_cast<unsigned int*>(w.loss_scalar + 48);
+  };
   if (phases & DRB_PHASE_UPDATE) {
+    fuse_finalize(0);
     if ((r = run_adam(0, 4, 0, &n_reg))) return r;
-    if ((r = rezero_user_rows())) return r;
-    return launch_finalize_loss(ctx, w.loss_part, m->n_loss_blocks, inv_count, w.reg_part, n_reg, loss_out);
+    return rezero_user_rows();
   }
   if (!m->reg_slots_clear) {   // split form: unused entries of the three partial-sum slots must read as zero
     DRB_CUDA_TRY(ctx, cudaMemsetAsync(w.reg_part, 0, (size_t)3 * R * sizeof(float), ctx->stream));
@@ -660,8 +669,8 @@ int drb_cdae_step_phases(drb_cdae* m, const int32_t* uids, const int32_t* keep_o
     if ((r = run_adam(0, 0, 1, &n_reg))) return r;
   }
   if (phases & DRB_PHASE_UPDATE_REST) {
+    fuse_finalize(3 * R);
     if ((r = run_adam(1, 3, 2, &n_reg))) return r;
-    return launch_finalize_loss(ctx, w.loss_part, m->n_loss_blocks, inv_count, w.reg_part, 3 * R, loss_out);
   }
   return DRB_OK;
 }
@@ -898,7 +907,7 @@ struct drb_dmf {
   // copied there first), so there is one graph per (batch size, loss pointer, hyper-parameters).
   struct Graph {
     const void* loss_out;
-    int32_t batch; float beta1, beta2, eps, reg;
+    int32_t batch, phases, global_batch; float beta1, beta2, eps, reg;
     cudaGraphExec_t exec; int64_t launches;
   } graphs[8];
   int n_graphs, graph_next, graph_off, n_captures;
@@ -1075,6 +1084,10 @@ int drb_dmf_create(drb_ctx* ctx, const drb_dmf_desc* d, drb_dmf** out) {
     return drb_fail(DRB_E_INVALID, "drb_dmf_create: workspace too small (%lld < %lld bytes)",
                     (long long)d->workspace_bytes, (long long)need);
   }
+  if (cudaMemsetAsync(m->loss_scalar, 0, 64 * sizeof(float), ctx->stream) != cudaSuccess) {   // loss, step sizes, ticket
+    delete m;
+    return drb_fail(DRB_E_CUDA, "drb_dmf_create: workspace clear failed");
+  }
   *out = m;
   return DRB_OK;
 }
@@ -1088,22 +1101,86 @@ int drb_dmf_destroy(drb_dmf* m) {
   return DRB_OK;
 }
 
-// one training step enqueued on ctx->stream; alpha_dev != NULL: Adam step sizes come from device memory (graph capture)
+// Both towers have exactly two Dense layers of equal first width that fit the fused kernels: the forward pass of BOTH
+// towers is one launch (row gather + first layer, second layer fused in the same CTA) and so are the dense part of
+// the backward pass and the scatter into the first-layer kernels: memset + 5 kernels per step instead of 22.
+static bool dmf_fused_ok(const drb_dmf* m) {
+  const DmfTower& A = m->tw[0];
+  const DmfTower& B = m->tw[1];
+  return A.n_layers == 2 && B.n_layers == 2 && A.ld[0] == B.ld[0] && dmf_tower_bwd_fits(A.width[0], A.ld[0], A.width[1]) &&
+         dmf_tower_bwd_fits(B.width[0], B.ld[0], B.width[1]) && !getenv("DRB_DMF_UNFUSED");
+}
+
+static GatherArgs dmf_gather_args(drb_dmf* m, int t, const int32_t* ids, bool fuse_next) {
+  DmfTower& T = m->tw[t];
+  float* P = m->d.params;
+  GatherArgs g{};
+  g.indptr = T.indptr; g.indices = T.indices; g.values = T.values; g.rows = ids;
+  g.table = P + T.off_k[0]; g.ld = T.ld[0]; g.bias = P + T.off_b[0];
+  g.row_scale = T.row_scale; g.scale = 1.0f; g.act = DRB_ACT_RELU; g.width = T.width[0]; g.out = T.act[0];
+  if (fuse_next) {
+    g.next_k = P + T.off_k[1]; g.next_b = P + T.off_b[1]; g.next_ld = T.ld[1]; g.next_width = T.width[1];
+    g.next_act = DRB_ACT_RELU; g.next_out = T.act[1];
+  }
+  return g;
+}
+
+static int dmf_towers_fwd_fused(drb_dmf* m, const int32_t* uids, const int32_t* iids, int n) {
+  return launch_gather_pair(m->ctx, dmf_gather_args(m, 0, uids, true), dmf_gather_args(m, 1, iids, true), n);
+}
+
+static int dmf_towers_bwd_fused(drb_dmf* m, const int32_t* uids, const int32_t* iids, int n) {
+  float* P = m->d.params;
+  float* G = m->d.grads;
+  DmfTowerBwd tb[2];
+  ScatterArgs sc[2];
+  for (int t = 0; t < 2; t++) {
+    DmfTower& T = m->tw[t];
+    tb[t] = DmfTowerBwd{T.act[0], T.dpre[1], P + T.off_k[1], T.dpre[0], G + T.off_k[1], G + T.off_b[1], G + T.off_b[0],
+                        T.width[0], T.ld[0], T.width[1], T.ld[1]};
+    sc[t] = ScatterArgs{};
+    sc[t].indptr = T.indptr; sc[t].indices = T.indices; sc[t].values = T.values; sc[t].rows = t ? iids : uids;
+    sc[t].row_scale = T.row_scale; sc[t].scale = 1.0f; sc[t].d = T.dpre[0]; sc[t].ld = T.ld[0];
+    sc[t].gtable = G + T.off_k[0];
+  }
+  int r = launch_dmf_tower_bwd(m->ctx, tb[0], tb[1], n);
+  if (r) return r;
+  return launch_scatter_pair(m->ctx, sc[0], sc[1], n);
+}
+
+enum { DMF_PHASE_GRADS = 1, DMF_PHASE_UPDATE = 2 };
+
+// one training step enqueued on ctx->stream; alpha_dev != NULL: Adam step sizes come from device memory (graph capture).
+// phases: GRADS = forward + backward into the gradient arena (data parallel: the caller all-reduces it), UPDATE = Adam
+// + loss.  global_batch > 0: the loss mean and its gradient use it instead of `batch`.
 static int dmf_step_body(drb_dmf* m, const int32_t* uids, const int32_t* iids, const float* labels, int32_t batch,
-                         const drb_dmf_step_args* a, float* loss_out, const float* alpha_dev) {
+                         const drb_dmf_step_args* a, float* loss_out, const float* alpha_dev, int phases = 3,
+                         int global_batch = 0) {
   drb_ctx* ctx = m->ctx;
   int r;
+  const bool fused = dmf_fused_ok(m);
+  if (phases & DMF_PHASE_GRADS) {
   DRB_CUDA_TRY(ctx, cudaMemsetAsync(m->d.grads, 0, (size_t)m->L.total * sizeof(float), ctx->stream));
-  if ((r = dmf_tower_fwd(m, 0, uids, batch))) return r;
-  if ((r = dmf_tower_fwd(m, 1, iids, batch))) return r;
+  if (fused) {
+    if ((r = dmf_towers_fwd_fused(m, uids, iids, batch))) return r;
+  } else {
+    if ((r = dmf_tower_fwd(m, 0, uids, batch))) return r;
+    if ((r = dmf_tower_fwd(m, 1, iids, batch))) return r;
+  }
   const int lu = m->tw[0].n_layers - 1, li = m->tw[1].n_layers - 1;
   DmfHeadArgs h{};
   h.a = m->tw[0].act[lu]; h.e = m->tw[1].act[li]; h.ld = m->tw[0].ld[lu]; h.width = m->tw[0].width[lu];
   h.labels = labels; h.p_out = nullptr; h.da = m->tw[0].dpre[lu]; h.de = m->tw[1].dpre[li];
-  h.loss_part = m->loss_part; h.n = batch;
+  h.loss_part = m->loss_part; h.n = batch; h.n_global = global_batch;
   if ((r = launch_dmf_head(ctx, h))) return r;
-  if ((r = dmf_tower_bwd(m, 0, uids, batch))) return r;
-  if ((r = dmf_tower_bwd(m, 1, iids, batch))) return r;
+  if (fused) {
+    if ((r = dmf_towers_bwd_fused(m, uids, iids, batch))) return r;
+  } else {
+    if ((r = dmf_tower_bwd(m, 0, uids, batch))) return r;
+    if ((r = dmf_tower_bwd(m, 1, iids, batch))) return r;
+  }
+  }
+  if (!(phases & DMF_PHASE_UPDATE)) return DRB_OK;
   AdamArgs ad{};
   ad.w = m->d.params; ad.m = m->d.adam_m; ad.v = m->d.adam_v; ad.g = m->d.grads;
   ad.beta1 = a->beta1; ad.beta2 = a->beta2; ad.eps = a->epsilon;
@@ -1127,14 +1204,31 @@ static int dmf_step_body(drb_dmf* m, const int32_t* uids, const int32_t* iids, c
   }
   ad.nseg = ns;
   ad.reg_part = m->reg_part;
+  // the last Adam block also reduces the per-pair loss terms and the L2 partials into loss_out (one launch less)
+  ad.fin_loss_part = m->loss_part; ad.fin_n_loss = batch; ad.fin_scale = 1.0f / (float)(global_batch > 0 ? global_batch : batch);
+  ad.fin_n_reg = 0; ad.fin_reg_part = nullptr; ad.fin_loss_out = loss_out;
+  ad.fin_ticket = reinterpret_cast<unsigned int*>(m->loss_scalar + 48);
   int n_reg = 0;
-  if ((r = launch_adam(ctx, ad, &n_reg))) return r;
-  return launch_finalize_loss(ctx, m->loss_part, batch, 1.0f / (float)batch, m->reg_part, n_reg, loss_out);
+  return launch_adam(ctx, ad, &n_reg);
 }
 
 int drb_dmf_step(drb_dmf* m, const int32_t* uids, const int32_t* iids, const float* labels, int32_t batch,
                  const drb_dmf_step_args* a, float* loss_out) {
+  return drb_dmf_step_phases(m, uids, iids, labels, batch, a, loss_out, DRB_DMF_PHASE_ALL, 0);
+}
+
+int drb_dmf_grads_buffer(drb_dmf* m, float** ptr, int64_t* count) {
+  if (!m || !ptr || !count) return drb_fail(DRB_E_INVALID, "drb_dmf_grads_buffer: NULL argument");
+  *ptr = m->d.grads;
+  *count = m->L.total;
+  return DRB_OK;
+}
+
+int drb_dmf_step_phases(drb_dmf* m, const int32_t* uids, const int32_t* iids, const float* labels, int32_t batch,
+                        const drb_dmf_step_args* a, float* loss_out, int32_t phases, int32_t global_batch) {
   if (!m || !uids || !iids || !labels || !a || !loss_out) return drb_fail(DRB_E_INVALID, "drb_dmf_step: NULL argument");
+  if (!(phases & DRB_DMF_PHASE_ALL) || global_batch < 0 || (global_batch && global_batch < batch))
+    return drb_fail(DRB_E_INVALID, "drb_dmf_step_phases: bad phases / global_batch");
   if (batch <= 0 || batch > m->d.max_batch)
     return drb_fail(DRB_E_INVALID, "drb_dmf_step: batch %d outside (0, max_batch=%d]", batch, m->d.max_batch);
   if (!m->d.adam_m || !m->d.adam_v || !m->d.grads)
@@ -1143,7 +1237,7 @@ int drb_dmf_step(drb_dmf* m, const int32_t* uids, const int32_t* iids, const flo
   if (ctx->sticky) return drb_fail(DRB_E_CUDA, "context has a sticky CUDA error (%d)", ctx->sticky);
   m->item_rep_valid = false;           // the weights are about to change
   if (m->graph_off || ctx->profile)    // per-kernel profiling brackets every launch with events: direct launches
-    return dmf_step_body(m, uids, iids, labels, batch, a, loss_out, nullptr);
+    return dmf_step_body(m, uids, iids, labels, batch, a, loss_out, nullptr, phases, global_batch);
 
   if (uids != m->uids) DRB_CUDA_TRY(ctx, cudaMemcpyAsync(m->uids, uids, (size_t)batch * 4, cudaMemcpyDeviceToDevice, ctx->stream));
   if (iids != m->iids) DRB_CUDA_TRY(ctx, cudaMemcpyAsync(m->iids, iids, (size_t)batch * 4, cudaMemcpyDeviceToDevice, ctx->stream));
@@ -1152,19 +1246,20 @@ int drb_dmf_step(drb_dmf* m, const int32_t* uids, const int32_t* iids, const flo
   drb_dmf::Graph* g = nullptr;
   for (int i = 0; i < m->n_graphs; i++) {
     drb_dmf::Graph& c = m->graphs[i];
-    if (c.loss_out == loss_out && c.batch == batch && c.beta1 == a->beta1 && c.beta2 == a->beta2 && c.eps == a->epsilon && c.reg == a->reg_rate) { g = &c; break; }
+    if (c.loss_out == loss_out && c.batch == batch && c.phases == phases && c.global_batch == global_batch &&
+        c.beta1 == a->beta1 && c.beta2 == a->beta2 && c.eps == a->epsilon && c.reg == a->reg_rate) { g = &c; break; }
   }
   if (!g) {
     // capture the step once for this argument set (nothing executes during capture); a caller that keeps changing
     // the argument set would pay a capture per step: give up on graphs after 32 captures
     if (++m->n_captures > 32) {
       m->graph_off = 1;
-      return dmf_step_body(m, m->uids, m->iids, m->labels, batch, a, loss_out, nullptr);
+      return dmf_step_body(m, m->uids, m->iids, m->labels, batch, a, loss_out, nullptr, phases, global_batch);
     }
     if (!m->cap_stream && cudaStreamCreateWithFlags(&m->cap_stream, cudaStreamNonBlocking) != cudaSuccess) {
       cudaGetLastError();
       m->graph_off = 1;
-      return dmf_step_body(m, uids, iids, labels, batch, a, loss_out, nullptr);
+      return dmf_step_body(m, uids, iids, labels, batch, a, loss_out, nullptr, phases, global_batch);
     }
     cudaStream_t user = ctx->stream;
     const int64_t before = ctx->launches;
@@ -1174,7 +1269,7 @@ int drb_dmf_step(drb_dmf* m, const int32_t* uids, const int32_t* iids, const flo
     cudaError_t e = cudaStreamBeginCapture(m->cap_stream, cudaStreamCaptureModeThreadLocal);
     if (e == cudaSuccess) {
       ctx->stream = m->cap_stream;
-      r = dmf_step_body(m, m->uids, m->iids, m->labels, batch, a, loss_out, m->step_scalars);
+      r = dmf_step_body(m, m->uids, m->iids, m->labels, batch, a, loss_out, m->step_scalars, phases, global_batch);
       ctx->stream = user;
       e = cudaStreamEndCapture(m->cap_stream, &graph);
     }
@@ -1186,11 +1281,11 @@ int drb_dmf_step(drb_dmf* m, const int32_t* uids, const int32_t* iids, const flo
       cudaGetLastError();
       ctx->sticky = 0;
       m->graph_off = 1;
-      return dmf_step_body(m, uids, iids, labels, batch, a, loss_out, nullptr);
+      return dmf_step_body(m, uids, iids, labels, batch, a, loss_out, nullptr, phases, global_batch);
     }
     const int slot = m->n_graphs < 8 ? m->n_graphs++ : (m->graph_next++ & 7);
     if (m->graphs[slot].exec) cudaGraphExecDestroy(m->graphs[slot].exec);
-    m->graphs[slot] = drb_dmf::Graph{loss_out, batch, a->beta1, a->beta2, a->epsilon, a->reg_rate,
+    m->graphs[slot] = drb_dmf::Graph{loss_out, batch, phases, global_batch, a->beta1, a->beta2, a->epsilon, a->reg_rate,
                                      exec, captured};
     g = &m->graphs[slot];
   }

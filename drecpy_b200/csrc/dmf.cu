@@ -41,7 +41,7 @@ __global__ void __launch_bounds__(128) k_dmf_head(DmfHeadArgs h) {
   const float da_ = pc + KERAS_EPS, db_ = 1.0f - pc + KERAS_EPS;
   if (lane == 0) h.loss_part[warp] = -(t * logf(da_) + (1.0f - t) * logf(db_));
   const bool inside = (p >= KERAS_EPS) && (p <= one_m);
-  const float dp = inside ? -(t / da_ - (1.0f - t) / db_) / (float)h.n : 0.f;
+  const float dp = inside ? -(t / da_ - (1.0f - t) / db_) / (float)(h.n_global > 0 ? h.n_global : h.n) : 0.f;
   const float dc = (c > 1e-6f) ? dp : 0.f;
   for (int k = lane; k < h.ld; k += 32) {
     float ga = 0.f, ge = 0.f;
@@ -59,7 +59,67 @@ __global__ void __launch_bounds__(128) k_dmf_head(DmfHeadArgs h) {
   }
 }
 
+// Dense part of the backward pass of a two-layer tower, both towers in one launch (blockIdx.y), kRows batch rows per CTA:
+//   dpre0[r] = (dpre1[r] K1^T) * [act0[r] > 0];  dK1 += act0^T dpre1;  db1 += sum_r dpre1[r];  db0 += sum_r dpre0[r]
+// Replaces tape.gradient through the second Dense(relu) of dmf.py:50-51,57-58 (six launches per tower before: two
+// small GEMMs, two column-sum pairs).  Partial sums live in registers per CTA and reach the gradients by atomics.
+constexpr int kBwdRows = 8, kBwdThreads = 256, kBwdMaxW0 = 128, kBwdMaxW1 = 64;
+
+__global__ void __launch_bounds__(kBwdThreads) k_dmf_tower_bwd(DmfTowerBwd t0, DmfTowerBwd t1, int n) {
+  __shared__ float s_act[kBwdMaxW0], s_d1[kBwdMaxW1], s_d0[kBwdMaxW0];
+  const DmfTowerBwd t = blockIdx.y ? t1 : t0;
+  const int tid = threadIdx.x;
+  const int n_el = t.w0 * t.w1;                       // elements of dK1, element e = (c, j) = (e / w1, e % w1)
+  float gk[(kBwdMaxW0 * kBwdMaxW1) / kBwdThreads];    // this thread's elements e = tid + i * kBwdThreads
+#pragma unroll
+  for (int i = 0; i < (kBwdMaxW0 * kBwdMaxW1) / kBwdThreads; i++) gk[i] = 0.f;
+  float gb1 = 0.f, gb0 = 0.f;                         // column tid of db1 / db0
+  const int r0 = blockIdx.x * kBwdRows, r1 = min(n, r0 + kBwdRows);
+  for (int r = r0; r < r1; r++) {
+    if (tid < t.w0) s_act[tid] = t.act0[(int64_t)r * t.ld0 + tid];
+    if (tid < t.w1) s_d1[tid] = t.dpre1[(int64_t)r * t.ld1 + tid];
+    __syncthreads();
+    if (tid < t.ld0) {
+      float d = 0.f;
+      if (tid < t.w0 && s_act[tid] > 0.f) {
+        const float* krow = t.k1 + (int64_t)tid * t.ld1;
+        for (int j = 0; j < t.w1; j++) d = fmaf(s_d1[j], __ldg(krow + j), d);
+      }
+      t.dpre0[(int64_t)r * t.ld0 + tid] = d;
+      gb0 += d;
+    }
+    if (tid < t.w1) gb1 += s_d1[tid];
+#pragma unroll
+    for (int i = 0; i < (kBwdMaxW0 * kBwdMaxW1) / kBwdThreads; i++) {
+      const int e = tid + i * kBwdThreads;
+      if (e < n_el) gk[i] = fmaf(s_act[e / t.w1], s_d1[e % t.w1], gk[i]);
+    }
+    __syncthreads();
+  }
+  (void)s_d0;
+#pragma unroll
+  for (int i = 0; i < (kBwdMaxW0 * kBwdMaxW1) / kBwdThreads; i++) {
+    const int e = tid + i * kBwdThreads;
+    if (e < n_el && gk[i] != 0.f) atomicAdd(t.g_k1 + (int64_t)(e / t.w1) * t.ld1 + (e % t.w1), gk[i]);
+  }
+  if (tid < t.w1) atomicAdd(t.g_b1 + tid, gb1);
+  if (tid < t.w0) atomicAdd(t.g_b0 + tid, gb0);
+}
+
 }  // namespace
+
+int launch_dmf_tower_bwd(drb_ctx* ctx, const DmfTowerBwd& t0, const DmfTowerBwd& t1, int n) {
+  if (n <= 0) return DRB_OK;
+  for (const DmfTowerBwd* t : {&t0, &t1})
+    if (t->w0 > kBwdMaxW0 || t->w1 > kBwdMaxW1 || t->ld0 > kBwdThreads)
+      return drb_fail(DRB_E_INVALID, "dmf tower bwd: layer widths %d -> %d exceed the fused kernel's limits", t->w0, t->w1);
+  drb_prof_scope prof_(ctx, "k_dmf_tower_bwd");
+  k_dmf_tower_bwd<<<dim3((n + kBwdRows - 1) / kBwdRows, 2), kBwdThreads, 0, ctx->stream>>>(t0, t1, n);
+  DRB_LAUNCH_CHECK(ctx, "k_dmf_tower_bwd");
+  return DRB_OK;
+}
+
+bool dmf_tower_bwd_fits(int w0, int ld0, int w1) { return w0 <= kBwdMaxW0 && w1 <= kBwdMaxW1 && ld0 <= kBwdThreads; }
 
 int launch_dmf_head(drb_ctx* ctx, const DmfHeadArgs& a) {
   if (a.n <= 0) return DRB_OK;

@@ -22,8 +22,14 @@ struct GatherArgs {
   const int32_t* chunk_off;                                             // may be NULL; [n + 1] from launch_chunk_scan:
                                                                         // balanced form (pieces of 256 CSR entries,
                                                                         // atomics into out, then a finishing pass)
+  // optional fused dense layer on the row just produced (second Dense layer of a DMF tower), one-CTA-per-row form only:
+  // next_out[n, next_ld] = act(out . next_k[width x next_ld] + next_b); columns >= next_width are 0
+  const float* next_k; const float* next_b; int next_ld, next_width, next_act; float* next_out;
 };
+struct GatherPair { GatherArgs a[2]; };
 int launch_gather(drb_ctx* ctx, const GatherArgs& a, int n);
+// two gathers of equal row width as ONE launch (blockIdx.y selects): the two towers of a DMF step
+int launch_gather_pair(drb_ctx* ctx, const GatherArgs& a0, const GatherArgs& a1, int n);
 // chunk_off[b] = number of 256-entry pieces of the CSR rows rows[0..b), chunk_off[n] = total
 int launch_chunk_scan(drb_ctx* ctx, const int64_t* indptr, const int32_t* rows, int n, int32_t* chunk_off);
 
@@ -38,7 +44,9 @@ struct ScatterArgs {
   const int32_t* bias_rows;           // may be NULL; else the growbias row per batch row, -1 = skip (item-sharded)
   const int32_t* chunk_off;           // may be NULL; balanced form, see GatherArgs
 };
+struct ScatterPair { ScatterArgs a[2]; };
 int launch_scatter(drb_ctx* ctx, const ScatterArgs& a, int n);
+int launch_scatter_pair(drb_ctx* ctx, const ScatterArgs& a0, const ScatterArgs& a1, int n);
 
 // gtable[ids[r]] += rows[r]  (one warp per row, vector atomics) -- data-parallel exchange of the user-row gradients
 int launch_row_scatter(drb_ctx* ctx, const int32_t* ids, const float* rows, int n, int ld, float* gtable);
@@ -153,6 +161,12 @@ struct AdamArgs {
   float* reg_part;                    // [blocks] partial sums of regw * w^2 (pre-update weights)
   const float* alpha_dev;             // may be NULL; else alpha of segment s = alpha_dev[seg[s].alpha_idx] (graph replay:
                                       // the step sizes are the only scalars of a step that change from step to step)
+  // optional fused loss finalisation by the last block to finish (saves a launch on the latency-bound small shapes):
+  // fin_loss_out[0] = sum(fin_loss_part) * fin_scale + sum(reg_part[0 .. fin_n_reg)), [1] = the batch term alone.
+  // fin_n_reg == 0 means "the blocks of this launch".  fin_ticket: a zero-initialised device counter (self resetting).
+  // fin_reg_part: start of the partials to sum (NULL = reg_part).
+  const float* fin_loss_part; int fin_n_loss; float fin_scale; int fin_n_reg; const float* fin_reg_part;
+  float* fin_loss_out; unsigned int* fin_ticket;
 };
 // dst[i] = vals[i], i < n <= 8 (one tiny launch; the values travel as kernel arguments)
 int launch_set_scalars(drb_ctx* ctx, float* dst, const float* vals, int n);
@@ -171,8 +185,20 @@ struct DmfHeadArgs {
   float* da; float* de;                                   // may be NULL; d(pre-activation) of the last layers
   float* loss_part;                                       // [n] per-pair loss terms
   int n;
+  int n_global;                                           // data parallel: pairs over all ranks (0 = n), the 1/B of the loss
 };
 int launch_dmf_head(drb_ctx* ctx, const DmfHeadArgs& a);
+// dense part of the backward pass of a two-layer tower (Dense(w0, relu) -> Dense(w1, relu)), both towers in one launch:
+//   dpre0 = (dpre1 K1^T) * [act0 > 0],  dK1 += act0^T dpre1,  db1 += colsum(dpre1),  db0 += colsum(dpre0)
+// (gradient buffers pre-zeroed; partial sums per CTA, then atomics)
+struct DmfTowerBwd {
+  const float* act0; const float* dpre1; const float* k1;   // [n, ld0], [n, ld1], [w0 x ld1]
+  float* dpre0;                                              // [n, ld0]
+  float* g_k1; float* g_b1; float* g_b0;                     // gradients: [w0 x ld1], [ld1], [ld0]
+  int w0, ld0, w1, ld1;
+};
+int launch_dmf_tower_bwd(drb_ctx* ctx, const DmfTowerBwd& t0, const DmfTowerBwd& t1, int n);
+bool dmf_tower_bwd_fits(int w0, int ld0, int w1);
 
 // ------------------------------------------------------------------ score.cu
 struct CandScoreArgs {

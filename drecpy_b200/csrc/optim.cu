@@ -50,6 +50,36 @@ __global__ void __launch_bounds__(kAdamThreads) k_adam(AdamArgs a, int64_t total
     __syncthreads();
   }
   if (threadIdx.x == 0) a.reg_part[blockIdx.x] = sred[0];
+  if (!a.fin_loss_out) return;
+  // fused loss finalisation: the last block to get here sums the loss terms and the regularisation partials
+  __shared__ bool last;
+  __shared__ double sa[kAdamThreads], sb[kAdamThreads];
+  if (threadIdx.x == 0) {
+    __threadfence();
+    last = atomicInc(a.fin_ticket, gridDim.x - 1) == gridDim.x - 1;      // wraps to 0: ready for the next launch
+  }
+  __syncthreads();
+  if (!last) return;
+  __threadfence();
+  const int n_reg = a.fin_n_reg > 0 ? a.fin_n_reg : (int)gridDim.x;
+  double la = 0.0, lb = 0.0;
+  for (int i = threadIdx.x; i < a.fin_n_loss; i += kAdamThreads) la += (double)__ldcg(a.fin_loss_part + i);
+  const float* regs = a.fin_reg_part ? a.fin_reg_part : a.reg_part;
+  for (int i = threadIdx.x; i < n_reg; i += kAdamThreads) lb += (double)__ldcg(regs + i);
+  sa[threadIdx.x] = la;
+  sb[threadIdx.x] = lb;
+  __syncthreads();
+  for (int s = kAdamThreads / 2; s > 0; s >>= 1) {
+    if (threadIdx.x < s) {
+      sa[threadIdx.x] += sa[threadIdx.x + s];
+      sb[threadIdx.x] += sb[threadIdx.x + s];
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    a.fin_loss_out[0] = (float)(sa[0] * (double)a.fin_scale) + (float)sb[0];
+    a.fin_loss_out[1] = (float)(sa[0] * (double)a.fin_scale);
+  }
 }
 
 __global__ void __launch_bounds__(256) k_finalize_loss(const float* __restrict__ loss_part, int n_loss, float scale,

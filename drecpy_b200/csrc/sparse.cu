@@ -80,10 +80,14 @@ __device__ __forceinline__ void gather_accumulate(const GatherArgs& a, int64_t l
   }
 }
 
+// blockIdx.y selects one of two argument sets of equal row width: the two DMF towers run as one launch
+__device__ __forceinline__ void red_write(float4* red, int col, float y) { reinterpret_cast<float*>(red)[col] = y; }
+
 template <int LPR, int NV>
-__global__ void __launch_bounds__(kGatherThreads) k_gather(GatherArgs a) {
+__global__ void __launch_bounds__(kGatherThreads) k_gather(GatherArgs a0, GatherArgs a1) {
   constexpr int G = 32 / LPR;  // table rows streamed concurrently by one warp
   extern __shared__ float4 red[];  // [kWarps * G][ld4]
+  const GatherArgs a = blockIdx.y ? a1 : a0;
   const int b = blockIdx.x;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int sub = lane / LPR, c = lane % LPR;
@@ -118,13 +122,28 @@ __global__ void __launch_bounds__(kGatherThreads) k_gather(GatherArgs a) {
       if (a.rowbias) z += a.rowbias[(int64_t)brow * a.ld + col];
       if (a.bias) z += a.bias[col];
     }
-    a.out[(int64_t)b * a.ld + col] = (col < a.width) ? apply_act(z, a.act) : 0.f;
+    const float y = (col < a.width) ? apply_act(z, a.act) : 0.f;
+    a.out[(int64_t)b * a.ld + col] = y;
+    if (a.next_out) red_write(red, col, y);       // this thread is the only reader of column `col` of the partials
+  }
+  if (!a.next_out) return;
+  // fused second Dense layer of a DMF tower (dmf.py:48-58): next_out[b] = act(out[b] . next_k + next_b), exact fp32,
+  // fixed summation order
+  __syncthreads();
+  for (int n = threadIdx.x; n < a.next_ld; n += kGatherThreads) {
+    float z = 0.f;
+    if (n < a.next_width) {
+      for (int cc = 0; cc < a.width; cc++) z = fmaf(redf[cc], __ldg(a.next_k + (int64_t)cc * a.next_ld + n), z);
+      z = apply_act(z + a.next_b[n], a.next_act);
+    }
+    a.next_out[(int64_t)b * a.next_ld + n] = z;
   }
 }
 
 template <int LPR, int NV>
-__global__ void __launch_bounds__(kGatherThreads) k_scatter(ScatterArgs a) {
+__global__ void __launch_bounds__(kGatherThreads) k_scatter(ScatterArgs a0, ScatterArgs a1) {
   constexpr int G = 32 / LPR;
+  const ScatterArgs a = blockIdx.y ? a1 : a0;
   const int b = blockIdx.x;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int sub = lane / LPR, c = lane % LPR;
@@ -516,7 +535,26 @@ struct GatherLauncher {
   static int run(drb_ctx* ctx, const GatherArgs& a, int n, const char* name) {
     const size_t smem = (size_t)kWarps * (32 / LPR) * a.ld * sizeof(float);
     drb_prof_scope prof_(ctx, "k_gather");
-    k_gather<LPR, NV><<<n, kGatherThreads, smem, ctx->stream>>>(a);
+    k_gather<LPR, NV><<<n, kGatherThreads, smem, ctx->stream>>>(a, a);
+    DRB_LAUNCH_CHECK(ctx, name);
+    return DRB_OK;
+  }
+};
+template <int LPR, int NV>
+struct GatherPairLauncher {
+  static int run(drb_ctx* ctx, const GatherPair& p, int n, const char* name) {
+    const size_t smem = (size_t)kWarps * (32 / LPR) * p.a[0].ld * sizeof(float);
+    drb_prof_scope prof_(ctx, "k_gather");
+    k_gather<LPR, NV><<<dim3(n, 2), kGatherThreads, smem, ctx->stream>>>(p.a[0], p.a[1]);
+    DRB_LAUNCH_CHECK(ctx, name);
+    return DRB_OK;
+  }
+};
+template <int LPR, int NV>
+struct ScatterPairLauncher {
+  static int run(drb_ctx* ctx, const ScatterPair& p, int n, const char* name) {
+    drb_prof_scope prof_(ctx, "k_scatter");
+    k_scatter<LPR, NV><<<dim3(n, 2), kGatherThreads, 0, ctx->stream>>>(p.a[0], p.a[1]);
     DRB_LAUNCH_CHECK(ctx, name);
     return DRB_OK;
   }
@@ -525,7 +563,7 @@ template <int LPR, int NV>
 struct ScatterLauncher {
   static int run(drb_ctx* ctx, const ScatterArgs& a, int n, const char* name) {
     drb_prof_scope prof_(ctx, "k_scatter");
-    k_scatter<LPR, NV><<<n, kGatherThreads, 0, ctx->stream>>>(a);
+    k_scatter<LPR, NV><<<n, kGatherThreads, 0, ctx->stream>>>(a, a);
     DRB_LAUNCH_CHECK(ctx, name);
     return DRB_OK;
   }
@@ -588,6 +626,22 @@ int launch_gather(drb_ctx* ctx, const GatherArgs& a, int n) {
     return DRB_OK;
   }
   return dispatch_lpr<GatherLauncher>(ctx, a, n, a.ld, "k_gather");
+}
+
+int launch_gather_pair(drb_ctx* ctx, const GatherArgs& a0, const GatherArgs& a1, int n) {
+  if (n <= 0) return DRB_OK;
+  if (a0.ld != a1.ld || a0.ld % 4 || a0.chunk_off || a1.chunk_off)
+    return drb_fail(DRB_E_INVALID, "gather pair: both argument sets need the same row width");
+  GatherPair p{{a0, a1}};
+  return dispatch_lpr<GatherPairLauncher>(ctx, p, n, a0.ld, "k_gather");
+}
+
+int launch_scatter_pair(drb_ctx* ctx, const ScatterArgs& a0, const ScatterArgs& a1, int n) {
+  if (n <= 0) return DRB_OK;
+  if (a0.ld != a1.ld || a0.ld % 4 || a0.chunk_off || a1.chunk_off)
+    return drb_fail(DRB_E_INVALID, "scatter pair: both argument sets need the same row width");
+  ScatterPair p{{a0, a1}};
+  return dispatch_lpr<ScatterPairLauncher>(ctx, p, n, a0.ld, "k_scatter");
 }
 
 int launch_scatter(drb_ctx* ctx, const ScatterArgs& a, int n) {

@@ -13,6 +13,7 @@ import random
 import numpy as np
 
 from . import _lib
+from .parallel import DataParallel
 from .recommender import DeepRecommenderABC
 from .sampler import PointSampler
 
@@ -48,6 +49,8 @@ class DMF(DeepRecommenderABC):
             raise RuntimeError('drecpy_b200 needs a CUDA device (sm_100a); there is no CPU fallback')
         self._dev = torch.device(self.device or f'cuda:{torch.cuda.current_device()}')
         self._max_batch = int(max(batch_size, min(1024, max(self.n_users, self.n_items)), kwds.get('score_batch', 0)))
+        # data parallel over pair mini-batches: batch_size is PER RANK; replicated weights, one gradient all-reduce
+        self._dp = kwds.get('data_parallel') or DataParallel()
         self._alloc_and_init(kwds.get('init_weights', None))
         self._build_native()
         self._sampler = kwds.get('sampler') or PointSampler(self._data, neg_ratio, self.interaction_threshold, self.seed)
@@ -204,11 +207,19 @@ class DMF(DeepRecommenderABC):
                 slot = self._acquire_slot()
                 self._prepare_batch(slot, batch_size)
             self._next = None
-            args = self.step_args(reg_rate)
-            _lib.check(lib.drb_dmf_step_host(self._native, _lib.np_ptr(slot['uid_np']), _lib.np_ptr(slot['iid_np']),
-                                             _lib.np_ptr(slot['lab_np']), batch_size, C.byref(args), None))
-            if want_loss:
-                self._loss_host.copy_(self._loss_dev, non_blocking=True)
+            if self._dp.active:
+                d = self._dp_buffers(batch_size)
+                d['uid'].copy_(slot['uid'][:batch_size], non_blocking=True)
+                d['iid'].copy_(slot['iid'][:batch_size], non_blocking=True)
+                d['lab'].copy_(slot['lab'][:batch_size], non_blocking=True)
+                self._step -= 1                  # step_device advances it again
+                self.step_device(d['uid'], d['iid'], d['lab'], reg_rate, d['loss'])
+            else:
+                args = self.step_args(reg_rate)
+                _lib.check(lib.drb_dmf_step_host(self._native, _lib.np_ptr(slot['uid_np']), _lib.np_ptr(slot['iid_np']),
+                                                 _lib.np_ptr(slot['lab_np']), batch_size, C.byref(args), None))
+                if want_loss:
+                    self._loss_host.copy_(self._loss_dev, non_blocking=True)
             ev = self._torch.cuda.Event()
             ev.record(self._stream)
             slot['event'] = ev
@@ -218,15 +229,41 @@ class DMF(DeepRecommenderABC):
                 self._next = (nslot, batch_size)
             if not want_loss:
                 return None
+            if self._dp.active:
+                return self.global_loss(self._dp_dev['loss'])
             ev.synchronize()
             return float(self._loss_host[0])
 
+    def _dp_buffers(self, batch_size):
+        torch = self._torch
+        if not hasattr(self, '_dp_dev') or self._dp_dev['uid'].numel() != batch_size:
+            self._dp_dev = {'uid': torch.empty(batch_size, dtype=torch.int32, device=self._dev),
+                            'iid': torch.empty(batch_size, dtype=torch.int32, device=self._dev),
+                            'lab': torch.empty(batch_size, dtype=torch.float32, device=self._dev),
+                            'loss': torch.zeros(2, dtype=torch.float32, device=self._dev)}
+        return self._dp_dev
+
+    def global_loss(self, loss2):
+        """Reported loss of the global batch from this rank's [loss, batch term] pair (a collective when parallel)."""
+        return float(self._dp.global_loss(loss2).item()) if self._dp.active else float(loss2[0].item())
+
     def step_device(self, uids_dev, iids_dev, labels_dev, reg_rate, loss_dev):
+        """One step on device-resident pairs.  Data parallel: forward + backward on this rank's pairs with the loss mean
+        over the global batch, ONE all-reduce of the gradient arena (2.5 MB at the ml-1m shape), then the identical
+        Adam update on every rank."""
         self._step += 1
         args = self.step_args(reg_rate)
-        _lib.check(_lib.load().drb_dmf_step(self._native, _lib.t_ptr(uids_dev), _lib.t_ptr(iids_dev),
-                                            _lib.t_ptr(labels_dev), uids_dev.numel(), C.byref(args),
-                                            _lib.t_ptr(loss_dev)))
+        lib = _lib.load()
+        ptrs = (self._native, _lib.t_ptr(uids_dev), _lib.t_ptr(iids_dev), _lib.t_ptr(labels_dev), uids_dev.numel(),
+                C.byref(args), _lib.t_ptr(loss_dev))
+        dp = getattr(self, '_dp', None)
+        if dp is None or not dp.active:
+            _lib.check(lib.drb_dmf_step(*ptrs))
+            return
+        gb = uids_dev.numel() * dp.world
+        _lib.check(lib.drb_dmf_step_phases(*ptrs, 1, gb))
+        dp.all_reduce_sum(self._grads)
+        _lib.check(lib.drb_dmf_step_phases(*ptrs, 2, gb))
 
     def launch_count(self):
         return _lib.load().drb_ctx_launch_count(self._ctx)

@@ -290,6 +290,17 @@ int drb_dmf_destroy(drb_dmf* m);
  * loss_out: device float[2] ([0] reported loss, [1] its batch term). */
 int drb_dmf_step(drb_dmf* m, const int32_t* uids, const int32_t* iids, const float* labels, int32_t batch,
                  const drb_dmf_step_args* args, float* loss_out);
+/* The same step in two phases, for data parallelism over pair mini-batches (one process per GPU, replicated weights;
+ * the reference is single-process, so this layer is new):
+ *   DRB_DMF_PHASE_GRADS  forward + backward into the gradient arena (drb_dmf_grads_buffer), with the loss mean and its
+ *                        gradient over global_batch pairs (0 = batch); the caller all-reduces the arena (2.5 MB at the
+ *                        ml-1m shape) ...
+ *   DRB_DMF_PHASE_UPDATE ... then Adam + loss.  loss_out[1] is this rank's share of the batch term (sum it over ranks
+ *                        and add loss_out[0] - loss_out[1], the regularisation term, for the global reported loss). */
+enum { DRB_DMF_PHASE_GRADS = 1, DRB_DMF_PHASE_UPDATE = 2, DRB_DMF_PHASE_ALL = 3 };
+int drb_dmf_step_phases(drb_dmf* m, const int32_t* uids, const int32_t* iids, const float* labels, int32_t batch,
+                        const drb_dmf_step_args* args, float* loss_out, int32_t phases, int32_t global_batch);
+int drb_dmf_grads_buffer(drb_dmf* m, float** ptr, int64_t* count);
 int drb_dmf_step_host(drb_dmf* m, const int32_t* uids, const int32_t* iids, const float* labels, int32_t batch,
                       const drb_dmf_step_args* args, float* loss_host);
 int drb_dmf_loss_buffer(drb_dmf* m, float** ptr);

@@ -143,11 +143,15 @@ def test_c2_full_size_dmf_100_steps_vs_oracle():
         lo.append(float(o.step([x[0] for x in t], [x[1] for x in t], [o.standardize(x[2]) for x in t], 1e-4)))
     l, lo = np.array(l), np.array(lo)
     assert np.max(np.abs(l - lo) / np.abs(lo)) < 1e-3, (l[-3:], lo[-3:])
-    # weights after 100 Adam steps: a gradient element that is pure rounding noise moves its weight by up to lr per step
-    # in either direction, so agreement is stated relative to the tensor's scale (measured: 2.8e-3 on the widest layer)
+    # weights after 100 Adam steps: a gradient element that is pure rounding noise in one implementation moves its weight
+    # by up to lr = 1e-3 per step (Adam normalises the gradient), in either direction and differently from run to run
+    # (the scatter adds with atomics).  So: all but 0.1 % of the elements within 1e-3 of the tensor's scale, none
+    # further than a handful of Adam steps.
     for (k, b), (ko, bo) in zip(m.tower_weights('user_nn') + m.tower_weights('item_nn'), o.user_layers + o.item_layers):
-        assert rel_err(k.cpu().numpy(), ko) < 6e-3
-        assert rel_err(b.cpu().numpy(), bo) < 6e-3
+        for got, want in ((k.cpu().numpy(), ko), (b.cpu().numpy(), bo)):
+            d = np.abs(got.astype(np.float64) - want) / max(np.abs(want).max(), 1e-30)
+            assert np.quantile(d, 0.999) < 1e-3, np.quantile(d, 0.999)
+            assert d.max() < 0.3, d.max()
     p, po = m.forward_pairs(uu, ii), o.forward(uu, ii)[0]          # scores of the trained model
     assert np.max(np.abs(p - po) / np.abs(po)) < 1e-3
 

@@ -119,3 +119,70 @@ def test_item_sharded_step_matches_single_gpu(tmp_path):
         scale = np.abs(r['ref_' + k]).max()
         assert r[k].shape == r['ref_' + k].shape
         assert np.abs(r[k] - r['ref_' + k]).max() < 2e-4 * scale, k
+
+
+def _worker_dmf(rank, world, port, out):
+    import torch
+    import torch.distributed as dist
+    import drecpy_b200 as drb
+    from drecpy_b200.parallel import DataParallel
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group('nccl', rank=rank, world_size=world, device_id=torch.device(f'cuda:{rank}'))
+    U, I, B = 400, 600, 64
+    u, i, v = drb.synthetic_interactions(U, I, 20000, seed=5)
+    ds = drb.InteractionData(u, i, v)
+    ds.assign_internal_ids()
+    rng = np.random.default_rng(2)
+
+    def tower(in_dim, factors):
+        res = []
+        for f in factors:
+            lim = np.sqrt(6.0 / (in_dim + f))
+            res.append((rng.uniform(-lim, lim, (in_dim, f)).astype(np.float32), np.zeros(f, np.float32)))
+            in_dim = f
+        return res
+    w = {'user_nn': tower(I, [64, 32]), 'item_nn': tower(U, [64, 32])}
+    m = drb.DMF(seed=10, verbose=False, device=f'cuda:{rank}')
+    m.fit(ds, epochs=0, batch_size=B, reg_rate=1e-4, init_weights=w, data_parallel=DataParallel(dist))
+    # every rank takes its slice of the SAME global sample stream
+    gs = drb.PointSampler(ds, 5, 1e-3, 10)
+    losses = []
+    dev = torch.device(f'cuda:{rank}')
+    loss = torch.zeros(2, device=dev)
+    for s in range(6):
+        uu, ii, vv = gs.sample_arrays(B * world)
+        lab = m.labels_from_values(vv)
+        sl = slice(rank * B, (rank + 1) * B)
+        m.step_device(torch.as_tensor(uu[sl].copy(), device=dev), torch.as_tensor(ii[sl].copy(), device=dev),
+                      torch.as_tensor(lab[sl].copy(), device=dev), 1e-4, loss)
+        losses.append(m.global_loss(loss))
+    if rank == 0:
+        ref = drb.DMF(seed=10, verbose=False, device='cuda:0')
+        ref.fit(ds, epochs=0, batch_size=B * world, reg_rate=1e-4, init_weights=w)
+        gs = drb.PointSampler(ds, 5, 1e-3, 10)
+        ref_losses = []
+        rl = torch.zeros(2, device=dev)
+        for s in range(6):
+            uu, ii, vv = gs.sample_arrays(B * world)
+            ref.step_device(torch.as_tensor(uu.copy(), device=dev), torch.as_tensor(ii.copy(), device=dev),
+                            torch.as_tensor(ref.labels_from_values(vv), device=dev), 1e-4, rl)
+            ref_losses.append(float(rl[0]))
+        np.savez(out, losses=losses, ref_losses=ref_losses, p=m._params.cpu().numpy(), p_ref=ref._params.cpu().numpy())
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_dmf_two_gpu_step_matches_single_gpu(tmp_path):
+    """DMF data parallel: 2 ranks x 64 pairs == one rank x 128 pairs (same pairs, global loss mean, one all-reduce)."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip('needs 2 GPUs')
+    import torch.multiprocessing as mp
+    out = str(tmp_path / 'dmf_dp.npz')
+    mp.spawn(_worker_dmf, args=(2, _free_port(), out), nprocs=2, join=True)
+    r = np.load(out)
+    assert np.allclose(r['losses'], r['ref_losses'], rtol=1e-5), (r['losses'], r['ref_losses'])
+    scale = np.abs(r['p_ref']).max()
+    assert np.abs(r['p'] - r['p_ref']).max() < 2e-4 * scale
