@@ -37,7 +37,7 @@ class CdaeStepArgs(C.Structure):
     _fields_ = [('learning_rate', f32), ('beta1', f32), ('beta2', f32), ('epsilon', f32), ('reg_rate', f32),
                 ('t', i32 * 5), ('philox_seed', u64), ('philox_step', u64), ('global_batch', i32),
                 ('slot_offset', i32), ('skip_user_grad', i32), ('shard_items', i32), ('item_offset', i32),
-                ('n_items_global', i64), ('v_rows', vp)]
+                ('n_items_global', i64), ('v_rows', vp), ('keep_bytes', i64)]
 
 
 class DmfLayout(C.Structure):

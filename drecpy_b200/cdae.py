@@ -351,6 +351,8 @@ class CDAE(DeepRecommenderABC):
         self._step += 1
         self._cur_batch = uids_dev.numel()
         args = self.step_args(reg_rate)
+        if keep_dev is not None:
+            args.keep_bytes = keep_dev.numel()        # lets the small shapes replay the step as a CUDA graph
         lib = _lib.load()
         ptrs = (self._native, _lib.t_ptr(uids_dev), _lib.t_ptr(keep_off_dev), _lib.t_ptr(keep_dev), uids_dev.numel(),
                 C.byref(args), _lib.t_ptr(loss_dev))

@@ -195,6 +195,15 @@ struct drb_cdae {
   bool reg_slots_clear;                   // the three reg_part slots were zeroed in PREP (split UPDATE of this step)
   int n2, batch_pad;   // tcgen05 path: N of the backward GEMMs (hidden + ones feature, rounded to 16), padded batch
   float* z_dbg;        // tests only: drb_debug_cdae_capture_logits
+  // CUDA-graph replay of the whole step for the launch-bound shapes (ml-100k: ~15 launches of a few microseconds).
+  // One instantiated graph per (batch, mask mode, loss pointer, hyper-parameters); it reads the batch from the model's
+  // own uids / keep_off / keep buffers and the per-step scalars (five Adam step sizes, philox step) from device memory.
+  struct Graph {
+    const void* loss_out; int32_t batch; int has_keep; float beta1, beta2, eps, reg, lr_unused;
+    uint64_t philox_seed; cudaGraphExec_t exec; int64_t launches;
+  } graphs[8];
+  int n_graphs, graph_next, graph_off, n_captures;
+  cudaStream_t cap_stream;
 };
 
 // N of the backward GEMMs: hidden plus the constant-one feature that folds db' = colsum(dz) into dW'^T, rounded to 16.
@@ -315,6 +324,10 @@ int drb_cdae_create(drb_ctx* ctx, const drb_cdae_desc* desc, drb_cdae** out) {
   m->v_grad_clean = false;
   m->z_dbg = nullptr;
   m->rows_uids = nullptr; m->rows_n = 0; m->reg_slots_clear = false;
+  std::memset(m->graphs, 0, sizeof(m->graphs));
+  m->n_graphs = m->graph_next = m->n_captures = 0;
+  m->cap_stream = nullptr;
+  { const char* ge = getenv("DRB_GRAPH"); m->graph_off = (ge && atoi(ge) == 0) ? 1 : 0; }   // DRB_GRAPH=0: direct launches
   if (m->use_umma) {
     // dh = dz W'^T on the tensor cores has one 128 x n2 tile per 128 users: split the item range so that the grid
     // is ~2 waves of the SM count (the kernel is L2/HBM bandwidth bound, one CTA per SM)
@@ -347,7 +360,15 @@ int drb_cdae_create(drb_ctx* ctx, const drb_cdae_desc* desc, drb_cdae** out) {
   *out = m;
   return DRB_OK;
 }
-int drb_cdae_destroy(drb_cdae* m) { delete m; return DRB_OK; }
+int drb_cdae_destroy(drb_cdae* m) {
+  if (m) {
+    for (int i = 0; i < 8; i++)
+      if (m->graphs[i].exec) cudaGraphExecDestroy(m->graphs[i].exec);
+    if (m->cap_stream) cudaStreamDestroy(m->cap_stream);
+  }
+  delete m;
+  return DRB_OK;
+}
 
 static int cdae_hidden_into(drb_cdae* m, const int32_t* uids, int n, const int32_t* keep_off, const uint8_t* keep,
                             float scale, float* h, int act = DRB_ACT_SIGMOID, const int32_t* bias_rows = nullptr,
@@ -409,8 +430,13 @@ int drb_cdae_label_count_buffer(drb_cdae* m, float** ptr, int64_t* count) {
   return DRB_OK;
 }
 
-int drb_cdae_step_phases(drb_cdae* m, const int32_t* uids, const int32_t* keep_off, const uint8_t* keep,
-                         int32_t batch, const drb_cdae_step_args* a, float* loss_out, int32_t phases) {
+}  // extern "C"
+
+// scal_dev != NULL (graph capture): the five Adam step sizes are read from scal_dev[0..4] (reference variable order
+// [W, W_, V, b, b_]) and the philox step from scal_dev[5..6] (lo, hi words) -- the only per-step scalars of a step
+static int cdae_step_impl(drb_cdae* m, const int32_t* uids, const int32_t* keep_off, const uint8_t* keep,
+                          int32_t batch, const drb_cdae_step_args* a, float* loss_out, int32_t phases,
+                          const float* scal_dev) {
   if (!m || !uids || !keep_off || !a || !loss_out) return drb_fail(DRB_E_INVALID, "drb_cdae_step: NULL argument");
   if (batch <= 0 || batch > m->d.max_batch)
     return drb_fail(DRB_E_INVALID, "drb_cdae_step: batch %d outside (0, max_batch=%d]", batch, m->d.max_batch);
@@ -459,6 +485,7 @@ int drb_cdae_step_phases(drb_cdae* m, const int32_t* uids, const int32_t* keep_o
   bp.words_per_row = m->words_per_row;
   bp.keep_out = keep ? nullptr : w.keep;
   bp.seed = a->philox_seed; bp.step = a->philox_step; bp.q = m->d.corruption_level;
+  bp.step_dev = scal_dev ? reinterpret_cast<const uint32_t*>(scal_dev + 5) : nullptr;
   bp.slot_offset = a->slot_offset;
   bp.item_offset = sharded ? a->item_offset : 0;
   if ((r = launch_batch_prep(ctx, bp, batch))) return r;
@@ -617,6 +644,7 @@ int drb_cdae_step_phases(drb_cdae* m, const int32_t* uids, const int32_t* keep_o
   AdamArgs ad{};
   ad.w = P; ad.m = m->d.adam_m; ad.v = m->d.adam_v; ad.g = G;
   ad.beta1 = a->beta1; ad.beta2 = a->beta2; ad.eps = a->epsilon;
+  ad.alpha_dev = scal_dev;
   const float c = a->reg_rate / (float)gbatch;                      // cdae.py:82
   const int64_t offs[6] = {L.off_w2t, L.off_w, L.off_b, L.off_b2, L.off_v, L.total};   // arena order
   const int tmap[5] = {1, 0, 3, 4, 2};                                                  // -> [W, W_, V, b, b_]
@@ -628,6 +656,7 @@ int drb_cdae_step_phases(drb_cdae* m, const int32_t* uids, const int32_t* keep_o
       ad.seg[ns].off4 = offs[sidx] / 4;
       ad.seg[ns].n4 = (offs[sidx + 1] - offs[sidx]) / 4;
       ad.seg[ns].alpha = drb_adam_alpha(a->learning_rate, a->beta1, a->beta2, a->t[tmap[sidx]]);
+      ad.seg[ns].alpha_idx = tmap[sidx];
       ad.seg[ns].l2 = l2seg[sidx] ? c : 0.f;
       ad.seg[ns].regw = l2seg[sidx] ? 0.5f * c : 0.f;
     }
@@ -672,6 +701,89 @@ int drb_cdae_step_phases(drb_cdae* m, const int32_t* uids, const int32_t* keep_o
     fuse_finalize(3 * R);
     if ((r = run_adam(1, 3, 2, &n_reg))) return r;
   }
+  return DRB_OK;
+}
+
+extern "C" {
+
+int drb_cdae_step_phases(drb_cdae* m, const int32_t* uids, const int32_t* keep_off, const uint8_t* keep,
+                         int32_t batch, const drb_cdae_step_args* a, float* loss_out, int32_t phases) {
+  if (!m || !uids || !keep_off || !a || !loss_out) return drb_fail(DRB_E_INVALID, "drb_cdae_step: NULL argument");
+  drb_ctx* ctx = m->ctx;
+  // Graph replay: only the plain single-process step of a launch-bound shape, in steady state (dV known clean, so the
+  // captured step is the sparse-clear variant), with inputs that can be staged in the model's own buffers.
+  const bool own_inputs = uids == m->ws.uids && keep_off == m->ws.keep_off && (!keep || keep == m->ws.keep);
+  const bool small = (int64_t)batch * m->d.n_items <= ((int64_t)8 << 20);
+  const bool eligible = !m->graph_off && !ctx->profile && small && phases == DRB_PHASE_ALL && m->v_grad_clean &&
+                        a->global_batch == 0 && !a->shard_items && !a->skip_user_grad && !m->z_dbg &&
+                        batch > 0 && batch <= m->d.max_batch && m->d.adam_m && !ctx->sticky &&
+                        (own_inputs || !keep || a->keep_bytes > 0);
+  if (!eligible) return cdae_step_impl(m, uids, keep_off, keep, batch, a, loss_out, phases, nullptr);
+  CdaeWs& w = m->ws;
+  if (!own_inputs) {      // stage the caller's device arrays (outside the graph)
+    if (keep && a->keep_bytes > m->keep_cap)
+      return drb_fail(DRB_E_INVALID, "drb_cdae_step: keep_bytes %lld exceeds the staging capacity", (long long)a->keep_bytes);
+    DRB_CUDA_TRY(ctx, cudaMemcpyAsync(w.uids, uids, (size_t)batch * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+    DRB_CUDA_TRY(ctx, cudaMemcpyAsync(w.keep_off, keep_off, (size_t)(batch + 1) * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+    if (keep)
+      DRB_CUDA_TRY(ctx, cudaMemcpyAsync(w.keep, keep, (size_t)a->keep_bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+  }
+  const uint8_t* gkeep = keep ? w.keep : nullptr;
+  drb_cdae::Graph* g = nullptr;
+  for (int i = 0; i < m->n_graphs; i++) {
+    drb_cdae::Graph& c = m->graphs[i];
+    if (c.loss_out == loss_out && c.batch == batch && c.has_keep == (keep ? 1 : 0) && c.beta1 == a->beta1 &&
+        c.beta2 == a->beta2 && c.eps == a->epsilon && c.reg == a->reg_rate && c.philox_seed == a->philox_seed) { g = &c; break; }
+  }
+  float* scal = w.loss_scalar + 8;      // [8..14]: five step sizes + philox step (lo, hi)
+  if (!g) {
+    if (++m->n_captures > 32 ||
+        (!m->cap_stream && cudaStreamCreateWithFlags(&m->cap_stream, cudaStreamNonBlocking) != cudaSuccess)) {
+      cudaGetLastError();
+      m->graph_off = 1;
+      return cdae_step_impl(m, w.uids, w.keep_off, gkeep, batch, a, loss_out, phases, nullptr);
+    }
+    cudaStream_t user = ctx->stream;
+    const int64_t before = ctx->launches;
+    const bool clean_before = m->v_grad_clean;
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t exec = nullptr;
+    int r = DRB_OK;
+    cudaError_t e = cudaStreamBeginCapture(m->cap_stream, cudaStreamCaptureModeThreadLocal);
+    if (e == cudaSuccess) {
+      ctx->stream = m->cap_stream;
+      r = cdae_step_impl(m, w.uids, w.keep_off, gkeep, batch, a, loss_out, phases, scal);
+      ctx->stream = user;
+      e = cudaStreamEndCapture(m->cap_stream, &graph);
+    }
+    if (e == cudaSuccess && r == DRB_OK) e = cudaGraphInstantiate(&exec, graph, 0);
+    if (graph) cudaGraphDestroy(graph);
+    const int64_t captured = ctx->launches - before;
+    ctx->launches = before;
+    m->v_grad_clean = clean_before;      // nothing ran during capture
+    if (e != cudaSuccess || r != DRB_OK) {
+      cudaGetLastError();
+      ctx->sticky = 0;
+      m->graph_off = 1;
+      return cdae_step_impl(m, w.uids, w.keep_off, gkeep, batch, a, loss_out, phases, nullptr);
+    }
+    const int slot = m->n_graphs < 8 ? m->n_graphs++ : (m->graph_next++ & 7);
+    if (m->graphs[slot].exec) cudaGraphExecDestroy(m->graphs[slot].exec);
+    m->graphs[slot] = drb_cdae::Graph{loss_out, batch, keep ? 1 : 0, a->beta1, a->beta2, a->epsilon, a->reg_rate, 0.f,
+                                      a->philox_seed, exec, captured};
+    g = &m->graphs[slot];
+  }
+  float vals[7];
+  for (int j = 0; j < 5; j++) vals[j] = drb_adam_alpha(a->learning_rate, a->beta1, a->beta2, a->t[j]);
+  const uint32_t slo = (uint32_t)a->philox_step, shi = (uint32_t)(a->philox_step >> 32);
+  std::memcpy(&vals[5], &slo, 4);
+  std::memcpy(&vals[6], &shi, 4);
+  int r = launch_set_scalars(ctx, scal, vals, 7);
+  if (r) return r;
+  DRB_CUDA_TRY(ctx, cudaGraphLaunch(g->exec, ctx->stream));
+  ctx->launches += g->launches;
+  m->v_grad_clean = true;      // the captured step ends with the sparse re-zero of the sampled users' rows
+  m->rows_uids = nullptr; m->rows_n = 0;
   return DRB_OK;
 }
 

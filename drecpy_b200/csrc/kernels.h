@@ -59,6 +59,7 @@ struct BatchPrepArgs {
   int words_per_row;
   uint8_t* keep_out;       // may be NULL; philox keep bytes
   uint64_t seed, step; float q;
+  const uint32_t* step_dev;  // may be NULL; else the step counter is {step_dev[0], step_dev[1]} (lo, hi): graph replay
   int slot_offset;         // global slot of local row 0 (data parallel), part of the philox counter
   int item_offset;         // global id of local item 0 (item-sharded), part of the philox counter
 };

@@ -215,12 +215,13 @@ __global__ void __launch_bounds__(128) k_batch_prep(BatchPrepArgs a) {
   const int row = a.rows[b];
   const int64_t lo = a.indptr[row], hi = a.indptr[row + 1];
   const int koff = a.keep_off ? a.keep_off[b] : 0;
+  const uint64_t step = a.step_dev ? (((uint64_t)a.step_dev[1] << 32) | a.step_dev[0]) : a.step;
   for (int64_t j = lo + threadIdx.x; j < hi; j += blockDim.x) {
     const int item = a.indices[j];
     if (a.count) atomicAdd(a.count + item, 1.0f);
     if (a.label_bits) atomicOr(a.label_bits + (int64_t)b * a.words_per_row + (item >> 5), 1u << (item & 31));
     if (a.keep_out) {
-      const uint32_t x = philox_first((uint32_t)(item + a.item_offset), (uint32_t)(b + a.slot_offset), (uint32_t)a.step, (uint32_t)(a.step >> 32),
+      const uint32_t x = philox_first((uint32_t)(item + a.item_offset), (uint32_t)(b + a.slot_offset), (uint32_t)step, (uint32_t)(step >> 32),
                                       (uint32_t)a.seed, (uint32_t)(a.seed >> 32));
       const float u = (float)(x >> 8) * (1.0f / 16777216.0f);
       a.keep_out[koff + (j - lo)] = (u < a.q) ? 0 : 1;

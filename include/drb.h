@@ -163,6 +163,8 @@ typedef struct {
   int32_t item_offset;     /* global id of local item 0 (philox counter) */
   int64_t n_items_global;  /* loss normalisation 1 / (global_batch * n_items_global) */
   const int32_t* v_rows;   /* device [batch]: local row of V for users this rank owns, -1 otherwise */
+  int64_t keep_bytes;      /* optional: bytes of `keep` (= keep_off[batch]) when the caller knows it on the host; lets the
+                              launch-bound small shapes replay the step as a CUDA graph from device-resident inputs */
 } drb_cdae_step_args;
 
 enum {

@@ -272,6 +272,32 @@ def test_dmf_graph_replay_equals_direct_launches(monkeypatch):
         assert rel_err(a, b) < 1e-5
 
 
+@pytest.mark.parametrize('mask', ['mt19937', 'philox'])
+def test_cdae_graph_replay_equals_direct_launches(monkeypatch, mask):
+    """The ml-100k-sized step is launch bound: from the second step on drb_cdae_step replays an instantiated CUDA graph
+    (per-step scalars -- five Adam step sizes, philox step -- read from device memory).  DRB_GRAPH=0 launches every
+    kernel.  Same kernels, same order: the losses agree to the last bits and so do the weights."""
+    ds = _dataset(300, 500, 15000, seed=8)
+    w = _cdae_weights(300, 500, 24)
+    runs = []
+    for graph in ('1', '0'):
+        monkeypatch.setenv('DRB_GRAPH', graph)
+        m = _make_cdae(ds, 24, 48, w, rng_mode=mask)
+        n0 = m.launch_count()
+        losses = []
+        for s in range(1, 13):
+            m._step = s
+            losses.append(m._train_step(48 if s % 5 else 32, 1e-3, want_loss=True, prefetch=True))
+        runs.append((losses, m.launch_count() - n0, m._params.cpu().numpy()))
+    assert np.allclose(runs[0][0], runs[1][0], rtol=2e-6, atol=0), (runs[0][0], runs[1][0])
+    assert runs[0][1] > runs[1][1]                 # graph mode: one extra k_set_scalars per replayed step
+    assert rel_err(runs[0][2], runs[1][2]) < 1e-5
+    # and the graph path still matches the oracle over many steps
+    monkeypatch.setenv('DRB_GRAPH', '1')
+    m, o, l, lo = _run_cdae_steps(ds, 24, 48, 30, {}, {}, mask=mask)
+    assert np.max(np.abs(l - lo) / np.abs(lo)) < 1e-3
+
+
 def test_rank_order_ties_and_novelty():
     """(score desc, iid desc) == heapq.nlargest on (score, iid) tuples (cdae.py:102-103), duplicates collapsed,
     training items dropped when novelty."""
