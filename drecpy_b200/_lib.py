@@ -30,7 +30,8 @@ class CdaeDesc(C.Structure):
                 ('params', vp), ('adam_m', vp), ('adam_v', vp), ('grads', vp),
                 ('csr_indptr', vp), ('csr_indices', vp), ('seen_indptr', vp), ('seen_indices', vp),
                 ('corruption_level', f32), ('loss_kind', i32), ('label_mode', i32),
-                ('workspace', vp), ('workspace_bytes', i64), ('max_batch', i32), ('gemm_path', i32)]
+                ('workspace', vp), ('workspace_bytes', i64), ('max_batch', i32), ('gemm_path', i32),
+                ('output_mode', i32), ('neg_per_group', i32), ('neg_groups', i32)]
 
 
 class CdaeStepArgs(C.Structure):
@@ -94,6 +95,7 @@ SIGNATURES = {
     'drb_batch_offsets': (C.c_int, [vp, i32, vp, vp]),
     'drb_cdae_layout': (C.c_int, [i32, i32, i32, P(CdaeLayout)]),
     'drb_cdae_workspace_bytes': (i64, [i32, i32, i32, i32]),
+    'drb_cdae_workspace_bytes_sampled': (i64, [i32, i32, i32, i32]),
     'drb_cdae_create': (C.c_int, [vp, P(CdaeDesc), P(vp)]),
     'drb_cdae_destroy': (C.c_int, [vp]),
     'drb_cdae_step': (C.c_int, [vp, vp, vp, vp, i32, P(CdaeStepArgs), vp]),

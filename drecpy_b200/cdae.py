@@ -41,6 +41,12 @@ class CDAE(DeepRecommenderABC):
         self.adam_t = kwds.get('adam_t', 'per_variable')
         self.gemm = kwds.get('gemm', 'auto')
         assert self.gemm in _lib.DRB_GEMM
+        # output='sampled' (extension, not a reference behaviour): the training step scores each sampled user's
+        # positives plus neg_groups x neg_per_group drawn items instead of the whole catalog (oracle: CDAESampledOracle)
+        self.output = kwds.get('output', 'dense')
+        self.neg_per_group = int(kwds.get('neg_per_group', 64))
+        self.neg_groups = int(kwds.get('neg_groups', 1))
+        assert self.output in ('dense', 'sampled')
         assert self.label_mode in _lib.DRB_LABEL and self.rng_mode in ('mt19937', 'philox')
         assert self.adam_t in ('per_variable', 'per_step')
         self._native = None
@@ -130,7 +136,9 @@ class CDAE(DeepRecommenderABC):
         self._d_indices = torch.from_numpy(self._h_indices).to(dev)
         self._d_seen_indptr = torch.from_numpy(np.ascontiguousarray(seen[0])).to(dev)
         self._d_seen_indices = torch.from_numpy(np.ascontiguousarray(seen[1])).to(dev)
-        ws_bytes = lib.drb_cdae_workspace_bytes(self._nU, self._nI, self.hidden_factors, self._max_batch)
+        sampled = getattr(self, 'output', 'dense') == 'sampled'
+        ws_fn = lib.drb_cdae_workspace_bytes_sampled if sampled else lib.drb_cdae_workspace_bytes
+        ws_bytes = ws_fn(self._nU, self._nI, self.hidden_factors, self._max_batch)
         assert ws_bytes > 0
         self._workspace = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
         d = _lib.CdaeDesc()
@@ -144,6 +152,9 @@ class CDAE(DeepRecommenderABC):
         d.label_mode = _lib.DRB_LABEL[self.label_mode]
         d.workspace, d.workspace_bytes, d.max_batch = self._workspace.data_ptr(), ws_bytes, self._max_batch
         d.gemm_path = _lib.DRB_GEMM[self.gemm]
+        if sampled:
+            d.output_mode, d.neg_per_group = 1, self.neg_per_group
+            d.neg_groups = self._dp.world if getattr(self, '_sharded', False) else self.neg_groups
         self._native = _lib.vp()
         _lib.check(lib.drb_cdae_create(self._ctx, C.byref(d), C.byref(self._native)))
         ptr, cnt = _lib.vp(), _lib.i64()

@@ -218,13 +218,32 @@ static int64_t cdae_keep_cap(int32_t n_items, int32_t max_batch) {
 }
 
 static CdaeWs cdae_carve(void* base, const drb_cdae_layout_t& L, int n_items, int hidden, int max_batch,
-                         int label_mode, int splits, int sm_count, bool umma) {
+                         int label_mode, int splits, int sm_count, bool umma, bool sampled = false) {
   Carver c(base);
   CdaeWs w{};
   const int64_t B = max_batch;
   const int mt = (max_batch + 127) / 128;
   w.h = c.take<float>(B * L.ld);
-  w.dz = c.take<float>(B * L.items_pad);
+  // sampled-output models never form batch x items matrices: no dz, no per-tile column partials, a batch-sized loss buffer
+  w.dz = c.take<float>(sampled ? 64 : B * L.items_pad);
+  if (sampled) {
+    w.dh_part = c.take<float>(B * L.ld);
+    w.dz1 = c.take<float>(B * L.ld);
+    w.col_b2 = c.take<float>(64);
+    w.col_b = c.take<float>((int64_t)colpart_blocks(max_batch) * L.ld);
+    w.loss_part = c.take<float>(B);
+    w.reg_part = c.take<float>((int64_t)sm_count * 16 * 3);
+    w.label_count = c.take<float>(64);
+    w.loss_scalar = c.take<float>(64);
+    w.label_bits = c.take<uint32_t>(1);
+    w.uids = c.take<int32_t>(B);
+    w.keep_off = c.take<int32_t>(B + 1);
+    w.aux_i32 = c.take<int32_t>(3 * B + 64);
+    w.chunk_off = c.take<int32_t>(B + 64);
+    w.keep = c.take<uint8_t>(cdae_keep_cap(n_items, max_batch));
+    w.bytes = c.off;
+    return w;
+  }
   w.dh_part = c.take<float>((int64_t)splits * B * L.ld);
   w.dz1 = c.take<float>(B * L.ld);
   w.col_b2 = c.take<float>((int64_t)mt * L.items_pad);
@@ -284,6 +303,12 @@ int64_t drb_cdae_workspace_bytes(int32_t n_users, int32_t n_items, int32_t hidde
   return cdae_carve(nullptr, L, n_items, hidden, max_batch, DRB_LABEL_PER_USER, 32, 256, true).bytes;
 }
 
+int64_t drb_cdae_workspace_bytes_sampled(int32_t n_users, int32_t n_items, int32_t hidden, int32_t max_batch) {
+  drb_cdae_layout_t L;
+  if (drb_cdae_layout(n_users, n_items, hidden, &L) || max_batch <= 0) return -1;
+  return cdae_carve(nullptr, L, n_items, hidden, max_batch, DRB_LABEL_PER_USER, 1, 256, false, true).bytes;
+}
+
 int drb_cdae_create(drb_ctx* ctx, const drb_cdae_desc* desc, drb_cdae** out) {
   if (!ctx || !desc || !out) return drb_fail(DRB_E_INVALID, "drb_cdae_create: NULL argument");
   drb_cdae_layout_t L;
@@ -308,7 +333,12 @@ int drb_cdae_create(drb_ctx* ctx, const drb_cdae_desc* desc, drb_cdae** out) {
   m->words_per_row = (L.items_pad + 31) / 32;
   m->n2 = cdae_n2(desc->hidden);
   m->batch_pad = (int)drb_round_up(desc->max_batch, 8);
-  const bool umma_ok = umma_available() && m->n2 <= 256;
+  const bool sampled = desc->output_mode == DRB_OUTPUT_SAMPLED;
+  if (sampled && (desc->neg_per_group < 1 || desc->neg_groups < 1)) {
+    delete m;
+    return drb_fail(DRB_E_INVALID, "drb_cdae_create: sampled outputs need neg_per_group >= 1 and neg_groups >= 1");
+  }
+  const bool umma_ok = umma_available() && m->n2 <= 256 && !sampled;
   if ((desc->gemm_path == DRB_GEMM_TCGEN05 || desc->gemm_path == DRB_GEMM_TCGEN05_TF32) && !umma_ok) {
     delete m;
     return drb_fail(DRB_E_INVALID, "drb_cdae_create: the tcgen05 path needs hidden <= 256 and a driver with TMA support");
@@ -334,8 +364,9 @@ int drb_cdae_create(drb_ctx* ctx, const drb_cdae_desc* desc, drb_cdae** out) {
     const int mt = (desc->max_batch + 127) / 128;
     m->splits = std::max(1, std::min(32, std::min((2 * ctx->sm_count) / mt, desc->n_items / 256)));
   }
+  if (sampled) m->splits = 1;
   m->ws = cdae_carve(desc->workspace, L, desc->n_items, desc->hidden, desc->max_batch, desc->label_mode, m->splits,
-                     ctx->sm_count, m->use_umma);
+                     ctx->sm_count, m->use_umma, sampled);
   m->keep_cap = cdae_keep_cap(desc->n_items, desc->max_batch);
   if (m->ws.bytes > desc->workspace_bytes) {
     int64_t need = m->ws.bytes;
@@ -457,13 +488,15 @@ static int cdae_step_impl(drb_cdae* m, const int32_t* uids, const int32_t* keep_
   const float s = (float)(1.0 / (1.0 - (double)m->d.corruption_level));
   const bool sharded = a->shard_items != 0;       // item-sharded weights: this model holds items [item_offset, +I)
   const double items_global = sharded && a->n_items_global > 0 ? (double)a->n_items_global : (double)I;
-  const float inv_count = (float)(1.0 / ((double)gbatch * items_global));
+  const bool sampled = m->d.output_mode == DRB_OUTPUT_SAMPLED;   // positives + drawn items only (extension, sampled.cu)
+  const float inv_count = sampled ? (float)(1.0 / ((double)gbatch * m->d.neg_groups * m->d.neg_per_group))
+                                  : (float)(1.0 / ((double)gbatch * items_global));
   int r;
 
   if (phases & DRB_PHASE_PREP) {
   // 0. clear sparse-gradient regions [W | V | b | b2] (W2T's gradient is fully overwritten by the GEMM)
   // (the tcgen05 path accumulates dW'^T from two reduction halves with vector atomics, so it clears that too)
-  const int64_t clear_from = m->use_umma ? 0 : L.off_w;
+  const int64_t clear_from = (m->use_umma || sampled) ? 0 : L.off_w;
   // dV (U x K, the largest gradient) is only touched in the rows of the sampled users: on the plain single-process
   // step those rows are re-zeroed after the update (k_zero_rows) instead of clearing the whole table every step
   const bool sparse_clear_v = !sharded && m->v_grad_clean;
@@ -472,7 +505,9 @@ static int cdae_step_impl(drb_cdae* m, const int32_t* uids, const int32_t* keep_
   m->v_grad_clean = false;
   m->rows_uids = nullptr; m->rows_n = 0;
   m->reg_slots_clear = false;
-  if (per_user)
+  if (sampled) {
+    // labels are looked up per scored item; nothing to prepare but the philox mask
+  } else if (per_user)
     DRB_CUDA_TRY(ctx, cudaMemsetAsync(w.label_bits, 0, (size_t)batch * m->words_per_row * 4, ctx->stream));
   else
     DRB_CUDA_TRY(ctx, cudaMemsetAsync(w.label_count, 0, (size_t)L.items_pad * 4, ctx->stream));
@@ -480,15 +515,17 @@ static int cdae_step_impl(drb_cdae* m, const int32_t* uids, const int32_t* keep_
   // 1. labels of the batch (cdae.py:61-62) and, in counter mode, the corruption mask (cdae.py:63-64)
   BatchPrepArgs bp{};
   bp.indptr = m->d.csr_indptr; bp.indices = m->d.csr_indices; bp.rows = uids; bp.keep_off = keep_off;
-  bp.count = per_user ? nullptr : w.label_count;
-  bp.label_bits = per_user ? w.label_bits : nullptr;
+  bp.count = (per_user || sampled) ? nullptr : w.label_count;
+  bp.label_bits = (per_user && !sampled) ? w.label_bits : nullptr;
   bp.words_per_row = m->words_per_row;
   bp.keep_out = keep ? nullptr : w.keep;
   bp.seed = a->philox_seed; bp.step = a->philox_step; bp.q = m->d.corruption_level;
   bp.step_dev = scal_dev ? reinterpret_cast<const uint32_t*>(scal_dev + 5) : nullptr;
   bp.slot_offset = a->slot_offset;
   bp.item_offset = sharded ? a->item_offset : 0;
-  if ((r = launch_batch_prep(ctx, bp, batch))) return r;
+  if (!sampled || bp.keep_out) {
+    if ((r = launch_batch_prep(ctx, bp, batch))) return r;
+  }
   }  // PREP (data parallel: the caller all-reduces the label histogram here)
 
   const int n2 = m->n2, bp = m->batch_pad;
@@ -541,6 +578,27 @@ static int cdae_step_impl(drb_cdae* m, const int32_t* uids, const int32_t* keep_
   UmmaOperands o2{w.dzt_hi, w.dzt_lo, 32, w.hT_hi, w.hT_lo, bp, n2};
   o2.a_tiled_nib = drb_dz_nib(I);
   o2.a_tiled_rows = (int64_t)((m->d.max_batch + 127) / 128) * o2.a_tiled_nib * 128;
+  if ((phases & DRB_PHASE_GRADS_B) && sampled) {
+    // 3-5 in one kernel: output layer over positives + drawn items, loss terms, dW'^T / db' (atomics), dh
+    SampledOutArgs so{};
+    so.indptr = m->d.csr_indptr; so.indices = m->d.csr_indices; so.rows = uids;
+    so.h = w.h; so.ld = ld; so.w2t = P + L.off_w2t; so.b2 = P + L.off_b2;
+    so.g_w2t = G + L.off_w2t; so.g_b2 = G + L.off_b2; so.dh = w.dh_part; so.loss_part = w.loss_part;
+    so.n_items_total = sharded && a->n_items_global > 0 ? (int)a->n_items_global : I;
+    so.n_groups_total = m->d.neg_groups;
+    so.n_groups = sharded ? 1 : m->d.neg_groups;
+    so.item_offset = sharded ? a->item_offset : 0;
+    const int per_g = (so.n_items_total + so.n_groups_total - 1) / so.n_groups_total;
+    so.group_id0 = sharded ? a->item_offset / per_g : 0;
+    if (sharded && (a->item_offset % per_g != 0 || I > per_g))
+      return drb_fail(DRB_E_INVALID, "drb_cdae_step: item-sharded sampled outputs need one negative-sampling group per shard");
+    so.neg_per_group = m->d.neg_per_group;
+    so.seed = a->philox_seed; so.step = a->philox_step;
+    so.step_dev = scal_dev ? reinterpret_cast<const uint32_t*>(scal_dev + 5) : nullptr;
+    so.slot_offset = a->slot_offset; so.loss_kind = m->d.loss_kind; so.inv_count = inv_count;
+    if ((r = launch_sampled_out(ctx, so, batch))) return r;
+    m->n_loss_blocks = batch;
+  } else
   if (phases & DRB_PHASE_GRADS_B) {
   int n_blocks = 0;
   if (m->use_umma) {
@@ -596,7 +654,9 @@ static int cdae_step_impl(drb_cdae* m, const int32_t* uids, const int32_t* keep_
 
   if (phases & DRB_PHASE_GRADS_C) {
   // 5. K3: dh = dz W'^T  (B x K), split over the item range, partials reduced by the dz1 kernel
-  if (m->use_umma && m->half) {      // A = the [user tile][item block] copy of dz (K-major over items), B = W'^T
+  if (sampled) {
+    // dh already sits in plane 0 of dh_part (k_sampled_out)
+  } else if (m->use_umma && m->half) {      // A = the [user tile][item block] copy of dz (K-major over items), B = W'^T
     UmmaOperands o3{dzh.u_hi, dzh.u_lo, 64, w.wT_hi, w.wT_lo, m->ip8, n2};
     o3.a_tiled_nib = dzh.nib64; o3.a_tiled_rows = (int64_t)((m->d.max_batch + 127) / 128) * dzh.nib64 * 128;
     o3.half = true; o3.out_scale = dz_unscale; o3.out_scale_dev = inv_alpha_w; o3.name = "k_umma_gemm_dh";
@@ -843,7 +903,7 @@ int drb_cdae_rank_candidates(drb_cdae* m, const int32_t* uids, int32_t n, const 
   // lists longer than the shared-memory sorter takes (recommend(n=None): the whole catalog) sort their keys in the
   // dz workspace, as many users per launch as fit there
   void* scratch = m->ws.dz;
-  const int64_t scratch_bytes = (int64_t)m->d.max_batch * m->L.items_pad * 4;
+  const int64_t scratch_bytes = m->d.output_mode == DRB_OUTPUT_SAMPLED ? 256 : (int64_t)m->d.max_batch * m->L.items_pad * 4;
   int64_t per = m->d.max_batch;
   if (max_cand > 4096) {
     per = std::min<int64_t>(per, rank_scratch_rows(scratch_bytes, max_cand));
@@ -934,6 +994,8 @@ static int cdae_topk_impl(drb_cdae* m, const int32_t* uids, int32_t n, int32_t k
                           float* out_score, int32_t* n_out, bool exact_only) {
   if (!m || !uids || !out_iid || !out_score || !n_out || n < 0)
     return drb_fail(DRB_E_INVALID, "drb_cdae_topk: bad argument");
+  if (m->d.output_mode == DRB_OUTPUT_SAMPLED)
+    return drb_fail(DRB_E_STATE, "drb_cdae_topk: a model created for sampled-output training carries no score workspace");
   if (k < 1 || k > 2048) return drb_fail(DRB_E_INVALID, "drb_cdae_topk: k must be in [1, 2048]");
   // Tensor-core path: wide catalogs, blocks of >= 128 users.  DRB_TOPK_PATH=ffma forces the exact-fp32 GEMM + radix
   // select path, DRB_TOPK_CAP / DRB_TOPK_NS shrink the list capacity / first slice (tests of the overflow fallback).

@@ -80,6 +80,24 @@ int launch_sigmoid_rows(drb_ctx* ctx, float* x, int n, int ld, int width);
 // out[j] = sum_p part[p, ld + j]
 int launch_reduce_partials(drb_ctx* ctx, const float* part, int nparts, int ld, float* out, int n);
 
+// ------------------------------------------------------------------ sampled.cu
+// Sampled-output layer (extension for configs[4], see sampled.cu / oracle.cdae.CDAESampledOracle): forward + backward of
+// the output layer over each sampled user's positives and n_groups x neg_per_group drawn items.
+struct SampledOutArgs {
+  const int64_t* indptr; const int32_t* indices; const int32_t* rows;   // positives CSR over LOCAL item ids, column-sorted
+  const float* h; int ld;                     // [n, ld] hidden activations
+  const float* w2t; const float* b2;          // [n_items_local, ld], [n_items_local]
+  float* g_w2t; float* g_b2;                  // their gradients (pre-zeroed; vector atomics)
+  float* dh;                                  // [n, ld] written (partial over the local items when item-sharded)
+  float* loss_part;                           // [n] raw sums of the loss terms
+  int n_items_total, n_groups_total;          // the GLOBAL catalog and its partition into negative-sampling groups
+  int n_groups, group_id0, item_offset;       // groups this model holds: [group_id0, group_id0 + n_groups); global id of local item 0
+  int neg_per_group;
+  uint64_t seed, step; const uint32_t* step_dev; int slot_offset;
+  int loss_kind; float inv_count;             // 1 / (global batch * n_groups_total * neg_per_group)
+};
+int launch_sampled_out(drb_ctx* ctx, const SampledOutArgs& a, int n);
+
 // ------------------------------------------------------------------ gemm.cu
 enum { EPI_STORE = 0, EPI_BIAS_ACT = 1, EPI_MASK_POS = 2, EPI_CDAE_LOSS = 3 };
 enum { LAYOUT_KK = 0,   // A[m][k] k-contiguous, B[n][k] k-contiguous      (C = A * B^T)

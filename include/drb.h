@@ -40,6 +40,7 @@ enum {
 enum { DRB_LOSS_BCE = 0, DRB_LOSS_MSE = 1 };
 enum { DRB_LABEL_BATCH_MEAN = 0, DRB_LABEL_PER_USER = 1 };
 enum { DRB_ACT_NONE = 0, DRB_ACT_SIGMOID = 1, DRB_ACT_RELU = 2 };
+enum { DRB_OUTPUT_DENSE = 0, DRB_OUTPUT_SAMPLED = 1 };
 enum { DRB_GEMM_AUTO = 0, DRB_GEMM_FFMA = 1, DRB_GEMM_TCGEN05 = 2, DRB_GEMM_TCGEN05_TF32 = 3 };
 
 typedef struct drb_ctx drb_ctx;
@@ -128,6 +129,8 @@ typedef struct {
 int drb_cdae_layout(int32_t n_users, int32_t n_items, int32_t hidden, drb_cdae_layout_t* out);
 /* workspace bytes needed for batches up to max_batch (training) / max_score_users x max_candidates (scoring) */
 int64_t drb_cdae_workspace_bytes(int32_t n_users, int32_t n_items, int32_t hidden, int32_t max_batch);
+/* the same for a model created with output_mode = DRB_OUTPUT_SAMPLED (no batch x items buffers) */
+int64_t drb_cdae_workspace_bytes_sampled(int32_t n_users, int32_t n_items, int32_t hidden, int32_t max_batch);
 
 typedef struct {
   int32_t n_users, n_items, hidden;
@@ -147,6 +150,14 @@ typedef struct {
   int32_t max_batch;
   int32_t gemm_path;           /* DRB_GEMM_AUTO (tcgen05 when hidden <= 256), DRB_GEMM_FFMA (exact fp32 on the CUDA cores),
                                   DRB_GEMM_TCGEN05 (fp32-accurate 3xFP16 split products), DRB_GEMM_TCGEN05_TF32 (3xTF32) */
+  /* Sampled-output extension (NOT a reference behaviour: cdae.py:76 always scores the whole catalog; needed for catalogs
+   * like BASELINE.json configs[4], 1 M items, where that is 1.5 GFLOP per sampled user).  output_mode DRB_OUTPUT_SAMPLED:
+   * the training step scores each sampled user's positives plus neg_groups x neg_per_group uniformly drawn items (group
+   * g = the g-th of neg_groups contiguous item ranges; one group per rank when the weights are item-sharded), with
+   * per-user labels and the loss normalised by batch * neg_groups * neg_per_group.  Defined by
+   * oracle/cdae.py: CDAESampledOracle.  Scoring entry points are unchanged (dense). */
+  int32_t output_mode;         /* DRB_OUTPUT_DENSE (0, the reference) | DRB_OUTPUT_SAMPLED */
+  int32_t neg_per_group, neg_groups;
 } drb_cdae_desc;
 
 typedef struct {

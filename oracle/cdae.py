@@ -148,3 +148,82 @@ class CDAEOracle:
             t = 5 * (sidx - 1) + j + 1 if self.adam_t == 'per_variable' else sidx   # Q2
             adam_update(w, m, v, g.astype(F), self.lr, t, self.beta1, self.beta2, self.adam_eps)
         return total
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Sampled-output extension (NOT a reference behaviour; parity unpinned by the reference, pinned against this restatement).
+# BASELINE.json configs[4] (10 M users x 1 M items) cannot afford the reference's dense output layer (cdae.py:76 scores
+# all I items for every sampled user: 1.5 GFLOP per user at K = 256).  The sampled form scores, for sampled user b, its
+# positives N(u_b) and n_groups x neg_per_group uniformly drawn items (group g = a contiguous item range; one group per
+# item shard when the weights are sharded), with per-user labels (the CDAE paper's form) and the loss normalised by
+# B * n_groups * neg_per_group.  Everything else of the step (hidden layer, dense Adam + L2, per-variable step counter)
+# is the reference's.
+def sampled_negatives(n_items, n_groups, neg_per_group, slot, step, seed):
+    """The negative items of batch slot `slot` at optimizer step `step`: philox4x32-10 draws, counter = (draw, slot,
+    step_lo, step_hi), key = (seed_lo ^ 0x9E3779B9 * (group + 1), seed_hi); item = group_lo + x mod group_size."""
+    from .philox import philox_first
+    per = -(-n_items // n_groups)
+    out = []
+    d = np.arange(neg_per_group, dtype=np.uint32)
+    for g in range(n_groups):
+        lo, hi = min(n_items, g * per), min(n_items, (g + 1) * per)
+        k0 = (seed & 0xFFFFFFFF) ^ ((0x9E3779B9 * (g + 1)) & 0xFFFFFFFF)
+        x = philox_first(d, np.full_like(d, slot), np.full_like(d, step & 0xFFFFFFFF), np.full_like(d, step >> 32),
+                         k0, seed >> 32)
+        out.append(lo + (x.astype(np.int64) % max(hi - lo, 1)))
+    return np.concatenate(out)
+
+
+class CDAESampledOracle(CDAEOracle):
+    def __init__(self, *args, n_groups=1, neg_per_group=64, seed=10, **kw):
+        super().__init__(*args, **kw)
+        self.n_groups, self.neg_per_group, self.seed = n_groups, neg_per_group, seed
+
+    def grads_sampled(self, uids, keep, reg_rate, step):
+        uids = np.asarray(uids)
+        B, I = len(uids), self.n_items
+        s = F(1.0 / (1.0 - self.q))
+        y = self.desired(uids)
+        x = (y * keep * s).astype(F)
+        h = sigmoid(x @ self.W + self.V[uids] + self.b)
+        inv = F(1.0 / (B * self.n_groups * self.neg_per_group))
+        gW_ = np.zeros_like(self.W_)
+        gb_ = np.zeros_like(self.b_)
+        dh = np.zeros_like(h)
+        loss = 0.0
+        for b, u in enumerate(uids):
+            pos = self.positives(u)
+            neg = sampled_negatives(I, self.n_groups, self.neg_per_group, b, step, self.seed)
+            items = np.concatenate([pos, neg]).astype(np.int64)
+            t = np.concatenate([np.ones(len(pos), F), y[b, neg]])            # a drawn positive is labelled positive
+            z = (h[b] @ self.W_[:, items] + self.b_[items]).astype(F)
+            p = sigmoid(z)
+            if self.loss == 'bce':
+                pc = np.clip(p, KERAS_EPS, F(1) - KERAS_EPS)
+                elem = -(t * np.log(pc + KERAS_EPS) + (F(1) - t) * np.log(F(1) - pc + KERAS_EPS))
+                inside = (p >= KERAS_EPS) & (p <= F(1) - KERAS_EPS)
+                dp = -(t / (pc + KERAS_EPS) - (F(1) - t) / (F(1) - pc + KERAS_EPS)) * inside * inv
+            else:
+                elem = (p - t) ** 2
+                dp = F(2) * (p - t) * inv
+            loss += float(elem.sum(dtype=np.float64))
+            dz = (dp * p * (F(1) - p)).astype(F)
+            np.add.at(gW_.T, items, dz[:, None] * h[b][None, :])
+            np.add.at(gb_, items, dz)
+            dh[b] = dz @ self.W_[:, items].T
+        c = F(reg_rate / B)
+        reg = c * F(0.5) * sum(F((w.astype(np.float64) ** 2).sum()) for w in (self.W, self.W_, self.V))
+        dz1 = dh * h * (F(1) - h)
+        gV = c * self.V
+        np.add.at(gV, uids, dz1)
+        gW = x.T @ dz1 + c * self.W
+        return F(loss * float(inv) + reg), [gW, gW_ + c * self.W_, gV, dz1.sum(axis=0, dtype=F), gb_]
+
+    def step_sampled(self, uids, keep, reg_rate, step):
+        total, grads = self.grads_sampled(uids, keep, reg_rate, step)
+        self.step_count += 1
+        sidx = self.step_count
+        for j, (w, m, v, g) in enumerate(zip(self.vars, self.m, self.v, grads)):
+            t = 5 * (sidx - 1) + j + 1 if self.adam_t == 'per_variable' else sidx
+            adam_update(w, m, v, g.astype(F), self.lr, t, self.beta1, self.beta2, self.adam_eps)
+        return total

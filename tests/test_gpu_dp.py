@@ -186,3 +186,54 @@ def test_dmf_two_gpu_step_matches_single_gpu(tmp_path):
     assert np.allclose(r['losses'], r['ref_losses'], rtol=1e-5), (r['losses'], r['ref_losses'])
     scale = np.abs(r['p_ref']).max()
     assert np.abs(r['p'] - r['p_ref']).max() < 2e-4 * scale
+
+
+def _worker_items_sampled(rank, world, port, out):
+    import torch
+    import torch.distributed as dist
+    import drecpy_b200 as drb
+    from drecpy_b200.parallel import DataParallel
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group('nccl', rank=rank, world_size=world, device_id=torch.device(f'cuda:{rank}'))
+    U, I, K, B = 501, 904, 64, 96
+    u, i, v = drb.synthetic_interactions(U, I, 30000, seed=4)
+    ds = drb.InteractionData(u, i, v)
+    w = _weights(U, I, K)
+    kw = dict(hidden_factors=K, seed=10, verbose=False, rng_mode='philox', output='sampled', neg_per_group=24)
+    m = drb.CDAE(device=f'cuda:{rank}', **kw)
+    m.fit(ds, epochs=0, batch_size=B, init_weights=w, data_parallel=DataParallel(dist), parallel_mode='items')
+    losses = []
+    for s in range(1, 7):
+        m._step = s
+        losses.append(m._train_step(B, 1e-3, want_loss=True))
+    full = m.gather_full_weights()
+    if rank == 0:
+        ref = drb.CDAE(device='cuda:0', neg_groups=world, **kw)       # one negative-sampling group per shard
+        ref.fit(ds, epochs=0, batch_size=B * world, init_weights=w)
+        ref_losses = []
+        for s in range(1, 7):
+            ref._step = s
+            ref_losses.append(ref._train_step(B * world, 1e-3, want_loss=True))
+        np.savez(out, losses=losses, ref_losses=ref_losses,
+                 **{k: t.cpu().numpy() for k, t in full.items()},
+                 **{'ref_' + k: getattr(ref, k).cpu().numpy() for k in ('W', 'W_', 'V', 'b', 'b_')})
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_item_sharded_sampled_output_step_matches_single_gpu(tmp_path):
+    """configs[4]'s mode at toy size: item-sharded weights + sampled outputs on 2 GPUs == one GPU with two
+    negative-sampling groups (same draws, same positives), only batch x hidden activations travel."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip('needs 2 GPUs')
+    import torch.multiprocessing as mp
+    out = str(tmp_path / 'items_sampled.npz')
+    mp.spawn(_worker_items_sampled, args=(2, _free_port(), out), nprocs=2, join=True)
+    r = np.load(out)
+    assert np.allclose(r['losses'], r['ref_losses'], rtol=1e-5), (r['losses'], r['ref_losses'])
+    for k in ('W', 'W_', 'V', 'b', 'b_'):
+        scale = np.abs(r['ref_' + k]).max()
+        assert np.abs(r[k] - r['ref_' + k]).max() < 2e-4 * scale, k

@@ -298,6 +298,41 @@ def test_cdae_graph_replay_equals_direct_launches(monkeypatch, mask):
     assert np.max(np.abs(l - lo) / np.abs(lo)) < 1e-3
 
 
+@pytest.mark.parametrize('loss,K', [('bce', 36), ('mse', 200)])
+def test_cdae_sampled_output_steps_vs_oracle(loss, K):
+    """The sampled-output extension (BASELINE configs[4]'s mode): positives + 2 groups x 20 drawn items per sampled
+    user instead of the whole catalog, against oracle.cdae.CDAESampledOracle (same philox draws): every loss within
+    1e-4, weights within 5e-4 of their scale."""
+    from oracle.cdae import CDAESampledOracle
+    ds = _dataset(211, 389, 9000, seed=4)
+    U, I, B = 211, 389, 48
+    w = _cdae_weights(U, I, K)
+    m = _make_cdae(ds, K, B, w, rng_mode='philox', output='sampled', neg_per_group=20, neg_groups=2, loss=loss)
+    o = CDAESampledOracle(w['W'], w['W_'], w['V'], w['b'], w['b_'], ds.csr(), interaction_threshold=1e-3,
+                          learning_rate=1e-3, loss=loss, n_groups=2, neg_per_group=20, seed=10)
+    so = PointSamplerOracle(ds.uid, ds.iid, ds.interaction, 5, 1e-3, 10)
+    pos = ds.csr(1e-3)
+    l, lo = [], []
+    for s in range(1, 16):
+        m._step = s
+        l.append(m._train_step(B, 1e-3, want_loss=True))
+        uids = np.array([t[0] for t in so.sample(B)])
+        keep = np.ones((B, I), bool)
+        for b, u in enumerate(uids):
+            items = pos[1][pos[0][u]:pos[0][u + 1]]
+            keep[b, items] = ophilox.keep_mask(items, b, s, 10, o.q)
+        lo.append(float(o.step_sampled(uids, keep, 1e-3, s)))
+    l, lo = np.array(l), np.array(lo)
+    assert np.max(np.abs(l - lo) / np.abs(lo)) < 1e-4, (l, lo)
+    for name in ('W', 'V', 'b', 'b_'):
+        assert rel_err(getattr(m, name).cpu().numpy(), getattr(o, name)) < 5e-4, name
+    assert rel_err(m.W_.cpu().numpy(), o.W_) < 5e-4
+    # scoring of a sampled-output model still works (dense predict, candidate ranking)
+    p = m._predict(7)
+    assert p.shape == (I,) and np.all((p > 0) & (p < 1))
+    assert len(m._rank(7, list(range(0, I, 5)), 20, True)) == 20
+
+
 def test_rank_order_ties_and_novelty():
     """(score desc, iid desc) == heapq.nlargest on (score, iid) tuples (cdae.py:102-103), duplicates collapsed,
     training items dropped when novelty."""

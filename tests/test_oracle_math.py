@@ -127,3 +127,44 @@ def test_adam_matches_torch_adam_with_keras_epsilon_placement():
         v64 = 0.999 * v64 + 0.001 * g.astype(np.float64) ** 2
         w64 -= 1e-3 * np.sqrt(1 - 0.999 ** t) / (1 - 0.9 ** t) * m64 / (np.sqrt(v64) + 1e-7)
     assert np.allclose(w, w64, rtol=1e-5, atol=1e-7)
+
+
+@pytest.mark.parametrize('loss', ['bce', 'mse'])
+def test_cdae_sampled_output_grads_vs_autograd(loss):
+    """The sampled-output extension (configs[4]): positives + n_groups x neg_per_group drawn items per sampled user,
+    per-user labels, loss / (B * n_neg).  Hand-derived gradients of oracle.cdae.CDAESampledOracle vs autograd (fp64)."""
+    from oracle.cdae import CDAESampledOracle, sampled_negatives
+    U, I, K, B, q, reg, G, npg, step, seed = 17, 23, 6, 5, 0.2, 1e-2, 2, 4, 3, 10
+    uid, iid, val = _toy(U, I)
+    csr = ods.build_csr(uid, iid, val, U, I)
+    rng = np.random.default_rng(1)
+    W, W_, V = rng.normal(0, .3, (I, K)), rng.normal(0, .3, (K, I)), rng.normal(0, .3, (U, K))
+    b, b_ = rng.normal(0, .3, K), rng.normal(0, .3, I)
+    orc = CDAESampledOracle(W, W_, V, b, b_, csr, corruption_level=q, loss=loss, n_groups=G, neg_per_group=npg, seed=seed)
+    uids = np.array([3, 9, 3, 0, 16])
+    keep = rng.random((B, I)) >= q
+    total, grads = orc.grads_sampled(uids, keep, reg, step)
+
+    tW, tW_, tV, tb, tb_ = [torch.tensor(np.array(x, np.float32).astype(np.float64), requires_grad=True)
+                            for x in (W, W_, V, b, b_)]
+    y = torch.tensor(orc.desired(uids).astype(np.float64))
+    x = y * torch.tensor(keep.astype(np.float64)) / (1 - q)
+    L = 0
+    for r in range(B):
+        h = torch.sigmoid(x[r:r + 1] @ tW + tV[uids[r]] + tb)
+        neg = sampled_negatives(I, G, npg, r, step, seed)
+        assert len(neg) == G * npg and (neg[:npg] < 12).all() and (neg[npg:] >= 12).all()   # group ranges [0,12), [12,23)
+        items = np.concatenate([orc.positives(uids[r]), neg])
+        p = torch.sigmoid(h @ tW_[:, items] + tb_[items])[0]
+        t = y[r, items]
+        if loss == 'bce':
+            pc = torch.clamp(p, EPS, 1 - EPS)
+            L = L - (t * torch.log(pc + EPS) + (1 - t) * torch.log(1 - pc + EPS)).sum()
+        else:
+            L = L + ((p - t) ** 2).sum()
+    L = L / (B * G * npg) + sum(0.5 * (t_ ** 2).sum() for t_ in (tW, tW_, tV)) * reg / B
+    L.backward()
+    assert abs(float(total) - float(L.detach())) < 1e-5 * abs(float(L.detach()))
+    for g, t_ in zip(grads, (tW, tW_, tV, tb, tb_)):
+        ref = t_.grad.numpy()
+        assert np.allclose(g, ref, rtol=2e-4, atol=1e-7), np.abs(g - ref).max()
