@@ -40,7 +40,10 @@ C2 = dict(name='c2', title='dmf_ml1m_shape', origin='BASELINE.json configs[1]', 
 C4S = dict(C3, name='c4_sampled', title='ranking_evaluation_leave1out_100neg', origin='BASELINE.json configs[3]',
            model='rank_sampled', n_neg=100, k=10)
 C4F = dict(C3, name='c4_full', title='full_catalog_top100', origin='BASELINE.json configs[3]', model='topk', k=100)
-WORKLOADS = {c['name']: c for c in (C3, C1, SMALL, C2, C4S, C4F)}
+C5 = dict(name='c5', title='cdae_10m_x_1m_item_sharded', origin='BASELINE.json configs[4]', model='cdae_sharded',
+          n_users=10_000_000, n_items=1_000_000, nnz=1_000_000_000, hidden=256, batch=4096, q=0.2, lr=1e-3, reg=1e-3,
+          seed=10, zipf_a=1.0, neg_total=1024)
+WORKLOADS = {c['name']: c for c in (C3, C1, SMALL, C2, C4S, C4F, C5)}
 
 
 def load_peaks():
@@ -863,7 +866,144 @@ def run_rank_reference(args, cfg):
             'e2e': {'value': nu / dt, 'unit': 'users/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
 
 
-RUNNERS = {'cdae': (run_cdae_native, run_cdae_reference), 'dmf': (run_dmf_native, run_dmf_reference),
+# ========================================================================================== configs[4]: item-sharded CDAE
+def run_c5_native(args, cfg, D, arrays=None):
+    """CDAE K=256 on 10 M users x 1 M items / 1 B interactions, W / W' / b' sharded by item range and V by user range over
+    the ranks, sampled outputs (positives + neg_total drawn items per sampled user; the dense output layer of cdae.py:76
+    would cost 6.3 PFLOP per 4096-user step here).  Every rank generates only its own columns, on its GPU.  Per step the
+    ranks exchange two all-reduces of batch x hidden activations (partial pre-activation, partial dh): rows of the tables
+    never travel.  --c5-scale shrinks users / items / interactions by that factor for a quick run."""
+    import torch
+    import drecpy_b200 as drb
+    from drecpy_b200 import _lib
+    from drecpy_b200.parallel import DataParallel
+    sc = args.c5_scale
+    U, I, nnz = int(cfg['n_users'] * sc), int(cfg['n_items'] * sc), int(cfg['nnz'] * sc)
+    world, rank, dev = D.world, D.rank, D.dev
+    assert world > 1, 'configs[4] is the item-sharded multi-GPU mode: launch with torch.distributed.run (N >= 2)'
+    B, K, W = cfg['batch'], args.steps, args.warmup
+    Bg = B * world
+    neg_per_group = max(1, cfg['neg_total'] // world)
+    torch.cuda.reset_peak_memory_stats(dev)
+    t0 = time.time()
+    indptr, indices = drb.synthetic_item_shard(U, I, nnz, rank, world, seed=cfg['seed'], zipf_a=cfg['zipf_a'], device=str(dev))
+    t_data = time.time() - t0
+    nnz_local = int(indices.shape[0])
+    m = drb.CDAE(hidden_factors=cfg['hidden'], corruption_level=cfg['q'], loss='bce', seed=cfg['seed'], verbose=False,
+                 rng_mode='philox', device=str(dev), output='sampled', neg_per_group=neg_per_group)
+    m.fit_item_shard((indptr, indices), U, I, B, DataParallel(D.dist), learning_rate=cfg['lr'], reg_rate=cfg['reg'])
+    lib = _lib.load()
+    batches = []
+    nb = min(K + W, 16)
+    for _ in range(nb):
+        u = m._sampler.sample_arrays(Bg)[0].copy()
+        off = np.zeros(Bg + 1, np.int32)
+        _lib.check(lib.drb_batch_offsets(_lib.np_ptr(u), Bg, _lib.np_ptr(m._h_indptr), _lib.np_ptr(off)))
+        batches.append((torch.from_numpy(u).to(dev), torch.from_numpy(off).to(dev)))
+    loss_dev = torch.zeros(2, device=dev)
+
+    def step(s):
+        bt = batches[s % nb]
+        m.step_device(bt[0], bt[1], None, cfg['reg'], loss_dev)
+    l0 = [0]
+
+    def step_counted(s):
+        if s == W:
+            l0[0] = m.launch_count()
+        step(s)
+    ms_total, clock_info = timed_steps(D, step_counted, W, K)
+    launches = m.launch_count() - l0[0]
+    loss_value = m.global_loss(loss_dev)
+    # e2e: host sampler -> pinned staging -> H2D -> step -> D2H loss, exactly fit()'s per-step body
+    for _ in range(2):
+        m._step += 1
+        m._train_step(B, cfg['reg'], want_loss=True, prefetch=True)
+    D.barrier()
+    t0 = time.perf_counter()
+    for _ in range(K):
+        m._step += 1
+        loss_e2e = m._train_step(B, cfg['reg'], want_loss=True, prefetch=True)
+    torch.cuda.synchronize()
+    t_e2e = D.max_over_ranks(time.perf_counter() - t0)
+    kernels = profile_kernels(m._ctx, step, 3)
+    mem_gb = D.max_over_ranks(torch.cuda.max_memory_allocated(dev) / 2 ** 30)
+    nnz_total = int(D.sum_over_ranks(nnz_local))
+    if rank != 0:
+        return None
+    peaks = load_peaks()
+    ld = int(m._L.ld)
+    deg_loc = float(np.mean([float(b[1][-1].item()) for b in batches[:4]])) / Bg       # local positives per sampled user
+    n_params = int(m._L.total)
+    adam_ms, so_ms = kernels.get('k_adam', 0.0), kernels.get('k_sampled_out', 0.0)
+    alg_so = 8.0 * ld * (deg_loc + neg_per_group) * Bg
+    if adam_ms >= so_ms:
+        roofline = hbm_roofline('k_adam (dense Adam + L2 over this rank\'s shard: V rows dominate)', 28.0 * n_params, adam_ms, peaks,
+                                note='reference semantics: every row of V, W, W\' is updated every step (recommender_abc.py:328-334)')
+    else:
+        roofline = hbm_roofline('k_sampled_out', alg_so, so_ms, peaks)
+    roofline['secondary'] = {'k_sampled_out': {'bound': 'hbm', 'achieved': alg_so / (so_ms * 1e-3) / 1e9 if so_ms else None,
+                                               'peak': peaks['hbm'], 'unit': 'GB/s', 'algorithmic_bytes': alg_so,
+                                               'note': '8*K bytes per scored (user, item): W\' row in, gradient row out (atomics)'},
+                             'k_adam': {'bound': 'hbm', 'achieved': 28.0 * n_params / (adam_ms * 1e-3) / 1e9 if adam_ms else None,
+                                        'peak': peaks['hbm'], 'unit': 'GB/s'}}
+    roofline['share_of_step'] = max(adam_ms, so_ms) / max(sum(kernels.values()), 1e-9)
+    config = {'workload': f"{cfg['title']}: CDAE hidden_factors={cfg['hidden']} bce q={cfg['q']}, sampled outputs (positives + "
+                          f"{neg_per_group * world} drawn items per sampled user; extension, see DESIGN.md), synthetic {U}x{I} / "
+                          f"{nnz_total} interactions ({cfg['origin']}{'' if sc == 1.0 else f', scaled by {sc}'})",
+              'batch_per_gpu': B, 'global_batch': Bg, 'parallelism': f'item-sharded x{world} (W, W\', b\' by item range, V by user range)',
+              'mask_rng': 'philox (device)', 'adam': 'dense, per-variable step counter',
+              'bytes_exchanged_per_step_per_rank': 2 * Bg * ld * 4,
+              'exchange': 'two all-reduces of global_batch x hidden fp32 activations (partial pre-activation, partial dh); rows of W / W\' / V never travel',
+              'memory_per_rank_gb': round(mem_gb, 2), 'interactions_per_rank': nnz_local,
+              'l2': 'per-step working set (this rank\'s tables + Adam state: tens of GB) far exceeds the 126 MB L2'}
+    line = base_line(cfg, 'cdae_training_samples_per_sec', 'samples/s', Bg * K / (ms_total * 1e-3), world, K, W, ms_total,
+                     config, clock_info, launches)
+    line.update({'e2e': {'value': Bg * K / t_e2e, 'unit': 'samples/s', 'h2d_bytes_per_step': 8 * Bg + 4, 'd2h_bytes_per_step': 4,
+                         'ms_per_step': 1e3 * t_e2e / K},
+                 'roofline': roofline, 'cpu_baseline': None, 'kernels_ms_per_step': kernels, 'loss_last': loss_value,
+                 'loss_last_e2e': loss_e2e, 'data_gen_s': round(t_data, 1)})
+    return line
+
+
+def run_c5_reference(args, cfg):
+    """CPU arm of configs[4]: the sampled-output oracle on a shape scaled down until its dense intermediates fit (the
+    oracle, like the reference, densifies the sampled users' rows: 4096 x 1 M floats at full size)."""
+    import random
+    import drecpy_b200 as drb
+    from oracle.cdae import CDAESampledOracle
+    sc = 0.02
+    U, I, nnz, K, B = int(cfg['n_users'] * sc), int(cfg['n_items'] * sc), int(cfg['nnz'] * sc), cfg['hidden'], 512
+    u, i, v = drb.synthetic_interactions(U, I, nnz, seed=cfg['seed'], zipf_a=cfg['zipf_a'])
+    ds = drb.InteractionData(u, i, v)
+    ds.assign_internal_ids()
+    rng = np.random.default_rng(1)
+    U, I = ds.count_unique('uid'), ds.count_unique('iid')
+
+    def glorot(shape, fi, fo):
+        lim = np.sqrt(6.0 / (fi + fo))
+        return rng.uniform(-lim, lim, shape).astype(np.float32)
+    o = CDAESampledOracle(glorot((I, K), I, K), glorot((K, I), K, I), glorot((U, K), U, K), glorot((K,), K, K),
+                          glorot((I,), I, I), ds.csr(), interaction_threshold=1e-3, corruption_level=cfg['q'],
+                          learning_rate=cfg['lr'], n_groups=8, neg_per_group=cfg['neg_total'] // 8, seed=cfg['seed'])
+    brng = np.random.default_rng(0)
+    t0, n = time.time(), 0
+    while time.time() - t0 < 25.0 and n < max(1, args.steps):
+        uids = brng.integers(0, U, B)
+        keep = brng.random((B, I)) >= cfg['q']
+        loss = float(o.step_sampled(uids, keep, cfg['reg'], n + 1))
+        n += 1
+    dt = time.time() - t0
+    config = {'workload': f"{cfg['title']} scaled by {sc} ({U}x{I} / {len(u)} interactions), batch {B}: CPU arm of {cfg['origin']}",
+              'parallelism': 'cpu, one process', 'global_batch': B}
+    return {'impl': 'reference', 'metric': 'cdae_training_samples_per_sec', 'value': B * n / dt, 'unit': 'samples/s',
+            'n_gpus': args.gpus, 'steps': n, 'warmup': 0, 'ms_per_step': 1e3 * dt / n, 'higher_is_better': True,
+            'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic', 'config': config,
+            'cpu_baseline': {'value': B * n / dt, 'unit': 'samples/s', 'cores': os.cpu_count(), 'kind': 'port',
+                             'sample': f'{n} sampled-output oracle steps of {B} users on the scaled-down shape, {dt:.1f} s, rank 0 only'},
+            'e2e': {'value': B * n / dt, 'unit': 'samples/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}, 'loss_last': loss}
+
+
+RUNNERS = {'cdae_sharded': (run_c5_native, run_c5_reference), 'cdae': (run_cdae_native, run_cdae_reference), 'dmf': (run_dmf_native, run_dmf_reference),
            'rank_sampled': (run_rank_sampled_native, run_rank_reference), 'topk': (run_topk_native, run_rank_reference)}
 
 
@@ -880,6 +1020,7 @@ def main():
     ap.add_argument('--no-dp-parity', action='store_true')
     ap.add_argument('--scaling', default='weak', choices=['weak', 'strong'],
                     help='c3, N>1: weak = 4096 users per GPU (default, the driver\'s curve); strong = 4096 users globally')
+    ap.add_argument('--c5-scale', type=float, default=1.0, help='c5: shrink users / items / interactions by this factor')
     ap.add_argument('--parallel', default='data', choices=['data', 'items'],
                     help='N>1: data = replicated weights + gradient all-reduce; items = item-sharded weights')
     args = ap.parse_args()

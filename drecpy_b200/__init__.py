@@ -3,7 +3,7 @@
 Host code is Python and keeps DRecPy's public surface; all arithmetic runs in hand-written sm_100a CUDA behind
 the C-ABI library libdrb.so (include/drb.h), bound with ctypes.  PyTorch only owns device buffers.
 """
-from .dataset import InteractionData, synthetic_interactions
+from .dataset import InteractionData, synthetic_interactions, synthetic_item_shard
 from .sampler import PointSampler
 from .recommender import DeepRecommenderABC
 from .cdae import CDAE
@@ -15,6 +15,6 @@ from .loss_tracker import LossTracker
 
 InteractionDataset = InteractionData
 
-__all__ = ['InteractionData', 'InteractionDataset', 'synthetic_interactions', 'PointSampler', 'DeepRecommenderABC', 'leave_k_out',
+__all__ = ['InteractionData', 'InteractionDataset', 'synthetic_interactions', 'synthetic_item_shard', 'PointSampler', 'DeepRecommenderABC', 'leave_k_out',
            'CDAE', 'DMF', 'ranking_evaluation', 'HitRatio', 'NDCG', 'DCG', 'Precision', 'Recall',
            'MaxValidationValueRule', 'LossTracker']

@@ -28,6 +28,22 @@ from .sampler import PointSampler
 _RING = 4
 
 
+class UniformUserSampler:
+    """Seeded uniform user ids with PointSampler's array interface (sample_arrays).  For the sharded 10 M-user shape,
+    where the reference sampler's membership structures do not exist on any single rank; CDAE uses only the uid of a
+    sampled pair (cdae.py:52), and the reference's stream draws its users uniformly too."""
+
+    def __init__(self, n_users, seed):
+        self.n_users, self.rng = n_users, np.random.default_rng(abs(int(seed)))
+
+    def sample_arrays(self, n, out=None):
+        u = self.rng.integers(0, self.n_users, n, dtype=np.int32)
+        if out is None:
+            return u, np.zeros(n, np.int32), np.zeros(n, np.float64)
+        out[0][:n] = u
+        return out
+
+
 class CDAE(DeepRecommenderABC):
     def __init__(self, hidden_factors=50, corruption_level=0.2, loss='bce', **kwds):
         super(CDAE, self).__init__(**kwds)
@@ -87,6 +103,28 @@ class CDAE(DeepRecommenderABC):
         self._mask_rng = _lib.HostRng(self._mask_seed)      # replays self._rng of recommender_abc.py:74
         self._setup_staging(batch_size)
 
+    def fit_item_shard(self, shard_csr, n_users, n_items, batch_size, data_parallel, learning_rate=0.001,
+                       reg_rate=0.001, sampler=None, **kwds):
+        """Item-sharded training set-up for catalogs that never exist in one piece (BASELINE.json configs[4]: 10 M users
+        x 1 M items, 1 B interactions): every rank passes only ITS columns of the interaction matrix,
+        shard_csr = (indptr int64 [n_users + 1], indices int32 re-based to the shard, column-sorted), for the contiguous
+        item range rank * ceil(n_items / world) ...  Weights are drawn per shard on the device; `sampler` must yield the
+        same user ids on every rank (default: a seeded uniform user sampler).  No epochs are run: drive _train_step /
+        step_device.  The reference has no counterpart (it is single-process and dense)."""
+        import torch
+        self._torch = torch
+        self.n_users, self.n_items, self.n_rows = int(n_users), int(n_items), int(shard_csr[1].shape[0])
+        self.min_interaction, self.max_interaction = 0, 5
+        self.optimizer = {'learning_rate': learning_rate, 'beta_1': 0.9, 'beta_2': 0.999, 'epsilon': 1e-7}
+        self._step = 0
+        self.epoch_weights = {}
+        idx = shard_csr[1]                                   # numpy, or a torch tensor already on this rank's GPU
+        self._shard_csr = (np.ascontiguousarray(shard_csr[0], np.int64),
+                           idx if torch.is_tensor(idx) else np.ascontiguousarray(idx, np.int32))
+        self._pre_fit(learning_rate, 5, reg_rate, batch_size=batch_size, data_parallel=data_parallel,
+                      parallel_mode='items', sampler=sampler or UniformUserSampler(self.n_users, self.seed or 0), **kwds)
+        self.fitted = True
+
     def _alloc_and_init(self, init_weights):
         torch = self._torch
         lib = _lib.load()
@@ -104,6 +142,16 @@ class CDAE(DeepRecommenderABC):
         def glorot(shape, fan_in, fan_out):       # tf.initializers.GlorotUniform (cdae.py:35-41)
             lim = float(np.sqrt(6.0 / (fan_in + fan_out)))
             return (torch.rand(shape, generator=gen, dtype=torch.float32) * 2 - 1) * lim
+        if getattr(self, '_shard_csr', None) is not None:
+            # catalogs that only exist sharded (10 M x 1 M): draw this rank's rows only, on the device (same Glorot limits)
+            dgen = torch.Generator(device=dev).manual_seed(abs(int(self.seed or 0)) * 1000 + self._dp.rank)
+
+            def dglorot(view, fan_in, fan_out):
+                lim = float(np.sqrt(6.0 / (fan_in + fan_out)))
+                view.copy_((torch.rand(view.shape, generator=dgen, dtype=torch.float32, device=dev) * 2 - 1) * lim)
+            dglorot(self.W, I, K); dglorot(self.W_, K, I); dglorot(self.V, U, K); dglorot(self.b_, I, I)
+            self.b.copy_(glorot((K,), K, K))               # replicated: the same on every rank
+            return
         init = {'W': glorot((I, K), I, K), 'W_': glorot((K, I), K, I), 'V': glorot((U, K), U, K),
                 'b': glorot((K,), K, K), 'b_': glorot((I,), I, I)}
         for k, v in (init_weights or {}).items():
@@ -126,16 +174,26 @@ class CDAE(DeepRecommenderABC):
         _lib.check(lib.drb_ctx_create(dev.index or 0, C.byref(self._ctx)))
         self._stream = torch.cuda.current_stream(dev)
         _lib.check(lib.drb_ctx_set_stream(self._ctx, _lib.vp(self._stream.cuda_stream)))
-        pos = self._data.csr(self.interaction_threshold)     # positives: cdae.py:61
-        seen = self._data.csr()                              # every stored row: cdae.py:93-98
-        if self._sharded:                                    # keep the columns of this rank's item range, re-based
-            pos, seen = [self._restrict_columns(c, self._ilo, self._ihi) for c in (pos, seen)]
+        shard = getattr(self, '_shard_csr', None)
+        if shard is not None:                                # fit_item_shard: this rank's columns only, already re-based
+            pos = seen = (shard[0], shard[1], None)
+        else:
+            pos = self._data.csr(self.interaction_threshold)     # positives: cdae.py:61
+            seen = self._data.csr()                              # every stored row: cdae.py:93-98
+            if self._sharded:                                    # keep the columns of this rank's item range, re-based
+                pos, seen = [self._restrict_columns(c, self._ilo, self._ihi) for c in (pos, seen)]
         self._h_indptr = np.ascontiguousarray(pos[0])
-        self._h_indices = np.ascontiguousarray(pos[1])
         self._d_indptr = torch.from_numpy(self._h_indptr).to(dev)
-        self._d_indices = torch.from_numpy(self._h_indices).to(dev)
-        self._d_seen_indptr = torch.from_numpy(np.ascontiguousarray(seen[0])).to(dev)
-        self._d_seen_indices = torch.from_numpy(np.ascontiguousarray(seen[1])).to(dev)
+        if torch.is_tensor(pos[1]):                          # shard generated on the device: indices never visit the host
+            self._h_indices, self._d_indices = None, pos[1].to(dev).contiguous()
+        else:
+            self._h_indices = np.ascontiguousarray(pos[1])
+            self._d_indices = torch.from_numpy(self._h_indices).to(dev)
+        if seen[0] is pos[0] and seen[1] is pos[1]:          # one CSR serves both roles: no second copy in HBM
+            self._d_seen_indptr, self._d_seen_indices = self._d_indptr, self._d_indices
+        else:
+            self._d_seen_indptr = torch.from_numpy(np.ascontiguousarray(seen[0])).to(dev)
+            self._d_seen_indices = torch.from_numpy(np.ascontiguousarray(seen[1])).to(dev)
         sampled = getattr(self, 'output', 'dense') == 'sampled'
         ws_fn = lib.drb_cdae_workspace_bytes_sampled if sampled else lib.drb_cdae_workspace_bytes
         ws_bytes = ws_fn(self._nU, self._nI, self.hidden_factors, self._max_batch)

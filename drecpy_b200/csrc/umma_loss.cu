@@ -69,7 +69,9 @@ __device__ __forceinline__ void mbar_arrive_rank(uint32_t bar, uint32_t rank) { 
 // CTA issues cta_group::2 MMAs (M = 256) that read each CTA's own W' tile and each CTA's half of the shared h tile and
 // write each CTA's own accumulator, so the h tile is staged once per pair and the MMAs read a third less shared memory.
 // (TMA multicast of the h tile with one-CTA MMAs was measured first: no gain, 0.299 vs 0.302 ms.)
-template <int BN, int LOSS, bool PER_USER, int KB, int CL, bool H>
+// ZDBG: the test-only logit capture (drb_debug_cdae_capture_logits) is its own instantiation, so that the production
+// epilogue stays branch free (a per-element `if (z_dbg)` cost 6 % of the kernel)
+template <int BN, int LOSS, bool PER_USER, int KB, int CL, bool H, bool ZDBG>
 __global__ void __launch_bounds__(LOSS_THREADS, 1)
 k_umma_cdae_loss(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                  const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
@@ -249,7 +251,7 @@ k_umma_cdae_loss(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
         for (int j = 0; j < 16; j++) {
           const bool ok = item_ok && (row + j < p.M);
           const float z = H ? fmaf(__uint_as_float(r[j]), osc, bias) : __uint_as_float(r[j]) + bias;
-          if (p.z_dbg && ok) p.z_dbg[(int64_t)(row + j) * p.ldz + item] = z;
+          if (ZDBG && ok) p.z_dbg[(int64_t)(row + j) * p.ldz + item] = z;
           const float pr = fast_rcp(1.0f + fast_ex2(z * -1.4426950408889634f));
           float tgt = tgt_c;
           if (PER_USER) {   // one broadcast word per batch row: bit `lane` of word ib
@@ -376,7 +378,7 @@ k_umma_cdae_loss(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
   }
 }
 
-template <int BN, int LOSS, bool PER_USER, int KB, int CL, bool H>
+template <int BN, int LOSS, bool PER_USER, int KB, int CL, bool H, bool ZDBG>
 int run_loss(drb_ctx* ctx, const UmmaOperands& o, LossParams p, int* n_blocks_out) {
   CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
   int r;
@@ -389,7 +391,7 @@ int run_loss(drb_ctx* ctx, const UmmaOperands& o, LossParams p, int* n_blocks_ou
   p.m_tiles = (p.N + BM - 1) / BM;      // item tiles
   p.n_tiles = (p.M + BN - 1) / BN;      // batch tiles
   p.row_tiles = (p.M + 127) / 128;
-  auto kern = k_umma_cdae_loss<BN, LOSS, PER_USER, KB, CL, H>;
+  auto kern = k_umma_cdae_loss<BN, LOSS, PER_USER, KB, CL, H, ZDBG>;
   constexpr int SMEM = LossSmem<BN, KB, CL>::TOTAL;
   static bool attr_set = false;       // per template instantiation
   static int max_clusters = 0;
@@ -452,32 +454,30 @@ int launch_umma_cdae_loss(drb_ctx* ctx, const UmmaOperands& o, int M, int N, int
   static const int bn_env = getenv("DRB_LOSS_BN") ? atoi(getenv("DRB_LOSS_BN")) : 0;
   // 256 batch rows per tile halve the re-reads of the W' tile (the main loop is L2->SM bandwidth bound)
   const bool wide = bn_env ? (bn_env == 256) : (M > 128);
-  static const int bk_env = getenv("DRB_UMMA_BK") ? atoi(getenv("DRB_UMMA_BK")) : 0;   // profiling override: 16 | 32
   static const int cl_env = getenv("DRB_LOSS_CLUSTER") ? atoi(getenv("DRB_LOSS_CLUSTER")) : 0;   // override: 1 | 2
-#define DRB_LOSS_CASE_H(BN_, KB_, CL_, H_)                                                          \
-  {                                                                                                 \
-    if (loss_kind == DRB_LOSS_BCE)                                                                  \
-      return per_user ? run_loss<BN_, DRB_LOSS_BCE, true, KB_, CL_, H_>(ctx, o, p, n_blocks_out)    \
-                      : run_loss<BN_, DRB_LOSS_BCE, false, KB_, CL_, H_>(ctx, o, p, n_blocks_out);  \
-    return per_user ? run_loss<BN_, DRB_LOSS_MSE, true, KB_, CL_, H_>(ctx, o, p, n_blocks_out)      \
-                    : run_loss<BN_, DRB_LOSS_MSE, false, KB_, CL_, H_>(ctx, o, p, n_blocks_out);    \
+#define DRB_LOSS_CASE_Z(BN_, KB_, CL_, H_, Z_)                                                         \
+  {                                                                                                    \
+    if (loss_kind == DRB_LOSS_BCE)                                                                     \
+      return per_user ? run_loss<BN_, DRB_LOSS_BCE, true, KB_, CL_, H_, Z_>(ctx, o, p, n_blocks_out)   \
+                      : run_loss<BN_, DRB_LOSS_BCE, false, KB_, CL_, H_, Z_>(ctx, o, p, n_blocks_out); \
+    return per_user ? run_loss<BN_, DRB_LOSS_MSE, true, KB_, CL_, H_, Z_>(ctx, o, p, n_blocks_out)     \
+                    : run_loss<BN_, DRB_LOSS_MSE, false, KB_, CL_, H_, Z_>(ctx, o, p, n_blocks_out);   \
   }
-#define DRB_LOSS_CASE(BN_, KB_, CL_)                                                                \
-  {                                                                                                 \
-    if (o.half) DRB_LOSS_CASE_H(BN_, KB_, CL_, true)                                                \
-    DRB_LOSS_CASE_H(BN_, KB_, CL_, false)                                                           \
+#define DRB_LOSS_CASE(BN_, KB_, CL_)                                                                   \
+  {                                                                                                    \
+    if (o.half) {                                                                                      \
+      if (p.z_dbg) DRB_LOSS_CASE_Z(BN_, KB_, CL_, true, true)                                          \
+      DRB_LOSS_CASE_Z(BN_, KB_, CL_, true, false)                                                      \
+    }                                                                                                  \
+    if (p.z_dbg) DRB_LOSS_CASE_Z(BN_, KB_, CL_, false, true)                                           \
+    DRB_LOSS_CASE_Z(BN_, KB_, CL_, false, false)                                                       \
   }
+  // 128-byte stages only: the persistent loop keeps TMA ahead across tiles (64-byte stages measured 0.31 vs 0.30 ms)
   if (wide) {
-    if ((cl_env ? cl_env : DRB_LOSS_CLUSTER_DEFAULT) == 2) {
-      if ((bk_env ? bk_env : 32) == 16) DRB_LOSS_CASE(256, 16, 2)
-      DRB_LOSS_CASE(256, 32, 2)
-    }
-    // the persistent loop already keeps TMA ahead across tiles: 32-deep stages measured 0.30 ms, 16-deep 0.31 ms
-    if ((bk_env ? bk_env : 32) == 16) DRB_LOSS_CASE(256, 16, 1)
+    if ((cl_env ? cl_env : DRB_LOSS_CLUSTER_DEFAULT) == 2) DRB_LOSS_CASE(256, 32, 2)
     DRB_LOSS_CASE(256, 32, 1)
   }
-  if ((bk_env ? bk_env : 32) == 16) DRB_LOSS_CASE(128, 16, 1)
   DRB_LOSS_CASE(128, 32, 1)
 #undef DRB_LOSS_CASE
-#undef DRB_LOSS_CASE_H
+#undef DRB_LOSS_CASE_Z
 }

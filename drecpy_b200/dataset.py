@@ -270,3 +270,46 @@ def synthetic_interactions(n_users, n_items, nnz, seed=10, zipf_a=0.0, rating_lo
     u, i = key // n_items, key % n_items
     val = rng.integers(rating_low, rating_high + 1, len(u))
     return (u + 1).astype(np.int64), (i + 1).astype(np.int64), val.astype(np.int64)
+
+
+def synthetic_item_shard(n_users, n_items, nnz, rank, world, seed=10, zipf_a=1.0, device=None):
+    """The columns [rank * ceil(n_items / world), ...) of a synthetic users x items interaction matrix with about `nnz`
+    entries in total, generated WITHOUT ever forming the whole matrix (BASELINE.json configs[4]: 10 M x 1 M, 1 B
+    interactions does not fit one process comfortably, and every rank only ever touches its own columns).
+    Log-normal user activity (the same for every shard: seeded by `seed` alone), Zipf(zipf_a) item popularity inside the
+    shard (stratified draws), unique (user, item) pairs, items sorted inside a user's row.  With device='cuda:k' the
+    125 M entries of a configs[4] shard are drawn on the GPU in a fraction of a second and stay there.
+    Returns (indptr int64 numpy [n_users + 1], indices int32 local item ids: numpy, or a torch tensor on `device`)."""
+    import torch
+    dev = torch.device(device) if device is not None else torch.device('cpu')
+    per = -(-n_items // world)
+    lo, hi = min(n_items, rank * per), min(n_items, (rank + 1) * per)
+    n_loc = hi - lo
+    act = np.random.default_rng(seed).lognormal(0.0, 1.0, n_users)
+    lam = act * (nnz / world / act.sum())                       # expected entries of every user in this shard
+    rng = np.random.default_rng(seed * 7919 + 1 + rank)
+    deg = np.minimum(rng.poisson(lam), n_loc).astype(np.int64)
+    total = int(deg.sum())
+    # stratified draws: entry j of a row with d entries takes the popularity quantile (j + u) / d, so a row comes out
+    # sorted without any sort; equal neighbours (several strata of an active user inside one popular item) are dropped
+    g = torch.Generator(device=dev).manual_seed(seed * 104729 + rank)
+    tdeg = torch.from_numpy(deg).to(dev)
+    rows = torch.repeat_interleave(torch.arange(n_users, dtype=torch.int64, device=dev), tdeg)
+    start = torch.cumsum(tdeg, 0) - tdeg
+    q = torch.arange(total, dtype=torch.float64, device=dev) - start[rows].double()
+    q += torch.rand(total, generator=g, dtype=torch.float64, device=dev)
+    q /= tdeg[rows].double()
+    if zipf_a > 0:
+        pop = 1.0 / np.power(np.arange(1, n_loc + 1, dtype=np.float64), zipf_a)
+        cdf = torch.from_numpy(np.cumsum(pop / pop.sum())).to(dev)
+        items = torch.searchsorted(cdf, q).clamp_(0, n_loc - 1)
+    else:
+        items = (q * n_loc).long().clamp_(0, n_loc - 1)
+    del q
+    keep = torch.ones(total, dtype=torch.bool, device=dev)
+    keep[1:] = (items[1:] != items[:-1]) | (rows[1:] != rows[:-1])
+    rows, items = rows[keep], items[keep]
+    indices = items.to(torch.int32)
+    indptr = np.zeros(n_users + 1, np.int64)
+    np.cumsum(torch.bincount(rows, minlength=n_users).cpu().numpy(), out=indptr[1:])
+    return indptr, (indices if device is not None else indices.numpy())
