@@ -61,8 +61,11 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 
-__device__ __forceinline__ void mbar_arrive_rank(uint32_t bar, uint32_t rank) {   // same barrier offset in CTA `rank`
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(mapa_rank(bar, rank)) : "memory");
+// same barrier offset in CTA `rank`.  Relaxed: the arrival only says "this warp's tcgen05.ld of the accumulator have
+// completed" (tcgen05.wait::ld precedes it); a release at cluster scope is a MEMBAR that first drains the warp's ~150
+// outstanding dz stores (ncu: stall_membar + ERRBAR were 12 % of the kernel's samples)
+__device__ __forceinline__ void mbar_arrive_rank(uint32_t bar, uint32_t rank) {
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(mapa_rank(bar, rank)) : "memory");
 }
 
 // CL = 2: the two CTAs of a cluster (one TPC) work on two item tiles of the same batch tile as a CTA pair: the even
@@ -285,56 +288,52 @@ k_umma_cdae_loss(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
         if (H) {
           // fp16 hi/lo split of 16 values with 16 packed conversions (cvt.rn.f16x2.f32 handles two floats): hi is first
           // rounded to 11 significant bits in fp32 (Dekker: c = g * (2^13 + 1), hi = c - (c - g)), so its conversion
-          // is exact and lo = g - hi needs no conversion back.  r[j] = hi | lo << 16.
+          // is exact and lo = g - hi needs no conversion back.  hp[i] / lp[i] = users (2i, 2i + 1) packed low | high.
+          uint32_t hp[8], lp[8];
 #pragma unroll
           for (int j = 0; j < 16; j += 2) {
             const float c0 = __fmul_rn(lo[j], 8193.0f), c1 = __fmul_rn(lo[j + 1], 8193.0f);   // no fma contraction
             const float h0 = __fsub_rn(c0, __fsub_rn(c0, lo[j])), h1 = __fsub_rn(c1, __fsub_rn(c1, lo[j + 1]));
             const float l0 = __fsub_rn(lo[j], h0), l1 = __fsub_rn(lo[j + 1], h1);
-            uint32_t hp, lp;                        // .x = user j (low half), .y = user j + 1
-            asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(hp) : "f"(h1), "f"(h0));
-            asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(lp) : "f"(l1), "f"(l0));
-            r[j] = (hp & 0xffffu) | (lp << 16);
-            r[j + 1] = (hp >> 16) | (lp & 0xffff0000u);
+            asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(hp[j >> 1]) : "f"(h1), "f"(h0));
+            asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(lp[j >> 1]) : "f"(l1), "f"(l0));
           }
-        }
-        if (p.colsum) {                         // H: lo[] still holds the unsplit values
+          if (p.colsum) {                         // lo[] still holds the unsplit values
 #pragma unroll
-          for (int j = 0; j < 16; j++) csum += H ? lo[j] : __uint_as_float(r[j]) + lo[j];
-        }
-        if (H) {
+            for (int j = 0; j < 16; j++) csum += lo[j];
+          }
           // two tile-major fp16 copies (tiles of 128 rows x 64 halfs).  U = [user tile][item block]: for one user the
           // lanes of the warp are 32 consecutive items = 64 contiguous bytes.  I = [item tile][user block]: this
-          // thread's item row takes its 16 users = 32 contiguous bytes.  Every element of an existing tile is written
-          // (zeros outside the matrix): the backward GEMMs read whole tiles.
+          // thread's item row takes its 16 users = 32 contiguous bytes = hp[0..7] as they are.  Every element of an
+          // existing tile is written (zeros outside the matrix): the backward GEMMs read whole tiles.
           const int rt = row >> 7, cbu = (i0 >> 6) + (q >> 1);
           if (rt < p.dzh.row_tiles && cbu < p.dzh.nib64 && !(p.debug & 4)) {
             const int64_t off = ((int64_t)(rt * p.dzh.nib64 + cbu) * 128 + (row & 127)) * 64 + (q & 1) * 32 + lane;
             unsigned short* uh = reinterpret_cast<unsigned short*>(p.dzh.u_hi) + off;
             unsigned short* ul = reinterpret_cast<unsigned short*>(p.dzh.u_lo) + off;
 #pragma unroll
-            for (int j = 0; j < 16; j++) {
-              uh[j * 64] = (unsigned short)(r[j] & 0xffffu);
-              ul[j * 64] = (unsigned short)(r[j] >> 16);
+            for (int i = 0; i < 8; i++) {
+              uh[(2 * i) * 64] = (unsigned short)hp[i];
+              uh[(2 * i + 1) * 64] = (unsigned short)(hp[i] >> 16);
+              ul[(2 * i) * 64] = (unsigned short)lp[i];
+              ul[(2 * i + 1) * 64] = (unsigned short)(lp[i] >> 16);
             }
           }
           const int itile = i0 >> 7, ub = row >> 6;
           if (itile < p.dzh.item_tiles && ub < p.dzh.nub && !(p.debug & 4)) {
             const int64_t off = ((int64_t)(itile * p.dzh.nub + ub) * 128 + q * 32 + lane) * 64 + (row & 63);
-            uint32_t ph[8], pl[8];
-#pragma unroll
-            for (int j = 0; j < 8; j++) {
-              ph[j] = (r[2 * j] & 0xffffu) | (r[2 * j + 1] << 16);
-              pl[j] = (r[2 * j] >> 16) | (r[2 * j + 1] & 0xffff0000u);
-            }
             uint4* dh4 = reinterpret_cast<uint4*>(reinterpret_cast<unsigned short*>(p.dzh.i_hi) + off);
             uint4* dl4 = reinterpret_cast<uint4*>(reinterpret_cast<unsigned short*>(p.dzh.i_lo) + off);
-            dh4[0] = make_uint4(ph[0], ph[1], ph[2], ph[3]);
-            dh4[1] = make_uint4(ph[4], ph[5], ph[6], ph[7]);
-            dl4[0] = make_uint4(pl[0], pl[1], pl[2], pl[3]);
-            dl4[1] = make_uint4(pl[4], pl[5], pl[6], pl[7]);
+            dh4[0] = make_uint4(hp[0], hp[1], hp[2], hp[3]);
+            dh4[1] = make_uint4(hp[4], hp[5], hp[6], hp[7]);
+            dl4[0] = make_uint4(lp[0], lp[1], lp[2], lp[3]);
+            dl4[1] = make_uint4(lp[4], lp[5], lp[6], lp[7]);
           }
         } else {
+        if (p.colsum) {
+#pragma unroll
+          for (int j = 0; j < 16; j++) csum += __uint_as_float(r[j]) + lo[j];
+        }
         // tile-major store: row j of this chunk is the 128-byte line ((row tile, item block), row in tile) and the
         // lanes are its 32 floats.  Every row and column of an existing tile is written (zeros outside the matrix)
         // because the backward GEMMs read whole tiles.

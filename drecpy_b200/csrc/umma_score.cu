@@ -61,7 +61,9 @@ __device__ __forceinline__ void sc_mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 __device__ __forceinline__ void sc_mbar_arrive_rank(uint32_t bar, uint32_t rank) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(mapa_rank(bar, rank)) : "memory");
+  // relaxed: the arrival only reports completed tcgen05.ld reads (see umma_loss.cu); a cluster-scope release would
+  // first drain the warp's outstanding list stores
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(mapa_rank(bar, rank)) : "memory");
 }
 
 template <int BN, int KB, int CL, bool H>
