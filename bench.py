@@ -880,10 +880,9 @@ def run_c5_native(args, cfg, D, arrays=None):
     sc = args.c5_scale
     U, I, nnz = int(cfg['n_users'] * sc), int(cfg['n_items'] * sc), int(cfg['nnz'] * sc)
     world, rank, dev = D.world, D.rank, D.dev
-    assert world > 1, 'configs[4] is the item-sharded multi-GPU mode: launch with torch.distributed.run (N >= 2)'
     B, K, W = cfg['batch'], args.steps, args.warmup
     Bg = B * world
-    neg_per_group = max(1, cfg['neg_total'] // world)
+    neg_per_group = max(1, cfg['neg_total'] // world)      # one negative-sampling group per rank (= per item shard)
     torch.cuda.reset_peak_memory_stats(dev)
     t0 = time.time()
     indptr, indices = drb.synthetic_item_shard(U, I, nnz, rank, world, seed=cfg['seed'], zipf_a=cfg['zipf_a'], device=str(dev))
@@ -893,6 +892,8 @@ def run_c5_native(args, cfg, D, arrays=None):
                  rng_mode='philox', device=str(dev), output='sampled', neg_per_group=neg_per_group)
     m.fit_item_shard((indptr, indices), U, I, B, DataParallel(D.dist), learning_rate=cfg['lr'], reg_rate=cfg['reg'])
     lib = _lib.load()
+    if world == 1:
+        Bg = B
     batches = []
     nb = min(K + W, 16)
     for _ in range(nb):
