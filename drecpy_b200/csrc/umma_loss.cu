@@ -228,6 +228,8 @@ k_umma_cdae_loss(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
       const bool item_ok = item < p.N;
       const int ib = (i0 >> 5) + q;               // 32-item block of this warp
       const float bias = nbias, tgt_c = ncount / fbatch;
+      const float osc2 = osc * -1.4426950408889634f, nb2 = bias * -1.4426950408889634f;   // exp2 argument = fma(acc, osc2, nb2)
+      float sum_la = 0.f, sum_lb = 0.f;           // fast chunks: sums of lg2(p + eps), lg2(1 - p + eps) of this lane's item
       fetch_consts(t + unit_stride);
       mbar_wait(tfull_bar(as), (tl >> 1) & 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -250,6 +252,31 @@ k_umma_cdae_loss(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
         //   bce term   = -(t ln da + (1-t) ln db) = -ln2 (lg2 db + t (lg2 da - lg2 db))
         //   dL/dp      = ((1-t) da - t db) / (da db) / (B I) = (da - t (da + db)) / (da db) / (B I)   [p inside the clip]
         //   dL/dz      = dL/dp * p (1-p)
+        // Fast form of the same math for the common chunk (fp16 path, BCE, batch-mean labels): every (row, item) of the
+        // chunk exists and no logit is extreme (|z| < 15.2, so p stays strictly inside Keras' clip and the clip, the
+        // `inside` test and the row / item masks are the identity).  The logit is never formed: the exp2 argument is one
+        // fma; log terms are summed as two plain sums (the label is constant per lane); da + db = 1 + 2 eps.  One
+        // max-|arg| per element and one vote per chunk decide; the general form below handles everything else.
+        bool fast = false;
+        if (H && !ZDBG && LOSS == DRB_LOSS_BCE && !PER_USER) {
+          fast = item_ok && (row + 16 <= p.M);
+          float amax = 0.f;
+#pragma unroll
+          for (int j = 0; j < 16; j++) amax = fmaxf(amax, fabsf(fmaf(__uint_as_float(r[j]), osc2, nb2)));
+          fast = !__any_sync(0xffffffffu, !fast || amax > 22.0f);
+        }
+        if (fast) {
+#pragma unroll
+          for (int j = 0; j < 16; j++) {
+            const float e = fast_ex2(fmaf(__uint_as_float(r[j]), osc2, nb2));
+            const float pr = fast_rcp(1.0f + e);
+            const float da = pr + KERAS_EPS, db = 1.0f - pr + KERAS_EPS;
+            sum_la += fast_lg2(da);
+            sum_lb += fast_lg2(db);
+            const float num = fmaf(tgt_c, -(1.0f + 2.0f * KERAS_EPS), da);
+            lo[j] = num * (pr * (1.0f - pr)) * (fast_rcp(da * db) * gsc);
+          }
+        } else
 #pragma unroll
         for (int j = 0; j < 16; j++) {
           const bool ok = item_ok && (row + j < p.M);
@@ -348,6 +375,7 @@ k_umma_cdae_loss(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
         }
         }
       }
+      loss_local += -0.6931471805599453f * fmaf(tgt_c, sum_la - sum_lb, sum_lb);   // bce terms of the fast chunks
       if (p.colsum && item_ok) atomicAdd(p.colsum + item, H ? csum * (p.inv_count / DRB_DZ_F16_SCALE) : csum);
       // this warp has finished reading accumulator `as`
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
