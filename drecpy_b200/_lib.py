@@ -127,7 +127,7 @@ SIGNATURES = {
     'drb_debug_split_tf32': (C.c_int, [vp, vp, i32, i32, i32, vp, vp, vp, vp, i32, i32]),
     'drb_debug_umma_gemm': (C.c_int, [vp, vp, vp, i32, vp, vp, i32, i32, i32, i32, i32, i32, i32, vp, i32, i32, vp, i32]),
     'drb_debug_split_f16': (C.c_int, [vp, vp, i32, i32, i32, f32, vp, vp, i32, vp, vp, i32, i32]),
-    'drb_debug_umma_gemm_f16': (C.c_int, [vp, vp, vp, i32, vp, vp, i32, i32, i32, i32, i32, i32, f32, vp, i32, i32, vp, i32]),
+    'drb_debug_umma_gemm_f16': (C.c_int, [vp, vp, vp, i32, vp, vp, i32, i32, i32, i32, i32, i32, i32, f32, vp, i32, i32, vp, i32]),
     'drb_eval_candidates': (C.c_int, [i64, vp, vp, vp, vp, vp, vp, vp, vp, i64, i32, i64, f64, i64, f64, i32, i32, i64,
                                       i32, i64, vp, vp, vp, vp, vp]),
     'drb_leave_k_out': (C.c_int, [i64, vp, i64, f64, i32, i64, i64, i32, vp]),

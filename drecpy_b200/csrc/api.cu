@@ -155,14 +155,14 @@ int drb_debug_split_f16(drb_ctx* ctx, const float* src, int32_t rows, int32_t co
 }
 
 int drb_debug_umma_gemm_f16(drb_ctx* ctx, const void* a_hi, const void* a_lo, int32_t lda, const void* b_hi,
-                            const void* b_lo, int32_t ldb, int32_t b_rows, int32_t M, int32_t N, int32_t Kred,
+                            const void* b_lo, int32_t ldb, int32_t b_rows, int32_t a_mn_major, int32_t M, int32_t N, int32_t Kred,
                             int32_t splits, float out_scale, float* C, int32_t ldc, int32_t n_store, float* extra_col,
                             int32_t extra_col_index) {
   if (!ctx || !a_hi || !a_lo || !b_hi || !b_lo || !C) return drb_fail(DRB_E_INVALID, "drb_debug_umma_gemm_f16: NULL argument");
   if (!umma_available()) return drb_fail(DRB_E_NODEVICE, "tcgen05/TMA path unavailable");
   UmmaOperands o{a_hi, a_lo, lda, b_hi, b_lo, ldb, b_rows};
   o.half = true; o.out_scale = out_scale;
-  return launch_umma_store(ctx, o, false, M, N, Kred, splits, C, ldc, n_store, n_store, extra_col, extra_col_index);
+  return launch_umma_store(ctx, o, a_mn_major != 0, M, N, Kred, splits, C, ldc, n_store, n_store, extra_col, extra_col_index);
 }
 
 }  // extern "C"
@@ -571,7 +571,11 @@ static int cdae_step_impl(drb_cdae* m, const int32_t* uids, const int32_t* keep_
     dzh.row_tiles = (m->d.max_batch + 127) / 128; dzh.item_tiles = (I + 127) / 128;
     dzh.nib64 = drb_dz_nib64(I); dzh.nub = 2 * dzh.row_tiles;
     dzh.u_hi = w.dzt_hi; dzh.u_lo = reinterpret_cast<char*>(w.dzt_hi) + half_bytes;
-    dzh.i_hi = w.dzt_lo; dzh.i_lo = reinterpret_cast<char*>(w.dzt_lo) + half_bytes;
+    // one copy of dz (U) serves both backward GEMMs: dh reads it K-major, dW'^T reads it transposed through the MN-major
+    // descriptor.  DRB_DZ_COPIES=2 also writes the [item tile][user block] copy and feeds dW'^T from it (the round's
+    // first form: 0.1 ms of extra store time in the loss kernel).
+    static const bool two_copies = getenv("DRB_DZ_COPIES") && atoi(getenv("DRB_DZ_COPIES")) == 2;
+    if (two_copies) { dzh.i_hi = w.dzt_lo; dzh.i_lo = reinterpret_cast<char*>(w.dzt_lo) + half_bytes; }
   }
   const float dz_unscale = inv_count / DRB_DZ_F16_SCALE;      // fp16 dz holds dL/dz2 * 2^14 / inv_count
 
@@ -618,11 +622,18 @@ static int cdae_step_impl(drb_cdae* m, const int32_t* uids, const int32_t* keep_
     const int mt2 = (I + 127) / 128;
     const int s2 = batch >= 1024 ? std::max(1, std::min({16, (2 * ctx->sm_count + mt2 - 1) / mt2, batch / 512})) : 1;
     const bool colsum = cdae_colsum_in_loss(m->d.hidden);
-    if (m->half) {      // A = the [item tile][user block] copy of dz (K-major over users), B = h^T
+    if (m->half && dzh.i_hi) {      // A = the [item tile][user block] copy of dz (K-major over users), B = h^T
       UmmaOperands oh{dzh.i_hi, dzh.i_lo, 64, w.hT_hi, w.hT_lo, m->bp8, n2};
       oh.a_tiled_nib = dzh.nub; oh.a_tiled_rows = (int64_t)dzh.item_tiles * dzh.nub * 128;
       oh.half = true; oh.out_scale = dz_unscale / DRB_H_F16_SCALE; oh.name = "k_umma_gemm_dw";
       if ((r = launch_umma_store(ctx, oh, false, I, n2, batch, s2, G + L.off_w2t, ld, ld, m->d.hidden,
+                                 colsum ? nullptr : G + L.off_b2, colsum ? -1 : m->d.hidden, s2 > 1)))
+        return r;
+    } else if (m->half) {           // A = the one [user tile][item block] copy of dz, read MN-major (m = items contiguous)
+      UmmaOperands oh{dzh.u_hi, dzh.u_lo, 64, w.hT_hi, w.hT_lo, m->bp8, n2};
+      oh.a_tiled_nib = dzh.nib64; oh.a_tiled_rows = (int64_t)((m->d.max_batch + 127) / 128) * dzh.nib64 * 128;
+      oh.half = true; oh.out_scale = dz_unscale / DRB_H_F16_SCALE; oh.name = "k_umma_gemm_dw";
+      if ((r = launch_umma_store(ctx, oh, true, I, n2, batch, s2, G + L.off_w2t, ld, ld, m->d.hidden,
                                  colsum ? nullptr : G + L.off_b2, colsum ? -1 : m->d.hidden, s2 > 1)))
         return r;
     } else

@@ -54,7 +54,6 @@ __global__ void __launch_bounds__(THREADS, 1)
 k_umma_gemm(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
             const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo, UmmaParams p) {
   using S = Smem<BN, KB, CL>;
-  static_assert(!(H && A_MN), "fp16 operands are K-major only (the loss kernel writes dz in both orientations)");
   constexpr int BK = H ? 2 * KB : KB;            // elements of the reduction dimension per stage (KB: 4-byte units)
   constexpr int UK = H ? 16 : UMMA_K;            // elements one MMA consumes (32 bytes either way)
   constexpr int TW = H ? 64 : 32;                // width of a dz tile in elements (128 bytes)
@@ -120,10 +119,10 @@ k_umma_gemm(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
         if (p.a_tiled_nib > 0) {
           // dz tile-major layout: tile (row tile rt, column block cb) = 128 rows x 32 floats, contiguous 16 KB at
           // row ((rt * nib + cb) * 128) of a [*, 32] tensor
-          if (A_MN) {   // M runs over dz columns, K over dz rows: four boxes {32 cols, BK rows}
+          if (A_MN) {   // M runs over dz columns, K over dz rows: one box {TW cols (128 bytes), BK rows} per MN atom
 #pragma unroll
-            for (int j = 0; j < BM / 32; j++) {
-              const int row = ((k0 >> 7) * p.a_tiled_nib + (m0 >> 5) + j) * 128 + (k0 & 127);
+            for (int j = 0; j < BM / TW; j++) {
+              const int row = ((k0 >> 7) * p.a_tiled_nib + (m0 / TW) + j) * 128 + (k0 & 127);
               load(sa_hi + j * (BK * 128), &map_a_hi, full_bar(s), 0, row);
               load(sa_lo + j * (BK * 128), &map_a_lo, full_bar(s), 0, row);
             }
@@ -133,11 +132,11 @@ k_umma_gemm(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
             load(sa_lo, &map_a_lo, full_bar(s), k0 % TW, row);
           }
         } else if (A_MN) {
-          // A[m][k] stored as G[k][m] (m contiguous): four boxes of {32 m, BK k}, one per 32-wide MN atom column
+          // A[m][k] stored as G[k][m] (m contiguous): boxes of {TW m (128 bytes), BK k}, one per MN atom column
 #pragma unroll
-          for (int j = 0; j < BM / 32; j++) {
-            load(sa_hi + j * (BK * 128), &map_a_hi, full_bar(s), m0 + 32 * j, k0);
-            load(sa_lo + j * (BK * 128), &map_a_lo, full_bar(s), m0 + 32 * j, k0);
+          for (int j = 0; j < BM / TW; j++) {
+            load(sa_hi + j * (BK * 128), &map_a_hi, full_bar(s), m0 + TW * j, k0);
+            load(sa_lo + j * (BK * 128), &map_a_lo, full_bar(s), m0 + TW * j, k0);
           }
         } else {
           load(sa_hi, &map_a_hi, full_bar(s), k0, m0);
@@ -166,7 +165,12 @@ k_umma_gemm(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
         for (int kk = 0; kk < BK / UK; kk++) {
           if (kk >= kk_n) break;
           uint64_t a_hi, a_lo;
-          if (A_MN) {   // MN-major: rows = k (128 B = 32 m each); K atoms of 4 rows are 512 B apart, one MMA (K=8)
+          if (A_MN && H) {
+            // MN-major fp16: rows = k (128 B = 64 m each), SWIZZLE_128B; K atoms of 8 rows are 1024 B apart, one MMA
+            // (K = 16) spans two of them; MN atoms (64 halfs, one TMA box of BK rows) are BK * 128 B apart
+            a_hi = make_desc(sa_hi + kk * 2048, BK * 128, 1024, 2);
+            a_lo = make_desc(sa_lo + kk * 2048, BK * 128, 1024, 2);
+          } else if (A_MN) {   // MN-major tf32: rows = k (128 B = 32 m each); K atoms of 4 rows are 512 B apart, one MMA (K=8)
                         // spans two of them; MN atoms (32 floats, one TMA box of BK rows) are BK * 128 B apart
             a_hi = make_desc(sa_hi + kk * 1024, KB * 128, 512, 1);
             a_lo = make_desc(sa_lo + kk * 1024, KB * 128, 512, 1);
@@ -344,8 +348,14 @@ int run_umma(drb_ctx* ctx, const UmmaOperands& o, const UmmaParams& p, int* n_bl
   constexpr int SMEM = Smem<BN, KB, CL>::TOTAL;
   CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
   int r;
-  if (H) {      // fp16 hi / lo operands, K-major; tile-major dz = a [tiles * 128, 64 halfs] tensor
-    if (o.a_tiled_nib > 0) {
+  if (H) {      // fp16 hi / lo operands; tile-major dz = a [tiles * 128, 64 halfs] tensor
+    if (o.a_tiled_nib > 0 && A_MN) {          // MN-major: boxes of {64 halfs of M, 2 * KB rows of K}
+      if ((r = make_map_h(&ma_hi, o.a_hi, 64, o.a_tiled_rows, 64, 64, 2 * KB))) return r;
+      if ((r = make_map_h(&ma_lo, o.a_lo, 64, o.a_tiled_rows, 64, 64, 2 * KB))) return r;
+    } else if (A_MN) {                        // A given as G[k][m]
+      if ((r = make_map_h(&ma_hi, o.a_hi, p.M, p.Kred, o.lda, 64, 2 * KB))) return r;
+      if ((r = make_map_h(&ma_lo, o.a_lo, p.M, p.Kred, o.lda, 64, 2 * KB))) return r;
+    } else if (o.a_tiled_nib > 0) {
       if ((r = make_map_h(&ma_hi, o.a_hi, 64, o.a_tiled_rows, 64, 2 * KB, BM))) return r;
       if ((r = make_map_h(&ma_lo, o.a_lo, 64, o.a_tiled_rows, 64, 2 * KB, BM))) return r;
     } else {
@@ -453,12 +463,16 @@ int launch_umma_store(drb_ctx* ctx, const UmmaOperands& o, bool a_mn_major, int 
   static const int cl_env = getenv("DRB_UMMA_CLUSTER") ? atoi(getenv("DRB_UMMA_CLUSTER")) : 0;   // override: 1 | 2
 #define DRB_UMMA_CASE(BN, KB_DEFAULT, CL_DEFAULT)                                       \
   if (N <= BN) {                                                                        \
-    if (o.half) {   /* fp16 operands: K-major only */                                   \
-      if (a_mn_major) return drb_fail(DRB_E_INVALID, "umma store GEMM: fp16 operands are K-major only"); \
+    if (o.half) {   /* fp16 hi / lo operands */                                         \
       if ((bk_env ? bk_env : KB_DEFAULT) == 16) {                                       \
-        if ((cl_env ? cl_env : CL_DEFAULT) == 2) return run_umma<BN, false, 16, 2, true>(ctx, o, p, nullptr); \
+        if ((cl_env ? cl_env : CL_DEFAULT) == 2) {                                      \
+          if (a_mn_major) return run_umma<BN, true, 16, 2, true>(ctx, o, p, nullptr);   \
+          return run_umma<BN, false, 16, 2, true>(ctx, o, p, nullptr);                  \
+        }                                                                               \
+        if (a_mn_major) return run_umma<BN, true, 16, 1, true>(ctx, o, p, nullptr);     \
         return run_umma<BN, false, 16, 1, true>(ctx, o, p, nullptr);                    \
       }                                                                                 \
+      if (a_mn_major) return run_umma<BN, true, 32, 1, true>(ctx, o, p, nullptr);       \
       return run_umma<BN, false, 32, 1, true>(ctx, o, p, nullptr);                      \
     }                                                                                   \
     if ((bk_env ? bk_env : KB_DEFAULT) == 16) {                                         \

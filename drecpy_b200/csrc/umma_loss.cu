@@ -50,7 +50,8 @@ struct LossParams {
   float* z_dbg; int ldz;                   // tests only (drb_debug_cdae_capture_logits): z2 = h W'^T + b' as this kernel
                                            // formed it, row-major [M][ldz]; NULL in production
   int debug;   // DRB_LOSS_DEBUG bit mask (profiling experiments only, results are wrong): 1 = first 16-row chunk of
-               // each epilogue warp only, 2 = skip TMA + MMA, 4 = skip the dz stores, 8 = skip the B_lo loads, 16 = skip the MMAs
+               // each epilogue warp only, 2 = skip TMA + MMA, 4 = skip the dz stores, 8 = skip the B_lo loads, 16 = skip the MMAs,
+               // 32 = no lg2 in the fast epilogue form
 };
 
 __device__ __forceinline__ float fast_ex2(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
@@ -271,8 +272,8 @@ k_umma_cdae_loss(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
             const float e = fast_ex2(fmaf(__uint_as_float(r[j]), osc2, nb2));
             const float pr = fast_rcp(1.0f + e);
             const float da = pr + KERAS_EPS, db = 1.0f - pr + KERAS_EPS;
-            sum_la += fast_lg2(da);
-            sum_lb += fast_lg2(db);
+            sum_la += (p.debug & 32) ? da : fast_lg2(da);
+            sum_lb += (p.debug & 32) ? db : fast_lg2(db);
             const float num = fmaf(tgt_c, -(1.0f + 2.0f * KERAS_EPS), da);
             lo[j] = num * (pr * (1.0f - pr)) * (fast_rcp(da * db) * gsc);
           }
@@ -347,7 +348,7 @@ k_umma_cdae_loss(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
             }
           }
           const int itile = i0 >> 7, ub = row >> 6;
-          if (itile < p.dzh.item_tiles && ub < p.dzh.nub && !(p.debug & 4)) {
+          if (p.dzh.i_hi && itile < p.dzh.item_tiles && ub < p.dzh.nub && !(p.debug & 4)) {
             const int64_t off = ((int64_t)(itile * p.dzh.nub + ub) * 128 + q * 32 + lane) * 64 + (row & 63);
             uint4* dh4 = reinterpret_cast<uint4*>(reinterpret_cast<unsigned short*>(p.dzh.i_hi) + off);
             uint4* dl4 = reinterpret_cast<uint4*>(reinterpret_cast<unsigned short*>(p.dzh.i_lo) + off);

@@ -350,11 +350,12 @@ int drb_debug_umma_gemm(drb_ctx* ctx, const float* a_hi, const float* a_lo, int3
 
 /* The 3xFP16 forms of the same building blocks: x * alpha -> fp16 hi / lo ([rows][ldh halfs]; transposed [cols..][ldt
  * halfs], ones_row set to alpha), and C = out_scale * sum_k A(m,k) B(n,k) from K-major fp16 hi / lo operands
- * (A [M][lda halfs], B [b_rows][ldb halfs]; pitches are multiples of 8). */
+ * (A [M][lda halfs], or with a_mn_major != 0 A stored as [Kred][lda halfs] with m contiguous; B [b_rows][ldb halfs];
+ * pitches are multiples of 8). */
 int drb_debug_split_f16(drb_ctx* ctx, const float* src, int32_t rows, int32_t cols, int32_t ld, float alpha, void* hi,
                         void* lo, int32_t ldh, void* t_hi, void* t_lo, int32_t ldt, int32_t ones_row);
 int drb_debug_umma_gemm_f16(drb_ctx* ctx, const void* a_hi, const void* a_lo, int32_t lda, const void* b_hi,
-                            const void* b_lo, int32_t ldb, int32_t b_rows, int32_t M, int32_t N, int32_t Kred,
+                            const void* b_lo, int32_t ldb, int32_t b_rows, int32_t a_mn_major, int32_t M, int32_t N, int32_t Kred,
                             int32_t splits, float out_scale, float* C, int32_t ldc, int32_t n_store, float* extra_col,
                             int32_t extra_col_index);
 

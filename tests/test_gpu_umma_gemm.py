@@ -145,10 +145,37 @@ def test_umma_f16_kmajor(ctx, M, N, K, splits):
     ldc = (N + 3) // 4 * 4
     Cm = torch.full((splits, M, ldc), float('nan'), device='cuda')
     _lib.check(lib.drb_debug_umma_gemm_f16(ctx, _lib.t_ptr(a_hi), _lib.t_ptr(a_lo), a_hi.shape[1], _lib.t_ptr(b_hi),
-                                           _lib.t_ptr(b_lo), b_hi.shape[1], N, M, N, K, splits,
+                                           _lib.t_ptr(b_lo), b_hi.shape[1], N, 0, M, N, K, splits,
                                            1.0 / (alpha_a * alpha_b), _lib.t_ptr(Cm), ldc, N, None, -1))
     torch.cuda.synchronize()
     got = Cm.sum(0)[:, :N]
     want = a.double() @ b.double().t()
     ok, msg = _report(got, want, f'f16 kmajor {M}x{N}x{K}/{splits}')
     assert ok, msg
+
+
+@pytest.mark.parametrize('M,N,K', [(128, 64, 64), (300, 208, 200), (1000, 56, 1000), (26744, 208, 512)])
+def test_umma_f16_mnmajor_with_ones_column(ctx, M, N, K):
+    """dW'^T = dz^T h in fp16 hi/lo form with A MN-major (A given as G[k][m], the layout dz is written in): the transposed
+    operand is read through the MN-major SWIZZLE_128B descriptor; the constant-one row of B folds db' into the product."""
+    import torch
+    g = torch.Generator(device='cuda').manual_seed(M + N + K)
+    G = (torch.rand((K, M), device='cuda', generator=g) - 0.5) * 2.0          # dz / inv_count in [-1, 1]
+    G = G * torch.pow(10.0, -4 * torch.rand((K, M), device='cuda', generator=g))
+    H_ = torch.rand((K, N - 1), device='cuda', generator=g) * 0.999           # activations [batch, hidden]
+    alpha_g, alpha_h = 16384.0, 32768.0
+    g_hi, g_lo, _, _ = _split_f16(ctx, G, alpha_g)                            # [K][ldm] : m contiguous
+    _, _, ht_hi, ht_lo = _split_f16(ctx, H_, alpha_h, transpose=True, ones_row=N - 1, t_rows=N)
+    lib = _lib.load()
+    ldc = (N + 3) // 4 * 4
+    Cm = torch.full((1, M, ldc), float('nan'), device='cuda')
+    extra = torch.full((M,), float('nan'), device='cuda')
+    _lib.check(lib.drb_debug_umma_gemm_f16(ctx, _lib.t_ptr(g_hi), _lib.t_ptr(g_lo), g_hi.shape[1], _lib.t_ptr(ht_hi),
+                                           _lib.t_ptr(ht_lo), ht_hi.shape[1], N, 1, M, N, K, 1,
+                                           1.0 / (alpha_g * alpha_h), _lib.t_ptr(Cm), ldc, N - 1, _lib.t_ptr(extra), N - 1))
+    torch.cuda.synchronize()
+    want = G.double().t() @ H_.double()
+    ok, msg = _report(Cm[0][:, :N - 1], want, f'f16 mn-major {M}x{N}x{K}')
+    assert ok, msg
+    colsum = G.double().sum(0)
+    assert float((extra.double() - colsum).abs().max()) <= 1e-5 * float(colsum.abs().max()), 'ones column (db)'
