@@ -84,6 +84,13 @@ SIGNATURES = {
     'drb_rng_random_fill': (C.c_int, [vp, i64, vp]),
     'drb_rng_sample_indices': (C.c_int, [vp, i64, i64, vp]),
     'drb_rng_shuffle_i64': (C.c_int, [vp, i64, vp]),
+    'drb_rng_window': (C.c_int, [vp, vp]),
+    'drb_rng_set_window': (C.c_int, [vp, vp]),
+    'drb_rng_skip': (C.c_int, [vp, i64]),
+    'drb_mtjump_create': (C.c_int, [i64, i32, P(vp)]),
+    'drb_mtjump_destroy': (C.c_int, [vp]),
+    'drb_mtjump_polys': (C.c_int, [vp, vp]),
+    'drb_mtjump_apply_host': (C.c_int, [vp, i32, vp, vp]),
     'drb_rng_getstate': (C.c_int, [vp, vp]),
     'drb_rng_setstate': (C.c_int, [vp, vp]),
     'drb_sampler_create': (C.c_int, [i32, i32, vp, vp, vp, vp, vp, f64, u64, P(vp)]),
@@ -92,6 +99,7 @@ SIGNATURES = {
     'drb_sampler_getstate': (C.c_int, [vp, vp]),
     'drb_sampler_setstate': (C.c_int, [vp, vp]),
     'drb_cdae_corruption_keep_mt': (C.c_int, [vp, vp, i32, i32, f64, vp, vp, vp, vp, i64]),
+    'drb_mt_keep_device': (C.c_int, [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, u64]),
     'drb_batch_offsets': (C.c_int, [vp, i32, vp, vp]),
     'drb_cdae_layout': (C.c_int, [i32, i32, i32, P(CdaeLayout)]),
     'drb_cdae_workspace_bytes': (i64, [i32, i32, i32, i32]),

@@ -148,6 +148,22 @@ int drb_debug_umma_gemm(drb_ctx* ctx, const float* a_hi, const float* a_lo, int3
                            extra_col_index);
 }
 
+int drb_mt_keep_device(drb_ctx* ctx, const uint32_t* window_in, uint32_t* window_out, const uint64_t* polys,
+                       const uint64_t* poly_total, const int32_t* uids, const int32_t* keep_off, const int64_t* csr_indptr,
+                       const int32_t* csr_indices, uint8_t* keep, int32_t batch, int32_t n_items, int32_t users_per_cta,
+                       uint64_t threshold) {
+  if (!ctx || !window_in || !window_out || !poly_total || !uids || !keep_off || !csr_indptr || !csr_indices || !keep)
+    return drb_fail(DRB_E_INVALID, "drb_mt_keep_device: NULL argument");
+  if (batch <= 0 || n_items <= 0 || users_per_cta < 1) return drb_fail(DRB_E_INVALID, "drb_mt_keep_device: bad sizes");
+  MtKeepArgs a{};
+  a.window_in = window_in; a.window_out = window_out; a.polys = polys; a.poly_total = poly_total;
+  a.uids = uids; a.keep_off = keep_off; a.indptr = csr_indptr; a.indices = csr_indices; a.keep = keep;
+  a.batch = batch; a.n_items = n_items; a.ups = users_per_cta; a.n_cta = (batch + users_per_cta - 1) / users_per_cta;
+  a.threshold = threshold;
+  if (a.n_cta > 1 && !polys) return drb_fail(DRB_E_INVALID, "drb_mt_keep_device: jump polynomials missing");
+  return launch_mt_keep(ctx, a);
+}
+
 int drb_debug_split_f16(drb_ctx* ctx, const float* src, int32_t rows, int32_t cols, int32_t ld, float alpha, void* hi,
                         void* lo, int32_t ldh, void* t_hi, void* t_lo, int32_t ldt, int32_t ones_row) {
   if (!ctx || !src) return drb_fail(DRB_E_INVALID, "drb_debug_split_f16: NULL argument");

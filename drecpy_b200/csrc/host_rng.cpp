@@ -161,6 +161,32 @@ int drb_rng_shuffle_i64(drb_rng* rng, int64_t n, int64_t* x) {
   shuffle_i64(*rng, n, x);
   return DRB_OK;
 }
+// The next 624 UNTEMPERED output words of the generator (it is not advanced): with idx = 0 this is the mt[] array
+// itself, so (window, idx = 0) is a complete generator state -- the form the device replay of the corruption stream
+// (mt_device.cu) keeps.  drb_rng_set_window is the inverse.
+int drb_rng_window(const drb_rng* rng, uint32_t window[624]) {
+  if (!rng || !window) return drb_fail(DRB_E_INVALID, "drb_rng_window: NULL argument");
+  drb_rng c = *rng;
+  if (c.idx >= drb_rng::N) c.twist();
+  const int head = drb_rng::N - c.idx;
+  std::memcpy(window, c.mt + c.idx, (size_t)head * 4);
+  if (c.idx > 0) {
+    c.twist();
+    std::memcpy(window + head, c.mt, (size_t)(drb_rng::N - head) * 4);
+  }
+  return DRB_OK;
+}
+int drb_rng_set_window(drb_rng* rng, const uint32_t window[624]) {
+  if (!rng || !window) return drb_fail(DRB_E_INVALID, "drb_rng_set_window: NULL argument");
+  std::memcpy(rng->mt, window, sizeof(rng->mt));
+  rng->idx = 0;
+  return DRB_OK;
+}
+int drb_rng_skip(drb_rng* rng, int64_t n_outputs) {
+  if (!rng || n_outputs < 0) return drb_fail(DRB_E_INVALID, "drb_rng_skip: bad argument");
+  rng->skip(n_outputs);
+  return DRB_OK;
+}
 int drb_rng_getstate(const drb_rng* rng, uint32_t state[625]) {
   if (!rng || !state) return drb_fail(DRB_E_INVALID, "drb_rng_getstate: NULL argument");
   std::memcpy(state, rng->mt, sizeof(rng->mt));

@@ -80,6 +80,20 @@ int launch_sigmoid_rows(drb_ctx* ctx, float* x, int n, int ld, int width);
 // out[j] = sum_p part[p, ld + j]
 int launch_reduce_partials(drb_ctx* ctx, const float* part, int nparts, int ld, float* out, int n);
 
+// ------------------------------------------------------------------ mt_device.cu
+// Device replay of the reference's MT19937 corruption stream (cdae.py:63-64): keep bytes of the batch's positives.
+struct MtKeepArgs {
+  const uint32_t* window_in; uint32_t* window_out;     // 624-word windows: the stream at the start / end of this step
+  const uint64_t* polys;                               // [n_cta - 1][312]: jump polynomials of offsets p * ups * 2 * n_items
+  const uint64_t* poly_total;                          // [312]: offset batch * 2 * n_items
+  const int32_t* uids; const int32_t* keep_off;        // [batch], [batch + 1]
+  const int64_t* indptr; const int32_t* indices;       // CSR of positives, column-sorted
+  uint8_t* keep;                                       // [keep_off[batch]]
+  int batch, n_items, ups, n_cta;                      // ups = batch rows per CTA, n_cta = ceil(batch / ups)
+  uint64_t threshold;                                  // ceil(q * 2^53): a draw below it drops the entry
+};
+int launch_mt_keep(drb_ctx* ctx, const MtKeepArgs& a);
+
 // ------------------------------------------------------------------ sampled.cu
 // Sampled-output layer (extension for configs[4], see sampled.cu / oracle.cdae.CDAESampledOracle): forward + backward of
 // the output layer over each sampled user's positives and n_groups x neg_per_group drawn items.

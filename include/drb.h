@@ -85,6 +85,10 @@ int drb_rng_random_fill(drb_rng* rng, int64_t n, double* out);
 int drb_rng_sample_indices(drb_rng* rng, int64_t n, int64_t k, int64_t* out);
 int drb_rng_shuffle_i64(drb_rng* rng, int64_t n, int64_t* x);
 /* state[0..623] = mt, state[624] = index (same layout as random.getstate()[1]) */
+/* The next 624 untempered output words (generator not advanced) / the inverse; drb_rng_skip discards n outputs. */
+int drb_rng_window(const drb_rng* rng, uint32_t window[624]);
+int drb_rng_set_window(drb_rng* rng, const uint32_t window[624]);
+int drb_rng_skip(drb_rng* rng, int64_t n_outputs);
 int drb_rng_getstate(const drb_rng* rng, uint32_t state[625]);
 int drb_rng_setstate(drb_rng* rng, const uint32_t state[625]);
 
@@ -113,6 +117,25 @@ int drb_cdae_corruption_keep_mt(drb_rng* rng, const int32_t* uids, int32_t batch
                                 const int64_t* csr_indptr, const int32_t* csr_indices,
                                 int32_t* keep_off /* [batch+1] */, uint8_t* keep /* [sum deg] */,
                                 int64_t keep_capacity /* bytes available in keep; DRB_E_INVALID if too small */);
+/* Device replay of the same stream (rng_mode='mt19937_device').  MT19937 is GF(2)-linear: a block of the stream J outputs
+ * ahead is a fixed XOR-combination (the bits of t^J mod phi(t), phi = the characteristic polynomial) of the first
+ * 19937 + 623 words of the stream.  drb_mtjump_create computes those polynomials once per (n_items, batch) for the
+ * offsets seg_len * p, p = 1 .. n_seg (host, seconds); drb_mtjump_polys copies them out ([n_seg][312] uint64);
+ * drb_mtjump_apply_host is the host reference of one jump (tests). */
+typedef struct drb_mtjump drb_mtjump;
+int drb_mtjump_create(int64_t seg_len, int32_t n_seg, drb_mtjump** out);
+int drb_mtjump_destroy(drb_mtjump* j);
+int drb_mtjump_polys(const drb_mtjump* j, uint64_t* out);
+int drb_mtjump_apply_host(const drb_mtjump* j, int32_t p, const uint32_t* window_in, uint32_t* window_out);
+/* One step of the stream on the device: keep[keep_off[b] + j] for every stored positive j of sampled user uids[b], exactly
+ * what drb_cdae_corruption_keep_mt writes, from the 624-word window the step starts at (drb_rng_window); window_out
+ * receives the window after batch * 2 * n_items outputs.  polys: (ceil(batch / users_per_cta) - 1) polynomials of the
+ * offsets p * users_per_cta * 2 * n_items (drb_mtjump_create(users_per_cta * 2 * n_items, ...)), poly_total: the offset
+ * batch * 2 * n_items; threshold = ceil(q * 2^53).  All pointers are device pointers; users_per_cta <= 64. */
+int drb_mt_keep_device(drb_ctx* ctx, const uint32_t* window_in, uint32_t* window_out, const uint64_t* polys,
+                       const uint64_t* poly_total, const int32_t* uids, const int32_t* keep_off, const int64_t* csr_indptr,
+                       const int32_t* csr_indices, uint8_t* keep, int32_t batch, int32_t n_items, int32_t users_per_cta,
+                       uint64_t threshold);
 /* keep_off only (prefix of the sampled users' degrees), for the counter-based (philox) mask mode */
 int drb_batch_offsets(const int32_t* uids, int32_t batch, const int64_t* csr_indptr, int32_t* keep_off);
 
