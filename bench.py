@@ -219,8 +219,10 @@ def cdae_config(cfg, n_gpus, parallelism=None, flush=False):
                         f"{cfg['n_users']}x{cfg['n_items']} / {cfg['nnz']} interactions ({cfg['origin']})",
             'batch_per_gpu': cfg['batch'], 'global_batch': cfg['batch'] * n_gpus, 'neg_ratio': cfg['neg_ratio'],
             'label_mode': 'batch_mean', 'adam': 'dense, per-variable step counter',
-            'mask_rng': 'philox (device; documented deviation from the MT19937 stream)' if cfg['mask'] == 'philox'
-            else 'mt19937 (bit-exact replay of cdae.py:63-64 on the host, keep bytes uploaded)',
+            'mask_rng': {'philox': 'philox (device; documented deviation from the MT19937 stream)',
+                         'mt19937': 'mt19937 (bit-exact replay of cdae.py:63-64 on the host, keep bytes uploaded)',
+                         'mt19937_device': 'mt19937 (bit-exact replay of cdae.py:63-64 on the device by jump-ahead, '
+                                           'one k_mt_keep launch per step)'}[cfg['mask']],
             'item_popularity': f"zipf a={cfg['zipf_a']}" if cfg['zipf_a'] else 'uniform',
             'parallelism': parallelism or f'dp{n_gpus}',
             'l2': ('per-step working set (params + Adam state + dz ~ 2.7 GB) exceeds the 126 MB L2; no flush needed'
@@ -1021,11 +1023,15 @@ def main():
     ap.add_argument('--no-dp-parity', action='store_true')
     ap.add_argument('--scaling', default='weak', choices=['weak', 'strong'],
                     help='c3, N>1: weak = 4096 users per GPU (default, the driver\'s curve); strong = 4096 users globally')
+    ap.add_argument('--mask', default=None, choices=['philox', 'mt19937', 'mt19937_device'],
+                    help='CDAE workloads: corruption-mask generator (default: philox at c3, the host MT19937 replay at c1)')
     ap.add_argument('--c5-scale', type=float, default=1.0, help='c5: shrink users / items / interactions by this factor')
     ap.add_argument('--parallel', default='data', choices=['data', 'items'],
                     help='N>1: data = replicated weights + gradient all-reduce; items = item-sharded weights')
     args = ap.parse_args()
     cfg = dict(WORKLOADS[args.workload])
+    if args.mask and 'mask' in cfg:
+        cfg['mask'] = args.mask
     world = int(os.environ.get('WORLD_SIZE', '1'))
     if args.scaling == 'strong' and cfg['model'] == 'cdae' and world > 1:
         assert cfg['batch'] % world == 0
