@@ -39,7 +39,8 @@ C2 = dict(name='c2', title='dmf_ml1m_shape', origin='BASELINE.json configs[1]', 
           nnz=1_000_000, towers=[64, 32], batch=256, lr=1e-3, reg=1e-4, neg_ratio=5, seed=10, zipf_a=0.0)
 C4S = dict(C3, name='c4_sampled', title='ranking_evaluation_leave1out_100neg', origin='BASELINE.json configs[3]',
            model='rank_sampled', n_neg=100, k=10)
-C4F = dict(C3, name='c4_full', title='full_catalog_top100', origin='BASELINE.json configs[3]', model='topk', k=100)
+C4F = dict(C3, name='c4_full', title='full_catalog_top100', origin='BASELINE.json configs[3]', model='topk', k=100,
+           score_batch=int(os.environ.get('DRB_BENCH_SCORE_BATCH', 16384)))   # users per scoring block (fit(score_batch=))
 C5 = dict(name='c5', title='cdae_10m_x_1m_item_sharded', origin='BASELINE.json configs[4]', model='cdae_sharded',
           n_users=10_000_000, n_items=1_000_000, nnz=1_000_000_000, hidden=256, batch=4096, q=0.2, lr=1e-3, reg=1e-3,
           seed=10, zipf_a=1.0, neg_total=1024)
@@ -639,7 +640,7 @@ def rank_setup(cfg, D, arrays):
     t_split = time.perf_counter() - t0
     train.assign_internal_ids()
     m = drb.CDAE(hidden_factors=cfg['hidden'], seed=cfg['seed'], verbose=False, rng_mode='philox', device=str(D.dev))
-    m.fit(train, epochs=3, batch_size=4096)
+    m.fit(train, epochs=3, batch_size=4096, score_batch=cfg.get('score_batch', 0))
     return train, test, m, t_split
 
 

@@ -952,10 +952,13 @@ int drb_cdae_rank_candidates(drb_cdae* m, const int32_t* uids, int32_t n, const 
 }
 
 // Scratch of the tensor-core top-k, carved from the dz workspace (max_batch x items_pad floats):
-//   lists [B][cap] u64 | seen bitmap [B][words] u32 | cnt [B] | tau [B] | fallback: count, users [FB], rows [FB][items_pad]
+//   lists [B][cap] u64 | seen bitmap [B][words] u32 | cnt [B] | tau [B] | tau_z [B] | fallback: count, users [FB],
+//   rows [FB][items_pad]
 struct TopkScratch {
-  uint64_t* lists; uint32_t* bits; int32_t* cnt; uint32_t* tau; int32_t* fb_count; int32_t* fb_users; float* fb_rows;
+  uint64_t* lists; uint32_t* bits; int32_t* cnt; uint32_t* tau; float* tau_z; int32_t* fb_count; int32_t* fb_users;
+  float* fb_rows;
   int cap, fb_max; bool ok;
+  int n_stages; int bounds[12];      // item ranges [bounds[i-1], bounds[i]) of the filter passes (bounds[-1] = 0)
 };
 static constexpr int kTopkFallbackRows = 32;
 
@@ -967,6 +970,7 @@ static TopkScratch topk_scratch(drb_cdae* m, int cap) {
   t.bits = c.take<uint32_t>(B * words);
   t.cnt = c.take<int32_t>(B);
   t.tau = c.take<uint32_t>(B);
+  t.tau_z = c.take<float>(B);
   t.fb_count = c.take<int32_t>(64);
   t.fb_users = c.take<int32_t>(kTopkFallbackRows);
   t.fb_rows = c.take<float>((int64_t)kTopkFallbackRows * m->L.items_pad);
@@ -976,7 +980,7 @@ static TopkScratch topk_scratch(drb_cdae* m, int cap) {
 }
 
 // Full-catalog top-k on the tensor cores for one block of users (see umma_score.cu for the selection scheme).
-static int cdae_topk_umma_chunk(drb_cdae* m, const TopkScratch& S, int n_s, const int32_t* uids, int c, int k, int novelty,
+static int cdae_topk_umma_chunk(drb_cdae* m, const TopkScratch& S, const int32_t* uids, int c, int k, int novelty,
                                 int32_t* out_iid, float* out_score, int32_t* n_out) {
   drb_ctx* ctx = m->ctx;
   CdaeWs& w = m->ws;
@@ -1002,13 +1006,21 @@ static int cdae_topk_umma_chunk(drb_cdae* m, const TopkScratch& S, int n_s, cons
   UmmaOperands o{w.h_hi, w.h_lo, m->half ? m->ldh : ld, w.w2t_hi, w.w2t_lo, m->half ? m->ldh : ld, I};
   if (m->half) { o.half = true; o.out_scale = 1.0f / DRB_H_F16_SCALE; o.out_scale_dev = w.loss_scalar + 33; }
   const float* b2 = m->d.params + m->L.off_b2;
-  // pass 1: the first n_s items, everything unseen is listed; tau = k-th best of the slice
-  if ((r = launch_umma_score_filter(ctx, o, c, I, 0, n_s, ld, b2, bits, words, S.tau, S.cnt, S.lists, S.cap))) return r;
-  if ((r = launch_select_lists(ctx, S.lists, S.cap, S.cnt, S.tau, k, false, nullptr, nullptr, nullptr, c))) return r;
-  // pass 2: the rest of the catalog, only scores >= tau are listed; then the final order
-  if ((r = launch_umma_score_filter(ctx, o, c, I, n_s, I, ld, b2, bits, words, S.tau, S.cnt, S.lists, S.cap))) return r;
-  if ((r = launch_select_lists(ctx, S.lists, S.cap, S.cnt, S.tau, k, true, out_iid, out_score, n_out, c))) return r;
-  // users whose list overflowed (n_out == -1): exact fp32 scores + radix select, on the device, no host round trip
+  // Stage 0: the first slice, every unseen item is listed; tau = the k-th best of the slice.  Every further stage
+  // lists only what reaches the current tau (a logit pre-filter decides for most elements, umma_score.cu) and the
+  // select that follows tightens tau to the k-th best of everything seen so far: with item ranges growing
+  // geometrically each stage adds about (growth - 1) * k keys per user.  The last select emits the ranked lists.
+  for (int st = 0, lo = 0; st < S.n_stages; lo = S.bounds[st], st++) {
+    const bool last = st == S.n_stages - 1;
+    if ((r = launch_umma_score_filter(ctx, o, c, I, lo, S.bounds[st], ld, b2, bits, words, S.tau, st ? S.tau_z : nullptr,
+                                      S.cnt, S.lists, S.cap)))
+      return r;
+    if ((r = launch_select_lists(ctx, S.lists, S.cap, S.cnt, S.tau, S.tau_z, k, last, last ? out_iid : nullptr,
+                                 last ? out_score : nullptr, last ? n_out : nullptr, S.fb_users, S.fb_count, S.fb_max, c)))
+      return r;
+  }
+  // users whose list overflowed (n_out == -1, scratch rows claimed by the last select): exact fp32 scores + radix
+  // select, on the device, no host round trip
   TopkArgs t{};
   t.ld = m->L.items_pad; t.n_items = I; t.uids = uids;
   t.seen_indptr = m->d.seen_indptr; t.seen_indices = m->d.seen_indices; t.novelty = novelty; t.k = k;
@@ -1025,18 +1037,32 @@ static int cdae_topk_impl(drb_cdae* m, const int32_t* uids, int32_t n, int32_t k
     return drb_fail(DRB_E_STATE, "drb_cdae_topk: a model created for sampled-output training carries no score workspace");
   if (k < 1 || k > 2048) return drb_fail(DRB_E_INVALID, "drb_cdae_topk: k must be in [1, 2048]");
   // Tensor-core path: wide catalogs, blocks of >= 128 users.  DRB_TOPK_PATH=ffma forces the exact-fp32 GEMM + radix
-  // select path, DRB_TOPK_CAP / DRB_TOPK_NS shrink the list capacity / first slice (tests of the overflow fallback).
+  // select path; DRB_TOPK_CAP / DRB_TOPK_NS / DRB_TOPK_GROWTH shrink the list capacity / set the first slice / the growth
+  // of the item ranges from stage to stage (tests of the overflow fallback: a huge growth = two passes).
   const char* path_env = getenv("DRB_TOPK_PATH");
   const int cap_env = getenv("DRB_TOPK_CAP") ? atoi(getenv("DRB_TOPK_CAP")) : 0;
   const int ns_env = getenv("DRB_TOPK_NS") ? atoi(getenv("DRB_TOPK_NS")) : 0;
+  const int growth = getenv("DRB_TOPK_GROWTH") ? std::max(2, atoi(getenv("DRB_TOPK_GROWTH"))) : 3;
   const int I = m->d.n_items;
   const int cap = cap_env ? cap_env : 4096;
-  int n_s = ns_env ? ns_env : (int)drb_round_up(std::max<int64_t>(2048, 3ll * k * I / cap), 256);
+  // first slice: at least 4 k items (its k-th best is then a usable threshold); a stage over (growth - 1) times the
+  // items seen so far is expected to add (growth - 1) k keys to the k kept ones, three times that must fit the list
+  const int n_s = ns_env ? ns_env : (int)drb_round_up(std::max<int64_t>(1024, 4ll * k), 256);
   TopkScratch S{};
   bool fast = !exact_only && m->use_umma && n >= 128 && !(path_env && !strcmp(path_env, "ffma")) && (cap & (cap - 1)) == 0 &&
               n_s + k <= cap && n_s < I;
-  if (fast && !ns_env && !cap_env) fast = I >= 8192 && n_s <= I / 3;
+  if (fast && !ns_env && !cap_env) fast = I >= 8192 && n_s <= I / 3 && (3ll * (growth - 1) + 1) * k <= cap;
   if (fast) { S = topk_scratch(m, cap); fast = S.ok; }
+  if (fast) {
+    int64_t b = n_s;
+    while (true) {
+      S.bounds[S.n_stages++] = (int)b;
+      if (b >= I) break;
+      int64_t nx = drb_round_up(b * growth, 128);
+      if (S.n_stages == 11 || nx + nx / 4 >= I) nx = I;     // no short last stage
+      b = nx;
+    }
+  }
   if (fast) {   // hi/lo split of W' once per call (the weights do not change while scoring)
     int r;
     if (m->half) {
@@ -1054,7 +1080,7 @@ static int cdae_topk_impl(drb_cdae* m, const int32_t* uids, int32_t n, int32_t k
     const int c = std::min(m->d.max_batch, n - o);
     int r;
     if (fast && c >= 128) {
-      if ((r = cdae_topk_umma_chunk(m, S, n_s, uids + o, c, k, novelty, out_iid + (int64_t)o * k,
+      if ((r = cdae_topk_umma_chunk(m, S, uids + o, c, k, novelty, out_iid + (int64_t)o * k,
                                     out_score + (int64_t)o * k, n_out + o)))
         return r;
       continue;

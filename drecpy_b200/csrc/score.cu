@@ -286,15 +286,29 @@ __device__ void radix_select_u32(int n, int need, KeyFn key, int* hist, SelectSt
   }
 }
 
+// The score filter (umma_score.cu) forms a score as rcp.approx(1 + ex2.approx(z * -log2 e)) and lists it when its
+// orderable value reaches tau.  This returns a logit below which that cannot happen, so that the filter can discard
+// most elements on the logit alone: the approximate sigmoid is within 2^-17 relative of the true one wherever it is
+// not saturated (ex2.approx 2^-22, rcp.approx 2^-23, the rounded exponent argument |arg| * 2^-24 * ln 2 for |arg| up
+// to 126), the bound takes 2^-16 and rounds the logit down.
+__device__ __forceinline__ float logit_lower_bound(uint32_t tau_ord) {
+  const float pt = __uint_as_float(tau_ord & 0x7fffffffu);      // scores are positive: ord = bits | 0x80000000
+  if (!(pt > 0.f)) return __int_as_float(0xff800000);
+  const double pp = (double)fminf(pt, 1.0f) * (1.0 - 1.0 / 65536.0);
+  const float z = (float)log(pp / (1.0 - pp));
+  return z - 1e-5f * fabsf(z) - 1e-6f;
+}
+
 // One CTA per user over the user's list of 64-bit keys (orderable score << 32 | iid), copied to shared memory once.
 //   final == 0 (after the first item slice): radix-selects tau = the k-th best score, keeps the keys >= tau at the head
 //               of the list (unordered) and publishes tau (0 while fewer than k exist: the next pass takes everything);
 //   final != 0: radix-selects the k best keys -- score first, item id among equal scores, i.e. heapq.nlargest on
 //               (score, iid) tuples (cdae.py:102-103) -- sorts those k and emits them.
 // A list that overflowed its capacity marks the user (n_out = -1) for the exact fallback.
-__global__ void __launch_bounds__(256) k_select_lists(uint64_t* lists, int cap, int32_t* cnt, uint32_t* tau_ord, int k,
-                                                      int final, int P, int32_t* out_iid, float* out_score,
-                                                      int32_t* n_out) {
+__global__ void __launch_bounds__(256) k_select_lists(uint64_t* lists, int cap, int32_t* cnt, uint32_t* tau_ord,
+                                                      float* tau_z, int k, int final, int P, int32_t* out_iid,
+                                                      float* out_score, int32_t* n_out, int32_t* fb_users,
+                                                      int32_t* fb_count, int fb_max) {
   extern __shared__ uint64_t sm_keys[];            // [cap] the list, then [P] the selected keys (final)
   __shared__ int hist[256];
   __shared__ SelectState st;
@@ -304,8 +318,13 @@ __global__ void __launch_bounds__(256) k_select_lists(uint64_t* lists, int cap, 
   uint64_t* list = lists + (int64_t)u * cap;
   if (c > cap) {                    // overflow: the list is incomplete, this user goes through the exact fallback
     if (threadIdx.x == 0) {
-      if (final) n_out[u] = -1;
-      else tau_ord[u] = 0xffffffffu;         // nothing more is appended for this user; cnt stays > cap
+      if (final) {                  // claims a scratch row of the exact fallback (k_fallback_scores); beyond fb_max
+        n_out[u] = -1;              // rows n_out stays -1 and the host re-runs the user
+        const int slot = atomicAdd(fb_count, 1);
+        if (slot < fb_max) fb_users[slot] = u;
+      }
+      else { tau_ord[u] = 0xffffffffu; tau_z[u] = __int_as_float(0x7f800000); }   // nothing more is appended for this
+                                                                                  // user; cnt stays > cap
     }
     return;
   }
@@ -315,7 +334,7 @@ __global__ void __launch_bounds__(256) k_select_lists(uint64_t* lists, int cap, 
   auto ord_key = [&](int i, uint32_t* out) { *out = (uint32_t)(sm_keys[i] >> 32); return true; };
   if (!final) {
     if (c < k) {                    // fewer than k so far: keep everything, no threshold yet
-      if (threadIdx.x == 0) tau_ord[u] = 0u;
+      if (threadIdx.x == 0) { tau_ord[u] = 0u; tau_z[u] = __int_as_float(0xff800000); }
       return;
     }
     radix_select_u32(c, k, ord_key, hist, &st);
@@ -325,7 +344,7 @@ __global__ void __launch_bounds__(256) k_select_lists(uint64_t* lists, int cap, 
       if ((uint32_t)(key >> 32) >= t32) list[atomicAdd(&n_sel, 1)] = key;
     }
     __syncthreads();
-    if (threadIdx.x == 0) { cnt[u] = n_sel; tau_ord[u] = t32; }
+    if (threadIdx.x == 0) { cnt[u] = n_sel; tau_ord[u] = t32; tau_z[u] = logit_lower_bound(t32); }
     return;
   }
   uint64_t* sel = sm_keys + cap;
@@ -364,20 +383,15 @@ __global__ void __launch_bounds__(256) k_select_lists(uint64_t* lists, int cap, 
   emit_sorted(sel, P, k, out_iid + (int64_t)u * k, out_score + (int64_t)u * k, n_out + u);
 }
 
-// Exact fallback for users whose candidate list overflowed: claims a scratch row, fills it with the user's scores
+// Exact fallback for users whose candidate list overflowed: fills the user's claimed scratch row with the scores
 // sigmoid(h_u . W'_i + b'_i) over the whole catalog (one warp per item, fp32 FMA); k_topk (indirect) then ranks the row.
-__global__ void __launch_bounds__(256) k_fallback_scores(const int32_t* n_out, int n_users, const float* h, int ld_h,
-                                                         const float* table, int ld_t, const float* bias, int width,
-                                                         int n_items, float* rows, int ld_rows, int32_t* fb_users,
-                                                         int32_t* fb_count, int fb_max) {
-  __shared__ int slot_s;
-  const int u = blockIdx.x;
-  if (u >= n_users || n_out[u] != -1) return;
-  if (threadIdx.x == 0) slot_s = atomicAdd(fb_count, 1);
-  __syncthreads();
-  const int slot = slot_s;
-  if (slot >= fb_max) return;      // more overflows than scratch rows: n_out stays -1 and the host reports it
-  if (threadIdx.x == 0) fb_users[slot] = u;
+__global__ void __launch_bounds__(256) k_fallback_scores(const float* h, int ld_h, const float* table, int ld_t,
+                                                         const float* bias, int width, int n_items, float* rows,
+                                                         int ld_rows, const int32_t* fb_users, const int32_t* fb_count,
+                                                         int fb_max) {
+  const int slot = blockIdx.x;       // one CTA per claimed scratch row (k_select_lists claims them)
+  if (slot >= min(*fb_count, fb_max)) return;
+  const int u = fb_users[slot];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const float* ur = h + (int64_t)u * ld_h;
   float* row = rows + (int64_t)slot * ld_rows;
@@ -429,8 +443,9 @@ int launch_topk(drb_ctx* ctx, const TopkArgs& a, int n) {
   return DRB_OK;
 }
 
-int launch_select_lists(drb_ctx* ctx, uint64_t* lists, int cap, int32_t* cnt, uint32_t* tau_ord, int k, bool final,
-                        int32_t* out_iid, float* out_score, int32_t* n_out, int n) {
+int launch_select_lists(drb_ctx* ctx, uint64_t* lists, int cap, int32_t* cnt, uint32_t* tau_ord, float* tau_z, int k,
+                        bool final, int32_t* out_iid, float* out_score, int32_t* n_out, int32_t* fb_users, int32_t* fb_count,
+                        int fb_max, int n) {
   if (n <= 0) return DRB_OK;
   if (cap < 32 || (cap & (cap - 1)) || cap > 8192) return drb_fail(DRB_E_INVALID, "select_lists: cap must be a power of two in [32, 8192]");
   if (k < 1 || k > 2048) return drb_fail(DRB_E_INVALID, "select_lists: k must be in [1, 2048]");
@@ -443,7 +458,7 @@ int launch_select_lists(drb_ctx* ctx, uint64_t* lists, int cap, int32_t* cnt, ui
   const int P = next_pow2(k);
   drb_prof_scope prof_(ctx, final ? "k_select_lists_final" : "k_select_lists_tau");
   k_select_lists<<<n, 256, (size_t)(cap + (final ? P : 0)) * sizeof(uint64_t), ctx->stream>>>(
-      lists, cap, cnt, tau_ord, k, final ? 1 : 0, P, out_iid, out_score, n_out);
+      lists, cap, cnt, tau_ord, tau_z, k, final ? 1 : 0, P, out_iid, out_score, n_out, fb_users, fb_count, fb_max);
   DRB_LAUNCH_CHECK(ctx, "k_select_lists");
   return DRB_OK;
 }
@@ -453,8 +468,8 @@ int launch_topk_fallback(drb_ctx* ctx, const TopkArgs& a, int n, const float* h,
   if (n <= 0) return DRB_OK;
   {
     drb_prof_scope prof_(ctx, "k_fallback_scores");
-    k_fallback_scores<<<n, 256, 0, ctx->stream>>>(a.n_out, n, h, ld_h, table, ld_t, bias, width, a.n_items, rows, a.ld,
-                                                  fb_users, fb_count, fb_max);
+    k_fallback_scores<<<fb_max, 256, 0, ctx->stream>>>(h, ld_h, table, ld_t, bias, width, a.n_items, rows, a.ld, fb_users,
+                                                       fb_count, fb_max);
     DRB_LAUNCH_CHECK(ctx, "k_fallback_scores");
   }
   TopkArgs t = a;

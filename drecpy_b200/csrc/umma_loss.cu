@@ -51,7 +51,8 @@ struct LossParams {
                                            // formed it, row-major [M][ldz]; NULL in production
   int debug;   // DRB_LOSS_DEBUG bit mask (profiling experiments only, results are wrong): 1 = first 16-row chunk of
                // each epilogue warp only, 2 = skip TMA + MMA, 4 = skip the dz stores, 8 = skip the B_lo loads, 16 = skip the MMAs,
-               // 32 = no lg2 in the fast epilogue form
+               // 32 = no lg2 in the fast epilogue form; 64 (results stay right) = the five-MUFU fast form of round 2's
+               // first half instead of the 2.5-MUFU one
 };
 
 __device__ __forceinline__ float fast_ex2(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
@@ -266,7 +267,28 @@ k_umma_cdae_loss(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
           for (int j = 0; j < 16; j++) amax = fmaxf(amax, fabsf(fmaf(__uint_as_float(r[j]), osc2, nb2)));
           fast = !__any_sync(0xffffffffu, !fast || amax > 22.0f);
         }
-        if (fast) {
+        if (fast && !(p.debug & 64)) {
+          // One reciprocal per element: with s = 1 + e, t1 = 1 + eps s, t2 = e + eps s and R = 1 / (s t1 t2):
+          //   p = 1/s = R t1 t2,  da = p + eps = t1/s,  db = 1 - p + eps = t2/s,  p (1-p) / (da db) = e / (t1 t2) = e s R.
+          // The log terms of four elements are one lg2 of their product (da, db >= 3.4e-7 here: no underflow).
+          float pa = 1.0f, pb = 1.0f;
+#pragma unroll
+          for (int j = 0; j < 16; j++) {
+            const float e = fast_ex2(fmaf(__uint_as_float(r[j]), osc2, nb2));
+            const float s1 = 1.0f + e;
+            const float t12 = fmaf(KERAS_EPS, s1, 1.0f) * fmaf(KERAS_EPS, s1, e);
+            const float R = fast_rcp(s1 * t12);
+            const float pr = R * t12;
+            const float da = pr + KERAS_EPS, db = (1.0f + KERAS_EPS) - pr;
+            pa *= da; pb *= db;
+            if ((j & 3) == 3) {
+              sum_la += fast_lg2(pa); sum_lb += fast_lg2(pb);
+              pa = 1.0f; pb = 1.0f;
+            }
+            const float num = fmaf(tgt_c, -(1.0f + 2.0f * KERAS_EPS), da);
+            lo[j] = (num * e) * (R * (s1 * gsc));
+          }
+        } else if (fast) {
 #pragma unroll
           for (int j = 0; j < 16; j++) {
             const float e = fast_ex2(fmaf(__uint_as_float(r[j]), osc2, nb2));

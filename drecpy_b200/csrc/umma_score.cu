@@ -36,7 +36,8 @@ struct ScoreSmem {
   static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
   static constexpr int STAGES = 192 * 1024 / STAGE_BYTES;
   static constexpr int BAR_BYTES = 256;
-  static constexpr int TAU_BYTES = SC_EPI_WARPS * (BN / 4) * 8;   // per epilogue warp: (threshold, seen word) of its users
+  // per epilogue warp and user of its column quarter: (exact threshold, seen word) + the conservative logit threshold
+  static constexpr int TAU_BYTES = SC_EPI_WARPS * (BN / 4) * 12;
   static constexpr int TOTAL = STAGES * STAGE_BYTES + 1024 + BAR_BYTES + TAU_BYTES;
 };
 
@@ -47,12 +48,14 @@ struct ScoreParams {
   const float* bias;                       // b' [n_items]
   const uint32_t* seen_bits; int words_per_row;   // NULL (no novelty filter) or [M][words_per_row]
   const uint32_t* tau_ord;                 // [M] orderable-score threshold per user (0 = take everything)
+  const float* tau_z;                      // [M] logit below which no score can reach tau_ord (k_select_lists), or NULL:
+                                           // no pre-filter (first slice: every unseen item is listed)
   int32_t* cnt;                            // [M] entries appended so far (may exceed cap: overflow)
   uint64_t* lists; int cap;                // [M][cap]
   int m_tiles, n_tiles;
   float out_scale; const float* out_scale_dev;   // H: accumulator -> logit (undoes the fp16 operand scaling)
   int debug;   // DRB_SCORE_DEBUG bit mask (profiling experiments only, results are wrong): 1 = no appends, 2 = no seen
-               // bitmap loads, 4 = no MMAs, 8 = no sigmoid
+               // bitmap loads, 4 = no MMAs, 8 = nothing passes the logit pre-filter
 };
 
 __device__ __forceinline__ float sc_ex2(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
@@ -85,6 +88,7 @@ k_umma_score_filter(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
   const uint32_t tmem_ptr_addr = bars + 8u * (2 * S::STAGES + 4);
   volatile uint32_t* tmem_ptr_generic = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_ptr_addr - raw));
   uint2* tau_smem = reinterpret_cast<uint2*>(smem_raw + (bars + S::BAR_BYTES - raw));
+  float* tz_smem = reinterpret_cast<float*>(tau_smem + SC_EPI_WARPS * (BN / 4));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nkb = (p.Kred + BK - 1) / BK;
@@ -192,6 +196,7 @@ k_umma_score_filter(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
     const int q = warp & 3, cq = (warp - 2) >> 2;
     constexpr int CW = BN / 4;                    // users of this warp per tile
     uint2* my_tau = tau_smem + (warp - 2) * CW;    // .x = threshold, .y = the user's seen-bitmap word for this item block
+    float* my_tz = tz_smem + (warp - 2) * CW;      // logit pre-filter threshold of the same users
     const uint32_t lt_mask = (1u << lane) - 1u;
     const float osc = H ? p.out_scale * (p.out_scale_dev ? __ldg(p.out_scale_dev) : 1.0f) : 1.0f;
     float nbias;
@@ -210,18 +215,22 @@ k_umma_score_filter(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
       const float bias = nbias;
       fetch_bias(t + unit_stride);
       // thresholds and seen-bitmap words of this warp's users, fetched before the accumulator is waited for (users
-      // beyond the block never pass)
+      // beyond the block never pass: their pre-filter threshold is +inf)
       __syncwarp();
 #pragma unroll
       for (int c = lane; c < CW; c += 32) {
         const int row = r0 + cq * CW + c;
         uint2 v = make_uint2(0xffffffffu, 0u);
+        float tz = __int_as_float(0x7f800000);
         if (row < p.M) {
           v.x = __ldg(p.tau_ord + row);
           if (p.seen_bits && !(p.debug & 2) && ib < p.words_per_row)
             v.y = __ldg(p.seen_bits + (int64_t)row * p.words_per_row + ib);
+          tz = p.tau_z ? __ldg(p.tau_z + row) : __int_as_float(0xff800000);
+          if (p.debug & 8) tz = __int_as_float(0x7f800000);
         }
         my_tau[c] = v;
+        my_tz[c] = tz;
       }
       __syncwarp();
       mbar_wait(tfull_bar(as), (tl >> 1) & 1);
@@ -237,18 +246,32 @@ k_umma_score_filter(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
 #pragma unroll
         for (int j = 0; j < 16; j++) r[j] = rn[j];
         if (cl + 16 < CW) tmem_ld16_issue(tbase + cl + 16, rn);
-        uint32_t bal[16];
-        // 1. score, knock-out, threshold test: r[j] becomes the orderable score, bal[j] the lanes that pass for user j
+        float tz[16];
+#pragma unroll
+        for (int j = 0; j < 16; j += 4) {
+          const float4 v = *reinterpret_cast<const float4*>(my_tz + cl + j);      // broadcast reads
+          tz[j] = v.x; tz[j + 1] = v.y; tz[j + 2] = v.z; tz[j + 3] = v.w;
+        }
+        uint32_t bal[16], anyb = 0u;
+        // 1. Pre-filter on the logit: one fma, one compare and one vote per element.  The exact test -- the fp32 sigmoid
+        //    value as an orderable integer against the user's threshold, the seen-bitmap knock-out -- runs only for the
+        //    (user, 32-item) rows in which some lane passes; bal[j] = the lanes that really pass for user j, r[j]
+        //    becomes the orderable score there.
 #pragma unroll
         for (int j = 0; j < 16; j++) {
           const float z = H ? fmaf(__uint_as_float(r[j]), osc, bias) : __uint_as_float(r[j]) + bias;
-          const float pr = (p.debug & 8) ? fabsf(z) : sc_rcp(1.0f + sc_ex2(z * -1.4426950408889634f));   // sigmoid, > 0
-          const uint32_t ord = __float_as_uint(pr) | 0x80000000u;               // f2ord of a non-negative float
-          const uint2 ts = my_tau[cl + j];                                      // broadcast read
-          const bool pass = item_ok && (row + j < p.M) && !((ts.y >> lane) & 1u) && (ord >= ts.x);
-          r[j] = ord;
-          bal[j] = (p.debug & 1) ? 0u : __ballot_sync(0xffffffffu, pass);
+          bal[j] = 0u;
+          if (__any_sync(0xffffffffu, z >= tz[j])) {
+            const float pr = sc_rcp(1.0f + sc_ex2(z * -1.4426950408889634f));       // sigmoid, > 0
+            const uint32_t ord = __float_as_uint(pr) | 0x80000000u;                 // f2ord of a non-negative float
+            const uint2 ts = my_tau[cl + j];                                        // broadcast read
+            const bool pass = item_ok && !((ts.y >> lane) & 1u) && (ord >= ts.x);
+            r[j] = ord;
+            bal[j] = (p.debug & 1) ? 0u : __ballot_sync(0xffffffffu, pass);
+            anyb |= bal[j];
+          }
         }
+        if (anyb == 0u) continue;                  // warp-uniform
         // 2. one atomicAdd per (warp, user) reserves the slots of the passing lanes (all issued before any is consumed)
         int slot[16];
 #pragma unroll
@@ -342,12 +365,12 @@ int run_score(drb_ctx* ctx, const UmmaOperands& o, ScoreParams p, int n_items) {
 
 int launch_umma_score_filter(drb_ctx* ctx, const UmmaOperands& o, int n_users, int n_items, int item_begin, int item_end,
                              int Kred, const float* bias, const uint32_t* seen_bits, int words_per_row,
-                             const uint32_t* tau_ord, int32_t* cnt, uint64_t* lists, int cap) {
+                             const uint32_t* tau_ord, const float* tau_z, int32_t* cnt, uint64_t* lists, int cap) {
   if (item_begin % 128 != 0 || item_end > n_items || item_begin >= item_end)
     return drb_fail(DRB_E_INVALID, "score_filter: bad item range [%d, %d) of %d", item_begin, item_end, n_items);
   ScoreParams p{};
   p.M = n_users; p.item_begin = item_begin; p.item_end = item_end; p.Kred = Kred; p.bias = bias;
-  p.seen_bits = seen_bits; p.words_per_row = words_per_row; p.tau_ord = tau_ord; p.cnt = cnt; p.lists = lists; p.cap = cap;
+  p.seen_bits = seen_bits; p.words_per_row = words_per_row; p.tau_ord = tau_ord; p.tau_z = tau_z; p.cnt = cnt; p.lists = lists; p.cap = cap;
   p.debug = getenv("DRB_SCORE_DEBUG") ? atoi(getenv("DRB_SCORE_DEBUG")) : 0;
   p.out_scale = o.out_scale; p.out_scale_dev = o.out_scale_dev;
   if (o.half) {

@@ -101,14 +101,15 @@ def test_tensor_core_topk_matches_oracle(novelty):
 
 
 def test_tensor_core_topk_overflow_fallback(monkeypatch):
-    """Candidate lists are bounded.  With a tiny capacity (256 keys, first slice 128 items) most users overflow: up to
-    32 per block are re-done on the device by the exact path, the rest come back flagged and topk_batch re-runs them
-    through drb_cdae_topk_exact.  The answer does not change."""
+    """Candidate lists are bounded.  With a tiny capacity (256 keys, first slice 128 items, two passes only) most users
+    overflow: up to 32 per block are re-done on the device by the exact path, the rest come back flagged and topk_batch
+    re-runs them through drb_cdae_topk_exact.  The answer does not change."""
     ds, m, o = _setup(heavy_user=False)
     uids = np.arange(m.n_users, dtype=np.int32)
     ref_i, ref_s, ref_n = m.topk_batch(uids, 100, novelty=True, exact=True)
     monkeypatch.setenv('DRB_TOPK_CAP', '256')
     monkeypatch.setenv('DRB_TOPK_NS', '128')
+    monkeypatch.setenv('DRB_TOPK_GROWTH', '1000')       # one filtered pass over everything after the first slice
     l0 = m.launch_count()
     oi, os_, on = m.topk_batch(uids, 100, novelty=True)
     assert m.launch_count() > l0
@@ -123,3 +124,10 @@ def test_tensor_core_topk_overflow_fallback(monkeypatch):
     oi, os_, on = m.topk_batch(uids, 100, novelty=True)
     assert np.array_equal(on, ref_n)
     assert _check(m, o, ds, sample, 100, True, oi[sample], os_[sample], on[sample]) <= 2
+    # the default staging (item ranges growing 3x per stage, threshold tightened after each) with tiny first slices
+    monkeypatch.delenv('DRB_TOPK_GROWTH')
+    for ns in ('128', '512'):
+        monkeypatch.setenv('DRB_TOPK_NS', ns)
+        oi, os_, on = m.topk_batch(uids, 100, novelty=True)
+        assert np.array_equal(on, ref_n)
+        assert _check(m, o, ds, sample, 100, True, oi[sample], os_[sample], on[sample]) <= 2
