@@ -551,7 +551,18 @@ class CDAE(DeepRecommenderABC):
             d_c = torch.as_tensor(np.ascontiguousarray(cand, np.int32), device=self._dev)
             d_n = torch.as_tensor(np.ascontiguousarray(cand_count, np.int32), device=self._dev)
             o_i, o_s, o_n = self.rank_candidates_device(d_u, d_c, d_n, novelty)
-            return o_i.cpu().numpy(), o_s.cpu().numpy(), o_n.cpu().numpy()
+            return self._to_host(o_i, o_s, o_n)
+
+    def _to_host(self, *tensors):
+        """Device results -> numpy arrays through pinned host memory (torch's caching host allocator keeps the blocks,
+        so only the first call pays for pinning; a pageable .cpu() of the 111 MB of ranked lists of the ml-20m shape
+        took three times as long as computing them).  The arrays own their pinned block until they are dropped."""
+        torch = self._torch
+        host = [torch.empty(t.shape, dtype=t.dtype, pin_memory=True) for t in tensors]
+        for h, t in zip(host, tensors):
+            h.copy_(t, non_blocking=True)
+        torch.cuda.current_stream(self._dev).synchronize()
+        return tuple(h.numpy() for h in host)
 
     def topk_batch(self, uids, k, novelty=True, return_device=False, exact=False):
         """Full-catalog top-k for many users: (iids [n,k], scores [n,k], n_out [n]).  exact=True forces the exact-fp32
@@ -580,7 +591,7 @@ class CDAE(DeepRecommenderABC):
                 o_i[bad], o_s[bad], o_n[bad] = b_i, b_s, b_n
             if return_device:
                 return o_i, o_s, o_n
-            return o_i.cpu().numpy(), o_s.cpu().numpy(), o_n.cpu().numpy()
+            return self._to_host(o_i, o_s, o_n)
 
     def _recommend(self, uid, n, novelty, threshold):
         if n <= 2048:

@@ -956,6 +956,7 @@ int drb_cdae_rank_candidates(drb_cdae* m, const int32_t* uids, int32_t n, const 
 //   rows [FB][items_pad]
 struct TopkScratch {
   uint64_t* lists; uint32_t* bits; int32_t* cnt; uint32_t* tau; float* tau_z; int32_t* fb_count; int32_t* fb_users;
+  int32_t* big_users;                // users whose list is longer than the first select launch takes (score.cu)
   float* fb_rows;
   int cap, fb_max; bool ok;
   int n_stages; int bounds[12];      // item ranges [bounds[i-1], bounds[i]) of the filter passes (bounds[-1] = 0)
@@ -973,6 +974,7 @@ static TopkScratch topk_scratch(drb_cdae* m, int cap) {
   t.tau_z = c.take<float>(B);
   t.fb_count = c.take<int32_t>(64);
   t.fb_users = c.take<int32_t>(kTopkFallbackRows);
+  t.big_users = c.take<int32_t>(B);
   t.fb_rows = c.take<float>((int64_t)kTopkFallbackRows * m->L.items_pad);
   t.cap = cap; t.fb_max = kTopkFallbackRows;
   t.ok = c.off <= B * (int64_t)m->L.items_pad * 4;
@@ -993,7 +995,7 @@ static int cdae_topk_umma_chunk(drb_cdae* m, const TopkScratch& S, const int32_t
   } else if ((r = launch_split_tf32(ctx, w.h, c, ld, ld, w.h_hi, w.h_lo, nullptr, nullptr, 0, -1))) return r;
   DRB_CUDA_TRY(ctx, cudaMemsetAsync(S.cnt, 0, (size_t)c * 4, ctx->stream));
   DRB_CUDA_TRY(ctx, cudaMemsetAsync(S.tau, 0, (size_t)c * 4, ctx->stream));
-  DRB_CUDA_TRY(ctx, cudaMemsetAsync(S.fb_count, 0, 4, ctx->stream));
+  DRB_CUDA_TRY(ctx, cudaMemsetAsync(S.fb_count, 0, 64 * 4, ctx->stream));   // [0] fallback rows, [16 + stage] long lists
   const uint32_t* bits = nullptr;
   if (novelty) {     // the user's stored items as a bitmap (cdae.py:93-98): built like the per-user label bitmap
     DRB_CUDA_TRY(ctx, cudaMemsetAsync(S.bits, 0, (size_t)c * words * 4, ctx->stream));
@@ -1016,7 +1018,8 @@ static int cdae_topk_umma_chunk(drb_cdae* m, const TopkScratch& S, const int32_t
                                       S.cnt, S.lists, S.cap)))
       return r;
     if ((r = launch_select_lists(ctx, S.lists, S.cap, S.cnt, S.tau, S.tau_z, k, last, last ? out_iid : nullptr,
-                                 last ? out_score : nullptr, last ? n_out : nullptr, S.fb_users, S.fb_count, S.fb_max, c)))
+                                 last ? out_score : nullptr, last ? n_out : nullptr, S.fb_users, S.fb_count, S.fb_max,
+                                 S.big_users, S.fb_count + 16 + st, c)))
       return r;
   }
   // users whose list overflowed (n_out == -1, scratch rows claimed by the last select): exact fp32 scores + radix

@@ -263,7 +263,7 @@ int launch_umma_score_filter(drb_ctx* ctx, const UmmaOperands& o, int n_users, i
                              const uint32_t* tau_ord, const float* tau_z, int32_t* cnt, uint64_t* lists, int cap);
 int launch_select_lists(drb_ctx* ctx, uint64_t* lists, int cap, int32_t* cnt, uint32_t* tau_ord, float* tau_z, int k, bool final,
                         int32_t* out_iid, float* out_score, int32_t* n_out, int32_t* fb_users, int32_t* fb_count, int fb_max,
-                        int n);
+                        int32_t* big_users, int32_t* big_count, int n);
 // users with n_out == -1: scores by fp32 FMA into `rows` ([fb_max][a.ld]), then the radix-select top-k on those rows
 int launch_topk_fallback(drb_ctx* ctx, const TopkArgs& a, int n, const float* h, int ld_h, const float* table, int ld_t,
                          const float* bias, int width, float* rows, int32_t* fb_users, int32_t* fb_count, int fb_max);

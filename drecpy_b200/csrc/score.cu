@@ -300,73 +300,76 @@ __device__ __forceinline__ float logit_lower_bound(uint32_t tau_ord) {
 }
 
 // One CTA per user over the user's list of 64-bit keys (orderable score << 32 | iid), copied to shared memory once.
-//   final == 0 (after the first item slice): radix-selects tau = the k-th best score, keeps the keys >= tau at the head
-//               of the list (unordered) and publishes tau (0 while fewer than k exist: the next pass takes everything);
+//   final == 0 (after a filter stage that is not the last): radix-selects tau = the k-th best score, keeps the keys
+//               >= tau at the head of the list (unordered) and publishes tau and its logit bound (0 / -inf while fewer
+//               than k exist: the next stage takes everything);
 //   final != 0: radix-selects the k best keys -- score first, item id among equal scores, i.e. heapq.nlargest on
 //               (score, iid) tuples (cdae.py:102-103) -- sorts those k and emits them.
 // A list that overflowed its capacity marks the user (n_out = -1) for the exact fallback.
-__global__ void __launch_bounds__(256) k_select_lists(uint64_t* lists, int cap, int32_t* cnt, uint32_t* tau_ord,
-                                                      float* tau_z, int k, int final, int P, int32_t* out_iid,
-                                                      float* out_score, int32_t* n_out, int32_t* fb_users,
-                                                      int32_t* fb_count, int fb_max) {
-  extern __shared__ uint64_t sm_keys[];            // [cap] the list, then [P] the selected keys (final)
-  __shared__ int hist[256];
-  __shared__ SelectState st;
-  __shared__ int n_sel;
-  const int u = blockIdx.x;
-  const int c = cnt[u];
-  uint64_t* list = lists + (int64_t)u * cap;
-  if (c > cap) {                    // overflow: the list is incomplete, this user goes through the exact fallback
+// Two launches share the code: lists are a few hundred keys long almost always, so the first launch runs 64 threads per
+// user with shared memory for sm_cap = 1024 keys (32 users resident per SM instead of 7) and only records users with
+// longer lists; the second is a small persistent grid of 256-thread CTAs with room for `cap` keys over those users.
+struct SelectArgs {
+  uint64_t* lists; int cap; int32_t* cnt; uint32_t* tau_ord; float* tau_z; int k; int final; int P;
+  int32_t* out_iid; float* out_score; int32_t* n_out; int32_t* fb_users; int32_t* fb_count; int fb_max;
+  int sm_cap; int32_t* big_users; int32_t* big_count; int big_pass;
+};
+
+__device__ void select_user(const SelectArgs& a, int u, int c, uint64_t* sm_keys, int* hist, SelectState* st, int* n_sel) {
+  uint64_t* list = a.lists + (int64_t)u * a.cap;
+  const int k = a.k;
+  if (c > a.cap) {                  // overflow: the list is incomplete, this user goes through the exact fallback
     if (threadIdx.x == 0) {
-      if (final) {                  // claims a scratch row of the exact fallback (k_fallback_scores); beyond fb_max
-        n_out[u] = -1;              // rows n_out stays -1 and the host re-runs the user
-        const int slot = atomicAdd(fb_count, 1);
-        if (slot < fb_max) fb_users[slot] = u;
+      if (a.final) {                // claims a scratch row of the exact fallback (k_fallback_scores); beyond fb_max
+        a.n_out[u] = -1;            // rows n_out stays -1 and the host re-runs the user
+        const int slot = atomicAdd(a.fb_count, 1);
+        if (slot < a.fb_max) a.fb_users[slot] = u;
+      } else {                      // nothing more is appended for this user; cnt stays > cap
+        a.tau_ord[u] = 0xffffffffu; a.tau_z[u] = __int_as_float(0x7f800000);
       }
-      else { tau_ord[u] = 0xffffffffu; tau_z[u] = __int_as_float(0x7f800000); }   // nothing more is appended for this
-                                                                                  // user; cnt stays > cap
     }
     return;
   }
   for (int i = threadIdx.x; i < c; i += blockDim.x) sm_keys[i] = list[i];
-  if (threadIdx.x == 0) n_sel = 0;
+  if (threadIdx.x == 0) *n_sel = 0;
   __syncthreads();
   auto ord_key = [&](int i, uint32_t* out) { *out = (uint32_t)(sm_keys[i] >> 32); return true; };
-  if (!final) {
+  if (!a.final) {
     if (c < k) {                    // fewer than k so far: keep everything, no threshold yet
-      if (threadIdx.x == 0) { tau_ord[u] = 0u; tau_z[u] = __int_as_float(0xff800000); }
+      if (threadIdx.x == 0) { a.tau_ord[u] = 0u; a.tau_z[u] = __int_as_float(0xff800000); }
       return;
     }
-    radix_select_u32(c, k, ord_key, hist, &st);
-    const uint32_t t32 = st.prefix;
+    radix_select_u32(c, k, ord_key, hist, st);
+    const uint32_t t32 = st->prefix;
     for (int i = threadIdx.x; i < c; i += blockDim.x) {
       const uint64_t key = sm_keys[i];
-      if ((uint32_t)(key >> 32) >= t32) list[atomicAdd(&n_sel, 1)] = key;
+      if ((uint32_t)(key >> 32) >= t32) list[atomicAdd(n_sel, 1)] = key;
     }
     __syncthreads();
-    if (threadIdx.x == 0) { cnt[u] = n_sel; tau_ord[u] = t32; tau_z[u] = logit_lower_bound(t32); }
+    if (threadIdx.x == 0) { a.cnt[u] = *n_sel; a.tau_ord[u] = t32; a.tau_z[u] = logit_lower_bound(t32); }
     return;
   }
-  uint64_t* sel = sm_keys + cap;
+  const int P = a.P;
+  uint64_t* sel = sm_keys + (a.big_pass ? a.cap : a.sm_cap);
   for (int i = threadIdx.x; i < P; i += blockDim.x) sel[i] = 0ull;
   const int kk = min(k, c);
   if (kk == 0) {
-    if (threadIdx.x == 0) n_out[u] = 0;
+    if (threadIdx.x == 0) a.n_out[u] = 0;
     return;
   }
   uint32_t t32 = 0, tiid = 0;
   if (kk < c) {
-    radix_select_u32(c, kk, ord_key, hist, &st);
-    t32 = st.prefix;
-    const int need_eq = st.need, count_eq = st.bucket_count;
+    radix_select_u32(c, kk, ord_key, hist, st);
+    t32 = st->prefix;
+    const int need_eq = st->need, count_eq = st->bucket_count;
     __syncthreads();
     if (need_eq < count_eq) {       // ties on the threshold score: the need_eq largest item ids among them
       auto iid_key = [&](int i, uint32_t* out) {
         *out = (uint32_t)(sm_keys[i] & 0xffffffffu);
         return (uint32_t)(sm_keys[i] >> 32) == t32;
       };
-      radix_select_u32(c, need_eq, iid_key, hist, &st);
-      tiid = st.prefix;
+      radix_select_u32(c, need_eq, iid_key, hist, st);
+      tiid = st->prefix;
     }
   }
   __syncthreads();
@@ -374,13 +377,36 @@ __global__ void __launch_bounds__(256) k_select_lists(uint64_t* lists, int cap, 
     const uint64_t key = sm_keys[i];
     const uint32_t o = (uint32_t)(key >> 32), id = (uint32_t)(key & 0xffffffffu);
     if (kk == c || o > t32 || (o == t32 && id >= tiid)) {
-      const int pos = atomicAdd(&n_sel, 1);
+      const int pos = atomicAdd(n_sel, 1);
       if (pos < P) sel[pos] = key;
     }
   }
   __syncthreads();
   bitonic_desc(sel, P);
-  emit_sorted(sel, P, k, out_iid + (int64_t)u * k, out_score + (int64_t)u * k, n_out + u);
+  emit_sorted(sel, P, k, a.out_iid + (int64_t)u * k, a.out_score + (int64_t)u * k, a.n_out + u);
+}
+
+__global__ void __launch_bounds__(256) k_select_lists(SelectArgs a, int n_users) {
+  extern __shared__ uint64_t sm_keys[];            // [sm_cap | cap] the list, then [P] the selected keys (final)
+  __shared__ int hist[256];
+  __shared__ SelectState st;
+  __shared__ int n_sel;
+  if (!a.big_pass) {
+    const int u = blockIdx.x;
+    const int c = a.cnt[u];
+    if (c <= a.cap && c > a.sm_cap) {              // too long for this launch's shared memory: the second launch's
+      if (threadIdx.x == 0) a.big_users[atomicAdd(a.big_count, 1)] = u;
+      return;
+    }
+    select_user(a, u, c, sm_keys, hist, &st, &n_sel);
+    return;
+  }
+  const int n = min(*a.big_count, n_users);
+  for (int w = blockIdx.x; w < n; w += gridDim.x) {
+    const int u = a.big_users[w];
+    select_user(a, u, a.cnt[u], sm_keys, hist, &st, &n_sel);
+    __syncthreads();
+  }
 }
 
 // Exact fallback for users whose candidate list overflowed: fills the user's claimed scratch row with the scores
@@ -445,7 +471,7 @@ int launch_topk(drb_ctx* ctx, const TopkArgs& a, int n) {
 
 int launch_select_lists(drb_ctx* ctx, uint64_t* lists, int cap, int32_t* cnt, uint32_t* tau_ord, float* tau_z, int k,
                         bool final, int32_t* out_iid, float* out_score, int32_t* n_out, int32_t* fb_users, int32_t* fb_count,
-                        int fb_max, int n) {
+                        int fb_max, int32_t* big_users, int32_t* big_count, int n) {
   if (n <= 0) return DRB_OK;
   if (cap < 32 || (cap & (cap - 1)) || cap > 8192) return drb_fail(DRB_E_INVALID, "select_lists: cap must be a power of two in [32, 8192]");
   if (k < 1 || k > 2048) return drb_fail(DRB_E_INVALID, "select_lists: k must be in [1, 2048]");
@@ -455,11 +481,19 @@ int launch_select_lists(drb_ctx* ctx, uint64_t* lists, int cap, int32_t* cnt, ui
     if (e != cudaSuccess) return drb_fail(DRB_E_CUDA, "cudaFuncSetAttribute(k_select_lists) failed: %s", cudaGetErrorString(e));
     attr_set = true;
   }
-  const int P = next_pow2(k);
+  SelectArgs a{};
+  a.lists = lists; a.cap = cap; a.cnt = cnt; a.tau_ord = tau_ord; a.tau_z = tau_z; a.k = k; a.final = final ? 1 : 0;
+  a.P = next_pow2(k); a.out_iid = out_iid; a.out_score = out_score; a.n_out = n_out;
+  a.fb_users = fb_users; a.fb_count = fb_count; a.fb_max = fb_max;
+  a.sm_cap = std::min(cap, 1024); a.big_users = big_users; a.big_count = big_count;
   drb_prof_scope prof_(ctx, final ? "k_select_lists_final" : "k_select_lists_tau");
-  k_select_lists<<<n, 256, (size_t)(cap + (final ? P : 0)) * sizeof(uint64_t), ctx->stream>>>(
-      lists, cap, cnt, tau_ord, tau_z, k, final ? 1 : 0, P, out_iid, out_score, n_out, fb_users, fb_count, fb_max);
+  k_select_lists<<<n, 64, (size_t)(a.sm_cap + (final ? a.P : 0)) * sizeof(uint64_t), ctx->stream>>>(a, n);
   DRB_LAUNCH_CHECK(ctx, "k_select_lists");
+  if (cap > a.sm_cap) {             // users whose list is longer than 1024 keys (none, usually: the CTAs leave at once)
+    a.big_pass = 1;
+    k_select_lists<<<std::min(n, 7 * ctx->sm_count), 256, (size_t)(cap + (final ? a.P : 0)) * sizeof(uint64_t), ctx->stream>>>(a, n);
+    DRB_LAUNCH_CHECK(ctx, "k_select_lists");
+  }
   return DRB_OK;
 }
 

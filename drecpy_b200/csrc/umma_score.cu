@@ -28,6 +28,7 @@ namespace {
 
 constexpr int SC_EPI_WARPS = 16;
 constexpr int SC_THREADS = 64 + 32 * SC_EPI_WARPS;
+constexpr int SC_QCAP = 128;                 // entries of an epilogue warp's key queue (flushed when full and per tile)
 
 template <int BN, int KB, int CL>
 struct ScoreSmem {
@@ -38,7 +39,8 @@ struct ScoreSmem {
   static constexpr int BAR_BYTES = 256;
   // per epilogue warp and user of its column quarter: (exact threshold, seen word) + the conservative logit threshold
   static constexpr int TAU_BYTES = SC_EPI_WARPS * (BN / 4) * 12;
-  static constexpr int TOTAL = STAGES * STAGE_BYTES + 1024 + BAR_BYTES + TAU_BYTES;
+  static constexpr int QUEUE_BYTES = SC_EPI_WARPS * SC_QCAP * 10; // per epilogue warp: (key, user) waiting for a list slot
+  static constexpr int TOTAL = STAGES * STAGE_BYTES + 1024 + BAR_BYTES + TAU_BYTES + QUEUE_BYTES;
 };
 
 struct ScoreParams {
@@ -69,7 +71,35 @@ __device__ __forceinline__ void sc_mbar_arrive_rank(uint32_t bar, uint32_t rank)
   asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(mapa_rank(bar, rank)) : "memory");
 }
 
-template <int BN, int KB, int CL, bool H>
+// Gives the queued keys of one epilogue warp their list slots (one atomicAdd per key, all issued before any is
+// consumed) and stores them.  A queue entry is the final 64-bit key (orderable score << 32 | item id) plus the user's
+// row in the block.  Not inlined: the filter loop has 16 call sites and must stay inside the instruction cache.
+__device__ __noinline__ void sc_flush_queue(const uint64_t* qk, const unsigned short* qu, int qn, int32_t* cnt,
+                                            uint64_t* lists, int cap) {
+  const int lane = threadIdx.x & 31;
+  __syncwarp();
+  uint64_t ent[SC_QCAP / 32];
+  int row[SC_QCAP / 32], pos[SC_QCAP / 32];
+#pragma unroll
+  for (int bq = 0; bq < SC_QCAP / 32; bq++) {
+    const int e = bq * 32 + lane;
+    pos[bq] = 0x7fffffff;
+    if (e < qn) {
+      ent[bq] = qk[e];
+      row[bq] = qu[e];
+      pos[bq] = atomicAdd(cnt + row[bq], 1);
+    }
+  }
+#pragma unroll
+  for (int bq = 0; bq < SC_QCAP / 32; bq++)
+    if (pos[bq] < cap) lists[(int64_t)row[bq] * cap + pos[bq]] = ent[bq];
+  __syncwarp();
+}
+
+// FILTER = false: first slice, every unseen item is listed (one warp-aggregated atomicAdd per (warp, user) reserves the
+// slots).  FILTER = true: later stages, a logit pre-filter and the exact test leave few keys; they go to a per-warp
+// queue in shared memory and get their slots when the queue is flushed -- no global round trip inside the tile loop.
+template <int BN, int KB, int CL, bool H, bool FILTER>
 __global__ void __launch_bounds__(SC_THREADS, 1)
 k_umma_score_filter(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                     const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
@@ -89,6 +119,7 @@ k_umma_score_filter(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
   volatile uint32_t* tmem_ptr_generic = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_ptr_addr - raw));
   uint2* tau_smem = reinterpret_cast<uint2*>(smem_raw + (bars + S::BAR_BYTES - raw));
   float* tz_smem = reinterpret_cast<float*>(tau_smem + SC_EPI_WARPS * (BN / 4));
+  uint64_t* q_smem = reinterpret_cast<uint64_t*>(tz_smem + SC_EPI_WARPS * (BN / 4));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nkb = (p.Kred + BK - 1) / BK;
@@ -197,42 +228,62 @@ k_umma_score_filter(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
     constexpr int CW = BN / 4;                    // users of this warp per tile
     uint2* my_tau = tau_smem + (warp - 2) * CW;    // .x = threshold, .y = the user's seen-bitmap word for this item block
     float* my_tz = tz_smem + (warp - 2) * CW;      // logit pre-filter threshold of the same users
+    uint64_t* my_q = q_smem + (warp - 2) * SC_QCAP;                 // queued keys ...
+    unsigned short* my_qu = reinterpret_cast<unsigned short*>(q_smem + SC_EPI_WARPS * SC_QCAP) + (warp - 2) * SC_QCAP;  // ... and their users
     const uint32_t lt_mask = (1u << lane) - 1u;
     const float osc = H ? p.out_scale * (p.out_scale_dev ? __ldg(p.out_scale_dev) : 1.0f) : 1.0f;
+    // per-tile constants are fetched one tile ahead into registers (b' of this lane's item; thresholds and seen-bitmap
+    // words of users lane, lane + 32, ... of the warp's column quarter) so that no global load is waited for in the loop
     float nbias;
-    auto fetch_bias = [&](int t) {
-      const int item = unit_item0(t) + q * 32 + lane;
-      nbias = ((t < n_units) && (item < p.item_end)) ? __ldg(p.bias + item) : 0.f;
+    uint2 nv[CW / 32];
+    float ntz[CW / 32];
+    auto fetch_users = [&](int t, int i, uint2* v, float* tz) {   // user lane + 32 i of the warp's quarter in unit t
+      const int row = unit_row0(t) + cq * CW + lane + 32 * i;
+      const int ib = (unit_item0(t) >> 5) + q;     // 32-item block of this warp == word of the seen bitmap
+      *v = make_uint2(0xffffffffu, 0u);
+      if (FILTER) *tz = __int_as_float(0x7f800000);              // users beyond the block never pass
+      if (t < n_units && row < p.M) {
+        v->x = __ldg(p.tau_ord + row);
+        if (p.seen_bits && !(p.debug & 2) && ib < p.words_per_row)
+          v->y = __ldg(p.seen_bits + (int64_t)row * p.words_per_row + ib);
+        if (FILTER) *tz = (p.debug & 8) ? __int_as_float(0x7f800000) : __ldg(p.tau_z + row);
+      }
     };
-    fetch_bias(unit0);
+    auto fetch_consts = [&](int t) {
+      const int item = unit_item0(t) + q * 32 + lane;
+      nbias = (t < n_units && item < p.item_end) ? __ldg(p.bias + item) : 0.f;
+      if (FILTER) {
+#pragma unroll
+        for (int i = 0; i < CW / 32; i++) fetch_users(t, i, &nv[i], &ntz[i]);
+      }
+    };
+    fetch_consts(unit0);
+    int qn = 0;                                    // entries in the queue (warp-uniform); it lives across tiles and is
+    auto flush_queue = [&]() {                     // flushed when the next row of keys would not fit, and at the end
+      sc_flush_queue(my_q, my_qu, qn, p.cnt, p.lists, p.cap);
+      qn = 0;
+    };
     int tl = 0;
     for (int t = unit0; t < n_units; t += unit_stride, tl++) {
       const int i0 = unit_item0(t), r0 = unit_row0(t);
       const int as = tl & 1;
       const int item = i0 + q * 32 + lane;
       const bool item_ok = item < p.item_end;
-      const int ib = (i0 >> 5) + q;               // 32-item block of this warp == word of the seen bitmap
       const float bias = nbias;
-      fetch_bias(t + unit_stride);
-      // thresholds and seen-bitmap words of this warp's users, fetched before the accumulator is waited for (users
-      // beyond the block never pass: their pre-filter threshold is +inf)
       __syncwarp();
 #pragma unroll
-      for (int c = lane; c < CW; c += 32) {
-        const int row = r0 + cq * CW + c;
-        uint2 v = make_uint2(0xffffffffu, 0u);
-        float tz = __int_as_float(0x7f800000);
-        if (row < p.M) {
-          v.x = __ldg(p.tau_ord + row);
-          if (p.seen_bits && !(p.debug & 2) && ib < p.words_per_row)
-            v.y = __ldg(p.seen_bits + (int64_t)row * p.words_per_row + ib);
-          tz = p.tau_z ? __ldg(p.tau_z + row) : __int_as_float(0xff800000);
-          if (p.debug & 8) tz = __int_as_float(0x7f800000);
+      for (int i = 0; i < CW / 32; i++) {
+        if (FILTER) {
+          my_tau[lane + 32 * i] = nv[i];
+          my_tz[lane + 32 * i] = ntz[i];
+        } else {                                   // the short first slice fetches in place (registers are scarce there)
+          uint2 v; float tz;
+          fetch_users(t, i, &v, &tz);
+          my_tau[lane + 32 * i] = v;
         }
-        my_tau[c] = v;
-        my_tz[c] = tz;
       }
       __syncwarp();
+      fetch_consts(t + unit_stride);
       mbar_wait(tfull_bar(as), (tl >> 1) & 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN + cq * CW);
@@ -246,32 +297,51 @@ k_umma_score_filter(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
 #pragma unroll
         for (int j = 0; j < 16; j++) r[j] = rn[j];
         if (cl + 16 < CW) tmem_ld16_issue(tbase + cl + 16, rn);
-        float tz[16];
+        if (FILTER) {
+          // Pre-filter on the logit: one fma, one compare and one vote per element.  The exact test -- the fp32 sigmoid
+          // value as an orderable integer against the user's threshold, the seen-bitmap knock-out -- runs only for the
+          // (user, 32-item) rows in which some lane passes; the keys that really pass are queued.
 #pragma unroll
-        for (int j = 0; j < 16; j += 4) {
-          const float4 v = *reinterpret_cast<const float4*>(my_tz + cl + j);      // broadcast reads
-          tz[j] = v.x; tz[j + 1] = v.y; tz[j + 2] = v.z; tz[j + 3] = v.w;
+          for (int j4 = 0; j4 < 16; j4 += 4) {
+            const float4 tz4 = *reinterpret_cast<const float4*>(my_tz + cl + j4);    // broadcast read
+            const float tz[4] = {tz4.x, tz4.y, tz4.z, tz4.w};
+#pragma unroll
+            for (int jj = 0; jj < 4; jj++) {
+              const int j = j4 + jj;
+              const float z = H ? fmaf(__uint_as_float(r[j]), osc, bias) : __uint_as_float(r[j]) + bias;
+              if (__any_sync(0xffffffffu, z >= tz[jj])) {
+                const float pr = sc_rcp(1.0f + sc_ex2(z * -1.4426950408889634f));     // sigmoid, > 0
+                const uint32_t ord = __float_as_uint(pr) | 0x80000000u;               // f2ord of a non-negative float
+                const uint2 ts = my_tau[cl + j];                                      // broadcast read
+                const bool pass = item_ok && !((ts.y >> lane) & 1u) && (ord >= ts.x) && !(p.debug & 1);
+                const uint32_t bal = __ballot_sync(0xffffffffu, pass);
+                if (bal != 0u) {                   // warp-uniform
+                  const int n = __popc(bal);
+                  if (qn + n > SC_QCAP) flush_queue();
+                  if (pass) {
+                    const int e = qn + __popc(bal & lt_mask);
+                    my_q[e] = ((uint64_t)ord << 32) | (uint32_t)item;
+                    my_qu[e] = (unsigned short)(row + j);
+                  }
+                  qn += n;
+                }
+              }
+            }
+          }
+          continue;
         }
-        uint32_t bal[16], anyb = 0u;
-        // 1. Pre-filter on the logit: one fma, one compare and one vote per element.  The exact test -- the fp32 sigmoid
-        //    value as an orderable integer against the user's threshold, the seen-bitmap knock-out -- runs only for the
-        //    (user, 32-item) rows in which some lane passes; bal[j] = the lanes that really pass for user j, r[j]
-        //    becomes the orderable score there.
+        uint32_t bal[16];
+        // 1. score, knock-out, threshold test: r[j] becomes the orderable score, bal[j] the lanes that pass for user j
 #pragma unroll
         for (int j = 0; j < 16; j++) {
           const float z = H ? fmaf(__uint_as_float(r[j]), osc, bias) : __uint_as_float(r[j]) + bias;
-          bal[j] = 0u;
-          if (__any_sync(0xffffffffu, z >= tz[j])) {
-            const float pr = sc_rcp(1.0f + sc_ex2(z * -1.4426950408889634f));       // sigmoid, > 0
-            const uint32_t ord = __float_as_uint(pr) | 0x80000000u;                 // f2ord of a non-negative float
-            const uint2 ts = my_tau[cl + j];                                        // broadcast read
-            const bool pass = item_ok && !((ts.y >> lane) & 1u) && (ord >= ts.x);
-            r[j] = ord;
-            bal[j] = (p.debug & 1) ? 0u : __ballot_sync(0xffffffffu, pass);
-            anyb |= bal[j];
-          }
+          const float pr = sc_rcp(1.0f + sc_ex2(z * -1.4426950408889634f));         // sigmoid, > 0
+          const uint32_t ord = __float_as_uint(pr) | 0x80000000u;                   // f2ord of a non-negative float
+          const uint2 ts = my_tau[cl + j];                                          // broadcast read
+          const bool pass = item_ok && (row + j < p.M) && !((ts.y >> lane) & 1u) && (ord >= ts.x);
+          r[j] = ord;
+          bal[j] = (p.debug & 1) ? 0u : __ballot_sync(0xffffffffu, pass);
         }
-        if (anyb == 0u) continue;                  // warp-uniform
         // 2. one atomicAdd per (warp, user) reserves the slots of the passing lanes (all issued before any is consumed)
         int slot[16];
 #pragma unroll
@@ -298,6 +368,7 @@ k_umma_score_filter(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
         else sc_mbar_arrive(tempty_bar(as));
       }
     }
+    if (FILTER && qn > 0) flush_queue();
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   if (CL > 1) cluster_sync_all(); else __syncthreads();
@@ -308,7 +379,7 @@ k_umma_score_filter(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
   }
 }
 
-template <int BN, int KB, int CL, bool H>
+template <int BN, int KB, int CL, bool H, bool FILTER>
 int run_score(drb_ctx* ctx, const UmmaOperands& o, ScoreParams p, int n_items) {
   CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
   int r;
@@ -320,7 +391,7 @@ int run_score(drb_ctx* ctx, const UmmaOperands& o, ScoreParams p, int n_items) {
   if ((r = make_operand_map<H>(&mb_lo, o.a_lo, p.Kred, p.M, o.lda, KB, BN / CL))) return r;
   p.m_tiles = (p.item_end - p.item_begin + BM - 1) / BM;
   p.n_tiles = (p.M + BN - 1) / BN;
-  auto kern = k_umma_score_filter<BN, KB, CL, H>;
+  auto kern = k_umma_score_filter<BN, KB, CL, H, FILTER>;
   constexpr int SMEM = ScoreSmem<BN, KB, CL>::TOTAL;
   static bool attr_set = false;
   static int max_clusters = 0;
@@ -373,10 +444,17 @@ int launch_umma_score_filter(drb_ctx* ctx, const UmmaOperands& o, int n_users, i
   p.seen_bits = seen_bits; p.words_per_row = words_per_row; p.tau_ord = tau_ord; p.tau_z = tau_z; p.cnt = cnt; p.lists = lists; p.cap = cap;
   p.debug = getenv("DRB_SCORE_DEBUG") ? atoi(getenv("DRB_SCORE_DEBUG")) : 0;
   p.out_scale = o.out_scale; p.out_scale_dev = o.out_scale_dev;
-  if (o.half) {
-    if (n_users > 128) return run_score<256, 32, 2, true>(ctx, o, p, n_items);
-    return run_score<128, 32, 1, true>(ctx, o, p, n_items);
+  if (n_users > 65536) return drb_fail(DRB_E_INVALID, "score_filter: at most 65536 users per block");
+#define DRB_SCORE_CASE(F_)                                                             \
+  {                                                                                    \
+    if (o.half) {                                                                      \
+      if (n_users > 128) return run_score<256, 32, 2, true, F_>(ctx, o, p, n_items);   \
+      return run_score<128, 32, 1, true, F_>(ctx, o, p, n_items);                      \
+    }                                                                                  \
+    if (n_users > 128) return run_score<256, 32, 2, false, F_>(ctx, o, p, n_items);    \
+    return run_score<128, 32, 1, false, F_>(ctx, o, p, n_items);                       \
   }
-  if (n_users > 128) return run_score<256, 32, 2, false>(ctx, o, p, n_items);
-  return run_score<128, 32, 1, false>(ctx, o, p, n_items);
+  if (tau_z) DRB_SCORE_CASE(true)
+  DRB_SCORE_CASE(false)
+#undef DRB_SCORE_CASE
 }
