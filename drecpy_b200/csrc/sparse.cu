@@ -210,34 +210,21 @@ __device__ __forceinline__ uint32_t philox_first(uint32_t c0, uint32_t c1, uint3
   return c0;
 }
 
-// One CTA per sampled row.  The heaviest row of a 4096-user batch has ~35x the median degree and sets the duration of
-// the kernel, so every thread keeps four index loads in flight (256 threads: 1024 entries per round trip).
-__global__ void __launch_bounds__(256) k_batch_prep(BatchPrepArgs a) {
+__global__ void __launch_bounds__(128) k_batch_prep(BatchPrepArgs a) {
   const int b = blockIdx.x;
   const int row = a.rows[b];
   const int64_t lo = a.indptr[row], hi = a.indptr[row + 1];
   const int koff = a.keep_off ? a.keep_off[b] : 0;
   const uint64_t step = a.step_dev ? (((uint64_t)a.step_dev[1] << 32) | a.step_dev[0]) : a.step;
-  for (int64_t j0 = lo + threadIdx.x; j0 < hi; j0 += 4 * blockDim.x) {
-    int items[4];
-#pragma unroll
-    for (int u = 0; u < 4; u++) {
-      const int64_t j = j0 + (int64_t)u * blockDim.x;
-      items[u] = j < hi ? __ldg(a.indices + j) : -1;
-    }
-#pragma unroll
-    for (int u = 0; u < 4; u++) {
-      const int64_t j = j0 + (int64_t)u * blockDim.x;
-      const int item = items[u];
-      if (item < 0) continue;
-      if (a.count) atomicAdd(a.count + item, 1.0f);
-      if (a.label_bits) atomicOr(a.label_bits + (int64_t)b * a.words_per_row + (item >> 5), 1u << (item & 31));
-      if (a.keep_out) {
-        const uint32_t x = philox_first((uint32_t)(item + a.item_offset), (uint32_t)(b + a.slot_offset), (uint32_t)step,
-                                        (uint32_t)(step >> 32), (uint32_t)a.seed, (uint32_t)(a.seed >> 32));
-        const float uf = (float)(x >> 8) * (1.0f / 16777216.0f);
-        a.keep_out[koff + (j - lo)] = (uf < a.q) ? 0 : 1;
-      }
+  for (int64_t j = lo + threadIdx.x; j < hi; j += blockDim.x) {
+    const int item = a.indices[j];
+    if (a.count) atomicAdd(a.count + item, 1.0f);
+    if (a.label_bits) atomicOr(a.label_bits + (int64_t)b * a.words_per_row + (item >> 5), 1u << (item & 31));
+    if (a.keep_out) {
+      const uint32_t x = philox_first((uint32_t)(item + a.item_offset), (uint32_t)(b + a.slot_offset), (uint32_t)step, (uint32_t)(step >> 32),
+                                      (uint32_t)a.seed, (uint32_t)(a.seed >> 32));
+      const float u = (float)(x >> 8) * (1.0f / 16777216.0f);
+      a.keep_out[koff + (j - lo)] = (u < a.q) ? 0 : 1;
     }
   }
 }
@@ -676,7 +663,7 @@ int launch_row_scatter(drb_ctx* ctx, const int32_t* ids, const float* rows, int 
 int launch_batch_prep(drb_ctx* ctx, const BatchPrepArgs& a, int n) {
   if (n <= 0) return DRB_OK;
   drb_prof_scope prof_(ctx, "k_batch_prep");
-  k_batch_prep<<<n, 256, 0, ctx->stream>>>(a);
+  k_batch_prep<<<n, 128, 0, ctx->stream>>>(a);
   DRB_LAUNCH_CHECK(ctx, "k_batch_prep");
   return DRB_OK;
 }

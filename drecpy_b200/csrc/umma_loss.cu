@@ -49,10 +49,9 @@ struct LossParams {
   float out_scale; const float* out_scale_dev;   // H: accumulator -> logit (undoes the operand scaling)
   float* z_dbg; int ldz;                   // tests only (drb_debug_cdae_capture_logits): z2 = h W'^T + b' as this kernel
                                            // formed it, row-major [M][ldz]; NULL in production
-  int debug;   // DRB_LOSS_DEBUG bit mask (profiling experiments only, results are wrong): 1 = first 16-row chunk of
-               // each epilogue warp only, 2 = skip TMA + MMA, 4 = skip the dz stores, 8 = skip the B_lo loads, 16 = skip the MMAs,
-               // 32 = no lg2 in the fast epilogue form; 64 (results stay right) = the five-MUFU fast form of round 2's
-               // first half instead of the 2.5-MUFU one
+  uint32_t wait_ns;                        // sleep between polls of the accumulator-full barrier (epilogue warps)
+  int debug;   // DRB_LOSS_DEBUG bit mask (profiling experiments only, results are wrong): 2 = skip TMA + MMA, 4 = skip the dz stores, 8 = skip the B_lo loads, 16 = skip the MMAs,
+               // 32 = no lg2 in the fast epilogue form
 };
 
 __device__ __forceinline__ float fast_ex2(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
@@ -233,20 +232,13 @@ k_umma_cdae_loss(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
       const float osc2 = osc * -1.4426950408889634f, nb2 = bias * -1.4426950408889634f;   // exp2 argument = fma(acc, osc2, nb2)
       float sum_la = 0.f, sum_lb = 0.f;           // fast chunks: sums of lg2(p + eps), lg2(1 - p + eps) of this lane's item
       fetch_consts(t + unit_stride);
-      mbar_wait(tfull_bar(as), (tl >> 1) & 1);
+      mbar_wait_sleep(tfull_bar(as), (tl >> 1) & 1, p.wait_ns);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN + cq * CW);
-      uint32_t rn[16];
-      tmem_ld16_issue(tbase, rn);
       float csum = 0.f;                           // this lane's item: sum of dL/dz2 over the warp's batch rows
-#pragma unroll 1
-      for (int cl = 0; cl < ((p.debug & 1) ? 16 : CW); cl += 16) {
+      // one chunk = 16 batch rows of this warp's 32 items; r[] holds the accumulator values on entry
+      auto process_chunk = [&](uint32_t (&r)[16], const int cl) {
         const int row = r0 + cq * CW + cl;        // first of this chunk's 16 batch rows (same 128-row tile: 16 | 128)
-        uint32_t r[16];
-        tmem_ld16_wait(rn);
-#pragma unroll
-        for (int j = 0; j < 16; j++) r[j] = rn[j];
-        if (cl + 16 < CW) tmem_ld16_issue(tbase + cl + 16, rn);      // prefetch the next chunk behind the math
         float lo[16];
         // branch-free element math: 16 independent dependency chains the scheduler can interleave.  MUFU ops are
         // issued directly (ex2 / rcp / lg2 .approx.ftz: no denormal fix-up sequences), 5 per element.
@@ -267,7 +259,7 @@ k_umma_cdae_loss(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
           for (int j = 0; j < 16; j++) amax = fmaxf(amax, fabsf(fmaf(__uint_as_float(r[j]), osc2, nb2)));
           fast = !__any_sync(0xffffffffu, !fast || amax > 22.0f);
         }
-        if (fast && !(p.debug & 64)) {
+        if (fast) {
           // One reciprocal per element: with s = 1 + e, t1 = 1 + eps s, t2 = e + eps s and R = 1 / (s t1 t2):
           //   p = 1/s = R t1 t2,  da = p + eps = t1/s,  db = 1 - p + eps = t2/s,  p (1-p) / (da db) = e / (t1 t2) = e s R.
           // The log terms of four elements are one lg2 of their product (da, db >= 3.4e-7 here: no underflow).
@@ -282,22 +274,11 @@ k_umma_cdae_loss(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
             const float da = pr + KERAS_EPS, db = (1.0f + KERAS_EPS) - pr;
             pa *= da; pb *= db;
             if ((j & 3) == 3) {
-              sum_la += fast_lg2(pa); sum_lb += fast_lg2(pb);
+              sum_la += (p.debug & 32) ? pa : fast_lg2(pa); sum_lb += (p.debug & 32) ? pb : fast_lg2(pb);
               pa = 1.0f; pb = 1.0f;
             }
             const float num = fmaf(tgt_c, -(1.0f + 2.0f * KERAS_EPS), da);
             lo[j] = (num * e) * (R * (s1 * gsc));
-          }
-        } else if (fast) {
-#pragma unroll
-          for (int j = 0; j < 16; j++) {
-            const float e = fast_ex2(fmaf(__uint_as_float(r[j]), osc2, nb2));
-            const float pr = fast_rcp(1.0f + e);
-            const float da = pr + KERAS_EPS, db = 1.0f - pr + KERAS_EPS;
-            sum_la += (p.debug & 32) ? da : fast_lg2(da);
-            sum_lb += (p.debug & 32) ? db : fast_lg2(db);
-            const float num = fmaf(tgt_c, -(1.0f + 2.0f * KERAS_EPS), da);
-            lo[j] = num * (pr * (1.0f - pr)) * (fast_rcp(da * db) * gsc);
           }
         } else
 #pragma unroll
@@ -336,17 +317,15 @@ k_umma_cdae_loss(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
           }
         }
         if (H) {
-          // fp16 hi/lo split of 16 values with 16 packed conversions (cvt.rn.f16x2.f32 handles two floats): hi is first
-          // rounded to 11 significant bits in fp32 (Dekker: c = g * (2^13 + 1), hi = c - (c - g)), so its conversion
-          // is exact and lo = g - hi needs no conversion back.  hp[i] / lp[i] = users (2i, 2i + 1) packed low | high.
+          // fp16 hi/lo split of 16 values, two users at a time: hi = rn_f16(g) (one packed conversion for two values),
+          // converted back exactly, lo = rn_f16(g - hi) -- the residual of the value actually stored as hi.
+          // hp[i] / lp[i] = users (2i, 2i + 1) packed low | high.
           uint32_t hp[8], lp[8];
 #pragma unroll
           for (int j = 0; j < 16; j += 2) {
-            const float c0 = __fmul_rn(lo[j], 8193.0f), c1 = __fmul_rn(lo[j + 1], 8193.0f);   // no fma contraction
-            const float h0 = __fsub_rn(c0, __fsub_rn(c0, lo[j])), h1 = __fsub_rn(c1, __fsub_rn(c1, lo[j + 1]));
-            const float l0 = __fsub_rn(lo[j], h0), l1 = __fsub_rn(lo[j + 1], h1);
-            asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(hp[j >> 1]) : "f"(h1), "f"(h0));
-            asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(lp[j >> 1]) : "f"(l1), "f"(l0));
+            asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(hp[j >> 1]) : "f"(lo[j + 1]), "f"(lo[j]));
+            const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&hp[j >> 1]));
+            asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(lp[j >> 1]) : "f"(lo[j + 1] - hf.y), "f"(lo[j] - hf.x));
           }
           if (p.colsum) {                         // lo[] still holds the unsplit values
 #pragma unroll
@@ -397,6 +376,19 @@ k_umma_cdae_loss(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
           }
         }
         }
+      };
+      // two register sets in turn: the tcgen05.ld of the next chunk runs behind the math of this one and no value is
+      // ever copied between registers (CW is 32 or 64: an even number of chunks)
+      uint32_t ra[16], rb[16];
+      tmem_ld16_issue(tbase, ra);
+#pragma unroll 1
+      for (int cl = 0; cl < CW; cl += 32) {
+        tmem_ld16_wait(ra);
+        tmem_ld16_issue(tbase + cl + 16, rb);
+        process_chunk(ra, cl);
+        tmem_ld16_wait(rb);
+        if (cl + 32 < CW) tmem_ld16_issue(tbase + cl + 32, ra);
+        process_chunk(rb, cl + 16);
       }
       loss_local += -0.6931471805599453f * fmaf(tgt_c, sum_la - sum_lb, sum_lb);   // bce terms of the fast chunks
       if (p.colsum && item_ok) atomicAdd(p.colsum + item, H ? csum * (p.inv_count / DRB_DZ_F16_SCALE) : csum);
@@ -500,6 +492,8 @@ int launch_umma_cdae_loss(drb_ctx* ctx, const UmmaOperands& o, int M, int N, int
   p.inv_count = inv_count; p.batch = batch; p.loss_part = loss_part; p.colsum = dz_colsum;
   static const int dbg_env = getenv("DRB_LOSS_DEBUG") ? atoi(getenv("DRB_LOSS_DEBUG")) : 0;
   p.debug = dbg_env;
+  static const int wait_env = getenv("DRB_WAIT_NS") ? atoi(getenv("DRB_WAIT_NS")) : 100;
+  p.wait_ns = (uint32_t)wait_env;
   const bool per_user = label_count == nullptr;
   static const int bn_env = getenv("DRB_LOSS_BN") ? atoi(getenv("DRB_LOSS_BN")) : 0;
   // 256 batch rows per tile halve the re-reads of the W' tile (the main loop is L2->SM bandwidth bound)

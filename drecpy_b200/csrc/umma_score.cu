@@ -35,12 +35,17 @@ struct ScoreSmem {
   static constexpr int A_BYTES = BM * KB * 4;
   static constexpr int B_BYTES = (BN / CL) * KB * 4;
   static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
-  static constexpr int STAGES = 192 * 1024 / STAGE_BYTES;
   static constexpr int BAR_BYTES = 256;
   // per epilogue warp and user of its column quarter: (exact threshold, seen word) + the conservative logit threshold
-  static constexpr int TAU_BYTES = SC_EPI_WARPS * (BN / 4) * 12;
+  // (FILTER: two buffers of (seen word, logit threshold) + exact threshold, filled by cp.async one tile ahead; first
+  // slice: one buffer of (exact threshold, seen word))
+  static constexpr int TAU_BYTES = SC_EPI_WARPS * (BN / 4) * 24;
   static constexpr int QUEUE_BYTES = SC_EPI_WARPS * SC_QCAP * 10; // per epilogue warp: (key, user) waiting for a list slot
-  static constexpr int TOTAL = STAGES * STAGE_BYTES + 1024 + BAR_BYTES + TAU_BYTES + QUEUE_BYTES;
+  static constexpr int FIXED = 1024 + BAR_BYTES + TAU_BYTES + QUEUE_BYTES;
+  static constexpr int FIT = (227 * 1024 - FIXED) / STAGE_BYTES;       // pipeline stages that fit next to the rest
+  static constexpr int STAGES = FIT > 5 ? 5 : FIT;
+  static constexpr int TOTAL = STAGES * STAGE_BYTES + FIXED;
+  static_assert(STAGES >= 2, "score filter: the operand pipeline needs at least two stages");
 };
 
 struct ScoreParams {
@@ -56,6 +61,7 @@ struct ScoreParams {
   uint64_t* lists; int cap;                // [M][cap]
   int m_tiles, n_tiles;
   float out_scale; const float* out_scale_dev;   // H: accumulator -> logit (undoes the fp16 operand scaling)
+  uint32_t wait_ns;                        // sleep between polls of the accumulator-full barrier (epilogue warps)
   int debug;   // DRB_SCORE_DEBUG bit mask (profiling experiments only, results are wrong): 1 = no appends, 2 = no seen
                // bitmap loads, 4 = no MMAs, 8 = nothing passes the logit pre-filter
 };
@@ -118,8 +124,8 @@ k_umma_score_filter(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
   const uint32_t tmem_ptr_addr = bars + 8u * (2 * S::STAGES + 4);
   volatile uint32_t* tmem_ptr_generic = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_ptr_addr - raw));
   uint2* tau_smem = reinterpret_cast<uint2*>(smem_raw + (bars + S::BAR_BYTES - raw));
-  float* tz_smem = reinterpret_cast<float*>(tau_smem + SC_EPI_WARPS * (BN / 4));
-  uint64_t* q_smem = reinterpret_cast<uint64_t*>(tz_smem + SC_EPI_WARPS * (BN / 4));
+  uint32_t* tord_smem = reinterpret_cast<uint32_t*>(tau_smem + 2 * SC_EPI_WARPS * (BN / 4));   // [warp][2][CW]
+  uint64_t* q_smem = reinterpret_cast<uint64_t*>(tord_smem + 2 * SC_EPI_WARPS * (BN / 4));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nkb = (p.Kred + BK - 1) / BK;
@@ -226,38 +232,54 @@ k_umma_score_filter(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
     // column quarter (w-2)/4 of the tile: for one user the 32 lanes of a warp hold 32 consecutive items.
     const int q = warp & 3, cq = (warp - 2) >> 2;
     constexpr int CW = BN / 4;                    // users of this warp per tile
-    uint2* my_tau = tau_smem + (warp - 2) * CW;    // .x = threshold, .y = the user's seen-bitmap word for this item block
-    float* my_tz = tz_smem + (warp - 2) * CW;      // logit pre-filter threshold of the same users
+    // first slice: my_tau[c] = (exact threshold, seen word) of user c of the warp's column quarter, fetched in place.
+    // FILTER: my_sz[buf][c] = (seen word, logit threshold); the next tile's values arrive by cp.async while this tile is
+    // processed (no registers are held across the tile, nothing is waited for inside the loop); my_tord[buf][c] = the
+    // exact threshold, used on the slow path only.
+    uint2* my_tau = tau_smem + (warp - 2) * 2 * CW;
+    uint32_t* my_tord = tord_smem + (warp - 2) * 2 * CW;
     uint64_t* my_q = q_smem + (warp - 2) * SC_QCAP;                 // queued keys ...
     unsigned short* my_qu = reinterpret_cast<unsigned short*>(q_smem + SC_EPI_WARPS * SC_QCAP) + (warp - 2) * SC_QCAP;  // ... and their users
     const uint32_t lt_mask = (1u << lane) - 1u;
     const float osc = H ? p.out_scale * (p.out_scale_dev ? __ldg(p.out_scale_dev) : 1.0f) : 1.0f;
-    // per-tile constants are fetched one tile ahead into registers (b' of this lane's item; thresholds and seen-bitmap
-    // words of users lane, lane + 32, ... of the warp's column quarter) so that no global load is waited for in the loop
     float nbias;
-    uint2 nv[CW / 32];
-    float ntz[CW / 32];
-    auto fetch_users = [&](int t, int i, uint2* v, float* tz) {   // user lane + 32 i of the warp's quarter in unit t
+    auto fetch_users = [&](int t, int i, uint2* v) {   // first slice: user lane + 32 i of the warp's quarter in unit t
       const int row = unit_row0(t) + cq * CW + lane + 32 * i;
       const int ib = (unit_item0(t) >> 5) + q;     // 32-item block of this warp == word of the seen bitmap
       *v = make_uint2(0xffffffffu, 0u);
-      if (FILTER) *tz = __int_as_float(0x7f800000);              // users beyond the block never pass
       if (t < n_units && row < p.M) {
         v->x = __ldg(p.tau_ord + row);
         if (p.seen_bits && !(p.debug & 2) && ib < p.words_per_row)
           v->y = __ldg(p.seen_bits + (int64_t)row * p.words_per_row + ib);
-        if (FILTER) *tz = (p.debug & 8) ? __int_as_float(0x7f800000) : __ldg(p.tau_z + row);
       }
+    };
+    auto prefetch_users = [&](int t, int buf) {        // FILTER: (seen word, logit threshold) of unit t into buffer buf
+      const int ib = (unit_item0(t) >> 5) + q;
+#pragma unroll
+      for (int i = 0; i < CW / 32; i++) {
+        const int c = lane + 32 * i, row = unit_row0(t) + cq * CW + c;
+        uint2* dst = my_tau + buf * CW + c;
+        const uint32_t d32 = smem_u32(dst);
+        if (t < n_units && row < p.M && !(p.debug & 8)) {
+          if (p.seen_bits && !(p.debug & 2) && ib < p.words_per_row)
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d32), "l"(p.seen_bits + (int64_t)row * p.words_per_row + ib) : "memory");
+          else
+            dst->x = 0u;
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d32 + 4u), "l"(p.tau_z + row) : "memory");
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(my_tord + buf * CW + c)), "l"(p.tau_ord + row) : "memory");
+        } else {
+          *dst = make_uint2(0u, 0x7f800000u);          // users beyond the block never pass
+          my_tord[buf * CW + c] = 0xffffffffu;
+        }
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
     };
     auto fetch_consts = [&](int t) {
       const int item = unit_item0(t) + q * 32 + lane;
       nbias = (t < n_units && item < p.item_end) ? __ldg(p.bias + item) : 0.f;
-      if (FILTER) {
-#pragma unroll
-        for (int i = 0; i < CW / 32; i++) fetch_users(t, i, &nv[i], &ntz[i]);
-      }
     };
     fetch_consts(unit0);
+    if (FILTER) prefetch_users(unit0, 0);
     int qn = 0;                                    // entries in the queue (warp-uniform); it lives across tiles and is
     auto flush_queue = [&]() {                     // flushed when the next row of keys would not fit, and at the end
       sc_flush_queue(my_q, my_qu, qn, p.cnt, p.lists, p.cap);
@@ -271,20 +293,23 @@ k_umma_score_filter(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
       const bool item_ok = item < p.item_end;
       const float bias = nbias;
       __syncwarp();
+      const uint2* cur_sz = my_tau + (tl & 1) * CW;      // FILTER: this tile's (seen word, logit threshold) ...
+      const uint32_t* cur_tord = my_tord + (tl & 1) * CW;   // ... and exact thresholds
+      if (FILTER) {
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncwarp();
+        prefetch_users(t + unit_stride, (tl & 1) ^ 1);
+      } else {                                     // the short first slice fetches in place
 #pragma unroll
-      for (int i = 0; i < CW / 32; i++) {
-        if (FILTER) {
-          my_tau[lane + 32 * i] = nv[i];
-          my_tz[lane + 32 * i] = ntz[i];
-        } else {                                   // the short first slice fetches in place (registers are scarce there)
-          uint2 v; float tz;
-          fetch_users(t, i, &v, &tz);
+        for (int i = 0; i < CW / 32; i++) {
+          uint2 v;
+          fetch_users(t, i, &v);
           my_tau[lane + 32 * i] = v;
         }
+        __syncwarp();
       }
-      __syncwarp();
       fetch_consts(t + unit_stride);
-      mbar_wait(tfull_bar(as), (tl >> 1) & 1);
+      mbar_wait_sleep(tfull_bar(as), (tl >> 1) & 1, p.wait_ns);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN + cq * CW);
       uint32_t rn[16];
@@ -298,33 +323,48 @@ k_umma_score_filter(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
         for (int j = 0; j < 16; j++) r[j] = rn[j];
         if (cl + 16 < CW) tmem_ld16_issue(tbase + cl + 16, rn);
         if (FILTER) {
-          // Pre-filter on the logit: one fma, one compare and one vote per element.  The exact test -- the fp32 sigmoid
-          // value as an orderable integer against the user's threshold, the seen-bitmap knock-out -- runs only for the
-          // (user, 32-item) rows in which some lane passes; the keys that really pass are queued.
+          // Pre-filter on the logit: one fma and one compare per element, one vote per four users.  The exact test --
+          // the fp32 sigmoid value as an orderable integer against the user's threshold, the seen-bitmap knock-out --
+          // runs only for groups of four (user, 32-item) rows in which some lane passes, the four sigmoid chains side
+          // by side; the keys that really pass are queued.
 #pragma unroll
           for (int j4 = 0; j4 < 16; j4 += 4) {
-            const float4 tz4 = *reinterpret_cast<const float4*>(my_tz + cl + j4);    // broadcast read
-            const float tz[4] = {tz4.x, tz4.y, tz4.z, tz4.w};
+            const uint4 sz01 = *reinterpret_cast<const uint4*>(cur_sz + cl + j4);     // broadcast reads: (seen, tz) x 4
+            const uint4 sz23 = *reinterpret_cast<const uint4*>(cur_sz + cl + j4 + 2);
+            const float tz[4] = {__uint_as_float(sz01.y), __uint_as_float(sz01.w), __uint_as_float(sz23.y),
+                                 __uint_as_float(sz23.w)};
+            const uint32_t seen[4] = {sz01.x, sz01.z, sz23.x, sz23.z};
+            float z[4];
+            bool anyf = false;
 #pragma unroll
             for (int jj = 0; jj < 4; jj++) {
-              const int j = j4 + jj;
-              const float z = H ? fmaf(__uint_as_float(r[j]), osc, bias) : __uint_as_float(r[j]) + bias;
-              if (__any_sync(0xffffffffu, z >= tz[jj])) {
-                const float pr = sc_rcp(1.0f + sc_ex2(z * -1.4426950408889634f));     // sigmoid, > 0
-                const uint32_t ord = __float_as_uint(pr) | 0x80000000u;               // f2ord of a non-negative float
-                const uint2 ts = my_tau[cl + j];                                      // broadcast read
-                const bool pass = item_ok && !((ts.y >> lane) & 1u) && (ord >= ts.x) && !(p.debug & 1);
-                const uint32_t bal = __ballot_sync(0xffffffffu, pass);
-                if (bal != 0u) {                   // warp-uniform
-                  const int n = __popc(bal);
-                  if (qn + n > SC_QCAP) flush_queue();
-                  if (pass) {
-                    const int e = qn + __popc(bal & lt_mask);
-                    my_q[e] = ((uint64_t)ord << 32) | (uint32_t)item;
-                    my_qu[e] = (unsigned short)(row + j);
-                  }
-                  qn += n;
+              z[jj] = H ? fmaf(__uint_as_float(r[j4 + jj]), osc, bias) : __uint_as_float(r[j4 + jj]) + bias;
+              anyf |= z[jj] >= tz[jj];
+            }
+            if (!__any_sync(0xffffffffu, anyf)) continue;
+            uint32_t ord[4], bal[4];
+#pragma unroll
+            for (int jj = 0; jj < 4; jj++) {
+              const float pr = sc_rcp(1.0f + sc_ex2(z[jj] * -1.4426950408889634f));   // sigmoid, > 0
+              ord[jj] = __float_as_uint(pr) | 0x80000000u;                            // f2ord of a non-negative float
+            }
+#pragma unroll
+            for (int jj = 0; jj < 4; jj++) {
+              const uint32_t tau = cur_tord[cl + j4 + jj];                            // broadcast read
+              const bool pass = item_ok && !((seen[jj] >> lane) & 1u) && (ord[jj] >= tau) && !(p.debug & 1);
+              bal[jj] = __ballot_sync(0xffffffffu, pass);
+            }
+#pragma unroll
+            for (int jj = 0; jj < 4; jj++) {
+              if (bal[jj] != 0u) {                 // warp-uniform
+                const int n = __popc(bal[jj]);
+                if (qn + n > SC_QCAP) flush_queue();
+                if ((bal[jj] >> lane) & 1u) {
+                  const int e = qn + __popc(bal[jj] & lt_mask);
+                  my_q[e] = ((uint64_t)ord[jj] << 32) | (uint32_t)item;
+                  my_qu[e] = (unsigned short)(row + j4 + jj);
                 }
+                qn += n;
               }
             }
           }
@@ -443,12 +483,18 @@ int launch_umma_score_filter(drb_ctx* ctx, const UmmaOperands& o, int n_users, i
   p.M = n_users; p.item_begin = item_begin; p.item_end = item_end; p.Kred = Kred; p.bias = bias;
   p.seen_bits = seen_bits; p.words_per_row = words_per_row; p.tau_ord = tau_ord; p.tau_z = tau_z; p.cnt = cnt; p.lists = lists; p.cap = cap;
   p.debug = getenv("DRB_SCORE_DEBUG") ? atoi(getenv("DRB_SCORE_DEBUG")) : 0;
+  p.wait_ns = getenv("DRB_WAIT_NS") ? (uint32_t)atoi(getenv("DRB_WAIT_NS")) : 100u;
   p.out_scale = o.out_scale; p.out_scale_dev = o.out_scale_dev;
   if (n_users > 65536) return drb_fail(DRB_E_INVALID, "score_filter: at most 65536 users per block");
+  static const int kb_env = getenv("DRB_SCORE_KB") ? atoi(getenv("DRB_SCORE_KB")) : 32;
 #define DRB_SCORE_CASE(F_)                                                             \
   {                                                                                    \
     if (o.half) {                                                                      \
-      if (n_users > 128) return run_score<256, 32, 2, true, F_>(ctx, o, p, n_items);   \
+      if (n_users > 128) {                                                             \
+        /* DRB_SCORE_KB=16: five 32 KB stages instead of two 64 KB ones (measured slower) */ \
+        if (kb_env == 16) return run_score<256, 16, 2, true, F_>(ctx, o, p, n_items);  \
+        return run_score<256, 32, 2, true, F_>(ctx, o, p, n_items);                    \
+      }                                                                                \
       return run_score<128, 32, 1, true, F_>(ctx, o, p, n_items);                      \
     }                                                                                  \
     if (n_users > 128) return run_score<256, 32, 2, false, F_>(ctx, o, p, n_items);    \
