@@ -409,6 +409,72 @@ __global__ void __launch_bounds__(256) k_select_lists(SelectArgs a, int n_users)
   }
 }
 
+// Threshold select (final == 0) for lists of up to 1024 keys, one WARP per user and no shared memory: the 32-bit
+// orderable scores sit in registers (SLOTS per lane), the k-th largest is found bit by bit from the top (count the
+// keys that match the prefix so far and have the bit set; keep the bit when at least `need` do), then the list is
+// re-read and compacted in place to the keys >= tau.  Same results as select_user (the k-th largest value is unique),
+// about a third of its time: the CTA form spends its time in __syncthreads and shared-memory histograms.
+template <int SLOTS>
+__device__ __forceinline__ uint32_t warp_kth_largest(const uint64_t* list, int c, int k, int lane) {
+  uint32_t v[SLOTS];
+#pragma unroll
+  for (int i = 0; i < SLOTS; i++) {
+    const int idx = lane + 32 * i;
+    v[i] = idx < c ? (uint32_t)(list[idx] >> 32) : 0u;        // valid scores have the top bit set: 0 never counts
+  }
+  uint32_t prefix = 0u;
+  int need = k;
+#pragma unroll 1
+  for (int bit = 31; bit >= 0; bit--) {
+    const uint32_t cand = prefix | (1u << bit), hi = ~((1u << bit) - 1u);
+    int n1 = 0;
+#pragma unroll
+    for (int i = 0; i < SLOTS; i++) n1 += ((v[i] & hi) == cand);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) n1 += __shfl_xor_sync(0xffffffffu, n1, o);
+    if (n1 >= need) prefix = cand; else need -= n1;
+  }
+  return prefix;
+}
+
+__global__ void __launch_bounds__(256) k_select_tau_warp(SelectArgs a, int n_users) {
+  const int lane = threadIdx.x & 31;
+  const int u = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (u >= n_users) return;
+  const int c = a.cnt[u];
+  uint64_t* list = a.lists + (int64_t)u * a.cap;
+  if (c > a.cap) {                  // overflow: nothing more is appended for this user; cnt stays > cap
+    if (lane == 0) { a.tau_ord[u] = 0xffffffffu; a.tau_z[u] = __int_as_float(0x7f800000); }
+    return;
+  }
+  if (c > 1024) {                   // too long for the registers: the CTA form (second launch) takes it
+    if (lane == 0) a.big_users[atomicAdd(a.big_count, 1)] = u;
+    return;
+  }
+  if (c < a.k) {                    // fewer than k so far: keep everything, no threshold yet
+    if (lane == 0) { a.tau_ord[u] = 0u; a.tau_z[u] = __int_as_float(0xff800000); }
+    return;
+  }
+  uint32_t t32;
+  if (c <= 256) t32 = warp_kth_largest<8>(list, c, a.k, lane);
+  else if (c <= 512) t32 = warp_kth_largest<16>(list, c, a.k, lane);
+  else t32 = warp_kth_largest<32>(list, c, a.k, lane);
+  // compaction in place: chunk i is read completely before anything is written, and what is kept lands at positions
+  // below the chunk's end
+  int n_sel = 0;
+  for (int i0 = 0; i0 < c; i0 += 32) {
+    const int idx = i0 + lane;
+    const uint64_t key = idx < c ? list[idx] : 0ull;
+    const bool keep = idx < c && (uint32_t)(key >> 32) >= t32;
+    const uint32_t m = __ballot_sync(0xffffffffu, keep);
+    __syncwarp();
+    if (keep) list[n_sel + __popc(m & ((1u << lane) - 1u))] = key;
+    n_sel += __popc(m);
+    __syncwarp();
+  }
+  if (lane == 0) { a.cnt[u] = n_sel; a.tau_ord[u] = t32; a.tau_z[u] = logit_lower_bound(t32); }
+}
+
 // Exact fallback for users whose candidate list overflowed: fills the user's claimed scratch row with the scores
 // sigmoid(h_u . W'_i + b'_i) over the whole catalog (one warp per item, fp32 FMA); k_topk (indirect) then ranks the row.
 __global__ void __launch_bounds__(256) k_fallback_scores(const float* h, int ld_h, const float* table, int ld_t,
@@ -487,7 +553,12 @@ int launch_select_lists(drb_ctx* ctx, uint64_t* lists, int cap, int32_t* cnt, ui
   a.fb_users = fb_users; a.fb_count = fb_count; a.fb_max = fb_max;
   a.sm_cap = std::min(cap, 1024); a.big_users = big_users; a.big_count = big_count;
   drb_prof_scope prof_(ctx, final ? "k_select_lists_final" : "k_select_lists_tau");
-  k_select_lists<<<n, 64, (size_t)(a.sm_cap + (final ? a.P : 0)) * sizeof(uint64_t), ctx->stream>>>(a, n);
+  static const bool warp_form = !(getenv("DRB_SELECT_WARP") && atoi(getenv("DRB_SELECT_WARP")) == 0);
+  if (!final && warp_form && cap >= 1024) {
+    k_select_tau_warp<<<(n + 7) / 8, 256, 0, ctx->stream>>>(a, n);
+  } else {
+    k_select_lists<<<n, 64, (size_t)(a.sm_cap + (final ? a.P : 0)) * sizeof(uint64_t), ctx->stream>>>(a, n);
+  }
   DRB_LAUNCH_CHECK(ctx, "k_select_lists");
   if (cap > a.sm_cap) {             // users whose list is longer than 1024 keys (none, usually: the CTAs leave at once)
     a.big_pass = 1;
