@@ -40,7 +40,8 @@ C2 = dict(name='c2', title='dmf_ml1m_shape', origin='BASELINE.json configs[1]', 
 C4S = dict(C3, name='c4_sampled', title='ranking_evaluation_leave1out_100neg', origin='BASELINE.json configs[3]',
            model='rank_sampled', n_neg=100, k=10)
 C4F = dict(C3, name='c4_full', title='full_catalog_top100', origin='BASELINE.json configs[3]', model='topk', k=100,
-           score_batch=int(os.environ.get('DRB_BENCH_SCORE_BATCH', 16384)))   # users per scoring block (fit(score_batch=))
+           score_batch=int(os.environ.get('DRB_BENCH_SCORE_BATCH', -1)))   # users per scoring block (fit(score_batch=));
+                                                                           # -1: one 256-user tile per pair of SMs
 C5 = dict(name='c5', title='cdae_10m_x_1m_item_sharded', origin='BASELINE.json configs[4]', model='cdae_sharded',
           n_users=10_000_000, n_items=1_000_000, nnz=1_000_000_000, hidden=256, batch=4096, q=0.2, lr=1e-3, reg=1e-3,
           seed=10, zipf_a=1.0, neg_total=1024)
@@ -640,7 +641,11 @@ def rank_setup(cfg, D, arrays):
     t_split = time.perf_counter() - t0
     train.assign_internal_ids()
     m = drb.CDAE(hidden_factors=cfg['hidden'], seed=cfg['seed'], verbose=False, rng_mode='philox', device=str(D.dev))
-    m.fit(train, epochs=3, batch_size=4096, score_batch=cfg.get('score_batch', 0))
+    sb = cfg.get('score_batch', 0)
+    if sb < 0:      # the score filter runs CTA pairs over 256-user tiles: a block of (SMs / 2) tiles is one tile per pair
+        import torch
+        sb = (torch.cuda.get_device_properties(D.dev).multi_processor_count // 2) * 256
+    m.fit(train, epochs=3, batch_size=4096, score_batch=sb)
     return train, test, m, t_split
 
 

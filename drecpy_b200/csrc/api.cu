@@ -379,6 +379,7 @@ int drb_cdae_create(drb_ctx* ctx, const drb_cdae_desc* desc, drb_cdae** out) {
     // is ~2 waves of the SM count (the kernel is L2/HBM bandwidth bound, one CTA per SM)
     const int mt = (desc->max_batch + 127) / 128;
     m->splits = std::max(1, std::min(32, std::min((2 * ctx->sm_count) / mt, desc->n_items / 256)));
+    if (getenv("DRB_DH_SPLITS")) m->splits = std::max(1, std::min(32, atoi(getenv("DRB_DH_SPLITS"))));   // tuning override
   }
   if (sampled) m->splits = 1;
   m->ws = cdae_carve(desc->workspace, L, desc->n_items, desc->hidden, desc->max_batch, desc->label_mode, m->splits,
@@ -636,7 +637,8 @@ static int cdae_step_impl(drb_cdae* m, const int32_t* uids, const int32_t* keep_
     // e.g. 209 item tiles on 148 SMs would run as two uneven waves: split the batch reduction so the grid is ~2 waves
     // (the partial products accumulate with vector atomics into the pre-zeroed gradient)
     const int mt2 = (I + 127) / 128;
-    const int s2 = batch >= 1024 ? std::max(1, std::min({16, (2 * ctx->sm_count + mt2 - 1) / mt2, batch / 512})) : 1;
+    static const int s2_env = getenv("DRB_DW_SPLITS") ? atoi(getenv("DRB_DW_SPLITS")) : 0;             // tuning override
+    const int s2 = batch >= 1024 ? std::max(1, std::min({16, s2_env > 0 ? s2_env : (2 * ctx->sm_count + mt2 - 1) / mt2, batch / 512})) : 1;
     const bool colsum = cdae_colsum_in_loss(m->d.hidden);
     if (m->half && dzh.i_hi) {      // A = the [item tile][user block] copy of dz (K-major over users), B = h^T
       UmmaOperands oh{dzh.i_hi, dzh.i_lo, 64, w.hT_hi, w.hT_lo, m->bp8, n2};

@@ -66,44 +66,50 @@ __global__ void __launch_bounds__(128) k_dmf_head(DmfHeadArgs h) {
 constexpr int kBwdRows = 8, kBwdThreads = 256, kBwdMaxW0 = 128, kBwdMaxW1 = 64;
 
 __global__ void __launch_bounds__(kBwdThreads) k_dmf_tower_bwd(DmfTowerBwd t0, DmfTowerBwd t1, int n) {
-  __shared__ float s_act[kBwdMaxW0], s_d1[kBwdMaxW1], s_d0[kBwdMaxW0];
+  // all kBwdRows rows of the CTA are staged at once (one barrier): the C2 step is latency bound, and a row-by-row
+  // loop with two barriers per row was the longest kernel of the step
+  __shared__ float s_act[kBwdRows][kBwdMaxW0], s_d1[kBwdRows][kBwdMaxW1], s_gb0[kBwdMaxW0];
   const DmfTowerBwd t = blockIdx.y ? t1 : t0;
   const int tid = threadIdx.x;
-  const int n_el = t.w0 * t.w1;                       // elements of dK1, element e = (c, j) = (e / w1, e % w1)
-  float gk[(kBwdMaxW0 * kBwdMaxW1) / kBwdThreads];    // this thread's elements e = tid + i * kBwdThreads
-#pragma unroll
-  for (int i = 0; i < (kBwdMaxW0 * kBwdMaxW1) / kBwdThreads; i++) gk[i] = 0.f;
-  float gb1 = 0.f, gb0 = 0.f;                         // column tid of db1 / db0
-  const int r0 = blockIdx.x * kBwdRows, r1 = min(n, r0 + kBwdRows);
-  for (int r = r0; r < r1; r++) {
-    if (tid < t.w0) s_act[tid] = t.act0[(int64_t)r * t.ld0 + tid];
-    if (tid < t.w1) s_d1[tid] = t.dpre1[(int64_t)r * t.ld1 + tid];
-    __syncthreads();
-    if (tid < t.ld0) {
-      float d = 0.f;
-      if (tid < t.w0 && s_act[tid] > 0.f) {
-        const float* krow = t.k1 + (int64_t)tid * t.ld1;
-        for (int j = 0; j < t.w1; j++) d = fmaf(s_d1[j], __ldg(krow + j), d);
-      }
-      t.dpre0[(int64_t)r * t.ld0 + tid] = d;
-      gb0 += d;
-    }
-    if (tid < t.w1) gb1 += s_d1[tid];
-#pragma unroll
-    for (int i = 0; i < (kBwdMaxW0 * kBwdMaxW1) / kBwdThreads; i++) {
-      const int e = tid + i * kBwdThreads;
-      if (e < n_el) gk[i] = fmaf(s_act[e / t.w1], s_d1[e % t.w1], gk[i]);
-    }
-    __syncthreads();
+  const int r0 = blockIdx.x * kBwdRows, nr = min(n, r0 + kBwdRows) - r0;
+  for (int i = tid; i < kBwdRows * t.w0; i += kBwdThreads) {
+    const int r = i / t.w0, c = i % t.w0;
+    s_act[r][c] = r < nr ? t.act0[(int64_t)(r0 + r) * t.ld0 + c] : 0.f;
   }
-  (void)s_d0;
-#pragma unroll
-  for (int i = 0; i < (kBwdMaxW0 * kBwdMaxW1) / kBwdThreads; i++) {
-    const int e = tid + i * kBwdThreads;
-    if (e < n_el && gk[i] != 0.f) atomicAdd(t.g_k1 + (int64_t)(e / t.w1) * t.ld1 + (e % t.w1), gk[i]);
+  for (int i = tid; i < kBwdRows * t.w1; i += kBwdThreads) {
+    const int r = i / t.w1, j = i % t.w1;
+    s_d1[r][j] = r < nr ? t.dpre1[(int64_t)(r0 + r) * t.ld1 + j] : 0.f;
   }
-  if (tid < t.w1) atomicAdd(t.g_b1 + tid, gb1);
-  if (tid < t.w0) atomicAdd(t.g_b0 + tid, gb0);
+  if (tid < kBwdMaxW0) s_gb0[tid] = 0.f;
+  __syncthreads();
+  // dpre0[r][c] = (dpre1[r] . K1[c]) * [act0[r][c] > 0]; pad columns (c >= w0) are written as zeros
+  for (int o = tid; o < nr * t.ld0; o += kBwdThreads) {
+    const int r = o / t.ld0, c = o % t.ld0;
+    float d = 0.f;
+    if (c < t.w0 && s_act[r][c] > 0.f) {
+      const float* krow = t.k1 + (int64_t)c * t.ld1;
+      for (int j = 0; j < t.w1; j++) d = fmaf(s_d1[r][j], __ldg(krow + j), d);
+      atomicAdd(&s_gb0[c], d);
+    }
+    t.dpre0[(int64_t)(r0 + r) * t.ld0 + c] = d;
+  }
+  // dK1[c][j] += sum_r act0[r][c] dpre1[r][j]  (rows past the batch were staged as zeros)
+  const int n_el = t.w0 * t.w1;
+  for (int e = tid; e < n_el; e += kBwdThreads) {
+    const int c = e / t.w1, j = e % t.w1;
+    float g = 0.f;
+#pragma unroll
+    for (int r = 0; r < kBwdRows; r++) g = fmaf(s_act[r][c], s_d1[r][j], g);
+    if (g != 0.f) atomicAdd(t.g_k1 + (int64_t)c * t.ld1 + j, g);
+  }
+  if (tid < t.w1) {
+    float gb1 = 0.f;
+#pragma unroll
+    for (int r = 0; r < kBwdRows; r++) gb1 += s_d1[r][tid];
+    atomicAdd(t.g_b1 + tid, gb1);
+  }
+  __syncthreads();
+  if (tid < t.w0) atomicAdd(t.g_b0 + tid, s_gb0[tid]);
 }
 
 }  // namespace

@@ -47,6 +47,7 @@ struct UmmaParams {
   int a_tiled_nib;          // > 0: A lives in a tile-major dz layout (128-row tiles of 32 floats / 64 halfs) with this many
                             // column blocks per row tile
   float out_scale; const float* out_scale_dev;   // accumulators are multiplied by out_scale * (*out_scale_dev)
+  int stages;               // pipeline stages in use (<= Smem::STAGES): 3 lets two CTAs share an SM (DRB_UMMA_STAGES)
 };
 
 template <int BN, bool A_MN, int KB, int CL, bool H>
@@ -61,11 +62,12 @@ k_umma_gemm(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
   const bool leader = cta_rank == 0;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;   // SWIZZLE_128B atoms need 1024-byte alignment
-  const uint32_t bars = base + S::STAGES * S::STAGE_BYTES;       // full[STAGES], empty[STAGES], tmem_full, tmem_ptr
+  const int NS = p.stages;
+  const uint32_t bars = base + NS * S::STAGE_BYTES;              // full[NS], empty[NS], tmem_full, tmem_ptr
   auto full_bar = [&](int s) { return bars + 8u * s; };
-  auto empty_bar = [&](int s) { return bars + 8u * (S::STAGES + s); };
-  const uint32_t tmem_full_bar = bars + 8u * (2 * S::STAGES);
-  const uint32_t tmem_ptr_addr = bars + 8u * (2 * S::STAGES + 1);
+  auto empty_bar = [&](int s) { return bars + 8u * (NS + s); };
+  const uint32_t tmem_full_bar = bars + 8u * (2 * NS);
+  const uint32_t tmem_ptr_addr = bars + 8u * (2 * NS + 1);
   volatile uint32_t* tmem_ptr_generic =
       reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_ptr_addr - smem_u32(smem_raw)));
 
@@ -79,7 +81,7 @@ k_umma_gemm(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
   constexpr uint32_t TMEM_COLS = (BN <= 32) ? 32 : (BN <= 64) ? 64 : (BN <= 128) ? 128 : 256;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < S::STAGES; s++) {
+    for (int s = 0; s < NS; s++) {
       mbar_init(full_bar(s), 1);
       mbar_init(empty_bar(s), 1);
     }
@@ -109,8 +111,8 @@ k_umma_gemm(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
     // ------------------------------------------------------------------ TMA producer
     if (lane == 0) {
       for (int i = 0; i < nkb; i++) {
-        const int s = i % S::STAGES;
-        const uint32_t ph = (i / S::STAGES) & 1;
+        const int s = i % NS;
+        const uint32_t ph = (i / NS) & 1;
         mbar_wait(empty_bar(s), ph ^ 1);
         if (leader) mbar_expect_tx(full_bar(s), CL * S::STAGE_BYTES);
         const uint32_t sa_hi = base + s * S::STAGE_BYTES, sa_lo = sa_hi + S::A_BYTES;
@@ -153,8 +155,8 @@ k_umma_gemm(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
       // a_major [15], b_major [16], N>>3 [17,23), M>>4 [24,29)
       const uint32_t idesc = make_idesc<H>(BM * CL, BN, A_MN);
       for (int i = 0; i < nkb; i++) {
-        const int s = i % S::STAGES;
-        const uint32_t ph = (i / S::STAGES) & 1;
+        const int s = i % NS;
+        const uint32_t ph = (i / NS) & 1;
         mbar_wait(full_bar(s), ph);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t sa_hi = base + s * S::STAGE_BYTES, sa_lo = sa_hi + S::A_BYTES;
@@ -343,9 +345,13 @@ __global__ void k_publish_scale(const uint32_t* __restrict__ max_bits, float* __
 }
 
 template <int BN, bool A_MN, int KB, int CL, bool H>
-int run_umma(drb_ctx* ctx, const UmmaOperands& o, const UmmaParams& p, int* n_blocks_out) {
+int run_umma(drb_ctx* ctx, const UmmaOperands& o, const UmmaParams& p_in, int* n_blocks_out) {
   constexpr int BK = KB;
-  constexpr int SMEM = Smem<BN, KB, CL>::TOTAL;
+  using SM = Smem<BN, KB, CL>;
+  static const int st_env = getenv("DRB_UMMA_STAGES") ? atoi(getenv("DRB_UMMA_STAGES")) : 0;
+  UmmaParams p = p_in;
+  p.stages = (st_env >= 2 && st_env < SM::STAGES) ? st_env : SM::STAGES;
+  const int SMEM = p.stages * SM::STAGE_BYTES + 1024 + 256;
   CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
   int r;
   if (H) {      // fp16 hi / lo operands; tile-major dz = a [tiles * 128, 64 halfs] tensor
@@ -385,8 +391,8 @@ int run_umma(drb_ctx* ctx, const UmmaOperands& o, const UmmaParams& p, int* n_bl
   auto kern = k_umma_gemm<BN, A_MN, KB, CL, H>;
   static bool attr_set = false;   // per template instantiation
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
-    if (e != cudaSuccess) return drb_fail(DRB_E_CUDA, "cudaFuncSetAttribute(smem=%d) failed: %s", SMEM, cudaGetErrorString(e));
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::TOTAL);
+    if (e != cudaSuccess) return drb_fail(DRB_E_CUDA, "cudaFuncSetAttribute(smem=%d) failed: %s", SM::TOTAL, cudaGetErrorString(e));
     attr_set = true;
   }
   drb_prof_scope prof_(ctx, o.name ? o.name : (A_MN ? "k_umma_gemm_mn" : "k_umma_gemm_kk"));

@@ -17,12 +17,12 @@ epochs = int(sys.argv[2]) if len(sys.argv) > 2 else 3
 u, i, v = drb.synthetic_interactions(138493, 26744, 20_000_000, seed=10, zipf_a=1.0)
 ds = drb.InteractionData(u, i, v)
 m = drb.CDAE(hidden_factors=200, seed=10, verbose=False, rng_mode='philox')
-m.fit(ds, epochs=epochs, batch_size=4096)
+m.fit(ds, epochs=epochs, batch_size=4096, score_batch=int(os.environ.get('DRB_BENCH_SCORE_BATCH', 18944)))
 uids = torch.arange(n_users, dtype=torch.int32, device='cuda')
 lib = _lib.load()
 for dbg in os.environ.get('DBG_LIST', '0').split(','):
     os.environ['DRB_SCORE_DEBUG'] = dbg
-    m.topk_batch(uids[:8192], 100, novelty=True, return_device=True)
+    m.topk_batch(uids[:min(n_users, 18944)], 100, novelty=True, return_device=True)
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
