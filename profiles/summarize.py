@@ -52,5 +52,32 @@ def full(path):
                 print(f'   {h:80s} {d[h]:>18s} {u}')
 
 
+def traffic(path):
+    """dram bytes (read + write) per launch of the captured kernels, as the JSON bench.py reads for roofline.traffic
+    (keys = the names libdrb's own profiler uses)."""
+    import json
+    import re
+    out = subprocess.run(['ncu', '-i', path, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
+    rows = list(csv.reader(io.StringIO(out)))
+    header, units = rows[0], rows[1]
+    scale = {'byte': 1, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9}
+    res = {}
+    for r in rows[2:]:
+        d = dict(zip(header, r))
+        u = dict(zip(header, units))
+        name = d.get('Kernel Name', '')
+        key = re.search(r'(k_[a-z0-9_]+)', name).group(1)
+        if key == 'k_umma_gemm':                     # template argument 2: A read MN-major = dW'^T, K-major = dh
+            args = re.search(r'k_umma_gemm<([^>]*)>', name).group(1).replace('(int)', '').replace('(bool)', '').split(',')
+            key += '_dw' if args[1].strip() in ('1', 'true') else '_dh'
+        key = {'k_gather_chunks': 'k_gather', 'k_scatter_chunks': 'k_scatter'}.get(key, key)
+        tot = 0.0
+        for m in ('dram__bytes_read.sum', 'dram__bytes_write.sum'):
+            tot += float(d[m].replace(',', '')) * scale[u[m]]
+        res[key] = int(tot)
+    print(json.dumps({'source': f'{path} (ncu --set full --clock-control none, bench.py --steps 2 --warmup 3, ml-20m shape, '
+                                'B=4096)', 'dram_bytes_per_launch': res}, indent=1))
+
+
 if __name__ == '__main__':
-    {'launches': launches, 'full': full}[sys.argv[1]](sys.argv[2])
+    {'launches': launches, 'full': full, 'traffic': traffic}[sys.argv[1]](sys.argv[2])
