@@ -10,7 +10,7 @@ New keywords, all with reference-faithful defaults:
                             per-user targets of the CDAE paper
   rng_mode='mt19937'        bit-exact replay of the reference's corruption stream (n_items draws per sampled user,
                             cdae.py:63-64) on the host; 'mt19937_device' = the same stream, bit for bit, replayed on
-                            the GPU by jump-ahead (mask_stream.py: ~0.2 ms instead of ~0.3 s per 4096-user step);
+                            the GPU by jump-ahead (mask_stream.py: 1.4 ms instead of ~0.3 s per 4096-user step);
                             'philox' = counter-based mask generated on the GPU (documented deviation)
   adam_t='per_variable'     Adam step counter advances once per variable (Q2); 'per_step' = textbook Adam
   init_weights=None         dict with any of W, W_, V, b, b_ (reference shapes) to inject initial weights

@@ -4,7 +4,7 @@ DRecPy/Recommender/cdae.py:63-64 draws `self._rng.uniform(0, 1)` once per item f
 sequential random.Random of recommender_abc.py:74.  This class keeps that stream on the GPU: the current position as a
 624-word window, the jump polynomials of mt_jump.cpp for the step's segments (computed once per batch size, on the
 host), and one kernel launch per step (drb_mt_keep_device) that writes the same keep bytes the host replay
-(drb_cdae_corruption_keep_mt) would -- bit for bit, ~0.2 ms instead of ~0.3 s per step at the ml-20m shape.
+(drb_cdae_corruption_keep_mt) would -- bit for bit, 1.4 ms instead of ~0.3 s per step at the ml-20m shape.
 """
 import ctypes as C
 from fractions import Fraction
