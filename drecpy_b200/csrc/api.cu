@@ -190,6 +190,7 @@ struct CdaeWs {
   float *h_hi, *h_lo, *hT_hi, *hT_lo, *w2t_hi, *w2t_lo, *wT_hi, *wT_lo, *dzt_hi, *dzt_lo;   // dzt_*: tile-major dz
   int64_t hT_floats, wT_floats;
   uint32_t* label_bits;
+  uint32_t* row_touched;         // bit u: dV[u] received a gradient row this step (see AdamArgs::row_mask)
   int32_t *uids, *keep_off, *aux_i32, *chunk_off;
   uint8_t* keep;
   int64_t bytes;
@@ -233,13 +234,14 @@ static int64_t cdae_keep_cap(int32_t n_items, int32_t max_batch) {
   return std::min<int64_t>((int64_t)max_batch * n_items, (int64_t)1 << 30);
 }
 
-static CdaeWs cdae_carve(void* base, const drb_cdae_layout_t& L, int n_items, int hidden, int max_batch,
+static CdaeWs cdae_carve(void* base, const drb_cdae_layout_t& L, int n_users, int n_items, int hidden, int max_batch,
                          int label_mode, int splits, int sm_count, bool umma, bool sampled = false) {
   Carver c(base);
   CdaeWs w{};
   const int64_t B = max_batch;
   const int mt = (max_batch + 127) / 128;
   w.h = c.take<float>(B * L.ld);
+  w.row_touched = c.take<uint32_t>((n_users + 31) / 32 + 8);
   // sampled-output models never form batch x items matrices: no dz, no per-tile column partials, a batch-sized loss buffer
   w.dz = c.take<float>(sampled ? 64 : B * L.items_pad);
   if (sampled) {
@@ -316,13 +318,13 @@ int64_t drb_cdae_workspace_bytes(int32_t n_users, int32_t n_items, int32_t hidde
   drb_cdae_layout_t L;
   if (drb_cdae_layout(n_users, n_items, hidden, &L) || max_batch <= 0) return -1;
   // worst case over label modes and split counts (splits <= 32, 148+ SMs -> use 256 as an upper bound)
-  return cdae_carve(nullptr, L, n_items, hidden, max_batch, DRB_LABEL_PER_USER, 32, 256, true).bytes;
+  return cdae_carve(nullptr, L, n_users, n_items, hidden, max_batch, DRB_LABEL_PER_USER, 32, 256, true).bytes;
 }
 
 int64_t drb_cdae_workspace_bytes_sampled(int32_t n_users, int32_t n_items, int32_t hidden, int32_t max_batch) {
   drb_cdae_layout_t L;
   if (drb_cdae_layout(n_users, n_items, hidden, &L) || max_batch <= 0) return -1;
-  return cdae_carve(nullptr, L, n_items, hidden, max_batch, DRB_LABEL_PER_USER, 1, 256, false, true).bytes;
+  return cdae_carve(nullptr, L, n_users, n_items, hidden, max_batch, DRB_LABEL_PER_USER, 1, 256, false, true).bytes;
 }
 
 int drb_cdae_create(drb_ctx* ctx, const drb_cdae_desc* desc, drb_cdae** out) {
@@ -382,9 +384,11 @@ int drb_cdae_create(drb_ctx* ctx, const drb_cdae_desc* desc, drb_cdae** out) {
     if (getenv("DRB_DH_SPLITS")) m->splits = std::max(1, std::min(32, atoi(getenv("DRB_DH_SPLITS"))));   // tuning override
   }
   if (sampled) m->splits = 1;
-  m->ws = cdae_carve(desc->workspace, L, desc->n_items, desc->hidden, desc->max_batch, desc->label_mode, m->splits,
-                     ctx->sm_count, m->use_umma, sampled);
+  m->ws = cdae_carve(desc->workspace, L, desc->n_users, desc->n_items, desc->hidden, desc->max_batch, desc->label_mode,
+                     m->splits, ctx->sm_count, m->use_umma, sampled);
   m->keep_cap = cdae_keep_cap(desc->n_items, desc->max_batch);
+  if (m->ws.bytes <= desc->workspace_bytes)
+    cudaMemsetAsync(m->ws.row_touched, 0, ((size_t)(desc->n_users + 31) / 32 + 8) * 4, ctx->stream);
   if (m->ws.bytes > desc->workspace_bytes) {
     int64_t need = m->ws.bytes;
     delete m;
@@ -519,6 +523,8 @@ static int cdae_step_impl(drb_cdae* m, const int32_t* uids, const int32_t* keep_
   const bool sparse_clear_v = !sharded && m->v_grad_clean;
   const int64_t clear_to = sparse_clear_v ? L.off_v : L.total;
   DRB_CUDA_TRY(ctx, cudaMemsetAsync(G + clear_from, 0, (size_t)(clear_to - clear_from) * sizeof(float), ctx->stream));
+  if (!sparse_clear_v)   // dV was cleared as a whole: no row holds a gradient
+    DRB_CUDA_TRY(ctx, cudaMemsetAsync(w.row_touched, 0, ((size_t)(m->d.n_users + 31) / 32 + 8) * 4, ctx->stream));
   m->v_grad_clean = false;
   m->rows_uids = nullptr; m->rows_n = 0;
   m->reg_slots_clear = false;
@@ -721,6 +727,10 @@ static int cdae_step_impl(drb_cdae* m, const int32_t* uids, const int32_t* keep_
   sc.growbias = a->skip_user_grad ? nullptr : G + L.off_v;   // data parallel: user rows are exchanged instead
   sc.bias_rows = sharded ? a->v_rows : nullptr;              // item-sharded: only owned users' rows of V
   sc.chunk_off = w.chunk_off;                                // piece map of this batch (built in GRADS_A)
+  // plain single-process step: remember which rows of dV get a gradient, the Adam launch reads only those (the rest of
+  // dV is zero: it is re-zeroed row by row after every update)
+  const bool mask_rows = !sharded && !a->skip_user_grad;
+  sc.row_touched = mask_rows ? w.row_touched : nullptr;
   if ((r = launch_scatter(ctx, sc, batch))) return r;
   }  // GRADS_C / GRADS_C2 (data parallel: the caller exchanges dz1 rows and all-reduces dW, db here)
 
@@ -750,13 +760,17 @@ static int cdae_step_impl(drb_cdae* m, const int32_t* uids, const int32_t* keep_
       ad.seg[ns].regw = l2seg[sidx] ? 0.5f * c : 0.f;
     }
     ad.nseg = ns;
+    ad.row_mask = nullptr; ad.row_seg = -1;
+    if (!sharded && !a->skip_user_grad && first <= 4 && last >= 4) {     // segment 4 = V: only the sampled users' rows
+      ad.row_mask = w.row_touched; ad.row_seg = 4 - first; ad.row_len4 = ld / 4;
+    }
     ad.reg_part = w.reg_part + (int64_t)slot * R;
     return launch_adam(ctx, ad, n_out);
   };
   auto rezero_user_rows = [&]() -> int {      // leave dV all-zero again for the next step (see PREP)
     if (sharded) return DRB_OK;
     if (!a->skip_user_grad) {
-      if ((r = launch_zero_rows(ctx, G + L.off_v, uids, batch, ld))) return r;
+      if ((r = launch_zero_rows(ctx, G + L.off_v, uids, batch, ld, w.row_touched))) return r;
       m->v_grad_clean = true;
     } else if (m->rows_uids) {                // data parallel: the rows every rank added from the all-gathered list
       if ((r = launch_zero_rows(ctx, G + L.off_v, m->rows_uids, m->rows_n, ld))) return r;

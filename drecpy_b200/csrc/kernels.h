@@ -43,6 +43,8 @@ struct ScatterArgs {
   float* growbias;                    // may be NULL; [*, ld] += d[b] at rows[b]
   const int32_t* bias_rows;           // may be NULL; else the growbias row per batch row, -1 = skip (item-sharded)
   const int32_t* chunk_off;           // may be NULL; balanced form, see GatherArgs
+  uint32_t* row_touched = nullptr;    // may be NULL; bit r is set when growbias row r received a gradient (k_adam then
+                                      // knows which rows of a zero-initialised gradient table it has to read)
 };
 struct ScatterPair { ScatterArgs a[2]; };
 int launch_scatter(drb_ctx* ctx, const ScatterArgs& a, int n);
@@ -71,7 +73,7 @@ int launch_dz1(drb_ctx* ctx, const float* dh_part, int splits, const float* h, f
 // column partials of x[n, ld] per 32-row block (generic bias gradient)
 int launch_colpart(drb_ctx* ctx, const float* x, int n, int ld, float* colpart);
 // table[ids[r]][:] = 0 for r < n
-int launch_zero_rows(drb_ctx* ctx, float* table, const int32_t* ids, int n, int ld);
+int launch_zero_rows(drb_ctx* ctx, float* table, const int32_t* ids, int n, int ld, uint32_t* row_touched = nullptr);
 // out[i] = start + i
 int launch_iota(drb_ctx* ctx, int32_t* out, int n, int start);
 // out[e] = sum_s part[s][e] (e < n_elems); in-place sigmoid of x[n][ld] with columns >= width forced to 0
@@ -200,6 +202,9 @@ struct AdamArgs {
   // fin_reg_part: start of the partials to sum (NULL = reg_part).
   const float* fin_loss_part; int fin_n_loss; float fin_scale; int fin_n_reg; const float* fin_reg_part;
   float* fin_loss_out; unsigned int* fin_ticket;
+  // optional: segment `row_seg` is a [rows, 4 * row_len4] table whose gradient is zero except in the rows whose bit is
+  // set in row_mask (the user table of CDAE: only the sampled users' rows): the gradient of the other rows is not read
+  const uint32_t* row_mask = nullptr; int row_seg = -1; int row_len4 = 0;
 };
 // dst[i] = vals[i], i < n <= 8 (one tiny launch; the values travel as kernel arguments)
 int launch_set_scalars(drb_ctx* ctx, float* dst, const float* vals, int n);

@@ -28,7 +28,13 @@ __global__ void __launch_bounds__(kAdamThreads) k_adam(AdamArgs a, int64_t total
     float4 w = reinterpret_cast<float4*>(a.w)[i];
     float4 m = reinterpret_cast<float4*>(a.m)[i];
     float4 v = reinterpret_cast<float4*>(a.v)[i];
-    const float4 g0 = __ldg(reinterpret_cast<const float4*>(a.g) + i);
+    float4 g0 = make_float4(0.f, 0.f, 0.f, 0.f);
+    bool read_g = true;
+    if (s == a.row_seg) {          // rows of this table without a gradient this step hold zeros: do not read them
+      const uint32_t row = (uint32_t)(i - a.seg[s].off4) / (uint32_t)a.row_len4;
+      read_g = (__ldg(a.row_mask + (row >> 5)) >> (row & 31)) & 1u;
+    }
+    if (read_g) g0 = __ldg(reinterpret_cast<const float4*>(a.g) + i);
     reg += regw * (w.x * w.x + w.y * w.y + w.z * w.z + w.w * w.w);
 #define DRB_ADAM1(c)                                           \
     {                                                          \

@@ -163,6 +163,7 @@ __global__ void __launch_bounds__(kGatherThreads) k_scatter(ScatterArgs a0, Scat
   }
   const int brow = a.bias_rows ? a.bias_rows[b] : row;
   if (a.growbias && brow >= 0 && warp == 0 && sub == 0) {
+    if (a.row_touched && c == 0) atomicOr(a.row_touched + (brow >> 5), 1u << (brow & 31));
 #pragma unroll
     for (int v = 0; v < NV; v++) {
       const int c4 = c + v * LPR;
@@ -273,9 +274,10 @@ __global__ void k_colpart(const float* __restrict__ x, int n, int ld, float* __r
 }
 
 __global__ void __launch_bounds__(128) k_zero_rows(float* __restrict__ table, const int32_t* __restrict__ ids, int n,
-                                                   int ld) {
+                                                   int ld, uint32_t* __restrict__ row_touched) {
   const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (r >= n) return;
+  if (row_touched && lane == 0) atomicAnd(row_touched + (ids[r] >> 5), ~(1u << (ids[r] & 31)));
   float4* dst = reinterpret_cast<float4*>(table + (int64_t)ids[r] * ld);
   for (int c = lane; c < (ld >> 2); c += 32) dst[c] = make_float4(0.f, 0.f, 0.f, 0.f);
 }
@@ -485,6 +487,7 @@ __global__ void __launch_bounds__(kGatherThreads) k_scatter_chunks(ScatterArgs a
     }
     const int brow = a.bias_rows ? a.bias_rows[b] : row;
     if (a.growbias && brow >= 0 && piece == 0 && warp == 0 && sub == 0) {
+      if (a.row_touched && c == 0) atomicOr(a.row_touched + (brow >> 5), 1u << (brow & 31));
 #pragma unroll
       for (int v = 0; v < NV; v++) {
         const int c4 = c + v * LPR;
@@ -685,10 +688,10 @@ int launch_colpart(drb_ctx* ctx, const float* x, int n, int ld, float* colpart) 
   return nblk;
 }
 
-int launch_zero_rows(drb_ctx* ctx, float* table, const int32_t* ids, int n, int ld) {
+int launch_zero_rows(drb_ctx* ctx, float* table, const int32_t* ids, int n, int ld, uint32_t* row_touched) {
   if (n <= 0) return DRB_OK;
   drb_prof_scope prof_(ctx, "k_zero_rows");
-  k_zero_rows<<<(n * 32 + 127) / 128, 128, 0, ctx->stream>>>(table, ids, n, ld);
+  k_zero_rows<<<(n * 32 + 127) / 128, 128, 0, ctx->stream>>>(table, ids, n, ld, row_touched);
   DRB_LAUNCH_CHECK(ctx, "k_zero_rows");
   return DRB_OK;
 }
