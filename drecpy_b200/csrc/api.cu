@@ -465,7 +465,7 @@ int drb_cdae_dz1_buffer(drb_cdae* m, float** ptr, int64_t* count) {
 int drb_cdae_scatter_user_rows(drb_cdae* m, const int32_t* uids, const float* rows, int32_t n) {
   if (!m || !uids || !rows || n < 0) return drb_fail(DRB_E_INVALID, "drb_cdae_scatter_user_rows: bad argument");
   m->rows_uids = uids; m->rows_n = n;     // borrowed until the UPDATE of this step: those rows are re-zeroed after Adam
-  return launch_row_scatter(m->ctx, uids, rows, n, m->L.ld, m->d.grads + m->L.off_v);
+  return launch_row_scatter(m->ctx, uids, rows, n, m->L.ld, m->d.grads + m->L.off_v, m->ws.row_touched);
 }
 
 int drb_debug_cdae_capture_logits(drb_cdae* m, float* z_out) {
@@ -761,7 +761,8 @@ static int cdae_step_impl(drb_cdae* m, const int32_t* uids, const int32_t* keep_
     }
     ad.nseg = ns;
     ad.row_mask = nullptr; ad.row_seg = -1;
-    if (!sharded && !a->skip_user_grad && first <= 4 && last >= 4) {     // segment 4 = V: only the sampled users' rows
+    // segment 4 = V: only the sampled users' rows carry a gradient (data parallel: the rows added from the all-gathered list)
+    if (!sharded && (!a->skip_user_grad || m->rows_uids) && first <= 4 && last >= 4) {
       ad.row_mask = w.row_touched; ad.row_seg = 4 - first; ad.row_len4 = ld / 4;
     }
     ad.reg_part = w.reg_part + (int64_t)slot * R;
@@ -773,7 +774,7 @@ static int cdae_step_impl(drb_cdae* m, const int32_t* uids, const int32_t* keep_
       if ((r = launch_zero_rows(ctx, G + L.off_v, uids, batch, ld, w.row_touched))) return r;
       m->v_grad_clean = true;
     } else if (m->rows_uids) {                // data parallel: the rows every rank added from the all-gathered list
-      if ((r = launch_zero_rows(ctx, G + L.off_v, m->rows_uids, m->rows_n, ld))) return r;
+      if ((r = launch_zero_rows(ctx, G + L.off_v, m->rows_uids, m->rows_n, ld, w.row_touched))) return r;
       m->v_grad_clean = true;
     }
     return DRB_OK;

@@ -51,7 +51,8 @@ int launch_scatter(drb_ctx* ctx, const ScatterArgs& a, int n);
 int launch_scatter_pair(drb_ctx* ctx, const ScatterArgs& a0, const ScatterArgs& a1, int n);
 
 // gtable[ids[r]] += rows[r]  (one warp per row, vector atomics) -- data-parallel exchange of the user-row gradients
-int launch_row_scatter(drb_ctx* ctx, const int32_t* ids, const float* rows, int n, int ld, float* gtable);
+int launch_row_scatter(drb_ctx* ctx, const int32_t* ids, const float* rows, int n, int ld, float* gtable,
+                       uint32_t* row_touched = nullptr);
 
 // per batch row: label histogram (batch_mean) or bitmap (per_user) and, in philox mode, the keep bytes
 struct BatchPrepArgs {

@@ -231,9 +231,11 @@ __global__ void __launch_bounds__(128) k_batch_prep(BatchPrepArgs a) {
 }
 
 __global__ void __launch_bounds__(128) k_row_scatter(const int32_t* __restrict__ ids, const float* __restrict__ rows,
-                                                     int n, int ld, float* __restrict__ gtable) {
+                                                     int n, int ld, float* __restrict__ gtable,
+                                                     uint32_t* __restrict__ row_touched) {
   const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (r >= n) return;
+  if (row_touched && lane == 0) atomicOr(row_touched + (ids[r] >> 5), 1u << (ids[r] & 31));
   float4* dst = reinterpret_cast<float4*>(gtable + (int64_t)ids[r] * ld);
   const float4* src = reinterpret_cast<const float4*>(rows + (int64_t)r * ld);
   for (int c = lane; c < (ld >> 2); c += 32) atomicAdd(dst + c, __ldg(src + c));
@@ -655,10 +657,11 @@ int launch_scatter(drb_ctx* ctx, const ScatterArgs& a, int n) {
   return dispatch_lpr<ScatterLauncher>(ctx, a, n, a.ld, "k_scatter");
 }
 
-int launch_row_scatter(drb_ctx* ctx, const int32_t* ids, const float* rows, int n, int ld, float* gtable) {
+int launch_row_scatter(drb_ctx* ctx, const int32_t* ids, const float* rows, int n, int ld, float* gtable,
+                       uint32_t* row_touched) {
   if (n <= 0) return DRB_OK;
   drb_prof_scope prof_(ctx, "k_row_scatter");
-  k_row_scatter<<<(n * 32 + 127) / 128, 128, 0, ctx->stream>>>(ids, rows, n, ld, gtable);
+  k_row_scatter<<<(n * 32 + 127) / 128, 128, 0, ctx->stream>>>(ids, rows, n, ld, gtable, row_touched);
   DRB_LAUNCH_CHECK(ctx, "k_row_scatter");
   return DRB_OK;
 }
