@@ -232,7 +232,7 @@ def cdae_config(cfg, n_gpus, parallelism=None, flush=False):
                                 'working set is L2 resident; back-to-back steps'))}
 
 
-def cdae_roofline(kernels, cfg, n_params, peaks, traffic_table):
+def cdae_roofline(kernels, cfg, n_params, peaks, traffic_table, world=1):
     """Dominant family = the three output-layer GEMMs (forward + fused loss epilogue, dW'^T, dh): tensor bound.
     achieved = ALGORITHMIC flops (6*K*I per sampled user) / their time; peak = measured sustained bf16."""
     hidden, n_items, batch = cfg['hidden'], cfg['n_items'], cfg['batch']
@@ -245,7 +245,12 @@ def cdae_roofline(kernels, cfg, n_params, peaks, traffic_table):
     if tc_path and traffic_table and cfg['name'] == 'c3':
         traffic = sum(traffic_table.get(k, 0) for k in gemm) or None
     adam_ms = kernels.get('k_adam', float('nan'))
-    adam_gbs = 28.0 * n_params / (adam_ms * 1e-3) / 1e9
+    # 28 B per parameter (w, m, v read + written, g read); the gradient of user-table rows without a sampled user is
+    # known to be zero and is not read: at most `batch * world` of the n_users rows carry one
+    ld = -(-hidden // 4) * 4
+    v_rows_untouched = max(0, cfg['n_users'] - batch * max(1, world))
+    adam_bytes = 28.0 * n_params - 4.0 * v_rows_untouched * ld
+    adam_gbs = adam_bytes / (adam_ms * 1e-3) / 1e9
     return {'kernel': ' + '.join(sorted(gemm)) + (' (tcgen05 split-precision GEMMs: output layer fwd + fused loss '
                                                    "epilogue, dW'^T, dh)" if tc_path else ' (fp32 FFMA path)'),
             'bound': 'tensor', 'achieved': achieved, 'peak': peaks['tf'], 'unit': 'TFLOP/s',
@@ -256,7 +261,7 @@ def cdae_roofline(kernels, cfg, n_params, peaks, traffic_table):
             'peak_source': f"{peaks['src']} bf16 sustained",
             'share_of_step': gemm_ms / sum(kernels.values()) if kernels else None,
             'secondary': {'k_adam': {'bound': 'hbm', 'achieved': adam_gbs, 'peak': peaks['hbm'], 'unit': 'GB/s',
-                                     'frac': adam_gbs / peaks['hbm']}}}
+                                     'frac': adam_gbs / peaks['hbm'], 'algorithmic_bytes_per_step': adam_bytes}}}
 
 
 def dp_parity(D):
@@ -452,7 +457,7 @@ def run_cdae_native(args, cfg, D, arrays=None):
         return None
     peaks = load_peaks()
     n_params = int(m._L.total)                                   # parameters this rank updates (its shard when item-sharded)
-    roofline = cdae_roofline(kernels, cfg, n_params, peaks, load_traffic())
+    roofline = cdae_roofline(kernels, cfg, n_params, peaks, load_traffic(), D.world)
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         r = cdae_cpu_arm(cfg, ds, 2, 1, 60.0)
