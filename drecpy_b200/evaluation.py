@@ -182,18 +182,38 @@ def _fast_evaluation(model, data, users, t_indptr, t_order, thr, n_pos, n_neg, g
         p_lens = (pos_off[active + 1] - pos_off[active]).astype(np.int64)
         c_off = np.zeros(n + 1, np.int64); np.cumsum(c_lens, out=c_off[1:])
         p_off = np.zeros(n + 1, np.int64); np.cumsum(p_lens, out=p_off[1:])
-        c_src = np.arange(c_off[-1]) - np.repeat(c_off[:-1], c_lens) + np.repeat(cand_off[active], c_lens)
-        p_src = np.arange(p_off[-1]) - np.repeat(p_off[:-1], p_lens) + np.repeat(pos_off[active], p_lens)
-        c_flat, p_flat = cand[c_src], pos[p_src]
-        c_seg, p_seg = np.repeat(np.arange(n), c_lens), np.repeat(np.arange(n), p_lens)
+        # equal list lengths (the usual protocol: n_pos positives + n_neg negatives for everybody) need no per-element
+        # segment arithmetic: the source index is a broadcast add, the relevancy matrix a reshape
+        uniform_c = int(c_lens.min()) == int(c_lens.max())
+        uniform_p = int(p_lens.min()) == int(p_lens.max())
+        c_seg = p_seg = None
+
+        def flatten(off, flat, lens, tot, uniform):
+            """The active users' lists back to back (+ the segment ids when the lengths differ)."""
+            if uniform and len(flat) >= tot and off[active[0]] == 0 and off[active[-1] + 1] == tot:
+                return flat[:tot], None        # every list in between is empty: they already lie back to back
+            if uniform:
+                return flat[(off[active][:, None] + np.arange(int(lens[0]), dtype=np.int64)[None, :]).ravel()], None
+            seg = np.repeat(np.arange(n), lens)
+            start = np.zeros(n, np.int64); np.cumsum(lens[:-1], out=start[1:])
+            return flat[np.arange(tot) - np.repeat(start, lens) + np.repeat(off[active], lens)], seg
+        c_flat, c_seg = flatten(cand_off, cand, c_lens, int(c_off[-1]), uniform_c)
+        p_flat, p_seg = flatten(pos_off, pos, p_lens, int(p_off[-1]), uniform_p)
         big = int(max(c_flat.max(initial=0), t_item.max(initial=0), p_flat.max(initial=0))) + 2
         if big * (len(users) + 1) >= 2 ** 62 or c_flat.min(initial=0) < 0 or t_item.min(initial=0) < 0:
             return None
-        # corner case: duplicate items inside one candidate or positive list -> general path
-        ck = np.sort(c_seg * big + c_flat)
-        pk = np.sort(p_seg * big + p_flat)
-        if (len(ck) > 1 and (ck[1:] == ck[:-1]).any()) or (len(pk) > 1 and (pk[1:] == pk[:-1]).any()):
-            return None
+        # corner case: duplicate items inside one candidate or positive list -> general path.  Positives and negatives
+        # are distinct test rows of the user and generated negatives avoid both (ranking_evaluation.py:163-219), so a
+        # list can only repeat an item when the user's test rows do: check those (one key per test row) first.
+        t_seg = np.repeat(np.arange(len(users)), np.diff(t_indptr))
+        tk = np.sort(t_seg * big + t_item)
+        if len(tk) > 1 and (tk[1:] == tk[:-1]).any():
+            if c_seg is None: c_seg = np.repeat(np.arange(n), c_lens)
+            if p_seg is None: p_seg = np.repeat(np.arange(n), p_lens)
+            ck = np.sort(c_seg * big + c_flat)
+            pk = np.sort(p_seg * big + p_flat)
+            if (len(ck) > 1 and (ck[1:] == ck[:-1]).any()) or (len(pk) > 1 and (pk[1:] == pk[:-1]).any()):
+                return None
         ranked, n_out = model.rank_arrays(users[active], c_flat, c_off, novelty=novelty)
         c_max, L = int(c_lens.max()), ranked.shape[1]
         # relevancy lookup: first test row of (user, item), else 0  (ranking_evaluation.py:223); hits: the ranked item
@@ -217,9 +237,17 @@ def _fast_evaluation(model, data, users, t_indptr, t_order, thr, n_pos, n_neg, g
         rel_flat = np.zeros(len(c_flat_c))
         c_beg, c_end = np.ascontiguousarray(c_off[:-1]), np.ascontiguousarray(c_off[1:])
         lookup(t_beg, t_end, t_item_c, t_val_c, c_beg, c_end, c_flat_c, rel_flat)
-        rel_cand = np.full((n, c_max), -np.inf)
-        rel_cand[c_seg, np.arange(c_off[-1]) - np.repeat(c_off[:-1], c_lens)] = rel_flat
-        ideal = -np.sort(-rel_cand, axis=1)                       # relevancies of the ideal list, descending
+        if uniform_c:
+            rel_cand = rel_flat.reshape(n, c_max)
+        else:
+            rel_cand = np.full((n, c_max), -np.inf)
+            rel_cand[c_seg, np.arange(c_off[-1]) - np.repeat(c_off[:-1], c_lens)] = rel_flat
+        # relevancies of the ideal list, descending: only the first max(k) positions are ever read
+        k_top = min(max(ks), c_max)
+        if k_top < c_max:
+            ideal = -np.sort(np.partition(-rel_cand, k_top - 1, axis=1)[:, :k_top], axis=1)
+        else:
+            ideal = -np.sort(-rel_cand, axis=1)
         hit = np.zeros((n, L))
         p_flat_c = np.ascontiguousarray(p_flat, np.int64)
         lookup(np.ascontiguousarray(p_off[:-1]), np.ascontiguousarray(p_off[1:]), p_flat_c, None, r_beg, r_end,
