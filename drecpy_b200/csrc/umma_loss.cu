@@ -1,9 +1,11 @@
-// K2 on the tensor cores, persistent form: z2 = h W'^T (3xTF32 tcgen05.mma, TMA-fed) with the fused
+// K2 on the tensor cores, persistent form: z2 = h W'^T (fp32-accurate split products on tcgen05.mma: 3 x FP16, or
+// 3 x TF32; TMA-fed) with the fused
 // b' + sigmoid + Keras BCE/MSE + dL/dz2 epilogue of the CDAE training step.
 //
 // Replaces (reference, DRecPy/): Recommender/cdae.py:76 (tf.matmul(hidden, W_) + b_ + sigmoid) and cdae.py:78-79
 // (Keras loss on the (B,B,I) broadcast == batch-mean labels) plus d(loss)/d(z2) of tape.gradient.
-// p is never written to memory; the epilogue emits dL/dz2 already split into tf32 hi/lo for the backward GEMMs.
+// p is never written to memory; the epilogue emits dL/dz2 already split into fp16 (or tf32) hi/lo for the backward
+// GEMMs.
 //
 // The product is formed transposed, z2^T = W' h^T: MMA M = 128 items (TMEM lanes), N = up to 256 batch rows (TMEM
 // columns).  An epilogue warp therefore holds 32 consecutive items of one batch row across its lanes, which is one
@@ -14,8 +16,9 @@
 // extent is short (hidden <= 255 -> <= 8 k-blocks), so per-tile set-up and the exposed epilogue dominated the
 // one-tile-per-CTA version; here the TMA producer runs ahead across tiles, the accumulator is double-buffered in TMEM
 // (2 x BN columns) and the 16 epilogue warps drain tile t while the MMA warp fills tile t+1.
-// dz is written in a 128 x 32 tile-major layout (128 batch rows x 32 items = 16 KB contiguous), and the two backward
-// GEMMs later fetch whole tiles / 4 KB sub-tiles with single TMA boxes.
+// dz is written in a tile-major layout (128 batch rows x 64 halfs, or x 32 floats, = 16 KB contiguous), and the two
+// backward GEMMs later fetch whole tiles / sub-tiles with single TMA boxes (one copy: dh reads it K-major, dW'^T through
+// the MN-major descriptor).
 #include "umma_common.cuh"
 
 namespace {

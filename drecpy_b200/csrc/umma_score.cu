@@ -1,27 +1,29 @@
 // Full-catalog scoring on the tensor cores with the top-k selection kept on chip: scores = sigmoid(h W'^T + b') for a
-// block of users against a range of items (3xTF32 tcgen05.mma, TMA-fed, TMEM accumulators -- the persistent CTA-pair
-// skeleton of umma_loss.cu), and an epilogue that never writes a score to memory.  It compares every score with the
-// user's current threshold and appends the few that pass to that user's candidate list.
+// block of users against a range of items (fp32-accurate split products on tcgen05.mma -- 3 x FP16, or 3 x TF32 --,
+// TMA-fed, TMEM accumulators: the persistent CTA-pair skeleton of umma_loss.cu), and an epilogue that never writes a
+// score to memory.  It appends to every user's candidate list the keys that can still belong to the user's top k.
 //
 // Replaces (reference, DRecPy/): Recommender/recommender_abc.py:413-419 (_recommend = _rank over range(n_items)) ->
 // Recommender/cdae.py:84-103 (_predict over all items, drop the user's training items when novelty, heapq.nlargest on
 // (score, iid)), as driven for every user by Evaluation/Processes/recommendation_evaluation.py:164.
 //
-// Selection scheme (drb_cdae_topk in api.cu drives it):
-//   1. items [0, n_S): threshold 0, i.e. every unseen item of that slice lands in the list; k_select_lists sorts the
-//      list, keeps its best k and publishes tau = the k-th best score.  The k-th best of ANY subset is a lower bound of
-//      the final k-th best, so nothing below tau can be in the answer;
-//   2. items [n_S, I): only scores >= tau are appended (a few per cent of the catalog at worst, far less when the
-//      slice already holds popular items); k_select_lists then sorts k + appended keys and emits the answer in the
-//      reference's order (score desc, iid desc).
+// Selection scheme (drb_cdae_topk in api.cu drives it; DESIGN.md section 3):
+//   stage 0   items [0, n_S): every unseen item of the slice lands in the list (FILTER = false); the select kernel
+//             (score.cu) keeps the keys >= tau = the k-th best score and publishes tau and tau_z, a logit below which
+//             no score can reach tau.  The k-th best of ANY subset is a lower bound of the final k-th best, so nothing
+//             below tau can be in the answer;
+//   stage s   item ranges growing geometrically (FILTER = true): one fma + one compare against tau_z per element and
+//             one vote per four users decide for most elements; the exact test (fp32 sigmoid as an orderable integer
+//             against tau, seen-bitmap knock-out) runs only where some lane passes; passing keys go to a per-warp queue
+//             in shared memory and get their list slots when the queue is flushed.  After every stage but the last the
+//             select tightens tau; the last select emits the answer in the reference's order (score desc, iid desc).
 // Keys are 64-bit (orderable(score) << 32 | iid) as everywhere in score.cu.  The novelty filter is a per-user bitmap
-// of the user's stored items (built by k_batch_prep from the `seen` CSR): one broadcast 32-bit load covers the 32 items
-// a warp holds for one user.  A list that overflows its capacity is detected by k_select_lists and that user is
-// re-done by the exact fallback (score.cu), so the scheme is exact for any data.
+// of the user's stored items (built by k_batch_prep from the `seen` CSR): one 32-bit word covers the 32 items a warp
+// holds for one user.  A list that overflows its capacity is detected by the select kernel and that user is re-done by
+// the exact fallback (score.cu), so the scheme is exact for any data.
 //
 // Orientation as in umma_loss.cu: MMA M = 128 items on the TMEM lanes, N = 256 users on the TMEM columns; an epilogue
-// warp holds 32 consecutive items of one user across its lanes, so one ballot says which of them pass and one atomicAdd
-// per (warp, user) reserves their slots.
+// warp holds 32 consecutive items of one user across its lanes, so one ballot says which of them pass.
 #include "umma_common.cuh"
 
 namespace {
