@@ -240,6 +240,30 @@ def test_vectorised_evaluation_equals_per_user_protocol(golden_dir):
         assert fast == slow, (kw, fast, slow)
 
 
+def test_vectorised_evaluation_with_duplicate_test_rows_and_ragged_lists():
+    """The vectorised evaluator checks the users' TEST ROWS for repeated items first (a candidate list can only repeat an
+    item when they do) and only then the lists themselves; with duplicates it must hand over to the general path, and
+    without generated negatives the lists are ragged (segment arithmetic instead of a reshape)."""
+    u, i, v = drb.synthetic_interactions(200, 300, 6000, seed=33)
+    rng = np.random.default_rng(8)
+    mask = rng.random(len(u)) < 0.25
+    train = drb.InteractionData(u[~mask], i[~mask], v[~mask])
+    train.assign_internal_ids()
+    tu, ti, tv = u[mask], i[mask], v[mask]
+    dup = rng.choice(len(tu), 40, replace=False)                  # repeat 40 test rows: same (user, item) twice
+    test_dup = drb.InteractionData(np.concatenate([tu, tu[dup]]), np.concatenate([ti, ti[dup]]),
+                                   np.concatenate([tv, tv[dup]]))
+    test_plain = drb.InteractionData(tu, ti, tv)
+    model = FakeBatchModel(train)
+    for test in (test_dup, test_plain):
+        for kw in [dict(k=[3, 10], n_pos_interactions=None, n_neg_interactions=None, novelty=False),            # ragged
+                   dict(k=5, n_pos_interactions=1, n_neg_interactions=50, generate_negative_pairs=True, seed=3),  # uniform
+                   dict(k=[1, 4], n_pos_interactions=None, n_neg_interactions=7, novelty=True, seed=6)]:
+            fast = drb.ranking_evaluation(model, test, verbose=False, **kw)
+            slow = drb.ranking_evaluation(model, test, verbose=False, force_python=True, **kw)
+            assert fast == slow, (kw, fast, slow)
+
+
 # ------------------------------------------------------------------------------------------------ leave_k_out
 def test_leave_k_out_matches_live_reference_goldens():
     """drecpy_b200.leave_k_out (native per-user Random(seed + idx + 1).sample replay) against the row ids the live
