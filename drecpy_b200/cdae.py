@@ -17,6 +17,7 @@ New keywords, all with reference-faithful defaults:
   gemm='auto'               'tcgen05' = 3xTF32 tensor-core GEMMs (fp32-accurate), 'ffma' = exact-fp32 CUDA-core GEMMs
 """
 import ctypes as C
+import os
 import random
 
 import numpy as np
@@ -371,13 +372,22 @@ class CDAE(DeepRecommenderABC):
         lib = _lib.load()
         with self._lock:
             nxt = getattr(self, '_next', None)
-            if nxt is not None and nxt[1] == batch_size:
-                slot, keep_ptr = nxt[0], nxt[2]
+            if nxt is not None:
+                ready = nxt[2].result() if hasattr(nxt[2], 'result') else nxt[2]   # the prefetch thread is done with the
+            if nxt is not None and nxt[1] == batch_size:                            # sampler from here on
+                slot, keep_ptr = nxt[0], ready
             else:
                 slot = self._acquire_slot()
                 keep_ptr = self.prepare_batch(slot, batch_size)
             self._next = None
             self._cur_batch = batch_size
+            if prefetch:
+                # the NEXT batch is sampled (and, in 'mt19937' mode, its mask replayed) by a worker thread while this
+                # thread enqueues the step and the GPU runs it: ctypes releases the GIL inside the native sampler
+                nslot = self._acquire_slot()
+                pool = self._prefetch_pool()
+                self._next = (nslot, batch_size, pool.submit(self._prepare_in_thread, nslot, batch_size) if pool
+                              else None)
             if self._dp.active or self._mask_stream is not None:
                 self._enqueue_step_dp(slot, batch_size * (self._dp.world if self._sharded else 1), reg_rate)
             else:
@@ -390,15 +400,31 @@ class CDAE(DeepRecommenderABC):
             ev = self._torch.cuda.Event()
             ev.record(self._stream)
             slot['event'] = ev
-            if prefetch:
-                nslot = self._acquire_slot()
-                self._next = (nslot, batch_size, self.prepare_batch(nslot, batch_size))
+            if prefetch and self._next[2] is None:       # no worker thread (DRB_PREFETCH_THREAD=0): prepare it here
+                self._next = (self._next[0], batch_size, self.prepare_batch(self._next[0], batch_size))
             if not want_loss:
                 return None
             if self._dp.active or self._mask_stream is not None:
                 return self.global_loss(self._dp_dev['loss'])
             ev.synchronize()
             return float(self._loss_host[0])
+
+    def _prefetch_pool(self):
+        """One worker thread for the host side of the next batch (None when DRB_PREFETCH_THREAD=0)."""
+        pool = getattr(self, '_pool', None)
+        if pool is None and os.environ.get('DRB_PREFETCH_THREAD', '1') != '0':
+            from concurrent.futures import ThreadPoolExecutor
+            pool = self._pool = ThreadPoolExecutor(max_workers=1, thread_name_prefix='drb-prefetch')
+        return pool
+
+    def _prepare_in_thread(self, slot, batch_size):
+        with self._torch.cuda.device(self._dev):          # a growing pinned keep buffer is allocated for this device
+            return self.prepare_batch(slot, batch_size)
+
+    def _finish_fit(self):
+        nxt = getattr(self, '_next', None)                # a batch prefetched before an early stop: let the worker finish
+        if nxt is not None and hasattr(nxt[2], 'result'):
+            nxt[2].result()
 
     def _enqueue_step_dp(self, slot, batch_size, reg_rate):
         torch = self._torch

@@ -209,6 +209,7 @@ struct drb_sampler {
   const int64_t* all_indptr; const int32_t* all_iid;
   double neg_ratio;
   drb_rng rng, null_rng, pos_rng;  // point_sampler.py:30, mem_dataset.py:135-136, :113-114
+  std::vector<int64_t> slot, pos_slot, pos_row, cand_u, cand_i, cand_lo, cand_len;   // scratch of drb_sampler_sample
 };
 
 extern "C" {
@@ -232,34 +233,89 @@ int drb_sampler_create(int32_t max_uid, int32_t max_iid, const int64_t* pos_indp
 }
 int drb_sampler_destroy(drb_sampler* s) { delete s; return DRB_OK; }
 
+// The reference draws sample after sample (point_sampler.py:44-96), but its three random.Random streams are independent
+// objects: `rng` only decides positive / null per sample, `null_rng` only produces candidate (uid, iid) pairs for the null
+// samples (mem_dataset.py:158-163: a pair that is stored is simply skipped -- acceptance never changes what is drawn
+// next), `pos_rng` only serves the positive samples (mem_dataset.py:119-129).  So each stream can be consumed on its
+// own, in its own order, with the same outputs and the same final states -- and the memory lookups, which dominate
+// (a random user's CSR row is a cache miss per binary-search level), can be overlapped instead of sitting between two
+// draws: the null candidates are drawn in blocks of at most as many pairs as samples are still open (never one more
+// than the sequential loop would draw), their rows are prefetched, then tested; the positives' rows are gathered after
+// the stream has been walked.
 int drb_sampler_sample(drb_sampler* s, int64_t n, int32_t* uid, int32_t* iid, double* val) {
   if (!s || n < 0 || (n > 0 && (!uid || !iid || !val)))
     return drb_fail(DRB_E_INVALID, "drb_sampler_sample: bad argument");
   const double hi = s->neg_ratio + 1.0;
+  // 1. the decisions: slot = positions of the null samples, pos_slot = positions of the positive ones (sample order)
+  s->slot.clear(); s->pos_slot.clear();
   for (int64_t t = 0; t < n; t++) {
-    bool null_pair = (0.0 + (hi - 0.0) * s->rng.random()) > 1.0;  // point_sampler.py:58
-    if (null_pair) {
-      for (;;) {  // mem_dataset.py:158-163
-        int64_t u = s->null_rng.randint(0, s->max_uid);
-        int64_t i = s->null_rng.randint(0, s->max_iid);
-        const int32_t* lo = s->all_iid + s->all_indptr[u];
-        const int32_t* hi_ = s->all_iid + s->all_indptr[u + 1];
-        if (!std::binary_search(lo, hi_, (int32_t)i)) {
-          uid[t] = (int32_t)u; iid[t] = (int32_t)i; val[t] = 0.0;
-          break;
-        }
-      }
-    } else {
-      for (;;) {  // mem_dataset.py:119-129
-        int64_t u = s->pos_rng.randint(0, s->max_uid);
-        int64_t cnt = s->pos_indptr[u + 1] - s->pos_indptr[u];
-        if (cnt == 0) continue;
-        int64_t j = s->pos_rng.randint(0, cnt - 1);
-        int64_t r = s->pos_indptr[u] + j;
-        uid[t] = (int32_t)u; iid[t] = s->pos_iid[r]; val[t] = s->pos_val[r];
-        break;
+    const bool null_pair = (0.0 + (hi - 0.0) * s->rng.random()) > 1.0;  // point_sampler.py:58
+    (null_pair ? s->slot : s->pos_slot).push_back(t);
+  }
+  const int64_t n_null = (int64_t)s->slot.size(), n_pos = (int64_t)s->pos_slot.size();
+  // 2. null samples: the candidate stream, filtered in order (mem_dataset.py:158-163)
+  constexpr int64_t kBlock = 128;
+  s->cand_u.resize(kBlock); s->cand_i.resize(kBlock); s->cand_lo.resize(kBlock); s->cand_len.resize(kBlock);
+  int64_t filled = 0;
+  while (filled < n_null) {
+    const int64_t m = std::min<int64_t>(kBlock, n_null - filled);   // every candidate fills at most one open sample
+    for (int64_t k = 0; k < m; k++) {
+      s->cand_u[(size_t)k] = s->null_rng.randint(0, s->max_uid);
+      s->cand_i[(size_t)k] = s->null_rng.randint(0, s->max_iid);
+      __builtin_prefetch(s->all_indptr + s->cand_u[(size_t)k]);
+    }
+    // membership of the m candidates by m interleaved lower-bound searches: one level of every search per sweep, so
+    // that the cache misses of a level (one per candidate, all independent) overlap instead of forming a chain
+    int64_t longest = 0;
+    for (int64_t k = 0; k < m; k++) {
+      const int64_t lo = s->all_indptr[s->cand_u[(size_t)k]], len = s->all_indptr[s->cand_u[(size_t)k] + 1] - lo;
+      s->cand_lo[(size_t)k] = lo; s->cand_len[(size_t)k] = len;
+      longest = std::max(longest, len);
+      if (len > 0) __builtin_prefetch(s->all_iid + lo + (len >> 1));
+    }
+    for (; longest > 0; longest >>= 1) {
+      for (int64_t k = 0; k < m; k++) {
+        int64_t len = s->cand_len[(size_t)k];
+        if (len <= 0) continue;
+        int64_t lo = s->cand_lo[(size_t)k];
+        const int64_t half = len >> 1;
+        const bool right = s->all_iid[lo + half] < (int32_t)s->cand_i[(size_t)k];
+        lo = right ? lo + half + 1 : lo;
+        len = right ? len - half - 1 : half;
+        s->cand_lo[(size_t)k] = lo; s->cand_len[(size_t)k] = len;
+        if (len > 0) __builtin_prefetch(s->all_iid + lo + (len >> 1));
       }
     }
+    for (int64_t k = 0; k < m; k++) {         // cand_lo = first entry of the row that is >= the item (or the row's end)
+      const int64_t u = s->cand_u[(size_t)k], i = s->cand_i[(size_t)k];
+      const int64_t pos = s->cand_lo[(size_t)k];
+      const bool stored = pos < s->all_indptr[u + 1] && s->all_iid[pos] == (int32_t)i;
+      if (!stored) {
+        const int64_t t = s->slot[(size_t)filled++];
+        uid[t] = (int32_t)u; iid[t] = (int32_t)i; val[t] = 0.0;
+      }
+    }
+  }
+  // 3. positive samples (mem_dataset.py:119-129): the stream depends on the row lengths only (a 1 MB array); the rows
+  //    themselves are fetched after the stream has been walked
+  s->pos_row.resize((size_t)n_pos);
+  for (int64_t q = 0; q < n_pos; q++) {
+    for (;;) {
+      const int64_t u = s->pos_rng.randint(0, s->max_uid);
+      const int64_t cnt = s->pos_indptr[u + 1] - s->pos_indptr[u];
+      if (cnt == 0) continue;
+      const int64_t j = s->pos_rng.randint(0, cnt - 1);
+      const int64_t r = s->pos_indptr[u] + j;
+      uid[s->pos_slot[(size_t)q]] = (int32_t)u;
+      s->pos_row[(size_t)q] = r;
+      __builtin_prefetch(s->pos_iid + r);
+      __builtin_prefetch(s->pos_val + r);
+      break;
+    }
+  }
+  for (int64_t q = 0; q < n_pos; q++) {
+    const int64_t t = s->pos_slot[(size_t)q], r = s->pos_row[(size_t)q];
+    iid[t] = s->pos_iid[r]; val[t] = s->pos_val[r];
   }
   return DRB_OK;
 }

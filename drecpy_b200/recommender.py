@@ -350,7 +350,7 @@ class DeepRecommenderABC(ABC):
 
     # ------------------------------------------------------------------ persistence (recommender_abc.py:503-524)
     _TRANSIENT = ('_native', '_ctx', '_torch', '_workspace', '_slots', '_loss_host', '_loss_dev', '_stream', '_lock',
-                  '_mask_rng', '_mask_stream', '_keep_dev', '_sampler', '_dp', '_dp_dev', '_dp_gather', '_label_count', '_dz1', '_h_buf', '_keepalive', '_next',
+                  '_mask_rng', '_mask_stream', '_keep_dev', '_sampler', '_dp', '_dp_dev', '_dp_gather', '_label_count', '_dz1', '_h_buf', '_keepalive', '_next', '_pool',
                   '_d_indptr', '_d_indices', '_d_seen_indptr', '_d_seen_indices', '_dev_sparse', '_logger', '_dev')
 
     def __getstate__(self):
