@@ -99,6 +99,32 @@ def test_native_sampler_vs_oracle_c1_shape_and_state_roundtrip():
     assert s.sample(50) == a
 
 
+@pytest.mark.parametrize('density,neg_ratio', [(0.9, 5), (0.5, 1), (0.02, 9)])
+def test_native_sampler_stream_decoupling_under_heavy_rejection(density, neg_ratio):
+    """The native sampler walks the reference's three independent random.Random streams one after the other (decisions,
+    null pairs in blocks no longer than the number of open samples, positives) instead of sample by sample.  With a
+    nearly full matrix most null candidates are stored pairs and get skipped, with users without positives the
+    positive generator redraws: outputs, call boundaries (1, 7, 300 samples per call) and the final states of all
+    three streams must still equal the sample-by-sample oracle."""
+    rng = np.random.default_rng(3)
+    U, I = 60, 45
+    mask = rng.random((U, I)) < density
+    mask[7] = False                                           # a user without any interaction
+    uu, ii = np.nonzero(mask)
+    vv = rng.integers(0, 3, len(uu))                          # zeros: stored rows below the threshold
+    keep = np.ones(len(uu), bool)
+    ds = drb.InteractionData(uu[keep], ii[keep], vv[keep])
+    ds.assign_internal_ids()
+    s = drb.PointSampler(ds, neg_ratio, 1, 10)
+    o = PointSamplerOracle(ds.uid, ds.iid, ds.interaction, neg_ratio, 1, 10)
+    for n in (1, 7, 300, 0, 2):
+        got = s.sample(n)
+        want = [(a, b, int(c)) for a, b, c in o.sample(n)] if n else []
+        assert got == want, n
+    # one more draw from every stream: the states agree, not only the outputs so far
+    assert s.sample(64) == [(a, b, int(c)) for a, b, c in o.sample(64)]
+
+
 def test_corruption_mask_matches_python_stream():
     """cdae.py:63-64: n_items draws per sampled user, in item order; the native replay skips unused draws."""
     u, i, v = drb.synthetic_interactions(60, 97, 900, seed=3)
