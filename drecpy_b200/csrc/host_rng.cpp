@@ -589,6 +589,87 @@ int drb_eval_lookup(int64_t n_groups, const int64_t* tab_beg, const int64_t* tab
   return DRB_OK;
 }
 
+// ---------------------------------------------------------------------------------------------- metric sums
+int drb_eval_metrics(int64_t n_groups, const int64_t* tab_beg, const int64_t* tab_end, const int64_t* tab_key,
+                     const double* tab_val, const int64_t* ranked, int64_t ld_ranked, const int32_t* n_out,
+                     const int64_t* c_beg, const int64_t* c_end, const int64_t* c_key, const int64_t* p_beg,
+                     const int64_t* p_end, const int64_t* p_key, const int64_t* ks, int32_t n_ks, int32_t n_threads,
+                     double* dcg, double* idcg, int64_t* hits) {
+  if (n_groups < 0 || n_ks < 1 || !tab_beg || !tab_end || !tab_key || !tab_val || !ranked || !n_out || !c_beg ||
+      !c_end || !c_key || !p_beg || !p_end || !p_key || !ks || !dcg || !idcg || !hits)
+    return drb_fail(DRB_E_INVALID, "drb_eval_metrics: bad argument");
+  int64_t k_max = 0;
+  for (int j = 0; j < n_ks; j++) k_max = std::max(k_max, ks[j]);
+  auto worker = [&](int64_t lo, int64_t hi) {
+    std::vector<double> rel, gain;
+    std::vector<std::pair<int64_t, int64_t>> idx;       // (key, first row) of a long test table, sorted by key
+    std::vector<int64_t> psorted;
+    for (int64_t g = lo; g < hi; g++) {
+      const int64_t tb = tab_beg[g], te = tab_end[g];
+      const bool longtab = te - tb > 16;
+      if (longtab) {
+        idx.clear();
+        for (int64_t r = tb; r < te; r++) idx.emplace_back(tab_key[r], r);
+        std::sort(idx.begin(), idx.end());
+      }
+      auto relevancy = [&](int64_t key) -> double {     // first matching test row, else 0
+        if (longtab) {
+          auto it = std::lower_bound(idx.begin(), idx.end(), std::make_pair(key, (int64_t)INT64_MIN));
+          return (it != idx.end() && it->first == key) ? tab_val[it->second] : 0.0;
+        }
+        for (int64_t r = tb; r < te; r++)
+          if (tab_key[r] == key) return tab_val[r];
+        return 0.0;
+      };
+      const int64_t np_ = p_end[g] - p_beg[g];
+      const bool longpos = np_ > 16;
+      if (longpos) { psorted.assign(p_key + p_beg[g], p_key + p_end[g]); std::sort(psorted.begin(), psorted.end()); }
+      auto is_positive = [&](int64_t key) -> bool {
+        if (longpos) return std::binary_search(psorted.begin(), psorted.end(), key);
+        for (int64_t r = p_beg[g]; r < p_end[g]; r++)
+          if (p_key[r] == key) return true;
+        return false;
+      };
+      // ranked list: running DCG and hit count, read off at every cut-off
+      const int64_t nr = std::min<int64_t>(n_out[g], k_max);
+      double cur = 0.0;
+      int64_t nh = 0;
+      for (int j = 0; j < n_ks; j++) { dcg[g * n_ks + j] = 0.0; hits[g * n_ks + j] = 0; idcg[g * n_ks + j] = 0.0; }
+      for (int64_t i = 0; i < nr; i++) {
+        const int64_t item = ranked[g * ld_ranked + i];
+        cur += (std::pow(2.0, relevancy(item)) - 1.0) / std::log2(2.0 + (double)i);
+        nh += is_positive(item) ? 1 : 0;
+        for (int j = 0; j < n_ks; j++)
+          if (i < ks[j]) { dcg[g * n_ks + j] = cur; hits[g * n_ks + j] = nh; }
+      }
+      // ideal list: the candidates' relevancies in descending order
+      const int64_t nc = c_end[g] - c_beg[g];
+      rel.resize((size_t)nc);
+      for (int64_t q = 0; q < nc; q++) rel[(size_t)q] = relevancy(c_key[c_beg[g] + q]);
+      const int64_t top = std::min<int64_t>(nc, k_max);
+      std::partial_sort(rel.begin(), rel.begin() + top, rel.end(), std::greater<double>());
+      double best = 0.0;
+      for (int64_t i = 0; i < top; i++) {
+        best += (std::pow(2.0, rel[(size_t)i]) - 1.0) / std::log2(2.0 + (double)i);
+        for (int j = 0; j < n_ks; j++)
+          if (i < ks[j]) idcg[g * n_ks + j] = best;
+      }
+    }
+  };
+  int nt = std::max(1, std::min<int>(n_threads, 64));
+  if (n_groups < 1024) nt = 1;
+  if (nt == 1) {
+    worker(0, n_groups);
+  } else {
+    std::vector<std::thread> th;
+    const int64_t per = (n_groups + nt - 1) / nt;
+    for (int t = 0; t < nt; t++)
+      th.emplace_back(worker, std::min<int64_t>(n_groups, t * per), std::min<int64_t>(n_groups, (t + 1) * per));
+    for (auto& x : th) x.join();
+  }
+  return DRB_OK;
+}
+
 // ---------------------------------------------------------------------------------------------- leave-k-out split
 // DRecPy/Evaluation/Splits/leave_k_out.py:14-135 for every user at once.  User idx (order of first appearance) draws
 // from random.Random(seed + idx + 1) -- the reference increments the seed *before* creating each user's generator

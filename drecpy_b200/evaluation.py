@@ -215,61 +215,35 @@ def _fast_evaluation(model, data, users, t_indptr, t_order, thr, n_pos, n_neg, g
             if (len(ck) > 1 and (ck[1:] == ck[:-1]).any()) or (len(pk) > 1 and (pk[1:] == pk[:-1]).any()):
                 return None
         ranked, n_out = model.rank_arrays(users[active], c_flat, c_off, novelty=novelty)
-        c_max, L = int(c_lens.max()), ranked.shape[1]
-        # relevancy lookup: first test row of (user, item), else 0  (ranking_evaluation.py:223); hits: the ranked item
-        # is one of the user's sampled positives.  Both are grouped first-match lookups done natively for all users.
+        L = ranked.shape[1]
+        # per-user DCG / ideal DCG / hit counts at every cut-off, natively for all users (drb_eval_metrics: the relevancy
+        # of an item is its first test row of the user, else 0 -- ranking_evaluation.py:223 --, a hit is a ranked item
+        # among the user's sampled positives); same float64 operations in the same order as the metric classes above
         lib, nthr = _lib.load(), min(16, os.cpu_count() or 1)
         t_beg = np.ascontiguousarray(t_indptr[:-1][active].astype(np.int64))
         t_end = np.ascontiguousarray(t_indptr[1:][active].astype(np.int64))
         t_item_c, t_val_c = np.ascontiguousarray(t_item, np.int64), np.ascontiguousarray(t_val, np.float64)
-
-        def lookup(tab_beg, tab_end, tab_key, tab_val, q_beg, q_end, q_key, out):
-            _lib.check(lib.drb_eval_lookup(n, _lib.np_ptr(tab_beg), _lib.np_ptr(tab_end), _lib.np_ptr(tab_key),
-                                           _lib.np_ptr(tab_val) if tab_val is not None else None, _lib.np_ptr(q_beg),
-                                           _lib.np_ptr(q_end), _lib.np_ptr(q_key), 0.0, nthr, _lib.np_ptr(out)))
-        valid = np.arange(L)[None, :] < n_out[:, None]
         ranked_c = np.ascontiguousarray(ranked, np.int64)
-        r_beg = np.arange(n, dtype=np.int64) * L
-        r_end = r_beg + n_out.astype(np.int64)
-        rel_rank = np.zeros((n, L))
-        lookup(t_beg, t_end, t_item_c, t_val_c, r_beg, r_end, ranked_c.reshape(-1), rel_rank.reshape(-1))
-        c_flat_c = np.ascontiguousarray(c_flat, np.int64)
-        rel_flat = np.zeros(len(c_flat_c))
-        c_beg, c_end = np.ascontiguousarray(c_off[:-1]), np.ascontiguousarray(c_off[1:])
-        lookup(t_beg, t_end, t_item_c, t_val_c, c_beg, c_end, c_flat_c, rel_flat)
-        if uniform_c:
-            rel_cand = rel_flat.reshape(n, c_max)
-        else:
-            rel_cand = np.full((n, c_max), -np.inf)
-            rel_cand[c_seg, np.arange(c_off[-1]) - np.repeat(c_off[:-1], c_lens)] = rel_flat
-        # relevancies of the ideal list, descending: only the first max(k) positions are ever read
-        k_top = min(max(ks), c_max)
-        if k_top < c_max:
-            ideal = -np.sort(np.partition(-rel_cand, k_top - 1, axis=1)[:, :k_top], axis=1)
-        else:
-            ideal = -np.sort(-rel_cand, axis=1)
-        hit = np.zeros((n, L))
-        p_flat_c = np.ascontiguousarray(p_flat, np.int64)
-        lookup(np.ascontiguousarray(p_off[:-1]), np.ascontiguousarray(p_off[1:]), p_flat_c, None, r_beg, r_end,
-               ranked_c.reshape(-1), hit.reshape(-1))
-        is_pos = valid & (hit > 0.5)
+        n_out_c = np.ascontiguousarray(n_out, np.int32)
+        c_flat_c, p_flat_c = np.ascontiguousarray(c_flat, np.int64), np.ascontiguousarray(p_flat, np.int64)
+        ks_c = np.ascontiguousarray(ks, np.int64)
+        dcg, idcg = np.zeros((n, len(ks))), np.zeros((n, len(ks)))
+        hits_all = np.zeros((n, len(ks)), np.int64)
+        _lib.check(lib.drb_eval_metrics(
+            n, _lib.np_ptr(t_beg), _lib.np_ptr(t_end), _lib.np_ptr(t_item_c), _lib.np_ptr(t_val_c), _lib.np_ptr(ranked_c),
+            L, _lib.np_ptr(n_out_c), _lib.np_ptr(np.ascontiguousarray(c_off[:-1])), _lib.np_ptr(np.ascontiguousarray(c_off[1:])),
+            _lib.np_ptr(c_flat_c), _lib.np_ptr(np.ascontiguousarray(p_off[:-1])), _lib.np_ptr(np.ascontiguousarray(p_off[1:])),
+            _lib.np_ptr(p_flat_c), _lib.np_ptr(ks_c), len(ks), nthr, _lib.np_ptr(dcg), _lib.np_ptr(idcg),
+            _lib.np_ptr(hits_all)))
         for m in metrics:
-            for k_ in ks:
-                kk = min(k_, L)
+            for j, k_ in enumerate(ks):
                 n_rec = np.minimum(n_out, k_)
                 if type(m) is NDCG:
-                    cur = np.zeros(n); best = np.zeros(n)
-                    for i in range(min(k_, max(L, c_max))):       # sequential sums, position by position
-                        d = math.log2(2 + i)
-                        if i < L:
-                            cur = np.where(i < n_rec, cur + (2 ** rel_rank[:, i] - 1) / d, cur)
-                        if i < c_max:
-                            ok = (i < c_lens)
-                            best = np.where(ok, best + (2 ** np.where(ok, ideal[:, i], 0.0) - 1) / d, best)
+                    cur, best = dcg[:, j], idcg[:, j]
                     good = best != 0                                # ZeroDivisionError -> metric skipped for the user
                     vals = (cur[good] / best[good]).tolist()
                 else:
-                    hits = is_pos[:, :kk].sum(axis=1)
+                    hits = hits_all[:, j]
                     if type(m) is Precision:
                         good = n_rec > 0
                         vals = (hits[good] / n_rec[good]).tolist()

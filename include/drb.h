@@ -412,6 +412,22 @@ int drb_eval_lookup(int64_t n_groups, const int64_t* tab_beg, const int64_t* tab
                     const double* tab_val, const int64_t* q_beg, const int64_t* q_end, const int64_t* q_key,
                     double miss, int32_t n_threads, double* out);
 
+/* Per-user sums of the ranking metrics for every evaluated user at once (replaces the per-user metric calls of
+ * DRecPy/Evaluation/Processes/ranking_evaluation.py:222-241 -> Evaluation/Metrics/ranking.py:20-114: DCG / NDCG with
+ * strong relevancy, and the hit counts behind HitRatio / Recall / Precision).  For user g: the relevancy of an item is
+ * the value of the first row r in [tab_beg[g], tab_end[g]) with tab_key[r] == item, else 0 (ranking_evaluation.py:223);
+ * ranked[g * ld_ranked .. + n_out[g]) is the model's ranked list, [c_beg[g], c_end[g]) of c_key the candidate list and
+ * [p_beg[g], p_end[g]) of p_key the sampled positives.  For every cut-off ks[j] (ascending or not):
+ *   dcg[g * n_ks + j]  = sum_{i < min(ks[j], n_out[g])} (2^rel(ranked_i) - 1) / log2(2 + i), added in that order,
+ *   idcg[g * n_ks + j] = the same sum over the candidates' relevancies in descending order (i < min(ks[j], #candidates)),
+ *   hits[g * n_ks + j] = how many of the first min(ks[j], n_out[g]) ranked items are sampled positives.
+ * Same float64 operations in the same order as the reference's Python loops (pow, log2 of the C library). */
+int drb_eval_metrics(int64_t n_groups, const int64_t* tab_beg, const int64_t* tab_end, const int64_t* tab_key,
+                     const double* tab_val, const int64_t* ranked, int64_t ld_ranked, const int32_t* n_out,
+                     const int64_t* c_beg, const int64_t* c_end, const int64_t* c_key, const int64_t* p_beg,
+                     const int64_t* p_end, const int64_t* p_key, const int64_t* ks, int32_t n_ks, int32_t n_threads,
+                     double* dcg, double* idcg, int64_t* hits);
+
 /* Leave-k-out split for every user at once (replaces DRecPy/Evaluation/Splits/leave_k_out.py:58-135: one
  * interaction_dataset.select('user == ...') plus rng.sample per user on a thread pool).  Rows are given grouped by
  * user in order of first appearance, each group in DataFrame order: group idx spans user_indptr[idx]..[idx+1].  User
