@@ -290,6 +290,57 @@ def test_vectorised_evaluation_with_duplicate_test_rows_and_ragged_lists():
             assert fast == slow, (kw, fast, slow)
 
 
+def test_native_metric_sums_equal_the_metric_classes():
+    """drb_eval_metrics against the metric classes (restated from Evaluation/Metrics/ranking.py:20-114) user by user:
+    short and long test tables (linear scan / sorted index), few and many positives, real-valued relevancies with
+    repeated test rows (first row wins), ranked lists shorter than k, cut-offs beyond the list length."""
+    import ctypes as C
+    from drecpy_b200 import _lib
+    rng = np.random.default_rng(12)
+    n, L, ks = 40, 30, [1, 3, 10, 50]
+    t_beg, t_end, t_key, t_val, c_beg, c_end, c_key, p_beg, p_end, p_key = [], [], [], [], [], [], [], [], [], []
+    ranked = np.full((n, L), -1, np.int64)
+    n_out = np.zeros(n, np.int32)
+    for g in range(n):
+        nt = int(rng.integers(0, 40))                              # test rows of the user (some > 16: sorted path)
+        keys = rng.integers(0, 60, nt)
+        t_beg.append(len(t_key)); t_key += keys.tolist(); t_val += rng.choice([0.0, 1.0, 2.5, 4.0], nt).tolist()
+        t_end.append(len(t_key))
+        cands = rng.permutation(80)[:int(rng.integers(1, L + 1))]
+        c_beg.append(len(c_key)); c_key += cands.tolist(); c_end.append(len(c_key))
+        pos = rng.permutation(cands)[:int(rng.integers(1, min(len(cands), 25) + 1))]
+        p_beg.append(len(p_key)); p_key += pos.tolist(); p_end.append(len(p_key))
+        r = rng.permutation(cands)[:int(rng.integers(0, len(cands) + 1))]     # the model may drop candidates (novelty)
+        ranked[g, :len(r)] = r; n_out[g] = len(r)
+    arr = lambda x, t: np.ascontiguousarray(x, t)
+    A = dict(t_beg=arr(t_beg, np.int64), t_end=arr(t_end, np.int64), t_key=arr(t_key, np.int64), t_val=arr(t_val, np.float64),
+             c_beg=arr(c_beg, np.int64), c_end=arr(c_end, np.int64), c_key=arr(c_key, np.int64),
+             p_beg=arr(p_beg, np.int64), p_end=arr(p_end, np.int64), p_key=arr(p_key, np.int64), ks=arr(ks, np.int64))
+    dcg, idcg = np.zeros((n, len(ks))), np.zeros((n, len(ks)))
+    hits = np.zeros((n, len(ks)), np.int64)
+    P = _lib.np_ptr
+    _lib.check(_lib.load().drb_eval_metrics(n, P(A['t_beg']), P(A['t_end']), P(A['t_key']), P(A['t_val']), P(ranked), L,
+                                            P(n_out), P(A['c_beg']), P(A['c_end']), P(A['c_key']), P(A['p_beg']),
+                                            P(A['p_end']), P(A['p_key']), P(A['ks']), len(ks), 1, P(dcg), P(idcg), P(hits)))
+    ndcg, dcg_m, hr, prec = drb.NDCG(), drb.DCG(), drb.HitRatio(), drb.Precision()
+    for g in range(n):
+        rel = {}
+        for it in c_key[c_beg[g]:c_end[g]]:
+            first = [t_val[r] for r in range(t_beg[g], t_end[g]) if t_key[r] == it]
+            rel[it] = first[0] if first else 0
+        rec = ranked[g, :n_out[g]].tolist()
+        positives = p_key[p_beg[g]:p_end[g]]
+        for j, k in enumerate(ks):
+            assert dcg[g, j] == dcg_m(rec, k=k, relevancies=rel), (g, k)
+            best = sorted(rel, key=lambda x: -rel[x])
+            assert idcg[g, j] == dcg_m(best, k=k, relevancies=rel), (g, k)
+            if idcg[g, j] != 0:
+                assert dcg[g, j] / idcg[g, j] == ndcg(rec, k=k, relevancies=rel)
+            assert hits[g, j] / len(positives) == hr(rec, k=k, relevant_recommendations=positives)
+            if min(k, len(rec)):
+                assert hits[g, j] / min(k, len(rec)) == prec(rec, k=k, relevant_recommendations=positives)
+
+
 # ------------------------------------------------------------------------------------------------ leave_k_out
 def test_leave_k_out_matches_live_reference_goldens():
     """drecpy_b200.leave_k_out (native per-user Random(seed + idx + 1).sample replay) against the row ids the live
