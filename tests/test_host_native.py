@@ -500,6 +500,18 @@ def test_bench_roofline_object_from_committed_kernel_times():
     assert r['traffic'] == table['k_umma_cdae_loss'] + table['k_umma_gemm_mn'] + table['k_umma_gemm_kk']
     assert abs(r['algorithmic_flops_per_step'] - 6.0 * 200 * 26744 * 4096) < 1
     assert 0.8 < r['secondary']['k_adam']['frac'] < 1.0
+    # the closing round-2 line with the newest committed traffic table (what bench.py itself loads)
+    j2 = json.loads(open(os.path.join(root, 'profiles', 'r2_bench_n1.json')).read().strip().splitlines()[-1])
+    t2 = bench.load_traffic()
+    assert {'k_umma_cdae_loss', 'k_umma_gemm_dw', 'k_umma_gemm_dh', 'k_adam'} <= set(t2)
+    r3 = bench.cdae_roofline(j2['kernels_ms_per_step'], bench.C3, n_params, peaks, t2)
+    assert abs(r3['frac'] - j2['roofline']['frac']) < 1e-9 and 0.2 < r3['frac'] < 0.3
+    assert r3['traffic'] == t2['k_umma_cdae_loss'] + t2['k_umma_gemm_dw'] + t2['k_umma_gemm_dh'] < 1.6e9
+    # Adam: 28 B per parameter minus the unread gradient of user rows without a sampled user (N ranks touch N batches)
+    a1 = r3['secondary']['k_adam']['algorithmic_bytes_per_step']
+    a8 = bench.cdae_roofline(j2['kernels_ms_per_step'], bench.C3, n_params, peaks, t2, world=8)['secondary']['k_adam']
+    assert a1 == 28.0 * n_params - 4.0 * (138493 - 4096) * 200
+    assert a8['algorithmic_bytes_per_step'] == 28.0 * n_params - 4.0 * (138493 - 8 * 4096) * 200
     # FFMA path: no traffic claim
     r2 = bench.cdae_roofline({'k_sgemm_kk_loss': 2.5, 'k_sgemm_mn': 1.7, 'k_sgemm_kn': 2.8, 'k_adam': 0.17}, bench.C3,
                              n_params, peaks, table)
